@@ -1,0 +1,383 @@
+"""axcd — thin ctypes binding of the C ABI in include/axcd.h (the product's public API from Python).
+
+This module is plumbing only: it loads ``libaxcd.so`` (CUDA kernels + C ABI, built in-tree by
+``make -C axiom-physics-engine_b200`` / ``__graft_entry__.build()``) and ``libaxcd_scene.so`` (the
+host-only scene generator) and mirrors the reference-facing call shape
+``Broadphase::update / getPairCount`` and ``Narrowphase::detectCollisions / getContactCount``
+(reference: CLAUDE.md:162-178).  There is no CPU fallback: if the CUDA library is missing or no
+device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "libaxcd.so")
+SCENE_LIB_PATH = os.path.join(PKG_DIR, "libaxcd_scene.so")
+
+SHAPE_SPHERE, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_PLANE, SHAPE_CONVEX, SHAPE_MESH = range(6)
+FLAG_PAIR_DISTANCES = 1
+
+SHAPE_DT = np.dtype([("type", "<u4"), ("p0", "<f4"), ("p1", "<f4"), ("p2", "<f4")])
+CONTACT_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),
+                       ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("depth", "<f4"),
+                       ("status", "<u4")])
+
+# every symbol include/axcd.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "axcd_default_config", "axcd_create", "axcd_destroy", "axcd_set_shapes",
+    "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
+    "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
+    "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
+    "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
+]
+SCENE_SYMBOLS = ["axcd_scene_generate", "axcd_scene_generate_worlds", "axcd_scene_rng_u32"]
+
+
+class Config(C.Structure):
+    _fields_ = [("maxBodies", C.c_uint32), ("maxPairs", C.c_uint32), ("maxContacts", C.c_uint32),
+                ("maxHullVerts", C.c_uint32), ("numWorlds", C.c_uint32),
+                ("aabbMargin", C.c_float), ("gjkMaxIters", C.c_uint32),
+                ("epaMaxIters", C.c_uint32), ("epaMaxFaces", C.c_uint32), ("gjkTol", C.c_float),
+                ("epaTol", C.c_float), ("flags", C.c_uint32), ("deviceOrdinal", C.c_int32),
+                ("stream", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("numBodies", C.c_uint32), ("numPairs", C.c_uint32), ("numContacts", C.c_uint32),
+                ("numPenetrating", C.c_uint32), ("gjkFailures", C.c_uint32),
+                ("epaFailures", C.c_uint32), ("requiredPairs", C.c_uint32),
+                ("requiredContacts", C.c_uint32), ("refitMs", C.c_float), ("sortMs", C.c_float),
+                ("buildMs", C.c_float), ("pairMs", C.c_float), ("pairSortMs", C.c_float),
+                ("gjkMs", C.c_float), ("epaMs", C.c_float), ("totalMs", C.c_float),
+                ("broadphaseTime", C.c_float), ("narrowphaseTime", C.c_float),
+                ("bytesMoved", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SceneSpec(C.Structure):
+    _fields_ = [("numBodies", C.c_uint32), ("fracBox", C.c_float), ("fracSphere", C.c_float),
+                ("domain", C.c_float), ("sizeMin", C.c_float), ("sizeMax", C.c_float),
+                ("hullVerts", C.c_uint32), ("seed", C.c_uint64)]
+
+
+class AxcdError(RuntimeError):
+    def __init__(self, code, what, detail=""):
+        self.code = code
+        super().__init__(f"{what}: error {code} ({error_string(code)}) {detail}".strip())
+
+
+_lib = None
+_scene = None
+
+
+def load_library():
+    """Loads libaxcd.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `make -C {PKG_DIR}` "
+                              "(there is no CPU fallback for the collision path)")
+        lib = C.CDLL(LIB_PATH)
+        for name in ABI_SYMBOLS:
+            getattr(lib, name)
+        lib.axcd_error_string.restype = C.c_char_p
+        lib.axcd_last_device_error.restype = C.c_char_p
+        lib.axcd_last_device_error.argtypes = [C.c_void_p]
+        lib.axcd_destroy.restype = None
+        lib.axcd_destroy.argtypes = [C.c_void_p]
+        lib.axcd_default_config.restype = None
+        for name in ("axcd_create", "axcd_set_shapes", "axcd_set_transforms", "axcd_refit",
+                     "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_get_stats",
+                     "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
+                     "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64"):
+            getattr(lib, name).restype = C.c_int32
+        lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                        C.c_uint32, C.c_void_p]
+        lib.axcd_set_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        for name in ("axcd_refit", "axcd_broadphase", "axcd_narrowphase"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.axcd_step.argtypes = [C.c_void_p, C.c_void_p]
+        lib.axcd_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        lib.axcd_get_aabbs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        lib.axcd_get_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.axcd_get_pair_distances.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.axcd_get_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.axcd_test_sort_pairs32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                               C.c_uint32]
+        lib.axcd_test_sort_keys64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib = lib
+    return _lib
+
+
+def load_scene_library():
+    global _scene
+    if _scene is None:
+        if not os.path.exists(SCENE_LIB_PATH):
+            raise ImportError(f"{SCENE_LIB_PATH} is missing: run `make -C {PKG_DIR}`")
+        lib = C.CDLL(SCENE_LIB_PATH)
+        for name in SCENE_SYMBOLS:
+            getattr(lib, name)
+        lib.axcd_scene_generate.restype = C.c_int32
+        lib.axcd_scene_generate_worlds.restype = C.c_int32
+        _scene = lib
+    return _scene
+
+
+def error_string(code):
+    try:
+        return load_library().axcd_error_string(C.c_int32(code)).decode()
+    except Exception:
+        return "?"
+
+
+def default_config(**kw):
+    cfg = Config()
+    load_library().axcd_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# scenes
+# ------------------------------------------------------------------------------------------------
+class Scene:
+    """Host-side scene blobs: transforms (n,10) f32, shapes (n,) SHAPE_DT, hull (m,3) f32."""
+
+    def __init__(self, xf, shapes, hull=None, world_id=None, num_worlds=1, name=""):
+        self.xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(-1, 10)
+        self.shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
+        self.hull = np.ascontiguousarray(
+            hull if hull is not None else np.zeros((0, 3)), dtype=np.float32).reshape(-1, 3)
+        self.world_id = (np.ascontiguousarray(world_id, dtype=np.uint32)
+                         if world_id is not None else None)
+        self.num_worlds = num_worlds
+        self.name = name
+
+    @property
+    def n(self):
+        return self.xf.shape[0]
+
+
+def generate_scene(n, seed, domain, frac_box=0.5, frac_sphere=0.5, size=(0.25, 0.5),
+                   hull_verts=16, name=""):
+    lib = load_scene_library()
+    spec = SceneSpec(n, frac_box, frac_sphere, domain, size[0], size[1], hull_verts, seed)
+    xf = np.zeros((n, 10), np.float32)
+    shapes = np.zeros(n, SHAPE_DT)
+    # worst case every body is a hull; allocate by expectation + slack and retry
+    frac_hull = max(0.0, 1.0 - frac_box - frac_sphere)
+    cap = int(n * hull_verts * min(1.0, frac_hull * 1.2 + 0.01)) + 16 * hull_verts
+    while True:
+        hull = np.zeros((cap, 3), np.float32)
+        used = C.c_uint32(0)
+        rc = lib.axcd_scene_generate(C.byref(spec), _ptr(xf), _ptr(shapes), _ptr(hull),
+                                     C.c_uint32(cap), C.c_uint32(0), C.byref(used))
+        if rc == 601:
+            cap = n * hull_verts
+            continue
+        if rc != 0:
+            raise RuntimeError(f"scene generation failed: {rc}")
+        return Scene(xf, shapes, hull[:used.value].copy(), name=name)
+
+
+def generate_worlds(num_worlds, bodies_per_world, seed0, domain, frac_box=0.5, frac_sphere=0.5,
+                    size=(0.25, 0.5), hull_verts=16, name=""):
+    lib = load_scene_library()
+    n = num_worlds * bodies_per_world
+    spec = SceneSpec(bodies_per_world, frac_box, frac_sphere, domain, size[0], size[1],
+                     hull_verts, seed0)
+    xf = np.zeros((n, 10), np.float32)
+    shapes = np.zeros(n, SHAPE_DT)
+    wid = np.zeros(n, np.uint32)
+    frac_hull = max(0.0, 1.0 - frac_box - frac_sphere)
+    cap = n * hull_verts if frac_hull > 0 else 1
+    hull = np.zeros((cap, 3), np.float32)
+    used = C.c_uint32(0)
+    rc = lib.axcd_scene_generate_worlds(C.byref(spec), C.c_uint32(num_worlds), _ptr(xf),
+                                        _ptr(shapes), _ptr(wid), _ptr(hull), C.c_uint32(cap),
+                                        C.byref(used))
+    if rc != 0:
+        raise RuntimeError(f"scene generation failed: {rc}")
+    return Scene(xf, shapes, hull[:used.value].copy(), wid, num_worlds, name=name)
+
+
+# The named configurations of BASELINE.md / SURVEY.md 8(d)
+def config_scene(name, scale=1.0):
+    """scale < 1 shrinks body count at constant density (tests); 1.0 is the named size."""
+    def dens(n, L):
+        m = max(1, int(round(n * scale)))
+        return m, float(L * (m / n) ** (1.0 / 3.0))
+    if name == "C0":
+        n, L = dens(1000, 10.0)
+        return generate_scene(n, 1, L, name="C0")
+    if name == "C1":
+        n, L = dens(100_000, 46.4)
+        return generate_scene(n, 2, L, name="C1")
+    if name == "headline":
+        n, L = dens(1_000_000, 100.0)
+        return generate_scene(n, 3, L, name="headline")
+    if name == "C2":
+        n, L = dens(1_000_000, 100.0)
+        return generate_scene(n, 4, L, frac_box=0.4, frac_sphere=0.3, name="C2")
+    if name == "C3":
+        w = max(1, int(round(4096 * scale)))
+        return generate_worlds(w, 256, 1000, 6.35, name="C3")
+    if name == "C4":
+        n, L = dens(16_000_000, 252.0)
+        return generate_scene(n, 5, L, name="C4")
+    raise ValueError(name)
+
+
+# ------------------------------------------------------------------------------------------------
+# the collision world (one context == one GPU)
+# ------------------------------------------------------------------------------------------------
+class CollisionWorld:
+    """Owns an AxcdContext.  Mirrors Broadphase::update/getPairCount and
+    Narrowphase::detectCollisions/getContactCount."""
+
+    def __init__(self, max_bodies, max_pairs=None, max_contacts=None, max_hull_verts=0,
+                 num_worlds=1, device=0, stream=None, **cfg_kw):
+        self._lib = load_library()
+        max_pairs = max_pairs if max_pairs is not None else max(1024, 8 * max_bodies)
+        max_contacts = max_contacts if max_contacts is not None else max_pairs
+        self.cfg = default_config(maxBodies=max_bodies, maxPairs=max_pairs,
+                                  maxContacts=max_contacts, maxHullVerts=max_hull_verts,
+                                  numWorlds=num_worlds, deviceOrdinal=device,
+                                  stream=C.c_void_p(stream) if stream else None, **cfg_kw)
+        self._ctx = C.c_void_p()
+        rc = self._lib.axcd_create(C.byref(self.cfg), C.byref(self._ctx))
+        if rc != 0:
+            raise AxcdError(rc, "axcd_create")
+        self.n = 0
+
+    @classmethod
+    def for_scene(cls, scene, pairs_per_body=8, **kw):
+        w = cls(scene.n, max_pairs=max(1024, pairs_per_body * scene.n),
+                max_hull_verts=len(scene.hull), num_worlds=scene.num_worlds, **kw)
+        w.set_shapes(scene.shapes, scene.hull, scene.world_id)
+        w.set_transforms(scene.xf)
+        return w
+
+    def close(self):
+        if self._ctx:
+            self._lib.axcd_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise AxcdError(rc, what, self._lib.axcd_last_device_error(self._ctx).decode())
+
+    def set_shapes(self, shapes, hull=None, world_id=None):
+        shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
+        hull = np.ascontiguousarray(hull if hull is not None else np.zeros((0, 3)),
+                                    dtype=np.float32).reshape(-1, 3)
+        wid = np.ascontiguousarray(world_id, dtype=np.uint32) if world_id is not None else None
+        self.n = len(shapes)
+        self._check(self._lib.axcd_set_shapes(self._ctx, _ptr(shapes), len(shapes), _ptr(hull),
+                                              len(hull), _ptr(wid)), "axcd_set_shapes")
+
+    def set_transforms(self, xf, stride=40):
+        """xf: (n,10) float32 array (or any C-contiguous buffer of `stride`-byte records)."""
+        if isinstance(xf, np.ndarray) and stride == 40:
+            xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(-1, 10)
+            n = xf.shape[0]
+        else:
+            n = xf.nbytes // stride
+        self._check(self._lib.axcd_set_transforms(self._ctx, _ptr(xf), n, stride),
+                    "axcd_set_transforms")
+
+    def set_transforms_ptr(self, host_ptr, n, stride=40):
+        self._check(self._lib.axcd_set_transforms(self._ctx, C.c_void_p(host_ptr), n, stride),
+                    "axcd_set_transforms")
+
+    # Broadphase::update()
+    def update(self):
+        self._check(self._lib.axcd_refit(self._ctx), "axcd_refit")
+        self._check(self._lib.axcd_broadphase(self._ctx), "axcd_broadphase")
+
+    # Narrowphase::detectCollisions()
+    def detect_collisions(self):
+        self._check(self._lib.axcd_narrowphase(self._ctx), "axcd_narrowphase")
+
+    def refit(self):
+        self._check(self._lib.axcd_refit(self._ctx), "axcd_refit")
+
+    def step(self):
+        st = Stats()
+        self._check(self._lib.axcd_step(self._ctx, C.byref(st)), "axcd_step")
+        return st
+
+    def stats(self):
+        st = Stats()
+        self._check(self._lib.axcd_get_stats(self._ctx, C.byref(st)), "axcd_get_stats")
+        return st
+
+    def get_pair_count(self):
+        return self.stats().numPairs
+
+    def get_contact_count(self):
+        return self.stats().numContacts
+
+    def aabbs(self):
+        out = np.zeros((self.n, 6), np.float32)
+        self._check(self._lib.axcd_get_aabbs(self._ctx, _ptr(out), self.n), "axcd_get_aabbs")
+        return out
+
+    def pairs(self):
+        cap = max(1, self.stats().numPairs)
+        out = np.zeros((cap, 2), np.uint32)
+        cnt = C.c_uint32(0)
+        self._check(self._lib.axcd_get_pairs(self._ctx, _ptr(out), cap, C.byref(cnt)),
+                    "axcd_get_pairs")
+        return out[:cnt.value]
+
+    def pair_distances(self):
+        cap = max(1, self.stats().numPairs)
+        out = np.zeros(cap, np.float32)
+        cnt = C.c_uint32(0)
+        self._check(self._lib.axcd_get_pair_distances(self._ctx, _ptr(out), cap, C.byref(cnt)),
+                    "axcd_get_pair_distances")
+        return out[:cnt.value]
+
+    def contacts(self):
+        cap = max(1, self.stats().numContacts)
+        out = np.zeros(cap, CONTACT_DT)
+        cnt = C.c_uint32(0)
+        self._check(self._lib.axcd_get_contacts(self._ctx, _ptr(out), cap, C.byref(cnt)),
+                    "axcd_get_contacts")
+        return out[:cnt.value]
+
+    def contacts_into(self, host_ptr, cap):
+        cnt = C.c_uint32(0)
+        self._check(self._lib.axcd_get_contacts(self._ctx, C.c_void_p(host_ptr), cap,
+                                                C.byref(cnt)), "axcd_get_contacts")
+        return cnt.value
+
+    # test hooks for the device primitives
+    def test_sort_pairs32(self, keys, vals, key_bits=32):
+        keys = np.ascontiguousarray(keys, dtype=np.uint32).copy()
+        vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._check(self._lib.axcd_test_sort_pairs32(self._ctx, _ptr(keys), _ptr(vals),
+                                                     len(keys), key_bits), "sort_pairs32")
+        return keys, vals
+
+    def test_sort_keys64(self, keys, key_bits=64):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        self._check(self._lib.axcd_test_sort_keys64(self._ctx, _ptr(keys), len(keys), key_bits),
+                    "sort_keys64")
+        return keys

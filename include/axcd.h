@@ -1,0 +1,172 @@
+/*
+ * axcd.h — C ABI of the B200-native collision-detection path for the Axiom physics engine.
+ *
+ * The path: per-body world-space AABB refit -> broadphase candidate-pair finding (Morton radix
+ * sort + LBVH) -> GJK (+EPA for penetrating pairs) narrowphase.  It fills the reference's empty
+ * `axiom::collision` slot (reference: src/collision/.gitkeep, src/CMakeLists.txt:23-27) and is
+ * driven by the call shape the reference documents for it (reference: CLAUDE.md:162-178,
+ * include/axiom/core/profiler.hpp:13-23):
+ *
+ *      broadphase_.update();           -> axcd_refit + axcd_broadphase
+ *      broadphase_.getPairCount();     -> AxcdStats.numPairs
+ *      narrowphase_.detectCollisions();-> axcd_narrowphase
+ *      narrowphase_.getContactCount(); -> AxcdStats.numContacts
+ *
+ * Every entry point returns an `axiom::core::ErrorCode` value (reference:
+ * include/axiom/core/error_code.hpp:21-57); 0 == Success.  Nothing here throws or aborts on bad
+ * input.  All pointers are plain host pointers owned by the caller; the context owns all device
+ * memory.  One context == one CUDA device + one stream; a context is NOT thread-safe (the
+ * reference's device-facing objects have the same contract, include/axiom/gpu/vk_command.hpp:15).
+ *
+ * There is no CPU fallback behind this ABI: without a CUDA device axcd_create fails with
+ * AXCD_ERR_GPU_INIT (500) and no other entry point does any work.
+ */
+#ifndef AXCD_H
+#define AXCD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define AXCD_API __declspec(dllexport)
+#else
+#define AXCD_API __attribute__((visibility("default")))
+#endif
+
+/* ---- status codes == axiom::core::ErrorCode (include/axiom/core/error_code.hpp:21-57) ------ */
+enum {
+    AXCD_OK = 0,                     /* ErrorCode::Success                                     */
+    AXCD_ERR_OUT_OF_MEMORY = 200,    /* ErrorCode::OutOfMemory (host allocation)               */
+    AXCD_ERR_NULL_POINTER = 202,     /* ErrorCode::NullPointer                                 */
+    AXCD_ERR_INVALID_SHAPE = 300,    /* ErrorCode::InvalidShape                                */
+    AXCD_ERR_GJK_NO_CONVERGE = 301,  /* ErrorCode::GJKFailedToConverge   (per-contact status)  */
+    AXCD_ERR_EPA_NO_CONVERGE = 302,  /* ErrorCode::EPAFailedToConverge   (per-contact status)  */
+    AXCD_ERR_GPU_INIT = 500,         /* ErrorCode::VulkanInitializationFailed slot: device init */
+    AXCD_ERR_GPU_ALLOC = 502,        /* ErrorCode::BufferAllocationFailed                      */
+    AXCD_ERR_GPU_INVALID_OP = 503,   /* ErrorCode::GPU_INVALID_OPERATION (wrong call order)    */
+    AXCD_ERR_GPU_FAILED = 505,       /* ErrorCode::GPU_OPERATION_FAILED (CUDA / NCCL error)    */
+    AXCD_ERR_INVALID_PARAM = 600,    /* ErrorCode::InvalidParameter                            */
+    AXCD_ERR_OUT_OF_RANGE = 601      /* ErrorCode::OutOfRange (capacity exceeded)              */
+};
+
+/* ---- shape types: numeric order of debug::ShapeType (include/axiom/debug/physics_debug_draw.hpp:87-94)
+ * Only Sphere, Box and Convex are in scope; Capsule/Plane/Mesh -> AXCD_ERR_INVALID_SHAPE.      */
+enum { AXCD_SHAPE_SPHERE = 0, AXCD_SHAPE_BOX = 1, AXCD_SHAPE_CAPSULE = 2, AXCD_SHAPE_PLANE = 3,
+       AXCD_SHAPE_CONVEX = 4, AXCD_SHAPE_MESH = 5 };
+
+/* Flattened debug::DebugShape (physics_debug_draw.hpp:97-112): 16-byte POD.
+ *   Sphere : p0 = radius                                  (DebugShape::radius)
+ *   Box    : p0,p1,p2 = halfExtents.x/y/z                  (DebugShape::halfExtents)
+ *   Convex : p0 = bit pattern of uint32 firstVertex, p1 = bit pattern of uint32 vertexCount,
+ *            indexing the xyz-packed hull vertex pool (DebugShape::vertices / vertexCount,
+ *            src/debug/physics_debug_draw.cpp:285-288).                                         */
+typedef struct AxcdShape {
+    uint32_t type;
+    float p0, p1, p2;
+} AxcdShape;
+
+/* Narrowphase output record, derived from debug::DebugContactPoint
+ * (physics_debug_draw.hpp:128-132: position, normal, penetrationDepth) plus the pair ids.
+ * a < b are body indices; normal is unit length and points from body a to body b;
+ * position is the midpoint of the two witness (surface) points; depth >= 0.
+ * status: 0 ok, 301 GJK hit its iteration cap, 302 EPA hit its iteration/face cap.            */
+typedef struct AxcdContact {
+    uint32_t a, b;
+    float px, py, pz;
+    float nx, ny, nz;
+    float depth;
+    uint32_t status;
+} AxcdContact;
+
+/* POD config with in-header defaults (axcd_default_config), the reference's config idiom
+ * (include/axiom/gui/physics_panel.hpp:34-43).                                                 */
+typedef struct AxcdConfig {
+    uint32_t maxBodies;     /* capacity: bodies                                                 */
+    uint32_t maxPairs;      /* capacity: candidate pairs                                        */
+    uint32_t maxContacts;   /* capacity: contacts                                               */
+    uint32_t maxHullVerts;  /* capacity: hull vertex pool                                       */
+    uint32_t numWorlds;     /* 1 = single scene; >1 = batched independent worlds (worldId req.) */
+    float aabbMargin;       /* AABB::expand(float) applied after the tight fit; default 0       */
+    uint32_t gjkMaxIters;   /* default 32                                                       */
+    uint32_t epaMaxIters;   /* default 32                                                       */
+    uint32_t epaMaxFaces;   /* default 64 (hard cap 64)                                         */
+    float gjkTol;           /* relative GJK convergence tolerance, default 1e-6                 */
+    float epaTol;           /* EPA termination tolerance, default 1e-4                          */
+    uint32_t flags;         /* AXCD_FLAG_*                                                      */
+    int32_t deviceOrdinal;  /* CUDA device                                                      */
+    void* stream;           /* cudaStream_t to run on, or NULL for a context-owned stream       */
+} AxcdConfig;
+
+enum {
+    /* Also write the GJK distance of every candidate pair (0 for contacts) so that
+     * axcd_get_pair_distances works.  Off by default: separated pairs then stop at the first
+     * separating axis.                                                                          */
+    AXCD_FLAG_PAIR_DISTANCES = 1u
+};
+
+typedef struct AxcdStats {
+    uint32_t numBodies, numPairs, numContacts, numPenetrating; /* numPenetrating = EPA runs     */
+    uint32_t gjkFailures, epaFailures;  /* contacts whose status is 301 / 302                   */
+    uint32_t requiredPairs, requiredContacts; /* sizes that would have been needed (for 601)    */
+    float refitMs, sortMs, buildMs, pairMs, pairSortMs, gjkMs, epaMs, totalMs;
+    /* gui::PhysicsWorldStats sinks (include/axiom/gui/physics_panel.hpp:26-30)                 */
+    float broadphaseTime, narrowphaseTime;
+    uint64_t bytesMoved;    /* algorithmic HBM bytes of the step              */
+} AxcdStats;
+
+typedef struct AxcdContext AxcdContext; /* opaque */
+
+AXCD_API void axcd_default_config(AxcdConfig* cfg);
+AXCD_API int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out);
+AXCD_API void axcd_destroy(AxcdContext* ctx);
+
+/* Static scene description.  hullXYZ is xyz-packed (12 B per vertex); worldId may be NULL when
+ * numWorlds == 1.  Validates shape types/ranges -> 300 / 600 / 601.                            */
+AXCD_API int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n,
+                                 const float* hullXYZ, uint32_t nHullVerts,
+                                 const uint32_t* worldId);
+
+/* Per-step poses.  `transforms` is an array of axiom::math::Transform (40 B: position 0,
+ * rotation (x,y,z,w) 12, scale 28; include/axiom/math/transform.hpp:18-22) with the given byte
+ * stride (>= 40).  n must equal the n of axcd_set_shapes.  Host -> device copy.                */
+AXCD_API int32_t axcd_set_transforms(AxcdContext* ctx, const void* transforms, uint32_t n,
+                                     uint32_t strideBytes);
+
+/* The three stages (asynchronous on the context stream) and the fused step (synchronises and
+ * fills stats).  axcd_broadphase requires a refit since the last set_transforms, etc. -> 503.  */
+AXCD_API int32_t axcd_refit(AxcdContext* ctx);
+AXCD_API int32_t axcd_broadphase(AxcdContext* ctx);
+AXCD_API int32_t axcd_narrowphase(AxcdContext* ctx);
+AXCD_API int32_t axcd_step(AxcdContext* ctx, AxcdStats* outStats);
+/* Waits for the stream, then reports counts/timings of the last stages run.  Returns 601 if a
+ * capacity was exceeded (requiredPairs / requiredContacts say by how much).                    */
+AXCD_API int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* outStats);
+
+/* Blocking getters (device -> host copies).                                                    */
+AXCD_API int32_t axcd_get_aabbs(AxcdContext* ctx, void* outAabb24, uint32_t cap);
+AXCD_API int32_t axcd_get_pairs(AxcdContext* ctx, uint32_t* outPairs2, uint32_t cap,
+                                uint32_t* outCount); /* canonical: a<b, sorted by (a,b)         */
+AXCD_API int32_t axcd_get_pair_distances(AxcdContext* ctx, float* outDist, uint32_t cap,
+                                         uint32_t* outCount); /* needs AXCD_FLAG_PAIR_DISTANCES */
+AXCD_API int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap,
+                                   uint32_t* outCount); /* same (a,b) order                     */
+
+/* == axiom::core::errorCodeToString (src/core/error_code.cpp:5-62); static storage.            */
+AXCD_API const char* axcd_error_string(int32_t code);
+/* CUDA error text of the last failure on this context (static storage), "" if none.           */
+AXCD_API const char* axcd_last_device_error(AxcdContext* ctx);
+
+/* ---- self-test hooks for the device primitives (tests/ only; not part of the plug-in path) -- */
+/* Sorts n (key,value) pairs by the low `keyBits` bits of key with the hand-written radix sort. */
+AXCD_API int32_t axcd_test_sort_pairs32(AxcdContext* ctx, uint32_t* keys, uint32_t* vals,
+                                        uint32_t n, uint32_t keyBits);
+AXCD_API int32_t axcd_test_sort_keys64(AxcdContext* ctx, uint64_t* keys, uint32_t n,
+                                       uint32_t keyBits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AXCD_H */

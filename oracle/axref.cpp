@@ -1,0 +1,1009 @@
+/*
+ * axref.cpp — CPU ORACLE for the collision hot path (refit -> broadphase -> GJK/EPA).
+ *
+ * TEST INFRASTRUCTURE ONLY (see axref.h).  Scalar C++, IEEE binary32, built with
+ * -ffp-contract=off so no multiply-add is ever fused: every expression below rounds exactly as
+ * written, which is what lets the CUDA path (built -fmad=false) be bit-identical.
+ *
+ * What is restated from the reference (file:line under /root/reference) and what is authored:
+ *   Vec3 ops ................ include/axiom/math/vec3.hpp:15-280            (restated)
+ *   Quat * Vec3 ............. src/math/quat.cpp:33-38 -> glm::quat * glm::vec3 (GLM 1.0.x scalar
+ *                             formula; GLM itself is not in the snapshot)
+ *   Quat -> matrix .......... src/math/quat.cpp:117-129 -> glm::mat4_cast   (Appendix B)
+ *   Transform::transformPoint src/math/transform.cpp:86-93                  (restated)
+ *   AABB ops ................ include/axiom/math/aabb.hpp:47,132-135,143-160,213-215 (restated)
+ *   box corner order ........ src/debug/debug_draw.cpp:97-113               (restated)
+ *   sphere placement ........ src/debug/physics_debug_draw.cpp:246-248      (restated)
+ *   hull placement .......... src/debug/debug_draw.cpp:431-448              (restated)
+ *   DeterministicRNG ........ include/axiom/math/random.hpp:19-68           (restated)
+ *   broadphase, GJK, EPA .... ABSENT from the reference (src/collision/.gitkeep) — authored here
+ *                             from the spec in SURVEY.md Appendix A; "parity unpinned".
+ */
+#include "axref.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Vec3 (include/axiom/math/vec3.hpp)
+// ------------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+inline V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }   // vec3.hpp:52
+inline V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }   // vec3.hpp:60
+inline V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }      // vec3.hpp:84
+inline V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }                        // vec3.hpp:100
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }        // vec3.hpp:179
+inline V3 cross(V3 a, V3 b) {                                                     // vec3.hpp:188
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+inline bool same(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+
+struct Q4 {
+    float x, y, z, w;
+};
+
+// glm::quat * glm::vec3 (reached from src/math/quat.cpp:33-38):
+//   uv = cross(u, v); uuv = cross(u, uv); v + ((uv * q.w) + uuv) * 2
+inline V3 quatRotate(Q4 q, V3 v) {
+    V3 u = mk(q.x, q.y, q.z);
+    V3 uv = cross(u, v);
+    V3 uuv = cross(u, uv);
+    return v + ((uv * q.w) + uuv) * 2.0f;
+}
+
+// glm::quat * glm::quat (src/math/quat.cpp:27-31)
+inline Q4 quatMul(Q4 p, Q4 q) {
+    Q4 r;
+    r.w = p.w * q.w - p.x * q.x - p.y * q.y - p.z * q.z;
+    r.x = p.w * q.x + p.x * q.w + p.y * q.z - p.z * q.y;
+    r.y = p.w * q.y + p.y * q.w + p.z * q.x - p.x * q.z;
+    r.z = p.w * q.z + p.z * q.w + p.x * q.y - p.y * q.x;
+    return r;
+}
+
+// glm::mat3_cast (src/math/quat.cpp:117-129 via mat4_cast): columns c0,c1,c2.
+struct M3 {
+    V3 c0, c1, c2;
+};
+inline M3 quatToMat3(Q4 q) {
+    float qxx = q.x * q.x, qyy = q.y * q.y, qzz = q.z * q.z;
+    float qxz = q.x * q.z, qxy = q.x * q.y, qyz = q.y * q.z;
+    float qwx = q.w * q.x, qwy = q.w * q.y, qwz = q.w * q.z;
+    M3 m;
+    m.c0 = mk(1.0f - 2.0f * (qyy + qzz), 2.0f * (qxy + qwz), 2.0f * (qxz - qwy));
+    m.c1 = mk(2.0f * (qxy - qwz), 1.0f - 2.0f * (qxx + qzz), 2.0f * (qyz + qwx));
+    m.c2 = mk(2.0f * (qxz + qwy), 2.0f * (qyz - qwx), 1.0f - 2.0f * (qxx + qyy));
+    return m;
+}
+
+// axiom::math::Transform, 10 floats: position 0..2, rotation (x,y,z,w) 3..6, scale 7..9
+struct Xf {
+    V3 p;
+    Q4 q;
+    V3 s;
+};
+inline Xf loadXf(const float* f) {
+    Xf t;
+    t.p = mk(f[0], f[1], f[2]);
+    t.q = Q4{f[3], f[4], f[5], f[6]};
+    t.s = mk(f[7], f[8], f[9]);
+    return t;
+}
+// Transform::transformPoint (src/math/transform.cpp:86-93)
+inline V3 transformPoint(const Xf& t, V3 p) {
+    V3 scaled = mk(p.x * t.s.x, p.y * t.s.y, p.z * t.s.z);
+    V3 rotated = quatRotate(t.q, scaled);
+    return rotated + t.p;
+}
+
+// AABB (include/axiom/math/aabb.hpp)
+struct Box {
+    V3 lo, hi;
+};
+inline void expandPoint(Box& b, V3 p) {   // aabb.hpp:143-150
+    b.lo.x = (p.x < b.lo.x) ? p.x : b.lo.x;
+    b.lo.y = (p.y < b.lo.y) ? p.y : b.lo.y;
+    b.lo.z = (p.z < b.lo.z) ? p.z : b.lo.z;
+    b.hi.x = (p.x > b.hi.x) ? p.x : b.hi.x;
+    b.hi.y = (p.y > b.hi.y) ? p.y : b.hi.y;
+    b.hi.z = (p.z > b.hi.z) ? p.z : b.hi.z;
+}
+inline bool intersects(const float* a, const float* b) {   // aabb.hpp:132-135 (closed intervals)
+    return a[0] <= b[3] && a[3] >= b[0] && a[1] <= b[4] && a[4] >= b[1] && a[2] <= b[5] &&
+           a[5] >= b[2];
+}
+
+// DeterministicRNG (include/axiom/math/random.hpp:19-68)
+struct Rng {
+    uint64_t state;
+    explicit Rng(uint64_t seed) : state(seed | 1ULL) {
+        for (int i = 0; i < 10; ++i) next();
+    }
+    uint32_t next() {
+        uint64_t old = state;
+        state = old * 6364136223846793005ULL + 1442695040888963407ULL;
+        uint32_t xs = static_cast<uint32_t>(((old >> 18U) ^ old) >> 27U);
+        uint32_t rot = static_cast<uint32_t>(old >> 59U);
+        return (xs >> rot) | (xs << ((~rot + 1U) & 31));
+    }
+    float nextFloat() { return static_cast<float>(next()) / static_cast<float>(0x100000000ULL); }
+};
+
+enum { SHAPE_SPHERE = 0, SHAPE_BOX = 1, SHAPE_CONVEX = 4 };
+
+inline uint32_t fbits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+
+template <class F>
+void parallelFor(uint64_t n, int nthreads, F&& fn) {
+    if (nthreads <= 1 || n < 2048) {
+        fn(0, 0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    uint64_t chunk = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        uint64_t lo = std::min<uint64_t>(n, t * chunk), hi = std::min<uint64_t>(n, lo + chunk);
+        th.emplace_back([&fn, t, lo, hi] { fn(t, lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 1: refit
+// ------------------------------------------------------------------------------------------
+int refitOne(const Xf& t, const AxrefShape& s, const float* hull, uint32_t nHull, float margin,
+             float* out) {
+    Box b;
+    if (s.type == SHAPE_SPHERE) {
+        // AABB::fromCenterExtents(position, Vec3(r)) (aabb.hpp:213-215); rotation/scale ignored
+        // like the reference's sphere placement (src/debug/physics_debug_draw.cpp:246-248).
+        V3 r = mk(s.p0, s.p0, s.p0);
+        b.lo = t.p - r;
+        b.hi = t.p + r;
+    } else if (s.type == SHAPE_BOX) {
+        // corner order of src/debug/debug_draw.cpp:99-108
+        float hx = s.p0, hy = s.p1, hz = s.p2;
+        const V3 c[8] = {mk(-hx, -hy, -hz), mk(hx, -hy, -hz), mk(hx, -hy, hz), mk(-hx, -hy, hz),
+                         mk(-hx, hy, -hz),  mk(hx, hy, -hz),  mk(hx, hy, hz),  mk(-hx, hy, hz)};
+        V3 p0 = transformPoint(t, c[0]);
+        b.lo = p0;   // AABB(Vec3) (aabb.hpp:47)
+        b.hi = p0;
+        for (int k = 1; k < 8; ++k) expandPoint(b, transformPoint(t, c[k]));
+    } else if (s.type == SHAPE_CONVEX) {
+        uint32_t first = fbits(s.p0), cnt = fbits(s.p1);
+        if (cnt == 0 || static_cast<uint64_t>(first) + cnt > nHull) return 300;
+        const float* v = hull + 3ull * first;
+        V3 p0 = transformPoint(t, mk(v[0], v[1], v[2]));
+        b.lo = p0;
+        b.hi = p0;
+        for (uint32_t k = 1; k < cnt; ++k)
+            expandPoint(b, transformPoint(t, mk(v[3 * k], v[3 * k + 1], v[3 * k + 2])));
+    } else {
+        return 300;
+    }
+    if (margin != 0.0f) {   // AABB::expand(float) (aabb.hpp:156-160)
+        V3 m = mk(margin, margin, margin);
+        b.lo = b.lo - m;
+        b.hi = b.hi + m;
+    }
+    out[0] = b.lo.x; out[1] = b.lo.y; out[2] = b.lo.z;
+    out[3] = b.hi.x; out[4] = b.hi.y; out[5] = b.hi.z;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 3: narrowphase.  Convex "cores" in a frame translated so body A's position is the origin
+// (axes stay world-aligned).  Sphere = point core + radius margin; box and hull have no margin.
+// ------------------------------------------------------------------------------------------
+enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2 };
+struct Core {
+    int kind;
+    V3 c;            // centre relative to A's position
+    V3 e0, e1, e2;   // box: rotation columns * (halfExtent*scale); hull: rotation columns
+    V3 s;            // hull: scale
+    const float* verts;
+    uint32_t nv;
+    float r;         // sphere radius
+};
+
+Core makeCore(const Xf& t, const AxrefShape& sh, const float* hull, V3 origin) {
+    Core k{};
+    k.c = t.p - origin;
+    k.r = 0.0f;
+    if (sh.type == SHAPE_SPHERE) {
+        k.kind = CORE_POINT;
+        k.r = sh.p0;
+    } else if (sh.type == SHAPE_BOX) {
+        k.kind = CORE_BOX;
+        M3 m = quatToMat3(t.q);
+        k.e0 = m.c0 * (sh.p0 * t.s.x);
+        k.e1 = m.c1 * (sh.p1 * t.s.y);
+        k.e2 = m.c2 * (sh.p2 * t.s.z);
+    } else {
+        k.kind = CORE_HULL;
+        M3 m = quatToMat3(t.q);
+        k.e0 = m.c0; k.e1 = m.c1; k.e2 = m.c2;
+        k.s = t.s;
+        k.verts = hull + 3ull * fbits(sh.p0);
+        k.nv = fbits(sh.p1);
+    }
+    return k;
+}
+
+// Support point of a core in world-aligned direction d (need not be unit length).
+V3 support(const Core& k, V3 d) {
+    if (k.kind == CORE_POINT) return k.c;
+    if (k.kind == CORE_BOX) {
+        V3 p = k.c;
+        p = p + ((dot(d, k.e0) >= 0.0f) ? k.e0 : -k.e0);
+        p = p + ((dot(d, k.e1) >= 0.0f) ? k.e1 : -k.e1);
+        p = p + ((dot(d, k.e2) >= 0.0f) ? k.e2 : -k.e2);
+        return p;
+    }
+    // hull: local direction = scale * (R^T d); first maximal vertex wins
+    V3 l = mk(dot(d, k.e0) * k.s.x, dot(d, k.e1) * k.s.y, dot(d, k.e2) * k.s.z);
+    uint32_t best = 0;
+    float bestDot = dot(l, mk(k.verts[0], k.verts[1], k.verts[2]));
+    for (uint32_t i = 1; i < k.nv; ++i) {
+        float di = dot(l, mk(k.verts[3 * i], k.verts[3 * i + 1], k.verts[3 * i + 2]));
+        if (di > bestDot) {
+            bestDot = di;
+            best = i;
+        }
+    }
+    V3 lv = mk(k.verts[3 * best] * k.s.x, k.verts[3 * best + 1] * k.s.y,
+               k.verts[3 * best + 2] * k.s.z);
+    return ((k.e0 * lv.x + k.e1 * lv.y) + k.e2 * lv.z) + k.c;
+}
+
+struct Simplex {
+    V3 y[4];   // points of the Minkowski difference A - B
+    V3 a[4];   // the matching support points on A
+    float lam[4];
+    int n;
+};
+
+const float GJK_EPS_ABS2 = 1e-12f;   // |v|^2 at or below this: origin is on the simplex
+const float DEGENERATE_EPS = 1e-12f;
+
+// Closest point to the origin on segment [a,b]; mask bit0=a bit1=b.
+inline V3 closestSegment(V3 a, V3 b, float* la, float* lb, int* mask) {
+    V3 ab = b - a;
+    float t = -dot(a, ab);
+    if (t <= 0.0f) {
+        *la = 1.0f; *lb = 0.0f; *mask = 1;
+        return a;
+    }
+    float denom = dot(ab, ab);
+    if (t >= denom) {
+        *la = 0.0f; *lb = 1.0f; *mask = 2;
+        return b;
+    }
+    t = t / denom;
+    *la = 1.0f - t; *lb = t; *mask = 3;
+    return a + ab * t;
+}
+
+// Closest point to the origin on triangle (a,b,c) by Voronoi regions; mask bits a=1,b=2,c=4.
+inline V3 closestTriangle(V3 a, V3 b, V3 c, float* la, float* lb, float* lc, int* mask) {
+    V3 ab = b - a, ac = c - a;
+    float d1 = -dot(ab, a), d2 = -dot(ac, a);
+    if (d1 <= 0.0f && d2 <= 0.0f) {
+        *la = 1.0f; *lb = 0.0f; *lc = 0.0f; *mask = 1;
+        return a;
+    }
+    float d3 = -dot(ab, b), d4 = -dot(ac, b);
+    if (d3 >= 0.0f && d4 <= d3) {
+        *la = 0.0f; *lb = 1.0f; *lc = 0.0f; *mask = 2;
+        return b;
+    }
+    float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+        float v = d1 / (d1 - d3);
+        *la = 1.0f - v; *lb = v; *lc = 0.0f; *mask = 3;
+        return a + ab * v;
+    }
+    float d5 = -dot(ab, c), d6 = -dot(ac, c);
+    if (d6 >= 0.0f && d5 <= d6) {
+        *la = 0.0f; *lb = 0.0f; *lc = 1.0f; *mask = 4;
+        return c;
+    }
+    float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        float w = d2 / (d2 - d6);
+        *la = 1.0f - w; *lb = 0.0f; *lc = w; *mask = 5;
+        return a + ac * w;
+    }
+    float va = d3 * d6 - d5 * d4;
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        *la = 0.0f; *lb = 1.0f - w; *lc = w; *mask = 6;
+        return b + (c - b) * w;
+    }
+    float denom = 1.0f / (va + vb + vc);
+    float v = vb * denom, w = vc * denom;
+    *la = (1.0f - v) - w; *lb = v; *lc = w; *mask = 7;
+    return (a + ab * v) + ac * w;
+}
+
+// Is the origin strictly on the other side of plane (a,b,c) from d?  Degenerate (d in the plane)
+// counts as outside so the face is still examined.
+inline bool originOutside(V3 a, V3 b, V3 c, V3 d) {
+    V3 n = cross(b - a, c - a);
+    V3 ad = d - a;
+    float sp = -dot(a, n);
+    float sd = dot(ad, n);
+    if (sd * sd <= DEGENERATE_EPS * (dot(n, n) * dot(ad, ad))) return true;   // flat tetrahedron
+    return sp * sd < 0.0f;
+}
+
+// Reduce the simplex to the feature closest to the origin, set lam[], return that closest point.
+// *enclosed = true when a tetrahedron contains the origin.
+V3 solveSimplex(Simplex& s, bool* enclosed) {
+    *enclosed = false;
+    int mask = 0;
+    float l[4] = {0, 0, 0, 0};
+    V3 v = mk(0, 0, 0);
+    if (s.n == 2) {
+        v = closestSegment(s.y[0], s.y[1], &l[0], &l[1], &mask);
+    } else if (s.n == 3) {
+        v = closestTriangle(s.y[0], s.y[1], s.y[2], &l[0], &l[1], &l[2], &mask);
+    } else {
+        // tetrahedron: examine the faces the origin is outside of, keep the nearest result
+        static const int F[4][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 3, 2, 0}};
+        float best = FLT_MAX;
+        bool any = false;
+        for (int f = 0; f < 4; ++f) {
+            const int i = F[f][0], j = F[f][1], k = F[f][2], o = F[f][3];
+            if (!originOutside(s.y[i], s.y[j], s.y[k], s.y[o])) continue;
+            any = true;
+            float li, lj, lk;
+            int m;
+            V3 q = closestTriangle(s.y[i], s.y[j], s.y[k], &li, &lj, &lk, &m);
+            float qq = dot(q, q);
+            if (qq < best) {
+                best = qq;
+                v = q;
+                l[0] = l[1] = l[2] = l[3] = 0.0f;
+                l[i] = li; l[j] = lj; l[k] = lk;
+                mask = ((m & 1) ? (1 << i) : 0) | ((m & 2) ? (1 << j) : 0) |
+                       ((m & 4) ? (1 << k) : 0);
+            }
+        }
+        if (!any) {
+            *enclosed = true;
+            return mk(0, 0, 0);
+        }
+    }
+    int n = 0;
+    for (int i = 0; i < s.n; ++i) {
+        if (mask & (1 << i)) {
+            s.y[n] = s.y[i];
+            s.a[n] = s.a[i];
+            s.lam[n] = l[i];
+            ++n;
+        }
+    }
+    s.n = n;
+    return v;
+}
+
+enum { GJK_SEPARATED = 0, GJK_OVERLAP = 1 };
+struct GjkResult {
+    int state;      // GJK_SEPARATED: v is the closest point of A-B to the origin (or, without
+                    //   wantDistances, possibly only a separating direction); GJK_OVERLAP: cores
+                    //   touch/overlap
+    bool exact;     // separated && v converged (distance valid)
+    V3 v;
+    float vv;
+    uint32_t status;
+    uint32_t iters;
+};
+
+GjkResult gjk(const Core& A, const Core& B, const AxrefNarrowCfg& cfg, float marginSum,
+              Simplex& s) {
+    GjkResult r{};
+    V3 d0 = B.c - A.c;
+    if (dot(d0, d0) < 1e-12f) d0 = mk(1.0f, 0.0f, 0.0f);
+    s.a[0] = support(A, d0);
+    s.y[0] = s.a[0] - support(B, -d0);
+    s.lam[0] = 1.0f;
+    s.n = 1;
+    V3 v = s.y[0];
+    float vv = dot(v, v);
+    r.state = GJK_SEPARATED;
+    r.exact = true;
+    uint32_t it = 0;
+    for (;; ++it) {
+        if (vv <= GJK_EPS_ABS2) {
+            r.state = GJK_OVERLAP;
+            break;
+        }
+        if (it >= cfg.gjkMaxIters) {
+            r.status = 301;
+            break;
+        }
+        V3 a = support(A, -v);
+        V3 w = a - support(B, v);
+        float vw = dot(v, w);
+        if (!cfg.wantDistances && vw > 0.0f && vw * vw > vv * (marginSum * marginSum)) {
+            r.exact = false;   // separating axis with a gap larger than the margins
+            break;
+        }
+        if (vv - vw <= cfg.gjkTol * vv) break;   // converged: no closer point in direction -v
+        bool dup = false;
+        for (int i = 0; i < s.n; ++i) dup = dup || same(w, s.y[i]);
+        if (dup) break;
+        s.y[s.n] = w;
+        s.a[s.n] = a;
+        s.n++;
+        bool enclosed;
+        V3 nv = solveSimplex(s, &enclosed);
+        if (enclosed) {
+            r.state = GJK_OVERLAP;
+            v = nv;
+            vv = 0.0f;
+            break;
+        }
+        float nvv = dot(nv, nv);
+        bool stalled = nvv >= vv;
+        v = nv;
+        vv = nvv;
+        if (stalled) {
+            if (vv <= GJK_EPS_ABS2) r.state = GJK_OVERLAP;
+            break;
+        }
+    }
+    r.v = v;
+    r.vv = vv;
+    r.iters = it;
+    return r;
+}
+
+// ---- EPA ------------------------------------------------------------------------------------
+const int EPA_MAX_VERTS = 40;
+const int EPA_MAX_FACES = 64;
+struct EpaFace {
+    uint8_t i0, i1, i2, alive;
+    V3 n;
+    float d;
+};
+struct Epa {
+    V3 y[EPA_MAX_VERTS], a[EPA_MAX_VERTS];
+    int nv;
+    EpaFace f[EPA_MAX_FACES];
+    int nf;   // slots in use (alive or dead)
+};
+
+inline void epaSetFace(Epa& e, int slot, int i0, int i1, int i2) {
+    EpaFace& F = e.f[slot];
+    V3 n = cross(e.y[i1] - e.y[i0], e.y[i2] - e.y[i0]);
+    float len2 = dot(n, n);
+    F.alive = 1;
+    if (len2 <= 1e-30f) {   // zero-area face: never the closest, never visible
+        F.i0 = (uint8_t)i0; F.i1 = (uint8_t)i1; F.i2 = (uint8_t)i2;
+        F.n = mk(0, 0, 0);
+        F.d = FLT_MAX;
+        return;
+    }
+    float inv = 1.0f / std::sqrt(len2);
+    n = n * inv;
+    // Outward orientation comes from the winding (initial tetrahedron oriented explicitly, new
+    // faces inherit the horizon edge direction); d may be a hair negative when the origin sits on
+    // the boundary, and such a face is then simply the first one expanded.
+    float d = dot(n, e.y[i0]);
+    F.i0 = (uint8_t)i0; F.i1 = (uint8_t)i1; F.i2 = (uint8_t)i2;
+    F.n = n;
+    F.d = d;
+}
+
+struct EpaResult {
+    V3 n;        // unit, from A to B
+    float depth; // core penetration depth (>= 0)
+    V3 pa;       // witness point on A's core (A-centred frame)
+    V3 pb;       // witness point on B's core
+    uint32_t status;
+};
+
+// Fallback for a Minkowski difference that is degenerate at the origin: zero depth along n.
+inline EpaResult epaTouching(V3 n, V3 pa) {
+    EpaResult r;
+    float l2 = dot(n, n);
+    r.n = (l2 > 0.0f) ? n * (1.0f / std::sqrt(l2)) : mk(1.0f, 0.0f, 0.0f);
+    r.depth = 0.0f;
+    r.pa = pa;
+    r.pb = pa;
+    r.status = 0;
+    return r;
+}
+
+EpaResult epa(const Core& A, const Core& B, const AxrefNarrowCfg& cfg, const Simplex& s0) {
+    Epa e;
+    e.nv = s0.n;
+    for (int i = 0; i < s0.n; ++i) {
+        e.y[i] = s0.y[i];
+        e.a[i] = s0.a[i];
+    }
+    auto addSupport = [&](V3 d, int slot) {
+        e.a[slot] = support(A, d);
+        e.y[slot] = e.a[slot] - support(B, -d);
+    };
+    // --- grow the GJK simplex to a tetrahedron -------------------------------------------------
+    if (e.nv == 1) {
+        const V3 ax[6] = {mk(1, 0, 0), mk(-1, 0, 0), mk(0, 1, 0), mk(0, -1, 0), mk(0, 0, 1),
+                          mk(0, 0, -1)};
+        for (int k = 0; k < 6 && e.nv == 1; ++k) {
+            addSupport(ax[k], 1);
+            V3 d = e.y[1] - e.y[0];
+            if (dot(d, d) > DEGENERATE_EPS) e.nv = 2;
+        }
+        if (e.nv == 1) return epaTouching(mk(1, 0, 0), e.a[0]);
+    }
+    if (e.nv == 2) {
+        V3 d = e.y[1] - e.y[0];
+        const V3 ax[3] = {mk(1, 0, 0), mk(0, 1, 0), mk(0, 0, 1)};
+        V3 firstDir = mk(0, 0, 0);
+        for (int k = 0; k < 3 && e.nv == 2; ++k) {
+            V3 dir = cross(d, ax[k]);
+            if (dot(dir, dir) <= DEGENERATE_EPS) continue;
+            if (dot(firstDir, firstDir) == 0.0f) firstDir = dir;
+            for (int sgn = 0; sgn < 2 && e.nv == 2; ++sgn) {
+                addSupport(sgn ? -dir : dir, 2);
+                V3 c = cross(e.y[2] - e.y[0], d);
+                if (dot(c, c) > DEGENERATE_EPS) e.nv = 3;
+            }
+        }
+        if (e.nv == 2) return epaTouching(firstDir, e.a[0]);
+    }
+    if (e.nv == 3) {
+        V3 n = cross(e.y[1] - e.y[0], e.y[2] - e.y[0]);
+        float n2 = dot(n, n);
+        if (n2 <= 1e-30f) return epaTouching(mk(1, 0, 0), e.a[0]);
+        for (int sgn = 0; sgn < 2 && e.nv == 3; ++sgn) {
+            addSupport(sgn ? -n : n, 3);
+            float vol = dot(e.y[3] - e.y[0], n);
+            if (vol * vol > DEGENERATE_EPS * n2) e.nv = 4;
+        }
+        if (e.nv == 3) {
+            // flat at the origin: M has no thickness along n -> touching contact along +n
+            float la, lb, lc;
+            int m;
+            closestTriangle(e.y[0], e.y[1], e.y[2], &la, &lb, &lc, &m);
+            V3 pa = (e.a[0] * la + e.a[1] * lb) + e.a[2] * lc;
+            return epaTouching(n, pa);
+        }
+    }
+    // orientation: make (0,1,2) face away from vertex 3
+    if (dot(cross(e.y[1] - e.y[0], e.y[2] - e.y[0]), e.y[3] - e.y[0]) > 0.0f) {
+        std::swap(e.y[0], e.y[1]);
+        std::swap(e.a[0], e.a[1]);
+    }
+    epaSetFace(e, 0, 0, 1, 2);
+    epaSetFace(e, 1, 0, 3, 1);
+    epaSetFace(e, 2, 0, 2, 3);
+    epaSetFace(e, 3, 1, 3, 2);
+    e.nf = 4;
+    const int maxFaces = (int)std::min<uint32_t>(cfg.epaMaxFaces, EPA_MAX_FACES);
+
+    uint32_t status = 0;
+    int best = 0;
+    for (uint32_t it = 0;; ++it) {
+        best = -1;
+        float bd = FLT_MAX;
+        for (int i = 0; i < e.nf; ++i) {
+            if (e.f[i].alive && e.f[i].d < bd) {
+                bd = e.f[i].d;
+                best = i;
+            }
+        }
+        if (best < 0) {   // every face degenerate: give up on this polytope
+            return epaTouching(mk(1, 0, 0), e.a[0]);
+        }
+        const EpaFace fb = e.f[best];
+        V3 a = support(A, fb.n);
+        V3 w = a - support(B, -fb.n);
+        float dw = dot(w, fb.n);
+        float scale = (fb.d > 1.0f) ? fb.d : 1.0f;
+        if (dw - fb.d <= cfg.epaTol * scale) break;
+        bool dup = false;
+        for (int i = 0; i < e.nv; ++i) dup = dup || same(w, e.y[i]);
+        if (dup) break;
+        if (it >= cfg.epaMaxIters || e.nv >= EPA_MAX_VERTS) {
+            status = 302;
+            break;
+        }
+        // visible faces and horizon
+        uint8_t he0[EPA_MAX_FACES * 3], he1[EPA_MAX_FACES * 3];
+        int nh = 0, nvis = 0, nalive = 0;
+        uint8_t vis[EPA_MAX_FACES];
+        // A face counts as visible from w only when w is clearly in front of it: faces coplanar
+        // with w (common on boxes) must not be split by rounding noise into a ragged horizon.
+        const float wl = std::fabs(w.x) + std::fabs(w.y) + std::fabs(w.z);
+        const float visEps = 1e-6f * ((wl > 1.0f) ? wl : 1.0f);
+        for (int i = 0; i < e.nf; ++i) {
+            vis[i] = 0;
+            if (!e.f[i].alive) continue;
+            ++nalive;
+            if (dot(e.f[i].n, w) - e.f[i].d > visEps) {
+                vis[i] = 1;
+                ++nvis;
+            }
+        }
+        for (int i = 0; i < e.nf; ++i) {
+            if (!vis[i]) continue;
+            const uint8_t ev[3][2] = {{e.f[i].i0, e.f[i].i1}, {e.f[i].i1, e.f[i].i2},
+                                      {e.f[i].i2, e.f[i].i0}};
+            for (int k = 0; k < 3; ++k) {
+                int found = -1;
+                for (int h = 0; h < nh; ++h)
+                    if (he0[h] == ev[k][1] && he1[h] == ev[k][0]) {
+                        found = h;
+                        break;
+                    }
+                if (found >= 0) {
+                    he0[found] = he0[nh - 1];
+                    he1[found] = he1[nh - 1];
+                    --nh;
+                } else {
+                    he0[nh] = ev[k][0];
+                    he1[nh] = ev[k][1];
+                    ++nh;
+                }
+            }
+        }
+        // the horizon must be a simple loop: every vertex starts exactly one edge
+        bool loopOk = nh >= 3;
+        for (int h = 0; h < nh && loopOk; ++h)
+            for (int g = h + 1; g < nh; ++g)
+                if (he0[g] == he0[h] || he1[g] == he1[h]) {
+                    loopOk = false;
+                    break;
+                }
+        if (!loopOk || nalive - nvis + nh > maxFaces) {
+            status = 302;
+            break;
+        }
+        const int wi = e.nv;
+        e.y[wi] = w;
+        e.a[wi] = a;
+        e.nv++;
+        for (int i = 0; i < e.nf; ++i)
+            if (vis[i]) e.f[i].alive = 0;
+        int slot = 0;
+        for (int h = 0; h < nh; ++h) {
+            while (slot < e.nf && e.f[slot].alive) ++slot;
+            if (slot == e.nf) e.nf++;
+            epaSetFace(e, slot, he0[h], he1[h], wi);
+        }
+    }
+    const EpaFace fb = e.f[best];
+    EpaResult r;
+    r.n = fb.n;
+    r.depth = (fb.d > 0.0f) ? fb.d : 0.0f;
+    float la, lb, lc;
+    int m;
+    V3 p = closestTriangle(e.y[fb.i0], e.y[fb.i1], e.y[fb.i2], &la, &lb, &lc, &m);
+    r.pa = (e.a[fb.i0] * la + e.a[fb.i1] * lb) + e.a[fb.i2] * lc;
+    r.pb = r.pa - p;
+    r.status = status;
+    return r;
+}
+
+struct PairOut {
+    bool contact;
+    bool usedEpa;
+    float dist;   // signed: core distance - radii (<=0 for contacts); lower bound if !exact
+    AxrefContact c;
+    uint32_t iters;
+};
+
+PairOut collidePair(uint32_t ia, uint32_t ib, const Xf& ta, const AxrefShape& sa, const Xf& tb,
+                    const AxrefShape& sb, const float* hull, const AxrefNarrowCfg& cfg) {
+    PairOut o{};
+    o.c.a = ia;
+    o.c.b = ib;
+    V3 origin = ta.p;
+    V3 n, pa, pb;   // pa/pb: surface witness points in the A-centred frame
+    float depth;
+    uint32_t status = 0;
+    if (sa.type == SHAPE_SPHERE && sb.type == SHAPE_SPHERE) {
+        V3 d = tb.p - origin;
+        float dist = std::sqrt(dot(d, d));
+        float rs = sa.p0 + sb.p0;
+        depth = rs - dist;
+        o.dist = dist - rs;
+        if (!(depth >= 0.0f)) return o;
+        n = (dist > 0.0f) ? d * (1.0f / dist) : mk(1.0f, 0.0f, 0.0f);
+        pa = n * sa.p0;
+        pb = d - n * sb.p0;
+    } else {
+        Core A = makeCore(ta, sa, hull, origin);
+        Core B = makeCore(tb, sb, hull, origin);
+        float rs = A.r + B.r;
+        Simplex s;
+        GjkResult g = gjk(A, B, cfg, rs, s);
+        o.iters = g.iters;
+        status = g.status;
+        if (g.state == GJK_SEPARATED) {
+            float dist = std::sqrt(g.vv);
+            if (!g.exact) {
+                o.dist = dist - rs;   // not converged: only known to be separated
+                return o;
+            }
+            depth = rs - dist;
+            o.dist = dist - rs;
+            if (!(depth >= 0.0f)) return o;
+            // shallow contact: cores separated by less than the radii
+            n = -(g.v * (1.0f / dist));
+            V3 ca = mk(0, 0, 0);
+            for (int i = 0; i < s.n; ++i) ca = ca + s.a[i] * s.lam[i];
+            pa = ca + n * A.r;
+            pb = (ca - g.v) - n * B.r;
+        } else {
+            EpaResult e = epa(A, B, cfg, s);
+            o.usedEpa = true;
+            if (e.status) status = e.status;
+            n = e.n;
+            depth = e.depth + rs;
+            o.dist = -depth;
+            pa = e.pa + n * A.r;
+            pb = e.pb - n * B.r;
+        }
+    }
+    o.contact = true;
+    V3 mid = (pa + pb) * 0.5f + origin;
+    o.c.px = mid.x; o.c.py = mid.y; o.c.pz = mid.z;
+    o.c.nx = n.x; o.c.ny = n.y; o.c.nz = n.z;
+    o.c.depth = depth;
+    o.c.status = status;
+    return o;
+}
+
+}   // namespace
+
+// =============================================================================================
+extern "C" {
+
+void axref_quat_rotate(const float q[4], const float v[3], float out[3]) {
+    V3 r = quatRotate(Q4{q[0], q[1], q[2], q[3]}, mk(v[0], v[1], v[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void axref_quat_mul(const float p[4], const float q[4], float out[4]) {
+    Q4 r = quatMul(Q4{p[0], p[1], p[2], p[3]}, Q4{q[0], q[1], q[2], q[3]});
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void axref_quat_to_mat3(const float q[4], float o[9]) {
+    M3 m = quatToMat3(Q4{q[0], q[1], q[2], q[3]});
+    o[0] = m.c0.x; o[1] = m.c0.y; o[2] = m.c0.z;
+    o[3] = m.c1.x; o[4] = m.c1.y; o[5] = m.c1.z;
+    o[6] = m.c2.x; o[7] = m.c2.y; o[8] = m.c2.z;
+}
+void axref_transform_point(const float xf[10], const float p[3], float out[3]) {
+    V3 r = transformPoint(loadXf(xf), mk(p[0], p[1], p[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+void axref_rng_u32(uint64_t seed, uint32_t n, uint32_t* out) {
+    Rng r(seed);
+    for (uint32_t i = 0; i < n; ++i) out[i] = r.next();
+}
+void axref_rng_float(uint64_t seed, uint32_t n, float* out) {
+    Rng r(seed);
+    for (uint32_t i = 0; i < n; ++i) out[i] = r.nextFloat();
+}
+int axref_aabb_intersects(const float a[6], const float b[6]) { return intersects(a, b) ? 1 : 0; }
+
+int32_t axref_refit(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                    uint32_t nHullVerts, float margin, float* outAabb, int nthreads) {
+    if (n && (!xf || !shapes || !outAabb)) return 202;
+    std::vector<int> err((size_t)std::max(1, nthreads), 0);
+    parallelFor(n, nthreads, [&](int t, uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            int e = refitOne(loadXf(xf + 10 * i), shapes[i], hullXYZ, nHullVerts, margin,
+                             outAabb + 6 * i);
+            if (e) err[(size_t)t] = e;
+        }
+    });
+    for (int e : err)
+        if (e) return e;
+    return 0;
+}
+
+int32_t axref_broadphase_brute(const float* aabb, uint32_t n, const uint32_t* worldId,
+                               uint32_t* outPairs, uint64_t cap, uint64_t* outCount) {
+    uint64_t cnt = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = i + 1; j < n; ++j) {
+            if (worldId && worldId[i] != worldId[j]) continue;
+            if (!intersects(aabb + 6ull * i, aabb + 6ull * j)) continue;
+            if (cnt < cap) {
+                outPairs[2 * cnt] = i;
+                outPairs[2 * cnt + 1] = j;
+            }
+            ++cnt;
+        }
+    *outCount = cnt;
+    return cnt > cap ? 601 : 0;
+}
+
+// Uniform grid keyed on the AABB centre with cell edge >= the largest AABB extent: two
+// intersecting boxes then have centres at most one cell apart on every axis, so the 27-cell
+// neighbourhood is complete.  The overlap decision itself is always the exact predicate above.
+int32_t axref_broadphase_grid(const float* aabb, uint32_t n, const uint32_t* worldId,
+                              uint32_t* outPairs, uint64_t cap, uint64_t* outCount,
+                              int nthreads) {
+    *outCount = 0;
+    if (n == 0) return 0;
+    // bodies with a NaN/inf box never intersect anything (every compare is false / handled by
+    // the exact predicate for inf): leave non-finite ones out of the grid and test them brutally.
+    std::vector<uint32_t> finite, odd;
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    double maxExt = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* b = aabb + 6ull * i;
+        bool ok = true;
+        for (int k = 0; k < 6; ++k) ok = ok && std::isfinite(b[k]);
+        if (!ok || b[0] > b[3] || b[1] > b[4] || b[2] > b[5]) {
+            odd.push_back(i);
+            continue;
+        }
+        finite.push_back(i);
+        for (int k = 0; k < 3; ++k) {
+            double c = 0.5 * ((double)b[k] + (double)b[k + 3]);
+            lo[k] = std::min(lo[k], c);
+            hi[k] = std::max(hi[k], c);
+            maxExt = std::max(maxExt, (double)b[k + 3] - (double)b[k]);
+        }
+    }
+    std::vector<std::vector<uint64_t>> found((size_t)std::max(1, nthreads));
+    if (!finite.empty()) {
+        double cell = std::max(maxExt * 1.0001, 1e-9);
+        // cap the grid at ~4 cells per body
+        double span = std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], cell});
+        double maxCells = std::max(1.0, std::cbrt(4.0 * (double)finite.size()));
+        if (span / cell > maxCells) cell = span / maxCells;
+        int64_t dim[3];
+        for (int k = 0; k < 3; ++k) dim[k] = (int64_t)std::floor((hi[k] - lo[k]) / cell) + 1;
+        auto cellOf = [&](uint32_t i, int64_t c[3]) {
+            const float* b = aabb + 6ull * i;
+            for (int k = 0; k < 3; ++k) {
+                double ctr = 0.5 * ((double)b[k] + (double)b[k + 3]);
+                int64_t v = (int64_t)std::floor((ctr - lo[k]) / cell);
+                c[k] = std::min<int64_t>(std::max<int64_t>(v, 0), dim[k] - 1);
+            }
+        };
+        const uint64_t ncell = (uint64_t)dim[0] * dim[1] * dim[2];
+        std::vector<uint32_t> start(ncell + 1, 0), items(finite.size());
+        std::vector<uint64_t> cid(finite.size());
+        for (size_t k = 0; k < finite.size(); ++k) {
+            int64_t c[3];
+            cellOf(finite[k], c);
+            cid[k] = ((uint64_t)c[2] * dim[1] + c[1]) * dim[0] + c[0];
+            start[cid[k] + 1]++;
+        }
+        for (uint64_t c = 0; c < ncell; ++c) start[c + 1] += start[c];
+        {
+            std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+            for (size_t k = 0; k < finite.size(); ++k) items[fill[cid[k]]++] = finite[k];
+        }
+        parallelFor(finite.size(), nthreads, [&](int t, uint64_t a, uint64_t b) {
+            auto& out = found[(size_t)t];
+            for (uint64_t k = a; k < b; ++k) {
+                const uint32_t i = finite[k];
+                int64_t c[3];
+                cellOf(i, c);
+                for (int64_t z = std::max<int64_t>(c[2] - 1, 0); z <= std::min(c[2] + 1, dim[2] - 1); ++z)
+                for (int64_t y = std::max<int64_t>(c[1] - 1, 0); y <= std::min(c[1] + 1, dim[1] - 1); ++y)
+                for (int64_t x = std::max<int64_t>(c[0] - 1, 0); x <= std::min(c[0] + 1, dim[0] - 1); ++x) {
+                    uint64_t cc = ((uint64_t)z * dim[1] + y) * dim[0] + x;
+                    for (uint32_t p = start[cc]; p < start[cc + 1]; ++p) {
+                        const uint32_t j = items[p];
+                        if (j <= i) continue;
+                        if (worldId && worldId[i] != worldId[j]) continue;
+                        if (intersects(aabb + 6ull * i, aabb + 6ull * j))
+                            out.push_back(((uint64_t)i << 32) | j);
+                    }
+                }
+            }
+        });
+    }
+    // non-finite boxes: exact predicate against everybody (normally finds nothing)
+    for (uint32_t i : odd)
+        for (uint32_t j = 0; j < n; ++j) {
+            if (j == i) continue;
+            if (worldId && worldId[i] != worldId[j]) continue;
+            bool jOdd = std::binary_search(odd.begin(), odd.end(), j);
+            if (jOdd && j < i) continue;   // odd-odd pairs once
+            if (intersects(aabb + 6ull * i, aabb + 6ull * j)) {
+                uint32_t a = std::min(i, j), b = std::max(i, j);
+                found[0].push_back(((uint64_t)a << 32) | b);
+            }
+        }
+    std::vector<uint64_t> all;
+    size_t total = 0;
+    for (auto& f : found) total += f.size();
+    all.reserve(total);
+    for (auto& f : found) all.insert(all.end(), f.begin(), f.end());
+    std::sort(all.begin(), all.end());
+    *outCount = all.size();
+    for (size_t k = 0; k < all.size() && k < cap; ++k) {
+        outPairs[2 * k] = (uint32_t)(all[k] >> 32);
+        outPairs[2 * k + 1] = (uint32_t)all[k];
+    }
+    return all.size() > cap ? 601 : 0;
+}
+
+int32_t axref_narrowphase(const float* xf, const AxrefShape* shapes, uint32_t n,
+                          const float* hullXYZ, uint32_t nHullVerts, const uint32_t* pairs,
+                          uint64_t npairs, const AxrefNarrowCfg* cfg, AxrefContact* outContacts,
+                          uint64_t cap, uint64_t* outCount, float* outDist,
+                          AxrefNarrowStats* stats, int nthreads) {
+    (void)nHullVerts;
+    if (!cfg || !outCount) return 202;
+    const int T = std::max(1, nthreads);
+    std::vector<std::vector<AxrefContact>> loc((size_t)T);
+    std::vector<AxrefNarrowStats> st((size_t)T, AxrefNarrowStats{});
+    std::vector<int> err((size_t)T, 0);
+    parallelFor(npairs, nthreads, [&](int t, uint64_t lo, uint64_t hi) {
+        for (uint64_t k = lo; k < hi; ++k) {
+            uint32_t a = pairs[2 * k], b = pairs[2 * k + 1];
+            if (a >= n || b >= n) {
+                err[(size_t)t] = 601;
+                continue;
+            }
+            PairOut o = collidePair(a, b, loadXf(xf + 10ull * a), shapes[a],
+                                    loadXf(xf + 10ull * b), shapes[b], hullXYZ, *cfg);
+            if (outDist) outDist[k] = o.contact ? ((o.dist < 0.0f) ? o.dist : 0.0f) : o.dist;
+            st[(size_t)t].gjkIterations += o.iters;
+            if (o.contact) {
+                loc[(size_t)t].push_back(o.c);
+                st[(size_t)t].numContacts++;
+                if (o.usedEpa) st[(size_t)t].numPenetrating++;
+                if (o.c.status == 301) st[(size_t)t].gjkFailures++;
+                if (o.c.status == 302) st[(size_t)t].epaFailures++;
+            }
+        }
+    });
+    uint64_t cnt = 0;
+    AxrefNarrowStats tot{};
+    for (int t = 0; t < T; ++t) {
+        for (auto& c : loc[(size_t)t]) {
+            if (cnt < cap) outContacts[cnt] = c;
+            ++cnt;
+        }
+        tot.numContacts += st[(size_t)t].numContacts;
+        tot.numPenetrating += st[(size_t)t].numPenetrating;
+        tot.gjkFailures += st[(size_t)t].gjkFailures;
+        tot.epaFailures += st[(size_t)t].epaFailures;
+        tot.gjkIterations += st[(size_t)t].gjkIterations;
+    }
+    *outCount = cnt;
+    if (stats) *stats = tot;
+    for (int e : err)
+        if (e) return e;
+    return cnt > cap ? 601 : 0;
+}
+
+int32_t axref_collide_pair(const float xfA[10], const AxrefShape* sa, const float xfB[10],
+                           const AxrefShape* sb, const float* hullXYZ, const AxrefNarrowCfg* cfg,
+                           AxrefContact* out, float* outDist, uint32_t* outUsedEpa) {
+    PairOut o = collidePair(0, 1, loadXf(xfA), *sa, loadXf(xfB), *sb, hullXYZ, *cfg);
+    if (out) *out = o.c;
+    if (outDist) *outDist = o.dist;
+    if (outUsedEpa) *outUsedEpa = o.usedEpa ? 1u : 0u;
+    return o.contact ? 1 : 0;
+}
+
+}   // extern "C"

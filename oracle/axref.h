@@ -1,0 +1,71 @@
+/*
+ * axref.h — C interface of the CPU ORACLE for the collision hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (axiom-physics-engine_b200/, include/) may
+ * include, link or call this.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs use it, and only as the checker / the timed CPU baseline.
+ *
+ * PARITY STATUS: "parity unpinned" for broadphase pair sets, GJK distances and EPA contacts — the
+ * reference snapshot has no collision code (src/collision/.gitkeep is empty), so no
+ * reference test or golden vector exists for them.  The math building blocks this oracle is
+ * composed of ARE pinned against the reference's own tests (tests/test_oracle_math.py cites them),
+ * and the authored algorithms are validated independently: brute-force O(N^2) overlap,
+ * closed-form sphere/box answers and a scipy QP cross-check (tests/test_oracle_*.py).
+ */
+#ifndef AXREF_H
+#define AXREF_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct AxrefShape { uint32_t type; float p0, p1, p2; } AxrefShape;   /* == AxcdShape   */
+typedef struct AxrefContact {                                                 /* == AxcdContact */
+    uint32_t a, b; float px, py, pz, nx, ny, nz, depth; uint32_t status;
+} AxrefContact;
+typedef struct AxrefNarrowCfg {
+    uint32_t gjkMaxIters, epaMaxIters, epaMaxFaces;
+    float gjkTol, epaTol;
+    uint32_t wantDistances;   /* 1: run GJK to convergence on every pair and report distances */
+} AxrefNarrowCfg;
+typedef struct AxrefNarrowStats {
+    uint64_t numContacts, numPenetrating, gjkFailures, epaFailures, gjkIterations;
+} AxrefNarrowStats;
+
+/* math KATs (pin the GLM-free restatement against the reference's own test expectations) */
+void axref_quat_rotate(const float q[4], const float v[3], float out[3]);
+void axref_quat_mul(const float p[4], const float q[4], float out[4]);
+void axref_quat_to_mat3(const float q[4], float outColMajor[9]);
+void axref_transform_point(const float xf[10], const float p[3], float out[3]);
+void axref_rng_u32(uint64_t seed, uint32_t n, uint32_t* out);
+void axref_rng_float(uint64_t seed, uint32_t n, float* out);
+int  axref_aabb_intersects(const float a[6], const float b[6]);
+
+/* stage 1: refit.  xf = n x 10 floats (axiom::math::Transform), out = n x 6 floats (AABB).    */
+int32_t axref_refit(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                    uint32_t nHullVerts, float margin, float* outAabb, int nthreads);
+
+/* stage 2: candidate pairs, canonical (a<b, sorted).  *outCount is the true count even when it
+ * exceeds cap (only cap pairs are written).  worldId may be NULL.                             */
+int32_t axref_broadphase_brute(const float* aabb, uint32_t n, const uint32_t* worldId,
+                               uint32_t* outPairs, uint64_t cap, uint64_t* outCount);
+int32_t axref_broadphase_grid(const float* aabb, uint32_t n, const uint32_t* worldId,
+                              uint32_t* outPairs, uint64_t cap, uint64_t* outCount, int nthreads);
+
+/* stage 3: narrowphase over given pairs (in the given order).  outDist may be NULL.           */
+int32_t axref_narrowphase(const float* xf, const AxrefShape* shapes, uint32_t n,
+                          const float* hullXYZ, uint32_t nHullVerts, const uint32_t* pairs,
+                          uint64_t npairs, const AxrefNarrowCfg* cfg, AxrefContact* outContacts,
+                          uint64_t cap, uint64_t* outCount, float* outDist,
+                          AxrefNarrowStats* stats, int nthreads);
+
+/* one pair, for closed-form checks: returns 1 if contact. dist = core GJK distance minus radii
+ * (<= 0 for contacts; exact only when cfg->wantDistances).                                    */
+int32_t axref_collide_pair(const float xfA[10], const AxrefShape* sa, const float xfB[10],
+                           const AxrefShape* sb, const float* hullXYZ, const AxrefNarrowCfg* cfg,
+                           AxrefContact* out, float* outDist, uint32_t* outUsedEpa);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -52,7 +52,8 @@ class Stats(C.Structure):
                 ("buildMs", C.c_float), ("pairMs", C.c_float), ("pairSortMs", C.c_float),
                 ("gjkMs", C.c_float), ("epaMs", C.c_float), ("totalMs", C.c_float),
                 ("broadphaseTime", C.c_float), ("narrowphaseTime", C.c_float),
-                ("bytesMoved", C.c_uint64)]
+                ("bytesMoved", C.c_uint64), ("kernelLaunches", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -1,0 +1,635 @@
+// C ABI (include/axcd.h) over the CUDA kernels: context, device buffers, stage orchestration.
+// No CPU fallback exists here: every stage is a kernel launch on the context's stream.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "axcd.h"
+#include "axcd_common.cuh"
+#include "axcd_lbvh.cuh"
+#include "axcd_narrow.cuh"
+#include "axcd_refit.cuh"
+#include "axcd_sort.cuh"
+
+using namespace axcd;
+
+namespace {
+
+enum Stage { ST_NONE = 0, ST_SHAPES = 1, ST_POSES = 2, ST_REFIT = 3, ST_BROAD = 4, ST_NARROW = 5 };
+enum Ev { EV_START, EV_REFIT, EV_SORT, EV_BUILD, EV_PAIR, EV_PAIRSORT, EV_BROAD_END, EV_N0, EV_GJK, EV_END, EV_COUNT };
+
+}  // namespace
+
+struct AxcdContext {
+    AxcdConfig cfg;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    int stage = ST_NONE;
+    uint32_t n = 0;          // bodies
+    uint32_t nHull = 0;
+    bool hasWorlds = false;
+    int idxBits = 1;         // bits of a body index inside a packed pair
+    int mortonBits = 10;     // per axis
+    int worldBits = 0;
+    uint32_t numPairs = 0;   // pairs held (<= maxPairs)
+    uint32_t foundPairs = 0; // pairs found (may exceed capacity)
+    uint32_t numContacts = 0, foundContacts = 0;
+    int pairBuf = 0;         // which of pairKeys[2] holds the sorted pairs
+    uint32_t launches[3] = {0, 0, 0};   // kernels launched by refit / broadphase / narrowphase
+    Counters hostCtr;
+    char lastErr[256] = {0};
+
+    // device buffers
+    float* dXf = nullptr;            // n * 10 floats (axiom::math::Transform AoS)
+    uint4* dShapes = nullptr;
+    float4* dHull = nullptr;
+    uint32_t* dWorld = nullptr;
+    float* dAabb = nullptr;          // n * 6 floats (axiom::math::AABB AoS)
+    uint32_t* dKeys[2] = {nullptr, nullptr};
+    uint32_t* dVals[2] = {nullptr, nullptr};
+    float4* dLeafLo = nullptr;
+    float4* dLeafHi = nullptr;
+    BvhNode* dNodes = nullptr;
+    uint32_t* dParent = nullptr;
+    uint32_t* dVisit = nullptr;
+    uint32_t* dWorldEnd = nullptr;
+    uint64_t* dPairKeys[2] = {nullptr, nullptr};
+    uint32_t* dFlags = nullptr;      // per pair
+    uint32_t* dOffsets = nullptr;    // per pair
+    AxcdContact* dTmpContacts = nullptr;   // per pair
+    AxcdContact* dContacts = nullptr;
+    float* dPairDist = nullptr;
+    uint32_t* dSortHist = nullptr;
+    uint32_t* dSortStatus = nullptr;
+    uint32_t* dScanStatus = nullptr;
+    Counters* dCtr = nullptr;
+    uint32_t* dContactTotal = nullptr;
+    void* hPinned = nullptr;         // staging for strided transform uploads
+    size_t hPinnedBytes = 0;
+    cudaEvent_t ev[EV_COUNT];
+    bool evValid[EV_COUNT];
+};
+
+namespace {
+
+int fail(AxcdContext* c, cudaError_t e, const char* what) {
+    if (c) snprintf(c->lastErr, sizeof(c->lastErr), "%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    if (e == cudaErrorMemoryAllocation) return AXCD_ERR_GPU_ALLOC;
+    return AXCD_ERR_GPU_FAILED;
+}
+
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return fail(ctx, _e, #call);        \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1));
+}
+
+int bitsFor(uint32_t n) {   // bits needed to represent values in [0, n)
+    int b = 1;
+    while (b < 32 && (1ull << b) < n) ++b;
+    return b;
+}
+
+void recordEv(AxcdContext* c, int e) {
+    cudaEventRecord(c->ev[e], c->stream);
+    c->evValid[e] = true;
+}
+
+float evMs(AxcdContext* c, int a, int b) {
+    if (!c->evValid[a] || !c->evValid[b]) return 0.0f;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.0f;
+    }
+    return ms;
+}
+
+uint32_t sortTilesFor(uint64_t n) { return (uint32_t)((n + kSortTile - 1) / kSortTile); }
+
+}  // namespace
+
+extern "C" {
+
+void axcd_default_config(AxcdConfig* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->maxBodies = 1024;
+    cfg->maxPairs = 8192;
+    cfg->maxContacts = 8192;
+    cfg->maxHullVerts = 0;
+    cfg->numWorlds = 1;
+    cfg->aabbMargin = 0.0f;
+    cfg->gjkMaxIters = 32;
+    cfg->epaMaxIters = 32;
+    cfg->epaMaxFaces = 64;
+    cfg->gjkTol = 1e-6f;
+    cfg->epaTol = 1e-4f;
+    cfg->flags = 0;
+    cfg->deviceOrdinal = 0;
+    cfg->stream = nullptr;
+}
+
+const char* axcd_error_string(int32_t code) {
+    // text of axiom::core::errorCodeToString (reference: src/core/error_code.cpp:5-62)
+    switch (code) {
+        case 0: return "Success";
+        case 100: return "Division by zero";
+        case 101: return "Cannot normalize zero vector";
+        case 102: return "Matrix is singular and cannot be inverted";
+        case 103: return "Quaternion is invalid (not normalized or contains NaN)";
+        case 200: return "Out of memory";
+        case 201: return "Invalid allocation parameters";
+        case 202: return "Unexpected null pointer";
+        case 300: return "Invalid collision shape";
+        case 301: return "GJK algorithm failed to converge";
+        case 302: return "EPA algorithm failed to converge";
+        case 400: return "Invalid rigid body properties";
+        case 401: return "Constraint solver failed to converge";
+        case 500: return "Vulkan initialization failed";
+        case 501: return "Shader compilation failed";
+        case 502: return "GPU buffer allocation failed";
+        case 503: return "Invalid GPU operation or state";
+        case 504: return "GPU operation timed out";
+        case 505: return "GPU operation failed";
+        case 600: return "Invalid parameter";
+        case 601: return "Value out of range";
+        default: return "Unknown error";
+    }
+}
+
+const char* axcd_last_device_error(AxcdContext* ctx) { return ctx ? ctx->lastErr : ""; }
+
+void axcd_destroy(AxcdContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
+                    ctx->dVals[0], ctx->dVals[1], ctx->dLeafLo, ctx->dLeafHi, ctx->dNodes, ctx->dParent,
+                    ctx->dVisit, ctx->dWorldEnd, ctx->dPairKeys[0], ctx->dPairKeys[1], ctx->dFlags,
+                    ctx->dOffsets, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
+                    ctx->dSortStatus, ctx->dScanStatus, ctx->dCtr, ctx->dContactTotal};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
+    if (!cfg || !out) return AXCD_ERR_NULL_POINTER;
+    *out = nullptr;
+    if (cfg->maxBodies == 0 || cfg->maxBodies > (1u << 28) || cfg->maxPairs == 0 || cfg->maxPairs > (1u << 30) ||
+        cfg->maxContacts == 0 || cfg->numWorlds == 0 || cfg->numWorlds > (1u << 20) || cfg->epaMaxFaces < 4 ||
+        !(cfg->gjkTol >= 0.0f) || !(cfg->epaTol >= 0.0f) || !(cfg->aabbMargin == cfg->aabbMargin))
+        return AXCD_ERR_INVALID_PARAM;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return AXCD_ERR_GPU_INIT;   // no device: there is no CPU path to fall back to
+    }
+    if (cfg->deviceOrdinal < 0 || cfg->deviceOrdinal >= ndev) return AXCD_ERR_INVALID_PARAM;
+    if (cudaSetDevice(cfg->deviceOrdinal) != cudaSuccess) {
+        cudaGetLastError();
+        return AXCD_ERR_GPU_INIT;
+    }
+    AxcdContext* ctx = new (std::nothrow) AxcdContext();
+    if (!ctx) return AXCD_ERR_OUT_OF_MEMORY;
+    ctx->cfg = *cfg;
+    if (ctx->cfg.epaMaxFaces > (uint32_t)kEpaMaxFaces) ctx->cfg.epaMaxFaces = kEpaMaxFaces;
+    for (int i = 0; i < EV_COUNT; ++i) {
+        ctx->ev[i] = nullptr;
+        ctx->evValid[i] = false;
+    }
+    int rc = AXCD_OK;
+    auto body = [&]() -> int {
+        if (cfg->stream) {
+            ctx->stream = static_cast<cudaStream_t>(cfg->stream);
+        } else {
+            CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->ownStream = true;
+        }
+        for (int i = 0; i < EV_COUNT; ++i) CU(cudaEventCreate(&ctx->ev[i]));
+        const size_t nb = cfg->maxBodies, np = cfg->maxPairs;
+        // +64 floats of slack: the staged 128-bit loads may touch the tail of the last block
+        CU(dalloc(&ctx->dXf, nb * 10 + 64));
+        CU(dalloc(&ctx->dShapes, nb));
+        CU(dalloc(&ctx->dHull, (size_t)cfg->maxHullVerts));
+        if (cfg->numWorlds > 1) {
+            CU(dalloc(&ctx->dWorld, nb));
+            CU(dalloc(&ctx->dWorldEnd, (size_t)cfg->numWorlds));
+        }
+        CU(dalloc(&ctx->dAabb, nb * 6 + 64));
+        for (int k = 0; k < 2; ++k) {
+            CU(dalloc(&ctx->dKeys[k], nb));
+            CU(dalloc(&ctx->dVals[k], nb));
+            CU(dalloc(&ctx->dPairKeys[k], np));
+        }
+        CU(dalloc(&ctx->dLeafLo, nb));
+        CU(dalloc(&ctx->dLeafHi, nb));
+        CU(dalloc(&ctx->dNodes, nb));
+        CU(dalloc(&ctx->dParent, 2 * nb));
+        CU(dalloc(&ctx->dVisit, nb));
+        CU(dalloc(&ctx->dFlags, np));
+        CU(dalloc(&ctx->dOffsets, np));
+        CU(dalloc(&ctx->dTmpContacts, np));
+        CU(dalloc(&ctx->dContacts, (size_t)cfg->maxContacts));
+        if (cfg->flags & AXCD_FLAG_PAIR_DISTANCES) CU(dalloc(&ctx->dPairDist, np));
+        CU(dalloc(&ctx->dSortHist, (size_t)kMaxPasses * kRadix));
+        const size_t maxTiles = sortTilesFor(nb > np ? nb : np);
+        CU(dalloc(&ctx->dSortStatus, (size_t)kMaxPasses * maxTiles * kRadix));
+        CU(dalloc(&ctx->dScanStatus, (np + kScanTile - 1) / kScanTile + 1));
+        CU(dalloc(&ctx->dCtr, 1));
+        CU(dalloc(&ctx->dContactTotal, 1));
+        CU(cudaMemsetAsync(ctx->dCtr, 0, sizeof(Counters), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return AXCD_OK;
+    };
+    rc = body();
+    if (rc != AXCD_OK) {
+        axcd_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return AXCD_OK;
+}
+
+int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, const float* hullXYZ,
+                        uint32_t nHullVerts, const uint32_t* worldId) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (n && !shapes) return AXCD_ERR_NULL_POINTER;
+    if (nHullVerts && !hullXYZ) return AXCD_ERR_NULL_POINTER;
+    if (n > ctx->cfg.maxBodies || nHullVerts > ctx->cfg.maxHullVerts) return AXCD_ERR_OUT_OF_RANGE;
+    if (ctx->cfg.numWorlds > 1 && n && !worldId) return AXCD_ERR_INVALID_PARAM;
+    for (uint32_t i = 0; i < n; ++i) {
+        const AxcdShape& s = shapes[i];
+        if (s.type == AXCD_SHAPE_CONVEX) {
+            uint32_t first, cnt;
+            memcpy(&first, &s.p0, 4);
+            memcpy(&cnt, &s.p1, 4);
+            if (cnt == 0 || (uint64_t)first + cnt > nHullVerts) return AXCD_ERR_INVALID_SHAPE;
+        } else if (s.type != AXCD_SHAPE_SPHERE && s.type != AXCD_SHAPE_BOX) {
+            return AXCD_ERR_INVALID_SHAPE;   // Capsule / Plane / Mesh are not in scope
+        }
+        if (ctx->cfg.numWorlds > 1 && worldId[i] >= ctx->cfg.numWorlds) return AXCD_ERR_OUT_OF_RANGE;
+    }
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    CU(cudaMemcpyAsync(ctx->dShapes, shapes, sizeof(AxcdShape) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (nHullVerts) {
+        float4* tmp = static_cast<float4*>(malloc(sizeof(float4) * nHullVerts));
+        if (!tmp) return AXCD_ERR_OUT_OF_MEMORY;
+        for (uint32_t i = 0; i < nHullVerts; ++i)
+            tmp[i] = make_float4(hullXYZ[3 * i], hullXYZ[3 * i + 1], hullXYZ[3 * i + 2], 0.0f);
+        cudaError_t e = cudaMemcpyAsync(ctx->dHull, tmp, sizeof(float4) * nHullVerts, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        free(tmp);
+        if (e != cudaSuccess) return fail(ctx, e, "hull upload");
+    }
+    ctx->hasWorlds = ctx->cfg.numWorlds > 1;
+    if (ctx->hasWorlds)
+        CU(cudaMemcpyAsync(ctx->dWorld, worldId, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->n = n;
+    ctx->nHull = nHullVerts;
+    ctx->idxBits = bitsFor(n > 1 ? n : 2);
+    ctx->worldBits = ctx->hasWorlds ? bitsFor(ctx->cfg.numWorlds) : 0;
+    // Morton resolution: ~1 bit/axis finer than one body per cell, within the 32-bit key
+    {
+        const uint32_t perWorld = ctx->hasWorlds ? (n / ctx->cfg.numWorlds + 1) : n;
+        int mb = (bitsFor(perWorld > 1 ? perWorld : 2) + 2) / 3 + 1;
+        const int room = (32 - ctx->worldBits) / 3;
+        if (mb > room) mb = room;
+        if (mb > 10) mb = 10;
+        if (mb < 1) mb = 1;
+        ctx->mortonBits = mb;
+    }
+    ctx->stage = ST_SHAPES;
+    return AXCD_OK;
+}
+
+int32_t axcd_set_transforms(AxcdContext* ctx, const void* transforms, uint32_t n, uint32_t strideBytes) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_SHAPES) return AXCD_ERR_GPU_INVALID_OP;
+    if (n != ctx->n || strideBytes < 40 || (strideBytes & 3u)) return AXCD_ERR_INVALID_PARAM;
+    if (n && !transforms) return AXCD_ERR_NULL_POINTER;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (n) {
+        if (strideBytes == 40) {
+            CU(cudaMemcpyAsync(ctx->dXf, transforms, (size_t)n * 40, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            CU(cudaMemcpy2DAsync(ctx->dXf, 40, transforms, strideBytes, 40, n, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    ctx->stage = ST_POSES;
+    return AXCD_OK;
+}
+
+int32_t axcd_refit(AxcdContext* ctx) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    recordEv(ctx, EV_START);
+    // reset per-step counters: bounds (min = +inf encoding, max = -inf encoding) and counts
+    Counters init;
+    memset(&init, 0, sizeof(init));
+    for (int k = 0; k < 3; ++k) {
+        init.boundsMin[k] = 0xffffffffu;
+        init.boundsMax[k] = 0u;
+    }
+    ctx->hostCtr = init;
+    CU(cudaMemcpyAsync(ctx->dCtr, &ctx->hostCtr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n) {
+        const uint32_t blocks = (ctx->n + kRefitThreads - 1) / kRefitThreads;
+        refitKernel<<<blocks, kRefitThreads, 0, ctx->stream>>>(
+            reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
+            reinterpret_cast<float4*>(ctx->dAabb), ctx->n, ctx->cfg.aabbMargin, ctx->dCtr);
+        CU(cudaGetLastError());
+    }
+    ctx->launches[0] = ctx->n ? 1 : 0;
+    recordEv(ctx, EV_REFIT);
+    ctx->stage = ST_REFIT;
+    return AXCD_OK;
+}
+
+int32_t axcd_broadphase(AxcdContext* ctx) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_REFIT) return AXCD_ERR_GPU_INVALID_OP;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    const uint32_t n = ctx->n;
+    cudaStream_t st = ctx->stream;
+    ctx->numPairs = ctx->foundPairs = 0;
+    ctx->launches[1] = 0;
+    if (n >= 2) {
+        // ---- Morton keys + radix sort ----------------------------------------------------------
+        const uint32_t blocks = (n + kRefitThreads - 1) / kRefitThreads;
+        mortonKernel<<<blocks, kRefitThreads, 0, st>>>(reinterpret_cast<const float4*>(ctx->dAabb),
+                                                       ctx->hasWorlds ? ctx->dWorld : nullptr, ctx->dKeys[0],
+                                                       ctx->dVals[0], n, ctx->mortonBits, ctx->dCtr);
+        CU(cudaGetLastError());
+        const int keyBits = 3 * ctx->mortonBits + ctx->worldBits;
+        const int passes = (keyBits + 7) / 8;
+        const int sb = radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0,
+                                                 passes, ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st);
+        CU(cudaGetLastError());
+        recordEv(ctx, EV_SORT);
+        const uint32_t* sKeys = ctx->dKeys[sb];
+        const uint32_t* sVals = ctx->dVals[sb];
+        // ---- LBVH ------------------------------------------------------------------------------
+        const int worldShift = 3 * ctx->mortonBits;
+        const uint32_t b256 = (n + 255) / 256;
+        gatherLeavesKernel<<<b256, 256, 0, st>>>(ctx->dAabb, sVals, sKeys, ctx->dLeafLo, ctx->dLeafHi, n,
+                                                 ctx->hasWorlds ? worldShift : 31);
+        if (ctx->hasWorlds) markWorldEndsKernel<<<b256, 256, 0, st>>>(sKeys, n, worldShift, ctx->dWorldEnd);
+        CU(cudaMemsetAsync(ctx->dVisit, 0, sizeof(uint32_t) * n, st));
+        buildTopologyKernel<<<b256, 256, 0, st>>>(sKeys, n, ctx->dNodes, ctx->dParent);
+        fitBoxesKernel<<<b256, 256, 0, st>>>(ctx->dLeafLo, ctx->dLeafHi, n, ctx->dNodes, ctx->dParent, ctx->dVisit);
+        CU(cudaGetLastError());
+        recordEv(ctx, EV_BUILD);
+        // ---- traversal ---------------------------------------------------------------------------
+        const uint32_t tb = (n + kTravThreads - 1) / kTravThreads;
+        findPairsKernel<<<tb, kTravThreads, 0, st>>>(ctx->dLeafLo, ctx->dLeafHi, ctx->dNodes,
+                                                     ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->idxBits,
+                                                     ctx->dPairKeys[0], ctx->cfg.maxPairs, ctx->dCtr);
+        CU(cudaGetLastError());
+        recordEv(ctx, EV_PAIR);
+        // the pair count sizes the next launches
+        uint32_t found = 0;
+        CU(cudaMemcpyAsync(&found, &ctx->dCtr->pairCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->foundPairs = found;
+        ctx->numPairs = found < ctx->cfg.maxPairs ? found : ctx->cfg.maxPairs;
+        // ---- canonical order: sort packed (a,b) keys -------------------------------------------
+        const int pairPasses = (2 * ctx->idxBits + 7) / 8;
+        ctx->pairBuf = radixSort<uint64_t, false>(ctx->dPairKeys[0], ctx->dPairKeys[1], nullptr, nullptr,
+                                                  ctx->numPairs, 0, pairPasses, ctx->dSortHist, ctx->dSortStatus,
+                                                  ctx->dCtr->sortTicket, st);
+        CU(cudaGetLastError());
+        recordEv(ctx, EV_PAIRSORT);
+        // morton, (hist, scan, passes), gather, [worldEnds], topology, fit, traversal, (hist, scan, passes)
+        ctx->launches[1] = 1 + (2 + passes) + 1 + (ctx->hasWorlds ? 1 : 0) + 2 + 1 + (ctx->numPairs ? 2 + pairPasses : 0);
+    } else {
+        recordEv(ctx, EV_SORT);
+        recordEv(ctx, EV_BUILD);
+        recordEv(ctx, EV_PAIR);
+        recordEv(ctx, EV_PAIRSORT);
+    }
+    recordEv(ctx, EV_BROAD_END);
+    ctx->stage = ST_BROAD;
+    return AXCD_OK;
+}
+
+int32_t axcd_narrowphase(AxcdContext* ctx) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_BROAD) return AXCD_ERR_GPU_INVALID_OP;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    recordEv(ctx, EV_N0);
+    ctx->numContacts = ctx->foundContacts = 0;
+    const uint32_t np = ctx->numPairs;
+    ctx->launches[2] = np ? 3 : 0;   // narrowphase, scan, compact
+    if (np) {
+        NarrowParams p;
+        p.gjkMaxIters = ctx->cfg.gjkMaxIters;
+        p.epaMaxIters = ctx->cfg.epaMaxIters;
+        p.epaMaxFaces = ctx->cfg.epaMaxFaces;
+        p.gjkTol = ctx->cfg.gjkTol;
+        p.epaTol = ctx->cfg.epaTol;
+        p.wantDistances = (ctx->cfg.flags & AXCD_FLAG_PAIR_DISTANCES) ? 1u : 0u;
+        const uint32_t blocks = (np + kNarrowThreads - 1) / kNarrowThreads;
+        narrowphaseKernel<<<blocks, kNarrowThreads, 0, st>>>(ctx->dPairKeys[ctx->pairBuf], np, ctx->idxBits, ctx->dXf,
+                                                             ctx->dShapes, ctx->dHull, p, ctx->dFlags,
+                                                             ctx->dTmpContacts, ctx->dPairDist, ctx->dCtr);
+        CU(cudaGetLastError());
+        recordEv(ctx, EV_GJK);
+        const uint32_t tiles = (np + kScanTile - 1) / kScanTile;
+        CU(cudaMemsetAsync(ctx->dScanStatus, 0, sizeof(uint32_t) * tiles, st));
+        CU(cudaMemsetAsync(&ctx->dCtr->scanTicket, 0, sizeof(uint32_t), st));
+        exclusiveScanKernel<<<tiles, kScanThreads, 0, st>>>(ctx->dFlags, ctx->dOffsets, np, ctx->dScanStatus,
+                                                            &ctx->dCtr->scanTicket, ctx->dContactTotal);
+        compactContactsKernel<<<(np + 255) / 256, 256, 0, st>>>(ctx->dFlags, ctx->dOffsets, ctx->dTmpContacts, np,
+                                                                ctx->dContacts, ctx->cfg.maxContacts);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&ctx->dCtr->contactCount, ctx->dContactTotal, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    } else {
+        recordEv(ctx, EV_GJK);
+    }
+    recordEv(ctx, EV_END);
+    ctx->stage = ST_NARROW;
+    return AXCD_OK;
+}
+
+int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
+    if (!ctx || !out) return AXCD_ERR_NULL_POINTER;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    memset(out, 0, sizeof(*out));
+    CU(cudaMemcpyAsync(&ctx->hostCtr, ctx->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    out->numBodies = ctx->n;
+    if (ctx->stage >= ST_BROAD) {
+        out->numPairs = ctx->numPairs;
+        out->requiredPairs = ctx->foundPairs;
+    }
+    if (ctx->stage >= ST_NARROW) {
+        ctx->foundContacts = ctx->hostCtr.contactCount;
+        ctx->numContacts = ctx->foundContacts < ctx->cfg.maxContacts ? ctx->foundContacts : ctx->cfg.maxContacts;
+        out->numContacts = ctx->numContacts;
+        out->requiredContacts = ctx->foundContacts;
+        out->numPenetrating = ctx->hostCtr.epaCount;
+        out->gjkFailures = ctx->hostCtr.gjkFailures;
+        out->epaFailures = ctx->hostCtr.epaFailures;
+    }
+    out->refitMs = evMs(ctx, EV_START, EV_REFIT);
+    if (ctx->stage >= ST_BROAD) {
+        out->sortMs = evMs(ctx, EV_REFIT, EV_SORT);
+        out->buildMs = evMs(ctx, EV_SORT, EV_BUILD);
+        out->pairMs = evMs(ctx, EV_BUILD, EV_PAIR);
+        out->pairSortMs = evMs(ctx, EV_PAIR, EV_PAIRSORT);
+        out->broadphaseTime = evMs(ctx, EV_START, EV_BROAD_END);
+    }
+    if (ctx->stage >= ST_NARROW) {
+        out->gjkMs = evMs(ctx, EV_N0, EV_GJK);
+        out->epaMs = 0.0f;   // EPA runs inside the narrowphase kernel in this version
+        out->narrowphaseTime = evMs(ctx, EV_N0, EV_END);
+        out->totalMs = evMs(ctx, EV_START, EV_END);
+    }
+    // algorithmic bytes: refit 80 B/body, Morton 32 B/body, sort (16 B * passes + 4) per
+    // element, pair sort (16 B * passes + 8) per pair, narrowphase gather 96 B/pair + 40 B/contact
+    {
+        const uint64_t n = ctx->n, np = out->numPairs, nc = out->numContacts;
+        const int passes = (3 * ctx->mortonBits + ctx->worldBits + 7) / 8;
+        const int ppasses = (2 * ctx->idxBits + 7) / 8;
+        out->bytesMoved = n * 80 + n * 32 + n * (16ull * passes + 4) + np * (16ull * ppasses + 8) + np * 96 + nc * 40;
+    }
+    out->kernelLaunches = ctx->launches[0] + (ctx->stage >= ST_BROAD ? ctx->launches[1] : 0) +
+                          (ctx->stage >= ST_NARROW ? ctx->launches[2] : 0);
+    if (ctx->foundPairs > ctx->cfg.maxPairs || ctx->foundContacts > ctx->cfg.maxContacts) return AXCD_ERR_OUT_OF_RANGE;
+    return AXCD_OK;
+}
+
+int32_t axcd_step(AxcdContext* ctx, AxcdStats* outStats) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    int32_t rc = axcd_refit(ctx);
+    if (rc) return rc;
+    rc = axcd_broadphase(ctx);
+    if (rc) return rc;
+    rc = axcd_narrowphase(ctx);
+    if (rc) return rc;
+    AxcdStats tmp;
+    rc = axcd_get_stats(ctx, outStats ? outStats : &tmp);
+    return rc;
+}
+
+int32_t axcd_get_aabbs(AxcdContext* ctx, void* outAabb24, uint32_t cap) {
+    if (!ctx || (!outAabb24 && ctx->n)) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_REFIT) return AXCD_ERR_GPU_INVALID_OP;
+    if (cap < ctx->n) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (ctx->n) CU(cudaMemcpyAsync(outAabb24, ctx->dAabb, (size_t)ctx->n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return AXCD_OK;
+}
+
+int32_t axcd_get_pairs(AxcdContext* ctx, uint32_t* outPairs2, uint32_t cap, uint32_t* outCount) {
+    if (!ctx || !outCount) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_BROAD) return AXCD_ERR_GPU_INVALID_OP;
+    *outCount = ctx->numPairs;
+    if (ctx->numPairs == 0) return AXCD_OK;
+    if (!outPairs2) return AXCD_ERR_NULL_POINTER;
+    if (cap < ctx->numPairs) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    // unpack (a << idxBits | b) on the host, in place from the back (8-byte keys -> 2 x 4-byte ids)
+    uint64_t* tmp = static_cast<uint64_t*>(malloc(sizeof(uint64_t) * ctx->numPairs));
+    if (!tmp) return AXCD_ERR_OUT_OF_MEMORY;
+    cudaError_t e = cudaMemcpyAsync(tmp, ctx->dPairKeys[ctx->pairBuf], sizeof(uint64_t) * ctx->numPairs,
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        free(tmp);
+        return fail(ctx, e, "get_pairs");
+    }
+    const uint64_t mask = (1ull << ctx->idxBits) - 1ull;
+    for (uint32_t k = 0; k < ctx->numPairs; ++k) {
+        outPairs2[2 * k] = (uint32_t)(tmp[k] >> ctx->idxBits);
+        outPairs2[2 * k + 1] = (uint32_t)(tmp[k] & mask);
+    }
+    free(tmp);
+    return AXCD_OK;
+}
+
+int32_t axcd_get_pair_distances(AxcdContext* ctx, float* outDist, uint32_t cap, uint32_t* outCount) {
+    if (!ctx || !outCount) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_NARROW || !ctx->dPairDist) return AXCD_ERR_GPU_INVALID_OP;
+    *outCount = ctx->numPairs;
+    if (ctx->numPairs == 0) return AXCD_OK;
+    if (!outDist) return AXCD_ERR_NULL_POINTER;
+    if (cap < ctx->numPairs) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    CU(cudaMemcpyAsync(outDist, ctx->dPairDist, sizeof(float) * ctx->numPairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return AXCD_OK;
+}
+
+int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap, uint32_t* outCount) {
+    if (!ctx || !outCount) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_NARROW) return AXCD_ERR_GPU_INVALID_OP;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    uint32_t found = 0;
+    CU(cudaMemcpyAsync(&found, &ctx->dCtr->contactCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->foundContacts = found;
+    ctx->numContacts = found < ctx->cfg.maxContacts ? found : ctx->cfg.maxContacts;
+    *outCount = ctx->numContacts;
+    if (ctx->numContacts == 0) return AXCD_OK;
+    if (!out) return AXCD_ERR_NULL_POINTER;
+    if (cap < ctx->numContacts) return AXCD_ERR_OUT_OF_RANGE;
+    CU(cudaMemcpyAsync(out, ctx->dContacts, sizeof(AxcdContact) * ctx->numContacts, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return AXCD_OK;
+}
+
+// ---- test hooks ----------------------------------------------------------------------------------
+int32_t axcd_test_sort_pairs32(AxcdContext* ctx, uint32_t* keys, uint32_t* vals, uint32_t n, uint32_t keyBits) {
+    if (!ctx || (n && (!keys || !vals))) return AXCD_ERR_NULL_POINTER;
+    if (n > ctx->cfg.maxBodies || keyBits == 0 || keyBits > 32) return AXCD_ERR_OUT_OF_RANGE;
+    if (n == 0) return AXCD_OK;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->dKeys[0], keys, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->dVals[0], vals, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    const int sb = radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0,
+                                             (int)(keyBits + 7) / 8, ctx->dSortHist, ctx->dSortStatus,
+                                             ctx->dCtr->sortTicket, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(keys, ctx->dKeys[sb], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(vals, ctx->dVals[sb], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AXCD_OK;
+}
+
+int32_t axcd_test_sort_keys64(AxcdContext* ctx, uint64_t* keys, uint32_t n, uint32_t keyBits) {
+    if (!ctx || (n && !keys)) return AXCD_ERR_NULL_POINTER;
+    if (n > ctx->cfg.maxPairs || keyBits == 0 || keyBits > 64) return AXCD_ERR_OUT_OF_RANGE;
+    if (n == 0) return AXCD_OK;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->dPairKeys[0], keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
+    const int sb = radixSort<uint64_t, false>(ctx->dPairKeys[0], ctx->dPairKeys[1], nullptr, nullptr, n, 0,
+                                              (int)(keyBits + 7) / 8, ctx->dSortHist, ctx->dSortStatus,
+                                              ctx->dCtr->sortTicket, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(keys, ctx->dPairKeys[sb], sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AXCD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// Shared device/host declarations for the collision path kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "axcd.h"
+
+namespace axcd {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// ---- float3 helpers.  Every expression is evaluated exactly as written (the library is built
+// -fmad=false), matching the reference's Vec3 operators (include/axiom/math/vec3.hpp:52-191). ----
+struct V3 {
+    float x, y, z;
+};
+__host__ __device__ __forceinline__ V3 mk3(float x, float y, float z) { return V3{x, y, z}; }
+__host__ __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
+__host__ __device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__host__ __device__ __forceinline__ bool same3(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+
+// glm::quat * glm::vec3 as reached from Quat::operator*(Vec3) (reference: src/math/quat.cpp:33-38;
+// formula: SURVEY.md Appendix B).  q = (x,y,z,w).
+__device__ __forceinline__ V3 quatRotate(float4 q, V3 v) {
+    V3 u = mk3(q.x, q.y, q.z);
+    V3 uv = cross3(u, v);
+    V3 uuv = cross3(u, uv);
+    return v + ((uv * q.w) + uuv) * 2.0f;
+}
+
+// order-preserving float <-> uint mapping for atomicMin/atomicMax on floats
+__device__ __forceinline__ uint32_t floatToOrdered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float orderedToFloat(uint32_t u) {
+    uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(v);
+#else
+    float f;
+    memcpy(&f, &v, 4);
+    return f;
+#endif
+}
+
+// One 64-byte LBVH internal node: both children's boxes live in the parent, so a traversal step is
+// one aligned 64-byte read.  Leaf-ness and child indices follow from (first, split, last):
+//   left  child covers sorted leaves [first, split]   -> leaf `split`   if first == split,
+//                                                        else internal node `split`
+//   right child covers sorted leaves [split+1, last]  -> leaf `split+1` if split+1 == last,
+//                                                        else internal node `split+1`
+struct __align__(64) BvhNode {
+    float lminx, lminy, lminz, lmaxx;
+    float lmaxy, lmaxz, rminx, rminy;
+    float rminz, rmaxx, rmaxy, rmaxz;
+    uint32_t first, split, last, pad;
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be one 64-byte record");
+
+// device-side counters block (one per context)
+struct Counters {
+    uint32_t boundsMin[3];   // ordered-uint encoded minima of AABB centres
+    uint32_t boundsMax[3];
+    uint32_t pairCount;      // candidate pairs found (may exceed capacity)
+    uint32_t contactCount;
+    uint32_t epaCount;
+    uint32_t gjkFailures;
+    uint32_t epaFailures;
+    uint32_t sortTicket[8];  // dynamic tile tickets, one per radix pass
+    uint32_t scanTicket;
+    uint32_t pad[3];
+};
+
+}  // namespace axcd

@@ -1,0 +1,202 @@
+// Stage 1: per-body world-space AABB refit + scene-bounds reduction, and Morton key generation.
+//
+// HBM layout: transforms stay in the reference's own 40-byte AoS `axiom::math::Transform`
+// (position 0, rotation 12, scale 28; include/axiom/math/transform.hpp:18-22) so the upload is one
+// cudaMemcpy of the caller's buffer; AABBs are written as the reference's 24-byte `AABB`
+// (include/axiom/math/aabb.hpp:18-21).  Neither record is 16-byte aligned per element, so each
+// 256-body block moves its 10,240 B of transforms / 6,144 B of AABBs with coalesced 128-bit
+// accesses through a shared-memory stage, and threads read their record from shared memory.
+// Algorithmic bytes: 40 (Transform) + 16 (shape) in, 24 (AABB) out = 80 B/body.
+#pragma once
+
+#include "axcd_common.cuh"
+
+namespace axcd {
+
+constexpr int kRefitThreads = 256;
+
+// Transform::transformPoint (reference: src/math/transform.cpp:86-93)
+__device__ __forceinline__ V3 transformPoint(V3 pos, float4 q, V3 scale, V3 p) {
+    V3 scaled = mk3(p.x * scale.x, p.y * scale.y, p.z * scale.z);
+    V3 rotated = quatRotate(q, scaled);
+    return rotated + pos;
+}
+
+// AABB::expand(Vec3) (reference: include/axiom/math/aabb.hpp:143-150), NaN-ignoring selects
+__device__ __forceinline__ void expandPoint(V3& lo, V3& hi, V3 p) {
+    lo.x = (p.x < lo.x) ? p.x : lo.x;
+    lo.y = (p.y < lo.y) ? p.y : lo.y;
+    lo.z = (p.z < lo.z) ? p.z : lo.z;
+    hi.x = (p.x > hi.x) ? p.x : hi.x;
+    hi.y = (p.y > hi.y) ? p.y : hi.y;
+    hi.z = (p.z > hi.z) ? p.z : hi.z;
+}
+
+__global__ void __launch_bounds__(kRefitThreads)
+refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 (base 16B aligned)
+            const uint4* __restrict__ shapes,    // AxcdShape as uint4
+            const float4* __restrict__ hull,     // hull vertices padded to float4
+            float4* __restrict__ aabb4,          // n*24 bytes viewed as float4
+            uint32_t n, float margin, Counters* __restrict__ ctr) {
+    __shared__ __align__(16) float sIn[kRefitThreads * 10];
+    __shared__ __align__(16) float sOut[kRefitThreads * 6];
+    __shared__ float sRed[6][kRefitThreads / 32];
+
+    const uint32_t base = blockIdx.x * kRefitThreads;
+    const uint32_t cnt = min((uint32_t)kRefitThreads, n - base);
+    const int tid = threadIdx.x;
+
+    // ---- stage the block's transforms: coalesced 128-bit loads --------------------------------
+    {
+        const uint32_t nFloats = cnt * 10;
+        const uint32_t nVec = nFloats / 4;                 // whole float4s
+        const float4* src = xf4 + (size_t)base * 10 / 4;   // base*40 B is a multiple of 16 B
+        float4* dst = reinterpret_cast<float4*>(sIn);
+        for (uint32_t i = tid; i < nVec; i += kRefitThreads) dst[i] = __ldg(src + i);
+        const float* srcF = reinterpret_cast<const float*>(src);
+        for (uint32_t i = nVec * 4 + tid; i < nFloats; i += kRefitThreads) sIn[i] = __ldg(srcF + i);
+    }
+    __syncthreads();
+
+    V3 lo = mk3(0.f, 0.f, 0.f), hi = lo;
+    bool valid = tid < (int)cnt;
+    if (valid) {
+        const float* t = sIn + tid * 10;
+        const V3 pos = mk3(t[0], t[1], t[2]);
+        const float4 q = make_float4(t[3], t[4], t[5], t[6]);
+        const V3 scl = mk3(t[7], t[8], t[9]);
+        const uint4 sh = __ldg(shapes + base + tid);
+        const float p0 = __uint_as_float(sh.y), p1 = __uint_as_float(sh.z), p2 = __uint_as_float(sh.w);
+        if (sh.x == AXCD_SHAPE_SPHERE) {
+            // AABB::fromCenterExtents(position, Vec3(r)) (aabb.hpp:213-215); rotation and scale
+            // ignored as in the reference's sphere placement (src/debug/physics_debug_draw.cpp:246-248)
+            lo = pos - mk3(p0, p0, p0);
+            hi = pos + mk3(p0, p0, p0);
+        } else if (sh.x == AXCD_SHAPE_BOX) {
+            // 8 corners in the order of src/debug/debug_draw.cpp:99-108, AABB(Vec3) then expand()
+            const float sx[8] = {-1.f, 1.f, 1.f, -1.f, -1.f, 1.f, 1.f, -1.f};
+            const float sy[8] = {-1.f, -1.f, -1.f, -1.f, 1.f, 1.f, 1.f, 1.f};
+            const float sz[8] = {-1.f, -1.f, 1.f, 1.f, -1.f, -1.f, 1.f, 1.f};
+            V3 c0 = transformPoint(pos, q, scl, mk3(sx[0] * p0, sy[0] * p1, sz[0] * p2));
+            lo = c0;
+            hi = c0;
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+                expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(sx[k] * p0, sy[k] * p1, sz[k] * p2)));
+        } else {   // AXCD_SHAPE_CONVEX (validated on the host): min/max over transformPoint(v_i)
+            const uint32_t first = sh.y, count = sh.z;
+            float4 v = __ldg(hull + first);
+            V3 c0 = transformPoint(pos, q, scl, mk3(v.x, v.y, v.z));
+            lo = c0;
+            hi = c0;
+            for (uint32_t k = 1; k < count; ++k) {
+                v = __ldg(hull + first + k);
+                expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(v.x, v.y, v.z)));
+            }
+        }
+        if (margin != 0.0f) {   // AABB::expand(float) (aabb.hpp:156-160)
+            lo = lo - mk3(margin, margin, margin);
+            hi = hi + mk3(margin, margin, margin);
+        }
+        float* o = sOut + tid * 6;
+        o[0] = lo.x; o[1] = lo.y; o[2] = lo.z;
+        o[3] = hi.x; o[4] = hi.y; o[5] = hi.z;
+    }
+
+    // ---- scene bounds of the AABB centres (for Morton normalisation; quality only) ------------
+    {
+        // AABB::center() (aabb.hpp:62)
+        V3 c = (lo + hi) * 0.5f;
+        const float big = 3.0e38f;
+        bool fin = valid && fabsf(c.x) < big && fabsf(c.y) < big && fabsf(c.z) < big;   // false for NaN
+        float v[6] = {fin ? c.x : big, fin ? c.y : big, fin ? c.z : big,
+                      fin ? c.x : -big, fin ? c.y : -big, fin ? c.z : -big};
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                v[k] = fminf(v[k], __shfl_xor_sync(0xffffffffu, v[k], off));
+                v[k + 3] = fmaxf(v[k + 3], __shfl_xor_sync(0xffffffffu, v[k + 3], off));
+            }
+        }
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sRed[k][tid >> 5] = v[k];
+        }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float r = sRed[tid][0];
+        for (int w = 1; w < kRefitThreads / 32; ++w)
+            r = (tid < 3) ? fminf(r, sRed[tid][w]) : fmaxf(r, sRed[tid][w]);
+        if (tid < 3) {
+            if (r < 3.0e38f) atomicMin(&ctr->boundsMin[tid], floatToOrdered(r));
+        } else {
+            if (r > -3.0e38f) atomicMax(&ctr->boundsMax[tid - 3], floatToOrdered(r));
+        }
+    }
+
+    // ---- write the block's AABBs: coalesced 128-bit stores -----------------------------------
+    {
+        const uint32_t nFloats = cnt * 6;
+        const uint32_t nVec = nFloats / 4;
+        float4* dst = aabb4 + (size_t)base * 6 / 4;   // base*24 B is a multiple of 16 B
+        const float4* src = reinterpret_cast<const float4*>(sOut);
+        for (uint32_t i = tid; i < nVec; i += kRefitThreads) dst[i] = src[i];
+        float* dstF = reinterpret_cast<float*>(dst);
+        for (uint32_t i = nVec * 4 + tid; i < nFloats; i += kRefitThreads) dstF[i] = sOut[i];
+    }
+}
+
+// ---- Morton keys -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expandBits10(uint32_t v) {   // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// key = worldId << (3*bitsPerAxis) | morton(centre).  Reads the 24-byte AABBs through a shared
+// stage (coalesced 128-bit loads), writes key (4 B) + body index (4 B): 32 B/body.
+__global__ void __launch_bounds__(kRefitThreads)
+mortonKernel(const float4* __restrict__ aabb4, const uint32_t* __restrict__ worldId,
+             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n,
+             int bitsPerAxis, const Counters* __restrict__ ctr) {
+    __shared__ __align__(16) float sIn[kRefitThreads * 6];
+    const uint32_t base = blockIdx.x * kRefitThreads;
+    const uint32_t cnt = min((uint32_t)kRefitThreads, n - base);
+    const int tid = threadIdx.x;
+    {
+        const uint32_t nFloats = cnt * 6, nVec = nFloats / 4;
+        const float4* src = aabb4 + (size_t)base * 6 / 4;
+        float4* dst = reinterpret_cast<float4*>(sIn);
+        for (uint32_t i = tid; i < nVec; i += kRefitThreads) dst[i] = __ldg(src + i);
+        const float* srcF = reinterpret_cast<const float*>(src);
+        for (uint32_t i = nVec * 4 + tid; i < nFloats; i += kRefitThreads) sIn[i] = __ldg(srcF + i);
+    }
+    __syncthreads();
+    if (tid >= (int)cnt) return;
+    const float* b = sIn + tid * 6;
+    const float cells = (float)(1u << bitsPerAxis);
+    uint32_t code = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float lo = orderedToFloat(ctr->boundsMin[k]);
+        const float hi = orderedToFloat(ctr->boundsMax[k]);
+        const float c = (b[k] + b[k + 3]) * 0.5f;
+        float ext = hi - lo;
+        float t = (ext > 0.0f) ? (c - lo) / ext : 0.0f;
+        t = t * cells;
+        // NaN / out-of-range centres clamp into the grid (quality only; never affects the pair set)
+        int q = (t >= 0.0f) ? ((t < cells) ? (int)t : (int)cells - 1) : 0;
+        q = min(max(q, 0), (int)cells - 1);
+        code |= expandBits10((uint32_t)q) << (2 - k);
+    }
+    if (worldId) code |= __ldg(worldId + base + tid) << (3 * bitsPerAxis);
+    keys[base + tid] = code;
+    vals[base + tid] = base + tid;
+}
+
+}  // namespace axcd

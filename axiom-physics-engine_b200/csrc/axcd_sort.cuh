@@ -1,0 +1,287 @@
+// Hand-written LSD radix sort (8-bit digits), "onesweep" style: one histogram kernel for all
+// passes, then one kernel per pass that ranks a 4096-key tile in shared memory, resolves its global
+// digit offsets with a decoupled look-back over per-tile status words, and scatters with coalesced
+// runs.  Keys are uint32 (+ uint32 payload) for the Morton sort and uint64 (no payload) for the
+// candidate-pair sort.  Stable.  Algorithmic HBM bytes per element per pass: read key(+val) and
+// write key(+val); plus one key read for the histogram.
+#pragma once
+
+#include "axcd_common.cuh"
+
+namespace axcd {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per tile
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kRadix = 256;
+constexpr int kMaxPasses = 8;
+
+constexpr uint32_t kFlagAggregate = 1u << 30;
+constexpr uint32_t kFlagInclusive = 2u << 30;
+constexpr uint32_t kFlagMask = 3u << 30;
+constexpr uint32_t kValueMask = ~kFlagMask;
+
+template <typename K>
+__device__ __forceinline__ uint32_t digitOf(K key, int shift) {
+    return (uint32_t)(key >> shift) & 0xffu;
+}
+
+// hist[p*256 + d] += number of keys whose p-th digit is d (all passes in one read of the keys)
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads)
+radixHistogramKernel(const K* __restrict__ keys, uint32_t n, int bitStart, int passes,
+                     uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[kMaxPasses * kRadix];
+    for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) sh[i] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * kSortThreads;
+    for (uint32_t i = blockIdx.x * kSortThreads + threadIdx.x; i < n; i += stride) {
+        const K k = keys[i];
+        for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * kRadix + digitOf(k, bitStart + 8 * p)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) {
+        const uint32_t v = sh[i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+}
+
+// In-place exclusive scan of each pass's 256 bins; one block of 256 threads, one warp-scan tree.
+__global__ void __launch_bounds__(kRadix)
+radixScanKernel(uint32_t* __restrict__ hist, int passes) {
+    __shared__ uint32_t warpSum[kRadix / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int p = 0; p < passes; ++p) {
+        const uint32_t v = hist[p * kRadix + tid];
+        uint32_t inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) warpSum[w] = inc;
+        __syncthreads();
+        uint32_t basev = 0;
+        for (int i = 0; i < w; ++i) basev += warpSum[i];
+        hist[p * kRadix + tid] = basev + inc - v;
+        __syncthreads();
+    }
+}
+
+// One radix pass.  `status` holds numTiles*256 words for this pass (zero-initialised); `ticket`
+// hands out tile indices in launch order so that a tile's predecessors have always started.
+template <typename K, bool HAS_VAL>
+__global__ void __launch_bounds__(kSortThreads)
+radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
+                    const uint32_t* __restrict__ valsIn, uint32_t* __restrict__ valsOut,
+                    uint32_t n, int shift, const uint32_t* __restrict__ globalBase,
+                    volatile uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+    __shared__ K sKeys[kSortTile];
+    __shared__ uint32_t sVals[HAS_VAL ? kSortTile : 1];
+    __shared__ uint32_t sWarpHist[kSortWarps][kRadix];
+    __shared__ uint32_t sDigitStart[kRadix];
+    __shared__ uint32_t sGlobalOff[kRadix];
+    __shared__ uint32_t sWarpTot[kSortWarps];
+    __shared__ uint32_t sTile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&sWarpHist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t tileBase = tile * kSortTile;
+    const uint32_t tileCount = min((uint32_t)kSortTile, n - tileBase);
+
+    // ---- load (warp-striped: warp w owns a contiguous 512-key span) and rank ------------------
+    K key[kSortItems];
+    uint32_t val[kSortItems];
+    uint32_t rank[kSortItems];
+    const uint32_t warpBase = tileBase + warp * (32 * kSortItems);
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t idx = warpBase + k * 32 + lane;
+        const bool ok = idx < n;
+        key[k] = ok ? keysIn[idx] : (K)~(K)0;   // padding sorts last (digit 255, highest index)
+        if (HAS_VAL) val[k] = ok ? valsIn[idx] : 0u;
+    }
+    const uint32_t lanemaskLt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t d = digitOf(key[k], shift);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t prev = 0;
+        if (lane == leader) {
+            prev = sWarpHist[warp][d];
+            sWarpHist[warp][d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[k] = prev + __popc(peers & lanemaskLt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-digit: exclusive prefix over warps, tile total, look-back -------------------------
+    uint32_t digitCount;
+    {
+        const int d = tid;   // kSortThreads == kRadix
+        uint32_t sum = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t t = sWarpHist[w][d];
+            sWarpHist[w][d] = sum;
+            sum += t;
+        }
+        digitCount = sum;
+        uint32_t pub = sum;
+        if (d == kRadix - 1) pub -= (kSortTile - tileCount);   // padding keys are not real
+        volatile uint32_t* st = status + (size_t)tile * kRadix;
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st[d] = kFlagInclusive | pub;
+        } else {
+            st[d] = kFlagAggregate | pub;
+            for (int t = (int)tile - 1; t >= 0; --t) {
+                volatile uint32_t* pt = status + (size_t)t * kRadix;
+                uint32_t s;
+                do { s = pt[d]; } while ((s & kFlagMask) == 0);
+                excl += s & kValueMask;
+                if ((s & kFlagMask) == kFlagInclusive) break;
+            }
+            st[d] = kFlagInclusive | (excl + pub);
+        }
+        sGlobalOff[d] = globalBase[d] + excl;
+    }
+    // ---- exclusive scan of the tile's digit counts (position of each digit's run in the tile) --
+    {
+        uint32_t inc = digitCount;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) sWarpTot[warp] = inc;
+        __syncthreads();
+        uint32_t basev = 0;
+#pragma unroll
+        for (int i = 0; i < kSortWarps; ++i) basev += (i < warp) ? sWarpTot[i] : 0u;
+        sDigitStart[tid] = basev + inc - digitCount;
+    }
+    __syncthreads();
+
+    // ---- local scatter into sorted order --------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t d = digitOf(key[k], shift);
+        const uint32_t pos = sDigitStart[d] + sWarpHist[warp][d] + rank[k];
+        sKeys[pos] = key[k];
+        if (HAS_VAL) sVals[pos] = val[k];
+    }
+    __syncthreads();
+
+    // ---- coalesced global scatter ----------------------------------------------------------------
+    for (uint32_t i = tid; i < tileCount; i += kSortThreads) {
+        const K kk = sKeys[i];
+        const uint32_t d = digitOf(kk, shift);
+        const uint32_t dst = sGlobalOff[d] + (i - sDigitStart[d]);
+        keysOut[dst] = kk;
+        if (HAS_VAL) valsOut[dst] = sVals[i];
+    }
+}
+
+// Host driver.  Sorts by key bits [bitStart, bitStart + 8*passes).  The sorted data ends in
+// (keysA, valsA) if `passes` is even, else in (keysB, valsB); returns which (0 = A, 1 = B).
+// scratchHist: kMaxPasses*256 words; scratchStatus: passes * numTiles * 256 words.
+template <typename K, bool HAS_VAL>
+inline int radixSort(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, uint32_t n, int bitStart,
+                     int passes, uint32_t* scratchHist, uint32_t* scratchStatus,
+                     uint32_t* tickets /* kMaxPasses words */, cudaStream_t stream) {
+    if (n == 0 || passes == 0) return 0;
+    const uint32_t numTiles = (n + kSortTile - 1) / kSortTile;
+    cudaMemsetAsync(scratchHist, 0, sizeof(uint32_t) * kMaxPasses * kRadix, stream);
+    cudaMemsetAsync(scratchStatus, 0, sizeof(uint32_t) * (size_t)passes * numTiles * kRadix, stream);
+    cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * kMaxPasses, stream);
+    uint32_t histBlocks = (n + kSortThreads * 8 - 1) / (kSortThreads * 8);
+    if (histBlocks > (uint32_t)kNumSMs * 8) histBlocks = kNumSMs * 8;
+    radixHistogramKernel<K><<<histBlocks, kSortThreads, 0, stream>>>(keysA, n, bitStart, passes, scratchHist);
+    radixScanKernel<<<1, kRadix, 0, stream>>>(scratchHist, passes);
+    K* kin = keysA;
+    K* kout = keysB;
+    uint32_t* vin = valsA;
+    uint32_t* vout = valsB;
+    for (int p = 0; p < passes; ++p) {
+        radixOnesweepKernel<K, HAS_VAL><<<numTiles, kSortThreads, 0, stream>>>(
+            kin, kout, vin, vout, n, bitStart + 8 * p, scratchHist + p * kRadix,
+            scratchStatus + (size_t)p * numTiles * kRadix, tickets + p);
+        K* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    return passes & 1;
+}
+
+// ---- single-pass exclusive scan of uint32 (decoupled look-back), used for compaction ------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// out[i] = sum of in[0..i); *total = sum of all.  status: numTiles words, zero-initialised.
+__global__ void __launch_bounds__(kScanThreads)
+exclusiveScanKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                    volatile uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                    uint32_t* __restrict__ total) {
+    __shared__ uint32_t sWarp[kScanThreads / 32];
+    __shared__ uint32_t sTile, sExcl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t base = tile * kScanTile + tid * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) sWarp[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, tileTotal = 0;
+#pragma unroll
+    for (int i = 0; i < kScanThreads / 32; ++i) {
+        wbase += (i < warp) ? sWarp[i] : 0u;
+        tileTotal += sWarp[i];
+    }
+    if (tid == 0) {
+        uint32_t excl = 0;
+        if (tile == 0) {
+            status[0] = kFlagInclusive | tileTotal;
+        } else {
+            status[tile] = kFlagAggregate | tileTotal;
+            for (int t = (int)tile - 1; t >= 0; --t) {
+                uint32_t s;
+                do { s = status[t]; } while ((s & kFlagMask) == 0);
+                excl += s & kValueMask;
+                if ((s & kFlagMask) == kFlagInclusive) break;
+            }
+            status[tile] = kFlagInclusive | (excl + tileTotal);
+        }
+        sExcl = excl;
+        if ((tile + 1) * (uint64_t)kScanTile >= n) *total = excl + tileTotal;
+    }
+    __syncthreads();
+    uint32_t run = sExcl + wbase + inc - sum;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+}  // namespace axcd

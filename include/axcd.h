@@ -115,6 +115,8 @@ typedef struct AxcdStats {
     /* gui::PhysicsWorldStats sinks (include/axiom/gui/physics_panel.hpp:26-30)                 */
     float broadphaseTime, narrowphaseTime;
     uint64_t bytesMoved;    /* algorithmic HBM bytes of the step              */
+    uint32_t kernelLaunches; /* kernels launched by the last refit+broadphase+narrowphase       */
+    uint32_t reserved;
 } AxcdStats;
 
 typedef struct AxcdContext AxcdContext; /* opaque */

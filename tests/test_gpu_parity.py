@@ -1,0 +1,230 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI vs the CPU oracle.
+
+Integer / index results (candidate pairs, contact pair set, statuses) must be BIT-EXACT after the
+canonical (a<b, sorted) ordering.  AABBs are float but compared bit-exactly too, because the
+candidate set is defined on them by exact compares.  Contact floats (position, normal, depth) and
+GJK distances: tolerance 1e-4 relative (BASELINE.json north_star), written as REL below.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import axcd
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def oracle_step(s, margin=0.0, brute=False, nthreads=8, want_distances=False):
+    rc, bb = O.refit(s.xf, s.shapes, s.hull, margin=margin, nthreads=nthreads)
+    assert rc == 0
+    pairs = O.broadphase(bb, s.world_id, brute=brute, nthreads=nthreads)
+    con, dist, st = O.narrowphase(s.xf, s.shapes, pairs, s.hull, nthreads=nthreads, want_distances=want_distances)
+    return bb, pairs, con, dist, st
+
+
+def assert_contacts_match(gc, oc):
+    assert len(gc) == len(oc)
+    assert np.array_equal(gc["a"], oc["a"]) and np.array_equal(gc["b"], oc["b"])   # bit-exact set + order
+    assert np.array_equal(gc["status"], oc["status"])
+    for f in ("px", "py", "pz", "nx", "ny", "nz", "depth"):
+        np.testing.assert_allclose(gc[f], oc[f], rtol=REL, atol=REL * 1e-2)
+
+
+def run_and_compare(s, margin=0.0, brute=False, **kw):
+    w = axcd.CollisionWorld.for_scene(s, aabbMargin=margin, **kw)
+    st = w.step()
+    bb, pairs, con, _, ost = oracle_step(s, margin=margin, brute=brute)
+    assert np.array_equal(w.aabbs().view(np.uint32), bb.view(np.uint32))          # bit-exact AABBs
+    gp = w.pairs()
+    assert st.numPairs == len(pairs)
+    assert np.array_equal(gp, pairs)                                              # bit-exact pair set
+    gc = w.contacts()
+    assert st.numContacts == len(con)
+    assert_contacts_match(gc, con)
+    assert st.numPenetrating == ost.numPenetrating
+    assert st.gjkFailures == ost.gjkFailures and st.epaFailures == ost.epaFailures
+    bitwise = all(np.array_equal(gc[f].view(np.uint32), con[f].view(np.uint32))
+                  for f in ("px", "py", "pz", "nx", "ny", "nz", "depth"))
+    w.close()
+    return st, bitwise
+
+
+# ------------------------------------------------------------------ device primitives ----------
+@pytest.mark.parametrize("n", [1, 2, 31, 4095, 4096, 4097, 100_000, 1_000_003])
+def test_radix_sort_pairs32_vs_numpy(n):
+    rng = np.random.default_rng(n)
+    w = axcd.CollisionWorld(max(n, 16))
+    for bits in (8, 24, 32):
+        keys = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
+        if n > 10:
+            keys[: n // 3] = keys[0]            # long runs of duplicates: stability matters
+        vals = np.arange(n, dtype=np.uint32)
+        k2, v2 = w.test_sort_pairs32(keys, vals, bits)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k2, keys[order])
+        assert np.array_equal(v2, vals[order])   # stable
+    w.close()
+
+
+@pytest.mark.parametrize("n", [1, 4097, 300_000])
+def test_radix_sort_keys64_vs_numpy(n):
+    rng = np.random.default_rng(n)
+    w = axcd.CollisionWorld(16, max_pairs=max(n, 1024))
+    for bits in (34, 40, 48):
+        keys = rng.integers(0, 1 << bits, n, dtype=np.uint64)
+        assert np.array_equal(w.test_sort_keys64(keys, bits), np.sort(keys))
+    w.close()
+
+
+# ------------------------------------------------------------------ parity per config ----------
+def test_c0_reference_scene_vs_bruteforce_oracle():
+    st, bitwise = run_and_compare(axcd.config_scene("C0"), brute=True)
+    assert st.numPairs == 2875 and st.numContacts == 1381
+    assert bitwise, "contact floats expected bit-identical (no FMA contraction on either side)"
+
+
+def test_c1_100k_single_scene():
+    st, bitwise = run_and_compare(axcd.config_scene("C1"))
+    assert st.numPairs > 250_000
+    assert bitwise
+
+
+def test_c2_hull_mix_epa_heavy_scaled():
+    st, bitwise = run_and_compare(axcd.config_scene("C2", scale=0.05))
+    assert st.numPenetrating > 0.2 * st.numPairs
+    assert bitwise
+
+
+def test_c3_batched_worlds_no_cross_world_pairs():
+    s = axcd.config_scene("C3", scale=64 / 4096)
+    st, _ = run_and_compare(s)
+    w = axcd.CollisionWorld.for_scene(s)
+    w.step()
+    p = w.pairs()
+    assert (s.world_id[p[:, 0]] == s.world_id[p[:, 1]]).all()
+    w.close()
+
+
+def test_aabb_margin_inflates_candidates():
+    s = axcd.config_scene("C0")
+    st0, _ = run_and_compare(s, brute=True)
+    st1, _ = run_and_compare(s, margin=0.1, brute=True)
+    assert st1.numPairs > st0.numPairs and st1.numContacts == st0.numContacts
+
+
+def test_pair_distances_mode():
+    s = axcd.config_scene("C2", scale=0.01)
+    w = axcd.CollisionWorld.for_scene(s, flags=axcd.FLAG_PAIR_DISTANCES)
+    w.step()
+    _, pairs, con, dist, _ = oracle_step(s, want_distances=True)
+    assert np.array_equal(w.pairs(), pairs)
+    assert_contacts_match(w.contacts(), con)
+    gd = w.pair_distances()
+    np.testing.assert_allclose(gd, dist, rtol=REL, atol=1e-6)
+    w.close()
+
+
+# ------------------------------------------------------------------ full size ------------------
+def test_headline_1m_bodies_full_size():
+    s = axcd.config_scene("headline")
+    w = axcd.CollisionWorld.for_scene(s)
+    st = w.step()
+    # oracle grid broadphase and narrowphase finish in seconds on the box's host cores
+    bb, pairs, con, _, ost = oracle_step(s, nthreads=16)
+    assert np.array_equal(w.aabbs().view(np.uint32), bb.view(np.uint32))
+    gp = w.pairs()
+    assert np.array_equal(gp, pairs)
+    key = gp[:, 0].astype(np.uint64) << np.uint64(32) | gp[:, 1]
+    assert (gp[:, 0] < gp[:, 1]).all() and (np.diff(key.astype(np.int64)) > 0).all()   # canonical
+    assert_contacts_match(w.contacts(), con)
+    # idempotence: a second step on the same poses gives the same answer
+    st2 = w.step()
+    assert (st2.numPairs, st2.numContacts) == (st.numPairs, st.numContacts)
+    assert np.array_equal(w.pairs(), gp)
+    w.close()
+
+
+# ------------------------------------------------------------------ edge cases -----------------
+def test_empty_single_and_two_bodies():
+    w = axcd.CollisionWorld(8)
+    w.set_shapes(np.zeros(0, axcd.SHAPE_DT))
+    w.set_transforms(np.zeros((0, 10), np.float32))
+    st = w.step()
+    assert (st.numPairs, st.numContacts) == (0, 0)
+    w.set_shapes(np.array([O.sphere(1.0)], axcd.SHAPE_DT))
+    w.set_transforms(np.array([O.xf()]))
+    st = w.step()
+    assert (st.numBodies, st.numPairs, st.numContacts) == (1, 0, 0)
+    w.set_shapes(np.array([O.sphere(1.0), O.box(1, 1, 1)], axcd.SHAPE_DT))
+    w.set_transforms(np.array([O.xf(), O.xf((1.5, 0, 0))]))
+    st = w.step()
+    assert (st.numPairs, st.numContacts) == (1, 1)
+    c = w.contacts()[0]
+    assert (c["a"], c["b"]) == (0, 1) and c["depth"] == pytest.approx(0.5, abs=1e-5)
+    w.close()
+
+
+def test_all_bodies_coincident_and_capacity_overflow():
+    n = 200
+    shapes = np.array([O.box(0.5, 0.5, 0.5)] * n, axcd.SHAPE_DT)
+    xf = np.array([O.xf((1, 2, 3))] * n)
+    s = axcd.Scene(xf, shapes)
+    st, _ = run_and_compare(s, brute=True, pairs_per_body=100)
+    assert st.numPairs == n * (n - 1) // 2
+    w = axcd.CollisionWorld(n, max_pairs=1024)
+    w.set_shapes(shapes)
+    w.set_transforms(xf)
+    with pytest.raises(axcd.AxcdError) as e:
+        w.step()
+    assert e.value.code == 601
+    stats = axcd.Stats()
+    assert w._lib.axcd_get_stats(w._ctx, C.byref(stats)) == 601
+    assert stats.requiredPairs == n * (n - 1) // 2 and stats.numPairs == 1024
+    w.close()
+
+
+def test_nan_and_touching_boxes():
+    shapes = np.array([O.box(0.5, 0.5, 0.5), O.box(0.5, 0.5, 0.5), O.sphere(0.5), O.sphere(0.5)], axcd.SHAPE_DT)
+    xf = np.array([O.xf((0, 0, 0)), O.xf((1, 0, 0)), O.xf((np.nan, 0, 0)), O.xf((0.25, 0.25, 0))])
+    st, _ = run_and_compare(axcd.Scene(xf, shapes), brute=True)
+    w = axcd.CollisionWorld.for_scene(axcd.Scene(xf, shapes))
+    w.step()
+    p = w.pairs().tolist()
+    assert [0, 1] in p                       # touching AABBs count (aabb.hpp:132-135)
+    assert all(2 not in q for q in p)        # a NaN box has no pairs
+    w.close()
+
+
+def test_error_behaviour():
+    w = axcd.CollisionWorld(8)
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_shapes(np.array([(2, 1.0, 1.0, 0.0)], axcd.SHAPE_DT))      # Capsule
+    assert e.value.code == 300
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_shapes(np.array([O.hull_shape(0, 4)], axcd.SHAPE_DT))       # hull range outside pool
+    assert e.value.code == 300
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_shapes(np.zeros(9, axcd.SHAPE_DT))                          # over capacity
+    assert e.value.code == 601
+    assert w._lib.axcd_refit(w._ctx) == 503                               # no poses yet
+    w.set_shapes(np.array([O.sphere(1.0)], axcd.SHAPE_DT))
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_transforms(np.zeros((2, 10), np.float32))                   # count mismatch
+    assert e.value.code == 600
+    w.set_transforms(np.array([O.xf()]))
+    assert w._lib.axcd_narrowphase(w._ctx) == 503                         # broadphase not run
+    w.close()
+
+
+def test_strided_transforms():
+    s = axcd.config_scene("C0")
+    w = axcd.CollisionWorld.for_scene(s)
+    wide = np.zeros((s.n, 16), np.float32)
+    wide[:, :10] = s.xf
+    w.set_transforms(wide, stride=64)
+    st = w.step()
+    assert st.numPairs == 2875 and st.numContacts == 1381
+    w.close()

@@ -55,16 +55,14 @@ struct AxcdContext {
     uint32_t* dVisit = nullptr;
     uint32_t* dWorldEnd = nullptr;
     uint64_t* dPairKeys[2] = {nullptr, nullptr};
-    uint32_t* dFlags = nullptr;      // per pair
-    uint32_t* dOffsets = nullptr;    // per pair
-    AxcdContact* dTmpContacts = nullptr;   // per pair
+    EpaWork* dEpaWork = nullptr;     // GJK -> EPA queue (maxContacts)
+    uint32_t* dEpaOverflow = nullptr;
+    uint32_t* dGjkStatus = nullptr;  // look-back status, one word per GJK tile
     AxcdContact* dContacts = nullptr;
     float* dPairDist = nullptr;
     uint32_t* dSortHist = nullptr;
     uint32_t* dSortStatus = nullptr;
-    uint32_t* dScanStatus = nullptr;
     Counters* dCtr = nullptr;
-    uint32_t* dContactTotal = nullptr;
     void* hPinned = nullptr;         // staging for strided transform uploads
     size_t hPinnedBytes = 0;
     cudaEvent_t ev[EV_COUNT];
@@ -173,9 +171,9 @@ void axcd_destroy(AxcdContext* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dLeafLo, ctx->dLeafHi, ctx->dNodes, ctx->dParent,
-                    ctx->dVisit, ctx->dWorldEnd, ctx->dPairKeys[0], ctx->dPairKeys[1], ctx->dFlags,
-                    ctx->dOffsets, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
-                    ctx->dSortStatus, ctx->dScanStatus, ctx->dCtr, ctx->dContactTotal};
+                    ctx->dVisit, ctx->dWorldEnd, ctx->dPairKeys[0], ctx->dPairKeys[1], ctx->dEpaWork,
+                    ctx->dEpaOverflow, ctx->dGjkStatus, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
+                    ctx->dSortStatus, ctx->dCtr};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
@@ -206,7 +204,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
     AxcdContext* ctx = new (std::nothrow) AxcdContext();
     if (!ctx) return AXCD_ERR_OUT_OF_MEMORY;
     ctx->cfg = *cfg;
-    if (ctx->cfg.epaMaxFaces > (uint32_t)kEpaMaxFaces) ctx->cfg.epaMaxFaces = kEpaMaxFaces;
+    if (ctx->cfg.epaMaxFaces > (uint32_t)kEpaHardFaces) ctx->cfg.epaMaxFaces = kEpaHardFaces;
     for (int i = 0; i < EV_COUNT; ++i) {
         ctx->ev[i] = nullptr;
         ctx->evValid[i] = false;
@@ -240,17 +238,16 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dNodes, nb));
         CU(dalloc(&ctx->dParent, 2 * nb));
         CU(dalloc(&ctx->dVisit, nb));
-        CU(dalloc(&ctx->dFlags, np));
-        CU(dalloc(&ctx->dOffsets, np));
-        CU(dalloc(&ctx->dTmpContacts, np));
+        CU(dalloc(&ctx->dEpaWork, (size_t)cfg->maxContacts));
+        CU(dalloc(&ctx->dEpaOverflow, (size_t)cfg->maxContacts));
+        CU(dalloc(&ctx->dGjkStatus, np / kGjkThreads + 2));
+        CU(cudaFuncSetAttribute(epaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaSmemBytes));
         CU(dalloc(&ctx->dContacts, (size_t)cfg->maxContacts));
         if (cfg->flags & AXCD_FLAG_PAIR_DISTANCES) CU(dalloc(&ctx->dPairDist, np));
         CU(dalloc(&ctx->dSortHist, (size_t)kMaxPasses * kRadix));
         const size_t maxTiles = sortTilesFor(nb > np ? nb : np);
         CU(dalloc(&ctx->dSortStatus, (size_t)kMaxPasses * maxTiles * kRadix));
-        CU(dalloc(&ctx->dScanStatus, (np + kScanTile - 1) / kScanTile + 1));
         CU(dalloc(&ctx->dCtr, 1));
-        CU(dalloc(&ctx->dContactTotal, 1));
         CU(cudaMemsetAsync(ctx->dCtr, 0, sizeof(Counters), ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         return AXCD_OK;
@@ -277,7 +274,7 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
             uint32_t first, cnt;
             memcpy(&first, &s.p0, 4);
             memcpy(&cnt, &s.p1, 4);
-            if (cnt == 0 || (uint64_t)first + cnt > nHullVerts) return AXCD_ERR_INVALID_SHAPE;
+            if (cnt == 0 || cnt > 65535u || (uint64_t)first + cnt > nHullVerts) return AXCD_ERR_INVALID_SHAPE;
         } else if (s.type != AXCD_SHAPE_SPHERE && s.type != AXCD_SHAPE_BOX) {
             return AXCD_ERR_INVALID_SHAPE;   // Capsule / Plane / Mesh are not in scope
         }
@@ -436,7 +433,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
     recordEv(ctx, EV_N0);
     ctx->numContacts = ctx->foundContacts = 0;
     const uint32_t np = ctx->numPairs;
-    ctx->launches[2] = np ? 3 : 0;   // narrowphase, scan, compact
+    ctx->launches[2] = np ? 3 : 0;   // GJK, EPA, EPA fallback
     if (np) {
         NarrowParams p;
         p.gjkMaxIters = ctx->cfg.gjkMaxIters;
@@ -445,21 +442,22 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         p.gjkTol = ctx->cfg.gjkTol;
         p.epaTol = ctx->cfg.epaTol;
         p.wantDistances = (ctx->cfg.flags & AXCD_FLAG_PAIR_DISTANCES) ? 1u : 0u;
-        const uint32_t blocks = (np + kNarrowThreads - 1) / kNarrowThreads;
-        narrowphaseKernel<<<blocks, kNarrowThreads, 0, st>>>(ctx->dPairKeys[ctx->pairBuf], np, ctx->idxBits, ctx->dXf,
-                                                             ctx->dShapes, ctx->dHull, p, ctx->dFlags,
-                                                             ctx->dTmpContacts, ctx->dPairDist, ctx->dCtr);
+        const uint32_t tiles = (np + kGjkThreads - 1) / kGjkThreads;
+        CU(cudaMemsetAsync(ctx->dGjkStatus, 0, sizeof(uint32_t) * (tiles + 1), st));
+        NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow};
+        const uint64_t* pairs = ctx->dPairKeys[ctx->pairBuf];
+        gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, &ctx->dCtr->pairCount, ctx->cfg.maxPairs, ctx->idxBits,
+                                                 ctx->dXf, ctx->dShapes, ctx->dHull, p, ctx->dContacts,
+                                                 ctx->cfg.maxContacts, q, ctx->dPairDist, ctx->dGjkStatus, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_GJK);
-        const uint32_t tiles = (np + kScanTile - 1) / kScanTile;
-        CU(cudaMemsetAsync(ctx->dScanStatus, 0, sizeof(uint32_t) * tiles, st));
-        CU(cudaMemsetAsync(&ctx->dCtr->scanTicket, 0, sizeof(uint32_t), st));
-        exclusiveScanKernel<<<tiles, kScanThreads, 0, st>>>(ctx->dFlags, ctx->dOffsets, np, ctx->dScanStatus,
-                                                            &ctx->dCtr->scanTicket, ctx->dContactTotal);
-        compactContactsKernel<<<(np + 255) / 256, 256, 0, st>>>(ctx->dFlags, ctx->dOffsets, ctx->dTmpContacts, np,
-                                                                ctx->dContacts, ctx->cfg.maxContacts);
+        // EPA: persistent grids, queue lengths are read on the device
+        epaKernel<<<kNumSMs * 2, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->idxBits, ctx->dXf,
+                                                                   ctx->dShapes, ctx->dHull, p, ctx->dContacts,
+                                                                   ctx->dPairDist, ctx->dCtr);
+        epaFallbackKernel<<<kNumSMs, 64, 0, st>>>(q, pairs, ctx->idxBits, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+                                                  ctx->dContacts, ctx->dPairDist, ctx->dCtr);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(&ctx->dCtr->contactCount, ctx->dContactTotal, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     } else {
         recordEv(ctx, EV_GJK);
     }
@@ -498,7 +496,7 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
     }
     if (ctx->stage >= ST_NARROW) {
         out->gjkMs = evMs(ctx, EV_N0, EV_GJK);
-        out->epaMs = 0.0f;   // EPA runs inside the narrowphase kernel in this version
+        out->epaMs = evMs(ctx, EV_GJK, EV_END);
         out->narrowphaseTime = evMs(ctx, EV_N0, EV_END);
         out->totalMs = evMs(ctx, EV_START, EV_END);
     }

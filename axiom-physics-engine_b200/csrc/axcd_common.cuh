@@ -10,6 +10,12 @@ namespace axcd {
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
+// decoupled look-back status words: 2 flag bits + 30 value bits
+constexpr uint32_t kFlagAggregate = 1u << 30;
+constexpr uint32_t kFlagInclusive = 2u << 30;
+constexpr uint32_t kFlagMask = 3u << 30;
+constexpr uint32_t kValueMask = ~kFlagMask;
+
 // ---- float3 helpers.  Every expression is evaluated exactly as written (the library is built
 // -fmad=false), matching the reference's Vec3 operators (include/axiom/math/vec3.hpp:52-191). ----
 struct V3 {
@@ -75,8 +81,9 @@ struct Counters {
     uint32_t gjkFailures;
     uint32_t epaFailures;
     uint32_t sortTicket[8];  // dynamic tile tickets, one per radix pass
-    uint32_t scanTicket;
-    uint32_t pad[3];
+    uint32_t gjkTicket;      // dynamic tile ticket of the GJK kernel
+    uint32_t epaOverflow;    // EPA pairs that outgrew the shared-memory polytope caps
+    uint32_t pad[2];
 };
 
 }  // namespace axcd

@@ -89,14 +89,19 @@ __device__ __forceinline__ Core makeCore(const BodyPose& t, uint4 sh, const floa
     return k;
 }
 
-// Support point of a core in world-aligned direction d (any length).
-__device__ __forceinline__ V3 support(const Core& k, V3 d) {
+// Support point of a core in world-aligned direction d (any length).  `id` names the chosen
+// vertex (box: one sign bit per axis, hull: vertex index) so the point can be rebuilt later with
+// pointFromId instead of being stored; both produce the same floats (same operation sequence).
+__device__ __forceinline__ V3 support(const Core& k, V3 d, uint32_t& id) {
+    id = 0;
     if (k.kind == CORE_POINT) return k.c;
     if (k.kind == CORE_BOX) {
+        const bool n0 = !(dot3(d, k.e0) >= 0.0f), n1 = !(dot3(d, k.e1) >= 0.0f), n2 = !(dot3(d, k.e2) >= 0.0f);
+        id = (n0 ? 1u : 0u) | (n1 ? 2u : 0u) | (n2 ? 4u : 0u);
         V3 p = k.c;
-        p = p + ((dot3(d, k.e0) >= 0.0f) ? k.e0 : -k.e0);
-        p = p + ((dot3(d, k.e1) >= 0.0f) ? k.e1 : -k.e1);
-        p = p + ((dot3(d, k.e2) >= 0.0f) ? k.e2 : -k.e2);
+        p = p + (n0 ? -k.e0 : k.e0);
+        p = p + (n1 ? -k.e1 : k.e1);
+        p = p + (n2 ? -k.e2 : k.e2);
         return p;
     }
     // hull: local direction = scale * (R^T d); the first maximal vertex wins
@@ -109,15 +114,39 @@ __device__ __forceinline__ V3 support(const Core& k, V3 d) {
         if (di > bestDot) {
             bestDot = di;
             bv = v;
+            id = i;
         }
     }
     const V3 lv = mk3(bv.x * k.s.x, bv.y * k.s.y, bv.z * k.s.z);
     return ((k.e0 * lv.x + k.e1 * lv.y) + k.e2 * lv.z) + k.c;
 }
 
+__device__ __forceinline__ V3 pointFromId(const Core& k, uint32_t id) {
+    if (k.kind == CORE_POINT) return k.c;
+    if (k.kind == CORE_BOX) {
+        V3 p = k.c;
+        p = p + ((id & 1u) ? -k.e0 : k.e0);
+        p = p + ((id & 2u) ? -k.e1 : k.e1);
+        p = p + ((id & 4u) ? -k.e2 : k.e2);
+        return p;
+    }
+    const float4 bv = __ldg(k.verts + id);
+    const V3 lv = mk3(bv.x * k.s.x, bv.y * k.s.y, bv.z * k.s.z);
+    return ((k.e0 * lv.x + k.e1 * lv.y) + k.e2 * lv.z) + k.c;
+}
+
+// Point of the Minkowski difference A - B in direction d; id = idA | idB << 16.
+__device__ __forceinline__ V3 supportDiff(const Core& A, const Core& B, V3 d, uint32_t& id) {
+    uint32_t ia, ib;
+    const V3 a = support(A, d, ia);
+    const V3 b = support(B, -d, ib);
+    id = ia | (ib << 16);
+    return a - b;
+}
+
 struct Simplex {
-    V3 y[4];   // points of the Minkowski difference A - B
-    V3 a[4];   // matching support points on A
+    V3 y[4];          // points of the Minkowski difference A - B
+    uint32_t id[4];   // which vertex of A (low 16 bits) and of B (high 16 bits) made each point
     float lam[4];
     int n;
 };
@@ -241,7 +270,7 @@ __device__ __forceinline__ V3 solveSimplex(Simplex& s, bool& enclosed) {
     for (int i = 0; i < 4; ++i) {
         if (i < s.n && (mask & (1 << i))) {
             s.y[n] = s.y[i];
-            s.a[n] = s.a[i];
+            s.id[n] = s.id[i];
             s.lam[n] = l[i];
             ++n;
         }
@@ -265,8 +294,7 @@ __device__ __forceinline__ GjkResult gjk(const Core& A, const Core& B, const Nar
     r.status = 0;
     V3 d0 = B.c - A.c;
     if (dot3(d0, d0) < 1e-12f) d0 = mk3(1.0f, 0.0f, 0.0f);
-    s.a[0] = support(A, d0);
-    s.y[0] = s.a[0] - support(B, -d0);
+    s.y[0] = supportDiff(A, B, d0, s.id[0]);
     s.lam[0] = 1.0f;
     s.n = 1;
     V3 v = s.y[0];
@@ -282,8 +310,8 @@ __device__ __forceinline__ GjkResult gjk(const Core& A, const Core& B, const Nar
             r.status = AXCD_ERR_GJK_NO_CONVERGE;
             break;
         }
-        const V3 a = support(A, -v);
-        const V3 w = a - support(B, v);
+        uint32_t wid;
+        const V3 w = supportDiff(A, B, -v, wid);
         const float vw = dot3(v, w);
         if (!cfg.wantDistances && vw > 0.0f && vw * vw > vv * (marginSum * marginSum)) {
             r.exact = false;   // separating axis with a gap larger than the radii
@@ -294,7 +322,7 @@ __device__ __forceinline__ GjkResult gjk(const Core& A, const Core& B, const Nar
         for (int i = 0; i < s.n; ++i) dup = dup || same3(w, s.y[i]);
         if (dup) break;
         s.y[s.n] = w;
-        s.a[s.n] = a;
+        s.id[s.n] = wid;
         s.n++;
         bool enclosed;
         const V3 nv = solveSimplex(s, enclosed);
@@ -319,36 +347,58 @@ __device__ __forceinline__ GjkResult gjk(const Core& A, const Core& B, const Nar
 }
 
 // ---- EPA ------------------------------------------------------------------------------------------
-constexpr int kEpaMaxVerts = 40;
-constexpr int kEpaMaxFaces = 64;
+// The polytope lives in per-thread storage addressed as base[word * STRIDE]:
+//   STRIDE = block size  -> a column of shared memory (the same word of all threads is contiguous,
+//                           so uniform-index accesses are conflict-free)
+//   STRIDE = 1           -> a private array (fallback kernel with the full caps)
+// words: [0, 3V) vertex y;  [3V, 4V) vertex ids;  [4V, 4V+4F) face (n.x,n.y,n.z,d);
+//        [4V+4F, 4V+5F) face indices i0 | i1<<8 | i2<<16;  then E/2 words of packed horizon edges.
+constexpr int kEpaHardVerts = 40;   // full caps (fallback path) == the oracle's
+constexpr int kEpaHardFaces = 64;
+constexpr int kEpaFastVerts = 16;   // shared-memory fast path; overflow -> fallback kernel
+constexpr int kEpaFastFaces = 28;
+constexpr int kEpaFastEdges = 24;
 
-struct EpaFace {
-    V3 n;
-    float d;
-    uint8_t i0, i1, i2, alive;
-};
-struct EpaPolytope {
-    V3 y[kEpaMaxVerts];
-    V3 a[kEpaMaxVerts];
-    EpaFace f[kEpaMaxFaces];
-    int nv, nf;
+template <int MAXV, int MAXF, int MAXE, int STRIDE>
+struct Poly {
+    static constexpr int kWords = 4 * MAXV + 5 * MAXF + MAXE / 2;
+    float* base;
+    __device__ __forceinline__ float& w(int i) const { return base[i * STRIDE]; }
+    __device__ __forceinline__ V3 y(int i) const { return mk3(w(3 * i), w(3 * i + 1), w(3 * i + 2)); }
+    __device__ __forceinline__ void setY(int i, V3 v) const { w(3 * i) = v.x; w(3 * i + 1) = v.y; w(3 * i + 2) = v.z; }
+    __device__ __forceinline__ uint32_t id(int i) const { return __float_as_uint(w(3 * MAXV + i)); }
+    __device__ __forceinline__ void setId(int i, uint32_t v) const { w(3 * MAXV + i) = __uint_as_float(v); }
+    __device__ __forceinline__ V3 fn(int f) const { return mk3(w(4 * MAXV + 4 * f), w(4 * MAXV + 4 * f + 1), w(4 * MAXV + 4 * f + 2)); }
+    __device__ __forceinline__ float fd(int f) const { return w(4 * MAXV + 4 * f + 3); }
+    __device__ __forceinline__ void setPlane(int f, V3 n, float d) const {
+        w(4 * MAXV + 4 * f) = n.x; w(4 * MAXV + 4 * f + 1) = n.y; w(4 * MAXV + 4 * f + 2) = n.z; w(4 * MAXV + 4 * f + 3) = d;
+    }
+    __device__ __forceinline__ uint32_t fi(int f) const { return __float_as_uint(w(4 * MAXV + 4 * MAXF + f)); }
+    __device__ __forceinline__ void setFi(int f, uint32_t v) const { w(4 * MAXV + 4 * MAXF + f) = __uint_as_float(v); }
+    __device__ __forceinline__ uint32_t edge(int h) const {
+        const uint32_t p = __float_as_uint(w(4 * MAXV + 5 * MAXF + (h >> 1)));
+        return (h & 1) ? (p >> 16) : (p & 0xffffu);
+    }
+    __device__ __forceinline__ void setEdge(int h, uint32_t e) const {
+        float& r = w(4 * MAXV + 5 * MAXF + (h >> 1));
+        const uint32_t p = __float_as_uint(r);
+        r = __uint_as_float((h & 1) ? ((p & 0xffffu) | (e << 16)) : ((p & 0xffff0000u) | e));
+    }
 };
 
-__device__ __forceinline__ void epaSetFace(EpaPolytope& e, int slot, int i0, int i1, int i2) {
-    EpaFace& F = e.f[slot];
-    V3 n = cross3(e.y[i1] - e.y[i0], e.y[i2] - e.y[i0]);
+template <class P>
+__device__ __forceinline__ void epaSetFace(const P& e, int slot, int i0, int i1, int i2) {
+    const V3 p0 = e.y(i0);
+    V3 n = cross3(e.y(i1) - p0, e.y(i2) - p0);
     const float len2 = dot3(n, n);
-    F.alive = 1;
-    F.i0 = (uint8_t)i0; F.i1 = (uint8_t)i1; F.i2 = (uint8_t)i2;
+    e.setFi(slot, (uint32_t)i0 | ((uint32_t)i1 << 8) | ((uint32_t)i2 << 16));
     if (len2 <= 1e-30f) {   // zero-area face: never the closest, never visible
-        F.n = mk3(0.f, 0.f, 0.f);
-        F.d = FLT_MAX;
+        e.setPlane(slot, mk3(0.f, 0.f, 0.f), FLT_MAX);
         return;
     }
     const float inv = 1.0f / sqrtf(len2);
     n = n * inv;
-    F.n = n;
-    F.d = dot3(n, e.y[i0]);
+    e.setPlane(slot, n, dot3(n, p0));
 }
 
 struct EpaResult {
@@ -356,6 +406,7 @@ struct EpaResult {
     float depth;
     V3 pa, pb;
     uint32_t status;
+    bool overflow;   // fast-path caps exceeded: rerun with the full caps
 };
 
 __device__ __forceinline__ EpaResult epaTouching(V3 n, V3 pa) {
@@ -366,297 +417,440 @@ __device__ __forceinline__ EpaResult epaTouching(V3 n, V3 pa) {
     r.pa = pa;
     r.pb = pa;
     r.status = 0;
+    r.overflow = false;
     return r;
 }
 
-__device__ __noinline__ EpaResult epa(const Core& A, const Core& B, const NarrowParams& cfg, const Simplex& s0,
-                                      EpaPolytope& e) {
-    e.nv = s0.n;
-    for (int i = 0; i < s0.n; ++i) {
-        e.y[i] = s0.y[i];
-        e.a[i] = s0.a[i];
-    }
+// EPA from a GJK end simplex (n0 points y0[], ids id0[]).  MAXV/MAXF/MAXE are storage caps; the
+// algorithmic caps (cfg.epaMaxFaces, kEpaHardVerts, cfg.epaMaxIters) give status 302, while hitting
+// a smaller storage cap sets `overflow` and the caller reruns the pair on the full-cap path.
+template <int MAXV, int MAXF, int MAXE, int STRIDE>
+__device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const NarrowParams& cfg, int n0,
+                                            const V3* y0, const uint32_t* id0,
+                                            const Poly<MAXV, MAXF, MAXE, STRIDE>& e) {
+    int nv = n0;
+    for (int i = 0; i < 4; ++i)
+        if (i < n0) {
+            e.setY(i, y0[i]);
+            e.setId(i, id0[i]);
+        }
+    uint32_t tid_;
     // ---- grow the GJK simplex to a tetrahedron -------------------------------------------------
-    if (e.nv == 1) {
-        for (int k = 0; k < 6 && e.nv == 1; ++k) {
+    if (nv == 1) {
+        for (int k = 0; k < 6 && nv == 1; ++k) {
             const float sg = (k & 1) ? -1.0f : 1.0f;
             const V3 ax = mk3((k >> 1) == 0 ? sg : 0.f, (k >> 1) == 1 ? sg : 0.f, (k >> 1) == 2 ? sg : 0.f);
-            e.a[1] = support(A, ax);
-            e.y[1] = e.a[1] - support(B, -ax);
-            const V3 d = e.y[1] - e.y[0];
-            if (dot3(d, d) > kDegenerateEps) e.nv = 2;
+            const V3 y1 = supportDiff(A, B, ax, tid_);
+            e.setY(1, y1);
+            e.setId(1, tid_);
+            const V3 d = y1 - e.y(0);
+            if (dot3(d, d) > kDegenerateEps) nv = 2;
         }
-        if (e.nv == 1) return epaTouching(mk3(1.f, 0.f, 0.f), e.a[0]);
+        if (nv == 1) return epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu));
     }
-    if (e.nv == 2) {
-        const V3 d = e.y[1] - e.y[0];
+    if (nv == 2) {
+        const V3 d = e.y(1) - e.y(0);
         V3 firstDir = mk3(0.f, 0.f, 0.f);
-        for (int k = 0; k < 3 && e.nv == 2; ++k) {
+        for (int k = 0; k < 3 && nv == 2; ++k) {
             const V3 ax = mk3(k == 0 ? 1.f : 0.f, k == 1 ? 1.f : 0.f, k == 2 ? 1.f : 0.f);
             const V3 dir = cross3(d, ax);
             if (dot3(dir, dir) <= kDegenerateEps) continue;
             if (dot3(firstDir, firstDir) == 0.0f) firstDir = dir;
-            for (int sgn = 0; sgn < 2 && e.nv == 2; ++sgn) {
-                const V3 dd = sgn ? -dir : dir;
-                e.a[2] = support(A, dd);
-                e.y[2] = e.a[2] - support(B, -dd);
-                const V3 c = cross3(e.y[2] - e.y[0], d);
-                if (dot3(c, c) > kDegenerateEps) e.nv = 3;
+            for (int sgn = 0; sgn < 2 && nv == 2; ++sgn) {
+                const V3 y2 = supportDiff(A, B, sgn ? -dir : dir, tid_);
+                e.setY(2, y2);
+                e.setId(2, tid_);
+                const V3 c = cross3(y2 - e.y(0), d);
+                if (dot3(c, c) > kDegenerateEps) nv = 3;
             }
         }
-        if (e.nv == 2) return epaTouching(firstDir, e.a[0]);
+        if (nv == 2) return epaTouching(firstDir, pointFromId(A, e.id(0) & 0xffffu));
     }
-    if (e.nv == 3) {
-        const V3 n = cross3(e.y[1] - e.y[0], e.y[2] - e.y[0]);
+    if (nv == 3) {
+        const V3 n = cross3(e.y(1) - e.y(0), e.y(2) - e.y(0));
         const float n2 = dot3(n, n);
-        if (n2 <= 1e-30f) return epaTouching(mk3(1.f, 0.f, 0.f), e.a[0]);
-        for (int sgn = 0; sgn < 2 && e.nv == 3; ++sgn) {
-            const V3 dd = sgn ? -n : n;
-            e.a[3] = support(A, dd);
-            e.y[3] = e.a[3] - support(B, -dd);
-            const float vol = dot3(e.y[3] - e.y[0], n);
-            if (vol * vol > kDegenerateEps * n2) e.nv = 4;
+        if (n2 <= 1e-30f) return epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu));
+        for (int sgn = 0; sgn < 2 && nv == 3; ++sgn) {
+            const V3 y3 = supportDiff(A, B, sgn ? -n : n, tid_);
+            e.setY(3, y3);
+            e.setId(3, tid_);
+            const float vol = dot3(y3 - e.y(0), n);
+            if (vol * vol > kDegenerateEps * n2) nv = 4;
         }
-        if (e.nv == 3) {   // flat at the origin: touching contact along +n
+        if (nv == 3) {   // flat at the origin: touching contact along +n
             float la, lb, lc;
             int m;
-            closestTriangle(e.y[0], e.y[1], e.y[2], la, lb, lc, m);
-            const V3 pa = (e.a[0] * la + e.a[1] * lb) + e.a[2] * lc;
+            closestTriangle(e.y(0), e.y(1), e.y(2), la, lb, lc, m);
+            const V3 pa = (pointFromId(A, e.id(0) & 0xffffu) * la + pointFromId(A, e.id(1) & 0xffffu) * lb) +
+                          pointFromId(A, e.id(2) & 0xffffu) * lc;
             return epaTouching(n, pa);
         }
     }
     // orientation: make (0,1,2) face away from vertex 3
-    if (dot3(cross3(e.y[1] - e.y[0], e.y[2] - e.y[0]), e.y[3] - e.y[0]) > 0.0f) {
-        V3 t = e.y[0]; e.y[0] = e.y[1]; e.y[1] = t;
-        t = e.a[0]; e.a[0] = e.a[1]; e.a[1] = t;
+    if (dot3(cross3(e.y(1) - e.y(0), e.y(2) - e.y(0)), e.y(3) - e.y(0)) > 0.0f) {
+        const V3 t = e.y(0);
+        e.setY(0, e.y(1));
+        e.setY(1, t);
+        const uint32_t ti = e.id(0);
+        e.setId(0, e.id(1));
+        e.setId(1, ti);
     }
     epaSetFace(e, 0, 0, 1, 2);
     epaSetFace(e, 1, 0, 3, 1);
     epaSetFace(e, 2, 0, 2, 3);
     epaSetFace(e, 3, 1, 3, 2);
-    e.nf = 4;
-    const int maxFaces = (int)min(cfg.epaMaxFaces, (uint32_t)kEpaMaxFaces);
+    uint64_t alive = 0xfull;   // bit f set = face slot f is part of the polytope
+    const int maxFaces = (int)min(cfg.epaMaxFaces, (uint32_t)kEpaHardFaces);
 
     uint32_t status = 0;
+    bool overflow = false;
     int best = 0;
     for (uint32_t it = 0;; ++it) {
         best = -1;
         float bd = FLT_MAX;
-        for (int i = 0; i < e.nf; ++i) {
-            if (e.f[i].alive && e.f[i].d < bd) {
-                bd = e.f[i].d;
+        for (uint64_t m = alive; m; m &= m - 1) {
+            const int i = __ffsll((long long)m) - 1;
+            const float di = e.fd(i);
+            if (di < bd) {
+                bd = di;
                 best = i;
             }
         }
-        if (best < 0) return epaTouching(mk3(1.f, 0.f, 0.f), e.a[0]);
-        const V3 bn = e.f[best].n;
-        const float bdist = e.f[best].d;
-        const V3 a = support(A, bn);
-        const V3 w = a - support(B, -bn);
+        if (best < 0) return epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu));
+        const V3 bn = e.fn(best);
+        uint32_t wid;
+        const V3 w = supportDiff(A, B, bn, wid);
         const float dw = dot3(w, bn);
-        const float scale = (bdist > 1.0f) ? bdist : 1.0f;
-        if (dw - bdist <= cfg.epaTol * scale) break;
+        const float scale = (bd > 1.0f) ? bd : 1.0f;
+        if (dw - bd <= cfg.epaTol * scale) break;
         bool dup = false;
-        for (int i = 0; i < e.nv; ++i) dup = dup || same3(w, e.y[i]);
+        for (int i = 0; i < nv; ++i) dup = dup || same3(w, e.y(i));
         if (dup) break;
-        if (it >= cfg.epaMaxIters || e.nv >= kEpaMaxVerts) {
+        if (it >= cfg.epaMaxIters || nv >= kEpaHardVerts) {
             status = AXCD_ERR_EPA_NO_CONVERGE;
             break;
         }
-        // visible faces (w clearly in front) and the horizon edge loop
-        uint8_t he0[kEpaMaxFaces * 3], he1[kEpaMaxFaces * 3];
-        uint64_t visMask = 0;
-        int nh = 0, nvis = 0, nalive = 0;
+        // visible faces: w clearly in front
         const float wl = fabsf(w.x) + fabsf(w.y) + fabsf(w.z);
         const float visEps = 1e-6f * ((wl > 1.0f) ? wl : 1.0f);
-        for (int i = 0; i < e.nf; ++i) {
-            if (!e.f[i].alive) continue;
-            ++nalive;
-            if (dot3(e.f[i].n, w) - e.f[i].d > visEps) {
-                visMask |= 1ull << i;
-                ++nvis;
-            }
+        uint64_t vis = 0;
+        for (uint64_t m = alive; m; m &= m - 1) {
+            const int i = __ffsll((long long)m) - 1;
+            if (dot3(e.fn(i), w) - e.fd(i) > visEps) vis |= 1ull << i;
         }
-        for (int i = 0; i < e.nf; ++i) {
-            if (!((visMask >> i) & 1ull)) continue;
-            const uint8_t v0 = e.f[i].i0, v1 = e.f[i].i1, v2 = e.f[i].i2;
+        // horizon in canonical order: visible faces by ascending slot, edges in winding order, an
+        // edge is kept iff its reverse is not an edge of a visible face
+        int nh = 0;
+        uint64_t starts = 0, ends = 0;
+        bool loopOk = true, edgeOverflow = false;
+        for (uint64_t m = vis; m; m &= m - 1) {
+            const int f = __ffsll((long long)m) - 1;
+            const uint32_t fi = e.fi(f);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const uint8_t ea = (k == 0) ? v0 : ((k == 1) ? v1 : v2);
-                const uint8_t eb = (k == 0) ? v1 : ((k == 1) ? v2 : v0);
-                int found = -1;
-                for (int h = 0; h < nh; ++h)
-                    if (he0[h] == eb && he1[h] == ea) {
-                        found = h;
-                        break;
-                    }
-                if (found >= 0) {
-                    he0[found] = he0[nh - 1];
-                    he1[found] = he1[nh - 1];
-                    --nh;
-                } else {
-                    he0[nh] = ea;
-                    he1[nh] = eb;
-                    ++nh;
+                const uint32_t ea = (fi >> (8 * k)) & 0xffu;
+                const uint32_t eb = (fi >> (8 * ((k + 1) % 3))) & 0xffu;
+                const uint32_t rev = eb | (ea << 8);   // the reverse edge as (start | end << 8)
+                bool shared = false;
+                for (uint64_t m2 = vis; m2; m2 &= m2 - 1) {
+                    const int g = __ffsll((long long)m2) - 1;
+                    const uint32_t gi = e.fi(g);
+                    const uint32_t g01 = gi & 0xffffu, g12 = (gi >> 8) & 0xffffu,
+                                   g20 = ((gi >> 16) & 0xffu) | ((gi & 0xffu) << 8);
+                    shared = shared || g01 == rev || g12 == rev || g20 == rev;
                 }
+                if (shared) continue;
+                if (((starts >> ea) & 1ull) || ((ends >> eb) & 1ull)) loopOk = false;
+                starts |= 1ull << ea;
+                ends |= 1ull << eb;
+                if (nh < MAXE) e.setEdge(nh, ea | (eb << 8));
+                else edgeOverflow = true;
+                ++nh;
             }
         }
-        bool loopOk = nh >= 3;
-        for (int h = 0; h < nh && loopOk; ++h)
-            for (int g = h + 1; g < nh; ++g)
-                if (he0[g] == he0[h] || he1[g] == he1[h]) {
-                    loopOk = false;
-                    break;
-                }
+        if (nh < 3) loopOk = false;
+        const int nalive = __popcll(alive), nvis = __popcll(vis);
         if (!loopOk || nalive - nvis + nh > maxFaces) {
             status = AXCD_ERR_EPA_NO_CONVERGE;
             break;
         }
-        const int wi = e.nv;
-        e.y[wi] = w;
-        e.a[wi] = a;
-        e.nv++;
-        for (int i = 0; i < e.nf; ++i)
-            if ((visMask >> i) & 1ull) e.f[i].alive = 0;
-        int slot = 0;
+        if (edgeOverflow || nv >= MAXV || nalive - nvis + nh > MAXF) {   // storage caps of this path
+            overflow = true;
+            break;
+        }
+        const int wi = nv;
+        e.setY(wi, w);
+        e.setId(wi, wid);
+        nv++;
+        alive &= ~vis;
         for (int h = 0; h < nh; ++h) {
-            while (slot < e.nf && e.f[slot].alive) ++slot;
-            if (slot == e.nf) e.nf++;
-            epaSetFace(e, slot, he0[h], he1[h], wi);
+            const int slot = __ffsll((long long)~alive) - 1;   // lowest free slot
+            const uint32_t ed = e.edge(h);
+            epaSetFace(e, slot, (int)(ed & 0xffu), (int)(ed >> 8), wi);
+            alive |= 1ull << slot;
         }
     }
-    const EpaFace fb = e.f[best];
     EpaResult r;
-    r.n = fb.n;
-    r.depth = (fb.d > 0.0f) ? fb.d : 0.0f;
+    r.overflow = overflow;
+    r.status = status;
+    if (overflow) {
+        r.n = mk3(1.f, 0.f, 0.f);
+        r.depth = 0.f;
+        r.pa = r.pb = mk3(0.f, 0.f, 0.f);
+        return r;
+    }
+    const uint32_t fi = e.fi(best);
+    const int i0 = fi & 0xffu, i1 = (fi >> 8) & 0xffu, i2 = (fi >> 16) & 0xffu;
+    const float fdist = e.fd(best);
+    r.n = e.fn(best);
+    r.depth = (fdist > 0.0f) ? fdist : 0.0f;
     float la, lb, lc;
     int m;
-    const V3 p = closestTriangle(e.y[fb.i0], e.y[fb.i1], e.y[fb.i2], la, lb, lc, m);
-    r.pa = (e.a[fb.i0] * la + e.a[fb.i1] * lb) + e.a[fb.i2] * lc;
+    const V3 p = closestTriangle(e.y(i0), e.y(i1), e.y(i2), la, lb, lc, m);
+    r.pa = (pointFromId(A, e.id(i0) & 0xffffu) * la + pointFromId(A, e.id(i1) & 0xffffu) * lb) +
+           pointFromId(A, e.id(i2) & 0xffffu) * lc;
     r.pb = r.pa - p;
-    r.status = status;
     return r;
 }
 
-// ---- one pair -------------------------------------------------------------------------------------
-struct PairResult {
-    bool contact;
-    bool usedEpa;
-    float dist;
-    AxcdContact c;
+// ---- contact record helpers ----------------------------------------------------------------------
+__device__ __forceinline__ void storeContact(AxcdContact* __restrict__ dst, uint32_t a, uint32_t b, V3 pos, V3 n,
+                                             float depth, uint32_t status) {
+    float2* o = reinterpret_cast<float2*>(dst);   // 40-byte record, 8-byte aligned
+    o[0] = make_float2(__uint_as_float(a), __uint_as_float(b));
+    o[1] = make_float2(pos.x, pos.y);
+    o[2] = make_float2(pos.z, n.x);
+    o[3] = make_float2(n.y, n.z);
+    o[4] = make_float2(depth, __uint_as_float(status));
+}
+
+// GJK -> EPA hand-off record (80 bytes, 16-byte aligned)
+struct __align__(16) EpaWork {
+    uint32_t pair, slot, n, pad;   // pair index, destination contact slot, simplex size (bit 31: GJK status 301)
+    float y[12];              // simplex points
+    uint32_t id[4];           // simplex vertex ids
+};
+static_assert(sizeof(EpaWork) == 80, "EpaWork must be 80 bytes");
+
+struct NarrowQueues {
+    EpaWork* work;        // capacity maxContacts
+    uint32_t* overflow;   // indices into work[] that need the full-cap path
 };
 
-__device__ __forceinline__ PairResult collidePair(uint32_t ia, uint32_t ib, const float* __restrict__ xf,
-                                                  const uint4* __restrict__ shapes,
-                                                  const float4* __restrict__ hull, const NarrowParams& cfg,
-                                                  EpaPolytope& scratch) {
-    PairResult o;
-    o.contact = false;
-    o.usedEpa = false;
-    o.dist = 0.0f;
-    o.c.a = ia;
-    o.c.b = ib;
+// ---- kernel 1: GJK over every candidate pair -------------------------------------------------------
+constexpr int kGjkThreads = 256;
+
+// One thread per (a,b)-sorted candidate pair.  Separated pairs write nothing; shallow contacts
+// (cores apart, spheres' radii overlapping) write their record; overlapping cores reserve their
+// contact slot and queue an EpaWork item.  Contact slots follow pair order: block-wide scan of the
+// contact flags + decoupled look-back across blocks (ticketed tiles).
+__global__ void __launch_bounds__(kGjkThreads, 2)
+gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
+          int idxBits, const float* __restrict__ xf, const uint4* __restrict__ shapes,
+          const float4* __restrict__ hull, NarrowParams cfg, AxcdContact* __restrict__ contacts,
+          uint32_t maxContacts, NarrowQueues q, float* __restrict__ pairDist,
+          volatile uint32_t* __restrict__ tileStatus, Counters* __restrict__ ctr) {
+    __shared__ uint32_t sWarp[kGjkThreads / 32];
+    __shared__ uint32_t sTile, sBase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(&ctr->gjkTicket, 1u);
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t npairs = min(*pairCount, maxPairs);
+    const uint32_t k = tile * kGjkThreads + tid;
+
+    // ---- per-pair GJK ----------------------------------------------------------------------------
+    int kind = 0;   // 0 none, 1 shallow contact, 2 needs EPA
+    uint32_t ia = 0, ib = 0, status = 0;
+    V3 n = mk3(0.f, 0.f, 0.f), pos = n;
+    float depth = 0.f;
+    Simplex s;
+    s.n = 0;
+    if (k < npairs) {
+        const uint64_t pk = pairs[k];
+        ia = (uint32_t)(pk >> idxBits);
+        ib = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
+        const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
+        const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
+        const V3 origin = ta.p;
+        float dist = 0.f;
+        if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_SPHERE) {
+            const float ra = __uint_as_float(sa.y), rb = __uint_as_float(sb.y);
+            const V3 d = tb.p - origin;
+            const float len = sqrtf(dot3(d, d));
+            const float rs = ra + rb;
+            depth = rs - len;
+            dist = len - rs;
+            if (depth >= 0.0f) {
+                kind = 1;
+                n = (len > 0.0f) ? d * (1.0f / len) : mk3(1.0f, 0.0f, 0.0f);
+                const V3 pa = n * ra;
+                const V3 pb = d - n * rb;
+                pos = (pa + pb) * 0.5f + origin;
+            }
+        } else {
+            const Core A = makeCore(ta, sa, hull, origin);
+            const Core B = makeCore(tb, sb, hull, origin);
+            const float rs = A.r + B.r;
+            const GjkResult g = gjk(A, B, cfg, rs, s);
+            status = g.status;
+            if (g.state == GJK_SEPARATED) {
+                const float len = sqrtf(g.vv);
+                dist = len - rs;
+                if (g.exact) {
+                    depth = rs - len;
+                    if (depth >= 0.0f) {
+                        kind = 1;
+                        n = -(g.v * (1.0f / len));
+                        V3 ca = mk3(0.f, 0.f, 0.f);
+                        for (int i = 0; i < s.n; ++i) ca = ca + pointFromId(A, s.id[i] & 0xffffu) * s.lam[i];
+                        const V3 pa = ca + n * A.r;
+                        const V3 pb = (ca - g.v) - n * B.r;
+                        pos = (pa + pb) * 0.5f + origin;
+                    }
+                }
+            } else {
+                kind = 2;
+            }
+        }
+        if (pairDist) pairDist[k] = (kind == 1) ? ((dist < 0.0f) ? dist : 0.0f) : dist;   // kind 2: EPA overwrites
+    }
+
+    // ---- contact slots in pair order -----------------------------------------------------------------
+    const uint32_t bal = __ballot_sync(0xffffffffu, kind != 0);
+    const uint32_t lanePrefix = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) sWarp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t warpPrefix = 0, tileTotal = 0;
+#pragma unroll
+    for (int i = 0; i < kGjkThreads / 32; ++i) {
+        warpPrefix += (i < warp) ? sWarp[i] : 0u;
+        tileTotal += sWarp[i];
+    }
+    if (warp == 0) {
+        // warp-parallel decoupled look-back
+        uint32_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) tileStatus[0] = kFlagInclusive | tileTotal;
+        } else {
+            if (lane == 0) tileStatus[tile] = kFlagAggregate | tileTotal;
+            int t = (int)tile - 1;
+            while (true) {
+                const int idx = t - lane;
+                uint32_t sv = kFlagInclusive;   // lanes before tile 0 act as an inclusive zero
+                if (idx >= 0) {
+                    do { sv = tileStatus[idx]; } while ((sv & kFlagMask) == 0);
+                }
+                const uint32_t incMask = __ballot_sync(0xffffffffu, (sv & kFlagMask) == kFlagInclusive);
+                const int firstInc = incMask ? (__ffs(incMask) - 1) : 32;
+                uint32_t v = (lane <= firstInc) ? (sv & kValueMask) : 0u;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                excl += v;
+                if (incMask) break;
+                t -= 32;
+            }
+            if (lane == 0) tileStatus[tile] = kFlagInclusive | (excl + tileTotal);
+        }
+        if (lane == 0) {
+            sBase = excl;
+            if ((uint64_t)(tile + 1) * kGjkThreads >= npairs) ctr->contactCount = excl + tileTotal;   // last tile
+        }
+    }
+    __syncthreads();
+    if (kind == 0) return;
+    const uint32_t slot = sBase + warpPrefix + lanePrefix;
+    if (slot >= maxContacts) return;
+    if (kind == 1) {
+        storeContact(contacts + slot, ia, ib, pos, n, depth, status);
+        if (status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
+    } else {
+        const uint32_t wq = atomicAdd(&ctr->epaCount, 1u);
+        EpaWork* wk = q.work + wq;
+        uint4* o = reinterpret_cast<uint4*>(wk);
+        o[0] = make_uint4(k, slot, (uint32_t)s.n | (status ? 0x80000000u : 0u), 0u);
+        float4* of = reinterpret_cast<float4*>(wk) + 1;
+        of[0] = make_float4(s.y[0].x, s.y[0].y, s.y[0].z, s.y[1].x);
+        of[1] = make_float4(s.y[1].y, s.y[1].z, s.y[2].x, s.y[2].y);
+        of[2] = make_float4(s.y[2].z, s.y[3].x, s.y[3].y, s.y[3].z);
+        o[4] = make_uint4(s.id[0], s.id[1], s.id[2], s.id[3]);
+    }
+}
+
+// ---- kernel 2: EPA over the queued pairs -------------------------------------------------------------
+constexpr int kEpaThreads = 128;
+constexpr int kEpaSmemBytes =
+    Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, kEpaThreads>::kWords * kEpaThreads * (int)sizeof(float);
+
+template <int MAXV, int MAXF, int MAXE, int STRIDE>
+__device__ __forceinline__ bool epaOne(const EpaWork* __restrict__ wk, const uint64_t* __restrict__ pairs, int idxBits,
+                                       const float* __restrict__ xf, const uint4* __restrict__ shapes,
+                                       const float4* __restrict__ hull, const NarrowParams& cfg,
+                                       AxcdContact* __restrict__ contacts, float* __restrict__ pairDist,
+                                       Counters* __restrict__ ctr, const Poly<MAXV, MAXF, MAXE, STRIDE>& poly) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(wk));
+    const float4 f0 = __ldg(reinterpret_cast<const float4*>(wk) + 1), f1 = __ldg(reinterpret_cast<const float4*>(wk) + 2),
+                 f2 = __ldg(reinterpret_cast<const float4*>(wk) + 3);
+    const uint4 idv = __ldg(reinterpret_cast<const uint4*>(wk) + 4);
+    const uint32_t pairIdx = h.x, slot = h.y;
+    const uint64_t pk = __ldg(pairs + pairIdx);
+    const uint32_t ia = (uint32_t)(pk >> idxBits), ib = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
+    const int n0 = (int)(h.z & 0xffu);
+    uint32_t status = (h.z & 0x80000000u) ? (uint32_t)AXCD_ERR_GJK_NO_CONVERGE : 0u;
+    const V3 y0[4] = {mk3(f0.x, f0.y, f0.z), mk3(f0.w, f1.x, f1.y), mk3(f1.z, f1.w, f2.x), mk3(f2.y, f2.z, f2.w)};
+    const uint32_t id0[4] = {idv.x, idv.y, idv.z, idv.w};
     const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
     const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
     const V3 origin = ta.p;
-    V3 n, pa, pb;
-    float depth;
-    uint32_t status = 0;
-    if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_SPHERE) {
-        const float ra = __uint_as_float(sa.y), rb = __uint_as_float(sb.y);
-        const V3 d = tb.p - origin;
-        const float dist = sqrtf(dot3(d, d));
-        const float rs = ra + rb;
-        depth = rs - dist;
-        o.dist = dist - rs;
-        if (!(depth >= 0.0f)) return o;
-        n = (dist > 0.0f) ? d * (1.0f / dist) : mk3(1.0f, 0.0f, 0.0f);
-        pa = n * ra;
-        pb = d - n * rb;
-    } else {
-        const Core A = makeCore(ta, sa, hull, origin);
-        const Core B = makeCore(tb, sb, hull, origin);
-        const float rs = A.r + B.r;
-        Simplex s;
-        const GjkResult g = gjk(A, B, cfg, rs, s);
-        status = g.status;
-        if (g.state == GJK_SEPARATED) {
-            const float dist = sqrtf(g.vv);
-            if (!g.exact) {
-                o.dist = dist - rs;
-                return o;
-            }
-            depth = rs - dist;
-            o.dist = dist - rs;
-            if (!(depth >= 0.0f)) return o;
-            n = -(g.v * (1.0f / dist));
-            V3 ca = mk3(0.f, 0.f, 0.f);
-            for (int i = 0; i < s.n; ++i) ca = ca + s.a[i] * s.lam[i];
-            pa = ca + n * A.r;
-            pb = (ca - g.v) - n * B.r;
-        } else {
-            const EpaResult e = epa(A, B, cfg, s, scratch);
-            o.usedEpa = true;
-            if (e.status) status = e.status;
-            n = e.n;
-            depth = e.depth + rs;
-            o.dist = -depth;
-            pa = e.pa + n * A.r;
-            pb = e.pb - n * B.r;
+    const Core A = makeCore(ta, sa, hull, origin);
+    const Core B = makeCore(tb, sb, hull, origin);
+    const EpaResult r = epaRun<MAXV, MAXF, MAXE, STRIDE>(A, B, cfg, n0, y0, id0, poly);
+    if (r.overflow) return false;
+    if (r.status) status = r.status;
+    const float rs = A.r + B.r;
+    const float depth = r.depth + rs;
+    const V3 pa = r.pa + r.n * A.r;
+    const V3 pb = r.pb - r.n * B.r;
+    const V3 pos = (pa + pb) * 0.5f + origin;
+    storeContact(contacts + slot, ia, ib, pos, r.n, depth, status);
+    if (pairDist) pairDist[pairIdx] = (depth > 0.0f) ? -depth : 0.0f;
+    if (status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
+    if (status == AXCD_ERR_EPA_NO_CONVERGE) atomicAdd(&ctr->epaFailures, 1u);
+    return true;
+}
+
+// Fast path: polytope in shared memory (one column per thread), persistent grid-stride over the
+// queue (its length is only known on the device).
+__global__ void __launch_bounds__(kEpaThreads)
+epaKernel(NarrowQueues q, uint32_t maxContacts, const uint64_t* __restrict__ pairs, int idxBits,
+          const float* __restrict__ xf, const uint4* __restrict__ shapes, const float4* __restrict__ hull,
+          NarrowParams cfg, AxcdContact* __restrict__ contacts, float* __restrict__ pairDist,
+          Counters* __restrict__ ctr) {
+    extern __shared__ float sPoly[];
+    using P = Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, kEpaThreads>;
+    P poly;
+    poly.base = sPoly + threadIdx.x;
+    const uint32_t count = min(ctr->epaCount, maxContacts);
+    for (uint32_t i = blockIdx.x * kEpaThreads + threadIdx.x; i < count; i += gridDim.x * kEpaThreads) {
+        if (!epaOne(q.work + i, pairs, idxBits, xf, shapes, hull, cfg, contacts, pairDist, ctr, poly)) {
+            const uint32_t o = atomicAdd(&ctr->epaOverflow, 1u);
+            q.overflow[o] = i;
         }
     }
-    o.contact = true;
-    const V3 mid = (pa + pb) * 0.5f + origin;
-    o.c.px = mid.x; o.c.py = mid.y; o.c.pz = mid.z;
-    o.c.nx = n.x; o.c.ny = n.y; o.c.nz = n.z;
-    o.c.depth = depth;
-    o.c.status = status;
-    return o;
 }
 
-// ---- kernels --------------------------------------------------------------------------------------
-constexpr int kNarrowThreads = 128;
-
-// One thread per candidate pair (pairs are (a,b)-sorted).  Writes flag[k] (1 = contact) and the
-// contact record into tmp[k]; a scan + compaction pass then packs contacts in pair order.
-__global__ void __launch_bounds__(kNarrowThreads)
-narrowphaseKernel(const uint64_t* __restrict__ pairs, uint32_t npairs, int idxBits,
-                  const float* __restrict__ xf, const uint4* __restrict__ shapes,
-                  const float4* __restrict__ hull, NarrowParams cfg, uint32_t* __restrict__ flags,
-                  AxcdContact* __restrict__ tmp, float* __restrict__ pairDist, Counters* __restrict__ ctr) {
-    const uint32_t k = blockIdx.x * kNarrowThreads + threadIdx.x;
-    if (k >= npairs) return;
-    const uint64_t pk = pairs[k];
-    const uint32_t a = (uint32_t)(pk >> idxBits), b = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
-    EpaPolytope scratch;
-    const PairResult r = collidePair(a, b, xf, shapes, hull, cfg, scratch);
-    flags[k] = r.contact ? 1u : 0u;
-    if (pairDist) pairDist[k] = r.contact ? ((r.dist < 0.0f) ? r.dist : 0.0f) : r.dist;
-    if (r.contact) {
-        // 40-byte record, 8-byte aligned
-        float2* o = reinterpret_cast<float2*>(tmp + k);
-        o[0] = make_float2(__uint_as_float(r.c.a), __uint_as_float(r.c.b));
-        o[1] = make_float2(r.c.px, r.c.py);
-        o[2] = make_float2(r.c.pz, r.c.nx);
-        o[3] = make_float2(r.c.ny, r.c.nz);
-        o[4] = make_float2(r.c.depth, __uint_as_float(r.c.status));
-        if (r.usedEpa) atomicAdd(&ctr->epaCount, 1u);
-        if (r.c.status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
-        if (r.c.status == AXCD_ERR_EPA_NO_CONVERGE) atomicAdd(&ctr->epaFailures, 1u);
-    }
-}
-
-__global__ void compactContactsKernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ offsets,
-                                      const AxcdContact* __restrict__ tmp, uint32_t npairs,
-                                      AxcdContact* __restrict__ out, uint32_t maxContacts) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= npairs || !flags[k]) return;
-    const uint32_t dst = offsets[k];
-    if (dst >= maxContacts) return;
-    const float2* s = reinterpret_cast<const float2*>(tmp + k);
-    float2* o = reinterpret_cast<float2*>(out + dst);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) o[i] = s[i];
+// Full-cap path for the few pairs whose polytope outgrew the shared-memory caps.
+__global__ void __launch_bounds__(64)
+epaFallbackKernel(NarrowQueues q, const uint64_t* __restrict__ pairs, int idxBits, const float* __restrict__ xf,
+                  const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
+                  AxcdContact* __restrict__ contacts, float* __restrict__ pairDist, Counters* __restrict__ ctr) {
+    using P = Poly<kEpaHardVerts, kEpaHardFaces, kEpaHardFaces * 3, 1>;
+    float store[P::kWords];
+    P poly;
+    poly.base = store;
+    const uint32_t count = ctr->epaOverflow;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        epaOne(q.work + q.overflow[i], pairs, idxBits, xf, shapes, hull, cfg, contacts, pairDist, ctr, poly);
 }
 
 }  // namespace axcd

@@ -17,10 +17,6 @@ constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kRadix = 256;
 constexpr int kMaxPasses = 8;
 
-constexpr uint32_t kFlagAggregate = 1u << 30;
-constexpr uint32_t kFlagInclusive = 2u << 30;
-constexpr uint32_t kFlagMask = 3u << 30;
-constexpr uint32_t kValueMask = ~kFlagMask;
 
 template <typename K>
 __device__ __forceinline__ uint32_t digitOf(K key, int shift) {

@@ -642,26 +642,25 @@ EpaResult epa(const Core& A, const Core& B, const AxrefNarrowCfg& cfg, const Sim
                 ++nvis;
             }
         }
+        // Horizon, in canonical order: visible faces by ascending slot, their edges in winding
+        // order, keeping a directed edge only if its reverse does not belong to a visible face.
+        uint64_t visEdge[EPA_MAX_VERTS];
+        for (int i = 0; i < e.nv; ++i) visEdge[i] = 0;
+        for (int i = 0; i < e.nf; ++i) {
+            if (!vis[i]) continue;
+            visEdge[e.f[i].i0] |= 1ull << e.f[i].i1;
+            visEdge[e.f[i].i1] |= 1ull << e.f[i].i2;
+            visEdge[e.f[i].i2] |= 1ull << e.f[i].i0;
+        }
         for (int i = 0; i < e.nf; ++i) {
             if (!vis[i]) continue;
             const uint8_t ev[3][2] = {{e.f[i].i0, e.f[i].i1}, {e.f[i].i1, e.f[i].i2},
                                       {e.f[i].i2, e.f[i].i0}};
             for (int k = 0; k < 3; ++k) {
-                int found = -1;
-                for (int h = 0; h < nh; ++h)
-                    if (he0[h] == ev[k][1] && he1[h] == ev[k][0]) {
-                        found = h;
-                        break;
-                    }
-                if (found >= 0) {
-                    he0[found] = he0[nh - 1];
-                    he1[found] = he1[nh - 1];
-                    --nh;
-                } else {
-                    he0[nh] = ev[k][0];
-                    he1[nh] = ev[k][1];
-                    ++nh;
-                }
+                if ((visEdge[ev[k][1]] >> ev[k][0]) & 1ull) continue;   // shared by two visible faces
+                he0[nh] = ev[k][0];
+                he1[nh] = ev[k][1];
+                ++nh;
             }
         }
         // the horizon must be a simple loop: every vertex starts exactly one edge

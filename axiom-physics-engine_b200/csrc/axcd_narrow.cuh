@@ -359,30 +359,58 @@ constexpr int kEpaFastVerts = 16;   // shared-memory fast path; overflow -> fall
 constexpr int kEpaFastFaces = 28;
 constexpr int kEpaFastEdges = 24;
 
+template <int MAXF> struct FaceMask { using T = uint64_t; };
+template <> struct FaceMask<28> { using T = uint32_t; };
+__device__ __forceinline__ int lowestBit(uint32_t m) { return __ffs((int)m) - 1; }
+__device__ __forceinline__ int lowestBit(uint64_t m) { return __ffsll((long long)m) - 1; }
+__device__ __forceinline__ int popCount(uint32_t m) { return __popc(m); }
+__device__ __forceinline__ int popCount(uint64_t m) { return __popcll(m); }
+
 template <int MAXV, int MAXF, int MAXE, int STRIDE>
 struct Poly {
-    static constexpr int kWords = 4 * MAXV + 5 * MAXF + MAXE / 2;
+    using Mask = typename FaceMask<MAXF>::T;
+    // per-vertex row of "visible directed edge a->b" bits: 16-bit rows (two per word) when
+    // MAXV <= 16, else 64-bit rows (two words)
+    static constexpr bool kSmallRows = MAXV <= 16;
+    static constexpr int kRowWords = kSmallRows ? (MAXV + 1) / 2 : 2 * MAXV;
+    static constexpr int kRowBase = 4 * MAXV + 5 * MAXF + MAXE / 2;
+    static constexpr int kWords = kRowBase + kRowWords;
     float* base;
     __device__ __forceinline__ float& w(int i) const { return base[i * STRIDE]; }
+    __device__ __forceinline__ uint32_t& u(int i) const { return reinterpret_cast<uint32_t*>(base)[i * STRIDE]; }
     __device__ __forceinline__ V3 y(int i) const { return mk3(w(3 * i), w(3 * i + 1), w(3 * i + 2)); }
     __device__ __forceinline__ void setY(int i, V3 v) const { w(3 * i) = v.x; w(3 * i + 1) = v.y; w(3 * i + 2) = v.z; }
-    __device__ __forceinline__ uint32_t id(int i) const { return __float_as_uint(w(3 * MAXV + i)); }
-    __device__ __forceinline__ void setId(int i, uint32_t v) const { w(3 * MAXV + i) = __uint_as_float(v); }
+    __device__ __forceinline__ uint32_t id(int i) const { return u(3 * MAXV + i); }
+    __device__ __forceinline__ void setId(int i, uint32_t v) const { u(3 * MAXV + i) = v; }
     __device__ __forceinline__ V3 fn(int f) const { return mk3(w(4 * MAXV + 4 * f), w(4 * MAXV + 4 * f + 1), w(4 * MAXV + 4 * f + 2)); }
     __device__ __forceinline__ float fd(int f) const { return w(4 * MAXV + 4 * f + 3); }
     __device__ __forceinline__ void setPlane(int f, V3 n, float d) const {
         w(4 * MAXV + 4 * f) = n.x; w(4 * MAXV + 4 * f + 1) = n.y; w(4 * MAXV + 4 * f + 2) = n.z; w(4 * MAXV + 4 * f + 3) = d;
     }
-    __device__ __forceinline__ uint32_t fi(int f) const { return __float_as_uint(w(4 * MAXV + 4 * MAXF + f)); }
-    __device__ __forceinline__ void setFi(int f, uint32_t v) const { w(4 * MAXV + 4 * MAXF + f) = __uint_as_float(v); }
+    __device__ __forceinline__ uint32_t fi(int f) const { return u(4 * MAXV + 4 * MAXF + f); }
+    __device__ __forceinline__ void setFi(int f, uint32_t v) const { u(4 * MAXV + 4 * MAXF + f) = v; }
     __device__ __forceinline__ uint32_t edge(int h) const {
-        const uint32_t p = __float_as_uint(w(4 * MAXV + 5 * MAXF + (h >> 1)));
+        const uint32_t p = u(4 * MAXV + 5 * MAXF + (h >> 1));
         return (h & 1) ? (p >> 16) : (p & 0xffffu);
     }
     __device__ __forceinline__ void setEdge(int h, uint32_t e) const {
-        float& r = w(4 * MAXV + 5 * MAXF + (h >> 1));
-        const uint32_t p = __float_as_uint(r);
-        r = __uint_as_float((h & 1) ? ((p & 0xffffu) | (e << 16)) : ((p & 0xffff0000u) | e));
+        uint32_t& r = u(4 * MAXV + 5 * MAXF + (h >> 1));
+        r = (h & 1) ? ((r & 0xffffu) | (e << 16)) : ((r & 0xffff0000u) | e);
+    }
+    __device__ __forceinline__ void clearRows(int nv) const {
+        if (kSmallRows) {
+            for (int i = 0; i < (nv + 1) / 2; ++i) u(kRowBase + i) = 0u;
+        } else {
+            for (int i = 0; i < 2 * nv; ++i) u(kRowBase + i) = 0u;
+        }
+    }
+    __device__ __forceinline__ void setEdgeBit(uint32_t a, uint32_t b) const {
+        if (kSmallRows) u(kRowBase + (a >> 1)) |= 1u << (b + 16 * (a & 1));
+        else u(kRowBase + 2 * a + (b >> 5)) |= 1u << (b & 31);
+    }
+    __device__ __forceinline__ bool edgeBit(uint32_t a, uint32_t b) const {
+        if (kSmallRows) return (u(kRowBase + (a >> 1)) >> (b + 16 * (a & 1))) & 1u;
+        return (u(kRowBase + 2 * a + (b >> 5)) >> (b & 31)) & 1u;
     }
 };
 
@@ -499,7 +527,10 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
     epaSetFace(e, 1, 0, 3, 1);
     epaSetFace(e, 2, 0, 2, 3);
     epaSetFace(e, 3, 1, 3, 2);
-    uint64_t alive = 0xfull;   // bit f set = face slot f is part of the polytope
+    using Mask = typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask;
+    const Mask one = 1;
+    Mask alive = 0xf;   // bit f set = face slot f is part of the polytope
+    int nf = 4;         // slots in use (alive or not)
     const int maxFaces = (int)min(cfg.epaMaxFaces, (uint32_t)kEpaHardFaces);
 
     uint32_t status = 0;
@@ -508,10 +539,9 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
     for (uint32_t it = 0;; ++it) {
         best = -1;
         float bd = FLT_MAX;
-        for (uint64_t m = alive; m; m &= m - 1) {
-            const int i = __ffsll((long long)m) - 1;
+        for (int i = 0; i < nf; ++i) {
             const float di = e.fd(i);
-            if (di < bd) {
+            if (((alive >> i) & one) && di < bd) {
                 bd = di;
                 best = i;
             }
@@ -533,33 +563,32 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
         // visible faces: w clearly in front
         const float wl = fabsf(w.x) + fabsf(w.y) + fabsf(w.z);
         const float visEps = 1e-6f * ((wl > 1.0f) ? wl : 1.0f);
-        uint64_t vis = 0;
-        for (uint64_t m = alive; m; m &= m - 1) {
-            const int i = __ffsll((long long)m) - 1;
-            if (dot3(e.fn(i), w) - e.fd(i) > visEps) vis |= 1ull << i;
+        Mask vis = 0;
+        for (int i = 0; i < nf; ++i) {
+            const bool v = dot3(e.fn(i), w) - e.fd(i) > visEps;
+            if (v && ((alive >> i) & one)) vis |= one << i;
+        }
+        // directed edges of the visible faces, as one bit row per start vertex
+        e.clearRows(nv);
+        for (Mask m = vis; m; m &= m - 1) {
+            const uint32_t fi = e.fi(lowestBit(m));
+            const uint32_t v0 = fi & 0xffu, v1 = (fi >> 8) & 0xffu, v2 = (fi >> 16) & 0xffu;
+            e.setEdgeBit(v0, v1);
+            e.setEdgeBit(v1, v2);
+            e.setEdgeBit(v2, v0);
         }
         // horizon in canonical order: visible faces by ascending slot, edges in winding order, an
         // edge is kept iff its reverse is not an edge of a visible face
         int nh = 0;
         uint64_t starts = 0, ends = 0;
         bool loopOk = true, edgeOverflow = false;
-        for (uint64_t m = vis; m; m &= m - 1) {
-            const int f = __ffsll((long long)m) - 1;
-            const uint32_t fi = e.fi(f);
+        for (Mask m = vis; m; m &= m - 1) {
+            const uint32_t fi = e.fi(lowestBit(m));
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const uint32_t ea = (fi >> (8 * k)) & 0xffu;
                 const uint32_t eb = (fi >> (8 * ((k + 1) % 3))) & 0xffu;
-                const uint32_t rev = eb | (ea << 8);   // the reverse edge as (start | end << 8)
-                bool shared = false;
-                for (uint64_t m2 = vis; m2; m2 &= m2 - 1) {
-                    const int g = __ffsll((long long)m2) - 1;
-                    const uint32_t gi = e.fi(g);
-                    const uint32_t g01 = gi & 0xffffu, g12 = (gi >> 8) & 0xffffu,
-                                   g20 = ((gi >> 16) & 0xffu) | ((gi & 0xffu) << 8);
-                    shared = shared || g01 == rev || g12 == rev || g20 == rev;
-                }
-                if (shared) continue;
+                if (e.edgeBit(eb, ea)) continue;   // shared by two visible faces
                 if (((starts >> ea) & 1ull) || ((ends >> eb) & 1ull)) loopOk = false;
                 starts |= 1ull << ea;
                 ends |= 1ull << eb;
@@ -569,7 +598,7 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
             }
         }
         if (nh < 3) loopOk = false;
-        const int nalive = __popcll(alive), nvis = __popcll(vis);
+        const int nalive = popCount(alive), nvis = popCount(vis);
         if (!loopOk || nalive - nvis + nh > maxFaces) {
             status = AXCD_ERR_EPA_NO_CONVERGE;
             break;
@@ -584,10 +613,11 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
         nv++;
         alive &= ~vis;
         for (int h = 0; h < nh; ++h) {
-            const int slot = __ffsll((long long)~alive) - 1;   // lowest free slot
+            const int slot = lowestBit((Mask)~alive);   // lowest free slot
             const uint32_t ed = e.edge(h);
             epaSetFace(e, slot, (int)(ed & 0xffu), (int)(ed >> 8), wi);
-            alive |= 1ull << slot;
+            alive |= one << slot;
+            nf = max(nf, slot + 1);
         }
     }
     EpaResult r;
@@ -639,17 +669,59 @@ struct NarrowQueues {
 
 // ---- kernel 1: GJK over every candidate pair -------------------------------------------------------
 constexpr int kGjkThreads = 256;
+constexpr int kNumClasses = 6;
 
-// One thread per (a,b)-sorted candidate pair.  Separated pairs write nothing; shallow contacts
-// (cores apart, spheres' radii overlapping) write their record; overlapping cores reserve their
-// contact slot and queue an EpaWork item.  Contact slots follow pair order: block-wide scan of the
-// contact flags + decoupled look-back across blocks (ticketed tiles).
+// Pair class by core kinds, so that a warp runs one kind of support function.
+__device__ __forceinline__ int pairClass(uint32_t typeA, uint32_t typeB) {
+    if (typeA == AXCD_SHAPE_CONVEX || typeB == AXCD_SHAPE_CONVEX) return 5;
+    if (typeA == AXCD_SHAPE_SPHERE) return (typeB == AXCD_SHAPE_SPHERE) ? 1 : 2;   // SS, point-box
+    return (typeB == AXCD_SHAPE_SPHERE) ? 3 : 4;                                   // box-point, box-box
+}
+
+// Block-local counting sort of the tile's items by class (stable).  cls in [0, kNumClasses);
+// returns through sOrder the item handled by each thread.  sCnt: kNumClasses * nWarps words.
+template <int THREADS>
+__device__ __forceinline__ void binByClass(int cls, uint32_t* sCnt, uint16_t* sOrder) {
+    constexpr int W = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t rank = 0;
+#pragma unroll
+    for (int c = 0; c < kNumClasses; ++c) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, cls == c);
+        if (lane == 0) sCnt[c * W + warp] = __popc(bal);
+        if (cls == c) rank = __popc(bal & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (tid == 0) {   // exclusive scan of the kNumClasses*W counts (class-major)
+        uint32_t run = 0;
+        for (int i = 0; i < kNumClasses * W; ++i) {
+            const uint32_t t = sCnt[i];
+            sCnt[i] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    sOrder[sCnt[cls * W + warp] + rank] = (uint16_t)tid;
+    __syncthreads();
+}
+
+// One thread per (a,b)-sorted candidate pair; inside a 256-pair tile the pairs are re-dealt to
+// threads by class (sphere-sphere / point-box / box-point / box-box / hull) so that warps do not
+// diverge on the support function.  Separated pairs write nothing; shallow contacts (cores apart,
+// radii overlapping) write their record; overlapping cores reserve their contact slot and queue an
+// EpaWork item.  Contact slots follow pair order: tile-wide scan of the contact flags in pair order
+// + decoupled look-back across tiles (ticketed).
 __global__ void __launch_bounds__(kGjkThreads, 2)
 gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
           int idxBits, const float* __restrict__ xf, const uint4* __restrict__ shapes,
           const float4* __restrict__ hull, NarrowParams cfg, AxcdContact* __restrict__ contacts,
           uint32_t maxContacts, NarrowQueues q, float* __restrict__ pairDist,
           volatile uint32_t* __restrict__ tileStatus, Counters* __restrict__ ctr) {
+    __shared__ uint32_t sCnt[kNumClasses * (kGjkThreads / 32)];
+    __shared__ uint16_t sOrder[kGjkThreads];
+    __shared__ uint32_t sA[kGjkThreads], sB[kGjkThreads];
+    __shared__ uint8_t sKind[kGjkThreads];
+    __shared__ uint32_t sSlot[kGjkThreads];
     __shared__ uint32_t sWarp[kGjkThreads / 32];
     __shared__ uint32_t sTile, sBase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -657,21 +729,37 @@ gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairC
     __syncthreads();
     const uint32_t tile = sTile;
     const uint32_t npairs = min(*pairCount, maxPairs);
-    const uint32_t k = tile * kGjkThreads + tid;
+    const uint32_t tileBase = tile * kGjkThreads;
+
+    // ---- deal the tile's pairs to threads by class -----------------------------------------------
+    {
+        int cls = 0;
+        if (tileBase + tid < npairs) {
+            const uint64_t pk = pairs[tileBase + tid];
+            const uint32_t a = (uint32_t)(pk >> idxBits), b = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
+            sA[tid] = a;
+            sB[tid] = b;
+            cls = pairClass(__ldg(&shapes[a].x), __ldg(&shapes[b].x));
+        }
+        binByClass<kGjkThreads>(cls, sCnt, sOrder);
+    }
+    const int j = sOrder[tid];           // local index of the pair this thread works on
+    const uint32_t k = tileBase + j;     // its global pair index
 
     // ---- per-pair GJK ----------------------------------------------------------------------------
     int kind = 0;   // 0 none, 1 shallow contact, 2 needs EPA
-    uint32_t ia = 0, ib = 0, status = 0;
+    uint32_t ia = 0, ib = 0, status = 0, sa_type = 0, sb_type = 0;
     V3 n = mk3(0.f, 0.f, 0.f), pos = n;
     float depth = 0.f;
     Simplex s;
     s.n = 0;
     if (k < npairs) {
-        const uint64_t pk = pairs[k];
-        ia = (uint32_t)(pk >> idxBits);
-        ib = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
+        ia = sA[j];
+        ib = sB[j];
         const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
         const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
+        sa_type = sa.x;
+        sb_type = sb.x;
         const V3 origin = ta.p;
         float dist = 0.f;
         if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_SPHERE) {
@@ -715,9 +803,12 @@ gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairC
         }
         if (pairDist) pairDist[k] = (kind == 1) ? ((dist < 0.0f) ? dist : 0.0f) : dist;   // kind 2: EPA overwrites
     }
+    sKind[j] = (uint8_t)kind;
+    __syncthreads();
 
-    // ---- contact slots in pair order -----------------------------------------------------------------
-    const uint32_t bal = __ballot_sync(0xffffffffu, kind != 0);
+    // ---- contact slots in pair order (thread t scans pair t) ----------------------------------------
+    const bool flag = sKind[tid] != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
     const uint32_t lanePrefix = __popc(bal & ((1u << lane) - 1u));
     if (lane == 0) sWarp[warp] = __popc(bal);
     __syncthreads();
@@ -758,17 +849,24 @@ gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairC
         }
     }
     __syncthreads();
+    sSlot[tid] = sBase + warpPrefix + lanePrefix;
+    __syncthreads();
     if (kind == 0) return;
-    const uint32_t slot = sBase + warpPrefix + lanePrefix;
+    const uint32_t slot = sSlot[j];
     if (slot >= maxContacts) return;
     if (kind == 1) {
         storeContact(contacts + slot, ia, ib, pos, n, depth, status);
         if (status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
     } else {
-        const uint32_t wq = atomicAdd(&ctr->epaCount, 1u);
-        EpaWork* wk = q.work + wq;
+        // warp-aggregated queue push (threads of a warp are class-sorted, so runs stay homogeneous)
+        const uint32_t m = __activemask();
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&ctr->epaCount, (uint32_t)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        EpaWork* wk = q.work + base + __popc(m & ((1u << lane) - 1u));
         uint4* o = reinterpret_cast<uint4*>(wk);
-        o[0] = make_uint4(k, slot, (uint32_t)s.n | (status ? 0x80000000u : 0u), 0u);
+        o[0] = make_uint4(k, slot, (uint32_t)s.n | (status ? 0x80000000u : 0u), (uint32_t)pairClass(sa_type, sb_type));
         float4* of = reinterpret_cast<float4*>(wk) + 1;
         of[0] = make_float4(s.y[0].x, s.y[0].y, s.y[0].z, s.y[1].x);
         of[1] = make_float4(s.y[1].y, s.y[1].z, s.y[2].x, s.y[2].y);
@@ -819,23 +917,31 @@ __device__ __forceinline__ bool epaOne(const EpaWork* __restrict__ wk, const uin
     return true;
 }
 
-// Fast path: polytope in shared memory (one column per thread), persistent grid-stride over the
-// queue (its length is only known on the device).
+// Fast path: polytope in shared memory (one column per thread).  Persistent blocks walk the queue
+// (its length is only known on the device) in 128-item chunks and re-deal each chunk to threads by
+// pair class, so a warp expands polytopes of one kind.
 __global__ void __launch_bounds__(kEpaThreads)
 epaKernel(NarrowQueues q, uint32_t maxContacts, const uint64_t* __restrict__ pairs, int idxBits,
           const float* __restrict__ xf, const uint4* __restrict__ shapes, const float4* __restrict__ hull,
           NarrowParams cfg, AxcdContact* __restrict__ contacts, float* __restrict__ pairDist,
           Counters* __restrict__ ctr) {
     extern __shared__ float sPoly[];
+    __shared__ uint32_t sCnt[kNumClasses * (kEpaThreads / 32)];
+    __shared__ uint16_t sOrder[kEpaThreads];
     using P = Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, kEpaThreads>;
     P poly;
     poly.base = sPoly + threadIdx.x;
     const uint32_t count = min(ctr->epaCount, maxContacts);
-    for (uint32_t i = blockIdx.x * kEpaThreads + threadIdx.x; i < count; i += gridDim.x * kEpaThreads) {
-        if (!epaOne(q.work + i, pairs, idxBits, xf, shapes, hull, cfg, contacts, pairDist, ctr, poly)) {
+    for (uint32_t chunk = blockIdx.x * kEpaThreads; chunk < count; chunk += gridDim.x * kEpaThreads) {
+        const uint32_t mine = chunk + threadIdx.x;
+        const int cls = (mine < count) ? (int)__ldg(&q.work[mine].pad) : 0;
+        binByClass<kEpaThreads>(cls, sCnt, sOrder);
+        const uint32_t i = chunk + sOrder[threadIdx.x];
+        if (i < count && !epaOne(q.work + i, pairs, idxBits, xf, shapes, hull, cfg, contacts, pairDist, ctr, poly)) {
             const uint32_t o = atomicAdd(&ctr->epaOverflow, 1u);
             q.overflow[o] = i;
         }
+        __syncthreads();
     }
 }
 

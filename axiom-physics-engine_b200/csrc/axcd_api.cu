@@ -57,7 +57,10 @@ struct AxcdContext {
     uint64_t* dPairKeys[2] = {nullptr, nullptr};
     EpaWork* dEpaWork = nullptr;     // GJK -> EPA queue (maxContacts)
     uint32_t* dEpaOverflow = nullptr;
-    uint32_t* dGjkStatus = nullptr;  // look-back status, one word per GJK tile
+    uint32_t* dSlotStatus = nullptr; // look-back status, one word per slot-scan tile
+    uint8_t* dFlags = nullptr;       // per pair: 0 none, 1 shallow contact, 2 EPA contact
+    uint32_t* dSlots = nullptr;      // per pair: contact slot
+    AxcdContact* dTmpContacts = nullptr;   // per pair: shallow contact records before compaction
     AxcdContact* dContacts = nullptr;
     float* dPairDist = nullptr;
     uint32_t* dSortHist = nullptr;
@@ -172,7 +175,7 @@ void axcd_destroy(AxcdContext* ctx) {
     void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dLeafLo, ctx->dLeafHi, ctx->dNodes, ctx->dParent,
                     ctx->dVisit, ctx->dWorldEnd, ctx->dPairKeys[0], ctx->dPairKeys[1], ctx->dEpaWork,
-                    ctx->dEpaOverflow, ctx->dGjkStatus, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
+                    ctx->dEpaOverflow, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
                     ctx->dSortStatus, ctx->dCtr};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -240,7 +243,10 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dVisit, nb));
         CU(dalloc(&ctx->dEpaWork, (size_t)cfg->maxContacts));
         CU(dalloc(&ctx->dEpaOverflow, (size_t)cfg->maxContacts));
-        CU(dalloc(&ctx->dGjkStatus, np / kGjkThreads + 2));
+        CU(dalloc(&ctx->dSlotStatus, np / kSlotTile + 2));
+        CU(dalloc(&ctx->dFlags, np + kSlotTile));
+        CU(dalloc(&ctx->dSlots, np));
+        CU(dalloc(&ctx->dTmpContacts, np));
         CU(cudaFuncSetAttribute(epaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaSmemBytes));
         CU(dalloc(&ctx->dContacts, (size_t)cfg->maxContacts));
         if (cfg->flags & AXCD_FLAG_PAIR_DISTANCES) CU(dalloc(&ctx->dPairDist, np));
@@ -433,7 +439,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
     recordEv(ctx, EV_N0);
     ctx->numContacts = ctx->foundContacts = 0;
     const uint32_t np = ctx->numPairs;
-    ctx->launches[2] = np ? 3 : 0;   // GJK, EPA, EPA fallback
+    ctx->launches[2] = np ? 4 : 0;   // GJK, slots, EPA, EPA fallback
     if (np) {
         NarrowParams p;
         p.gjkMaxIters = ctx->cfg.gjkMaxIters;
@@ -443,20 +449,27 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         p.epaTol = ctx->cfg.epaTol;
         p.wantDistances = (ctx->cfg.flags & AXCD_FLAG_PAIR_DISTANCES) ? 1u : 0u;
         const uint32_t tiles = (np + kGjkThreads - 1) / kGjkThreads;
-        CU(cudaMemsetAsync(ctx->dGjkStatus, 0, sizeof(uint32_t) * (tiles + 1), st));
+        const uint32_t slotTiles = (np + kSlotTile - 1) / kSlotTile;
+        CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * (slotTiles + 1), st));
         NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow};
         const uint64_t* pairs = ctx->dPairKeys[ctx->pairBuf];
-        gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, &ctx->dCtr->pairCount, ctx->cfg.maxPairs, ctx->idxBits,
-                                                 ctx->dXf, ctx->dShapes, ctx->dHull, p, ctx->dContacts,
-                                                 ctx->cfg.maxContacts, q, ctx->dPairDist, ctx->dGjkStatus, ctx->dCtr);
+        const uint32_t* pairCount = &ctx->dCtr->pairCount;
+        gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, pairCount, ctx->cfg.maxPairs, ctx->idxBits, ctx->dXf,
+                                                 ctx->dShapes, ctx->dHull, p, ctx->dFlags, ctx->dTmpContacts, q,
+                                                 ctx->cfg.maxContacts, ctx->dPairDist, ctx->dCtr);
+        slotKernel<<<slotTiles, kSlotThreads, 0, st>>>(ctx->dFlags, pairCount, ctx->cfg.maxPairs, ctx->dTmpContacts,
+                                                       ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
+                                                       ctx->dSlotStatus, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_GJK);
         // EPA: persistent grids, queue lengths are read on the device
         epaKernel<<<kNumSMs * 2, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->idxBits, ctx->dXf,
                                                                    ctx->dShapes, ctx->dHull, p, ctx->dContacts,
-                                                                   ctx->dPairDist, ctx->dCtr);
+                                                                   ctx->cfg.maxContacts, ctx->dSlots, ctx->dPairDist,
+                                                                   ctx->dCtr);
         epaFallbackKernel<<<kNumSMs, 64, 0, st>>>(q, pairs, ctx->idxBits, ctx->dXf, ctx->dShapes, ctx->dHull, p,
-                                                  ctx->dContacts, ctx->dPairDist, ctx->dCtr);
+                                                  ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots, ctx->dPairDist,
+                                                  ctx->dCtr);
         CU(cudaGetLastError());
     } else {
         recordEv(ctx, EV_GJK);

@@ -656,7 +656,7 @@ __device__ __forceinline__ void storeContact(AxcdContact* __restrict__ dst, uint
 
 // GJK -> EPA hand-off record (80 bytes, 16-byte aligned)
 struct __align__(16) EpaWork {
-    uint32_t pair, slot, n, pad;   // pair index, destination contact slot, simplex size (bit 31: GJK status 301)
+    uint32_t pair, unused, n, pad;   // pair index, -, simplex size (bit 31: GJK status 301), pair class
     float y[12];              // simplex points
     uint32_t id[4];           // simplex vertex ids
 };
@@ -705,31 +705,23 @@ __device__ __forceinline__ void binByClass(int cls, uint32_t* sCnt, uint16_t* sO
     __syncthreads();
 }
 
-// One thread per (a,b)-sorted candidate pair; inside a 256-pair tile the pairs are re-dealt to
-// threads by class (sphere-sphere / point-box / box-point / box-box / hull) so that warps do not
-// diverge on the support function.  Separated pairs write nothing; shallow contacts (cores apart,
-// radii overlapping) write their record; overlapping cores reserve their contact slot and queue an
-// EpaWork item.  Contact slots follow pair order: tile-wide scan of the contact flags in pair order
-// + decoupled look-back across tiles (ticketed).
+// One thread per (a,b)-sorted candidate pair; inside a tile the pairs are re-dealt to threads by
+// class (sphere-sphere / point-box / box-point / box-box / hull) so that warps do not diverge on
+// the support function.  Per pair it writes flag[k]: 0 = no contact, 1 = shallow contact (cores
+// apart, radii overlapping; record written to tmp[k]), 2 = cores overlap (EpaWork queued; EPA
+// writes the record).  Contact slots are assigned afterwards, in pair order, by slotKernel.
 __global__ void __launch_bounds__(kGjkThreads, 2)
 gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
           int idxBits, const float* __restrict__ xf, const uint4* __restrict__ shapes,
-          const float4* __restrict__ hull, NarrowParams cfg, AxcdContact* __restrict__ contacts,
-          uint32_t maxContacts, NarrowQueues q, float* __restrict__ pairDist,
-          volatile uint32_t* __restrict__ tileStatus, Counters* __restrict__ ctr) {
+          const float4* __restrict__ hull, NarrowParams cfg, uint8_t* __restrict__ flags,
+          AxcdContact* __restrict__ tmp, NarrowQueues q, uint32_t queueCap, float* __restrict__ pairDist,
+          Counters* __restrict__ ctr) {
     __shared__ uint32_t sCnt[kNumClasses * (kGjkThreads / 32)];
     __shared__ uint16_t sOrder[kGjkThreads];
     __shared__ uint32_t sA[kGjkThreads], sB[kGjkThreads];
-    __shared__ uint8_t sKind[kGjkThreads];
-    __shared__ uint32_t sSlot[kGjkThreads];
-    __shared__ uint32_t sWarp[kGjkThreads / 32];
-    __shared__ uint32_t sTile, sBase;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sTile = atomicAdd(&ctr->gjkTicket, 1u);
-    __syncthreads();
-    const uint32_t tile = sTile;
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t npairs = min(*pairCount, maxPairs);
-    const uint32_t tileBase = tile * kGjkThreads;
+    const uint32_t tileBase = blockIdx.x * kGjkThreads;
 
     // ---- deal the tile's pairs to threads by class -----------------------------------------------
     {
@@ -745,81 +737,129 @@ gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairC
     }
     const int j = sOrder[tid];           // local index of the pair this thread works on
     const uint32_t k = tileBase + j;     // its global pair index
+    if (k >= npairs) return;
 
     // ---- per-pair GJK ----------------------------------------------------------------------------
-    int kind = 0;   // 0 none, 1 shallow contact, 2 needs EPA
-    uint32_t ia = 0, ib = 0, status = 0, sa_type = 0, sb_type = 0;
+    int kind = 0;
+    uint32_t status = 0;
+    const uint32_t ia = sA[j], ib = sB[j];
     V3 n = mk3(0.f, 0.f, 0.f), pos = n;
-    float depth = 0.f;
+    float depth = 0.f, dist = 0.f;
     Simplex s;
     s.n = 0;
-    if (k < npairs) {
-        ia = sA[j];
-        ib = sB[j];
-        const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
-        const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
-        sa_type = sa.x;
-        sb_type = sb.x;
-        const V3 origin = ta.p;
-        float dist = 0.f;
-        if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_SPHERE) {
-            const float ra = __uint_as_float(sa.y), rb = __uint_as_float(sb.y);
-            const V3 d = tb.p - origin;
-            const float len = sqrtf(dot3(d, d));
-            const float rs = ra + rb;
-            depth = rs - len;
+    const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
+    const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
+    const V3 origin = ta.p;
+    if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_SPHERE) {
+        const float ra = __uint_as_float(sa.y), rb = __uint_as_float(sb.y);
+        const V3 d = tb.p - origin;
+        const float len = sqrtf(dot3(d, d));
+        const float rs = ra + rb;
+        depth = rs - len;
+        dist = len - rs;
+        if (depth >= 0.0f) {
+            kind = 1;
+            n = (len > 0.0f) ? d * (1.0f / len) : mk3(1.0f, 0.0f, 0.0f);
+            const V3 pa = n * ra;
+            const V3 pb = d - n * rb;
+            pos = (pa + pb) * 0.5f + origin;
+        }
+    } else {
+        const Core A = makeCore(ta, sa, hull, origin);
+        const Core B = makeCore(tb, sb, hull, origin);
+        const float rs = A.r + B.r;
+        const GjkResult g = gjk(A, B, cfg, rs, s);
+        status = g.status;
+        if (g.state == GJK_SEPARATED) {
+            const float len = sqrtf(g.vv);
             dist = len - rs;
-            if (depth >= 0.0f) {
-                kind = 1;
-                n = (len > 0.0f) ? d * (1.0f / len) : mk3(1.0f, 0.0f, 0.0f);
-                const V3 pa = n * ra;
-                const V3 pb = d - n * rb;
-                pos = (pa + pb) * 0.5f + origin;
+            if (g.exact) {
+                depth = rs - len;
+                if (depth >= 0.0f) {
+                    kind = 1;
+                    n = -(g.v * (1.0f / len));
+                    V3 ca = mk3(0.f, 0.f, 0.f);
+                    for (int i = 0; i < s.n; ++i) ca = ca + pointFromId(A, s.id[i] & 0xffffu) * s.lam[i];
+                    const V3 pa = ca + n * A.r;
+                    const V3 pb = (ca - g.v) - n * B.r;
+                    pos = (pa + pb) * 0.5f + origin;
+                }
             }
         } else {
-            const Core A = makeCore(ta, sa, hull, origin);
-            const Core B = makeCore(tb, sb, hull, origin);
-            const float rs = A.r + B.r;
-            const GjkResult g = gjk(A, B, cfg, rs, s);
-            status = g.status;
-            if (g.state == GJK_SEPARATED) {
-                const float len = sqrtf(g.vv);
-                dist = len - rs;
-                if (g.exact) {
-                    depth = rs - len;
-                    if (depth >= 0.0f) {
-                        kind = 1;
-                        n = -(g.v * (1.0f / len));
-                        V3 ca = mk3(0.f, 0.f, 0.f);
-                        for (int i = 0; i < s.n; ++i) ca = ca + pointFromId(A, s.id[i] & 0xffffu) * s.lam[i];
-                        const V3 pa = ca + n * A.r;
-                        const V3 pb = (ca - g.v) - n * B.r;
-                        pos = (pa + pb) * 0.5f + origin;
-                    }
-                }
-            } else {
-                kind = 2;
-            }
+            kind = 2;
         }
-        if (pairDist) pairDist[k] = (kind == 1) ? ((dist < 0.0f) ? dist : 0.0f) : dist;   // kind 2: EPA overwrites
     }
-    sKind[j] = (uint8_t)kind;
-    __syncthreads();
+    if (pairDist) pairDist[k] = (kind == 1) ? ((dist < 0.0f) ? dist : 0.0f) : dist;   // kind 2: EPA overwrites
+    flags[k] = (uint8_t)kind;
+    if (kind == 1) {
+        storeContact(tmp + k, ia, ib, pos, n, depth, status);
+        if (status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
+    } else if (kind == 2) {
+        // warp-aggregated queue push (threads of a warp are class-sorted, so runs stay homogeneous)
+        const uint32_t m = __activemask();
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&ctr->epaCount, (uint32_t)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const uint32_t wq = base + __popc(m & ((1u << lane) - 1u));
+        if (wq < queueCap) {
+            EpaWork* wk = q.work + wq;
+            uint4* o = reinterpret_cast<uint4*>(wk);
+            o[0] = make_uint4(k, 0u, (uint32_t)s.n | (status ? 0x80000000u : 0u), (uint32_t)pairClass(sa.x, sb.x));
+            float4* of = reinterpret_cast<float4*>(wk) + 1;
+            of[0] = make_float4(s.y[0].x, s.y[0].y, s.y[0].z, s.y[1].x);
+            of[1] = make_float4(s.y[1].y, s.y[1].z, s.y[2].x, s.y[2].y);
+            of[2] = make_float4(s.y[2].z, s.y[3].x, s.y[3].y, s.y[3].z);
+            o[4] = make_uint4(s.id[0], s.id[1], s.id[2], s.id[3]);
+        }
+    }
+}
 
-    // ---- contact slots in pair order (thread t scans pair t) ----------------------------------------
-    const bool flag = sKind[tid] != 0;
-    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
-    const uint32_t lanePrefix = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) sWarp[warp] = __popc(bal);
+// ---- kernel 1b: contact slots in pair order ------------------------------------------------------------
+// Exclusive scan of (flag != 0) over the pairs (single pass, decoupled look-back, ticketed tiles).
+// Writes slot[k] for every contact pair, moves the shallow contacts tmp[k] -> contacts[slot], and
+// leaves the total in ctr->contactCount.  EPA later writes its records to contacts[slot[k]].
+constexpr int kSlotThreads = 256;
+constexpr int kSlotItems = 8;
+constexpr int kSlotTile = kSlotThreads * kSlotItems;
+
+__global__ void __launch_bounds__(kSlotThreads)
+slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
+           const AxcdContact* __restrict__ tmp, AxcdContact* __restrict__ contacts, uint32_t maxContacts,
+           uint32_t* __restrict__ slots, volatile uint32_t* __restrict__ tileStatus, Counters* __restrict__ ctr) {
+    __shared__ uint32_t sWarp[kSlotThreads / 32];
+    __shared__ uint32_t sTile, sBase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(&ctr->gjkTicket, 1u);
+    __syncthreads();
+    const uint32_t tile = sTile;
+    const uint32_t npairs = min(*pairCount, maxPairs);
+    const uint32_t base = tile * kSlotTile + tid * kSlotItems;
+    // 8 one-byte flags per thread: one 8-byte load (flags buffer is padded to a tile multiple)
+    const uint2 fl = (base < npairs) ? __ldg(reinterpret_cast<const uint2*>(flags + base)) : make_uint2(0u, 0u);
+    uint32_t f[kSlotItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kSlotItems; ++i) {
+        const uint32_t word = (i < 4) ? fl.x : fl.y;
+        f[i] = (base + i < npairs) ? ((word >> (8 * (i & 3))) & 0xffu) : 0u;
+        sum += f[i] ? 1u : 0u;
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) sWarp[warp] = inc;
     __syncthreads();
     uint32_t warpPrefix = 0, tileTotal = 0;
 #pragma unroll
-    for (int i = 0; i < kGjkThreads / 32; ++i) {
+    for (int i = 0; i < kSlotThreads / 32; ++i) {
         warpPrefix += (i < warp) ? sWarp[i] : 0u;
         tileTotal += sWarp[i];
     }
-    if (warp == 0) {
-        // warp-parallel decoupled look-back
+    if (warp == 0) {   // warp-parallel decoupled look-back
         uint32_t excl = 0;
         if (tile == 0) {
             if (lane == 0) tileStatus[0] = kFlagInclusive | tileTotal;
@@ -845,33 +885,23 @@ gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairC
         }
         if (lane == 0) {
             sBase = excl;
-            if ((uint64_t)(tile + 1) * kGjkThreads >= npairs) ctr->contactCount = excl + tileTotal;   // last tile
+            if ((uint64_t)(tile + 1) * kSlotTile >= npairs) ctr->contactCount = excl + tileTotal;   // last tile
         }
     }
     __syncthreads();
-    sSlot[tid] = sBase + warpPrefix + lanePrefix;
-    __syncthreads();
-    if (kind == 0) return;
-    const uint32_t slot = sSlot[j];
-    if (slot >= maxContacts) return;
-    if (kind == 1) {
-        storeContact(contacts + slot, ia, ib, pos, n, depth, status);
-        if (status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
-    } else {
-        // warp-aggregated queue push (threads of a warp are class-sorted, so runs stay homogeneous)
-        const uint32_t m = __activemask();
-        const int leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&ctr->epaCount, (uint32_t)__popc(m));
-        base = __shfl_sync(m, base, leader);
-        EpaWork* wk = q.work + base + __popc(m & ((1u << lane) - 1u));
-        uint4* o = reinterpret_cast<uint4*>(wk);
-        o[0] = make_uint4(k, slot, (uint32_t)s.n | (status ? 0x80000000u : 0u), (uint32_t)pairClass(sa_type, sb_type));
-        float4* of = reinterpret_cast<float4*>(wk) + 1;
-        of[0] = make_float4(s.y[0].x, s.y[0].y, s.y[0].z, s.y[1].x);
-        of[1] = make_float4(s.y[1].y, s.y[1].z, s.y[2].x, s.y[2].y);
-        of[2] = make_float4(s.y[2].z, s.y[3].x, s.y[3].y, s.y[3].z);
-        o[4] = make_uint4(s.id[0], s.id[1], s.id[2], s.id[3]);
+    uint32_t run = sBase + warpPrefix + inc - sum;
+#pragma unroll
+    for (int i = 0; i < kSlotItems; ++i) {
+        if (!f[i]) continue;
+        const uint32_t k = base + i;
+        slots[k] = run;
+        if (f[i] == 1u && run < maxContacts) {
+            const float2* src = reinterpret_cast<const float2*>(tmp + k);
+            float2* dst = reinterpret_cast<float2*>(contacts + run);
+#pragma unroll
+            for (int w = 0; w < 5; ++w) dst[w] = src[w];
+        }
+        ++run;
     }
 }
 
@@ -884,13 +914,15 @@ template <int MAXV, int MAXF, int MAXE, int STRIDE>
 __device__ __forceinline__ bool epaOne(const EpaWork* __restrict__ wk, const uint64_t* __restrict__ pairs, int idxBits,
                                        const float* __restrict__ xf, const uint4* __restrict__ shapes,
                                        const float4* __restrict__ hull, const NarrowParams& cfg,
-                                       AxcdContact* __restrict__ contacts, float* __restrict__ pairDist,
+                                       AxcdContact* __restrict__ contacts, uint32_t maxContacts,
+                                       const uint32_t* __restrict__ slots, float* __restrict__ pairDist,
                                        Counters* __restrict__ ctr, const Poly<MAXV, MAXF, MAXE, STRIDE>& poly) {
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(wk));
     const float4 f0 = __ldg(reinterpret_cast<const float4*>(wk) + 1), f1 = __ldg(reinterpret_cast<const float4*>(wk) + 2),
                  f2 = __ldg(reinterpret_cast<const float4*>(wk) + 3);
     const uint4 idv = __ldg(reinterpret_cast<const uint4*>(wk) + 4);
-    const uint32_t pairIdx = h.x, slot = h.y;
+    const uint32_t pairIdx = h.x;
+    const uint32_t slot = __ldg(slots + pairIdx);
     const uint64_t pk = __ldg(pairs + pairIdx);
     const uint32_t ia = (uint32_t)(pk >> idxBits), ib = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
     const int n0 = (int)(h.z & 0xffu);
@@ -910,7 +942,7 @@ __device__ __forceinline__ bool epaOne(const EpaWork* __restrict__ wk, const uin
     const V3 pa = r.pa + r.n * A.r;
     const V3 pb = r.pb - r.n * B.r;
     const V3 pos = (pa + pb) * 0.5f + origin;
-    storeContact(contacts + slot, ia, ib, pos, r.n, depth, status);
+    if (slot < maxContacts) storeContact(contacts + slot, ia, ib, pos, r.n, depth, status);
     if (pairDist) pairDist[pairIdx] = (depth > 0.0f) ? -depth : 0.0f;
     if (status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
     if (status == AXCD_ERR_EPA_NO_CONVERGE) atomicAdd(&ctr->epaFailures, 1u);
@@ -921,23 +953,23 @@ __device__ __forceinline__ bool epaOne(const EpaWork* __restrict__ wk, const uin
 // (its length is only known on the device) in 128-item chunks and re-deal each chunk to threads by
 // pair class, so a warp expands polytopes of one kind.
 __global__ void __launch_bounds__(kEpaThreads)
-epaKernel(NarrowQueues q, uint32_t maxContacts, const uint64_t* __restrict__ pairs, int idxBits,
+epaKernel(NarrowQueues q, uint32_t queueCap, const uint64_t* __restrict__ pairs, int idxBits,
           const float* __restrict__ xf, const uint4* __restrict__ shapes, const float4* __restrict__ hull,
-          NarrowParams cfg, AxcdContact* __restrict__ contacts, float* __restrict__ pairDist,
-          Counters* __restrict__ ctr) {
+          NarrowParams cfg, AxcdContact* __restrict__ contacts, uint32_t maxContacts,
+          const uint32_t* __restrict__ slots, float* __restrict__ pairDist, Counters* __restrict__ ctr) {
     extern __shared__ float sPoly[];
     __shared__ uint32_t sCnt[kNumClasses * (kEpaThreads / 32)];
     __shared__ uint16_t sOrder[kEpaThreads];
     using P = Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, kEpaThreads>;
     P poly;
     poly.base = sPoly + threadIdx.x;
-    const uint32_t count = min(ctr->epaCount, maxContacts);
+    const uint32_t count = min(ctr->epaCount, queueCap);
     for (uint32_t chunk = blockIdx.x * kEpaThreads; chunk < count; chunk += gridDim.x * kEpaThreads) {
         const uint32_t mine = chunk + threadIdx.x;
         const int cls = (mine < count) ? (int)__ldg(&q.work[mine].pad) : 0;
         binByClass<kEpaThreads>(cls, sCnt, sOrder);
         const uint32_t i = chunk + sOrder[threadIdx.x];
-        if (i < count && !epaOne(q.work + i, pairs, idxBits, xf, shapes, hull, cfg, contacts, pairDist, ctr, poly)) {
+        if (i < count && !epaOne(q.work + i, pairs, idxBits, xf, shapes, hull, cfg, contacts, maxContacts, slots, pairDist, ctr, poly)) {
             const uint32_t o = atomicAdd(&ctr->epaOverflow, 1u);
             q.overflow[o] = i;
         }
@@ -949,14 +981,15 @@ epaKernel(NarrowQueues q, uint32_t maxContacts, const uint64_t* __restrict__ pai
 __global__ void __launch_bounds__(64)
 epaFallbackKernel(NarrowQueues q, const uint64_t* __restrict__ pairs, int idxBits, const float* __restrict__ xf,
                   const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
-                  AxcdContact* __restrict__ contacts, float* __restrict__ pairDist, Counters* __restrict__ ctr) {
+                  AxcdContact* __restrict__ contacts, uint32_t maxContacts, const uint32_t* __restrict__ slots,
+                  float* __restrict__ pairDist, Counters* __restrict__ ctr) {
     using P = Poly<kEpaHardVerts, kEpaHardFaces, kEpaHardFaces * 3, 1>;
     float store[P::kWords];
     P poly;
     poly.base = store;
     const uint32_t count = ctr->epaOverflow;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
-        epaOne(q.work + q.overflow[i], pairs, idxBits, xf, shapes, hull, cfg, contacts, pairDist, ctr, poly);
+        epaOne(q.work + q.overflow[i], pairs, idxBits, xf, shapes, hull, cfg, contacts, maxContacts, slots, pairDist, ctr, poly);
 }
 
 }  // namespace axcd

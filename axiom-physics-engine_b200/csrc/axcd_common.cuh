@@ -83,7 +83,8 @@ struct Counters {
     uint32_t sortTicket[8];  // dynamic tile tickets, one per radix pass
     uint32_t gjkTicket;      // dynamic tile ticket of the GJK kernel
     uint32_t epaOverflow;    // EPA pairs that outgrew the shared-memory polytope caps
-    uint32_t pad[2];
+    uint32_t epaCursor;      // next unclaimed EPA queue item
+    uint32_t pad[1];
 };
 
 }  // namespace axcd

@@ -449,13 +449,25 @@ __device__ __forceinline__ EpaResult epaTouching(V3 n, V3 pa) {
     return r;
 }
 
-// EPA from a GJK end simplex (n0 points y0[], ids id0[]).  MAXV/MAXF/MAXE are storage caps; the
-// algorithmic caps (cfg.epaMaxFaces, kEpaHardVerts, cfg.epaMaxIters) give status 302, while hitting
-// a smaller storage cap sets `overflow` and the caller reruns the pair on the full-cap path.
+// EPA from a GJK end simplex (n0 points y0[], ids id0[]), split into init / iterate / finish so a
+// persistent lane can interleave pairs.  MAXV/MAXF/MAXE are storage caps; the algorithmic caps
+// (cfg.epaMaxFaces, kEpaHardVerts, cfg.epaMaxIters) give status 302, while hitting a smaller
+// storage cap sets `overflow` and the caller reruns the pair on the full-cap path.
+template <class Mask>
+struct EpaState {
+    int nv, nf, best;
+    Mask alive;        // bit f set = face slot f is part of the polytope
+    uint32_t it, status;
+    bool overflow, degenerate;
+};
+
+// Grows the simplex to an oriented tetrahedron.  Returns 0 when the expansion can start, 1 when the
+// Minkowski difference is degenerate at the origin and `touching` already is the answer.
 template <int MAXV, int MAXF, int MAXE, int STRIDE>
-__device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const NarrowParams& cfg, int n0,
-                                            const V3* y0, const uint32_t* id0,
-                                            const Poly<MAXV, MAXF, MAXE, STRIDE>& e) {
+__device__ __forceinline__ int epaInit(const Core& A, const Core& B, int n0, const V3* y0, const uint32_t* id0,
+                                       const Poly<MAXV, MAXF, MAXE, STRIDE>& e,
+                                       EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st,
+                                       EpaResult& touching) {
     int nv = n0;
     for (int i = 0; i < 4; ++i)
         if (i < n0) {
@@ -474,7 +486,7 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
             const V3 d = y1 - e.y(0);
             if (dot3(d, d) > kDegenerateEps) nv = 2;
         }
-        if (nv == 1) return epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu));
+        if (nv == 1) { touching = epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu)); return 1; }
     }
     if (nv == 2) {
         const V3 d = e.y(1) - e.y(0);
@@ -492,12 +504,12 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
                 if (dot3(c, c) > kDegenerateEps) nv = 3;
             }
         }
-        if (nv == 2) return epaTouching(firstDir, pointFromId(A, e.id(0) & 0xffffu));
+        if (nv == 2) { touching = epaTouching(firstDir, pointFromId(A, e.id(0) & 0xffffu)); return 1; }
     }
     if (nv == 3) {
         const V3 n = cross3(e.y(1) - e.y(0), e.y(2) - e.y(0));
         const float n2 = dot3(n, n);
-        if (n2 <= 1e-30f) return epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu));
+        if (n2 <= 1e-30f) { touching = epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu)); return 1; }
         for (int sgn = 0; sgn < 2 && nv == 3; ++sgn) {
             const V3 y3 = supportDiff(A, B, sgn ? -n : n, tid_);
             e.setY(3, y3);
@@ -511,7 +523,7 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
             closestTriangle(e.y(0), e.y(1), e.y(2), la, lb, lc, m);
             const V3 pa = (pointFromId(A, e.id(0) & 0xffffu) * la + pointFromId(A, e.id(1) & 0xffffu) * lb) +
                           pointFromId(A, e.id(2) & 0xffffu) * lc;
-            return epaTouching(n, pa);
+            { touching = epaTouching(n, pa); return 1; }
         }
     }
     // orientation: make (0,1,2) face away from vertex 3
@@ -527,108 +539,132 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
     epaSetFace(e, 1, 0, 3, 1);
     epaSetFace(e, 2, 0, 2, 3);
     epaSetFace(e, 3, 1, 3, 2);
+    st.nv = nv;
+    st.nf = 4;
+    st.best = 0;
+    st.alive = 0xf;
+    st.it = 0;
+    st.status = 0;
+    st.overflow = false;
+    st.degenerate = false;
+    return 0;
+}
+
+// One expansion step.  Returns true when the pair is finished (converged, capped or overflowed).
+template <int MAXV, int MAXF, int MAXE, int STRIDE>
+__device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const NarrowParams& cfg,
+                                           const Poly<MAXV, MAXF, MAXE, STRIDE>& e,
+                                           EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st) {
     using Mask = typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask;
     const Mask one = 1;
-    Mask alive = 0xf;   // bit f set = face slot f is part of the polytope
-    int nf = 4;         // slots in use (alive or not)
     const int maxFaces = (int)min(cfg.epaMaxFaces, (uint32_t)kEpaHardFaces);
-
-    uint32_t status = 0;
-    bool overflow = false;
-    int best = 0;
-    for (uint32_t it = 0;; ++it) {
-        best = -1;
-        float bd = FLT_MAX;
-        for (int i = 0; i < nf; ++i) {
-            const float di = e.fd(i);
-            if (((alive >> i) & one) && di < bd) {
-                bd = di;
-                best = i;
-            }
-        }
-        if (best < 0) return epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu));
-        const V3 bn = e.fn(best);
-        uint32_t wid;
-        const V3 w = supportDiff(A, B, bn, wid);
-        const float dw = dot3(w, bn);
-        const float scale = (bd > 1.0f) ? bd : 1.0f;
-        if (dw - bd <= cfg.epaTol * scale) break;
-        bool dup = false;
-        for (int i = 0; i < nv; ++i) dup = dup || same3(w, e.y(i));
-        if (dup) break;
-        if (it >= cfg.epaMaxIters || nv >= kEpaHardVerts) {
-            status = AXCD_ERR_EPA_NO_CONVERGE;
-            break;
-        }
-        // visible faces: w clearly in front
-        const float wl = fabsf(w.x) + fabsf(w.y) + fabsf(w.z);
-        const float visEps = 1e-6f * ((wl > 1.0f) ? wl : 1.0f);
-        Mask vis = 0;
-        for (int i = 0; i < nf; ++i) {
-            const bool v = dot3(e.fn(i), w) - e.fd(i) > visEps;
-            if (v && ((alive >> i) & one)) vis |= one << i;
-        }
-        // directed edges of the visible faces, as one bit row per start vertex
-        e.clearRows(nv);
-        for (Mask m = vis; m; m &= m - 1) {
-            const uint32_t fi = e.fi(lowestBit(m));
-            const uint32_t v0 = fi & 0xffu, v1 = (fi >> 8) & 0xffu, v2 = (fi >> 16) & 0xffu;
-            e.setEdgeBit(v0, v1);
-            e.setEdgeBit(v1, v2);
-            e.setEdgeBit(v2, v0);
-        }
-        // horizon in canonical order: visible faces by ascending slot, edges in winding order, an
-        // edge is kept iff its reverse is not an edge of a visible face
-        int nh = 0;
-        uint64_t starts = 0, ends = 0;
-        bool loopOk = true, edgeOverflow = false;
-        for (Mask m = vis; m; m &= m - 1) {
-            const uint32_t fi = e.fi(lowestBit(m));
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const uint32_t ea = (fi >> (8 * k)) & 0xffu;
-                const uint32_t eb = (fi >> (8 * ((k + 1) % 3))) & 0xffu;
-                if (e.edgeBit(eb, ea)) continue;   // shared by two visible faces
-                if (((starts >> ea) & 1ull) || ((ends >> eb) & 1ull)) loopOk = false;
-                starts |= 1ull << ea;
-                ends |= 1ull << eb;
-                if (nh < MAXE) e.setEdge(nh, ea | (eb << 8));
-                else edgeOverflow = true;
-                ++nh;
-            }
-        }
-        if (nh < 3) loopOk = false;
-        const int nalive = popCount(alive), nvis = popCount(vis);
-        if (!loopOk || nalive - nvis + nh > maxFaces) {
-            status = AXCD_ERR_EPA_NO_CONVERGE;
-            break;
-        }
-        if (edgeOverflow || nv >= MAXV || nalive - nvis + nh > MAXF) {   // storage caps of this path
-            overflow = true;
-            break;
-        }
-        const int wi = nv;
-        e.setY(wi, w);
-        e.setId(wi, wid);
-        nv++;
-        alive &= ~vis;
-        for (int h = 0; h < nh; ++h) {
-            const int slot = lowestBit((Mask)~alive);   // lowest free slot
-            const uint32_t ed = e.edge(h);
-            epaSetFace(e, slot, (int)(ed & 0xffu), (int)(ed >> 8), wi);
-            alive |= one << slot;
-            nf = max(nf, slot + 1);
+    int& nv = st.nv;
+    int& nf = st.nf;
+    int& best = st.best;
+    Mask& alive = st.alive;
+    best = -1;
+    float bd = FLT_MAX;
+    for (int i = 0; i < nf; ++i) {
+        const float di = e.fd(i);
+        if (((alive >> i) & one) && di < bd) {
+            bd = di;
+            best = i;
         }
     }
+    if (best < 0) {   // every face degenerate: give up on this polytope
+        st.degenerate = true;
+        return true;
+    }
+    const V3 bn = e.fn(best);
+    uint32_t wid;
+    const V3 w = supportDiff(A, B, bn, wid);
+    const float dw = dot3(w, bn);
+    const float scale = (bd > 1.0f) ? bd : 1.0f;
+    if (dw - bd <= cfg.epaTol * scale) return true;
+    bool dup = false;
+    for (int i = 0; i < nv; ++i) dup = dup || same3(w, e.y(i));
+    if (dup) return true;
+    if (st.it >= cfg.epaMaxIters || nv >= kEpaHardVerts) {
+        st.status = AXCD_ERR_EPA_NO_CONVERGE;
+        return true;
+    }
+    // visible faces: w clearly in front
+    const float wl = fabsf(w.x) + fabsf(w.y) + fabsf(w.z);
+    const float visEps = 1e-6f * ((wl > 1.0f) ? wl : 1.0f);
+    Mask vis = 0;
+    for (int i = 0; i < nf; ++i) {
+        const bool v = dot3(e.fn(i), w) - e.fd(i) > visEps;
+        if (v && ((alive >> i) & one)) vis |= one << i;
+    }
+    // directed edges of the visible faces, as one bit row per start vertex
+    e.clearRows(nv);
+    for (Mask m = vis; m; m &= m - 1) {
+        const uint32_t fi = e.fi(lowestBit(m));
+        const uint32_t v0 = fi & 0xffu, v1 = (fi >> 8) & 0xffu, v2 = (fi >> 16) & 0xffu;
+        e.setEdgeBit(v0, v1);
+        e.setEdgeBit(v1, v2);
+        e.setEdgeBit(v2, v0);
+    }
+    // horizon in canonical order: visible faces by ascending slot, edges in winding order, an
+    // edge is kept iff its reverse is not an edge of a visible face
+    int nh = 0;
+    uint64_t starts = 0, ends = 0;
+    bool loopOk = true, edgeOverflow = false;
+    for (Mask m = vis; m; m &= m - 1) {
+        const uint32_t fi = e.fi(lowestBit(m));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t ea = (fi >> (8 * k)) & 0xffu;
+            const uint32_t eb = (fi >> (8 * ((k + 1) % 3))) & 0xffu;
+            if (e.edgeBit(eb, ea)) continue;   // shared by two visible faces
+            if (((starts >> ea) & 1ull) || ((ends >> eb) & 1ull)) loopOk = false;
+            starts |= 1ull << ea;
+            ends |= 1ull << eb;
+            if (nh < MAXE) e.setEdge(nh, ea | (eb << 8));
+            else edgeOverflow = true;
+            ++nh;
+        }
+    }
+    if (nh < 3) loopOk = false;
+    const int nalive = popCount(alive), nvis = popCount(vis);
+    if (!loopOk || nalive - nvis + nh > maxFaces) {
+        st.status = AXCD_ERR_EPA_NO_CONVERGE;
+        return true;
+    }
+    if (edgeOverflow || nv >= MAXV || nalive - nvis + nh > MAXF) {   // storage caps of this path
+        st.overflow = true;
+        return true;
+    }
+    const int wi = nv;
+    e.setY(wi, w);
+    e.setId(wi, wid);
+    nv++;
+    alive &= ~vis;
+    for (int h = 0; h < nh; ++h) {
+        const int slot = lowestBit((Mask)~alive);   // lowest free slot
+        const uint32_t ed = e.edge(h);
+        epaSetFace(e, slot, (int)(ed & 0xffu), (int)(ed >> 8), wi);
+        alive |= one << slot;
+        nf = max(nf, slot + 1);
+    }
+    st.it++;
+    return false;
+}
+
+template <int MAXV, int MAXF, int MAXE, int STRIDE>
+__device__ __forceinline__ EpaResult epaFinish(const Core& A, const Poly<MAXV, MAXF, MAXE, STRIDE>& e,
+                                               const EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st) {
+    if (st.degenerate) return epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu));
     EpaResult r;
-    r.overflow = overflow;
-    r.status = status;
-    if (overflow) {
+    r.overflow = st.overflow;
+    r.status = st.status;
+    if (st.overflow) {
         r.n = mk3(1.f, 0.f, 0.f);
         r.depth = 0.f;
         r.pa = r.pb = mk3(0.f, 0.f, 0.f);
         return r;
     }
+    const int best = st.best;
     const uint32_t fi = e.fi(best);
     const int i0 = fi & 0xffu, i1 = (fi >> 8) & 0xffu, i2 = (fi >> 16) & 0xffu;
     const float fdist = e.fd(best);
@@ -641,6 +677,18 @@ __device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const 
            pointFromId(A, e.id(i2) & 0xffffu) * lc;
     r.pb = r.pa - p;
     return r;
+}
+
+template <int MAXV, int MAXF, int MAXE, int STRIDE>
+__device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const NarrowParams& cfg, int n0,
+                                            const V3* y0, const uint32_t* id0,
+                                            const Poly<MAXV, MAXF, MAXE, STRIDE>& e) {
+    EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask> st;
+    EpaResult touching;
+    if (epaInit(A, B, n0, y0, id0, e, st, touching)) return touching;
+    while (!epaIterate(A, B, cfg, e, st)) {
+    }
+    return epaFinish(A, e, st);
 }
 
 // ---- contact record helpers ----------------------------------------------------------------------
@@ -909,71 +957,130 @@ slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairC
 constexpr int kEpaThreads = 128;
 constexpr int kEpaSmemBytes =
     Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, kEpaThreads>::kWords * kEpaThreads * (int)sizeof(float);
+constexpr int kEpaChunk = 64;        // queue items a warp claims at a time
+constexpr int kEpaBatchLanes = 8;    // refill / finalize once this many lanes wait for it
+
+// What a lane carries for the pair it is expanding.
+struct EpaLane {
+    Core A, B;
+    V3 origin;
+    uint32_t pairIdx, ia, ib, status, queueIdx;
+};
 
 template <int MAXV, int MAXF, int MAXE, int STRIDE>
-__device__ __forceinline__ bool epaOne(const EpaWork* __restrict__ wk, const uint64_t* __restrict__ pairs, int idxBits,
-                                       const float* __restrict__ xf, const uint4* __restrict__ shapes,
-                                       const float4* __restrict__ hull, const NarrowParams& cfg,
-                                       AxcdContact* __restrict__ contacts, uint32_t maxContacts,
-                                       const uint32_t* __restrict__ slots, float* __restrict__ pairDist,
-                                       Counters* __restrict__ ctr, const Poly<MAXV, MAXF, MAXE, STRIDE>& poly) {
+__device__ __forceinline__ int epaBegin(const EpaWork* __restrict__ wk, const uint64_t* __restrict__ pairs, int idxBits,
+                                        const float* __restrict__ xf, const uint4* __restrict__ shapes,
+                                        const float4* __restrict__ hull, const Poly<MAXV, MAXF, MAXE, STRIDE>& poly,
+                                        EpaLane& L, EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st,
+                                        EpaResult& touching) {
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(wk));
     const float4 f0 = __ldg(reinterpret_cast<const float4*>(wk) + 1), f1 = __ldg(reinterpret_cast<const float4*>(wk) + 2),
                  f2 = __ldg(reinterpret_cast<const float4*>(wk) + 3);
     const uint4 idv = __ldg(reinterpret_cast<const uint4*>(wk) + 4);
-    const uint32_t pairIdx = h.x;
-    const uint32_t slot = __ldg(slots + pairIdx);
-    const uint64_t pk = __ldg(pairs + pairIdx);
-    const uint32_t ia = (uint32_t)(pk >> idxBits), ib = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
+    L.pairIdx = h.x;
+    const uint64_t pk = __ldg(pairs + L.pairIdx);
+    L.ia = (uint32_t)(pk >> idxBits);
+    L.ib = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
     const int n0 = (int)(h.z & 0xffu);
-    uint32_t status = (h.z & 0x80000000u) ? (uint32_t)AXCD_ERR_GJK_NO_CONVERGE : 0u;
+    L.status = (h.z & 0x80000000u) ? (uint32_t)AXCD_ERR_GJK_NO_CONVERGE : 0u;
     const V3 y0[4] = {mk3(f0.x, f0.y, f0.z), mk3(f0.w, f1.x, f1.y), mk3(f1.z, f1.w, f2.x), mk3(f2.y, f2.z, f2.w)};
     const uint32_t id0[4] = {idv.x, idv.y, idv.z, idv.w};
-    const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
-    const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
-    const V3 origin = ta.p;
-    const Core A = makeCore(ta, sa, hull, origin);
-    const Core B = makeCore(tb, sb, hull, origin);
-    const EpaResult r = epaRun<MAXV, MAXF, MAXE, STRIDE>(A, B, cfg, n0, y0, id0, poly);
-    if (r.overflow) return false;
-    if (r.status) status = r.status;
-    const float rs = A.r + B.r;
-    const float depth = r.depth + rs;
-    const V3 pa = r.pa + r.n * A.r;
-    const V3 pb = r.pb - r.n * B.r;
-    const V3 pos = (pa + pb) * 0.5f + origin;
-    if (slot < maxContacts) storeContact(contacts + slot, ia, ib, pos, r.n, depth, status);
-    if (pairDist) pairDist[pairIdx] = (depth > 0.0f) ? -depth : 0.0f;
-    if (status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
-    if (status == AXCD_ERR_EPA_NO_CONVERGE) atomicAdd(&ctr->epaFailures, 1u);
-    return true;
+    const BodyPose ta = loadPose(xf, L.ia), tb = loadPose(xf, L.ib);
+    const uint4 sa = __ldg(shapes + L.ia), sb = __ldg(shapes + L.ib);
+    L.origin = ta.p;
+    L.A = makeCore(ta, sa, hull, L.origin);
+    L.B = makeCore(tb, sb, hull, L.origin);
+    return epaInit(L.A, L.B, n0, y0, id0, poly, st, touching);
 }
 
-// Fast path: polytope in shared memory (one column per thread).  Persistent blocks walk the queue
-// (its length is only known on the device) in 128-item chunks and re-deal each chunk to threads by
-// pair class, so a warp expands polytopes of one kind.
+__device__ __forceinline__ void epaEmit(const EpaLane& L, const EpaResult& r, AxcdContact* __restrict__ contacts,
+                                        uint32_t maxContacts, const uint32_t* __restrict__ slots,
+                                        float* __restrict__ pairDist, Counters* __restrict__ ctr) {
+    uint32_t status = L.status;
+    if (r.status) status = r.status;
+    const float rs = L.A.r + L.B.r;
+    const float depth = r.depth + rs;
+    const V3 pa = r.pa + r.n * L.A.r;
+    const V3 pb = r.pb - r.n * L.B.r;
+    const V3 pos = (pa + pb) * 0.5f + L.origin;
+    const uint32_t slot = __ldg(slots + L.pairIdx);
+    if (slot < maxContacts) storeContact(contacts + slot, L.ia, L.ib, pos, r.n, depth, status);
+    if (pairDist) pairDist[L.pairIdx] = (depth > 0.0f) ? -depth : 0.0f;
+    if (status == AXCD_ERR_GJK_NO_CONVERGE) atomicAdd(&ctr->gjkFailures, 1u);
+    if (status == AXCD_ERR_EPA_NO_CONVERGE) atomicAdd(&ctr->epaFailures, 1u);
+}
+
+// Fast path: polytope in shared memory (one column per thread).  Each lane is a small state machine
+// (EMPTY -> RUNNING -> DONE -> EMPTY): all RUNNING lanes of a warp execute one expansion step per
+// trip, and refills / finalisations are batched (>= kEpaBatchLanes lanes, or nothing else to do), so
+// a pair that needs 2 steps does not hold its lane hostage to a neighbour that needs 15.  Warps claim
+// queue items in chunks; the queue length is only known on the device.
 __global__ void __launch_bounds__(kEpaThreads)
 epaKernel(NarrowQueues q, uint32_t queueCap, const uint64_t* __restrict__ pairs, int idxBits,
           const float* __restrict__ xf, const uint4* __restrict__ shapes, const float4* __restrict__ hull,
           NarrowParams cfg, AxcdContact* __restrict__ contacts, uint32_t maxContacts,
           const uint32_t* __restrict__ slots, float* __restrict__ pairDist, Counters* __restrict__ ctr) {
     extern __shared__ float sPoly[];
-    __shared__ uint32_t sCnt[kNumClasses * (kEpaThreads / 32)];
-    __shared__ uint16_t sOrder[kEpaThreads];
     using P = Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, kEpaThreads>;
     P poly;
     poly.base = sPoly + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const uint32_t count = min(ctr->epaCount, queueCap);
-    for (uint32_t chunk = blockIdx.x * kEpaThreads; chunk < count; chunk += gridDim.x * kEpaThreads) {
-        const uint32_t mine = chunk + threadIdx.x;
-        const int cls = (mine < count) ? (int)__ldg(&q.work[mine].pad) : 0;
-        binByClass<kEpaThreads>(cls, sCnt, sOrder);
-        const uint32_t i = chunk + sOrder[threadIdx.x];
-        if (i < count && !epaOne(q.work + i, pairs, idxBits, xf, shapes, hull, cfg, contacts, maxContacts, slots, pairDist, ctr, poly)) {
-            const uint32_t o = atomicAdd(&ctr->epaOverflow, 1u);
-            q.overflow[o] = i;
+    enum { EMPTY = 0, RUNNING = 1, DONE = 2 };
+    int state = EMPTY;
+    EpaLane L;
+    EpaState<P::Mask> st;
+    uint32_t cur = 0, end = 0;   // this warp's claimed queue range (warp-uniform)
+    bool drained = false;        // no more items to claim (warp-uniform)
+    while (true) {
+        const uint32_t running = __ballot_sync(0xffffffffu, state == RUNNING);
+        const uint32_t done = __ballot_sync(0xffffffffu, state == DONE);
+        // ---- finalise finished pairs, batched ---------------------------------------------------
+        if (done && (__popc(done) >= kEpaBatchLanes || !running)) {
+            if (state == DONE) {
+                const EpaResult r = epaFinish(L.A, poly, st);
+                if (r.overflow) {
+                    const uint32_t o = atomicAdd(&ctr->epaOverflow, 1u);
+                    q.overflow[o] = L.queueIdx;   // rerun from the queue entry of this pair
+                } else {
+                    epaEmit(L, r, contacts, maxContacts, slots, pairDist, ctr);
+                }
+                state = EMPTY;
+            }
         }
-        __syncthreads();
+        // ---- refill empty lanes, batched ----------------------------------------------------------
+        const uint32_t empty = __ballot_sync(0xffffffffu, state == EMPTY);
+        if (!drained && empty && (__popc(empty) >= kEpaBatchLanes || !running)) {
+            if (cur >= end) {   // claim the next chunk for the warp
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(&ctr->epaCursor, (uint32_t)kEpaChunk);
+                cur = __shfl_sync(0xffffffffu, c, 0);
+                end = min(cur + kEpaChunk, count);
+                if (cur >= count) drained = true;
+            }
+            if (!drained) {
+                const uint32_t mine = cur + __popc(empty & ((1u << lane) - 1u));
+                if (state == EMPTY && mine < end) {
+                    EpaResult touching;
+                    L.queueIdx = mine;
+                    if (epaBegin(q.work + mine, pairs, idxBits, xf, shapes, hull, poly, L, st, touching)) {
+                        epaEmit(L, touching, contacts, maxContacts, slots, pairDist, ctr);
+                    } else {
+                        state = RUNNING;
+                    }
+                }
+                cur = min(cur + (uint32_t)__popc(empty), end);
+            }
+        }
+        // ---- one expansion step for every running lane ------------------------------------------------
+        const uint32_t nowRunning = __ballot_sync(0xffffffffu, state == RUNNING);
+        if (!nowRunning) {
+            if (drained && !__ballot_sync(0xffffffffu, state == DONE)) break;
+            continue;
+        }
+        if (state == RUNNING) {
+            if (epaIterate(L.A, L.B, cfg, poly, st)) state = DONE;
+        }
     }
 }
 
@@ -988,8 +1095,17 @@ epaFallbackKernel(NarrowQueues q, const uint64_t* __restrict__ pairs, int idxBit
     P poly;
     poly.base = store;
     const uint32_t count = ctr->epaOverflow;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
-        epaOne(q.work + q.overflow[i], pairs, idxBits, xf, shapes, hull, cfg, contacts, maxContacts, slots, pairDist, ctr, poly);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        EpaLane L;
+        EpaState<P::Mask> st;
+        EpaResult r;
+        if (!epaBegin(q.work + q.overflow[i], pairs, idxBits, xf, shapes, hull, poly, L, st, r)) {
+            while (!epaIterate(L.A, L.B, cfg, poly, st)) {
+            }
+            r = epaFinish(L.A, poly, st);
+        }
+        epaEmit(L, r, contacts, maxContacts, slots, pairDist, ctr);
+    }
 }
 
 }  // namespace axcd

@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libaxcd.so")
+# AXCD_LIB lets a tuning run point at an alternative build of the same ABI
+LIB_PATH = os.environ.get("AXCD_LIB") or os.path.join(PKG_DIR, "libaxcd.so")
 SCENE_LIB_PATH = os.path.join(PKG_DIR, "libaxcd_scene.so")
 
 SHAPE_SPHERE, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_PLANE, SHAPE_CONVEX, SHAPE_MESH = range(6)

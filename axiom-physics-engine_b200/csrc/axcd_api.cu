@@ -29,13 +29,11 @@ struct AxcdContext {
     uint32_t n = 0;          // bodies
     uint32_t nHull = 0;
     bool hasWorlds = false;
-    int idxBits = 1;         // bits of a body index inside a packed pair
     int mortonBits = 10;     // per axis
     int worldBits = 0;
     uint32_t numPairs = 0;   // pairs held (<= maxPairs)
     uint32_t foundPairs = 0; // pairs found (may exceed capacity)
     uint32_t numContacts = 0, foundContacts = 0;
-    int pairBuf = 0;         // which of pairKeys[2] holds the sorted pairs
     uint32_t launches[3] = {0, 0, 0};   // kernels launched by refit / broadphase / narrowphase
     Counters hostCtr;
     char lastErr[256] = {0};
@@ -48,13 +46,17 @@ struct AxcdContext {
     float* dAabb = nullptr;          // n * 6 floats (axiom::math::AABB AoS)
     uint32_t* dKeys[2] = {nullptr, nullptr};
     uint32_t* dVals[2] = {nullptr, nullptr};
-    float4* dLeafLo = nullptr;
-    float4* dLeafHi = nullptr;
+    float4* dSegLo = nullptr;        // segment tree over sorted leaves, heap layout, 2*P entries
+    float4* dSegHi = nullptr;
+    uint32_t segP = 0;               // leaf level size (power of two >= n)
     BvhNode* dNodes = nullptr;
-    uint32_t* dParent = nullptr;
-    uint32_t* dVisit = nullptr;
     uint32_t* dWorldEnd = nullptr;
-    uint64_t* dPairKeys[2] = {nullptr, nullptr};
+    uint2* dPairsTmp = nullptr;      // candidate pairs as found (unordered)
+    uint2* dPairs = nullptr;         // candidate pairs, canonical order
+    uint32_t* dBodyCount = nullptr;  // pairs per body a; [n, 2n) = fill cursors of the scatter
+    uint32_t* dBodyStart = nullptr;  // exclusive scan of dBodyCount
+    uint32_t* dSegB = nullptr;       // per-body segments of partner indices
+    uint32_t* dScanStatus = nullptr;
     EpaWork* dEpaWork = nullptr;     // GJK -> EPA queue (maxContacts)
     uint32_t* dEpaOverflow = nullptr;
     uint32_t* dSlotStatus = nullptr; // look-back status, one word per slot-scan tile
@@ -115,7 +117,24 @@ float evMs(AxcdContext* c, int a, int b) {
 
 uint32_t sortTilesFor(uint64_t n) { return (uint32_t)((n + kSortTile - 1) / kSortTile); }
 
+// Waits for the stream and brings the device counters (pair / contact counts) to the host.
+
+
 }  // namespace
+
+int refreshCountersImpl(AxcdContext* ctx) {
+    CU(cudaMemcpyAsync(&ctx->hostCtr, ctx->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stage >= ST_BROAD) {
+        ctx->foundPairs = ctx->hostCtr.pairCount;
+        ctx->numPairs = ctx->foundPairs < ctx->cfg.maxPairs ? ctx->foundPairs : ctx->cfg.maxPairs;
+    }
+    if (ctx->stage >= ST_NARROW) {
+        ctx->foundContacts = ctx->hostCtr.contactCount;
+        ctx->numContacts = ctx->foundContacts < ctx->cfg.maxContacts ? ctx->foundContacts : ctx->cfg.maxContacts;
+    }
+    return AXCD_OK;
+}
 
 extern "C" {
 
@@ -173,8 +192,8 @@ void axcd_destroy(AxcdContext* ctx) {
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
-                    ctx->dVals[0], ctx->dVals[1], ctx->dLeafLo, ctx->dLeafHi, ctx->dNodes, ctx->dParent,
-                    ctx->dVisit, ctx->dWorldEnd, ctx->dPairKeys[0], ctx->dPairKeys[1], ctx->dEpaWork,
+                    ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
+                    ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
                     ctx->dSortStatus, ctx->dCtr};
     for (void* b : bufs)
@@ -234,13 +253,20 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         for (int k = 0; k < 2; ++k) {
             CU(dalloc(&ctx->dKeys[k], nb));
             CU(dalloc(&ctx->dVals[k], nb));
-            CU(dalloc(&ctx->dPairKeys[k], np));
         }
-        CU(dalloc(&ctx->dLeafLo, nb));
-        CU(dalloc(&ctx->dLeafHi, nb));
+        CU(dalloc(&ctx->dPairsTmp, np));
+        CU(dalloc(&ctx->dPairs, np));
+        CU(dalloc(&ctx->dBodyCount, 2 * nb));
+        CU(dalloc(&ctx->dBodyStart, nb + 1));
+        CU(dalloc(&ctx->dSegB, np));
+        CU(dalloc(&ctx->dScanStatus, nb / kScanTile + 2));
+        {
+            size_t P = 1;
+            while (P < nb) P <<= 1;
+            CU(dalloc(&ctx->dSegLo, 2 * P));
+            CU(dalloc(&ctx->dSegHi, 2 * P));
+        }
         CU(dalloc(&ctx->dNodes, nb));
-        CU(dalloc(&ctx->dParent, 2 * nb));
-        CU(dalloc(&ctx->dVisit, nb));
         CU(dalloc(&ctx->dEpaWork, (size_t)cfg->maxContacts));
         CU(dalloc(&ctx->dEpaOverflow, (size_t)cfg->maxContacts));
         CU(dalloc(&ctx->dSlotStatus, np / kSlotTile + 2));
@@ -304,7 +330,15 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->n = n;
     ctx->nHull = nHullVerts;
-    ctx->idxBits = bitsFor(n > 1 ? n : 2);
+    {
+        uint32_t P = 1;
+        while (P < n) P <<= 1;
+        ctx->segP = P;
+        // leaf slots beyond n stay empty boxes for good; upper levels are rebuilt every step
+        fillEmptyBoxesKernel<<<(2 * P + 255) / 256, 256, 0, ctx->stream>>>(ctx->dSegLo, ctx->dSegHi, 2 * P);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->worldBits = ctx->hasWorlds ? bitsFor(ctx->cfg.numWorlds) : 0;
     // Morton resolution: ~1 bit/axis finer than one body per cell, within the 32-bit key
     {
@@ -390,36 +424,54 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         // ---- LBVH ------------------------------------------------------------------------------
         const int worldShift = 3 * ctx->mortonBits;
         const uint32_t b256 = (n + 255) / 256;
-        gatherLeavesKernel<<<b256, 256, 0, st>>>(ctx->dAabb, sVals, sKeys, ctx->dLeafLo, ctx->dLeafHi, n,
+        const uint32_t P = ctx->segP;
+        float4* leafLo = ctx->dSegLo + P;
+        float4* leafHi = ctx->dSegHi + P;
+        gatherLeavesKernel<<<b256, 256, 0, st>>>(ctx->dAabb, sVals, sKeys, leafLo, leafHi, n,
                                                  ctx->hasWorlds ? worldShift : 31);
         if (ctx->hasWorlds) markWorldEndsKernel<<<b256, 256, 0, st>>>(sKeys, n, worldShift, ctx->dWorldEnd);
-        CU(cudaMemsetAsync(ctx->dVisit, 0, sizeof(uint32_t) * n, st));
-        buildTopologyKernel<<<b256, 256, 0, st>>>(sKeys, n, ctx->dNodes, ctx->dParent);
-        fitBoxesKernel<<<b256, 256, 0, st>>>(ctx->dLeafLo, ctx->dLeafHi, n, ctx->dNodes, ctx->dParent, ctx->dVisit);
+        uint32_t segLaunches = 1;
+        {
+            const uint32_t bottomBlocks = P > (uint32_t)kSegLeaves ? P / kSegLeaves : 1;
+            segBuildBottomKernel<<<bottomBlocks, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, P);
+            uint32_t count = bottomBlocks;   // nodes in the level the bottom pass ended on
+            while (count > 1) {
+                ++segLaunches;
+                if (count <= (uint32_t)kSegLeaves) {
+                    segBuildTopKernel<<<1, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, count);
+                    count = 1;
+                } else {
+                    // a middle pass: treat the level as leaves of a smaller tree
+                    segBuildBottomKernel<<<count / kSegLeaves, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, count);
+                    count /= kSegLeaves;
+                }
+            }
+        }
+        buildTopologyKernel<<<b256, 256, 0, st>>>(sKeys, n, ctx->dSegLo, ctx->dSegHi, P, ctx->dNodes);
         CU(cudaGetLastError());
         recordEv(ctx, EV_BUILD);
         // ---- traversal ---------------------------------------------------------------------------
+        CU(cudaMemsetAsync(ctx->dBodyCount, 0, sizeof(uint32_t) * 2 * n, st));
         const uint32_t tb = (n + kTravThreads - 1) / kTravThreads;
-        findPairsKernel<<<tb, kTravThreads, 0, st>>>(ctx->dLeafLo, ctx->dLeafHi, ctx->dNodes,
-                                                     ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->idxBits,
-                                                     ctx->dPairKeys[0], ctx->cfg.maxPairs, ctx->dCtr);
+        findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes,
+                                                     ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
+                                                     ctx->cfg.maxPairs, ctx->dBodyCount, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIR);
-        // the pair count sizes the next launches
-        uint32_t found = 0;
-        CU(cudaMemcpyAsync(&found, &ctx->dCtr->pairCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        ctx->foundPairs = found;
-        ctx->numPairs = found < ctx->cfg.maxPairs ? found : ctx->cfg.maxPairs;
-        // ---- canonical order: sort packed (a,b) keys -------------------------------------------
-        const int pairPasses = (2 * ctx->idxBits + 7) / 8;
-        ctx->pairBuf = radixSort<uint64_t, false>(ctx->dPairKeys[0], ctx->dPairKeys[1], nullptr, nullptr,
-                                                  ctx->numPairs, 0, pairPasses, ctx->dSortHist, ctx->dSortStatus,
-                                                  ctx->dCtr->sortTicket, st);
+        // ---- canonical order: counting sort by body a, then tiny per-body sorts by b ------------------
+        const uint32_t scanTiles = (n + kScanTile - 1) / kScanTile;
+        CU(cudaMemsetAsync(ctx->dScanStatus, 0, sizeof(uint32_t) * (scanTiles + 1), st));
+        exclusiveScanKernel<<<scanTiles, kScanThreads, 0, st>>>(ctx->dBodyCount, ctx->dBodyStart, n, ctx->dScanStatus,
+                                                                &ctx->dCtr->scanTicket, &ctx->dCtr->storedPairs);
+        scatterPairsKernel<<<kNumSMs * 8, 256, 0, st>>>(ctx->dPairsTmp, &ctx->dCtr->pairCount, ctx->cfg.maxPairs,
+                                                        ctx->dBodyStart, ctx->dBodyCount + n, ctx->dSegB);
+        sortSegmentsKernel<<<b256, 256, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIRSORT);
-        // morton, (hist, scan, passes), gather, [worldEnds], topology, fit, traversal, (hist, scan, passes)
-        ctx->launches[1] = 1 + (2 + passes) + 1 + (ctx->hasWorlds ? 1 : 0) + 2 + 1 + (ctx->numPairs ? 2 + pairPasses : 0);
+        // no host round trip here: the narrowphase kernels read the pair count on the device
+        // morton, (hist, scan, passes), gather, [worldEnds], range tree, topology+fit, traversal, scan, scatter,
+        // segment sort
+        ctx->launches[1] = 1 + (2 + passes) + 1 + (ctx->hasWorlds ? 1 : 0) + segLaunches + 1 + 1 + 3;
     } else {
         recordEv(ctx, EV_SORT);
         recordEv(ctx, EV_BUILD);
@@ -438,9 +490,8 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
     cudaStream_t st = ctx->stream;
     recordEv(ctx, EV_N0);
     ctx->numContacts = ctx->foundContacts = 0;
-    const uint32_t np = ctx->numPairs;
-    ctx->launches[2] = np ? 4 : 0;   // GJK, slots, EPA, EPA fallback
-    if (np) {
+    ctx->launches[2] = 0;
+    if (ctx->n >= 2) {
         NarrowParams p;
         p.gjkMaxIters = ctx->cfg.gjkMaxIters;
         p.epaMaxIters = ctx->cfg.epaMaxIters;
@@ -448,29 +499,34 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         p.gjkTol = ctx->cfg.gjkTol;
         p.epaTol = ctx->cfg.epaTol;
         p.wantDistances = (ctx->cfg.flags & AXCD_FLAG_PAIR_DISTANCES) ? 1u : 0u;
-        const uint32_t tiles = (np + kGjkThreads - 1) / kGjkThreads;
-        const uint32_t slotTiles = (np + kSlotTile - 1) / kSlotTile;
-        CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * (slotTiles + 1), st));
+        // The pair count lives on the device: persistent grids sized for the capacity, capped at a
+        // few resident waves.
+        const uint32_t mp = ctx->cfg.maxPairs;
+        uint32_t tiles = (mp + kGjkThreads - 1) / kGjkThreads;
+        if (tiles > (uint32_t)kNumSMs * AXCD_GJK_MIN_BLOCKS) tiles = kNumSMs * AXCD_GJK_MIN_BLOCKS;   // one resident wave
+        const uint32_t slotTilesMax = (mp + kSlotTile - 1) / kSlotTile;
+        const uint32_t slotBlocks = slotTilesMax < (uint32_t)kNumSMs * 4 ? slotTilesMax : kNumSMs * 4;
+        CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * (slotTilesMax + 1), st));
         NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow};
-        const uint64_t* pairs = ctx->dPairKeys[ctx->pairBuf];
+        const uint2* pairs = ctx->dPairs;
         const uint32_t* pairCount = &ctx->dCtr->pairCount;
-        gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, pairCount, ctx->cfg.maxPairs, ctx->idxBits, ctx->dXf,
-                                                 ctx->dShapes, ctx->dHull, p, ctx->dFlags, ctx->dTmpContacts, q,
-                                                 ctx->cfg.maxContacts, ctx->dPairDist, ctx->dCtr);
-        slotKernel<<<slotTiles, kSlotThreads, 0, st>>>(ctx->dFlags, pairCount, ctx->cfg.maxPairs, ctx->dTmpContacts,
-                                                       ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
-                                                       ctx->dSlotStatus, ctx->dCtr);
+        gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, pairCount, mp, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+                                                 ctx->dFlags, ctx->dTmpContacts, q, ctx->cfg.maxContacts,
+                                                 ctx->dPairDist, ctx->dCtr);
+        slotKernel<<<slotBlocks, kSlotThreads, 0, st>>>(ctx->dFlags, pairCount, mp, ctx->dTmpContacts, ctx->dContacts,
+                                                        ctx->cfg.maxContacts, ctx->dSlots, ctx->dSlotStatus, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_GJK);
         // EPA: persistent grids, queue lengths are read on the device
-        epaKernel<<<kNumSMs * 2, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->idxBits, ctx->dXf,
+        epaKernel<<<kNumSMs * 2, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf,
                                                                    ctx->dShapes, ctx->dHull, p, ctx->dContacts,
                                                                    ctx->cfg.maxContacts, ctx->dSlots, ctx->dPairDist,
                                                                    ctx->dCtr);
-        epaFallbackKernel<<<kNumSMs, 64, 0, st>>>(q, pairs, ctx->idxBits, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+        epaFallbackKernel<<<kNumSMs, 64, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
                                                   ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots, ctx->dPairDist,
                                                   ctx->dCtr);
         CU(cudaGetLastError());
+        ctx->launches[2] = 4;   // GJK, slots, EPA, EPA fallback
     } else {
         recordEv(ctx, EV_GJK);
     }
@@ -483,16 +539,16 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
     if (!ctx || !out) return AXCD_ERR_NULL_POINTER;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     memset(out, 0, sizeof(*out));
-    CU(cudaMemcpyAsync(&ctx->hostCtr, ctx->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    {
+        const int rc = refreshCountersImpl(ctx);
+        if (rc) return rc;
+    }
     out->numBodies = ctx->n;
     if (ctx->stage >= ST_BROAD) {
         out->numPairs = ctx->numPairs;
         out->requiredPairs = ctx->foundPairs;
     }
     if (ctx->stage >= ST_NARROW) {
-        ctx->foundContacts = ctx->hostCtr.contactCount;
-        ctx->numContacts = ctx->foundContacts < ctx->cfg.maxContacts ? ctx->foundContacts : ctx->cfg.maxContacts;
         out->numContacts = ctx->numContacts;
         out->requiredContacts = ctx->foundContacts;
         out->numPenetrating = ctx->hostCtr.epaCount;
@@ -518,8 +574,7 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
     {
         const uint64_t n = ctx->n, np = out->numPairs, nc = out->numContacts;
         const int passes = (3 * ctx->mortonBits + ctx->worldBits + 7) / 8;
-        const int ppasses = (2 * ctx->idxBits + 7) / 8;
-        out->bytesMoved = n * 80 + n * 32 + n * (16ull * passes + 4) + np * (16ull * ppasses + 8) + np * 96 + nc * 40;
+        out->bytesMoved = n * 80 + n * 32 + n * (16ull * passes + 4) + np * 40 + np * 96 + nc * 40;
     }
     out->kernelLaunches = ctx->launches[0] + (ctx->stage >= ST_BROAD ? ctx->launches[1] : 0) +
                           (ctx->stage >= ST_NARROW ? ctx->launches[2] : 0);
@@ -553,33 +608,29 @@ int32_t axcd_get_aabbs(AxcdContext* ctx, void* outAabb24, uint32_t cap) {
 int32_t axcd_get_pairs(AxcdContext* ctx, uint32_t* outPairs2, uint32_t cap, uint32_t* outCount) {
     if (!ctx || !outCount) return AXCD_ERR_NULL_POINTER;
     if (ctx->stage < ST_BROAD) return AXCD_ERR_GPU_INVALID_OP;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    {
+        const int rc = refreshCountersImpl(ctx);
+        if (rc) return rc;
+    }
     *outCount = ctx->numPairs;
     if (ctx->numPairs == 0) return AXCD_OK;
     if (!outPairs2) return AXCD_ERR_NULL_POINTER;
     if (cap < ctx->numPairs) return AXCD_ERR_OUT_OF_RANGE;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
-    // unpack (a << idxBits | b) on the host, in place from the back (8-byte keys -> 2 x 4-byte ids)
-    uint64_t* tmp = static_cast<uint64_t*>(malloc(sizeof(uint64_t) * ctx->numPairs));
-    if (!tmp) return AXCD_ERR_OUT_OF_MEMORY;
-    cudaError_t e = cudaMemcpyAsync(tmp, ctx->dPairKeys[ctx->pairBuf], sizeof(uint64_t) * ctx->numPairs,
-                                    cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        free(tmp);
-        return fail(ctx, e, "get_pairs");
-    }
-    const uint64_t mask = (1ull << ctx->idxBits) - 1ull;
-    for (uint32_t k = 0; k < ctx->numPairs; ++k) {
-        outPairs2[2 * k] = (uint32_t)(tmp[k] >> ctx->idxBits);
-        outPairs2[2 * k + 1] = (uint32_t)(tmp[k] & mask);
-    }
-    free(tmp);
+    CU(cudaMemcpyAsync(outPairs2, ctx->dPairs, sizeof(uint2) * ctx->numPairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return AXCD_OK;
 }
 
 int32_t axcd_get_pair_distances(AxcdContext* ctx, float* outDist, uint32_t cap, uint32_t* outCount) {
     if (!ctx || !outCount) return AXCD_ERR_NULL_POINTER;
     if (ctx->stage < ST_NARROW || !ctx->dPairDist) return AXCD_ERR_GPU_INVALID_OP;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    {
+        const int rc = refreshCountersImpl(ctx);
+        if (rc) return rc;
+    }
     *outCount = ctx->numPairs;
     if (ctx->numPairs == 0) return AXCD_OK;
     if (!outDist) return AXCD_ERR_NULL_POINTER;
@@ -594,11 +645,10 @@ int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap, uint
     if (!ctx || !outCount) return AXCD_ERR_NULL_POINTER;
     if (ctx->stage < ST_NARROW) return AXCD_ERR_GPU_INVALID_OP;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
-    uint32_t found = 0;
-    CU(cudaMemcpyAsync(&found, &ctx->dCtr->contactCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->foundContacts = found;
-    ctx->numContacts = found < ctx->cfg.maxContacts ? found : ctx->cfg.maxContacts;
+    {
+        const int rc = refreshCountersImpl(ctx);
+        if (rc) return rc;
+    }
     *outCount = ctx->numContacts;
     if (ctx->numContacts == 0) return AXCD_OK;
     if (!out) return AXCD_ERR_NULL_POINTER;
@@ -633,12 +683,13 @@ int32_t axcd_test_sort_keys64(AxcdContext* ctx, uint64_t* keys, uint32_t n, uint
     if (n == 0) return AXCD_OK;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     cudaStream_t st = ctx->stream;
-    CU(cudaMemcpyAsync(ctx->dPairKeys[0], keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
-    const int sb = radixSort<uint64_t, false>(ctx->dPairKeys[0], ctx->dPairKeys[1], nullptr, nullptr, n, 0,
+    uint64_t* kb[2] = {reinterpret_cast<uint64_t*>(ctx->dPairsTmp), reinterpret_cast<uint64_t*>(ctx->dPairs)};
+    CU(cudaMemcpyAsync(kb[0], keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
+    const int sb = radixSort<uint64_t, false>(kb[0], kb[1], nullptr, nullptr, n, 0,
                                               (int)(keyBits + 7) / 8, ctx->dSortHist, ctx->dSortStatus,
                                               ctx->dCtr->sortTicket, st);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(keys, ctx->dPairKeys[sb], sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(keys, kb[sb], sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return AXCD_OK;
 }

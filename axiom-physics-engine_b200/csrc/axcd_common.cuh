@@ -84,7 +84,9 @@ struct Counters {
     uint32_t gjkTicket;      // dynamic tile ticket of the GJK kernel
     uint32_t epaOverflow;    // EPA pairs that outgrew the shared-memory polytope caps
     uint32_t epaCursor;      // next unclaimed EPA queue item
-    uint32_t pad[1];
+    uint32_t scanTicket;     // tile ticket of the body-count scan
+    uint32_t storedPairs;    // pairs actually stored (<= capacity) = total of the body-count scan
+    uint32_t pad[3];
 };
 
 }  // namespace axcd

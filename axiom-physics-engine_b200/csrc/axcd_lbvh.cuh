@@ -49,10 +49,111 @@ __device__ __forceinline__ int karrasDelta(const uint32_t* __restrict__ keys, in
     return x ? __clz(x) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
 }
 
-// One thread per internal node i in [0, n-1): finds its leaf range and split, records parents.
-// parent[] is indexed by leaf (0..n-1) then internal node (n + i); bit 31 marks "right child".
-__global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t n,
-                                    BvhNode* __restrict__ nodes, uint32_t* __restrict__ parent) {
+// ---- boxes of aligned leaf ranges (segment tree over the Morton-sorted leaves) --------------------
+// Heap layout over P = 2^k >= n leaves: node h covers the leaves of its subtree, leaves live at
+// [P, 2P) (slots >= n hold empty boxes), parents of h are h >> 1.  Any sorted range [l, r] is then the
+// union of O(log(r-l)) tree nodes, which is how buildTopologyKernel fits the LBVH boxes without
+// atomics or fences.  Unions use fminf/fmaxf so a NaN leaf box (which can never intersect anything)
+// cannot poison its ancestors.
+constexpr int kSegThreads = 256;
+constexpr int kSegLeaves = 2 * kSegThreads;   // leaves per block in the bottom pass
+
+__global__ void fillEmptyBoxesKernel(float4* __restrict__ lo, float4* __restrict__ hi, uint32_t count) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const float inf = __int_as_float(0x7f800000);
+    lo[k] = make_float4(inf, inf, inf, 0.f);
+    hi[k] = make_float4(-inf, -inf, -inf, 0.f);
+}
+
+// Reduces `width` consecutive nodes starting at heap index `base` (a whole level or a block's slice
+// of it) upward while more than `stopAt` nodes remain, writing every produced level.
+__device__ __forceinline__ void segReduceUp(float4* __restrict__ lo, float4* __restrict__ hi, uint32_t base,
+                                            uint32_t width, float (*sLo)[3], float (*sHi)[3]) {
+    // sLo/sHi hold the current level (width entries) on entry
+    uint32_t w = width, b = base;
+    while (w > 1) {
+        const uint32_t half = w >> 1;
+        __syncthreads();
+        float l0, l1, l2, h0, h1, h2;
+        const uint32_t t = threadIdx.x;
+        const bool act = t < half;
+        if (act) {
+            l0 = fminf(sLo[2 * t][0], sLo[2 * t + 1][0]);
+            l1 = fminf(sLo[2 * t][1], sLo[2 * t + 1][1]);
+            l2 = fminf(sLo[2 * t][2], sLo[2 * t + 1][2]);
+            h0 = fmaxf(sHi[2 * t][0], sHi[2 * t + 1][0]);
+            h1 = fmaxf(sHi[2 * t][1], sHi[2 * t + 1][1]);
+            h2 = fmaxf(sHi[2 * t][2], sHi[2 * t + 1][2]);
+        }
+        __syncthreads();
+        b >>= 1;
+        if (act) {
+            sLo[t][0] = l0; sLo[t][1] = l1; sLo[t][2] = l2;
+            sHi[t][0] = h0; sHi[t][1] = h1; sHi[t][2] = h2;
+            lo[b + t] = make_float4(l0, l1, l2, 0.f);
+            hi[b + t] = make_float4(h0, h1, h2, 0.f);
+        }
+        w = half;
+    }
+}
+
+// Bottom pass: each block reduces its kSegLeaves leaves up to one node.
+__global__ void __launch_bounds__(kSegThreads)
+segBuildBottomKernel(float4* __restrict__ lo, float4* __restrict__ hi, uint32_t P) {
+    __shared__ float sLo[kSegLeaves][3], sHi[kSegLeaves][3];
+    const uint32_t width = min((uint32_t)kSegLeaves, P);
+    const uint32_t base = P + blockIdx.x * kSegLeaves;
+    for (uint32_t t = threadIdx.x; t < width; t += kSegThreads) {
+        const float4 a = lo[base + t], b = hi[base + t];
+        sLo[t][0] = a.x; sLo[t][1] = a.y; sLo[t][2] = a.z;
+        sHi[t][0] = b.x; sHi[t][1] = b.y; sHi[t][2] = b.z;
+    }
+    segReduceUp(lo, hi, base, width, sLo, sHi);
+}
+
+// Top pass (one block): reduces the level holding `count` <= kSegLeaves nodes (heap base = count)
+// to the root.
+__global__ void __launch_bounds__(kSegThreads)
+segBuildTopKernel(float4* __restrict__ lo, float4* __restrict__ hi, uint32_t count) {
+    __shared__ float sLo[kSegLeaves][3], sHi[kSegLeaves][3];
+    for (uint32_t t = threadIdx.x; t < count; t += kSegThreads) {
+        const float4 a = lo[count + t], b = hi[count + t];
+        sLo[t][0] = a.x; sLo[t][1] = a.y; sLo[t][2] = a.z;
+        sHi[t][0] = b.x; sHi[t][1] = b.y; sHi[t][2] = b.z;
+    }
+    segReduceUp(lo, hi, count, count, sLo, sHi);
+}
+
+// Box of the sorted leaf range [l, r] (inclusive).
+__device__ __forceinline__ void segQuery(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t P,
+                                         uint32_t l, uint32_t r, float* out /*6*/) {
+    const float inf = __int_as_float(0x7f800000);
+    float a0 = inf, a1 = inf, a2 = inf, b0 = -inf, b1 = -inf, b2 = -inf;
+    uint32_t x = l + P, y = r + P + 1;
+    while (x < y) {
+        if (x & 1u) {
+            const float4 p = __ldg(lo + x), q = __ldg(hi + x);
+            a0 = fminf(a0, p.x); a1 = fminf(a1, p.y); a2 = fminf(a2, p.z);
+            b0 = fmaxf(b0, q.x); b1 = fmaxf(b1, q.y); b2 = fmaxf(b2, q.z);
+            ++x;
+        }
+        if (y & 1u) {
+            --y;
+            const float4 p = __ldg(lo + y), q = __ldg(hi + y);
+            a0 = fminf(a0, p.x); a1 = fminf(a1, p.y); a2 = fminf(a2, p.z);
+            b0 = fmaxf(b0, q.x); b1 = fmaxf(b1, q.y); b2 = fmaxf(b2, q.z);
+        }
+        x >>= 1;
+        y >>= 1;
+    }
+    out[0] = a0; out[1] = a1; out[2] = a2; out[3] = b0; out[4] = b1; out[5] = b2;
+}
+
+// One thread per internal node i in [0, n-1): finds its leaf range and split (Karras 2012), then
+// fits both children's boxes with two range queries and writes the finished 64-byte node.
+__global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t n, const float4* __restrict__ segLo,
+                                    const float4* __restrict__ segHi, uint32_t P, BvhNode* __restrict__ nodes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = (int)n;
     if (i >= N - 1) return;
@@ -73,46 +174,14 @@ __global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t 
     }
     const int gamma = i + s * d + min(d, 0);
     const int first = min(i, j), last = max(i, j);
-    BvhNode* nd = nodes + i;
-    nd->first = (uint32_t)first;
-    nd->split = (uint32_t)gamma;
-    nd->last = (uint32_t)last;
-    nd->pad = 0;
-    // left child: leaf gamma if first == gamma else internal gamma
-    parent[(first == gamma) ? gamma : N + gamma] = (uint32_t)i;
-    parent[(gamma + 1 == last) ? gamma + 1 : N + gamma + 1] = (uint32_t)i | 0x80000000u;
-    if (i == 0) parent[N + 0] = 0xffffffffu;   // root
-}
-
-// One thread per leaf climbs; the second arrival at a node continues with the union.  Boxes are
-// written into the parent's child slots.  Internal unions use fminf/fmaxf so a NaN leaf box (which
-// can never intersect anything) cannot poison its ancestors.
-__global__ void fitBoxesKernel(const float4* __restrict__ leafLo, const float4* __restrict__ leafHi,
-                               uint32_t n, BvhNode* __restrict__ nodes, const uint32_t* __restrict__ parent,
-                               uint32_t* __restrict__ visit) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n || n < 2) return;
-    const float4 lo = leafLo[k], hi = leafHi[k];
-    float bx0 = lo.x, by0 = lo.y, bz0 = lo.z, bx1 = hi.x, by1 = hi.y, bz1 = hi.z;
-    uint32_t p = parent[k];
-    while (true) {
-        const bool right = (p & 0x80000000u) != 0;
-        const uint32_t pi = p & 0x7fffffffu;
-        volatile float* f = reinterpret_cast<volatile float*>(nodes + pi);
-        if (!right) {
-            f[0] = bx0; f[1] = by0; f[2] = bz0; f[3] = bx1; f[4] = by1; f[5] = bz1;
-        } else {
-            f[6] = bx0; f[7] = by0; f[8] = bz0; f[9] = bx1; f[10] = by1; f[11] = bz1;
-        }
-        __threadfence();
-        if (atomicAdd(visit + pi, 1u) == 0u) return;   // first arrival: sibling not done yet
-        __threadfence();
-        const int o = right ? 0 : 6;                   // sibling's slot
-        bx0 = fminf(bx0, f[o + 0]); by0 = fminf(by0, f[o + 1]); bz0 = fminf(bz0, f[o + 2]);
-        bx1 = fmaxf(bx1, f[o + 3]); by1 = fmaxf(by1, f[o + 4]); bz1 = fmaxf(bz1, f[o + 5]);
-        p = parent[n + pi];
-        if (p == 0xffffffffu) return;   // root done
-    }
+    float L[6], R[6];
+    segQuery(segLo, segHi, P, (uint32_t)first, (uint32_t)gamma, L);
+    segQuery(segLo, segHi, P, (uint32_t)gamma + 1u, (uint32_t)last, R);
+    float4* o = reinterpret_cast<float4*>(nodes + i);
+    o[0] = make_float4(L[0], L[1], L[2], L[3]);
+    o[1] = make_float4(L[4], L[5], R[0], R[1]);
+    o[2] = make_float4(R[2], R[3], R[4], R[5]);
+    reinterpret_cast<uint4*>(o)[3] = make_uint4((uint32_t)first, (uint32_t)gamma, (uint32_t)last, 0u);
 }
 
 // ---- traversal ------------------------------------------------------------------------------------
@@ -126,12 +195,15 @@ __device__ __forceinline__ bool boxesIntersect(float ax0, float ay0, float az0, 
     return ax0 <= bx1 && ax1 >= bx0 && ay0 <= by1 && ay1 >= by0 && az0 <= bz1 && az1 >= bz0;
 }
 
-// Packed candidate pair: (min(bodyA,bodyB) << idxBits) | max(...).
+// Emits each candidate pair once as (a, b) = (min, max) of the two body indices, unordered, into
+// `pairs` (staged per block in shared memory, flushed with coalesced stores), and counts the
+// pairs of every body a in bodyCount[a] for the counting sort that follows (orderPairs*).
 __global__ void __launch_bounds__(kTravThreads)
 findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ leafHi,
                 const BvhNode* __restrict__ nodes, const uint32_t* __restrict__ worldEnd, uint32_t n,
-                int idxBits, uint64_t* __restrict__ pairs, uint32_t maxPairs, Counters* __restrict__ ctr) {
-    __shared__ uint64_t sPool[kTravPool];
+                uint2* __restrict__ pairs, uint32_t maxPairs, uint32_t* __restrict__ bodyCount,
+                Counters* __restrict__ ctr) {
+    __shared__ uint2 sPool[kTravPool];
     __shared__ uint32_t sCount, sBase;
     if (threadIdx.x == 0) sCount = 0;
     __syncthreads();
@@ -167,14 +239,16 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                     continue;
                 }
                 const uint32_t bodyJ = __float_as_uint(__ldg(&leafLo[child].w));
-                const uint32_t a = min(bodyI, bodyJ), b = max(bodyI, bodyJ);
-                const uint64_t pk = ((uint64_t)a << idxBits) | b;
+                const uint2 pr = make_uint2(min(bodyI, bodyJ), max(bodyI, bodyJ));
                 const uint32_t slot = atomicAdd(&sCount, 1u);
                 if (slot < kTravPool) {
-                    sPool[slot] = pk;
+                    sPool[slot] = pr;
                 } else {   // pool full: append directly
                     const uint32_t g = atomicAdd(&ctr->pairCount, 1u);
-                    if (g < maxPairs) pairs[g] = pk;
+                    if (g < maxPairs) {
+                        pairs[g] = pr;
+                        atomicAdd(&bodyCount[pr.x], 1u);
+                    }
                 }
             }
         }
@@ -186,7 +260,58 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
     if (cnt) {
         const uint32_t base = sBase;
         for (uint32_t k = threadIdx.x; k < cnt; k += kTravThreads)
-            if (base + k < maxPairs) pairs[base + k] = sPool[k];
+            if (base + k < maxPairs) {
+                const uint2 pr = sPool[k];
+                pairs[base + k] = pr;
+                atomicAdd(&bodyCount[pr.x], 1u);
+            }
+    }
+}
+
+// ---- canonical pair order by counting sort ---------------------------------------------------------
+// bodyStart = exclusive scan of bodyCount (done with exclusiveScanKernel).  scatterPairsKernel drops
+// every pair's b into its body-a segment (order inside a segment is arbitrary); sortSegmentsKernel
+// then sorts each segment and writes the final (a, b) list, which is thereby sorted by (a, b).
+__global__ void scatterPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount,
+                                   uint32_t maxPairs, const uint32_t* __restrict__ bodyStart,
+                                   uint32_t* __restrict__ bodyFill, uint32_t* __restrict__ segB) {
+    const uint32_t np = min(*pairCount, maxPairs);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+        const uint2 pr = pairs[k];
+        const uint32_t pos = bodyStart[pr.x] + atomicAdd(&bodyFill[pr.x], 1u);
+        segB[pos] = pr.y;
+    }
+}
+
+constexpr int kSegLocal = 32;
+
+__global__ void sortSegmentsKernel(const uint32_t* __restrict__ bodyStart, const uint32_t* __restrict__ bodyCount,
+                                   uint32_t n, uint32_t* __restrict__ segB, uint2* __restrict__ out) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint32_t start = bodyStart[a], len = bodyCount[a];
+    if (len == 0) return;
+    if (len <= kSegLocal) {
+        uint32_t v[kSegLocal];
+        for (uint32_t k = 0; k < len; ++k) v[k] = segB[start + k];
+        for (uint32_t k = 1; k < len; ++k) {   // insertion sort (segments average ~3 entries)
+            const uint32_t x = v[k];
+            int j = (int)k - 1;
+            while (j >= 0 && v[j] > x) {
+                v[j + 1] = v[j];
+                --j;
+            }
+            v[j + 1] = x;
+        }
+        for (uint32_t k = 0; k < len; ++k) out[start + k] = make_uint2(a, v[k]);
+    } else {
+        // long segment (a body touching > 32 others): rank each element by counting smaller ones
+        for (uint32_t k = 0; k < len; ++k) {
+            const uint32_t x = segB[start + k];
+            uint32_t r = 0;
+            for (uint32_t m = 0; m < len; ++m) r += (segB[start + m] < x) ? 1u : 0u;
+            out[start + r] = make_uint2(a, x);   // b values within a segment are distinct
+        }
     }
 }
 

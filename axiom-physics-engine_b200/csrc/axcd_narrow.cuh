@@ -716,7 +716,10 @@ struct NarrowQueues {
 };
 
 // ---- kernel 1: GJK over every candidate pair -------------------------------------------------------
-constexpr int kGjkThreads = 256;
+#ifndef AXCD_GJK_THREADS
+#define AXCD_GJK_THREADS 128
+#endif
+constexpr int kGjkThreads = AXCD_GJK_THREADS;
 constexpr int kNumClasses = 6;
 
 // Pair class by core kinds, so that a warp runs one kind of support function.
@@ -758,9 +761,12 @@ __device__ __forceinline__ void binByClass(int cls, uint32_t* sCnt, uint16_t* sO
 // the support function.  Per pair it writes flag[k]: 0 = no contact, 1 = shallow contact (cores
 // apart, radii overlapping; record written to tmp[k]), 2 = cores overlap (EpaWork queued; EPA
 // writes the record).  Contact slots are assigned afterwards, in pair order, by slotKernel.
-__global__ void __launch_bounds__(kGjkThreads, 2)
-gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
-          int idxBits, const float* __restrict__ xf, const uint4* __restrict__ shapes,
+#ifndef AXCD_GJK_MIN_BLOCKS
+#define AXCD_GJK_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(kGjkThreads, AXCD_GJK_MIN_BLOCKS)
+gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
+          const float* __restrict__ xf, const uint4* __restrict__ shapes,
           const float4* __restrict__ hull, NarrowParams cfg, uint8_t* __restrict__ flags,
           AxcdContact* __restrict__ tmp, NarrowQueues q, uint32_t queueCap, float* __restrict__ pairDist,
           Counters* __restrict__ ctr) {
@@ -769,14 +775,16 @@ gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairC
     __shared__ uint32_t sA[kGjkThreads], sB[kGjkThreads];
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t npairs = min(*pairCount, maxPairs);
-    const uint32_t tileBase = blockIdx.x * kGjkThreads;
+    // persistent blocks: the pair count is only known on the device
+    for (uint32_t tileBase = blockIdx.x * kGjkThreads; tileBase < npairs; tileBase += gridDim.x * kGjkThreads) {
+    __syncthreads();   // sA/sB/sOrder of the previous tile are no longer in use
 
     // ---- deal the tile's pairs to threads by class -----------------------------------------------
     {
         int cls = 0;
         if (tileBase + tid < npairs) {
-            const uint64_t pk = pairs[tileBase + tid];
-            const uint32_t a = (uint32_t)(pk >> idxBits), b = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
+            const uint2 pk = pairs[tileBase + tid];
+            const uint32_t a = pk.x, b = pk.y;
             sA[tid] = a;
             sB[tid] = b;
             cls = pairClass(__ldg(&shapes[a].x), __ldg(&shapes[b].x));
@@ -785,7 +793,7 @@ gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairC
     }
     const int j = sOrder[tid];           // local index of the pair this thread works on
     const uint32_t k = tileBase + j;     // its global pair index
-    if (k >= npairs) return;
+    if (k >= npairs) continue;
 
     // ---- per-pair GJK ----------------------------------------------------------------------------
     int kind = 0;
@@ -861,6 +869,7 @@ gjkKernel(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ pairC
             o[4] = make_uint4(s.id[0], s.id[1], s.id[2], s.id[3]);
         }
     }
+    }   // tile loop
 }
 
 // ---- kernel 1b: contact slots in pair order ------------------------------------------------------------
@@ -878,10 +887,13 @@ slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairC
     __shared__ uint32_t sWarp[kSlotThreads / 32];
     __shared__ uint32_t sTile, sBase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t npairs = min(*pairCount, maxPairs);
+    while (true) {   // persistent blocks take ticketed tiles until the pairs run out
+    __syncthreads();
     if (tid == 0) sTile = atomicAdd(&ctr->gjkTicket, 1u);
     __syncthreads();
     const uint32_t tile = sTile;
-    const uint32_t npairs = min(*pairCount, maxPairs);
+    if ((uint64_t)tile * kSlotTile >= npairs) break;
     const uint32_t base = tile * kSlotTile + tid * kSlotItems;
     // 8 one-byte flags per thread: one 8-byte load (flags buffer is padded to a tile multiple)
     const uint2 fl = (base < npairs) ? __ldg(reinterpret_cast<const uint2*>(flags + base)) : make_uint2(0u, 0u);
@@ -951,6 +963,7 @@ slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairC
         }
         ++run;
     }
+    }   // tile loop
 }
 
 // ---- kernel 2: EPA over the queued pairs -------------------------------------------------------------
@@ -968,7 +981,7 @@ struct EpaLane {
 };
 
 template <int MAXV, int MAXF, int MAXE, int STRIDE>
-__device__ __forceinline__ int epaBegin(const EpaWork* __restrict__ wk, const uint64_t* __restrict__ pairs, int idxBits,
+__device__ __forceinline__ int epaBegin(const EpaWork* __restrict__ wk, const uint2* __restrict__ pairs,
                                         const float* __restrict__ xf, const uint4* __restrict__ shapes,
                                         const float4* __restrict__ hull, const Poly<MAXV, MAXF, MAXE, STRIDE>& poly,
                                         EpaLane& L, EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st,
@@ -978,9 +991,9 @@ __device__ __forceinline__ int epaBegin(const EpaWork* __restrict__ wk, const ui
                  f2 = __ldg(reinterpret_cast<const float4*>(wk) + 3);
     const uint4 idv = __ldg(reinterpret_cast<const uint4*>(wk) + 4);
     L.pairIdx = h.x;
-    const uint64_t pk = __ldg(pairs + L.pairIdx);
-    L.ia = (uint32_t)(pk >> idxBits);
-    L.ib = (uint32_t)(pk & ((1ull << idxBits) - 1ull));
+    const uint2 pk = __ldg(pairs + L.pairIdx);
+    L.ia = pk.x;
+    L.ib = pk.y;
     const int n0 = (int)(h.z & 0xffu);
     L.status = (h.z & 0x80000000u) ? (uint32_t)AXCD_ERR_GJK_NO_CONVERGE : 0u;
     const V3 y0[4] = {mk3(f0.x, f0.y, f0.z), mk3(f0.w, f1.x, f1.y), mk3(f1.z, f1.w, f2.x), mk3(f2.y, f2.z, f2.w)};
@@ -1016,7 +1029,7 @@ __device__ __forceinline__ void epaEmit(const EpaLane& L, const EpaResult& r, Ax
 // a pair that needs 2 steps does not hold its lane hostage to a neighbour that needs 15.  Warps claim
 // queue items in chunks; the queue length is only known on the device.
 __global__ void __launch_bounds__(kEpaThreads)
-epaKernel(NarrowQueues q, uint32_t queueCap, const uint64_t* __restrict__ pairs, int idxBits,
+epaKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs,
           const float* __restrict__ xf, const uint4* __restrict__ shapes, const float4* __restrict__ hull,
           NarrowParams cfg, AxcdContact* __restrict__ contacts, uint32_t maxContacts,
           const uint32_t* __restrict__ slots, float* __restrict__ pairDist, Counters* __restrict__ ctr) {
@@ -1063,7 +1076,7 @@ epaKernel(NarrowQueues q, uint32_t queueCap, const uint64_t* __restrict__ pairs,
                 if (state == EMPTY && mine < end) {
                     EpaResult touching;
                     L.queueIdx = mine;
-                    if (epaBegin(q.work + mine, pairs, idxBits, xf, shapes, hull, poly, L, st, touching)) {
+                    if (epaBegin(q.work + mine, pairs, xf, shapes, hull, poly, L, st, touching)) {
                         epaEmit(L, touching, contacts, maxContacts, slots, pairDist, ctr);
                     } else {
                         state = RUNNING;
@@ -1086,7 +1099,7 @@ epaKernel(NarrowQueues q, uint32_t queueCap, const uint64_t* __restrict__ pairs,
 
 // Full-cap path for the few pairs whose polytope outgrew the shared-memory caps.
 __global__ void __launch_bounds__(64)
-epaFallbackKernel(NarrowQueues q, const uint64_t* __restrict__ pairs, int idxBits, const float* __restrict__ xf,
+epaFallbackKernel(NarrowQueues q, const uint2* __restrict__ pairs, const float* __restrict__ xf,
                   const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
                   AxcdContact* __restrict__ contacts, uint32_t maxContacts, const uint32_t* __restrict__ slots,
                   float* __restrict__ pairDist, Counters* __restrict__ ctr) {
@@ -1099,7 +1112,7 @@ epaFallbackKernel(NarrowQueues q, const uint64_t* __restrict__ pairs, int idxBit
         EpaLane L;
         EpaState<P::Mask> st;
         EpaResult r;
-        if (!epaBegin(q.work + q.overflow[i], pairs, idxBits, xf, shapes, hull, poly, L, st, r)) {
+        if (!epaBegin(q.work + q.overflow[i], pairs, xf, shapes, hull, poly, L, st, r)) {
             while (!epaIterate(L.A, L.B, cfg, poly, st)) {
             }
             r = epaFinish(L.A, poly, st);

@@ -102,6 +102,29 @@ def test_c1_100k_single_scene():
     assert bitwise
 
 
+def test_traversal_heavy_tailed_sizes():
+    # a few huge boxes among many small ones (deep, unbalanced overlap structure)
+    rng = np.random.default_rng(7)
+    n = 20000
+    pos = rng.uniform(0, 30, (n, 3)).astype(np.float32)
+    h = (rng.uniform(0.05, 1.0, (n, 3)) ** 4 * 8 + 0.05).astype(np.float32)
+    xf = np.zeros((n, 10), np.float32)
+    xf[:, :3] = pos
+    xf[:, 6] = 1.0
+    xf[:, 7:] = 1.0
+    shapes = np.zeros(n, axcd.SHAPE_DT)
+    shapes["type"] = 1
+    shapes["p0"], shapes["p1"], shapes["p2"] = h[:, 0], h[:, 1], h[:, 2]
+    s = axcd.Scene(xf, shapes)
+    w = axcd.CollisionWorld.for_scene(s, pairs_per_body=400)
+    st = w.step()
+    rc, bb = O.refit(s.xf, s.shapes)
+    pairs = O.broadphase(bb, nthreads=8)
+    assert st.numPairs == len(pairs)
+    assert np.array_equal(w.pairs(), pairs)
+    w.close()
+
+
 def test_c2_hull_mix_epa_heavy_scaled():
     st, bitwise = run_and_compare(axcd.config_scene("C2", scale=0.05))
     assert st.numPenetrating > 0.2 * st.numPairs

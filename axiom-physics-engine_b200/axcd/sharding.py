@@ -1,0 +1,215 @@
+"""Multi-GPU sharding of the collision path; host-side logic only.
+
+Two modes, both one process per GPU with ``torch.distributed`` as plumbing:
+
+* **Independent worlds** (config C3, or one scene per rank): ``shard_worlds`` gives rank r the
+  worlds ``[r*W/R, (r+1)*W/R)``.  No data-path collective exists or is needed.
+* **One huge scene** (config C4): 1-D slab decomposition along x.  ``plan_slabs`` picks equal-count
+  splitters from the AABB centres; every rank then needs all bodies whose x-interval meets its slab
+  (its own plus *ghosts*), which ``exchange_ghosts`` moves with point-to-point sends (NCCL over
+  NVLink on GPUs, gloo in the CPU tests).  De-duplication rule: a pair (i, j) is reported by the
+  rank whose slab contains ``x* = max(min_i.x, min_j.x)`` — the left end of the pair's x-overlap.
+  Both x-intervals contain x*, so both bodies are present on that rank, and slabs partition the
+  axis, so exactly one rank reports each pair.
+
+Everything here works on numpy arrays; the per-rank compute is whatever collision backend the
+caller plugs in (the CUDA ``CollisionWorld`` on GPUs, the CPU oracle in the gloo tests).
+"""
+import numpy as np
+
+from . import SHAPE_CONVEX, SHAPE_DT, Scene
+
+
+# ---------------------------------------------------------------------------------------------
+# independent worlds
+# ---------------------------------------------------------------------------------------------
+def world_range(num_worlds, rank, size):
+    return rank * num_worlds // size, (rank + 1) * num_worlds // size
+
+
+def _subset(scene, idx, world_id=None, num_worlds=1):
+    """Scene restricted to bodies idx (hull vertex ranges are re-packed)."""
+    shapes = scene.shapes[idx].copy()
+    hull_parts, used = [], 0
+    is_hull = shapes["type"] == SHAPE_CONVEX
+    if is_hull.any():
+        first = shapes["p0"].view(np.uint32)
+        count = shapes["p1"].view(np.uint32)
+        new_first = first.copy()
+        for k in np.nonzero(is_hull)[0]:
+            hull_parts.append(scene.hull[first[k]:first[k] + count[k]])
+            new_first[k] = used
+            used += int(count[k])
+        shapes["p0"] = new_first.view(np.float32)
+    hull = np.concatenate(hull_parts) if hull_parts else np.zeros((0, 3), np.float32)
+    return Scene(scene.xf[idx], shapes, hull, world_id, num_worlds, scene.name)
+
+
+def shard_worlds(scene, rank, size):
+    """Returns (local_scene, global_index_of_local_body)."""
+    lo, hi = world_range(scene.num_worlds, rank, size)
+    idx = np.nonzero((scene.world_id >= lo) & (scene.world_id < hi))[0]
+    local = _subset(scene, idx, scene.world_id[idx] - lo, max(1, hi - lo))
+    return local, idx.astype(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------
+# slab decomposition of one scene
+# ---------------------------------------------------------------------------------------------
+def plan_slabs(center_x, size):
+    """Equal-count splitters on the centre x coordinate: slab r = [edges[r], edges[r+1])."""
+    cx = np.sort(np.asarray(center_x, dtype=np.float64))
+    cx = cx[np.isfinite(cx)]
+    edges = np.empty(size + 1, np.float64)
+    edges[0], edges[-1] = -np.inf, np.inf
+    for r in range(1, size):
+        edges[r] = cx[min(len(cx) - 1, r * len(cx) // size)] if len(cx) else 0.0
+    return edges
+
+
+def owner_of(center_x, edges):
+    """Rank owning each body: the slab that contains its AABB centre (NaN -> rank 0)."""
+    cx = np.nan_to_num(np.asarray(center_x, np.float64), nan=-np.inf)
+    return np.clip(np.searchsorted(edges, cx, side="right") - 1, 0, len(edges) - 2).astype(np.int32)
+
+
+def slab_mask(aabb, edges, r):
+    """Bodies whose closed x-interval [min.x, max.x] meets the half-open slab r."""
+    return (aabb[:, 0] < edges[r + 1]) & (aabb[:, 3] >= edges[r])
+
+
+def _pack(scene, idx, gid):
+    """Flat float32 payload for bodies idx: per body 10 xf + 4 shape words + 1 id, then hull xyz."""
+    sub = _subset(scene, idx)
+    body = np.zeros((len(idx), 15), np.float32)
+    body[:, :10] = sub.xf
+    body[:, 10:14] = sub.shapes.view(np.float32).reshape(-1, 4)
+    body[:, 14] = gid[idx].astype(np.uint32).view(np.float32)
+    header = np.array([len(idx), len(sub.hull)], np.uint32).view(np.float32)
+    return np.concatenate([header, body.ravel(), sub.hull.ravel()]).astype(np.float32)
+
+
+def _unpack(buf):
+    nb, nh = buf[:2].view(np.uint32)
+    body = buf[2:2 + 15 * nb].reshape(nb, 15)
+    hull = buf[2 + 15 * nb:2 + 15 * nb + 3 * nh].reshape(nh, 3)
+    shapes = np.ascontiguousarray(body[:, 10:14]).view(SHAPE_DT).reshape(-1)
+    return body[:, :10].copy(), shapes.copy(), hull.copy(), body[:, 14].copy().view(np.uint32)
+
+
+def exchange_ghosts(owned, owned_gid, owned_aabb, edges, rank, size, dist=None, device="cpu"):
+    """Sends every owned body to each other rank whose slab its x-interval meets; returns the
+    local scene (owned + ghosts, ordered by global id) and the global id of each local body.
+
+    ``dist`` is ``torch.distributed`` (initialised) or None for a single process."""
+    parts = [(owned.xf, owned.shapes, owned.hull, owned_gid)]
+    if size > 1:
+        import torch
+        payloads = {}
+        for r in range(size):
+            if r == rank:
+                continue
+            idx = np.nonzero(slab_mask(owned_aabb, edges, r))[0]
+            payloads[r] = _pack(owned, idx, owned_gid)
+        # sizes first (one all_gather), then pairwise non-blocking sends / receives
+        my_sizes = torch.zeros(size, dtype=torch.int64, device=device)
+        for r, p in payloads.items():
+            my_sizes[r] = len(p)
+        all_sizes = [torch.zeros(size, dtype=torch.int64, device=device) for _ in range(size)]
+        dist.all_gather(all_sizes, my_sizes)
+        recv = {r: torch.empty(int(all_sizes[r][rank]), dtype=torch.float32, device=device)
+                for r in range(size) if r != rank}
+        send = {r: torch.from_numpy(p).to(device) for r, p in payloads.items()}
+        reqs = []
+        for r in range(size):
+            if r == rank:
+                continue
+            reqs.append(dist.isend(send[r], dst=r))
+            reqs.append(dist.irecv(recv[r], src=r))
+        for q in reqs:
+            q.wait()
+        for r in sorted(recv):
+            parts.append(_unpack(recv[r].cpu().numpy()))
+    xf = np.concatenate([p[0] for p in parts])
+    shapes = np.concatenate([p[1] for p in parts])
+    gid = np.concatenate([p[3] for p in parts]).astype(np.uint32)
+    # re-base hull ranges of the appended parts
+    hull_parts, used, off = [], 0, 0
+    for p in parts:
+        nb = len(p[0])
+        is_hull = shapes["type"][off:off + nb] == SHAPE_CONVEX
+        if is_hull.any():
+            first = shapes["p0"][off:off + nb].view(np.uint32)
+            first[is_hull] += used
+        hull_parts.append(p[2])
+        used += len(p[2])
+        off += nb
+    hull = np.concatenate(hull_parts) if hull_parts else np.zeros((0, 3), np.float32)
+    # local index order = global id order, so every pair is evaluated with the same body in the
+    # "A" role as in a single-process run (contact floats then match bit for bit)
+    order = np.argsort(gid, kind="stable")
+    return Scene(xf[order], shapes[order], hull, name=owned.name), gid[order]
+
+
+def filter_pairs_for_rank(pairs_local, local_aabb, local_gid, edges, rank):
+    """Keeps the local pairs this rank must report (x* rule) and returns them as canonical
+    (a<b, sorted) GLOBAL id pairs plus the boolean mask over pairs_local."""
+    if len(pairs_local) == 0:
+        return np.zeros((0, 2), np.uint32), np.zeros(0, bool)
+    i, j = pairs_local[:, 0], pairs_local[:, 1]
+    xs = np.maximum(local_aabb[i, 0], local_aabb[j, 0]).astype(np.float64)
+    keep = (xs >= edges[rank]) & (xs < edges[rank + 1])
+    gi, gj = local_gid[i[keep]], local_gid[j[keep]]
+    a, b = np.minimum(gi, gj), np.maximum(gi, gj)
+    order = np.lexsort((b, a))
+    return np.stack([a[order], b[order]], axis=1).astype(np.uint32), keep
+
+
+class CudaBackend:
+    """Per-rank collision backend on this rank's GPU (the product path: CollisionWorld over the C ABI)."""
+
+    def __init__(self, device=0, pairs_per_body=8):
+        self.device = device
+        self.pairs_per_body = pairs_per_body
+
+    def refit(self, scene):
+        from . import CollisionWorld
+        w = CollisionWorld.for_scene(scene, pairs_per_body=self.pairs_per_body, device=self.device)
+        w.refit()
+        bb = w.aabbs()
+        w.close()
+        return bb
+
+    def step(self, scene):
+        from . import CollisionWorld
+        w = CollisionWorld.for_scene(scene, pairs_per_body=self.pairs_per_body, device=self.device)
+        w.step()
+        out = (w.aabbs(), w.pairs().copy(), w.contacts().copy())
+        w.close()
+        return out
+
+
+def slab_step(scene_owned, owned_gid, edges, rank, size, backend, dist=None, device="cpu"):
+    """One sharded broadphase+narrowphase step.
+
+    backend(scene) -> (aabb (n,6), pairs (m,2) local canonical, contacts structured array) is the
+    per-rank collision implementation.  Returns (global pairs this rank reports, their contacts
+    with global ids)."""
+    owned_aabb = backend.refit(scene_owned)
+    local, gid = exchange_ghosts(scene_owned, owned_gid, owned_aabb, edges, rank, size, dist, device)
+    aabb, pairs, contacts = backend.step(local)
+    gp, keep = filter_pairs_for_rank(pairs, aabb, gid, edges, rank)
+    # contacts follow the same rule, keyed by their pair
+    if len(contacts):
+        kept = {(int(a), int(b)) for a, b in pairs[keep]}
+        cm = np.array([(int(a), int(b)) in kept for a, b in zip(contacts["a"], contacts["b"])], bool)
+        c = contacts[cm].copy()
+        ga, gb = gid[c["a"]], gid[c["b"]]
+        swap = ga > gb
+        c["a"], c["b"] = np.minimum(ga, gb), np.maximum(ga, gb)
+        for f in ("nx", "ny", "nz"):   # normal points from a to b: flip when the ids swap order
+            c[f] = np.where(swap, -c[f], c[f])
+        c = c[np.lexsort((c["b"], c["a"]))]
+    else:
+        c = contacts
+    return gp, c

@@ -1,0 +1,46 @@
+// Drives the C++ façade (include/axiom/collision/collision_world.hpp) the way the reference's
+// PhysicsWorld::step would (CLAUDE.md:162-178).  Prints "pairs contacts"; exit code 0 on success,
+// 77 when no CUDA device is present (so the CPU-only test can tell "linked fine" from "failed").
+#include "axiom/collision/collision_world.hpp"
+#include "axcd_scene.h"
+
+#include <cstdio>
+#include <vector>
+
+using namespace axiom;
+
+int main() {
+    const std::uint32_t n = 1000;   // config C0: seed 1, L = 10, 50/50 boxes and spheres
+    AxcdSceneSpec spec{n, 0.5f, 0.5f, 10.0f, 0.25f, 0.5f, 16, 1};
+    std::vector<math::Transform> xf(n);
+    std::vector<collision::Shape> shapes(n);
+    std::uint32_t hullUsed = 0;
+    if (axcd_scene_generate(&spec, reinterpret_cast<float*>(xf.data()), shapes.data(), nullptr, 0, 0, &hullUsed) != 0)
+        return 2;
+
+    collision::CollisionConfig cfg;
+    cfg.maxBodies = n;
+    cfg.maxPairs = 16 * n;
+    cfg.maxContacts = 16 * n;
+    auto created = collision::CollisionWorld::create(cfg);
+    if (created.isFailure()) {
+        std::printf("create failed: %d %s\n", static_cast<int>(created.errorCode()), created.errorMessage());
+        return created.errorCode() == core::ErrorCode::VulkanInitializationFailed ? 77 : 3;
+    }
+    auto& world = *created.value();
+    if (world.setShapes(shapes.data(), n).isFailure()) return 4;
+    if (world.setTransforms(xf.data(), n).isFailure()) return 5;
+    collision::Broadphase broadphase(world);
+    collision::Narrowphase narrowphase(world);
+    if (broadphase.update().isFailure()) return 6;
+    const std::uint32_t pairs = broadphase.getPairCount();
+    if (narrowphase.detectCollisions().isFailure()) return 7;
+    const std::uint32_t contacts = narrowphase.getContactCount();
+    std::vector<collision::ContactPoint> out(contacts ? contacts : 1);
+    auto got = world.getContacts(out.data(), static_cast<std::uint32_t>(out.size()));
+    if (got.isFailure() || got.value() != contacts) return 8;
+    for (std::uint32_t k = 0; k < contacts; ++k)
+        if (!(out[k].a < out[k].b) || !(out[k].depth >= 0.0f)) return 9;
+    std::printf("%u %u\n", pairs, contacts);
+    return 0;
+}

@@ -1,0 +1,34 @@
+"""The C++20 façade (include/axiom/collision/collision_world.hpp) compiles against the C ABI and
+behaves like the documented Broadphase/Narrowphase call shape (reference: CLAUDE.md:162-178)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "axiom-physics-engine_b200")
+EXE = os.path.join(PKG, "facade_smoke")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", PKG, "facade_smoke"], stdout=subprocess.DEVNULL)
+
+
+def test_facade_links_and_refuses_without_device():
+    import torch
+    _build()
+    r = subprocess.run([EXE], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        # no device: create() must fail with the GPU-init code, never fall back to a CPU path
+        assert r.returncode == 77, r.stdout + r.stderr
+        assert "500" in r.stdout
+
+
+@pytest.mark.gpu
+def test_facade_c0_counts():
+    _build()
+    r = subprocess.run([EXE], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split() == ["2875", "1381"]   # C0 fixture: candidate pairs, contacts

@@ -455,7 +455,8 @@ __device__ __forceinline__ EpaResult epaTouching(V3 n, V3 pa) {
 // storage cap sets `overflow` and the caller reruns the pair on the full-cap path.
 template <class Mask>
 struct EpaState {
-    int nv, nf, best;
+    int nv, nf, best;  // best = closest alive face (lowest slot on ties), bd its plane distance
+    float bd;
     Mask alive;        // bit f set = face slot f is part of the polytope
     uint32_t it, status;
     bool overflow, degenerate;
@@ -541,7 +542,15 @@ __device__ __forceinline__ int epaInit(const Core& A, const Core& B, int n0, con
     epaSetFace(e, 3, 1, 3, 2);
     st.nv = nv;
     st.nf = 4;
-    st.best = 0;
+    st.best = -1;
+    st.bd = FLT_MAX;
+    for (int i = 0; i < 4; ++i) {
+        const float di = e.fd(i);
+        if (di < st.bd) {
+            st.bd = di;
+            st.best = i;
+        }
+    }
     st.alive = 0xf;
     st.it = 0;
     st.status = 0;
@@ -562,15 +571,7 @@ __device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const N
     int& nf = st.nf;
     int& best = st.best;
     Mask& alive = st.alive;
-    best = -1;
-    float bd = FLT_MAX;
-    for (int i = 0; i < nf; ++i) {
-        const float di = e.fd(i);
-        if (((alive >> i) & one) && di < bd) {
-            bd = di;
-            best = i;
-        }
-    }
+    const float bd = st.bd;   // closest face: found while the previous step scanned the faces
     if (best < 0) {   // every face degenerate: give up on this polytope
         st.degenerate = true;
         return true;
@@ -592,9 +593,19 @@ __device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const N
     const float wl = fabsf(w.x) + fabsf(w.y) + fabsf(w.z);
     const float visEps = 1e-6f * ((wl > 1.0f) ? wl : 1.0f);
     Mask vis = 0;
+    int nbest = -1;          // closest face among those that survive this step
+    float nbd = FLT_MAX;
     for (int i = 0; i < nf; ++i) {
-        const bool v = dot3(e.fn(i), w) - e.fd(i) > visEps;
-        if (v && ((alive >> i) & one)) vis |= one << i;
+        const float di = e.fd(i);
+        const bool v = dot3(e.fn(i), w) - di > visEps;
+        if ((alive >> i) & one) {
+            if (v) {
+                vis |= one << i;
+            } else if (di < nbd) {
+                nbd = di;
+                nbest = i;
+            }
+        }
     }
     // directed edges of the visible faces, as one bit row per start vertex
     e.clearRows(nv);
@@ -646,7 +657,14 @@ __device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const N
         epaSetFace(e, slot, (int)(ed & 0xffu), (int)(ed >> 8), wi);
         alive |= one << slot;
         nf = max(nf, slot + 1);
+        const float di = e.fd(slot);   // the closest face is the lowest slot among the minima
+        if (di < nbd || (di == nbd && slot < nbest)) {
+            nbd = di;
+            nbest = slot;
+        }
     }
+    best = nbest;
+    st.bd = nbd;
     st.it++;
     return false;
 }
@@ -885,6 +903,7 @@ slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairC
            const AxcdContact* __restrict__ tmp, AxcdContact* __restrict__ contacts, uint32_t maxContacts,
            uint32_t* __restrict__ slots, volatile uint32_t* __restrict__ tileStatus, Counters* __restrict__ ctr) {
     __shared__ uint32_t sWarp[kSlotThreads / 32];
+    __shared__ uint32_t sSlotOut[kSlotTile];
     __shared__ uint32_t sTile, sBase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t npairs = min(*pairCount, maxPairs);
@@ -949,19 +968,29 @@ slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairC
         }
     }
     __syncthreads();
+    // hand the per-pair results to a striped mapping (consecutive lanes = consecutive pairs) so the
+    // slot stores and the 40-byte record moves coalesce
     uint32_t run = sBase + warpPrefix + inc - sum;
 #pragma unroll
     for (int i = 0; i < kSlotItems; ++i) {
-        if (!f[i]) continue;
-        const uint32_t k = base + i;
-        slots[k] = run;
-        if (f[i] == 1u && run < maxContacts) {
+        sSlotOut[tid * kSlotItems + i] = f[i] ? (run | (f[i] << 30)) : 0xffffffffu;   // slot < 2^30
+        run += f[i] ? 1u : 0u;
+    }
+    __syncthreads();
+    const uint32_t tileBase = tile * kSlotTile;
+#pragma unroll
+    for (int i = 0; i < kSlotItems; ++i) {
+        const uint32_t local = i * kSlotThreads + tid;
+        const uint32_t v = sSlotOut[local];
+        if (v == 0xffffffffu) continue;
+        const uint32_t k = tileBase + local, slot = v & 0x3fffffffu;
+        slots[k] = slot;
+        if ((v >> 30) == 1u && slot < maxContacts) {
             const float2* src = reinterpret_cast<const float2*>(tmp + k);
-            float2* dst = reinterpret_cast<float2*>(contacts + run);
+            float2* dst = reinterpret_cast<float2*>(contacts + slot);
 #pragma unroll
             for (int w = 0; w < 5; ++w) dst[w] = src[w];
         }
-        ++run;
     }
     }   // tile loop
 }

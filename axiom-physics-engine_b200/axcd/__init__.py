@@ -19,6 +19,7 @@ SCENE_LIB_PATH = os.path.join(PKG_DIR, "libaxcd_scene.so")
 
 SHAPE_SPHERE, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_PLANE, SHAPE_CONVEX, SHAPE_MESH = range(6)
 FLAG_PAIR_DISTANCES = 1
+FLAG_EPA_COOPERATIVE = 2
 
 SHAPE_DT = np.dtype([("type", "<u4"), ("p0", "<f4"), ("p1", "<f4"), ("p2", "<f4")])
 CONTACT_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),

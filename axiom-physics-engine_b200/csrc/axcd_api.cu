@@ -8,6 +8,7 @@
 #include "axcd.h"
 #include "axcd_common.cuh"
 #include "axcd_lbvh.cuh"
+#include "axcd_epa_coop.cuh"
 #include "axcd_narrow.cuh"
 #include "axcd_refit.cuh"
 #include "axcd_sort.cuh"
@@ -518,10 +519,16 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         CU(cudaGetLastError());
         recordEv(ctx, EV_GJK);
         // EPA: persistent grids, queue lengths are read on the device
-        epaKernel<<<kNumSMs * 2, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf,
-                                                                   ctx->dShapes, ctx->dHull, p, ctx->dContacts,
-                                                                   ctx->cfg.maxContacts, ctx->dSlots, ctx->dPairDist,
-                                                                   ctx->dCtr);
+        if (!(ctx->cfg.flags & AXCD_FLAG_EPA_COOPERATIVE)) {
+            epaKernel<<<kNumSMs * 2, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf,
+                                                                       ctx->dShapes, ctx->dHull, p, ctx->dContacts,
+                                                                       ctx->cfg.maxContacts, ctx->dSlots,
+                                                                       ctx->dPairDist, ctx->dCtr);
+        } else {
+            epaCoopKernel<<<kNumSMs * 3, kCoopThreads, 0, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf, ctx->dShapes,
+                                                                ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts,
+                                                                ctx->dSlots, ctx->dPairDist, ctx->dCtr);
+        }
         epaFallbackKernel<<<kNumSMs, 64, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
                                                   ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots, ctx->dPairDist,
                                                   ctx->dCtr);

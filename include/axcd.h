@@ -104,7 +104,11 @@ enum {
     /* Also write the GJK distance of every candidate pair (0 for contacts) so that
      * axcd_get_pair_distances works.  Off by default: separated pairs then stop at the first
      * separating axis.                                                                          */
-    AXCD_FLAG_PAIR_DISTANCES = 1u
+    AXCD_FLAG_PAIR_DISTANCES = 1u,
+    /* Run EPA with the cooperative kernel (8 lanes per pair, faces in registers) instead of the
+     * default one-thread-per-pair kernel.  Same results; slower on B200 so far (profiles/), kept
+     * for A/B measurements.                                                                     */
+    AXCD_FLAG_EPA_COOPERATIVE = 2u
 };
 
 typedef struct AxcdStats {

@@ -141,6 +141,11 @@ def test_c3_batched_worlds_no_cross_world_pairs():
     w.close()
 
 
+def test_cooperative_epa_flag_is_bit_identical():
+    st, bitwise = run_and_compare(axcd.config_scene("C2", scale=0.02), flags=axcd.FLAG_EPA_COOPERATIVE)
+    assert bitwise and st.numPenetrating > 0
+
+
 def test_aabb_margin_inflates_candidates():
     s = axcd.config_scene("C0")
     st0, _ = run_and_compare(s, brute=True)

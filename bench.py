@@ -168,6 +168,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the collision path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- workload ---------------------------------------------------------------------------------
@@ -325,7 +327,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=list(WORKLOADS))

@@ -883,13 +883,19 @@ int32_t axref_broadphase_grid(const float* aabb, uint32_t n, const uint32_t* wor
                 c[k] = std::min<int64_t>(std::max<int64_t>(v, 0), dim[k] - 1);
             }
         };
-        const uint64_t ncell = (uint64_t)dim[0] * dim[1] * dim[2];
+        // batched worlds share one coordinate frame: give every world its own copy of the grid
+        const uint64_t cellsPerWorld = (uint64_t)dim[0] * dim[1] * dim[2];
+        uint64_t nWorlds = 1;
+        if (worldId)
+            for (uint32_t i : finite) nWorlds = std::max<uint64_t>(nWorlds, (uint64_t)worldId[i] + 1);
+        const uint64_t ncell = cellsPerWorld * nWorlds;
         std::vector<uint32_t> start(ncell + 1, 0), items(finite.size());
         std::vector<uint64_t> cid(finite.size());
         for (size_t k = 0; k < finite.size(); ++k) {
             int64_t c[3];
             cellOf(finite[k], c);
-            cid[k] = ((uint64_t)c[2] * dim[1] + c[1]) * dim[0] + c[0];
+            cid[k] = ((uint64_t)c[2] * dim[1] + c[1]) * dim[0] + c[0] +
+                     (worldId ? (uint64_t)worldId[finite[k]] * cellsPerWorld : 0);
             start[cid[k] + 1]++;
         }
         for (uint64_t c = 0; c < ncell; ++c) start[c + 1] += start[c];
@@ -906,7 +912,8 @@ int32_t axref_broadphase_grid(const float* aabb, uint32_t n, const uint32_t* wor
                 for (int64_t z = std::max<int64_t>(c[2] - 1, 0); z <= std::min(c[2] + 1, dim[2] - 1); ++z)
                 for (int64_t y = std::max<int64_t>(c[1] - 1, 0); y <= std::min(c[1] + 1, dim[1] - 1); ++y)
                 for (int64_t x = std::max<int64_t>(c[0] - 1, 0); x <= std::min(c[0] + 1, dim[0] - 1); ++x) {
-                    uint64_t cc = ((uint64_t)z * dim[1] + y) * dim[0] + x;
+                    uint64_t cc = ((uint64_t)z * dim[1] + y) * dim[0] + x +
+                                  (worldId ? (uint64_t)worldId[i] * cellsPerWorld : 0);
                     for (uint32_t p = start[cc]; p < start[cc + 1]; ++p) {
                         const uint32_t j = items[p];
                         if (j <= i) continue;

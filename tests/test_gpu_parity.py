@@ -146,6 +146,25 @@ def test_cooperative_epa_flag_is_bit_identical():
     assert bitwise and st.numPenetrating > 0
 
 
+def test_non_unit_scales_boxes_and_hulls():
+    """Transform.scale enters refit (transformPoint) and the GJK cores (half-extents, hull vertices):
+    non-uniform positive scales on a hull/box/sphere mix must stay bit-exact too."""
+    s = axcd.config_scene("C2", scale=0.02)
+    rng = np.random.default_rng(11)
+    s.xf[:, 7:10] = rng.uniform(0.5, 1.6, (s.n, 3)).astype(np.float32)
+    st, bitwise = run_and_compare(s)
+    assert bitwise and st.numPenetrating > 0
+
+
+def test_large_coordinates_far_from_origin():
+    """Bodies 10^4 units from the origin: the A-centred GJK frame keeps the narrowphase well
+    conditioned; sets stay bit-exact."""
+    s = axcd.config_scene("C0")
+    s.xf[:, :3] += np.float32(10000.0)
+    st, bitwise = run_and_compare(s, brute=True)
+    assert bitwise and st.numPairs > 2000
+
+
 def test_aabb_margin_inflates_candidates():
     s = axcd.config_scene("C0")
     st0, _ = run_and_compare(s, brute=True)

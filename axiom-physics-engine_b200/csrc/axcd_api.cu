@@ -282,6 +282,8 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dSortStatus, (size_t)kMaxPasses * maxTiles * kRadix));
         CU(dalloc(&ctx->dCtr, 1));
         CU(cudaMemsetAsync(ctx->dCtr, 0, sizeof(Counters), ctx->stream));
+        // slotKernel reads the per-pair flags 8 bytes at a time and masks the tail: keep the tail defined
+        CU(cudaMemsetAsync(ctx->dFlags, 0, np + kSlotTile, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         return AXCD_OK;
     };

@@ -275,6 +275,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dSlots, np));
         CU(dalloc(&ctx->dTmpContacts, np));
         CU(cudaFuncSetAttribute(epaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaSmemBytes));
+        CU(cudaFuncSetAttribute(epaFallbackKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaFallbackSmemBytes));
         CU(dalloc(&ctx->dContacts, (size_t)cfg->maxContacts));
         if (cfg->flags & AXCD_FLAG_PAIR_DISTANCES) CU(dalloc(&ctx->dPairDist, np));
         CU(dalloc(&ctx->dSortHist, (size_t)kMaxPasses * kRadix));
@@ -531,7 +532,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
                                                                 ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts,
                                                                 ctx->dSlots, ctx->dPairDist, ctx->dCtr);
         }
-        epaFallbackKernel<<<kNumSMs, 64, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+        epaFallbackKernel<<<kNumSMs * 2, kEpaFallbackThreads, kEpaFallbackSmemBytes, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
                                                   ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots, ctx->dPairDist,
                                                   ctx->dCtr);
         CU(cudaGetLastError());

@@ -1126,20 +1126,25 @@ epaKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs,
     }
 }
 
-// Full-cap path for the few pairs whose polytope outgrew the shared-memory caps.
-__global__ void __launch_bounds__(64)
+// Full-cap path for the few pairs (~0.2 %) whose polytope outgrew the fast caps: one warp per block,
+// the 2.6 KB full-cap polytope of each lane in shared memory (84 KB per block), so these longest
+// expansions are not left crawling through local memory at the end of the step.
+constexpr int kEpaFallbackThreads = 32;
+using FallbackPoly = Poly<kEpaHardVerts, kEpaHardFaces, kEpaHardFaces * 3, kEpaFallbackThreads>;
+constexpr int kEpaFallbackSmemBytes = FallbackPoly::kWords * kEpaFallbackThreads * (int)sizeof(float);
+
+__global__ void __launch_bounds__(kEpaFallbackThreads)
 epaFallbackKernel(NarrowQueues q, const uint2* __restrict__ pairs, const float* __restrict__ xf,
                   const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
                   AxcdContact* __restrict__ contacts, uint32_t maxContacts, const uint32_t* __restrict__ slots,
                   float* __restrict__ pairDist, Counters* __restrict__ ctr) {
-    using P = Poly<kEpaHardVerts, kEpaHardFaces, kEpaHardFaces * 3, 1>;
-    float store[P::kWords];
-    P poly;
-    poly.base = store;
+    extern __shared__ float sPoly[];
+    FallbackPoly poly;
+    poly.base = sPoly + threadIdx.x;
     const uint32_t count = ctr->epaOverflow;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         EpaLane L;
-        EpaState<P::Mask> st;
+        EpaState<FallbackPoly::Mask> st;
         EpaResult r;
         if (!epaBegin(q.work + q.overflow[i], pairs, xf, shapes, hull, poly, L, st, r)) {
             while (!epaIterate(L.A, L.B, cfg, poly, st)) {

@@ -280,8 +280,18 @@ def run_ours(args):
     dom = max(avg, key=avg.get)
     dom_name, dom_bytes = stage_info[dom]
     dom_gbs = dom_bytes / (avg[dom] * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of
+    # this same workload (profiles/); null for other workloads
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        key = {"epaMs": "epaKernel", "gjkMs": "gjkKernel", "pairMs": "findPairsKernel", "refitMs": "refitKernel"}.get(dom)
+        if args.workload == "headline" and key:
+            traffic = tj.get(key + "_dram_bytes_per_launch")
+    except Exception:
+        pass
     roofline = {"kernel": dom_name, "bound": "hbm", "achieved": round(dom_gbs, 1), "peak": hbm_peak,
-                "unit": "GB/s", "frac": round(dom_gbs / hbm_peak, 4), "traffic": None,
+                "unit": "GB/s", "frac": round(dom_gbs / hbm_peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "launch_ms": round(avg[dom], 4),
                 "note": "the dominant kernel (EPA/GJK) is FP32-CUDA-core issue/latency bound, not HBM "
                         "bound: its HBM fraction is reported because the contract asks for one; the "

@@ -60,6 +60,8 @@ struct AxcdContext {
     uint32_t* dScanStatus = nullptr;
     EpaWork* dEpaWork = nullptr;     // GJK -> EPA queue (maxContacts)
     uint32_t* dEpaOverflow = nullptr;
+    float* dEpaSpill = nullptr;      // polytopes of pairs that outgrew the fast EPA caps
+    uint32_t spillCap = 0;
     uint32_t* dSlotStatus = nullptr; // look-back status, one word per slot-scan tile
     uint8_t* dFlags = nullptr;       // per pair: 0 none, 1 shallow contact, 2 EPA contact
     uint32_t* dSlots = nullptr;      // per pair: contact slot
@@ -195,7 +197,7 @@ void axcd_destroy(AxcdContext* ctx) {
     void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
-                    ctx->dEpaOverflow, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
+                    ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
                     ctx->dSortStatus, ctx->dCtr};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -270,6 +272,8 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dNodes, nb));
         CU(dalloc(&ctx->dEpaWork, (size_t)cfg->maxContacts));
         CU(dalloc(&ctx->dEpaOverflow, (size_t)cfg->maxContacts));
+        ctx->spillCap = cfg->maxContacts < 65536u ? cfg->maxContacts : 65536u;
+        CU(dalloc(&ctx->dEpaSpill, (size_t)ctx->spillCap * (Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, 1>::kWords + kSpillStateWords)));
         CU(dalloc(&ctx->dSlotStatus, np / kSlotTile + 2));
         CU(dalloc(&ctx->dFlags, np + kSlotTile));
         CU(dalloc(&ctx->dSlots, np));
@@ -511,7 +515,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         const uint32_t slotTilesMax = (mp + kSlotTile - 1) / kSlotTile;
         const uint32_t slotBlocks = slotTilesMax < (uint32_t)kNumSMs * 4 ? slotTilesMax : kNumSMs * 4;
         CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * (slotTilesMax + 1), st));
-        NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow};
+        NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow, ctx->dEpaSpill, ctx->spillCap};
         const uint2* pairs = ctx->dPairs;
         const uint32_t* pairCount = &ctx->dCtr->pairCount;
         gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, pairCount, mp, ctx->dXf, ctx->dShapes, ctx->dHull, p,

@@ -138,7 +138,7 @@ epaCoopKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs
                 if (overflow) {
                     if (gl == 0) {
                         const uint32_t o = atomicAdd(&ctr->epaOverflow, 1u);
-                        q.overflow[o] = PU[CW_PAIR + 4];
+                        q.overflow[o] = PU[CW_PAIR + 4];   // (no spill: the full-cap kernel restarts the pair)
                     }
                 } else {
                     // every lane computes the (uniform) result; lane 0 writes it

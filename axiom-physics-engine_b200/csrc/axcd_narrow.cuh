@@ -728,9 +728,12 @@ struct __align__(16) EpaWork {
 };
 static_assert(sizeof(EpaWork) == 80, "EpaWork must be 80 bytes");
 
+constexpr int kSpillStateWords = 8;   // nv, nf, best, bd, alive, it, (2 spare)
 struct NarrowQueues {
     EpaWork* work;        // capacity maxContacts
-    uint32_t* overflow;   // indices into work[] that need the full-cap path
+    uint32_t* overflow;   // indices into work[] that need the full-cap path; bit 31: polytope spilled
+    float* spill;         // spillCap x (fast polytope words + kSpillStateWords): state to resume from
+    uint32_t spillCap;
 };
 
 // ---- kernel 1: GJK over every candidate pair -------------------------------------------------------
@@ -1014,7 +1017,7 @@ __device__ __forceinline__ int epaBegin(const EpaWork* __restrict__ wk, const ui
                                         const float* __restrict__ xf, const uint4* __restrict__ shapes,
                                         const float4* __restrict__ hull, const Poly<MAXV, MAXF, MAXE, STRIDE>& poly,
                                         EpaLane& L, EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st,
-                                        EpaResult& touching) {
+                                        EpaResult& touching, bool skipInit = false) {
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(wk));
     const float4 f0 = __ldg(reinterpret_cast<const float4*>(wk) + 1), f1 = __ldg(reinterpret_cast<const float4*>(wk) + 2),
                  f2 = __ldg(reinterpret_cast<const float4*>(wk) + 3);
@@ -1032,6 +1035,7 @@ __device__ __forceinline__ int epaBegin(const EpaWork* __restrict__ wk, const ui
     L.origin = ta.p;
     L.A = makeCore(ta, sa, hull, L.origin);
     L.B = makeCore(tb, sb, hull, L.origin);
+    if (skipInit) return 0;   // the caller restores a spilled polytope instead
     return epaInit(L.A, L.B, n0, y0, id0, poly, st, touching);
 }
 
@@ -1082,8 +1086,19 @@ epaKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs,
             if (state == DONE) {
                 const EpaResult r = epaFinish(L.A, poly, st);
                 if (r.overflow) {
+                    // hand the pair to the full-cap kernel together with its polytope, so that kernel
+                    // continues the expansion instead of repeating it (nothing of the overflowing
+                    // step has been applied yet)
                     const uint32_t o = atomicAdd(&ctr->epaOverflow, 1u);
-                    q.overflow[o] = L.queueIdx;   // rerun from the queue entry of this pair
+                    const bool spilled = o < q.spillCap;
+                    q.overflow[o] = L.queueIdx | (spilled ? 0x80000000u : 0u);
+                    if (spilled) {
+                        float* dst = q.spill + (size_t)o * (P::kWords + kSpillStateWords);
+                        for (int i = 0; i < P::kWords; ++i) dst[i] = poly.w(i);
+                        uint32_t* du = reinterpret_cast<uint32_t*>(dst + P::kWords);
+                        du[0] = (uint32_t)st.nv; du[1] = (uint32_t)st.nf; du[2] = (uint32_t)st.best;
+                        du[3] = __float_as_uint(st.bd); du[4] = (uint32_t)st.alive; du[5] = st.it;
+                    }
                 } else {
                     epaEmit(L, r, contacts, maxContacts, slots, pairDist, ctr);
                 }
@@ -1146,7 +1161,29 @@ epaFallbackKernel(NarrowQueues q, const uint2* __restrict__ pairs, const float* 
         EpaLane L;
         EpaState<FallbackPoly::Mask> st;
         EpaResult r;
-        if (!epaBegin(q.work + q.overflow[i], pairs, xf, shapes, hull, poly, L, st, r)) {
+        const uint32_t ov = q.overflow[i];
+        const bool resume = (ov & 0x80000000u) != 0;
+        L.queueIdx = ov & 0x7fffffffu;
+        if (!epaBegin(q.work + L.queueIdx, pairs, xf, shapes, hull, poly, L, st, r, resume)) {
+            if (resume) {
+                // restore the spilled fast-path polytope into the full-cap layout, section by section
+                using FP = Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, 1>;
+                const float* src = q.spill + (size_t)i * (FP::kWords + kSpillStateWords);
+                const uint32_t* su = reinterpret_cast<const uint32_t*>(src + FP::kWords);
+                st.nv = (int)su[0]; st.nf = (int)su[1]; st.best = (int)su[2];
+                st.bd = __uint_as_float(su[3]); st.alive = (FallbackPoly::Mask)su[4]; st.it = su[5];
+                st.status = 0; st.overflow = false; st.degenerate = false;
+                FP fp;
+                fp.base = const_cast<float*>(src);
+                for (int v = 0; v < st.nv; ++v) {
+                    poly.setY(v, fp.y(v));
+                    poly.setId(v, fp.id(v));
+                }
+                for (int f = 0; f < st.nf; ++f) {
+                    poly.setPlane(f, fp.fn(f), fp.fd(f));
+                    poly.setFi(f, fp.fi(f));
+                }
+            }
             while (!epaIterate(L.A, L.B, cfg, poly, st)) {
             }
             r = epaFinish(L.A, poly, st);

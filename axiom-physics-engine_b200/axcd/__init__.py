@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
-    "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
+    "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
 ]
 SCENE_SYMBOLS = ["axcd_scene_generate", "axcd_scene_generate_worlds", "axcd_scene_rng_u32"]
 
@@ -96,7 +96,8 @@ def load_library():
         for name in ("axcd_create", "axcd_set_shapes", "axcd_set_transforms", "axcd_refit",
                      "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_get_stats",
                      "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
-                     "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64"):
+                     "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
+                     "axcd_test_sort_bench"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -112,6 +113,7 @@ def load_library():
         lib.axcd_test_sort_pairs32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                C.c_uint32]
         lib.axcd_test_sort_keys64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.axcd_test_sort_bench.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -378,6 +380,12 @@ class CollisionWorld:
         self._check(self._lib.axcd_test_sort_pairs32(self._ctx, _ptr(keys), _ptr(vals),
                                                      len(keys), key_bits), "sort_pairs32")
         return keys, vals
+
+    def sort_bench(self, n, key_bits=32, iters=10):
+        """Average ms of one device-resident (key,value) radix sort of n pseudo-random keys."""
+        ms = C.c_float(0)
+        self._check(self._lib.axcd_test_sort_bench(self._ctx, n, key_bits, iters, C.byref(ms)), "sort_bench")
+        return ms.value
 
     def test_sort_keys64(self, keys, key_bits=64):
         keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()

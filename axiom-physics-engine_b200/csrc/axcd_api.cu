@@ -708,4 +708,31 @@ int32_t axcd_test_sort_keys64(AxcdContext* ctx, uint64_t* keys, uint32_t n, uint
     return AXCD_OK;
 }
 
+int32_t axcd_test_sort_bench(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uint32_t iters, float* outMsPerSort) {
+    if (!ctx || !outMsPerSort) return AXCD_ERR_NULL_POINTER;
+    if (n == 0 || n > ctx->cfg.maxBodies || keyBits == 0 || keyBits > 32 || iters == 0) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float total = 0.0f;
+    const int passes = (int)(keyBits + 7) / 8;
+    for (uint32_t it = 0; it <= iters; ++it) {   // iteration 0 is a warm-up
+        fillRandomKeysKernel<<<kNumSMs * 8, 256, 0, st>>>(ctx->dKeys[0], ctx->dVals[0], n, keyBits, 0x9E3779B9u * (it + 1));
+        CU(cudaEventRecord(e0, st));
+        radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0, passes,
+                                  ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st);
+        CU(cudaEventRecord(e1, st));
+        CU(cudaStreamSynchronize(st));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (it) total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *outMsPerSort = total / (float)iters;
+    return AXCD_OK;
+}
+
 }  // extern "C"

@@ -216,6 +216,17 @@ inline int radixSort(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, uint3
     return passes & 1;
 }
 
+// pseudo-random keys for the sort timing hook (splitmix-style hash of the index)
+__global__ void fillRandomKeysKernel(uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, uint32_t keyBits,
+                                     uint32_t seed) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t x = i * 0x9E3779B9u + seed;
+        x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+        keys[i] = keyBits >= 32 ? x : (x & ((1u << keyBits) - 1u));
+        vals[i] = i;
+    }
+}
+
 // ---- single-pass exclusive scan of uint32 (decoupled look-back), used for compaction ------------
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;

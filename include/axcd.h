@@ -171,6 +171,10 @@ AXCD_API int32_t axcd_test_sort_pairs32(AxcdContext* ctx, uint32_t* keys, uint32
                                         uint32_t n, uint32_t keyBits);
 AXCD_API int32_t axcd_test_sort_keys64(AxcdContext* ctx, uint64_t* keys, uint32_t n,
                                        uint32_t keyBits);
+/* Device-resident timing of the (key,value) radix sort on n pseudo-random keys: average ms of
+ * `iters` sorts (CUDA events on the context stream, inputs regenerated on the device each time). */
+AXCD_API int32_t axcd_test_sort_bench(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uint32_t iters,
+                                      float* outMsPerSort);
 
 #ifdef __cplusplus
 }

@@ -138,12 +138,28 @@ radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
             st[d] = kFlagInclusive | pub;
         } else {
             st[d] = kFlagAggregate | pub;
-            for (int t = (int)tile - 1; t >= 0; --t) {
-                volatile uint32_t* pt = status + (size_t)t * kRadix;
-                uint32_t s;
-                do { s = pt[d]; } while ((s & kFlagMask) == 0);
-                excl += s & kValueMask;
-                if ((s & kFlagMask) == kFlagInclusive) break;
+            // Decoupled look-back, kLookback predecessors per round: the loads of a round are
+            // independent (all in flight together), so a deep walk costs one L2 round trip per
+            // kLookback tiles instead of one per tile.
+            constexpr int kLookback = 16;
+            int t = (int)tile - 1;
+            bool found = false;
+            while (!found && t >= 0) {
+                uint32_t sv[kLookback];
+#pragma unroll
+                for (int w = 0; w < kLookback; ++w) {
+                    const int idx = t - w;
+                    sv[w] = (idx >= 0) ? status[(size_t)idx * kRadix + d] : uint32_t(kFlagInclusive);
+                }
+#pragma unroll
+                for (int w = 0; w < kLookback; ++w) {
+                    if (found) continue;
+                    uint32_t sw = sv[w];
+                    while ((sw & kFlagMask) == 0) sw = status[(size_t)(t - w) * kRadix + d];   // not published yet
+                    excl += sw & kValueMask;
+                    found = (sw & kFlagMask) == kFlagInclusive;
+                }
+                t -= kLookback;
             }
             st[d] = kFlagInclusive | (excl + pub);
         }

@@ -185,8 +185,14 @@ __global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t 
 }
 
 // ---- traversal ------------------------------------------------------------------------------------
-constexpr int kTravThreads = 128;
-constexpr int kTravPool = 2048;    // pairs staged per block before the coalesced flush
+#ifndef AXCD_TRAV_THREADS
+#define AXCD_TRAV_THREADS 64
+#endif
+#ifndef AXCD_TRAV_POOL
+#define AXCD_TRAV_POOL 1024
+#endif
+constexpr int kTravThreads = AXCD_TRAV_THREADS;
+constexpr int kTravPool = AXCD_TRAV_POOL;   // pairs staged per block before the coalesced flush    // pairs staged per block before the coalesced flush
 constexpr int kTravStack = 64;
 
 // AABB::intersects (aabb.hpp:132-135): closed intervals, any NaN -> false

@@ -812,7 +812,11 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCoun
         }
         binByClass<kGjkThreads>(cls, sCnt, sOrder);
     }
+#ifdef AXCD_GJK_NO_BINNING
+    const int j = tid;
+#else
     const int j = sOrder[tid];           // local index of the pair this thread works on
+#endif
     const uint32_t k = tileBase + j;     // its global pair index
     if (k >= npairs) continue;
 

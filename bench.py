@@ -37,6 +37,7 @@ WORKLOADS = {
     "C1": "100k mixed boxes/spheres, L=46.4, seed 2",
     "C2": "1M bodies 40% box / 30% sphere / 30% 16-vertex hulls, L=100, seed 4 (EPA-heavy)",
     "C3": "4096 independent 256-body worlds batched, L=6.35, seed 1000+world",
+    "C4": "16M-body single scene (scaled by --scale), x-slab decomposition with ghost exchange over NCCL",
 }
 
 
@@ -127,7 +128,7 @@ def run_reference(args):
     import axcd
     import oracle_lib as O
     nthreads = host_threads()
-    scale = {"headline": 0.25, "C2": 0.1, "C1": 1.0, "C3": 0.25}[args.workload]
+    scale = {"headline": 0.25, "C2": 0.1, "C1": 1.0, "C3": 0.25, "C4": 0.015}[args.workload]
     s = axcd.config_scene(args.workload, scale=scale)
     for _ in range(args.warmup):
         oracle_step(O, s, nthreads)
@@ -155,7 +156,77 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_slab(args):
+    """--workload C4: one scene split into x-slabs, one slab per rank; ghosts travel over NCCL
+    (axcd/sharding.py).  Round-1 status: the per-rank collision step is the CUDA path, the ghost
+    selection and the de-duplication filter are host-side numpy — functional, not yet tuned — so
+    this mode is timed with a wall clock (barrier + synchronize on both sides), max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import axcd
+    from axcd import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    s = axcd.config_scene("C4", scale=args.scale)
+    edges = sharding.plan_slabs(s.xf[:, 0], world)
+    mine = np.nonzero(sharding.owner_of(s.xf[:, 0], edges) == rank)[0]
+    owned = sharding._subset(s, mine)
+    gid = mine.astype(np.uint32)
+    backend = sharding.CudaBackend(device=local)
+    dev = f"cuda:{local}"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        sharding.slab_step(owned, gid, edges, rank, world, backend, dist if world > 1 else None, dev)
+    steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    units = 0
+    for _ in range(steps):
+        gp, gc = sharding.slab_step(owned, gid, edges, rank, world, backend, dist if world > 1 else None, dev)
+        units += len(gp) + len(gc)
+    barrier()
+    sec = time.perf_counter() - t0
+    t = torch.tensor([sec, float(units), float(len(gp)), float(len(gc))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        sec, units, npairs, ncon = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
+    else:
+        npairs, ncon = float(len(gp)), float(len(gc))
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": units / sec, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * sec / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS["C4"], "bodies_total": int(s.n), "scale": args.scale,
+                       "candidate_pairs": int(npairs), "contacts": int(ncon),
+                       "parallelism": f"{world} x-slabs, ghost bodies exchanged point-to-point over NCCL, "
+                                      "x* ownership rule for de-duplication",
+                       "note": "round-1 functional path: ghost selection and pair filtering are host-side "
+                               "numpy; wall-clock timed"},
+            "gpu_launches": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
+    if args.workload == "C4":
+        return run_slab(args)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -173,8 +244,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- workload ---------------------------------------------------------------------------------
+    scaling = "weak"
     if args.workload == "headline" and world > 1:
         s = axcd.generate_scene(1_000_000, 3 + rank, 100.0, name="headline")   # one world per rank
+    elif args.workload == "C3" and world > 1:
+        from axcd import sharding
+        s, _ = sharding.shard_worlds(axcd.config_scene("C3"), rank, world)      # worlds [r*W/R, (r+1)*W/R)
+        scaling = "strong"
     else:
         s = axcd.config_scene(args.workload)
     stream = torch.cuda.Stream()
@@ -314,7 +390,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "bodies_per_gpu": int(n),
                        "candidate_pairs": int(npairs), "contacts": int(ncon),
                        "epa_runs": int(st.numPenetrating),
@@ -342,6 +418,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scale", type=float, default=0.125, help="C4 only: fraction of the 16M bodies")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

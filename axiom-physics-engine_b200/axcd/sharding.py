@@ -199,10 +199,11 @@ def slab_step(scene_owned, owned_gid, edges, rank, size, backend, dist=None, dev
     local, gid = exchange_ghosts(scene_owned, owned_gid, owned_aabb, edges, rank, size, dist, device)
     aabb, pairs, contacts = backend.step(local)
     gp, keep = filter_pairs_for_rank(pairs, aabb, gid, edges, rank)
-    # contacts follow the same rule, keyed by their pair
+    # contacts follow the same rule, keyed by their pair (both lists are in canonical local order)
     if len(contacts):
-        kept = {(int(a), int(b)) for a, b in pairs[keep]}
-        cm = np.array([(int(a), int(b)) in kept for a, b in zip(contacts["a"], contacts["b"])], bool)
+        pk = pairs[:, 0].astype(np.uint64) << np.uint64(32) | pairs[:, 1].astype(np.uint64)
+        ck = contacts["a"].astype(np.uint64) << np.uint64(32) | contacts["b"].astype(np.uint64)
+        cm = keep[np.searchsorted(pk, ck)]
         c = contacts[cm].copy()
         ga, gb = gid[c["a"]], gid[c["b"]]
         swap = ga > gb

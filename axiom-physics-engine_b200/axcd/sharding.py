@@ -120,14 +120,19 @@ def exchange_ghosts(owned, owned_gid, owned_aabb, edges, rank, size, dist=None, 
         recv = {r: torch.empty(int(all_sizes[r][rank]), dtype=torch.float32, device=device)
                 for r in range(size) if r != rank}
         send = {r: torch.from_numpy(p).to(device) for r, p in payloads.items()}
-        reqs = []
+        # one grouped exchange (ncclGroupStart/End under NCCL: un-grouped send-then-recv on both sides
+        # of a pair would wait on each other); empty messages are skipped on both ends
+        ops = []
         for r in range(size):
             if r == rank:
                 continue
-            reqs.append(dist.isend(send[r], dst=r))
-            reqs.append(dist.irecv(recv[r], src=r))
-        for q in reqs:
-            q.wait()
+            if send[r].numel():
+                ops.append(dist.P2POp(dist.isend, send[r], r))
+            if recv[r].numel():
+                ops.append(dist.P2POp(dist.irecv, recv[r], r))
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
         for r in sorted(recv):
             parts.append(_unpack(recv[r].cpu().numpy()))
     xf = np.concatenate([p[0] for p in parts])

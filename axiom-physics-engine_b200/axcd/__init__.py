@@ -32,6 +32,7 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
+    "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
 ]
 SCENE_SYMBOLS = ["axcd_scene_generate", "axcd_scene_generate_worlds", "axcd_scene_rng_u32"]
@@ -97,7 +98,7 @@ def load_library():
                      "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_get_stats",
                      "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
                      "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
-                     "axcd_test_sort_bench"):
+                     "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -113,6 +114,9 @@ def load_library():
         lib.axcd_test_sort_pairs32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                C.c_uint32]
         lib.axcd_test_sort_keys64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.axcd_set_slab.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint32]
+        lib.axcd_set_body_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.axcd_set_ghosts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.axcd_test_sort_bench.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = lib
     return _lib
@@ -372,6 +376,24 @@ class CollisionWorld:
         self._check(self._lib.axcd_get_contacts(self._ctx, C.c_void_p(host_ptr), cap,
                                                 C.byref(cnt)), "axcd_get_contacts")
         return cnt.value
+
+    # ---- x-slab mode (one scene across several GPUs) -------------------------------------------
+    def set_slab(self, x_lo, x_hi, enable=True):
+        self._check(self._lib.axcd_set_slab(self._ctx, float(x_lo), float(x_hi), 1 if enable else 0),
+                    "axcd_set_slab")
+
+    def set_body_keys(self, keys, first=0):
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        self._check(self._lib.axcd_set_body_keys(self._ctx, _ptr(keys), first, len(keys)),
+                    "axcd_set_body_keys")
+
+    def set_ghosts(self, n_owned, xf, shapes, keys):
+        xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(-1, 10)
+        shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        self._check(self._lib.axcd_set_ghosts(self._ctx, n_owned, len(xf), _ptr(xf), _ptr(shapes),
+                                              _ptr(keys)), "axcd_set_ghosts")
+        self.n = n_owned + len(xf)
 
     # test hooks for the device primitives
     def test_sort_pairs32(self, keys, vals, key_bits=32):

@@ -44,6 +44,10 @@ struct AxcdContext {
     uint4* dShapes = nullptr;
     float4* dHull = nullptr;
     uint32_t* dWorld = nullptr;
+    uint32_t* dBodyKeys = nullptr;   // slab mode: global id of every local body
+    bool slabOn = false;
+    float slabLo = 0.0f, slabHi = 0.0f;
+    uint32_t nOwned = 0;             // slab mode: bodies [0, nOwned) are owned, the rest are ghosts
     float* dAabb = nullptr;          // n * 6 floats (axiom::math::AABB AoS)
     uint32_t* dKeys[2] = {nullptr, nullptr};
     uint32_t* dVals[2] = {nullptr, nullptr};
@@ -125,6 +129,28 @@ uint32_t sortTilesFor(uint64_t n) { return (uint32_t)((n + kSortTile - 1) / kSor
 
 }  // namespace
 
+// Everything that depends on the body count: range-tree size (empty leaf slots beyond n) and the
+// Morton resolution.
+int resizeBodies(AxcdContext* ctx, uint32_t n) {
+    ctx->n = n;
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    ctx->segP = P;
+    // leaf slots beyond n stay empty boxes; upper levels are rebuilt every step
+    fillEmptyBoxesKernel<<<(2 * P + 255) / 256, 256, 0, ctx->stream>>>(ctx->dSegLo, ctx->dSegHi, 2 * P);
+    CU(cudaGetLastError());
+    ctx->worldBits = ctx->hasWorlds ? bitsFor(ctx->cfg.numWorlds) : 0;
+    // Morton resolution: ~1 bit/axis finer than one body per cell, within the 32-bit key
+    const uint32_t perWorld = ctx->hasWorlds ? (n / ctx->cfg.numWorlds + 1) : n;
+    int mb = (bitsFor(perWorld > 1 ? perWorld : 2) + 2) / 3 + 1;
+    const int room = (32 - ctx->worldBits) / 3;
+    if (mb > room) mb = room;
+    if (mb > 10) mb = 10;
+    if (mb < 1) mb = 1;
+    ctx->mortonBits = mb;
+    return AXCD_OK;
+}
+
 int refreshCountersImpl(AxcdContext* ctx) {
     CU(cudaMemcpyAsync(&ctx->hostCtr, ctx->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -194,7 +220,7 @@ void axcd_destroy(AxcdContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
+    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
@@ -253,6 +279,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
             CU(dalloc(&ctx->dWorldEnd, (size_t)cfg->numWorlds));
         }
         CU(dalloc(&ctx->dAabb, nb * 6 + 64));
+        CU(dalloc(&ctx->dBodyKeys, nb));
         for (int k = 0; k < 2; ++k) {
             CU(dalloc(&ctx->dKeys[k], nb));
             CU(dalloc(&ctx->dVals[k], nb));
@@ -336,27 +363,11 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
     if (ctx->hasWorlds)
         CU(cudaMemcpyAsync(ctx->dWorld, worldId, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->n = n;
     ctx->nHull = nHullVerts;
+    ctx->nOwned = n;
     {
-        uint32_t P = 1;
-        while (P < n) P <<= 1;
-        ctx->segP = P;
-        // leaf slots beyond n stay empty boxes for good; upper levels are rebuilt every step
-        fillEmptyBoxesKernel<<<(2 * P + 255) / 256, 256, 0, ctx->stream>>>(ctx->dSegLo, ctx->dSegHi, 2 * P);
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(ctx->stream));
-    }
-    ctx->worldBits = ctx->hasWorlds ? bitsFor(ctx->cfg.numWorlds) : 0;
-    // Morton resolution: ~1 bit/axis finer than one body per cell, within the 32-bit key
-    {
-        const uint32_t perWorld = ctx->hasWorlds ? (n / ctx->cfg.numWorlds + 1) : n;
-        int mb = (bitsFor(perWorld > 1 ? perWorld : 2) + 2) / 3 + 1;
-        const int room = (32 - ctx->worldBits) / 3;
-        if (mb > room) mb = room;
-        if (mb > 10) mb = 10;
-        if (mb < 1) mb = 1;
-        ctx->mortonBits = mb;
+        const int rc = resizeBodies(ctx, n);
+        if (rc) return rc;
     }
     ctx->stage = ST_SHAPES;
     return AXCD_OK;
@@ -365,7 +376,7 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
 int32_t axcd_set_transforms(AxcdContext* ctx, const void* transforms, uint32_t n, uint32_t strideBytes) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
     if (ctx->stage < ST_SHAPES) return AXCD_ERR_GPU_INVALID_OP;
-    if (n != ctx->n || strideBytes < 40 || (strideBytes & 3u)) return AXCD_ERR_INVALID_PARAM;
+    if ((n != ctx->n && n != ctx->nOwned) || strideBytes < 40 || (strideBytes & 3u)) return AXCD_ERR_INVALID_PARAM;
     if (n && !transforms) return AXCD_ERR_NULL_POINTER;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (n) {
@@ -463,7 +474,8 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         const uint32_t tb = (n + kTravThreads - 1) / kTravThreads;
         findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes,
                                                      ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
-                                                     ctx->cfg.maxPairs, ctx->dBodyCount, ctx->dCtr);
+                                                     ctx->cfg.maxPairs, ctx->dBodyCount,
+                                                     SlabRule{ctx->slabOn ? 1 : 0, ctx->slabLo, ctx->slabHi, ctx->dBodyKeys}, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIR);
         // ---- canonical order: counting sort by body a, then tiny per-body sorts by b ------------------
@@ -669,6 +681,48 @@ int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap, uint
     if (cap < ctx->numContacts) return AXCD_ERR_OUT_OF_RANGE;
     CU(cudaMemcpyAsync(out, ctx->dContacts, sizeof(AxcdContact) * ctx->numContacts, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return AXCD_OK;
+}
+
+int32_t axcd_set_slab(AxcdContext* ctx, float xLo, float xHi, uint32_t enable) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (enable && !(xLo <= xHi)) return AXCD_ERR_INVALID_PARAM;
+    if (enable && ctx->cfg.numWorlds > 1) return AXCD_ERR_INVALID_PARAM;   // slabs split ONE scene
+    ctx->slabOn = enable != 0;
+    ctx->slabLo = xLo;
+    ctx->slabHi = xHi;
+    return AXCD_OK;
+}
+
+int32_t axcd_set_body_keys(AxcdContext* ctx, const uint32_t* keys, uint32_t first, uint32_t count) {
+    if (!ctx || (count && !keys)) return AXCD_ERR_NULL_POINTER;
+    if ((uint64_t)first + count > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (count) CU(cudaMemcpyAsync(ctx->dBodyKeys + first, keys, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+    return AXCD_OK;
+}
+
+int32_t axcd_set_ghosts(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts, const void* transforms40,
+                        const AxcdShape* shapes, const uint32_t* keys) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;   // owned bodies first
+    if (nGhosts && (!transforms40 || !shapes || !keys)) return AXCD_ERR_NULL_POINTER;
+    if (nOwned != ctx->nOwned) return AXCD_ERR_INVALID_PARAM;
+    if ((uint64_t)nOwned + nGhosts > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    for (uint32_t i = 0; i < nGhosts; ++i)
+        if (shapes[i].type != AXCD_SHAPE_SPHERE && shapes[i].type != AXCD_SHAPE_BOX) return AXCD_ERR_INVALID_SHAPE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    if (nGhosts) {
+        CU(cudaMemcpyAsync(ctx->dXf + (size_t)nOwned * 10, transforms40, (size_t)nGhosts * 40, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->dShapes + nOwned, shapes, sizeof(AxcdShape) * nGhosts, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->dBodyKeys + nOwned, keys, sizeof(uint32_t) * nGhosts, cudaMemcpyHostToDevice, st));
+    }
+    if (ctx->n != nOwned + nGhosts) {
+        const int rc = resizeBodies(ctx, nOwned + nGhosts);
+        if (rc) return rc;
+    }
+    ctx->stage = ST_POSES;
     return AXCD_OK;
 }
 

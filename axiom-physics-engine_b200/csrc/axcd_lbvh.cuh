@@ -201,6 +201,12 @@ __device__ __forceinline__ bool boxesIntersect(float ax0, float ay0, float az0, 
     return ax0 <= bx1 && ax1 >= bx0 && ay0 <= by1 && ay1 >= by0 && az0 <= bz1 && az1 >= bz0;
 }
 
+struct SlabRule {
+    int enabled;
+    float lo, hi;            // this rank's slab [lo, hi) on the x axis
+    const uint32_t* keys;    // global id of every local body
+};
+
 // Emits each candidate pair once as (a, b) = (min, max) of the two body indices, unordered, into
 // `pairs` (staged per block in shared memory, flushed with coalesced stores), and counts the
 // pairs of every body a in bodyCount[a] for the counting sort that follows (orderPairs*).
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(kTravThreads)
 findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ leafHi,
                 const BvhNode* __restrict__ nodes, const uint32_t* __restrict__ worldEnd, uint32_t n,
                 uint2* __restrict__ pairs, uint32_t maxPairs, uint32_t* __restrict__ bodyCount,
-                Counters* __restrict__ ctr) {
+                SlabRule slab, Counters* __restrict__ ctr) {
     __shared__ uint2 sPool[kTravPool];
     __shared__ uint32_t sCount, sBase;
     if (threadIdx.x == 0) sCount = 0;
@@ -245,7 +251,17 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                     continue;
                 }
                 const uint32_t bodyJ = __float_as_uint(__ldg(&leafLo[child].w));
-                const uint2 pr = make_uint2(min(bodyI, bodyJ), max(bodyI, bodyJ));
+                uint2 pr = make_uint2(min(bodyI, bodyJ), max(bodyI, bodyJ));
+                if (slab.enabled) {
+                    // one huge scene split into x-slabs: this rank reports the pair only if the left end
+                    // of the pair's x-overlap, max(min_i.x, min_j.x), lies in its slab (exactly one rank
+                    // does), and orients it by global id so both bodies play the same role as in a
+                    // single-GPU run
+                    const float jx = c ? q1.z : q0.x;   // min.x of the leaf child, as stored in the node
+                    const float xs = (lo.x > jx) ? lo.x : jx;
+                    if (!(xs >= slab.lo && xs < slab.hi)) continue;
+                    if (slab.keys[pr.x] > slab.keys[pr.y]) pr = make_uint2(pr.y, pr.x);
+                }
                 const uint32_t slot = atomicAdd(&sCount, 1u);
                 if (slot < kTravPool) {
                     sPool[slot] = pr;

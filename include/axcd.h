@@ -160,6 +160,21 @@ AXCD_API int32_t axcd_get_pair_distances(AxcdContext* ctx, float* outDist, uint3
 AXCD_API int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap,
                                    uint32_t* outCount); /* same (a,b) order                     */
 
+/* ---- one huge scene across several GPUs: x-slab mode ---------
+ * Bodies [0, nOwned) are the ones this rank owns (set with axcd_set_shapes / axcd_set_transforms as
+ * usual, keys = their global ids).  Every step the caller appends the ghost bodies received from the
+ * other ranks with axcd_set_ghosts, after which the context holds nOwned + nGhosts bodies.  With the
+ * slab rule enabled a candidate pair is kept only if max(min_a.x, min_b.x) lies in [xLo, xHi) — exactly
+ * one rank keeps each pair — and pairs are oriented by key (key[a] < key[b]) instead of by local
+ * index, so each contact is computed exactly as a single-GPU run would.  Hull shapes are not
+ * accepted as ghosts in this version (-> 300).                                                    */
+AXCD_API int32_t axcd_set_slab(AxcdContext* ctx, float xLo, float xHi, uint32_t enable);
+AXCD_API int32_t axcd_set_body_keys(AxcdContext* ctx, const uint32_t* keys, uint32_t first,
+                                    uint32_t count);
+AXCD_API int32_t axcd_set_ghosts(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts,
+                                 const void* transforms40, const AxcdShape* shapes,
+                                 const uint32_t* keys);
+
 /* == axiom::core::errorCodeToString (src/core/error_code.cpp:5-62); static storage.            */
 AXCD_API const char* axcd_error_string(int32_t code);
 /* CUDA error text of the last failure on this context (static storage), "" if none.           */

@@ -32,7 +32,8 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
-    "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
+    "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
+    "axcd_set_ghosts_device",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
 ]
 SCENE_SYMBOLS = ["axcd_scene_generate", "axcd_scene_generate_worlds", "axcd_scene_rng_u32"]
@@ -98,7 +99,8 @@ def load_library():
                      "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_get_stats",
                      "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
                      "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
-                     "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts"):
+                     "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
+                     "axcd_pack_ghosts", "axcd_set_ghosts_device"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -117,6 +119,8 @@ def load_library():
         lib.axcd_set_slab.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint32]
         lib.axcd_set_body_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         lib.axcd_set_ghosts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.axcd_pack_ghosts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.axcd_set_ghosts_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         lib.axcd_test_sort_bench.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = lib
     return _lib
@@ -394,6 +398,20 @@ class CollisionWorld:
         self._check(self._lib.axcd_set_ghosts(self._ctx, n_owned, len(xf), _ptr(xf), _ptr(shapes),
                                               _ptr(keys)), "axcd_set_ghosts")
         self.n = n_owned + len(xf)
+
+    def pack_ghosts(self, edges, num_ranks, my_rank):
+        """Device-side ghost selection.  Returns (device pointers, counts) per destination rank."""
+        e = np.ascontiguousarray(edges, dtype=np.float32)
+        ptrs = (C.c_void_p * num_ranks)()
+        counts = np.zeros(num_ranks, np.uint32)
+        self._check(self._lib.axcd_pack_ghosts(self._ctx, _ptr(e), num_ranks, my_rank, ptrs, _ptr(counts)),
+                    "axcd_pack_ghosts")
+        return [p or 0 for p in ptrs], counts
+
+    def set_ghosts_device(self, n_owned, n_ghosts, dev_ptr):
+        self._check(self._lib.axcd_set_ghosts_device(self._ctx, n_owned, n_ghosts, C.c_void_p(dev_ptr)),
+                    "axcd_set_ghosts_device")
+        self.n = n_owned + n_ghosts
 
     # test hooks for the device primitives
     def test_sort_pairs32(self, keys, vals, key_bits=32):

@@ -194,6 +194,14 @@ class CudaBackend:
         return out
 
 
+class _DevBuf:
+    """Zero-copy view of a device buffer owned by the C library (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
 class SlabRank:
     """One rank of the x-slab decomposition on the CUDA path (fast variant of slab_step).
 
@@ -266,7 +274,67 @@ class SlabRank:
         received = self.exchange(self.ghost_payloads(bb), dist, device) if self.size > 1 else []
         return self.step_with(received)
 
+    # ---- device-resident variant: no AABB download, no host-side selection ---------------------------
+    def pack_device(self):
+        """Refit + device-side ghost selection.  Returns {rank: float32 CUDA tensor view (records*16)}."""
+        import torch
+        self.w.refit()
+        ptrs, counts = self.w.pack_ghosts(np.asarray(self.edges, np.float32), self.size, self.rank)
+        dev = f"cuda:{self.w.cfg.deviceOrdinal}"
+        out = {}
+        for r in range(self.size):
+            if r == self.rank:
+                continue
+            n = int(counts[r]) * 16
+            out[r] = (torch.as_tensor(_DevBuf(ptrs[r], n), device=dev) if n else
+                      torch.empty(0, dtype=torch.float32, device=dev))
+        return out
+
+    def exchange_device(self, send, dist):
+        import torch
+        dev = f"cuda:{self.w.cfg.deviceOrdinal}"
+        my_sizes = torch.zeros(self.size, dtype=torch.int64, device=dev)
+        for r, t in send.items():
+            my_sizes[r] = t.numel()
+        all_sizes = [torch.zeros(self.size, dtype=torch.int64, device=dev) for _ in range(self.size)]
+        dist.all_gather(all_sizes, my_sizes)
+        recv = {r: torch.empty(int(all_sizes[r][self.rank]), dtype=torch.float32, device=dev)
+                for r in range(self.size) if r != self.rank}
+        ops = []
+        for r in range(self.size):
+            if r == self.rank:
+                continue
+            if send[r].numel():
+                ops.append(dist.P2POp(dist.isend, send[r], r))
+            if recv[r].numel():
+                ops.append(dist.P2POp(dist.irecv, recv[r], r))
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
+        return [recv[r] for r in sorted(recv)]
+
+    def step_with_device(self, received):
+        """received: list of CUDA float32 tensors of ghost records from the other ranks."""
+        import torch
+        torch.cuda.current_stream().synchronize()   # the records must be complete before our stream reads them
+        if received:
+            allrec = torch.cat(received) if len(received) > 1 else received[0]
+        else:
+            allrec = None
+        ng = (allrec.numel() // 16) if allrec is not None else 0
+        self.w.set_ghosts_device(self.owned.n, ng, allrec.data_ptr() if ng else 0)
+        self._keep = allrec   # keep the buffer alive until the step has consumed it
+        self.local_gid = None
+        return self.w.step()
+
+    def step_device(self, dist=None):
+        send = self.pack_device()
+        received = self.exchange_device(send, dist) if self.size > 1 else []
+        return self.step_with_device(received)
+
     def pairs_global(self):
+        if self.local_gid is None:
+            raise RuntimeError("global ids of device-side ghosts are not mirrored on the host; use step()")
         p = self.local_gid[self.w.pairs()]
         return p[np.lexsort((p[:, 1], p[:, 0]))]
 

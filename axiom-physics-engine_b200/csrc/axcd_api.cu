@@ -48,6 +48,9 @@ struct AxcdContext {
     bool slabOn = false;
     float slabLo = 0.0f, slabHi = 0.0f;
     uint32_t nOwned = 0;             // slab mode: bodies [0, nOwned) are owned, the rest are ghosts
+    float4* dGhostSend = nullptr;    // slab mode: numRanks send buffers of ghost records
+    uint32_t* dGhostCount = nullptr;
+    uint32_t ghostRanks = 0, ghostCap = 0;
     float* dAabb = nullptr;          // n * 6 floats (axiom::math::AABB AoS)
     uint32_t* dKeys[2] = {nullptr, nullptr};
     uint32_t* dVals[2] = {nullptr, nullptr};
@@ -220,7 +223,7 @@ void axcd_destroy(AxcdContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
+    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
@@ -717,6 +720,65 @@ int32_t axcd_set_ghosts(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts, con
         CU(cudaMemcpyAsync(ctx->dXf + (size_t)nOwned * 10, transforms40, (size_t)nGhosts * 40, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->dShapes + nOwned, shapes, sizeof(AxcdShape) * nGhosts, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->dBodyKeys + nOwned, keys, sizeof(uint32_t) * nGhosts, cudaMemcpyHostToDevice, st));
+    }
+    if (ctx->n != nOwned + nGhosts) {
+        const int rc = resizeBodies(ctx, nOwned + nGhosts);
+        if (rc) return rc;
+    }
+    ctx->stage = ST_POSES;
+    return AXCD_OK;
+}
+
+int32_t axcd_pack_ghosts(AxcdContext* ctx, const float* edges, uint32_t numRanks, uint32_t myRank, void** outDevPtrs,
+                         uint32_t* outCounts) {
+    if (!ctx || !edges || !outDevPtrs || !outCounts) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_REFIT) return AXCD_ERR_GPU_INVALID_OP;
+    if (numRanks == 0 || numRanks > 64 || myRank >= numRanks) return AXCD_ERR_INVALID_PARAM;
+    if (ctx->nHull) return AXCD_ERR_INVALID_SHAPE;   // hull ghosts would need their vertices shipped too
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    const uint32_t cap = ctx->cfg.maxBodies - ctx->nOwned;
+    if (ctx->ghostRanks != numRanks || ctx->ghostCap != cap || !ctx->dGhostSend) {
+        if (ctx->dGhostSend) cudaFree(ctx->dGhostSend);
+        if (ctx->dGhostCount) cudaFree(ctx->dGhostCount);
+        ctx->dGhostSend = nullptr;
+        ctx->dGhostCount = nullptr;
+        CU(dalloc(&ctx->dGhostSend, (size_t)numRanks * cap * (kGhostWords / 4)));
+        CU(dalloc(&ctx->dGhostCount, (size_t)numRanks));
+        ctx->ghostRanks = numRanks;
+        ctx->ghostCap = cap;
+    }
+    CU(cudaMemsetAsync(ctx->dGhostCount, 0, sizeof(uint32_t) * numRanks, st));
+    const uint32_t blocks = (ctx->nOwned + 255) / 256;
+    for (uint32_t r = 0; r < numRanks; ++r) {
+        outDevPtrs[r] = nullptr;
+        outCounts[r] = 0;
+        if (r == myRank || ctx->nOwned == 0) continue;
+        float4* buf = ctx->dGhostSend + (size_t)r * cap * (kGhostWords / 4);
+        packGhostsKernel<<<blocks, 256, 0, st>>>(ctx->dAabb, ctx->dXf, ctx->dShapes, ctx->dBodyKeys, ctx->nOwned, edges[r],
+                                                 edges[r + 1], buf, cap, ctx->dGhostCount + r);
+        outDevPtrs[r] = buf;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(outCounts, ctx->dGhostCount, sizeof(uint32_t) * numRanks, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    bool over = false;
+    for (uint32_t r = 0; r < numRanks; ++r)
+        if (outCounts[r] > cap) over = true;
+    return over ? AXCD_ERR_OUT_OF_RANGE : AXCD_OK;
+}
+
+int32_t axcd_set_ghosts_device(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts, const void* devRecords) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;
+    if (nGhosts && !devRecords) return AXCD_ERR_NULL_POINTER;
+    if (nOwned != ctx->nOwned) return AXCD_ERR_INVALID_PARAM;
+    if ((uint64_t)nOwned + nGhosts > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (nGhosts) {
+        unpackGhostsKernel<<<(nGhosts + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const float4*>(devRecords), nGhosts, nOwned,
+                                                                            ctx->dXf, ctx->dShapes, ctx->dBodyKeys);
+        CU(cudaGetLastError());
     }
     if (ctx->n != nOwned + nGhosts) {
         const int rc = resizeBodies(ctx, nOwned + nGhosts);

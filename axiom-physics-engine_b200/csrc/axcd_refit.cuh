@@ -199,4 +199,54 @@ mortonKernel(const float4* __restrict__ aabb4, const uint32_t* __restrict__ worl
     vals[base + tid] = base + tid;
 }
 
+// ---- x-slab mode: ghost records --------------------------------------------------------------------
+// A ghost record is 16 floats (64 B): Transform (10), shape (4 words), global id, pad.
+constexpr int kGhostWords = 16;
+
+// Packs every owned body whose closed x-interval [min.x, max.x] meets the half-open slab [lo, hi) of
+// a destination rank into that rank's send buffer (warp-aggregated append; order is irrelevant, the
+// pair orientation comes from the global ids).
+__global__ void packGhostsKernel(const float* __restrict__ aabb, const float* __restrict__ xf,
+                                 const uint4* __restrict__ shapes, const uint32_t* __restrict__ keys,
+                                 uint32_t nOwned, float lo, float hi, float4* __restrict__ out, uint32_t cap,
+                                 uint32_t* __restrict__ counter) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false;
+    if (i < nOwned) {
+        const float mn = __ldg(aabb + (size_t)i * 6), mx = __ldg(aabb + (size_t)i * 6 + 3);
+        take = mn < hi && mx >= lo;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, take);
+    if (!bal) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(counter, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (!take) return;
+    const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+    if (slot >= cap) return;   // counted, not stored: the host sees counter > cap
+    const float* t = xf + (size_t)i * 10;
+    const uint4 sh = __ldg(shapes + i);
+    float4* o = out + (size_t)slot * (kGhostWords / 4);
+    o[0] = make_float4(t[0], t[1], t[2], t[3]);
+    o[1] = make_float4(t[4], t[5], t[6], t[7]);
+    o[2] = make_float4(t[8], t[9], __uint_as_float(sh.x), __uint_as_float(sh.y));
+    o[3] = make_float4(__uint_as_float(sh.z), __uint_as_float(sh.w), __uint_as_float(__ldg(keys + i)), 0.0f);
+}
+
+// Appends received ghost records after the owned bodies.
+__global__ void unpackGhostsKernel(const float4* __restrict__ in, uint32_t count, uint32_t first,
+                                   float* __restrict__ xf, uint4* __restrict__ shapes, uint32_t* __restrict__ keys) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= count) return;
+    const float4* r = in + (size_t)g * (kGhostWords / 4);
+    const float4 a = r[0], b = r[1], c = r[2], d = r[3];
+    float* t = xf + (size_t)(first + g) * 10;
+    t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w;
+    t[4] = b.x; t[5] = b.y; t[6] = b.z; t[7] = b.w;
+    t[8] = c.x; t[9] = c.y;
+    shapes[first + g] = make_uint4(__float_as_uint(c.z), __float_as_uint(c.w), __float_as_uint(d.x), __float_as_uint(d.y));
+    keys[first + g] = __float_as_uint(d.z);
+}
+
 }  // namespace axcd

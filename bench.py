@@ -158,8 +158,8 @@ def run_reference(args):
 
 def run_slab(args):
     """--workload C4: one scene split into x-slabs, one slab per rank; ghosts travel over NCCL
-    (axcd/sharding.py SlabRank).  The ownership rule and the orientation by global id run inside the
-    traversal kernel; ghost selection is still host-side numpy on the owned AABBs, so this mode is
+    (axcd/sharding.py SlabRank).  Ghost selection, the ownership rule and the orientation by global id all
+    run on the device; the exchange goes through torch.distributed, so this mode is
     timed with a wall clock (barrier + synchronize on both sides), max over ranks; the device time of
     the collision step alone is reported next to it."""
     import numpy as np
@@ -191,14 +191,14 @@ def run_slab(args):
         torch.cuda.synchronize()
 
     for _ in range(max(1, min(args.warmup, 3))):
-        st = rk.step(d, dev)
+        st = rk.step_device(d)
     steps = max(1, min(args.steps, 20))
     barrier()
     t0 = time.perf_counter()
     units = 0
     dev_ms = 0.0
     for _ in range(steps):
-        st = rk.step(d, dev)
+        st = rk.step_device(d)
         units += st.numPairs + st.numContacts
         dev_ms += st.totalMs
     barrier()
@@ -223,9 +223,9 @@ def run_slab(args):
                        "parallelism": f"{world} x-slabs, ghost bodies exchanged point-to-point over NCCL, "
                                       "x* ownership rule for de-duplication",
                        "device_ms_per_step_rank0": dev_ms / steps,
-                       "note": "wall-clock per step includes the host-side ghost selection (numpy on the "
-                               "owned AABBs) and the NCCL exchange; device_ms is the CUDA-event time of "
-                               "refit+broadphase+narrowphase on rank 0"},
+                       "note": "wall-clock per step = refit + device-side ghost selection + NCCL exchange of "
+                               "the ghost records + refit/broadphase/narrowphase; device_ms is the "
+                               "CUDA-event time of the last three on rank 0"},
             "gpu_launches": None}))
     if world > 1:
         dist.destroy_process_group()

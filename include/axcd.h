@@ -175,6 +175,18 @@ AXCD_API int32_t axcd_set_ghosts(AxcdContext* ctx, uint32_t nOwned, uint32_t nGh
                                  const void* transforms40, const AxcdShape* shapes,
                                  const uint32_t* keys);
 
+/* Device-side variant of the ghost hand-off (no host copies).  axcd_pack_ghosts (after axcd_refit):
+ * for every destination rank r != myRank selects the owned bodies whose x-interval meets slab
+ * [edges[r], edges[r+1]) and packs them as 64-byte records into a device buffer; outDevPtrs[r] /
+ * outCounts[r] (host arrays of numRanks entries) receive the DEVICE pointer and the record count
+ * (outDevPtrs[myRank] = NULL).  The caller moves the records rank to rank (NCCL) and appends what it
+ * received — one contiguous device buffer of nGhosts records — with axcd_set_ghosts_device.
+ * Returns 601 if a send buffer was too small (capacity: maxBodies - nOwned records each).       */
+AXCD_API int32_t axcd_pack_ghosts(AxcdContext* ctx, const float* edges, uint32_t numRanks,
+                                  uint32_t myRank, void** outDevPtrs, uint32_t* outCounts);
+AXCD_API int32_t axcd_set_ghosts_device(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts,
+                                        const void* devRecords);
+
 /* == axiom::core::errorCodeToString (src/core/error_code.cpp:5-62); static storage.            */
 AXCD_API const char* axcd_error_string(int32_t code);
 /* CUDA error text of the last failure on this context (static storage), "" if none.           */

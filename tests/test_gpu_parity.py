@@ -357,3 +357,38 @@ def test_slab_rank_fast_path_virtual_ranks():
     con = np.concatenate(got_c)
     con = con[np.lexsort((con["b"], con["a"]))]
     assert np.array_equal(con, ref_con)
+
+
+def test_slab_rank_device_side_ghosts_match_host_side():
+    """axcd_pack_ghosts / axcd_set_ghosts_device: ghost selection and hand-off entirely on the device
+    must give every rank the same pair / contact counts as the host-side selection."""
+    import torch
+    from axcd import sharding
+    s = axcd.config_scene("C1", scale=0.2)
+    size = 3
+    cx = s.xf[:, 0]
+    edges = sharding.plan_slabs(cx, size)
+    owner = sharding.owner_of(cx, edges)
+    ranks = []
+    for r in range(size):
+        mine = np.nonzero(owner == r)[0]
+        ranks.append(sharding.SlabRank(sharding._subset(s, mine), mine.astype(np.uint32), edges, r, size))
+    host_payloads = [rk.ghost_payloads(rk.owned_aabbs()) for rk in ranks]
+    host_counts = []
+    for r, rk in enumerate(ranks):
+        st = rk.step_with([host_payloads[o][r] for o in range(size) if o != r])
+        host_counts.append((st.numBodies, st.numPairs, st.numContacts))
+    dev_payloads = [rk.pack_device() for rk in ranks]
+    for r, rk in enumerate(ranks):
+        for o in range(size):
+            if o != r:   # same ghost sets as the host path (order may differ)
+                assert dev_payloads[o][r].numel() // 16 == (len(host_payloads[o][r]) - 2) // 15
+        st = rk.step_with_device([dev_payloads[o][r].clone() for o in range(size) if o != r])
+        assert (st.numBodies, st.numPairs, st.numContacts) == host_counts[r]
+    total_pairs = sum(c[1] for c in host_counts)
+    w = axcd.CollisionWorld.for_scene(s)
+    assert w.step().numPairs == total_pairs
+    w.close()
+    for rk in ranks:
+        rk.close()
+    torch.cuda.synchronize()

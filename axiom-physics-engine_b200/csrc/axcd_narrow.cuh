@@ -1007,7 +1007,10 @@ constexpr int kEpaThreads = 128;
 constexpr int kEpaSmemBytes =
     Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, kEpaThreads>::kWords * kEpaThreads * (int)sizeof(float);
 constexpr int kEpaChunk = 64;        // queue items a warp claims at a time
-constexpr int kEpaBatchLanes = 8;    // refill / finalize once this many lanes wait for it
+#ifndef AXCD_EPA_BATCH
+#define AXCD_EPA_BATCH 16
+#endif
+constexpr int kEpaBatchLanes = AXCD_EPA_BATCH;    // refill / finalize once this many lanes wait for it
 
 // What a lane carries for the pair it is expanding.
 struct EpaLane {

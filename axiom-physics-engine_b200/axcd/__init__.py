@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
-    "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
+    "axcd_set_filters", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
     "axcd_set_ghosts_device",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
 ]
@@ -100,7 +100,7 @@ def load_library():
                      "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
                      "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
                      "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
-                     "axcd_pack_ghosts", "axcd_set_ghosts_device"):
+                     "axcd_pack_ghosts", "axcd_set_ghosts_device", "axcd_set_filters"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -119,6 +119,7 @@ def load_library():
         lib.axcd_set_slab.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint32]
         lib.axcd_set_body_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         lib.axcd_set_ghosts.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.axcd_set_filters.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         lib.axcd_pack_ghosts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.axcd_set_ghosts_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         lib.axcd_test_sort_bench.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -380,6 +381,14 @@ class CollisionWorld:
         self._check(self._lib.axcd_get_contacts(self._ctx, C.c_void_p(host_ptr), cap,
                                                 C.byref(cnt)), "axcd_get_contacts")
         return cnt.value
+
+    def set_filters(self, filters):
+        """filters: (n,3) array of (categoryBits, maskBits, groupIndex) or None to switch filtering off."""
+        if filters is None:
+            self._check(self._lib.axcd_set_filters(self._ctx, None, 0), "axcd_set_filters")
+            return
+        f = np.ascontiguousarray(filters, dtype=np.int64).reshape(-1, 3).astype(np.uint32)
+        self._check(self._lib.axcd_set_filters(self._ctx, _ptr(f), len(f)), "axcd_set_filters")
 
     # ---- x-slab mode (one scene across several GPUs) -------------------------------------------
     def set_slab(self, x_lo, x_hi, enable=True):

@@ -45,6 +45,8 @@ struct AxcdContext {
     float4* dHull = nullptr;
     uint32_t* dWorld = nullptr;
     uint32_t* dBodyKeys = nullptr;   // slab mode: global id of every local body
+    uint4* dFilters = nullptr;       // (category, mask, group, pad) per body
+    bool filtersOn = false;
     bool slabOn = false;
     float slabLo = 0.0f, slabHi = 0.0f;
     uint32_t nOwned = 0;             // slab mode: bodies [0, nOwned) are owned, the rest are ghosts
@@ -223,7 +225,7 @@ void axcd_destroy(AxcdContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
+    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
@@ -345,8 +347,8 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
             memcpy(&first, &s.p0, 4);
             memcpy(&cnt, &s.p1, 4);
             if (cnt == 0 || cnt > 65535u || (uint64_t)first + cnt > nHullVerts) return AXCD_ERR_INVALID_SHAPE;
-        } else if (s.type != AXCD_SHAPE_SPHERE && s.type != AXCD_SHAPE_BOX) {
-            return AXCD_ERR_INVALID_SHAPE;   // Capsule / Plane / Mesh are not in scope
+        } else if (s.type != AXCD_SHAPE_SPHERE && s.type != AXCD_SHAPE_BOX && s.type != AXCD_SHAPE_CAPSULE) {
+            return AXCD_ERR_INVALID_SHAPE;   // Plane / Mesh are not in scope
         }
         if (ctx->cfg.numWorlds > 1 && worldId[i] >= ctx->cfg.numWorlds) return AXCD_ERR_OUT_OF_RANGE;
     }
@@ -478,7 +480,8 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes,
                                                      ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
                                                      ctx->cfg.maxPairs, ctx->dBodyCount,
-                                                     SlabRule{ctx->slabOn ? 1 : 0, ctx->slabLo, ctx->slabHi, ctx->dBodyKeys}, ctx->dCtr);
+                                                     SlabRule{ctx->slabOn ? 1 : 0, ctx->slabLo, ctx->slabHi, ctx->dBodyKeys},
+                                                     ctx->filtersOn ? ctx->dFilters : nullptr, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIR);
         // ---- canonical order: counting sort by body a, then tiny per-body sorts by b ------------------
@@ -687,6 +690,27 @@ int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap, uint
     return AXCD_OK;
 }
 
+int32_t axcd_set_filters(AxcdContext* ctx, const AxcdFilter* filters, uint32_t n) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (!filters) {
+        ctx->filtersOn = false;
+        return AXCD_OK;
+    }
+    if (n > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (!ctx->dFilters) CU(dalloc(&ctx->dFilters, (size_t)ctx->cfg.maxBodies));
+    uint4* tmp = static_cast<uint4*>(malloc(sizeof(uint4) * (n ? n : 1)));
+    if (!tmp) return AXCD_ERR_OUT_OF_MEMORY;
+    for (uint32_t i = 0; i < n; ++i)
+        tmp[i] = make_uint4(filters[i].categoryBits, filters[i].maskBits, (uint32_t)filters[i].groupIndex, 0u);
+    cudaError_t e = cudaMemcpyAsync(ctx->dFilters, tmp, sizeof(uint4) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    free(tmp);
+    if (e != cudaSuccess) return fail(ctx, e, "filter upload");
+    ctx->filtersOn = true;
+    return AXCD_OK;
+}
+
 int32_t axcd_set_slab(AxcdContext* ctx, float xLo, float xHi, uint32_t enable) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
     if (enable && !(xLo <= xHi)) return AXCD_ERR_INVALID_PARAM;
@@ -713,7 +737,9 @@ int32_t axcd_set_ghosts(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts, con
     if (nOwned != ctx->nOwned) return AXCD_ERR_INVALID_PARAM;
     if ((uint64_t)nOwned + nGhosts > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
     for (uint32_t i = 0; i < nGhosts; ++i)
-        if (shapes[i].type != AXCD_SHAPE_SPHERE && shapes[i].type != AXCD_SHAPE_BOX) return AXCD_ERR_INVALID_SHAPE;
+        if (shapes[i].type != AXCD_SHAPE_SPHERE && shapes[i].type != AXCD_SHAPE_BOX &&
+            shapes[i].type != AXCD_SHAPE_CAPSULE)
+            return AXCD_ERR_INVALID_SHAPE;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     cudaStream_t st = ctx->stream;
     if (nGhosts) {

@@ -201,6 +201,14 @@ __device__ __forceinline__ bool boxesIntersect(float ax0, float ay0, float az0, 
     return ax0 <= bx1 && ax1 >= bx0 && ay0 <= by1 && ay1 >= by0 && az0 <= bz1 && az1 >= bz0;
 }
 
+// gui::FilterInfo rule (include/axiom/gui/body_inspector.hpp:38-42); records are (category, mask, group, pad)
+__device__ __forceinline__ bool shouldCollide(const uint4* __restrict__ filt, uint32_t i, uint32_t j) {
+    const uint4 a = __ldg(filt + i), b = __ldg(filt + j);
+    const int ga = (int)a.z, gb = (int)b.z;
+    if (ga == gb && ga != 0) return ga > 0;
+    return (a.y & b.x) != 0u && (a.x & b.y) != 0u;
+}
+
 struct SlabRule {
     int enabled;
     float lo, hi;            // this rank's slab [lo, hi) on the x axis
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(kTravThreads)
 findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ leafHi,
                 const BvhNode* __restrict__ nodes, const uint32_t* __restrict__ worldEnd, uint32_t n,
                 uint2* __restrict__ pairs, uint32_t maxPairs, uint32_t* __restrict__ bodyCount,
-                SlabRule slab, Counters* __restrict__ ctr) {
+                SlabRule slab, const uint4* __restrict__ filters, Counters* __restrict__ ctr) {
     __shared__ uint2 sPool[kTravPool];
     __shared__ uint32_t sCount, sBase;
     if (threadIdx.x == 0) sCount = 0;
@@ -252,6 +260,7 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                 }
                 const uint32_t bodyJ = __float_as_uint(__ldg(&leafLo[child].w));
                 uint2 pr = make_uint2(min(bodyI, bodyJ), max(bodyI, bodyJ));
+                if (filters && !shouldCollide(filters, bodyI, bodyJ)) continue;
                 if (slab.enabled) {
                     // one huge scene split into x-slabs: this rank reports the pair only if the left end
                     // of the pair's x-overlap, max(min_i.x, min_j.x), lies in its slab (exactly one rank

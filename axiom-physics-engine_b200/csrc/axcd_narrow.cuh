@@ -16,7 +16,7 @@
 
 namespace axcd {
 
-enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2 };
+enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2, CORE_SEGMENT = 3 };
 
 struct Core {
     int kind;
@@ -72,6 +72,13 @@ __device__ __forceinline__ Core makeCore(const BodyPose& t, uint4 sh, const floa
     if (sh.x == AXCD_SHAPE_SPHERE) {
         k.kind = CORE_POINT;
         k.r = p0;
+    } else if (sh.x == AXCD_SHAPE_CAPSULE) {
+        // segment core along the local Y axis (half length height/2, scaled by scale.y) + radius
+        k.kind = CORE_SEGMENT;
+        V3 c0, c1, c2;
+        quatToColumns(t.q, c0, c1, c2);
+        k.e0 = c1 * ((p1 * 0.5f) * t.s.y);
+        k.r = p0;
     } else if (sh.x == AXCD_SHAPE_BOX) {
         k.kind = CORE_BOX;
         V3 c0, c1, c2;
@@ -95,6 +102,11 @@ __device__ __forceinline__ Core makeCore(const BodyPose& t, uint4 sh, const floa
 __device__ __forceinline__ V3 support(const Core& k, V3 d, uint32_t& id) {
     id = 0;
     if (k.kind == CORE_POINT) return k.c;
+    if (k.kind == CORE_SEGMENT) {
+        const bool n0 = !(dot3(d, k.e0) >= 0.0f);
+        id = n0 ? 1u : 0u;
+        return k.c + (n0 ? -k.e0 : k.e0);
+    }
     if (k.kind == CORE_BOX) {
         const bool n0 = !(dot3(d, k.e0) >= 0.0f), n1 = !(dot3(d, k.e1) >= 0.0f), n2 = !(dot3(d, k.e2) >= 0.0f);
         id = (n0 ? 1u : 0u) | (n1 ? 2u : 0u) | (n2 ? 4u : 0u);
@@ -123,6 +135,7 @@ __device__ __forceinline__ V3 support(const Core& k, V3 d, uint32_t& id) {
 
 __device__ __forceinline__ V3 pointFromId(const Core& k, uint32_t id) {
     if (k.kind == CORE_POINT) return k.c;
+    if (k.kind == CORE_SEGMENT) return k.c + ((id & 1u) ? -k.e0 : k.e0);
     if (k.kind == CORE_BOX) {
         V3 p = k.c;
         p = p + ((id & 1u) ? -k.e0 : k.e0);
@@ -745,7 +758,9 @@ constexpr int kNumClasses = 6;
 
 // Pair class by core kinds, so that a warp runs one kind of support function.
 __device__ __forceinline__ int pairClass(uint32_t typeA, uint32_t typeB) {
-    if (typeA == AXCD_SHAPE_CONVEX || typeB == AXCD_SHAPE_CONVEX) return 5;
+    if (typeA == AXCD_SHAPE_CONVEX || typeB == AXCD_SHAPE_CONVEX || typeA == AXCD_SHAPE_CAPSULE ||
+        typeB == AXCD_SHAPE_CAPSULE)
+        return 5;   // hulls and capsules share the "other" class
     if (typeA == AXCD_SHAPE_SPHERE) return (typeB == AXCD_SHAPE_SPHERE) ? 1 : 2;   // SS, point-box
     return (typeB == AXCD_SHAPE_SPHERE) ? 3 : 4;                                   // box-point, box-box
 }

@@ -83,6 +83,18 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
 #pragma unroll
             for (int k = 1; k < 8; ++k)
                 expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(sx[k] * p0, sy[k] * p1, sz[k] * p2)));
+        } else if (sh.x == AXCD_SHAPE_CAPSULE) {
+            // p0 = radius, p1 = height: box of the two end spheres, endpoints placed as the reference
+            // does (src/debug/physics_debug_draw.cpp:254-266: local (0, -+height/2, 0) through
+            // transformPoint); the radius is not scaled
+            const V3 half = mk3(0.0f, p1 * 0.5f, 0.0f);
+            const V3 start = transformPoint(pos, q, scl, -half);
+            const V3 end = transformPoint(pos, q, scl, half);
+            lo = start;
+            hi = start;
+            expandPoint(lo, hi, end);
+            lo = lo - mk3(p0, p0, p0);
+            hi = hi + mk3(p0, p0, p0);
         } else {   // AXCD_SHAPE_CONVEX (validated on the host): min/max over transformPoint(v_i)
             const uint32_t first = sh.y, count = sh.z;
             float4 v = __ldg(hull + first);

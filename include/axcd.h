@@ -53,13 +53,15 @@ enum {
 };
 
 /* ---- shape types: numeric order of debug::ShapeType (include/axiom/debug/physics_debug_draw.hpp:87-94)
- * Only Sphere, Box and Convex are in scope; Capsule/Plane/Mesh -> AXCD_ERR_INVALID_SHAPE.      */
+ * Sphere, Box, Capsule and Convex are in scope; Plane/Mesh -> AXCD_ERR_INVALID_SHAPE.            */
 enum { AXCD_SHAPE_SPHERE = 0, AXCD_SHAPE_BOX = 1, AXCD_SHAPE_CAPSULE = 2, AXCD_SHAPE_PLANE = 3,
        AXCD_SHAPE_CONVEX = 4, AXCD_SHAPE_MESH = 5 };
 
 /* Flattened debug::DebugShape (physics_debug_draw.hpp:97-112): 16-byte POD.
  *   Sphere : p0 = radius                                  (DebugShape::radius)
  *   Box    : p0,p1,p2 = halfExtents.x/y/z                  (DebugShape::halfExtents)
+ *   Capsule: p0 = radius, p1 = height of the segment between the cap centres, local Y axis
+ *            (DebugShape::radius / height; src/debug/physics_debug_draw.cpp:254-266)
  *   Convex : p0 = bit pattern of uint32 firstVertex, p1 = bit pattern of uint32 vertexCount,
  *            indexing the xyz-packed hull vertex pool (DebugShape::vertices / vertexCount,
  *            src/debug/physics_debug_draw.cpp:285-288).                                         */
@@ -159,6 +161,17 @@ AXCD_API int32_t axcd_get_pair_distances(AxcdContext* ctx, float* outDist, uint3
                                          uint32_t* outCount); /* needs AXCD_FLAG_PAIR_DISTANCES */
 AXCD_API int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap,
                                    uint32_t* outCount); /* same (a,b) order                     */
+
+/* Collision filtering, gui::FilterInfo semantics (include/axiom/gui/body_inspector.hpp:38-42):
+ * two bodies with the same non-zero groupIndex collide iff it is positive; otherwise both
+ * (maskBits & other.categoryBits) must be non-zero.  Applied when candidate pairs are emitted.
+ * filters = n records, or NULL to switch filtering off (the default).                           */
+typedef struct AxcdFilter {
+    uint32_t categoryBits;
+    uint32_t maskBits;
+    int32_t groupIndex;
+} AxcdFilter;
+AXCD_API int32_t axcd_set_filters(AxcdContext* ctx, const AxcdFilter* filters, uint32_t n);
 
 /* ---- one huge scene across several GPUs: x-slab mode ---------
  * Bodies [0, nOwned) are the ones this rank owns (set with axcd_set_shapes / axcd_set_transforms as

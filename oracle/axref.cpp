@@ -122,6 +122,18 @@ inline bool intersects(const float* a, const float* b) {   // aabb.hpp:132-135 (
            a[5] >= b[2];
 }
 
+// gui::FilterInfo (include/axiom/gui/body_inspector.hpp:38-42): category / mask bits and a group
+// index, Box2D rule: same non-zero group -> collide iff the group is positive; otherwise both masks
+// must accept the other's category.  filt = n x 3 words (categoryBits, maskBits, groupIndex as int32).
+inline bool shouldCollide(const uint32_t* filt, uint32_t i, uint32_t j) {
+    if (!filt) return true;
+    const uint32_t* a = filt + 3ull * i;
+    const uint32_t* b = filt + 3ull * j;
+    const int32_t ga = (int32_t)a[2], gb = (int32_t)b[2];
+    if (ga == gb && ga != 0) return ga > 0;
+    return (a[1] & b[0]) != 0 && (a[0] & b[1]) != 0;
+}
+
 // DeterministicRNG (include/axiom/math/random.hpp:19-68)
 struct Rng {
     uint64_t state;
@@ -138,7 +150,7 @@ struct Rng {
     float nextFloat() { return static_cast<float>(next()) / static_cast<float>(0x100000000ULL); }
 };
 
-enum { SHAPE_SPHERE = 0, SHAPE_BOX = 1, SHAPE_CONVEX = 4 };
+enum { SHAPE_SPHERE = 0, SHAPE_BOX = 1, SHAPE_CAPSULE = 2, SHAPE_CONVEX = 4 };
 
 inline uint32_t fbits(float f) {
     uint32_t u;
@@ -182,6 +194,19 @@ int refitOne(const Xf& t, const AxrefShape& s, const float* hull, uint32_t nHull
         b.lo = p0;   // AABB(Vec3) (aabb.hpp:47)
         b.hi = p0;
         for (int k = 1; k < 8; ++k) expandPoint(b, transformPoint(t, c[k]));
+    } else if (s.type == SHAPE_CAPSULE) {
+        // p0 = radius, p1 = height.  Endpoints as the reference places them
+        // (src/debug/physics_debug_draw.cpp:254-266): local (0, -+height/2, 0) through transformPoint;
+        // the radius is not scaled.  Box of the two end spheres.
+        V3 half = mk(0.0f, s.p1 * 0.5f, 0.0f);
+        V3 start = transformPoint(t, -half);
+        V3 end = transformPoint(t, half);
+        b.lo = start;
+        b.hi = start;
+        expandPoint(b, end);
+        V3 r = mk(s.p0, s.p0, s.p0);
+        b.lo = b.lo - r;
+        b.hi = b.hi + r;
     } else if (s.type == SHAPE_CONVEX) {
         uint32_t first = fbits(s.p0), cnt = fbits(s.p1);
         if (cnt == 0 || static_cast<uint64_t>(first) + cnt > nHull) return 300;
@@ -208,7 +233,7 @@ int refitOne(const Xf& t, const AxrefShape& s, const float* hull, uint32_t nHull
 // Stage 3: narrowphase.  Convex "cores" in a frame translated so body A's position is the origin
 // (axes stay world-aligned).  Sphere = point core + radius margin; box and hull have no margin.
 // ------------------------------------------------------------------------------------------
-enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2 };
+enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2, CORE_SEGMENT = 3 };
 struct Core {
     int kind;
     V3 c;            // centre relative to A's position
@@ -225,6 +250,12 @@ Core makeCore(const Xf& t, const AxrefShape& sh, const float* hull, V3 origin) {
     k.r = 0.0f;
     if (sh.type == SHAPE_SPHERE) {
         k.kind = CORE_POINT;
+        k.r = sh.p0;
+    } else if (sh.type == SHAPE_CAPSULE) {
+        // segment core along the local Y axis (half length height/2, scaled by scale.y) + radius
+        k.kind = CORE_SEGMENT;
+        M3 m = quatToMat3(t.q);
+        k.e0 = m.c1 * ((sh.p1 * 0.5f) * t.s.y);
         k.r = sh.p0;
     } else if (sh.type == SHAPE_BOX) {
         k.kind = CORE_BOX;
@@ -246,6 +277,7 @@ Core makeCore(const Xf& t, const AxrefShape& sh, const float* hull, V3 origin) {
 // Support point of a core in world-aligned direction d (need not be unit length).
 V3 support(const Core& k, V3 d) {
     if (k.kind == CORE_POINT) return k.c;
+    if (k.kind == CORE_SEGMENT) return k.c + ((dot(d, k.e0) >= 0.0f) ? k.e0 : -k.e0);
     if (k.kind == CORE_BOX) {
         V3 p = k.c;
         p = p + ((dot(d, k.e0) >= 0.0f) ? k.e0 : -k.e0);
@@ -820,13 +852,14 @@ int32_t axref_refit(const float* xf, const AxrefShape* shapes, uint32_t n, const
     return 0;
 }
 
-int32_t axref_broadphase_brute(const float* aabb, uint32_t n, const uint32_t* worldId,
-                               uint32_t* outPairs, uint64_t cap, uint64_t* outCount) {
+int32_t axref_broadphase_brute_f(const float* aabb, uint32_t n, const uint32_t* worldId, const uint32_t* filt,
+                                 uint32_t* outPairs, uint64_t cap, uint64_t* outCount) {
     uint64_t cnt = 0;
     for (uint32_t i = 0; i < n; ++i)
         for (uint32_t j = i + 1; j < n; ++j) {
             if (worldId && worldId[i] != worldId[j]) continue;
             if (!intersects(aabb + 6ull * i, aabb + 6ull * j)) continue;
+            if (!shouldCollide(filt, i, j)) continue;
             if (cnt < cap) {
                 outPairs[2 * cnt] = i;
                 outPairs[2 * cnt + 1] = j;
@@ -840,9 +873,21 @@ int32_t axref_broadphase_brute(const float* aabb, uint32_t n, const uint32_t* wo
 // Uniform grid keyed on the AABB centre with cell edge >= the largest AABB extent: two
 // intersecting boxes then have centres at most one cell apart on every axis, so the 27-cell
 // neighbourhood is complete.  The overlap decision itself is always the exact predicate above.
+int32_t axref_broadphase_brute(const float* aabb, uint32_t n, const uint32_t* worldId,
+                               uint32_t* outPairs, uint64_t cap, uint64_t* outCount) {
+    return axref_broadphase_brute_f(aabb, n, worldId, nullptr, outPairs, cap, outCount);
+}
+
+int32_t axref_broadphase_grid_f(const float* aabb, uint32_t n, const uint32_t* worldId, const uint32_t* filt,
+                                uint32_t* outPairs, uint64_t cap, uint64_t* outCount, int nthreads);
 int32_t axref_broadphase_grid(const float* aabb, uint32_t n, const uint32_t* worldId,
                               uint32_t* outPairs, uint64_t cap, uint64_t* outCount,
                               int nthreads) {
+    return axref_broadphase_grid_f(aabb, n, worldId, nullptr, outPairs, cap, outCount, nthreads);
+}
+
+int32_t axref_broadphase_grid_f(const float* aabb, uint32_t n, const uint32_t* worldId, const uint32_t* filt,
+                                uint32_t* outPairs, uint64_t cap, uint64_t* outCount, int nthreads) {
     *outCount = 0;
     if (n == 0) return 0;
     // bodies with a NaN/inf box never intersect anything (every compare is false / handled by
@@ -918,7 +963,7 @@ int32_t axref_broadphase_grid(const float* aabb, uint32_t n, const uint32_t* wor
                         const uint32_t j = items[p];
                         if (j <= i) continue;
                         if (worldId && worldId[i] != worldId[j]) continue;
-                        if (intersects(aabb + 6ull * i, aabb + 6ull * j))
+                        if (intersects(aabb + 6ull * i, aabb + 6ull * j) && shouldCollide(filt, i, j))
                             out.push_back(((uint64_t)i << 32) | j);
                     }
                 }
@@ -932,7 +977,7 @@ int32_t axref_broadphase_grid(const float* aabb, uint32_t n, const uint32_t* wor
             if (worldId && worldId[i] != worldId[j]) continue;
             bool jOdd = std::binary_search(odd.begin(), odd.end(), j);
             if (jOdd && j < i) continue;   // odd-odd pairs once
-            if (intersects(aabb + 6ull * i, aabb + 6ull * j)) {
+            if (intersects(aabb + 6ull * i, aabb + 6ull * j) && shouldCollide(filt, i, j)) {
                 uint32_t a = std::min(i, j), b = std::max(i, j);
                 found[0].push_back(((uint64_t)a << 32) | b);
             }

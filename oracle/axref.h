@@ -52,6 +52,13 @@ int32_t axref_broadphase_brute(const float* aabb, uint32_t n, const uint32_t* wo
 int32_t axref_broadphase_grid(const float* aabb, uint32_t n, const uint32_t* worldId,
                               uint32_t* outPairs, uint64_t cap, uint64_t* outCount, int nthreads);
 
+/* the same with collision filters: filt = n x 3 words (categoryBits, maskBits, groupIndex as int32),
+ * gui::FilterInfo semantics (include/axiom/gui/body_inspector.hpp:38-42); NULL = no filtering.  */
+int32_t axref_broadphase_brute_f(const float* aabb, uint32_t n, const uint32_t* worldId, const uint32_t* filt,
+                                 uint32_t* outPairs, uint64_t cap, uint64_t* outCount);
+int32_t axref_broadphase_grid_f(const float* aabb, uint32_t n, const uint32_t* worldId, const uint32_t* filt,
+                                uint32_t* outPairs, uint64_t cap, uint64_t* outCount, int nthreads);
+
 /* stage 3: narrowphase over given pairs (in the given order).  outDist may be NULL.           */
 int32_t axref_narrowphase(const float* xf, const AxrefShape* shapes, uint32_t n,
                           const float* hullXYZ, uint32_t nHullVerts, const uint32_t* pairs,

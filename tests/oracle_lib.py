@@ -41,6 +41,8 @@ def lib():
         _LIB.axref_refit.restype = C.c_int32
         _LIB.axref_broadphase_brute.restype = C.c_int32
         _LIB.axref_broadphase_grid.restype = C.c_int32
+        _LIB.axref_broadphase_brute_f.restype = C.c_int32
+        _LIB.axref_broadphase_grid_f.restype = C.c_int32
         _LIB.axref_narrowphase.restype = C.c_int32
         _LIB.axref_collide_pair.restype = C.c_int32
         _LIB.axref_aabb_intersects.restype = C.c_int
@@ -106,21 +108,23 @@ def refit(xf, shapes, hull=None, margin=0.0, nthreads=1):
     return rc, out
 
 
-def broadphase(aabb, world_id=None, brute=False, nthreads=1, cap=None):
+def broadphase(aabb, world_id=None, brute=False, nthreads=1, cap=None, filters=None):
     aabb = f32(aabb).reshape(-1, 6)
     n = aabb.shape[0]
     wid = np.ascontiguousarray(world_id, dtype=np.uint32) if world_id is not None else None
+    flt = (np.ascontiguousarray(np.asarray(filters, dtype=np.int64).reshape(-1, 3).astype(np.uint32))
+           if filters is not None else None)   # groupIndex is signed: wrap, do not range-check
     if cap is None:
         cap = max(1024, 16 * n)
     while True:
         out = np.zeros((cap, 2), np.uint32)
         cnt = C.c_uint64(0)
         if brute:
-            rc = lib().axref_broadphase_brute(_p(aabb), C.c_uint32(n), _p(wid), _p(out),
-                                              C.c_uint64(cap), C.byref(cnt))
+            rc = lib().axref_broadphase_brute_f(_p(aabb), C.c_uint32(n), _p(wid), _p(flt), _p(out),
+                                                C.c_uint64(cap), C.byref(cnt))
         else:
-            rc = lib().axref_broadphase_grid(_p(aabb), C.c_uint32(n), _p(wid), _p(out),
-                                             C.c_uint64(cap), C.byref(cnt), C.c_int(nthreads))
+            rc = lib().axref_broadphase_grid_f(_p(aabb), C.c_uint32(n), _p(wid), _p(flt), _p(out),
+                                               C.c_uint64(cap), C.byref(cnt), C.c_int(nthreads))
         if rc == 601:
             cap = int(cnt.value)
             continue
@@ -182,6 +186,10 @@ def sphere(r):
 
 def box(hx, hy, hz):
     return (1, hx, hy, hz)
+
+
+def capsule(r, height):
+    return (2, r, height, 0.0)
 
 
 def hull_shape(first, count):

@@ -258,7 +258,7 @@ def test_nan_and_touching_boxes():
 def test_error_behaviour():
     w = axcd.CollisionWorld(8)
     with pytest.raises(axcd.AxcdError) as e:
-        w.set_shapes(np.array([(2, 1.0, 1.0, 0.0)], axcd.SHAPE_DT))      # Capsule
+        w.set_shapes(np.array([(3, 1.0, 1.0, 0.0)], axcd.SHAPE_DT))      # Plane
     assert e.value.code == 300
     with pytest.raises(axcd.AxcdError) as e:
         w.set_shapes(np.array([O.hull_shape(0, 4)], axcd.SHAPE_DT))       # hull range outside pool

@@ -112,7 +112,7 @@ def test_refit_hull_matches_numpy_transform_point():
 def test_refit_margin_and_invalid_shape():
     rc, bb = O.refit([O.xf()], [O.sphere(1)], margin=0.25)
     np.testing.assert_array_equal(bb[0], (-1.25, -1.25, -1.25, 1.25, 1.25, 1.25))
-    rc, _ = O.refit([O.xf()], [(2, 1.0, 1.0, 0.0)])  # Capsule -> InvalidShape
+    rc, _ = O.refit([O.xf()], [(3, 1.0, 1.0, 0.0)])  # Plane -> InvalidShape
     assert rc == 300
     rc, _ = O.refit([O.xf()], [O.hull_shape(0, 4)], np.zeros((2, 3), np.float32))
     assert rc == 300

@@ -16,8 +16,9 @@ constexpr uint32_t kFlagInclusive = 2u << 30;
 constexpr uint32_t kFlagMask = 3u << 30;
 constexpr uint32_t kValueMask = ~kFlagMask;
 
-// ---- float3 helpers.  Every expression is evaluated exactly as written (the library is built
-// -fmad=false), matching the reference's Vec3 operators (include/axiom/math/vec3.hpp:52-191). ----
+// ---- float3 helpers.  The library is built -fmad=false, so nothing is contracted implicitly: every
+// expression rounds exactly as written and the only fused operations are the explicit fmaf calls
+// below (reference operators: include/axiom/math/vec3.hpp:52-191). ----
 struct V3 {
     float x, y, z;
 };
@@ -26,9 +27,12 @@ __host__ __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk3(a.x + 
 __host__ __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __host__ __device__ __forceinline__ V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 __host__ __device__ __forceinline__ V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
-__host__ __device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// dot / cross use ONE explicit fused pattern (fmaf = a single rounding), the same one the CPU oracle
+// uses: the reference's own build (-mfma, default contraction) fuses these sums in a compiler-chosen
+// way, so a pinned pattern is as faithful as an unfused one and keeps FFMA throughput on the GPU.
+__host__ __device__ __forceinline__ float dot3(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 __host__ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
-    return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return mk3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
 __host__ __device__ __forceinline__ bool same3(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 
@@ -38,7 +42,8 @@ __device__ __forceinline__ V3 quatRotate(float4 q, V3 v) {
     V3 u = mk3(q.x, q.y, q.z);
     V3 uv = cross3(u, v);
     V3 uuv = cross3(u, uv);
-    return v + ((uv * q.w) + uuv) * 2.0f;
+    V3 t = mk3(fmaf(uv.x, q.w, uuv.x), fmaf(uv.y, q.w, uuv.y), fmaf(uv.z, q.w, uuv.z));
+    return mk3(fmaf(t.x, 2.0f, v.x), fmaf(t.y, 2.0f, v.y), fmaf(t.z, 2.0f, v.z));
 }
 
 // order-preserving float <-> uint mapping for atomicMin/atomicMax on floats

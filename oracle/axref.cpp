@@ -2,8 +2,10 @@
  * axref.cpp — CPU ORACLE for the collision hot path (refit -> broadphase -> GJK/EPA).
  *
  * TEST INFRASTRUCTURE ONLY (see axref.h).  Scalar C++, IEEE binary32, built with
- * -ffp-contract=off so no multiply-add is ever fused: every expression below rounds exactly as
- * written, which is what lets the CUDA path (built -fmad=false) be bit-identical.
+ * -ffp-contract=off so the compiler never fuses a multiply-add on its own: every expression below
+ * rounds exactly as written, and the only fused operations are the explicit std::fmaf calls in
+ * dot / cross / quatRotate.  The CUDA path (built -fmad=false, same explicit fmaf calls) is
+ * therefore bit-identical.
  *
  * What is restated from the reference (file:line under /root/reference) and what is authored:
  *   Vec3 ops ................ include/axiom/math/vec3.hpp:15-280            (restated)
@@ -41,9 +43,14 @@ inline V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); } 
 inline V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }   // vec3.hpp:60
 inline V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }      // vec3.hpp:84
 inline V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }                        // vec3.hpp:100
-inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }        // vec3.hpp:179
-inline V3 cross(V3 a, V3 b) {                                                     // vec3.hpp:188
-    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+// dot / cross: the reference writes them as plain products and sums (vec3.hpp:179-191) and builds
+// with -mfma and GCC's default contraction, which turns those into fused multiply-adds in a
+// compiler-chosen pattern.  This restatement pins ONE explicit pattern (std::fmaf = one rounding),
+// identical in the CUDA kernels, so CPU and GPU stay bit-identical while the GPU keeps FFMA throughput.
+inline float dot(V3 a, V3 b) { return std::fmaf(a.z, b.z, std::fmaf(a.y, b.y, a.x * b.x)); }
+inline V3 cross(V3 a, V3 b) {
+    return mk(std::fmaf(a.y, b.z, -(a.z * b.y)), std::fmaf(a.z, b.x, -(a.x * b.z)),
+              std::fmaf(a.x, b.y, -(a.y * b.x)));
 }
 inline bool same(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
 
@@ -57,7 +64,8 @@ inline V3 quatRotate(Q4 q, V3 v) {
     V3 u = mk(q.x, q.y, q.z);
     V3 uv = cross(u, v);
     V3 uuv = cross(u, uv);
-    return v + ((uv * q.w) + uuv) * 2.0f;
+    V3 t = mk(std::fmaf(uv.x, q.w, uuv.x), std::fmaf(uv.y, q.w, uuv.y), std::fmaf(uv.z, q.w, uuv.z));
+    return mk(std::fmaf(t.x, 2.0f, v.x), std::fmaf(t.y, 2.0f, v.y), std::fmaf(t.z, 2.0f, v.z));
 }
 
 // glm::quat * glm::quat (src/math/quat.cpp:27-31)

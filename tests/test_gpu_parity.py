@@ -392,3 +392,56 @@ def test_slab_rank_device_side_ghosts_match_host_side():
     for rk in ranks:
         rk.close()
     torch.cuda.synchronize()
+
+
+def test_degenerate_pair_zoo_bit_exact():
+    """Thousands of isolated pairs in awkward configurations — coincident centres, axis-aligned
+    rotations, exactly touching faces, zero-size boxes, zero-height capsules, duplicate hull
+    vertices, wildly different scales — all shape combinations.  Every pair sits in its own cell far
+    from the others, so the candidate set is exactly the intended pairs; the CUDA path must agree
+    with the oracle bit for bit on all of them."""
+    rng = np.random.default_rng(1234)
+    npairs = 6000
+    hull_pool = []
+    xf = np.zeros((2 * npairs, 10), np.float32)
+    shapes = np.zeros(2 * npairs, axcd.SHAPE_DT)
+
+    def rand_quat(k):
+        mode = k % 4
+        if mode == 0:
+            return (0, 0, 0, 1)                                             # identity
+        if mode == 1:
+            return O.axis_angle(np.eye(3)[rng.integers(0, 3)], np.pi / 2 * rng.integers(0, 4))   # axis-aligned
+        return O.axis_angle(rng.normal(size=3), rng.uniform(0, 6.28))
+
+    def rand_shape(k):
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            return (0, [0.0, 1e-3, 0.3, 0.5][rng.integers(0, 4)], 0, 0)
+        if kind == 1:
+            h = rng.uniform(0.2, 0.5, 3)
+            if k % 7 == 0:
+                h[rng.integers(0, 3)] = 0.0                                  # flat box
+            return (1, h[0], h[1], h[2])
+        if kind == 2:
+            return (2, rng.uniform(0.05, 0.3), [0.0, 0.6][rng.integers(0, 2)], 0)   # some zero-height capsules
+        first = len(hull_pool)
+        v = rng.normal(size=(8, 3)) * 0.3
+        if k % 5 == 0:
+            v[4:] = v[:4]                                                    # duplicate vertices
+        hull_pool.extend(v.tolist())
+        return (4, np.array([first], np.uint32).view(np.float32)[0], np.array([8], np.uint32).view(np.float32)[0], 0)
+
+    for k in range(npairs):
+        cell = np.array([k % 40, (k // 40) % 40, k // 1600], np.float32) * 10.0
+        offs = [np.zeros(3), np.array([0.5, 0, 0]), np.array([1.0, 0, 0]), rng.uniform(-0.8, 0.8, 3)][k % 4]
+        for side in range(2):
+            i = 2 * k + side
+            xf[i, :3] = cell + (offs if side else 0)
+            xf[i, 3:7] = rand_quat(k + side)
+            xf[i, 7:10] = [1, 1, 1] if k % 3 else rng.uniform(0.25, 3.0, 3)
+            shapes[i] = rand_shape(k + side)
+    s = axcd.Scene(xf, shapes, np.array(hull_pool, np.float32).reshape(-1, 3) if hull_pool else None)
+    st, bitwise = run_and_compare(s)
+    assert bitwise
+    assert st.numPairs > npairs // 2 and st.numContacts > npairs // 4

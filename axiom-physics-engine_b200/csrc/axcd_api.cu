@@ -80,6 +80,7 @@ struct AxcdContext {
     uint32_t* dSortHist = nullptr;
     uint32_t* dSortStatus = nullptr;
     Counters* dCtr = nullptr;
+    Counters* dCtrInit = nullptr;    // per-step initial value of the counters (device copy: async reset)
     void* hPinned = nullptr;         // staging for strided transform uploads
     size_t hPinnedBytes = 0;
     cudaEvent_t ev[EV_COUNT];
@@ -229,7 +230,7 @@ void axcd_destroy(AxcdContext* ctx) {
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
-                    ctx->dSortStatus, ctx->dCtr};
+                    ctx->dSortStatus, ctx->dCtr, ctx->dCtrInit};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
@@ -318,6 +319,16 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         const size_t maxTiles = sortTilesFor(nb > np ? nb : np);
         CU(dalloc(&ctx->dSortStatus, (size_t)kMaxPasses * maxTiles * kRadix));
         CU(dalloc(&ctx->dCtr, 1));
+        CU(dalloc(&ctx->dCtrInit, 1));
+        {
+            Counters init;
+            memset(&init, 0, sizeof(init));
+            for (int k = 0; k < 3; ++k) {
+                init.boundsMin[k] = 0xffffffffu;   // ordered-uint encodings of +inf / -inf
+                init.boundsMax[k] = 0u;
+            }
+            CU(cudaMemcpy(ctx->dCtrInit, &init, sizeof(Counters), cudaMemcpyHostToDevice));
+        }
         CU(cudaMemsetAsync(ctx->dCtr, 0, sizeof(Counters), ctx->stream));
         // slotKernel reads the per-pair flags 8 bytes at a time and masks the tail: keep the tail defined
         CU(cudaMemsetAsync(ctx->dFlags, 0, np + kSlotTile, ctx->stream));
@@ -401,14 +412,7 @@ int32_t axcd_refit(AxcdContext* ctx) {
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     recordEv(ctx, EV_START);
     // reset per-step counters: bounds (min = +inf encoding, max = -inf encoding) and counts
-    Counters init;
-    memset(&init, 0, sizeof(init));
-    for (int k = 0; k < 3; ++k) {
-        init.boundsMin[k] = 0xffffffffu;
-        init.boundsMax[k] = 0u;
-    }
-    ctx->hostCtr = init;
-    CU(cudaMemcpyAsync(ctx->dCtr, &ctx->hostCtr, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->dCtr, ctx->dCtrInit, sizeof(Counters), cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->n) {
         const uint32_t blocks = (ctx->n + kRefitThreads - 1) / kRefitThreads;
         refitKernel<<<blocks, kRefitThreads, 0, ctx->stream>>>(

@@ -754,7 +754,6 @@ struct NarrowQueues {
 #define AXCD_GJK_THREADS 128
 #endif
 constexpr int kGjkThreads = AXCD_GJK_THREADS;
-constexpr int kNumClasses = 6;
 
 // Pair class by core kinds, so that a warp runs one kind of support function.
 __device__ __forceinline__ int pairClass(uint32_t typeA, uint32_t typeB) {
@@ -763,33 +762,6 @@ __device__ __forceinline__ int pairClass(uint32_t typeA, uint32_t typeB) {
         return 5;   // hulls and capsules share the "other" class
     if (typeA == AXCD_SHAPE_SPHERE) return (typeB == AXCD_SHAPE_SPHERE) ? 1 : 2;   // SS, point-box
     return (typeB == AXCD_SHAPE_SPHERE) ? 3 : 4;                                   // box-point, box-box
-}
-
-// Block-local counting sort of the tile's items by class (stable).  cls in [0, kNumClasses);
-// returns through sOrder the item handled by each thread.  sCnt: kNumClasses * nWarps words.
-template <int THREADS>
-__device__ __forceinline__ void binByClass(int cls, uint32_t* sCnt, uint16_t* sOrder) {
-    constexpr int W = THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t rank = 0;
-#pragma unroll
-    for (int c = 0; c < kNumClasses; ++c) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, cls == c);
-        if (lane == 0) sCnt[c * W + warp] = __popc(bal);
-        if (cls == c) rank = __popc(bal & ((1u << lane) - 1u));
-    }
-    __syncthreads();
-    if (tid == 0) {   // exclusive scan of the kNumClasses*W counts (class-major)
-        uint32_t run = 0;
-        for (int i = 0; i < kNumClasses * W; ++i) {
-            const uint32_t t = sCnt[i];
-            sCnt[i] = run;
-            run += t;
-        }
-    }
-    __syncthreads();
-    sOrder[sCnt[cls * W + warp] + rank] = (uint16_t)tid;
-    __syncthreads();
 }
 
 // One thread per (a,b)-sorted candidate pair; inside a tile the pairs are re-dealt to threads by

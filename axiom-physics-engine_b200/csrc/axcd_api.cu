@@ -81,8 +81,6 @@ struct AxcdContext {
     uint32_t* dSortStatus = nullptr;
     Counters* dCtr = nullptr;
     Counters* dCtrInit = nullptr;    // per-step initial value of the counters (device copy: async reset)
-    void* hPinned = nullptr;         // staging for strided transform uploads
-    size_t hPinnedBytes = 0;
     cudaEvent_t ev[EV_COUNT];
     bool evValid[EV_COUNT];
 };
@@ -233,7 +231,6 @@ void axcd_destroy(AxcdContext* ctx) {
                     ctx->dSortStatus, ctx->dCtr, ctx->dCtrInit};
     for (void* b : bufs)
         if (b) cudaFree(b);
-    if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -546,7 +546,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         recordEv(ctx, EV_GJK);
         // EPA: persistent grids, queue lengths are read on the device
         if (!(ctx->cfg.flags & AXCD_FLAG_EPA_COOPERATIVE)) {
-            epaKernel<<<kNumSMs * 2, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf,
+            epaKernel<<<kNumSMs * kEpaBlocksPerSM, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf,
                                                                        ctx->dShapes, ctx->dHull, p, ctx->dContacts,
                                                                        ctx->cfg.maxContacts, ctx->dSlots,
                                                                        ctx->dPairDist, ctx->dCtr);

@@ -368,12 +368,19 @@ __device__ __forceinline__ GjkResult gjk(const Core& A, const Core& B, const Nar
 //        [4V+4F, 4V+5F) face indices i0 | i1<<8 | i2<<16;  then E/2 words of packed horizon edges.
 constexpr int kEpaHardVerts = 40;   // full caps (fallback path) == the oracle's
 constexpr int kEpaHardFaces = 64;
-constexpr int kEpaFastVerts = 16;   // shared-memory fast path; overflow -> fallback kernel
-constexpr int kEpaFastFaces = 28;
-constexpr int kEpaFastEdges = 24;
+// shared-memory fast path; a pair that outgrows it is spilled and finished by the fallback kernel.
+// Sized from the measured distribution of final polytope sizes (profiles/epa_polytope_hist.py).
+#ifndef AXCD_EPA_FAST_VERTS
+#define AXCD_EPA_FAST_VERTS 14   // 99.2 % of the headline's EPA runs end with <= 14 vertices / 24 faces
+#define AXCD_EPA_FAST_FACES 24
+#define AXCD_EPA_FAST_EDGES 20
+#endif
+constexpr int kEpaFastVerts = AXCD_EPA_FAST_VERTS;
+constexpr int kEpaFastFaces = AXCD_EPA_FAST_FACES;
+constexpr int kEpaFastEdges = AXCD_EPA_FAST_EDGES;
+static_assert(kEpaFastVerts <= 16 && kEpaFastFaces <= 32 && kEpaFastEdges % 2 == 0, "fast-path caps");
 
-template <int MAXF> struct FaceMask { using T = uint64_t; };
-template <> struct FaceMask<28> { using T = uint32_t; };
+template <int MAXF> struct FaceMask { using T = std::conditional_t<(MAXF <= 32), uint32_t, uint64_t>; };
 __device__ __forceinline__ int lowestBit(uint32_t m) { return __ffs((int)m) - 1; }
 __device__ __forceinline__ int lowestBit(uint64_t m) { return __ffsll((long long)m) - 1; }
 __device__ __forceinline__ int popCount(uint32_t m) { return __popc(m); }
@@ -990,7 +997,12 @@ slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairC
 }
 
 // ---- kernel 2: EPA over the queued pairs -------------------------------------------------------------
-constexpr int kEpaThreads = 128;
+#ifndef AXCD_EPA_THREADS
+#define AXCD_EPA_THREADS 96      // 96 x 772 B = 72 KB of polytopes per block, three blocks per SM
+#define AXCD_EPA_BLOCKS_PER_SM 3
+#endif
+constexpr int kEpaThreads = AXCD_EPA_THREADS;
+constexpr int kEpaBlocksPerSM = AXCD_EPA_BLOCKS_PER_SM;
 constexpr int kEpaSmemBytes =
     Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, kEpaThreads>::kWords * kEpaThreads * (int)sizeof(float);
 constexpr int kEpaChunk = 64;        // queue items a warp claims at a time
@@ -1135,7 +1147,7 @@ epaKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs,
     }
 }
 
-// Full-cap path for the few pairs (~0.2 %) whose polytope outgrew the fast caps: one warp per block,
+// Full-cap path for the few pairs (~1 %) whose polytope outgrew the fast caps: one warp per block,
 // the 2.6 KB full-cap polytope of each lane in shared memory (84 KB per block), so these longest
 // expansions are not left crawling through local memory at the end of the step.
 constexpr int kEpaFallbackThreads = 32;

@@ -24,6 +24,7 @@
 #include "axref.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -570,6 +571,20 @@ inline EpaResult epaTouching(V3 n, V3 pa) {
     return r;
 }
 
+#ifdef AXREF_EPA_HIST
+// Diagnostic build only (make -C oracle hist): distribution of the polytope size EPA ends with, used
+// to size the CUDA fast-path storage caps (profiles/r01_experiments.md).
+static std::atomic<uint64_t> gEpaHistV[EPA_MAX_VERTS + 1], gEpaHistF[EPA_MAX_FACES + 1];
+inline void epaHistRecord(int nv, int nf) {
+    gEpaHistV[nv].fetch_add(1, std::memory_order_relaxed);
+    gEpaHistF[nf].fetch_add(1, std::memory_order_relaxed);
+}
+extern "C" void axref_epa_hist(uint64_t* outV, uint64_t* outF) {
+    for (int i = 0; i <= EPA_MAX_VERTS; ++i) outV[i] = gEpaHistV[i].exchange(0);
+    for (int i = 0; i <= EPA_MAX_FACES; ++i) outF[i] = gEpaHistF[i].exchange(0);
+}
+#endif
+
 EpaResult epa(const Core& A, const Core& B, const AxrefNarrowCfg& cfg, const Simplex& s0) {
     Epa e;
     e.nv = s0.n;
@@ -728,6 +743,9 @@ EpaResult epa(const Core& A, const Core& B, const AxrefNarrowCfg& cfg, const Sim
             epaSetFace(e, slot, he0[h], he1[h], wi);
         }
     }
+#ifdef AXREF_EPA_HIST
+    epaHistRecord(e.nv, e.nf);
+#endif
     const EpaFace fb = e.f[best];
     EpaResult r;
     r.n = fb.n;

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Runs bench.py once per library variant under axiom-physics-engine_b200/variants/ and prints the stage table.
+# usage (on the GPU box): bash profiles/variant_sweep.sh A B C ...
+mkdir -p gpurun_out
+for t in "$@"; do
+  AXCD_LIB=$PWD/axiom-physics-engine_b200/variants/libaxcd_$t.so timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/sweep_$t.json 2> gpurun_out/sweep_$t.err
+  python - "$t" <<'PY'
+import json,sys
+t=sys.argv[1]
+try:
+    d=json.loads(open(f"gpurun_out/sweep_{t}.json").read().strip().splitlines()[-1])
+    print(t, "ms/step", round(d["ms_per_step"],4), {k:round(v,4) for k,v in d["stages"].items()} if isinstance(d.get("stages"),dict) else d.get("stages"))
+except Exception as e:
+    print(t, "FAILED", e)
+PY
+done

@@ -34,7 +34,7 @@ def default_cfg(want_distances=False):
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(ORACLE_DIR, "libaxref.so")
+        path = os.environ.get("AXREF_LIB") or os.path.join(ORACLE_DIR, "libaxref.so")   # override: diagnostic builds
         if not os.path.exists(path):
             subprocess.check_call(["make", "-C", ORACLE_DIR, "libaxref.so"])
         _LIB = C.CDLL(path)

@@ -9,6 +9,7 @@
 #include "axcd_common.cuh"
 #include "axcd_lbvh.cuh"
 #include "axcd_epa_coop.cuh"
+#include "axcd_epa_warp.cuh"
 #include "axcd_narrow.cuh"
 #include "axcd_refit.cuh"
 #include "axcd_sort.cuh"
@@ -309,7 +310,6 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dSlots, np));
         CU(dalloc(&ctx->dTmpContacts, np));
         CU(cudaFuncSetAttribute(epaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaSmemBytes));
-        CU(cudaFuncSetAttribute(epaFallbackKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaFallbackSmemBytes));
         CU(dalloc(&ctx->dContacts, (size_t)cfg->maxContacts));
         if (cfg->flags & AXCD_FLAG_PAIR_DISTANCES) CU(dalloc(&ctx->dPairDist, np));
         CU(dalloc(&ctx->dSortHist, (size_t)kMaxPasses * kRadix));
@@ -555,9 +555,9 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
                                                                 ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts,
                                                                 ctx->dSlots, ctx->dPairDist, ctx->dCtr);
         }
-        epaFallbackKernel<<<kNumSMs * 2, kEpaFallbackThreads, kEpaFallbackSmemBytes, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
-                                                  ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots, ctx->dPairDist,
-                                                  ctx->dCtr);
+        epaWarpFallbackKernel<<<kNumSMs * 8, kWarpFbThreads, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+                                                                      ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
+                                                                      ctx->dPairDist, ctx->dCtr);
         CU(cudaGetLastError());
         ctx->launches[2] = 4;   // GJK, slots, EPA, EPA fallback
     } else {

@@ -417,6 +417,7 @@ struct Poly {
         uint32_t& r = u(4 * MAXV + 5 * MAXF + (h >> 1));
         r = (h & 1) ? ((r & 0xffffu) | (e << 16)) : ((r & 0xffff0000u) | e);
     }
+    __device__ __forceinline__ uint32_t& edgeWord(int h) const { return u(4 * MAXV + 5 * MAXF + h); }   // unpacked use
     __device__ __forceinline__ void clearRows(int nv) const {
         if (kSmallRows) {
             for (int i = 0; i < (nv + 1) / 2; ++i) u(kRowBase + i) = 0u;
@@ -1144,57 +1145,6 @@ epaKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs,
         if (state == RUNNING) {
             if (epaIterate(L.A, L.B, cfg, poly, st)) state = DONE;
         }
-    }
-}
-
-// Full-cap path for the few pairs (~1 %) whose polytope outgrew the fast caps: one warp per block,
-// the 2.6 KB full-cap polytope of each lane in shared memory (84 KB per block), so these longest
-// expansions are not left crawling through local memory at the end of the step.
-constexpr int kEpaFallbackThreads = 32;
-using FallbackPoly = Poly<kEpaHardVerts, kEpaHardFaces, kEpaHardFaces * 3, kEpaFallbackThreads>;
-constexpr int kEpaFallbackSmemBytes = FallbackPoly::kWords * kEpaFallbackThreads * (int)sizeof(float);
-
-__global__ void __launch_bounds__(kEpaFallbackThreads)
-epaFallbackKernel(NarrowQueues q, const uint2* __restrict__ pairs, const float* __restrict__ xf,
-                  const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
-                  AxcdContact* __restrict__ contacts, uint32_t maxContacts, const uint32_t* __restrict__ slots,
-                  float* __restrict__ pairDist, Counters* __restrict__ ctr) {
-    extern __shared__ float sPoly[];
-    FallbackPoly poly;
-    poly.base = sPoly + threadIdx.x;
-    const uint32_t count = ctr->epaOverflow;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        EpaLane L;
-        EpaState<FallbackPoly::Mask> st;
-        EpaResult r;
-        const uint32_t ov = q.overflow[i];
-        const bool resume = (ov & 0x80000000u) != 0;
-        L.queueIdx = ov & 0x7fffffffu;
-        if (!epaBegin(q.work + L.queueIdx, pairs, xf, shapes, hull, poly, L, st, r, resume)) {
-            if (resume) {
-                // restore the spilled fast-path polytope into the full-cap layout, section by section
-                using FP = Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, 1>;
-                const float* src = q.spill + (size_t)i * (FP::kWords + kSpillStateWords);
-                const uint32_t* su = reinterpret_cast<const uint32_t*>(src + FP::kWords);
-                st.nv = (int)su[0]; st.nf = (int)su[1]; st.best = (int)su[2];
-                st.bd = __uint_as_float(su[3]); st.alive = (FallbackPoly::Mask)su[4]; st.it = su[5];
-                st.status = 0; st.overflow = false; st.degenerate = false;
-                FP fp;
-                fp.base = const_cast<float*>(src);
-                for (int v = 0; v < st.nv; ++v) {
-                    poly.setY(v, fp.y(v));
-                    poly.setId(v, fp.id(v));
-                }
-                for (int f = 0; f < st.nf; ++f) {
-                    poly.setPlane(f, fp.fn(f), fp.fd(f));
-                    poly.setFi(f, fp.fi(f));
-                }
-            }
-            while (!epaIterate(L.A, L.B, cfg, poly, st)) {
-            }
-            r = epaFinish(L.A, poly, st);
-        }
-        epaEmit(L, r, contacts, maxContacts, slots, pairDist, ctr);
     }
 }
 

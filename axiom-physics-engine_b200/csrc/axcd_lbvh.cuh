@@ -192,7 +192,7 @@ __global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t 
 #define AXCD_TRAV_POOL 1024
 #endif
 constexpr int kTravThreads = AXCD_TRAV_THREADS;
-constexpr int kTravPool = AXCD_TRAV_POOL;   // pairs staged per block before the coalesced flush    // pairs staged per block before the coalesced flush
+constexpr int kTravPool = AXCD_TRAV_POOL;   // pairs staged per block before the coalesced flush
 constexpr int kTravStack = 64;
 
 // AABB::intersects (aabb.hpp:132-135): closed intervals, any NaN -> false
@@ -233,11 +233,13 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
         const float4 lo = leafLo[i], hi = leafHi[i];
         const uint32_t bodyI = __float_as_uint(lo.w);
         const uint32_t wEnd = worldEnd ? worldEnd[__float_as_uint(hi.w)] : n - 1;
+        // The node to visit next is carried in a register; the stack (local memory) only holds the
+        // second child when both are internal, so a plain descent never round-trips through it.
+        constexpr uint32_t kNone = 0xffffffffu;
         uint32_t stack[kTravStack];
         int sp = 0;
-        stack[sp++] = 0;
-        while (sp > 0) {
-            const uint32_t ni = stack[--sp];
+        uint32_t ni = 0;
+        while (true) {
             const float4* np = reinterpret_cast<const float4*>(nodes + ni);
             const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
             const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(np) + 3);
@@ -248,6 +250,7 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
             // right child: sorted leaves [split+1, last]
             const bool hitR = last > i && split + 1 <= wEnd &&
                               boxesIntersect(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
+            uint32_t next = kNone;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const bool hit = c ? hitR : hitL;
@@ -255,7 +258,8 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                 const bool leaf = c ? (split + 1 == last) : (first == split);
                 const uint32_t child = c ? split + 1 : split;
                 if (!leaf) {
-                    if (sp < kTravStack) stack[sp++] = child;
+                    if (next == kNone) next = child;
+                    else if (sp < kTravStack) stack[sp++] = child;
                     continue;
                 }
                 const uint32_t bodyJ = __float_as_uint(__ldg(&leafLo[child].w));
@@ -282,6 +286,9 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                     }
                 }
             }
+            if (next != kNone) ni = next;
+            else if (sp > 0) ni = stack[--sp];
+            else break;
         }
     }
     __syncthreads();

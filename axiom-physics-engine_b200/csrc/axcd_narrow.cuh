@@ -580,6 +580,15 @@ __device__ __forceinline__ int epaInit(const Core& A, const Core& B, int n0, con
     return 0;
 }
 
+// The per-face / per-vertex scans of one expansion step are independent iterations over shared
+// memory: unrolled by 4 they give the latency-bound EPA kernel (9 warps per SM) some ILP.  Measured
+// (profiles/r01_experiments.md): 1 -> 0.85 ms, 4 -> 0.80 ms, 8 -> 0.87 ms; unrolling the face
+// construction loop (sqrt + divide chains) costs more in divergence than it hides.
+#ifndef AXCD_EPA_UNROLL
+#define AXCD_EPA_UNROLL 4
+#endif
+#define AXCD_STR_(x) #x
+#define AXCD_UNROLL(n) _Pragma(AXCD_STR_(unroll n))
 // One expansion step.  Returns true when the pair is finished (converged, capped or overflowed).
 template <int MAXV, int MAXF, int MAXE, int STRIDE>
 __device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const NarrowParams& cfg,
@@ -604,6 +613,7 @@ __device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const N
     const float scale = (bd > 1.0f) ? bd : 1.0f;
     if (dw - bd <= cfg.epaTol * scale) return true;
     bool dup = false;
+    AXCD_UNROLL(AXCD_EPA_UNROLL)
     for (int i = 0; i < nv; ++i) dup = dup || same3(w, e.y(i));
     if (dup) return true;
     if (st.it >= cfg.epaMaxIters || nv >= kEpaHardVerts) {
@@ -616,6 +626,7 @@ __device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const N
     Mask vis = 0;
     int nbest = -1;          // closest face among those that survive this step
     float nbd = FLT_MAX;
+    AXCD_UNROLL(AXCD_EPA_UNROLL)
     for (int i = 0; i < nf; ++i) {
         const float di = e.fd(i);
         const bool v = dot3(e.fn(i), w) - di > visEps;
@@ -1068,7 +1079,7 @@ __device__ __forceinline__ void epaEmit(const EpaLane& L, const EpaResult& r, Ax
 // trip, and refills / finalisations are batched (>= kEpaBatchLanes lanes, or nothing else to do), so
 // a pair that needs 2 steps does not hold its lane hostage to a neighbour that needs 15.  Warps claim
 // queue items in chunks; the queue length is only known on the device.
-__global__ void __launch_bounds__(kEpaThreads)
+__global__ void __launch_bounds__(kEpaThreads, kEpaBlocksPerSM)
 epaKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs,
           const float* __restrict__ xf, const uint4* __restrict__ shapes, const float4* __restrict__ hull,
           NarrowParams cfg, AxcdContact* __restrict__ contacts, uint32_t maxContacts,

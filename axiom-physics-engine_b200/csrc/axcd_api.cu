@@ -425,7 +425,8 @@ int32_t axcd_refit(AxcdContext* ctx) {
 
 int32_t axcd_broadphase(AxcdContext* ctx) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
-    if (ctx->stage < ST_REFIT) return AXCD_ERR_GPU_INVALID_OP;
+    // the per-step device counters are reset by axcd_refit: each stage runs once per refit
+    if (ctx->stage != ST_REFIT) return AXCD_ERR_GPU_INVALID_OP;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     const uint32_t n = ctx->n;
     cudaStream_t st = ctx->stream;
@@ -512,7 +513,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
 
 int32_t axcd_narrowphase(AxcdContext* ctx) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
-    if (ctx->stage < ST_BROAD) return AXCD_ERR_GPU_INVALID_OP;
+    if (ctx->stage != ST_BROAD) return AXCD_ERR_GPU_INVALID_OP;   // once per broadphase (see above)
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     cudaStream_t st = ctx->stream;
     recordEv(ctx, EV_N0);
@@ -555,7 +556,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
                                                                 ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts,
                                                                 ctx->dSlots, ctx->dPairDist, ctx->dCtr);
         }
-        epaWarpFallbackKernel<<<kNumSMs * 8, kWarpFbThreads, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+        epaWarpFallbackKernel<<<kNumSMs * kWarpFbBlocksPerSM, kWarpFbThreads, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
                                                                       ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
                                                                       ctx->dPairDist, ctx->dCtr);
         CU(cudaGetLastError());

@@ -120,7 +120,8 @@ struct Counters {
     uint32_t epaCursor;      // next unclaimed EPA queue item
     uint32_t scanTicket;     // tile ticket of the body-count scan
     uint32_t storedPairs;    // pairs actually stored (<= capacity) = total of the body-count scan
-    uint32_t pad[3];
+    uint32_t fallbackCursor; // next unclaimed overflow item (full-cap EPA)
+    uint32_t pad[2];
 };
 
 }  // namespace axcd

@@ -20,6 +20,10 @@
 
 namespace axcd {
 
+#ifndef AXCD_WARPFB_BLOCKS
+#define AXCD_WARPFB_BLOCKS 4
+#endif
+constexpr int kWarpFbBlocksPerSM = AXCD_WARPFB_BLOCKS;
 constexpr int kWarpFbWarps = 4;
 constexpr int kWarpFbThreads = kWarpFbWarps * 32;
 // MAXE = 2 x 192: the horizon list keeps one edge per word here (lanes write it concurrently)
@@ -49,7 +53,7 @@ __device__ __forceinline__ void warpPlane(const WarpPoly& e, int i0, int i1, int
     F.d[j] = dot3(n, p0);
 }
 
-__global__ void __launch_bounds__(kWarpFbThreads)
+__global__ void __launch_bounds__(kWarpFbThreads, AXCD_WARPFB_BLOCKS)
 epaWarpFallbackKernel(NarrowQueues q, const uint2* __restrict__ pairs, const float* __restrict__ xf,
                       const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
                       AxcdContact* __restrict__ contacts, uint32_t maxContacts, const uint32_t* __restrict__ slots,
@@ -62,10 +66,13 @@ epaWarpFallbackKernel(NarrowQueues q, const uint2* __restrict__ pairs, const flo
     poly.base = sMem + warp * kWarpFbWords;
     uint32_t* scratch = reinterpret_cast<uint32_t*>(poly.base + WarpPoly::kWords);
     const uint32_t count = ctr->epaOverflow;
-    const uint32_t warpsTotal = gridDim.x * kWarpFbWarps;
     const int maxFaces = (int)min(cfg.epaMaxFaces, (uint32_t)kEpaHardFaces);
 
-    for (uint32_t item = blockIdx.x * kWarpFbWarps + warp; item < count; item += warpsTotal) {
+    while (true) {   // persistent warps claim overflow items one at a time (their lengths vary widely)
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&ctr->fallbackCursor, 1u);
+        item = __shfl_sync(kFull, item, 0);
+        if (item >= count) break;
         EpaLane L;
         EpaState<WarpPoly::Mask> st;
         EpaResult r;

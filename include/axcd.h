@@ -144,7 +144,9 @@ AXCD_API int32_t axcd_set_transforms(AxcdContext* ctx, const void* transforms, u
                                      uint32_t strideBytes);
 
 /* The three stages (asynchronous on the context stream) and the fused step (synchronises and
- * fills stats).  axcd_broadphase requires a refit since the last set_transforms, etc. -> 503.  */
+ * fills stats).  Each stage runs once per refit, in order: axcd_broadphase needs an axcd_refit
+ * since the last set_transforms, axcd_narrowphase needs a fresh axcd_broadphase; calling a stage
+ * out of order or twice returns 503 (GPU invalid operation).                                   */
 AXCD_API int32_t axcd_refit(AxcdContext* ctx);
 AXCD_API int32_t axcd_broadphase(AxcdContext* ctx);
 AXCD_API int32_t axcd_narrowphase(AxcdContext* ctx);

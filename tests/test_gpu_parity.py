@@ -273,6 +273,13 @@ def test_error_behaviour():
     assert e.value.code == 600
     w.set_transforms(np.array([O.xf()]))
     assert w._lib.axcd_narrowphase(w._ctx) == 503                         # broadphase not run
+    # each stage runs once per refit (the per-step device counters are reset there)
+    assert w._lib.axcd_refit(w._ctx) == 0
+    assert w._lib.axcd_broadphase(w._ctx) == 0
+    assert w._lib.axcd_broadphase(w._ctx) == 503
+    assert w._lib.axcd_narrowphase(w._ctx) == 0
+    assert w._lib.axcd_narrowphase(w._ctx) == 503
+    assert w._lib.axcd_refit(w._ctx) == 0                                 # a new step may start at any point
     w.close()
 
 

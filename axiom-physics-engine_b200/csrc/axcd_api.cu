@@ -73,6 +73,7 @@ struct AxcdContext {
     float* dEpaSpill = nullptr;      // polytopes of pairs that outgrew the fast EPA caps
     uint32_t spillCap = 0;
     uint32_t* dSlotStatus = nullptr; // look-back status, one word per slot-scan tile
+    uint32_t* dChunks = nullptr;     // class-homogeneous chunks of 32 pair indices for the GJK kernel
     uint8_t* dFlags = nullptr;       // per pair: 0 none, 1 shallow contact, 2 EPA contact
     uint32_t* dSlots = nullptr;      // per pair: contact slot
     AxcdContact* dTmpContacts = nullptr;   // per pair: shallow contact records before compaction
@@ -228,7 +229,7 @@ void axcd_destroy(AxcdContext* ctx) {
     void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
-                    ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
+                    ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
                     ctx->dSortStatus, ctx->dCtr, ctx->dCtrInit};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -306,6 +307,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         ctx->spillCap = cfg->maxContacts < 65536u ? cfg->maxContacts : 65536u;
         CU(dalloc(&ctx->dEpaSpill, (size_t)ctx->spillCap * (Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, 1>::kWords + kSpillStateWords)));
         CU(dalloc(&ctx->dSlotStatus, np / kSlotTile + 2));
+        CU(dalloc(&ctx->dChunks, (size_t)chunkCapFor(cfg->maxPairs) * 32));
         CU(dalloc(&ctx->dFlags, np + kSlotTile));
         CU(dalloc(&ctx->dSlots, np));
         CU(dalloc(&ctx->dTmpContacts, np));
@@ -538,7 +540,10 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow, ctx->dEpaSpill, ctx->spillCap};
         const uint2* pairs = ctx->dPairs;
         const uint32_t* pairCount = &ctx->dCtr->pairCount;
-        gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, pairCount, mp, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+        const uint32_t chunkCap = chunkCapFor(mp);
+        classifyPairsKernel<<<classifyBlocksFor(mp), kClsThreads, 0, st>>>(pairs, pairCount, mp, ctx->dShapes, ctx->dChunks,
+                                                                            chunkCap, ctx->dCtr);
+        gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dHull, p,
                                                  ctx->dFlags, ctx->dTmpContacts, q, ctx->cfg.maxContacts,
                                                  ctx->dPairDist, ctx->dCtr);
         slotKernel<<<slotBlocks, kSlotThreads, 0, st>>>(ctx->dFlags, pairCount, mp, ctx->dTmpContacts, ctx->dContacts,
@@ -560,7 +565,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
                                                                       ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
                                                                       ctx->dPairDist, ctx->dCtr);
         CU(cudaGetLastError());
-        ctx->launches[2] = 4;   // GJK, slots, EPA, EPA fallback
+        ctx->launches[2] = 5;   // classify, GJK, slots, EPA, EPA fallback
     } else {
         recordEv(ctx, EV_GJK);
     }

@@ -64,33 +64,6 @@ __host__ __device__ __forceinline__ float orderedToFloat(uint32_t u) {
 
 constexpr int kNumClasses = 6;
 
-// Block-local counting sort of the tile's items by class (stable).  cls in [0, kNumClasses);
-// returns through sOrder the item handled by each thread.  sCnt: kNumClasses * nWarps words.
-template <int THREADS>
-__device__ __forceinline__ void binByClass(int cls, uint32_t* sCnt, uint16_t* sOrder) {
-    constexpr int W = THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t rank = 0;
-#pragma unroll
-    for (int c = 0; c < kNumClasses; ++c) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, cls == c);
-        if (lane == 0) sCnt[c * W + warp] = __popc(bal);
-        if (cls == c) rank = __popc(bal & ((1u << lane) - 1u));
-    }
-    __syncthreads();
-    if (tid == 0) {   // exclusive scan of the kNumClasses*W counts (class-major)
-        uint32_t run = 0;
-        for (int i = 0; i < kNumClasses * W; ++i) {
-            const uint32_t t = sCnt[i];
-            sCnt[i] = run;
-            run += t;
-        }
-    }
-    __syncthreads();
-    sOrder[sCnt[cls * W + warp] + rank] = (uint16_t)tid;
-    __syncthreads();
-}
-
 // One 64-byte LBVH internal node: both children's boxes live in the parent, so a traversal step is
 // one aligned 64-byte read.  Leaf-ness and child indices follow from (first, split, last):
 //   left  child covers sorted leaves [first, split]   -> leaf `split`   if first == split,
@@ -121,7 +94,8 @@ struct Counters {
     uint32_t scanTicket;     // tile ticket of the body-count scan
     uint32_t storedPairs;    // pairs actually stored (<= capacity) = total of the body-count scan
     uint32_t fallbackCursor; // next unclaimed overflow item (full-cap EPA)
-    uint32_t pad[2];
+    uint32_t gjkChunks;      // 32-pair class-homogeneous chunks queued for the GJK kernel
+    uint32_t gjkChunkCursor; // next unclaimed chunk
 };
 
 }  // namespace axcd

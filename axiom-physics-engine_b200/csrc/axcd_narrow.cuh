@@ -359,6 +359,73 @@ __device__ __forceinline__ GjkResult gjk(const Core& A, const Core& B, const Nar
     return r;
 }
 
+// ---- sphere against box, closed form ------------------------------------------------------------------
+// The box as in makeCore: centre cX, unit axes = the columns of Quat::toMatrix, half lengths
+// |halfExtent * scale|; all points relative to A's position.
+//   outside: closest box point q by clamping the centre's box coordinates; gap = |q - cS| - r
+//   inside : leave through the nearest face (lowest axis on ties); depth = face gap + r
+// nsx = unit direction from the sphere towards the box, ps / px = witness points on the sphere / box.
+struct SphereBox {
+    bool contact;
+    float dist, depth;
+    V3 nsx, ps, px;
+};
+__device__ __forceinline__ SphereBox sphereBox(V3 cS, float r, V3 cX, const BodyPose& tX, uint4 sX) {
+    SphereBox o;
+    V3 ax[3];
+    quatToColumns(tX.q, ax[0], ax[1], ax[2]);
+    const float half[3] = {fabsf(__uint_as_float(sX.y) * tX.s.x), fabsf(__uint_as_float(sX.z) * tX.s.y),
+                           fabsf(__uint_as_float(sX.w) * tX.s.z)};
+    const V3 d = cS - cX;
+    float x[3];
+    bool inside = true;
+    V3 q = cX;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        x[i] = dot3(d, ax[i]);
+        float k = x[i];
+        if (k > half[i]) {
+            k = half[i];
+            inside = false;
+        } else if (k < -half[i]) {
+            k = -half[i];
+            inside = false;
+        }
+        q = q + ax[i] * k;
+    }
+    if (!inside) {
+        const V3 v = q - cS;
+        const float l = sqrtf(dot3(v, v));
+        o.dist = l - r;
+        o.depth = r - l;
+        o.contact = o.depth >= 0.0f;
+        o.nsx = (l > 0.0f) ? v * (1.0f / l) : mk3(1.0f, 0.0f, 0.0f);
+        o.ps = cS + o.nsx * r;
+        o.px = q;
+        return o;
+    }
+    int best = 0;
+    float gap = half[0] - fabsf(x[0]);
+#pragma unroll
+    for (int i = 1; i < 3; ++i) {
+        const float g = half[i] - fabsf(x[i]);
+        if (g < gap) {
+            gap = g;
+            best = i;
+        }
+    }
+    const V3 axb = (best == 0) ? ax[0] : ((best == 1) ? ax[1] : ax[2]);
+    const float xb = (best == 0) ? x[0] : ((best == 1) ? x[1] : x[2]);
+    const V3 out = (xb >= 0.0f) ? axb : -axb;   // from the box centre's side towards the sphere
+    o.contact = true;
+    o.depth = gap + r;
+    o.dist = -o.depth;
+    o.nsx = -out;
+    o.ps = cS + o.nsx * r;
+    o.px = cS + out * gap;
+    return o;
+}
+
 // ---- EPA ------------------------------------------------------------------------------------------
 // The polytope lives in per-thread storage addressed as base[word * STRIDE]:
 //   STRIDE = block size  -> a column of shared memory (the same word of all threads is contiguous,
@@ -783,53 +850,157 @@ __device__ __forceinline__ int pairClass(uint32_t typeA, uint32_t typeB) {
     return (typeB == AXCD_SHAPE_SPHERE) ? 3 : 4;                                   // box-point, box-box
 }
 
-// One thread per (a,b)-sorted candidate pair; inside a tile the pairs are re-dealt to threads by
-// class (sphere-sphere / point-box / box-point / box-box / hull) so that warps do not diverge on
-// the support function.  Per pair it writes flag[k]: 0 = no contact, 1 = shallow contact (cores
-// apart, radii overlapping; record written to tmp[k]), 2 = cores overlap (EpaWork queued; EPA
-// writes the record).  Contact slots are assigned afterwards, in pair order, by slotKernel.
+// ---- kernel 0: deal the pairs into class-homogeneous chunks of 32 --------------------------------------
+// A 50/50 box/sphere scene has 25 % box-box pairs that cost an order of magnitude more than the rest.
+// Binning inside a block tile leaves one warp per tile grinding through them while its neighbours
+// idle at the tile barrier, so the binning is global instead: this pass classifies every pair
+// (sphere-sphere / sphere-box / box-sphere / box-box / other) and emits chunks of 32 pair indices of
+// ONE class; gjkKernel's warps then claim chunks by ticket, with no block barrier and no mixed warps.
+// Output order does not matter: every result of gjkKernel is stored by pair index.
+constexpr int kClsThreads = 256;
+constexpr int kClsItems = 4;
+constexpr int kClsTile = kClsThreads * kClsItems;
+constexpr uint32_t kNoPair = 0xffffffffu;
+static_assert(kClsThreads >= kNumClasses * 32, "one thread per carry slot");
+
+__host__ __device__ constexpr uint32_t classifyBlocksFor(uint32_t maxPairs) {
+    const uint32_t tiles = (maxPairs + kClsTile - 1) / kClsTile;
+    return tiles < (uint32_t)kNumSMs * 4 ? (tiles ? tiles : 1u) : (uint32_t)kNumSMs * 4;
+}
+__host__ __device__ constexpr uint32_t chunkCapFor(uint32_t maxPairs) {
+    return maxPairs / 32 + classifyBlocksFor(maxPairs) * kNumClasses + 1;   // full chunks + every block's padded tails
+}
+
+__global__ void __launch_bounds__(kClsThreads)
+classifyPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
+                    const uint4* __restrict__ shapes, uint32_t* __restrict__ chunks, uint32_t chunkCap,
+                    Counters* __restrict__ ctr) {
+    __shared__ uint32_t sCarry[kNumClasses][32];   // < 32 leftovers per class from the earlier tiles
+    __shared__ uint32_t sCarryN[kNumClasses];
+    __shared__ uint32_t sCnt[kNumClasses];         // carry + this tile, per class
+    __shared__ uint32_t sBase[kNumClasses];        // start of each class in sItems
+    __shared__ uint32_t sChunkStart[kNumClasses + 1];   // first chunk (within the tile) of each class
+    __shared__ uint32_t sItems[kClsTile + kNumClasses * 32];
+    __shared__ uint32_t sChunkBase;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t npairs = min(*pairCount, maxPairs);
+    if (tid < kNumClasses) sCarryN[tid] = 0;
+    __syncthreads();
+    for (uint32_t tileBase = blockIdx.x * kClsTile; tileBase < npairs; tileBase += gridDim.x * kClsTile) {
+        if (tid < kNumClasses) sCnt[tid] = sCarryN[tid];   // the carry takes the first slots of its class
+        __syncthreads();
+        int cls[kClsItems];
+        uint32_t pos[kClsItems];
+#pragma unroll
+        for (int j = 0; j < kClsItems; ++j) {
+            const uint32_t k = tileBase + j * kClsThreads + tid;
+            cls[j] = -1;
+            pos[j] = 0;
+            if (k < npairs) {
+                const uint2 pk = __ldg(pairs + k);
+                cls[j] = pairClass(__ldg(&shapes[pk.x].x), __ldg(&shapes[pk.y].x));
+            }
+#pragma unroll
+            for (int c = 0; c < kNumClasses; ++c) {   // warp-aggregated slot reservation
+                const uint32_t bal = __ballot_sync(0xffffffffu, cls[j] == c);
+                if (!bal) continue;
+                const int leader = __ffs(bal) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&sCnt[c], (uint32_t)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (cls[j] == c) pos[j] = base + __popc(bal & ((1u << lane) - 1u));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0, ch = 0;
+            for (int c = 0; c < kNumClasses; ++c) {
+                sBase[c] = run;
+                sChunkStart[c] = ch;
+                run += sCnt[c];
+                ch += sCnt[c] >> 5;
+            }
+            sChunkStart[kNumClasses] = ch;
+            sChunkBase = ch ? atomicAdd(&ctr->gjkChunks, ch) : 0u;
+        }
+        __syncthreads();
+        if (tid < kNumClasses * 32) {
+            const int c = tid >> 5, i = tid & 31;
+            if ((uint32_t)i < sCarryN[c]) sItems[sBase[c] + i] = sCarry[c][i];
+        }
+#pragma unroll
+        for (int j = 0; j < kClsItems; ++j)
+            if (cls[j] >= 0) sItems[sBase[cls[j]] + pos[j]] = tileBase + j * kClsThreads + tid;
+        __syncthreads();
+        // full chunks go out (coalesced), the remainder of each class is carried to the next tile
+        const uint32_t nOut = sChunkStart[kNumClasses] * 32;
+        for (uint32_t e = tid; e < nOut; e += kClsThreads) {
+            const uint32_t ch = e >> 5;
+            int c = 0;
+#pragma unroll
+            for (int t = 1; t < kNumClasses; ++t) c += (ch >= sChunkStart[t]) ? 1 : 0;
+            const uint32_t g = sChunkBase + ch;
+            if (g < chunkCap) chunks[(size_t)g * 32 + (e & 31)] = sItems[sBase[c] + ((ch - sChunkStart[c]) << 5) + (e & 31)];
+        }
+        uint32_t carryVal = 0, rem = 0;
+        if (tid < kNumClasses * 32) {
+            const int c = tid >> 5, i = tid & 31;
+            rem = sCnt[c] & 31u;
+            if ((uint32_t)i < rem) carryVal = sItems[sBase[c] + (sCnt[c] & ~31u) + i];
+        }
+        __syncthreads();
+        if (tid < kNumClasses * 32) {
+            const int c = tid >> 5, i = tid & 31;
+            if ((uint32_t)i < rem) sCarry[c][i] = carryVal;
+            if (i == 0) sCarryN[c] = rem;
+        }
+        __syncthreads();
+    }
+    // what is left: one padded chunk per class that still holds pairs
+    if (tid == 0) {
+        uint32_t ch = 0;
+        for (int c = 0; c < kNumClasses; ++c) {
+            sChunkStart[c] = ch;
+            ch += sCarryN[c] ? 1u : 0u;
+        }
+        sChunkBase = ch ? atomicAdd(&ctr->gjkChunks, ch) : 0u;
+    }
+    __syncthreads();
+    if (tid < kNumClasses * 32) {
+        const int c = tid >> 5, i = tid & 31;
+        const uint32_t g = sChunkBase + sChunkStart[c];
+        if (sCarryN[c] && g < chunkCap) chunks[(size_t)g * 32 + i] = ((uint32_t)i < sCarryN[c]) ? sCarry[c][i] : kNoPair;
+    }
+}
+
+// One lane per candidate pair, one class-homogeneous chunk of 32 pairs per warp at a time (claimed
+// by ticket).  Per pair it writes flag[k]: 0 = no contact, 1 = shallow contact (cores apart, radii
+// overlapping, or a closed-form sphere case; record written to tmp[k]), 2 = cores overlap (EpaWork
+// queued; EPA writes the record).  Contact slots are assigned afterwards, in pair order, by slotKernel.
 #ifndef AXCD_GJK_MIN_BLOCKS
 #define AXCD_GJK_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(kGjkThreads, AXCD_GJK_MIN_BLOCKS)
-gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
+gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, uint32_t chunkCap,
           const float* __restrict__ xf, const uint4* __restrict__ shapes,
           const float4* __restrict__ hull, NarrowParams cfg, uint8_t* __restrict__ flags,
           AxcdContact* __restrict__ tmp, NarrowQueues q, uint32_t queueCap, float* __restrict__ pairDist,
           Counters* __restrict__ ctr) {
-    __shared__ uint32_t sCnt[kNumClasses * (kGjkThreads / 32)];
-    __shared__ uint16_t sOrder[kGjkThreads];
-    __shared__ uint32_t sA[kGjkThreads], sB[kGjkThreads];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t npairs = min(*pairCount, maxPairs);
-    // persistent blocks: the pair count is only known on the device
-    for (uint32_t tileBase = blockIdx.x * kGjkThreads; tileBase < npairs; tileBase += gridDim.x * kGjkThreads) {
-    __syncthreads();   // sA/sB/sOrder of the previous tile are no longer in use
-
-    // ---- deal the tile's pairs to threads by class -----------------------------------------------
-    {
-        int cls = 0;
-        if (tileBase + tid < npairs) {
-            const uint2 pk = pairs[tileBase + tid];
-            const uint32_t a = pk.x, b = pk.y;
-            sA[tid] = a;
-            sB[tid] = b;
-            cls = pairClass(__ldg(&shapes[a].x), __ldg(&shapes[b].x));
-        }
-        binByClass<kGjkThreads>(cls, sCnt, sOrder);
-    }
-#ifdef AXCD_GJK_NO_BINNING
-    const int j = tid;
-#else
-    const int j = sOrder[tid];           // local index of the pair this thread works on
-#endif
-    const uint32_t k = tileBase + j;     // its global pair index
-    if (k >= npairs) continue;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nChunks = min(ctr->gjkChunks, chunkCap);
+    while (true) {
+    uint32_t chunk = 0;
+    if (lane == 0) chunk = atomicAdd(&ctr->gjkChunkCursor, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= nChunks) break;
+    const uint32_t k = __ldg(chunks + (size_t)chunk * 32 + lane);   // global pair index
+    if (k == kNoPair) continue;
 
     // ---- per-pair GJK ----------------------------------------------------------------------------
     int kind = 0;
     uint32_t status = 0;
-    const uint32_t ia = sA[j], ib = sB[j];
+    const uint2 pk = __ldg(pairs + k);
+    const uint32_t ia = pk.x, ib = pk.y;
     V3 n = mk3(0.f, 0.f, 0.f), pos = n;
     float depth = 0.f, dist = 0.f;
     Simplex s;
@@ -850,6 +1021,24 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCoun
             const V3 pa = n * ra;
             const V3 pb = d - n * rb;
             pos = (pa + pb) * 0.5f + origin;
+        }
+    } else if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_BOX) {
+        const SphereBox r = sphereBox(mk3(0.f, 0.f, 0.f), __uint_as_float(sa.y), tb.p - origin, tb, sb);
+        dist = r.dist;
+        if (r.contact) {
+            kind = 1;
+            depth = r.depth;
+            n = r.nsx;
+            pos = (r.ps + r.px) * 0.5f + origin;
+        }
+    } else if (sa.x == AXCD_SHAPE_BOX && sb.x == AXCD_SHAPE_SPHERE) {
+        const SphereBox r = sphereBox(tb.p - origin, __uint_as_float(sb.y), mk3(0.f, 0.f, 0.f), ta, sa);
+        dist = r.dist;
+        if (r.contact) {
+            kind = 1;
+            depth = r.depth;
+            n = -r.nsx;
+            pos = (r.px + r.ps) * 0.5f + origin;
         }
     } else {
         const Core A = makeCore(ta, sa, hull, origin);
@@ -900,7 +1089,7 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCoun
             o[4] = make_uint4(s.id[0], s.id[1], s.id[2], s.id[3]);
         }
     }
-    }   // tile loop
+    }   // chunk loop
 }
 
 // ---- kernel 1b: contact slots in pair order ------------------------------------------------------------

@@ -759,6 +759,67 @@ EpaResult epa(const Core& A, const Core& B, const AxrefNarrowCfg& cfg, const Sim
     return r;
 }
 
+// Sphere against box in closed form (the box as in makeCore: centre cX, unit axes = the columns of
+// Quat::toMatrix, half lengths |halfExtent * scale|; all points relative to A's position).
+//   outside: closest box point q by clamping the centre's box coordinates; gap = |q - cS| - r
+//   inside : leave through the nearest face (lowest axis on ties); depth = face gap + r
+// nsx = unit direction from the sphere towards the box, ps / px = witness points on the sphere / box.
+struct SphereBox {
+    bool contact;
+    float dist, depth;
+    V3 nsx, ps, px;
+};
+SphereBox sphereBox(V3 cS, float r, V3 cX, const Xf& tX, const AxrefShape& sX) {
+    SphereBox o{};
+    M3 m = quatToMat3(tX.q);
+    const V3 ax[3] = {m.c0, m.c1, m.c2};
+    const float half[3] = {std::fabs(sX.p0 * tX.s.x), std::fabs(sX.p1 * tX.s.y), std::fabs(sX.p2 * tX.s.z)};
+    V3 d = cS - cX;
+    float x[3];
+    bool inside = true;
+    V3 q = cX;
+    for (int i = 0; i < 3; ++i) {
+        x[i] = dot(d, ax[i]);
+        float k = x[i];
+        if (k > half[i]) {
+            k = half[i];
+            inside = false;
+        } else if (k < -half[i]) {
+            k = -half[i];
+            inside = false;
+        }
+        q = q + ax[i] * k;
+    }
+    if (!inside) {
+        V3 v = q - cS;
+        float l = std::sqrt(dot(v, v));
+        o.dist = l - r;
+        o.depth = r - l;
+        o.contact = o.depth >= 0.0f;
+        o.nsx = (l > 0.0f) ? v * (1.0f / l) : mk(1.0f, 0.0f, 0.0f);
+        o.ps = cS + o.nsx * r;
+        o.px = q;
+        return o;
+    }
+    int best = 0;
+    float gap = half[0] - std::fabs(x[0]);
+    for (int i = 1; i < 3; ++i) {
+        float g = half[i] - std::fabs(x[i]);
+        if (g < gap) {
+            gap = g;
+            best = i;
+        }
+    }
+    V3 out = (x[best] >= 0.0f) ? ax[best] : -ax[best];   // from the box centre's side towards the sphere
+    o.contact = true;
+    o.depth = gap + r;
+    o.dist = -o.depth;
+    o.nsx = -out;
+    o.ps = cS + o.nsx * r;
+    o.px = cS + out * gap;
+    return o;
+}
+
 struct PairOut {
     bool contact;
     bool usedEpa;
@@ -786,6 +847,22 @@ PairOut collidePair(uint32_t ia, uint32_t ib, const Xf& ta, const AxrefShape& sa
         n = (dist > 0.0f) ? d * (1.0f / dist) : mk(1.0f, 0.0f, 0.0f);
         pa = n * sa.p0;
         pb = d - n * sb.p0;
+    } else if (sa.type == SHAPE_SPHERE && sb.type == SHAPE_BOX) {
+        SphereBox r = sphereBox(mk(0, 0, 0), sa.p0, tb.p - origin, tb, sb);
+        o.dist = r.dist;
+        if (!r.contact) return o;
+        depth = r.depth;
+        n = r.nsx;
+        pa = r.ps;
+        pb = r.px;
+    } else if (sa.type == SHAPE_BOX && sb.type == SHAPE_SPHERE) {
+        SphereBox r = sphereBox(tb.p - origin, sb.p0, mk(0, 0, 0), ta, sa);
+        o.dist = r.dist;
+        if (!r.contact) return o;
+        depth = r.depth;
+        n = -r.nsx;
+        pa = r.px;
+        pb = r.ps;
     } else {
         Core A = makeCore(ta, sa, hull, origin);
         Core B = makeCore(tb, sb, hull, origin);

@@ -116,7 +116,55 @@ def test_sphere_vs_axis_aligned_box_clamped_point():
         if hit and abs(expect) > 1e-3 and (outside > 1e-3 or np.sort(hf - np.abs(cf))[1] - np.sort(hf - np.abs(cf))[0] > 1e-3):
             np.testing.assert_allclose([con["nx"], con["ny"], con["nz"]], n, atol=2e-4)
             assert abs(con["depth"] + expect) < TOL
-            assert epa == (outside <= 1e-6)
+        assert not epa   # sphere-box is closed form, inside or outside
+
+
+def test_sphere_vs_rotated_scaled_box_closed_form():
+    """Independent numpy restatement: clamp the sphere centre in the box frame (rotation from the
+    quaternion, half lengths = halfExtent * scale), both argument orders."""
+    rng = np.random.default_rng(12)
+    for it in range(400):
+        h = rng.uniform(0.2, 0.9, 3)
+        sc = rng.uniform(0.5, 1.5, 3)
+        axis = rng.normal(size=3)
+        q = O.axis_angle(axis / np.linalg.norm(axis), rng.uniform(0, 2 * np.pi))
+        cb = rng.uniform(-1, 1, 3)
+        cs = cb + rng.uniform(-1.8, 1.8, 3)
+        r = rng.uniform(0.1, 0.6)
+        R = O.quat_to_mat3(q).astype(float)
+        half = np.float32(h).astype(float) * np.float32(sc).astype(float)
+        x = R.T @ (np.float32(cs).astype(float) - np.float32(cb).astype(float))
+        k = np.clip(x, -half, half)
+        out = np.linalg.norm(x - k)
+        if np.any(np.abs(x) > half):
+            expect = out - float(np.float32(r))
+            n_box_to_sphere = R @ ((x - k) / out) if out > 0 else None
+        else:
+            gaps = half - np.abs(x)
+            j = int(np.argmin(gaps))
+            expect = -(gaps[j] + float(np.float32(r)))
+            n_box_to_sphere = R[:, j] * (1.0 if x[j] >= 0 else -1.0)
+            if np.sort(gaps)[1] - np.sort(gaps)[0] < 1e-3:
+                n_box_to_sphere = None   # ambiguous exit face
+        box_first = it % 2 == 0
+        if box_first:
+            hit, con, dist, epa = O.collide_pair(O.xf(cb, q, sc), O.box(*h), O.xf(cs), O.sphere(r))
+        else:
+            hit, con, dist, epa = O.collide_pair(O.xf(cs), O.sphere(r), O.xf(cb, q, sc), O.box(*h))
+        assert not epa
+        assert abs(dist - expect) < TOL
+        if abs(expect) > 1e-3:
+            assert hit == (expect < 0)
+        if hit and abs(expect) > 1e-3:
+            assert abs(con["depth"] + expect) < TOL
+            if n_box_to_sphere is not None:
+                n = n_box_to_sphere if box_first else -n_box_to_sphere   # normal points from A to B
+                np.testing.assert_allclose([con["nx"], con["ny"], con["nz"]], n, atol=2e-4)
+                # contact position = midpoint of the two surface witness points
+                if out > 0 or not np.any(np.abs(x) > half):
+                    surf_box = np.float32(cb).astype(float) + R @ (k if np.any(np.abs(x) > half) else x + (half[j] - abs(x[j])) * np.eye(3)[j] * (1 if x[j] >= 0 else -1))
+                    surf_sph = np.float32(cs).astype(float) - n_box_to_sphere * float(np.float32(r))
+                    np.testing.assert_allclose([con["px"], con["py"], con["pz"]], (surf_box + surf_sph) / 2, atol=5e-4)
 
 
 def test_axis_aligned_box_box_min_overlap_axis():

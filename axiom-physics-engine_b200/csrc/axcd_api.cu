@@ -43,6 +43,7 @@ struct AxcdContext {
     // device buffers
     float* dXf = nullptr;            // n * 10 floats (axiom::math::Transform AoS)
     uint4* dShapes = nullptr;
+    uint8_t* dType8 = nullptr;       // shape type per body, rewritten by every refit
     float4* dHull = nullptr;
     uint32_t* dWorld = nullptr;
     uint32_t* dBodyKeys = nullptr;   // slab mode: global id of every local body
@@ -226,7 +227,7 @@ void axcd_destroy(AxcdContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
+    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dType8, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
@@ -278,6 +279,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         // +64 floats of slack: the staged 128-bit loads may touch the tail of the last block
         CU(dalloc(&ctx->dXf, nb * 10 + 64));
         CU(dalloc(&ctx->dShapes, nb));
+        CU(dalloc(&ctx->dType8, nb));
         CU(dalloc(&ctx->dHull, (size_t)cfg->maxHullVerts));
         if (cfg->numWorlds > 1) {
             CU(dalloc(&ctx->dWorld, nb));
@@ -416,7 +418,7 @@ int32_t axcd_refit(AxcdContext* ctx) {
         const uint32_t blocks = (ctx->n + kRefitThreads - 1) / kRefitThreads;
         refitKernel<<<blocks, kRefitThreads, 0, ctx->stream>>>(
             reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
-            reinterpret_cast<float4*>(ctx->dAabb), ctx->n, ctx->cfg.aabbMargin, ctx->dCtr);
+            reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin, ctx->dCtr);
         CU(cudaGetLastError());
     }
     ctx->launches[0] = ctx->n ? 1 : 0;
@@ -479,7 +481,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         CU(cudaGetLastError());
         recordEv(ctx, EV_BUILD);
         // ---- traversal ---------------------------------------------------------------------------
-        CU(cudaMemsetAsync(ctx->dBodyCount, 0, sizeof(uint32_t) * 2 * n, st));
+        CU(cudaMemsetAsync(ctx->dBodyCount, 0, sizeof(uint32_t) * n, st));
         const uint32_t tb = (n + kTravThreads - 1) / kTravThreads;
         findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes,
                                                      ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
@@ -491,10 +493,12 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         // ---- canonical order: counting sort by body a, then tiny per-body sorts by b ------------------
         const uint32_t scanTiles = (n + kScanTile - 1) / kScanTile;
         CU(cudaMemsetAsync(ctx->dScanStatus, 0, sizeof(uint32_t) * (scanTiles + 1), st));
-        exclusiveScanKernel<<<scanTiles, kScanThreads, 0, st>>>(ctx->dBodyCount, ctx->dBodyStart, n, ctx->dScanStatus,
-                                                                &ctx->dCtr->scanTicket, &ctx->dCtr->storedPairs);
+        // the scan writes the segment starts twice: dBodyStart stays, the copy is the scatter's fill cursor
+        exclusiveScanKernel<<<scanTiles, kScanThreads, 0, st>>>(ctx->dBodyCount, ctx->dBodyStart, ctx->dBodyCount + n, n,
+                                                                ctx->dScanStatus, &ctx->dCtr->scanTicket,
+                                                                &ctx->dCtr->storedPairs);
         scatterPairsKernel<<<kNumSMs * 8, 256, 0, st>>>(ctx->dPairsTmp, &ctx->dCtr->pairCount, ctx->cfg.maxPairs,
-                                                        ctx->dBodyStart, ctx->dBodyCount + n, ctx->dSegB);
+                                                        ctx->dBodyCount + n, ctx->dSegB);
         sortSegmentsKernel<<<b256, 256, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIRSORT);
@@ -541,7 +545,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         const uint2* pairs = ctx->dPairs;
         const uint32_t* pairCount = &ctx->dCtr->pairCount;
         const uint32_t chunkCap = chunkCapFor(mp);
-        classifyPairsKernel<<<classifyBlocksFor(mp), kClsThreads, 0, st>>>(pairs, pairCount, mp, ctx->dShapes, ctx->dChunks,
+        classifyPairsKernel<<<classifyBlocksFor(mp), kClsThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dChunks,
                                                                             chunkCap, ctx->dCtr);
         gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dHull, p,
                                                  ctx->dFlags, ctx->dTmpContacts, q, ctx->cfg.maxContacts,

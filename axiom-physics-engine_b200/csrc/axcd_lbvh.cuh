@@ -307,16 +307,17 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
 }
 
 // ---- canonical pair order by counting sort ---------------------------------------------------------
-// bodyStart = exclusive scan of bodyCount (done with exclusiveScanKernel).  scatterPairsKernel drops
+// bodyStart = exclusive scan of bodyCount (done with exclusiveScanKernel, which also writes the copy
+// that serves as the fill cursor).  scatterPairsKernel drops
 // every pair's b into its body-a segment (order inside a segment is arbitrary); sortSegmentsKernel
 // then sorts each segment and writes the final (a, b) list, which is thereby sorted by (a, b).
 __global__ void scatterPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount,
-                                   uint32_t maxPairs, const uint32_t* __restrict__ bodyStart,
-                                   uint32_t* __restrict__ bodyFill, uint32_t* __restrict__ segB) {
+                                   uint32_t maxPairs, uint32_t* __restrict__ bodyCursor,   // starts as a copy of bodyStart
+                                   uint32_t* __restrict__ segB) {
     const uint32_t np = min(*pairCount, maxPairs);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
         const uint2 pr = pairs[k];
-        const uint32_t pos = bodyStart[pr.x] + atomicAdd(&bodyFill[pr.x], 1u);
+        const uint32_t pos = atomicAdd(&bodyCursor[pr.x], 1u);
         segB[pos] = pr.y;
     }
 }

@@ -873,7 +873,7 @@ __host__ __device__ constexpr uint32_t chunkCapFor(uint32_t maxPairs) {
 
 __global__ void __launch_bounds__(kClsThreads)
 classifyPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
-                    const uint4* __restrict__ shapes, uint32_t* __restrict__ chunks, uint32_t chunkCap,
+                    const uint8_t* __restrict__ type8, uint32_t* __restrict__ chunks, uint32_t chunkCap,
                     Counters* __restrict__ ctr) {
     __shared__ uint32_t sCarry[kNumClasses][32];   // < 32 leftovers per class from the earlier tiles
     __shared__ uint32_t sCarryN[kNumClasses];
@@ -898,18 +898,15 @@ classifyPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict_
             pos[j] = 0;
             if (k < npairs) {
                 const uint2 pk = __ldg(pairs + k);
-                cls[j] = pairClass(__ldg(&shapes[pk.x].x), __ldg(&shapes[pk.y].x));
+                cls[j] = pairClass(__ldg(type8 + pk.x), __ldg(type8 + pk.y));
             }
-#pragma unroll
-            for (int c = 0; c < kNumClasses; ++c) {   // warp-aggregated slot reservation
-                const uint32_t bal = __ballot_sync(0xffffffffu, cls[j] == c);
-                if (!bal) continue;
-                const int leader = __ffs(bal) - 1;
-                uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(&sCnt[c], (uint32_t)__popc(bal));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (cls[j] == c) pos[j] = base + __popc(bal & ((1u << lane) - 1u));
-            }
+            // warp-aggregated slot reservation: the lanes of one class elect a leader
+            const uint32_t peers = __match_any_sync(0xffffffffu, cls[j]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader && cls[j] >= 0) base = atomicAdd(&sCnt[cls[j]], (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            pos[j] = base + __popc(peers & ((1u << lane) - 1u));
         }
         __syncthreads();
         if (tid == 0) {

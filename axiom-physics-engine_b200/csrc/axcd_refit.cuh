@@ -37,6 +37,7 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
             const uint4* __restrict__ shapes,    // AxcdShape as uint4
             const float4* __restrict__ hull,     // hull vertices padded to float4
             float4* __restrict__ aabb4,          // n*24 bytes viewed as float4
+            uint8_t* __restrict__ type8,         // out: shape type per body, compact (pair classification gathers it)
             uint32_t n, float margin, Counters* __restrict__ ctr) {
     __shared__ __align__(16) float sIn[kRefitThreads * 10];
     __shared__ __align__(16) float sOut[kRefitThreads * 6];
@@ -66,6 +67,7 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
         const float4 q = make_float4(t[3], t[4], t[5], t[6]);
         const V3 scl = mk3(t[7], t[8], t[9]);
         const uint4 sh = __ldg(shapes + base + tid);
+        type8[base + tid] = (uint8_t)sh.x;
         const float p0 = __uint_as_float(sh.y), p1 = __uint_as_float(sh.z), p2 = __uint_as_float(sh.w);
         if (sh.x == AXCD_SHAPE_SPHERE) {
             // AABB::fromCenterExtents(position, Vec3(r)) (aabb.hpp:213-215); rotation and scale

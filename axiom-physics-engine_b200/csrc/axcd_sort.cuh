@@ -247,10 +247,11 @@ __global__ void fillRandomKeysKernel(uint32_t* __restrict__ keys, uint32_t* __re
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
+static_assert(kScanItems == 8, "the scan kernel moves 8 words per thread as two uint4");
 
-// out[i] = sum of in[0..i); *total = sum of all.  status: numTiles words, zero-initialised.
+// out[i] = out2[i] = sum of in[0..i); *total = sum of all.  status: numTiles words, zero-initialised.
 __global__ void __launch_bounds__(kScanThreads)
-exclusiveScanKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+exclusiveScanKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ out2, uint32_t n,
                     volatile uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
                     uint32_t* __restrict__ total) {
     __shared__ uint32_t sWarp[kScanThreads / 32];
@@ -262,11 +263,15 @@ exclusiveScanKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
     const uint32_t base = tile * kScanTile + tid * kScanItems;
     uint32_t v[kScanItems];
     uint32_t sum = 0;
+    if (base + kScanItems <= n) {   // cudaMalloc'd input, base is a multiple of 8 words: two 16-byte loads
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(in + base)), b = __ldg(reinterpret_cast<const uint4*>(in + base) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        v[k] = (base + k < n) ? in[base + k] : 0u;
-        sum += v[k];
+        for (int k = 0; k < kScanItems; ++k) v[k] = (base + k < n) ? in[base + k] : 0u;
     }
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) sum += v[k];
     uint32_t inc = sum;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -281,29 +286,62 @@ exclusiveScanKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
         wbase += (i < warp) ? sWarp[i] : 0u;
         tileTotal += sWarp[i];
     }
-    if (tid == 0) {
+    if (warp == 0) {   // warp-parallel decoupled look-back: 32 predecessor tiles per step
         uint32_t excl = 0;
         if (tile == 0) {
-            status[0] = kFlagInclusive | tileTotal;
+            if (lane == 0) status[0] = kFlagInclusive | tileTotal;
         } else {
-            status[tile] = kFlagAggregate | tileTotal;
-            for (int t = (int)tile - 1; t >= 0; --t) {
-                uint32_t s;
-                do { s = status[t]; } while ((s & kFlagMask) == 0);
-                excl += s & kValueMask;
-                if ((s & kFlagMask) == kFlagInclusive) break;
+            if (lane == 0) status[tile] = kFlagAggregate | tileTotal;
+            int t = (int)tile - 1;
+            while (true) {
+                const int idx = t - lane;
+                uint32_t sv = kFlagInclusive;   // lanes before tile 0 act as an inclusive zero
+                if (idx >= 0) {
+                    do { sv = status[idx]; } while ((sv & kFlagMask) == 0);
+                }
+                const uint32_t incMask = __ballot_sync(0xffffffffu, (sv & kFlagMask) == kFlagInclusive);
+                const int firstInc = incMask ? (__ffs(incMask) - 1) : 32;
+                uint32_t v2 = (lane <= firstInc) ? (sv & kValueMask) : 0u;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+                excl += v2;
+                if (incMask) break;
+                t -= 32;
             }
-            status[tile] = kFlagInclusive | (excl + tileTotal);
+            if (lane == 0) status[tile] = kFlagInclusive | (excl + tileTotal);
         }
-        sExcl = excl;
-        if ((tile + 1) * (uint64_t)kScanTile >= n) *total = excl + tileTotal;
+        if (lane == 0) {
+            sExcl = excl;
+            if ((tile + 1) * (uint64_t)kScanTile >= n) *total = excl + tileTotal;
+        }
     }
     __syncthreads();
     uint32_t run = sExcl + wbase + inc - sum;
+    if (base + kScanItems <= n) {
+        uint32_t o[kScanItems];
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        if (base + k < n) out[base + k] = run;
-        run += v[k];
+        for (int k = 0; k < kScanItems; ++k) {
+            o[k] = run;
+            run += v[k];
+        }
+        reinterpret_cast<uint4*>(out + base)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<uint4*>(out + base)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        if ((reinterpret_cast<uintptr_t>(out2 + base) & 15u) == 0) {
+            reinterpret_cast<uint4*>(out2 + base)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<uint4*>(out2 + base)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) out2[base + k] = o[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (base + k < n) {
+                out[base + k] = run;
+                out2[base + k] = run;
+            }
+            run += v[k];
+        }
     }
 }
 

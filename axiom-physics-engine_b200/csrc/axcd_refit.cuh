@@ -75,16 +75,45 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
             lo = pos - mk3(p0, p0, p0);
             hi = pos + mk3(p0, p0, p0);
         } else if (sh.x == AXCD_SHAPE_BOX) {
-            // 8 corners in the order of src/debug/debug_draw.cpp:99-108, AABB(Vec3) then expand()
-            const float sx[8] = {-1.f, 1.f, 1.f, -1.f, -1.f, 1.f, 1.f, -1.f};
-            const float sy[8] = {-1.f, -1.f, -1.f, -1.f, 1.f, 1.f, 1.f, 1.f};
-            const float sz[8] = {-1.f, -1.f, 1.f, 1.f, -1.f, -1.f, 1.f, 1.f};
-            V3 c0 = transformPoint(pos, q, scl, mk3(sx[0] * p0, sy[0] * p1, sz[0] * p2));
-            lo = c0;
-            hi = c0;
-#pragma unroll
-            for (int k = 1; k < 8; ++k)
-                expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(sx[k] * p0, sy[k] * p1, sz[k] * p2)));
+            // 8 corners in the order of src/debug/debug_draw.cpp:99-108, AABB(Vec3) then expand().
+            // The corners come in antipodal pairs +-c, and every step of transformPoint before the
+            // final "+ position" is odd under round-to-nearest: (-c)*scale == -(c*scale) and
+            // quatRotate(q, -v) == -quatRotate(q, v) bit for bit (products and fmaf negate exactly).
+            // So 4 rotations r_k give all 8 corners as pos +- r_k, and because fl(pos + r) is
+            // monotone in r the select-based min/max over the 8 corners equals pos -+ max_k |r_k|.
+            // Exceptions, sent down the literal 8-corner path: a zero position component (the sign
+            // of an exact zero sum, -0 + -0, depends on the sign of a zero r) and non-finite data
+            // (NaN corners are skipped by expand(), which is order-dependent).
+            const V3 sc = mk3(p0 * scl.x, p1 * scl.y, p2 * scl.z);   // corner 6 = (+,+,+), scaled
+            const V3 r0 = quatRotate(q, sc);                               // corner 6 (-> 0)
+            const V3 r1 = quatRotate(q, mk3(sc.x, -sc.y, -sc.z));           // corner 1 (-> 7)
+            const V3 r2 = quatRotate(q, mk3(sc.x, -sc.y, sc.z));            // corner 2 (-> 4)
+            const V3 r3 = quatRotate(q, mk3(sc.x, sc.y, -sc.z));            // corner 5 (-> 3)
+            const V3 m = mk3(fmaxf(fmaxf(fabsf(r0.x), fabsf(r1.x)), fmaxf(fabsf(r2.x), fabsf(r3.x))),
+                             fmaxf(fmaxf(fabsf(r0.y), fabsf(r1.y)), fmaxf(fabsf(r2.y), fabsf(r3.y))),
+                             fmaxf(fmaxf(fabsf(r0.z), fabsf(r1.z)), fmaxf(fabsf(r2.z), fabsf(r3.z))));
+            // finite check on everything the result depends on; NaN anywhere makes the sum NaN
+            // (fmaxf would drop a NaN operand, so the r_k are summed, not m)
+            const float chk = (fabsf(r0.x) + fabsf(r0.y) + fabsf(r0.z)) + (fabsf(r1.x) + fabsf(r1.y) + fabsf(r1.z)) +
+                              (fabsf(r2.x) + fabsf(r2.y) + fabsf(r2.z)) + (fabsf(r3.x) + fabsf(r3.y) + fabsf(r3.z)) +
+                              (fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z));
+            if (chk < 3.0e38f && pos.x != 0.0f && pos.y != 0.0f && pos.z != 0.0f) {
+                lo = pos - m;
+                hi = pos + m;
+            } else {
+                // corner k of debug_draw.cpp:99-108: x sign + for k in {1,2,5,6}, y sign + for k >= 4,
+                // z sign + for k in {2,3,6,7}
+                V3 c0 = transformPoint(pos, q, scl, mk3(-p0, -p1, -p2));
+                lo = c0;
+                hi = c0;
+#pragma unroll 1
+                for (int k = 1; k < 8; ++k) {
+                    const float cx = ((k ^ (k >> 1)) & 1) ? p0 : -p0;
+                    const float cy = (k & 4) ? p1 : -p1;
+                    const float cz = (k & 2) ? p2 : -p2;
+                    expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(cx, cy, cz)));
+                }
+            }
         } else if (sh.x == AXCD_SHAPE_CAPSULE) {
             // p0 = radius, p1 = height: box of the two end spheres, endpoints placed as the reference
             // does (src/debug/physics_debug_draw.cpp:254-266: local (0, -+height/2, 0) through

@@ -25,6 +25,14 @@ SHAPE_DT = np.dtype([("type", "<u4"), ("p0", "<f4"), ("p1", "<f4"), ("p2", "<f4"
 CONTACT_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),
                        ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("depth", "<f4"),
                        ("status", "<u4")])
+MANIFOLD_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                        ("count", "<u4"), ("px", "<f4", (4,)), ("py", "<f4", (4,)), ("pz", "<f4", (4,)),
+                        ("depth", "<f4", (4,))])
+RAY_DT = np.dtype([("ox", "<f4"), ("oy", "<f4"), ("oz", "<f4"), ("dx", "<f4"), ("dy", "<f4"), ("dz", "<f4"),
+                   ("tMax", "<f4"), ("world", "<u4")])
+RAYHIT_DT = np.dtype([("body", "<u4"), ("t", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                      ("flags", "<u4")])
+NO_HIT = 0xFFFFFFFF
 
 # every symbol include/axcd.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -32,6 +40,7 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
+    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast",
     "axcd_set_filters", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
     "axcd_set_ghosts_device",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
@@ -57,7 +66,7 @@ class Stats(C.Structure):
                 ("gjkMs", C.c_float), ("epaMs", C.c_float), ("totalMs", C.c_float),
                 ("broadphaseTime", C.c_float), ("narrowphaseTime", C.c_float),
                 ("bytesMoved", C.c_uint64), ("kernelLaunches", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("contactPointCount", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -100,7 +109,8 @@ def load_library():
                      "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
                      "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
                      "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
-                     "axcd_pack_ghosts", "axcd_set_ghosts_device", "axcd_set_filters"):
+                     "axcd_pack_ghosts", "axcd_set_ghosts_device", "axcd_set_filters",
+                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -113,6 +123,11 @@ def load_library():
         lib.axcd_get_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.axcd_get_pair_distances.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.axcd_get_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.axcd_build_manifolds.argtypes = [C.c_void_p]
+        lib.axcd_get_manifolds.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.axcd_query_aabbs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                         C.c_void_p]
+        lib.axcd_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.axcd_test_sort_pairs32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                C.c_uint32]
         lib.axcd_test_sort_keys64.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
@@ -381,6 +396,43 @@ class CollisionWorld:
         self._check(self._lib.axcd_get_contacts(self._ctx, C.c_void_p(host_ptr), cap,
                                                 C.byref(cnt)), "axcd_get_contacts")
         return cnt.value
+
+    def build_manifolds(self):
+        """Contact manifolds of the last narrowphase (asynchronous; once per narrowphase)."""
+        self._check(self._lib.axcd_build_manifolds(self._ctx), "axcd_build_manifolds")
+
+    def manifolds(self):
+        """(records in contact order, total contact-point count)."""
+        cap = max(1, self.stats().numContacts)
+        out = np.zeros(cap, MANIFOLD_DT)
+        cnt, pts = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.axcd_get_manifolds(self._ctx, _ptr(out), cap, C.byref(cnt), C.byref(pts)),
+                    "axcd_get_manifolds")
+        return out[:cnt.value], pts.value
+
+    # ---- scene queries on the LBVH of the last broadphase ------------------------------------------
+    def query_aabbs(self, boxes, query_world=None):
+        """(query, body) index pairs, sorted, for query boxes (k,6) float32 = (min, max)."""
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 6)
+        qw = np.ascontiguousarray(query_world, dtype=np.uint32) if query_world is not None else None
+        cap = max(1024, 8 * len(boxes))
+        while True:
+            out = np.zeros((cap, 2), np.uint32)
+            cnt = C.c_uint32(0)
+            rc = self._lib.axcd_query_aabbs(self._ctx, _ptr(boxes), _ptr(qw), len(boxes), _ptr(out), cap,
+                                            C.byref(cnt))
+            if rc == 601 and cnt.value > cap:
+                cap = cnt.value
+                continue
+            self._check(rc, "axcd_query_aabbs")
+            return out[:cnt.value]
+
+    def raycast(self, rays):
+        """Closest hit per ray; rays is a RAY_DT array, the result a RAYHIT_DT array."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DT)
+        out = np.zeros(max(1, len(rays)), RAYHIT_DT)
+        self._check(self._lib.axcd_raycast(self._ctx, _ptr(rays), len(rays), _ptr(out)), "axcd_raycast")
+        return out[:len(rays)]
 
     def set_filters(self, filters):
         """filters: (n,3) array of (categoryBits, maskBits, groupIndex) or None to switch filtering off."""

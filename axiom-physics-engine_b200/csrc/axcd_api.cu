@@ -11,6 +11,8 @@
 #include "axcd_epa_coop.cuh"
 #include "axcd_epa_warp.cuh"
 #include "axcd_narrow.cuh"
+#include "axcd_manifold.cuh"
+#include "axcd_query.cuh"
 #include "axcd_refit.cuh"
 #include "axcd_sort.cuh"
 
@@ -79,6 +81,14 @@ struct AxcdContext {
     uint32_t* dSlots = nullptr;      // per pair: contact slot
     AxcdContact* dTmpContacts = nullptr;   // per pair: shallow contact records before compaction
     AxcdContact* dContacts = nullptr;
+    AxcdManifold* dManifolds = nullptr;   // allocated by the first axcd_build_manifolds
+    bool manifoldsValid = false;          // built for the current narrowphase result
+    int sortedBuf = 0;                    // which of dKeys/dVals holds the sorted order of the last broadphase
+    // scene-query scratch (grow-only)
+    void* dQIn = nullptr;      size_t qInBytes = 0;      // query boxes / rays (+ worlds)
+    void* dQCount = nullptr;   size_t qCountBytes = 0;   // counts, starts, cursors, scan status, ticket/total
+    void* dQSeg = nullptr;     size_t qSegBytes = 0;     // hit bodies per query segment
+    void* dQOut = nullptr;     size_t qOutBytes = 0;     // sorted (query, body) hits / ray hits
     float* dPairDist = nullptr;
     uint32_t* dSortHist = nullptr;
     uint32_t* dSortStatus = nullptr;
@@ -230,7 +240,7 @@ void axcd_destroy(AxcdContext* ctx) {
     void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dType8, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
-                    ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dPairDist, ctx->dSortHist,
+                    ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dManifolds, ctx->dQIn, ctx->dQCount, ctx->dQSeg, ctx->dQOut, ctx->dPairDist, ctx->dSortHist,
                     ctx->dSortStatus, ctx->dCtr, ctx->dCtrInit};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -412,6 +422,7 @@ int32_t axcd_refit(AxcdContext* ctx) {
     if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     recordEv(ctx, EV_START);
+    ctx->manifoldsValid = false;
     // reset per-step counters: bounds (min = +inf encoding, max = -inf encoding) and counts
     CU(cudaMemcpyAsync(ctx->dCtr, ctx->dCtrInit, sizeof(Counters), cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->n) {
@@ -449,6 +460,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
                                                  passes, ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st);
         CU(cudaGetLastError());
         recordEv(ctx, EV_SORT);
+        ctx->sortedBuf = sb;
         const uint32_t* sKeys = ctx->dKeys[sb];
         const uint32_t* sVals = ctx->dVals[sb];
         // ---- LBVH ------------------------------------------------------------------------------
@@ -524,6 +536,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
     cudaStream_t st = ctx->stream;
     recordEv(ctx, EV_N0);
     ctx->numContacts = ctx->foundContacts = 0;
+    ctx->manifoldsValid = false;
     ctx->launches[2] = 0;
     if (ctx->n >= 2) {
         NarrowParams p;
@@ -597,6 +610,7 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
         out->numPenetrating = ctx->hostCtr.epaCount;
         out->gjkFailures = ctx->hostCtr.gjkFailures;
         out->epaFailures = ctx->hostCtr.epaFailures;
+        out->contactPointCount = ctx->manifoldsValid ? ctx->hostCtr.manifoldPoints : 0;
     }
     out->refitMs = evMs(ctx, EV_START, EV_REFIT);
     if (ctx->stage >= ST_BROAD) {
@@ -698,6 +712,137 @@ int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap, uint
     if (cap < ctx->numContacts) return AXCD_ERR_OUT_OF_RANGE;
     CU(cudaMemcpyAsync(out, ctx->dContacts, sizeof(AxcdContact) * ctx->numContacts, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return AXCD_OK;
+}
+
+int32_t axcd_build_manifolds(AxcdContext* ctx) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_NARROW) return AXCD_ERR_GPU_INVALID_OP;
+    if (ctx->manifoldsValid) return AXCD_ERR_GPU_INVALID_OP;   // once per narrowphase, like the other stages
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (!ctx->dManifolds) CU(dalloc(&ctx->dManifolds, (size_t)ctx->cfg.maxContacts));
+    if (ctx->n >= 2) {
+        uint32_t blocks = (ctx->cfg.maxContacts + kManThreads - 1) / kManThreads;
+        if (blocks > (uint32_t)kNumSMs * 8) blocks = kNumSMs * 8;   // the contact count lives on the device
+        manifoldKernel<<<blocks, kManThreads, 0, ctx->stream>>>(ctx->dContacts, &ctx->dCtr->contactCount, ctx->cfg.maxContacts,
+                                                                ctx->dXf, ctx->dShapes,
+                                                                reinterpret_cast<float4*>(ctx->dManifolds),
+                                                                &ctx->dCtr->manifoldPoints);
+        CU(cudaGetLastError());
+    }
+    ctx->manifoldsValid = true;
+    return AXCD_OK;
+}
+
+int32_t axcd_get_manifolds(AxcdContext* ctx, AxcdManifold* out, uint32_t cap, uint32_t* outCount, uint32_t* outPointCount) {
+    if (!ctx || !outCount) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_NARROW || !ctx->manifoldsValid) return AXCD_ERR_GPU_INVALID_OP;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    {
+        const int rc = refreshCountersImpl(ctx);
+        if (rc) return rc;
+    }
+    *outCount = ctx->numContacts;
+    if (outPointCount) *outPointCount = ctx->hostCtr.manifoldPoints;
+    if (ctx->numContacts == 0) return AXCD_OK;
+    if (!out) return AXCD_ERR_NULL_POINTER;
+    if (cap < ctx->numContacts) return AXCD_ERR_OUT_OF_RANGE;
+    CU(cudaMemcpyAsync(out, ctx->dManifolds, sizeof(AxcdManifold) * ctx->numContacts, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return AXCD_OK;
+}
+
+namespace {
+cudaError_t growScratch(void** p, size_t* cur, size_t need) {
+    if (need <= *cur) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cur = 0;
+    const cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess) *cur = need;
+    return e;
+}
+QueryTree queryTreeOf(const AxcdContext* ctx) {
+    QueryTree T;
+    T.leafLo = ctx->dSegLo + ctx->segP;
+    T.nodes = ctx->dNodes;
+    T.sortedKeys = ctx->dKeys[ctx->sortedBuf];
+    T.aabb = ctx->dAabb;
+    T.worldId = ctx->hasWorlds ? ctx->dWorld : nullptr;
+    T.n = ctx->n;
+    T.worldShift = 3 * ctx->mortonBits;
+    T.hasWorlds = ctx->hasWorlds ? 1 : 0;
+    return T;
+}
+}  // namespace
+
+int32_t axcd_query_aabbs(AxcdContext* ctx, const float* boxes6, const uint32_t* queryWorld, uint32_t nq,
+                         uint32_t* outHits2, uint32_t cap, uint32_t* outCount) {
+    if (!ctx || !outCount || (nq && !boxes6)) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_BROAD) return AXCD_ERR_GPU_INVALID_OP;
+    *outCount = 0;
+    if (nq == 0 || ctx->n == 0) return AXCD_OK;
+    if (nq > (1u << 28)) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    const uint32_t scanTiles = (nq + kScanTile - 1) / kScanTile;
+    // layout of dQCount: counts[nqPad] | starts[nqPad] | cursor copy[nqPad] | status[scanTiles + 1] | ticket | total
+    const uint32_t nqPad = (nq + 3u) & ~3u;   // the scan stores 16-byte vectors: keep every sub-buffer aligned
+    const size_t words = 3 * (size_t)nqPad + scanTiles + 1 + 2;
+    CU(growScratch(&ctx->dQIn, &ctx->qInBytes, (size_t)nq * 28));
+    CU(growScratch(&ctx->dQCount, &ctx->qCountBytes, words * 4));
+    float* dBoxes = static_cast<float*>(ctx->dQIn);
+    uint32_t* dQW = reinterpret_cast<uint32_t*>(dBoxes + (size_t)nq * 6);
+    uint32_t* dCounts = static_cast<uint32_t*>(ctx->dQCount);
+    uint32_t* dStarts = dCounts + nqPad;
+    uint32_t* dCursor = dStarts + nqPad;
+    uint32_t* dStatus = dCursor + nqPad;
+    uint32_t* dTicket = dStatus + scanTiles + 1;
+    uint32_t* dTotal = dTicket + 1;
+    CU(cudaMemcpyAsync(dBoxes, boxes6, (size_t)nq * 24, cudaMemcpyHostToDevice, st));
+    const bool useWorld = ctx->hasWorlds && queryWorld;
+    if (useWorld) CU(cudaMemcpyAsync(dQW, queryWorld, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dStatus, 0, sizeof(uint32_t) * (scanTiles + 3), st));
+    const QueryTree T = queryTreeOf(ctx);
+    const uint32_t blocks = (nq + kQueryThreads - 1) / kQueryThreads;
+    queryAabbKernel<false><<<blocks, kQueryThreads, 0, st>>>(T, dBoxes, useWorld ? dQW : nullptr, nq, dCounts, nullptr, nullptr);
+    exclusiveScanKernel<<<scanTiles, kScanThreads, 0, st>>>(dCounts, dStarts, dCursor, nq, dStatus, dTicket, dTotal);
+    CU(cudaGetLastError());
+    uint32_t total = 0;
+    CU(cudaMemcpyAsync(&total, dTotal, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *outCount = total;
+    if (total == 0) return AXCD_OK;
+    if (total > cap) return AXCD_ERR_OUT_OF_RANGE;   // *outCount says how many slots are needed
+    if (!outHits2) return AXCD_ERR_NULL_POINTER;
+    CU(growScratch(&ctx->dQSeg, &ctx->qSegBytes, (size_t)total * 4));
+    CU(growScratch(&ctx->dQOut, &ctx->qOutBytes, (size_t)total * 8));
+    queryAabbKernel<true><<<blocks, kQueryThreads, 0, st>>>(T, dBoxes, useWorld ? dQW : nullptr, nq, dCounts, dStarts,
+                                                            static_cast<uint32_t*>(ctx->dQSeg));
+    sortSegmentsKernel<<<(nq + 255) / 256, 256, 0, st>>>(dStarts, dCounts, nq, static_cast<uint32_t*>(ctx->dQSeg),
+                                                          static_cast<uint2*>(ctx->dQOut));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(outHits2, ctx->dQOut, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AXCD_OK;
+}
+
+int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRayHit* outHits) {
+    if (!ctx || (nq && (!rays || !outHits))) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_BROAD) return AXCD_ERR_GPU_INVALID_OP;
+    if (nq == 0) return AXCD_OK;
+    if (nq > (1u << 26)) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    CU(growScratch(&ctx->dQIn, &ctx->qInBytes, (size_t)nq * sizeof(AxcdRay)));
+    CU(growScratch(&ctx->dQOut, &ctx->qOutBytes, (size_t)nq * sizeof(AxcdRayHit)));
+    CU(cudaMemcpyAsync(ctx->dQIn, rays, (size_t)nq * sizeof(AxcdRay), cudaMemcpyHostToDevice, st));
+    const QueryTree T = queryTreeOf(ctx);
+    raycastKernel<<<(nq + kQueryThreads - 1) / kQueryThreads, kQueryThreads, 0, st>>>(
+        T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes, static_cast<uint32_t*>(ctx->dQOut));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(outHits, ctx->dQOut, (size_t)nq * sizeof(AxcdRayHit), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return AXCD_OK;
 }
 

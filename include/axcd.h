@@ -122,7 +122,8 @@ typedef struct AxcdStats {
     float broadphaseTime, narrowphaseTime;
     uint64_t bytesMoved;    /* algorithmic HBM bytes of the step              */
     uint32_t kernelLaunches; /* kernels launched by the last refit+broadphase+narrowphase       */
-    uint32_t reserved;
+    uint32_t contactPointCount; /* gui::PhysicsWorldStats::contactPointCount (physics_panel.hpp:21):
+                                   manifold points of the last axcd_build_manifolds, else 0      */
 } AxcdStats;
 
 typedef struct AxcdContext AxcdContext; /* opaque */
@@ -163,6 +164,57 @@ AXCD_API int32_t axcd_get_pair_distances(AxcdContext* ctx, float* outDist, uint3
                                          uint32_t* outCount); /* needs AXCD_FLAG_PAIR_DISTANCES */
 AXCD_API int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap,
                                    uint32_t* outCount); /* same (a,b) order                     */
+
+/* ---- contact manifolds -------------------------------------------------
+ * One manifold per contact, in contact order: 1..4 points that share the contact's normal.  Each
+ * point is one debug::DebugContactPoint (position, normal, penetrationDepth;
+ * include/axiom/debug/physics_debug_draw.hpp:128-132) and the total is what
+ * gui::PhysicsWorldStats::contactPointCount reports (include/axiom/gui/physics_panel.hpp:21).
+ * Box-box contacts are clipped feature against feature (reference face / incident face, at most
+ * four points kept); every other shape pair keeps the narrowphase point.  Unused slots are zero. */
+typedef struct AxcdManifold {
+    uint32_t a, b;          /* == the contact's                                                  */
+    float nx, ny, nz;       /* == the contact's normal (a -> b)                                  */
+    uint32_t count;         /* 1..4                                                              */
+    float px[4], py[4], pz[4];
+    float depth[4];
+} AxcdManifold;
+/* Asynchronous on the context stream; needs axcd_narrowphase (or axcd_step) first; once per
+ * narrowphase (503 otherwise).  The device buffer (88 B x maxContacts) is allocated on first use. */
+AXCD_API int32_t axcd_build_manifolds(AxcdContext* ctx);
+AXCD_API int32_t axcd_get_manifolds(AxcdContext* ctx, AxcdManifold* out, uint32_t cap,
+                                    uint32_t* outCount, uint32_t* outPointCount /* or NULL */);
+
+/* ---- scene queries on the LBVH of the last broadphase ("scene queries",
+ * reference: CLAUDE.md:88).  Both need axcd_broadphase (or axcd_step) first and block until done.
+ *
+ * AABB overlap query: for each query box (axiom::math::AABB, 24 B) every body whose world AABB meets
+ * it under AABB::intersects (closed intervals, include/axiom/math/aabb.hpp:132-135).  outHits2
+ * receives (query, body) index pairs sorted by (query, body).  queryWorld (one world id per query)
+ * restricts each query to one world in batched mode; NULL = all worlds.  Returns 601 when cap is too
+ * small; *outCount then says how many pairs there are.                                             */
+AXCD_API int32_t axcd_query_aabbs(AxcdContext* ctx, const float* boxes6, const uint32_t* queryWorld,
+                                  uint32_t nq, uint32_t* outHits2, uint32_t cap, uint32_t* outCount);
+
+/* Closest-hit ray cast.  A body is hit iff the ray passes the slab test of its AABB within [0, tMax]
+ * and its shape test does: spheres, oriented boxes and capsules in closed form; convex hulls answer
+ * with their AABB (flags = 1).  t is the parameter along (dx,dy,dz), which need not be unit length;
+ * the normal is the unit surface normal at the hit (zero when the origin is inside the shape, t = 0, or
+ * for AABB-level hits).  No hit: body = 0xffffffff, t = tMax.  Ties go to the lower body index.
+ * `world` selects the world in batched mode (ignored when numWorlds == 1).                          */
+typedef struct AxcdRay {
+    float ox, oy, oz;
+    float dx, dy, dz;
+    float tMax;
+    uint32_t world;
+} AxcdRay;
+typedef struct AxcdRayHit {
+    uint32_t body;
+    float t;
+    float nx, ny, nz;
+    uint32_t flags;
+} AxcdRayHit;
+AXCD_API int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRayHit* outHits);
 
 /* Collision filtering, gui::FilterInfo semantics (include/axiom/gui/body_inspector.hpp:38-42):
  * two bodies with the same non-zero groupIndex collide iff it is positive; otherwise both

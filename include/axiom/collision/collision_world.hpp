@@ -81,7 +81,11 @@ static_assert(sizeof(math::AABB) == 24, "AABB must be the reference's 24-byte re
 
 using Shape = AxcdShape;            // flattened debug::DebugShape (physics_debug_draw.hpp:97-112)
 using ContactPoint = AxcdContact;   // debug::DebugContactPoint + pair ids (physics_debug_draw.hpp:128-132)
+using ContactManifold = AxcdManifold;   // 1..4 DebugContactPoints sharing one normal
+using Ray = AxcdRay;
+using RayHit = AxcdRayHit;
 struct BodyPair { std::uint32_t a, b; };
+struct QueryHit { std::uint32_t query, body; };
 
 struct CollisionConfig : AxcdConfig {
     CollisionConfig() { axcd_default_config(this); }
@@ -142,6 +146,31 @@ public:
         const std::int32_t rc = axcd_get_contacts(ctx_, out, capacity, &n);
         if (rc != AXCD_OK) return fail<std::uint32_t>(rc);
         return core::Result<std::uint32_t>::success(n);
+    }
+    /// Contact manifolds of the last narrowphase (box-box feature clipping, 1..4 points each);
+    /// stats().contactPointCount then reports gui::PhysicsWorldStats::contactPointCount.
+    core::Result<void> buildManifolds() { return wrap(axcd_build_manifolds(ctx_)); }
+    core::Result<std::uint32_t> getManifolds(ContactManifold* out, std::uint32_t capacity,
+                                             std::uint32_t* outPointCount = nullptr) {
+        std::uint32_t n = 0;
+        const std::int32_t rc = axcd_get_manifolds(ctx_, out, capacity, &n, outPointCount);
+        if (rc != AXCD_OK) return fail<std::uint32_t>(rc);
+        return core::Result<std::uint32_t>::success(n);
+    }
+    /// Scene queries on the LBVH of the last broadphase.  queryAABBs: (query, body) hits sorted by
+    /// (query, body); on OutOfRange the value needed is written to *required.
+    core::Result<std::uint32_t> queryAABBs(const math::AABB* boxes, std::uint32_t count, QueryHit* out,
+                                           std::uint32_t capacity, const std::uint32_t* queryWorld = nullptr,
+                                           std::uint32_t* required = nullptr) {
+        std::uint32_t n = 0;
+        const std::int32_t rc = axcd_query_aabbs(ctx_, reinterpret_cast<const float*>(boxes), queryWorld, count,
+                                                 reinterpret_cast<std::uint32_t*>(out), capacity, &n);
+        if (required) *required = n;
+        if (rc != AXCD_OK) return fail<std::uint32_t>(rc);
+        return core::Result<std::uint32_t>::success(n);
+    }
+    core::Result<void> rayCast(const Ray* rays, std::uint32_t count, RayHit* outHits) {
+        return wrap(axcd_raycast(ctx_, rays, count, outHits));
     }
     std::uint32_t bodyCount() const noexcept { return bodyCount_; }
 

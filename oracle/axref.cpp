@@ -906,6 +906,312 @@ PairOut collidePair(uint32_t ia, uint32_t ib, const Xf& ta, const AxrefShape& sa
     return o;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Stage 4: contact manifolds.  One manifold per contact, 1..4 points that share
+// the contact's normal; each point expands to a debug::DebugContactPoint (position, normal,
+// penetrationDepth; include/axiom/debug/physics_debug_draw.hpp:128-132) and the sum of the point
+// counts is gui::PhysicsWorldStats::contactPointCount (include/axiom/gui/physics_panel.hpp:21).
+// Box-box: feature clipping — reference face = the face of either box most aligned with the
+// contact normal (ties: body a), incident face = the other box's face most anti-parallel to it,
+// clipped (Sutherland-Hodgman) against the reference face's four side planes; vertices on or below
+// the reference face are kept (position = midpoint between the vertex and its projection onto the
+// reference face, depth = distance below the face) and reduced to at most four.  Every other class,
+// and a box-box contact whose clip comes out empty, keeps the single narrowphase point.
+// ------------------------------------------------------------------------------------------
+struct BoxFrame {
+    V3 c;          // centre relative to A's position
+    V3 ax[3];      // unit axes: the columns of Quat::toMatrix
+    float h[3];    // half lengths |halfExtent * scale|
+};
+BoxFrame makeBoxFrame(const Xf& t, const AxrefShape& sh, V3 origin) {
+    BoxFrame f;
+    M3 m = quatToMat3(t.q);
+    f.c = t.p - origin;
+    f.ax[0] = m.c0; f.ax[1] = m.c1; f.ax[2] = m.c2;
+    f.h[0] = std::fabs(sh.p0 * t.s.x);
+    f.h[1] = std::fabs(sh.p1 * t.s.y);
+    f.h[2] = std::fabs(sh.p2 * t.s.z);
+    return f;
+}
+inline int argmaxAbs3(const float d[3]) {   // lowest index on ties
+    int k = 0;
+    float best = std::fabs(d[0]);
+    if (std::fabs(d[1]) > best) { best = std::fabs(d[1]); k = 1; }
+    if (std::fabs(d[2]) > best) { k = 2; }
+    return k;
+}
+
+void buildManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, const Xf& tb,
+                   const AxrefShape& sb, AxrefManifold& m) {
+    m.a = c.a; m.b = c.b;
+    m.nx = c.nx; m.ny = c.ny; m.nz = c.nz;
+    m.count = 1;
+    for (int k = 0; k < 4; ++k) { m.px[k] = m.py[k] = m.pz[k] = 0.0f; m.depth[k] = 0.0f; }
+    m.px[0] = c.px; m.py[0] = c.py; m.pz[0] = c.pz;
+    m.depth[0] = c.depth;
+    if (sa.type != SHAPE_BOX || sb.type != SHAPE_BOX) return;
+    const V3 origin = ta.p;
+    const V3 n = mk(c.nx, c.ny, c.nz);
+    const BoxFrame A = makeBoxFrame(ta, sa, origin), B = makeBoxFrame(tb, sb, origin);
+    const float da[3] = {dot(n, A.ax[0]), dot(n, A.ax[1]), dot(n, A.ax[2])};
+    const float db[3] = {dot(n, B.ax[0]), dot(n, B.ax[1]), dot(n, B.ax[2])};
+    const int ia = argmaxAbs3(da), ib = argmaxAbs3(db);
+    const bool refIsA = std::fabs(da[ia]) >= std::fabs(db[ib]);
+    const BoxFrame& R = refIsA ? A : B;
+    const BoxFrame& I = refIsA ? B : A;
+    const int i = refIsA ? ia : ib;
+    // outward normal of the reference face, facing the other box (n points from a to b)
+    const float sgn = refIsA ? ((da[ia] >= 0.0f) ? 1.0f : -1.0f) : ((db[ib] >= 0.0f) ? -1.0f : 1.0f);
+    const V3 nr = R.ax[i] * sgn;
+    const float di[3] = {dot(nr, I.ax[0]), dot(nr, I.ax[1]), dot(nr, I.ax[2])};
+    const int j = argmaxAbs3(di);
+    const float sI = (di[j] >= 0.0f) ? -1.0f : 1.0f;
+    const int ju = (j + 1) % 3, jv = (j + 2) % 3;
+    const V3 fc = I.c + I.ax[j] * (sI * I.h[j]);
+    const V3 eu = I.ax[ju] * I.h[ju], ev = I.ax[jv] * I.h[jv];
+    V3 poly[8], tmp[8];
+    int np = 4;
+    poly[0] = (fc + eu) + ev;
+    poly[1] = (fc - eu) + ev;
+    poly[2] = (fc - eu) - ev;
+    poly[3] = (fc + eu) - ev;
+    // clip against the reference face's side planes: s * dot(p - cR, ax_w) <= h_w
+    for (int side = 0; side < 4 && np > 0; ++side) {
+        const int w = (i + 1 + (side >> 1)) % 3;
+        const float s = (side & 1) ? -1.0f : 1.0f;
+        const V3 pn = R.ax[w] * s;
+        const float hw = R.h[w];
+        int nt = 0;
+        V3 prev = poly[np - 1];
+        float dprev = dot(prev - R.c, pn) - hw;
+        for (int k = 0; k < np; ++k) {
+            const V3 cur = poly[k];
+            const float dcur = dot(cur - R.c, pn) - hw;
+            const bool inPrev = dprev <= 0.0f, inCur = dcur <= 0.0f;
+            if (inPrev != inCur) {
+                const float t = dprev / (dprev - dcur);
+                tmp[nt++] = prev + (cur - prev) * t;
+            }
+            if (inCur) tmp[nt++] = cur;
+            prev = cur;
+            dprev = dcur;
+        }
+        np = nt;
+        for (int k = 0; k < np; ++k) poly[k] = tmp[k];
+    }
+    // keep the vertices on or below the reference face
+    V3 pos[8];
+    float dep[8];
+    int nk = 0;
+    for (int k = 0; k < np; ++k) {
+        const float sep = dot(poly[k] - R.c, nr) - R.h[i];
+        if (sep <= 0.0f) {
+            pos[nk] = poly[k] - nr * (sep * 0.5f);
+            dep[nk] = -sep;
+            ++nk;
+        }
+    }
+    if (nk == 0) return;   // degenerate clip: the narrowphase point stands
+    bool keep[8];
+    for (int k = 0; k < 8; ++k) keep[k] = k < nk;
+    if (nk > 4) {
+        // reduction: deepest, farthest from it, largest triangle, then the vertex farthest outside it
+        for (int k = 0; k < nk; ++k) keep[k] = false;
+        int p0 = 0;
+        for (int k = 1; k < nk; ++k)
+            if (dep[k] > dep[p0]) p0 = k;
+        int p1 = -1;
+        float best = -1.0f;
+        for (int k = 0; k < nk; ++k) {
+            if (k == p0) continue;
+            const V3 d = pos[k] - pos[p0];
+            const float dd = dot(d, d);
+            if (dd > best) { best = dd; p1 = k; }
+        }
+        const V3 e = pos[p1] - pos[p0];
+        float area[8];
+        for (int k = 0; k < nk; ++k) area[k] = dot(cross(e, pos[k] - pos[p0]), nr);
+        int p2 = -1;
+        best = 0.0f;
+        for (int k = 0; k < nk; ++k) {
+            if (k == p0 || k == p1) continue;
+            if (std::fabs(area[k]) > best) { best = std::fabs(area[k]); p2 = k; }
+        }
+        keep[p0] = keep[p1] = true;
+        if (p2 >= 0) {
+            keep[p2] = true;
+            // fourth point: the vertex farthest outside the triangle (p0,p1,p2), measured as the
+            // largest parallelogram area beyond one of its three edges
+            const float flip = (area[p2] >= 0.0f) ? -1.0f : 1.0f;
+            const V3 e12 = pos[p2] - pos[p1], e20 = pos[p0] - pos[p2];
+            int p3 = -1;
+            best = 0.0f;
+            for (int k = 0; k < nk; ++k) {
+                if (k == p0 || k == p1 || k == p2) continue;
+                const float o01 = area[k] * flip;
+                const float o12 = dot(cross(e12, pos[k] - pos[p1]), nr) * flip;
+                const float o20 = dot(cross(e20, pos[k] - pos[p2]), nr) * flip;
+                float v = o01;
+                if (o12 > v) v = o12;
+                if (o20 > v) v = o20;
+                if (v > best) { best = v; p3 = k; }
+            }
+            if (p3 >= 0) keep[p3] = true;
+        }
+    }
+    int cnt = 0;
+    for (int k = 0; k < nk; ++k) {
+        if (!keep[k]) continue;
+        const V3 w = pos[k] + origin;
+        m.px[cnt] = w.x; m.py[cnt] = w.y; m.pz[cnt] = w.z;
+        m.depth[cnt] = dep[k];
+        ++cnt;
+    }
+    m.count = (uint32_t)cnt;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Scene queries ("scene queries", CLAUDE.md:88).  The oracle answers by brute
+// force over all bodies; the CUDA path answers through the LBVH and must return the same sets / the
+// same closest body.
+//   AABB query: every body whose AABB meets the query box under AABB::intersects (closed intervals).
+//   Ray cast  : a body is hit iff the ray's slab test against its AABB passes within [0, tMax] AND the
+//               shape test (sphere / oriented box / capsule in closed form) reports t in [0, tMax]; hull
+//               bodies answer with their AABB (flag 1).  The reported t is max(shape t, AABB entry t);
+//               the closest hit is the minimum (t, body index).  Origin inside a shape: t = 0, normal 0.
+// ------------------------------------------------------------------------------------------
+inline bool raySlab(V3 o, V3 d, const float* lo, const float* hi, float tMax, float* tNear) {
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    float tn = 0.0f, tf = tMax;
+    for (int k = 0; k < 3; ++k) {
+        if (!(lo[k] <= hi[k])) return false;   // empty or NaN box
+        if (dd[k] == 0.0f) {
+            if (!(lo[k] <= oo[k] && oo[k] <= hi[k])) return false;
+            continue;
+        }
+        const float inv = 1.0f / dd[k];
+        const float t1 = (lo[k] - oo[k]) * inv, t2 = (hi[k] - oo[k]) * inv;
+        const float a = (t1 < t2) ? t1 : t2, b = (t1 < t2) ? t2 : t1;
+        if (a > tn) tn = a;
+        if (b < tf) tf = b;
+    }
+    if (!(tn <= tf)) return false;
+    *tNear = tn;
+    return true;
+}
+
+struct ShapeHit {
+    bool hit;
+    float t;
+    V3 n;
+};
+inline ShapeHit raySphere(V3 m /* origin - centre */, V3 d, float r, float tMax) {
+    ShapeHit h{false, 0.0f, mk(0, 0, 0)};
+    const float dd = dot(d, d), b = dot(m, d), cc = dot(m, m) - r * r;
+    if (cc <= 0.0f) {
+        h.hit = true;
+        return h;
+    }
+    const float disc = b * b - dd * cc;
+    if (!(disc >= 0.0f)) return h;
+    const float t = (-b - std::sqrt(disc)) / dd;
+    if (!(t >= 0.0f && t <= tMax)) return h;
+    h.hit = true;
+    h.t = t;
+    h.n = (m + d * t) * (1.0f / r);
+    return h;
+}
+ShapeHit rayShape(V3 o, V3 d, float tMax, const Xf& t, const AxrefShape& sh) {
+    ShapeHit h{false, 0.0f, mk(0, 0, 0)};
+    const V3 m = o - t.p;
+    if (sh.type == SHAPE_SPHERE) return raySphere(m, d, sh.p0, tMax);
+    if (sh.type == SHAPE_BOX) {
+        M3 mm = quatToMat3(t.q);
+        const V3 ax[3] = {mm.c0, mm.c1, mm.c2};
+        const float half[3] = {std::fabs(sh.p0 * t.s.x), std::fabs(sh.p1 * t.s.y), std::fabs(sh.p2 * t.s.z)};
+        float ol[3], dl[3];
+        bool inside = true;
+        for (int k = 0; k < 3; ++k) {
+            ol[k] = dot(m, ax[k]);
+            dl[k] = dot(d, ax[k]);
+            if (!(std::fabs(ol[k]) <= half[k])) inside = false;
+        }
+        if (inside) {
+            h.hit = true;
+            return h;
+        }
+        float tn = -3.0e38f, tf = 3.0e38f;
+        int axis = -1;
+        for (int k = 0; k < 3; ++k) {
+            if (dl[k] == 0.0f) {
+                if (!(std::fabs(ol[k]) <= half[k])) return h;
+                continue;
+            }
+            const float inv = 1.0f / dl[k];
+            const float t1 = (-half[k] - ol[k]) * inv, t2 = (half[k] - ol[k]) * inv;
+            const float a = (t1 < t2) ? t1 : t2, b = (t1 < t2) ? t2 : t1;
+            if (a > tn) { tn = a; axis = k; }
+            if (b < tf) tf = b;
+        }
+        if (!(tn <= tf) || !(tf >= 0.0f) || axis < 0) return h;
+        const float tt = (tn < 0.0f) ? 0.0f : tn;
+        if (!(tt <= tMax)) return h;
+        h.hit = true;
+        h.t = tt;
+        h.n = (dl[axis] > 0.0f) ? -ax[axis] : ax[axis];
+        return h;
+    }
+    if (sh.type == SHAPE_CAPSULE) {
+        // segment pa..pb = centre -+ column1 * (height/2 * scale.y), as the narrowphase core; radius unscaled
+        M3 mm = quatToMat3(t.q);
+        const V3 e = mm.c1 * ((sh.p1 * 0.5f) * t.s.y);
+        const float r = sh.p0;
+        const V3 oa = m + e;          // origin - pa   (pa = centre - e)
+        const V3 ob = m - e;          // origin - pb
+        const V3 ba = e * 2.0f;
+        const float baba = dot(ba, ba), baoa = dot(ba, oa);
+        // origin inside: distance to the segment <= r
+        {
+            float sgm = (baba > 0.0f) ? baoa / baba : 0.0f;
+            sgm = (sgm < 0.0f) ? 0.0f : ((sgm > 1.0f) ? 1.0f : sgm);
+            const V3 q = oa - ba * sgm;
+            if (dot(q, q) <= r * r) {
+                h.hit = true;
+                return h;
+            }
+        }
+        bool any = false;
+        float best = 0.0f;
+        V3 bn = mk(0, 0, 0);
+        const float dd = dot(d, d), bard = dot(ba, d), rdoa = dot(d, oa), oaoa = dot(oa, oa);
+        const float a = baba * dd - bard * bard;
+        if (a > 0.0f) {
+            const float b = baba * rdoa - baoa * bard;
+            const float c = (baba * oaoa - baoa * baoa) - (r * r) * baba;
+            const float disc = b * b - a * c;
+            if (disc >= 0.0f) {
+                const float tc = (-b - std::sqrt(disc)) / a;
+                const float y = baoa + tc * bard;
+                if (tc >= 0.0f && tc <= tMax && y > 0.0f && y < baba) {
+                    any = true;
+                    best = tc;
+                    bn = ((oa + d * tc) - ba * (y / baba)) * (1.0f / r);
+                }
+            }
+        }
+        const ShapeHit ha = raySphere(oa, d, r, tMax), hb = raySphere(ob, d, r, tMax);
+        if (ha.hit && (!any || ha.t < best)) { any = true; best = ha.t; bn = ha.n; }
+        if (hb.hit && (!any || hb.t < best)) { any = true; best = hb.t; bn = hb.n; }
+        h.hit = any;
+        h.t = best;
+        h.n = bn;
+        return h;
+    }
+    return h;   // hulls are answered at AABB level by the caller
+}
+
 }   // namespace
 
 // =============================================================================================
@@ -1159,5 +1465,82 @@ int32_t axref_collide_pair(const float xfA[10], const AxrefShape* sa, const floa
     if (outUsedEpa) *outUsedEpa = o.usedEpa ? 1u : 0u;
     return o.contact ? 1 : 0;
 }
+
+int32_t axref_manifolds(const float* xf, const AxrefShape* shapes, uint32_t n, const AxrefContact* contacts,
+                        uint64_t ncontacts, AxrefManifold* out, uint64_t* outPointCount, int nthreads) {
+    if (!out && ncontacts) return 202;
+    const int T = std::max(1, nthreads);
+    std::vector<uint64_t> pts((size_t)T, 0);
+    std::vector<int> err((size_t)T, 0);
+    parallelFor(ncontacts, nthreads, [&](int t, uint64_t lo, uint64_t hi) {
+        for (uint64_t k = lo; k < hi; ++k) {
+            const AxrefContact& c = contacts[k];
+            if (c.a >= n || c.b >= n) {
+                err[(size_t)t] = 601;
+                continue;
+            }
+            buildManifold(c, loadXf(xf + 10ull * c.a), shapes[c.a], loadXf(xf + 10ull * c.b), shapes[c.b], out[k]);
+            pts[(size_t)t] += out[k].count;
+        }
+    });
+    uint64_t tot = 0;
+    for (uint64_t p : pts) tot += p;
+    if (outPointCount) *outPointCount = tot;
+    for (int e : err)
+        if (e) return e;
+    return 0;
+}
+
+
+int32_t axref_query_aabbs(const float* aabb, uint32_t n, const uint32_t* worldId, const float* qboxes,
+                          const uint32_t* qworld, uint32_t nq, uint32_t* outHits, uint64_t cap, uint64_t* outCount) {
+    if (!outCount) return 202;
+    uint64_t cnt = 0;
+    for (uint32_t q = 0; q < nq; ++q) {
+        for (uint32_t i = 0; i < n; ++i) {
+            if (worldId && qworld && worldId[i] != qworld[q]) continue;
+            if (!intersects(qboxes + 6ull * q, aabb + 6ull * i)) continue;
+            if (cnt < cap) {
+                outHits[2 * cnt] = q;
+                outHits[2 * cnt + 1] = i;
+            }
+            ++cnt;
+        }
+    }
+    *outCount = cnt;
+    return cnt > cap ? 601 : 0;
+}
+
+int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* aabb, uint32_t n,
+                      const uint32_t* worldId, const AxrefRay* rays, uint32_t nq, AxrefRayHit* out, int nthreads) {
+    parallelFor(nq, nthreads, [&](int, uint64_t lo, uint64_t hi) {
+        for (uint64_t q = lo; q < hi; ++q) {
+            const AxrefRay& r = rays[q];
+            const V3 o = mk(r.ox, r.oy, r.oz), d = mk(r.dx, r.dy, r.dz);
+            AxrefRayHit best{0xffffffffu, r.tMax, 0.0f, 0.0f, 0.0f, 0u};
+            bool have = false;
+            for (uint32_t i = 0; i < n; ++i) {
+                if (worldId && worldId[i] != r.world) continue;
+                float tNear;
+                if (!raySlab(o, d, aabb + 6ull * i, aabb + 6ull * i + 3, r.tMax, &tNear)) continue;
+                ShapeHit h{true, tNear, mk(0, 0, 0)};
+                uint32_t flags = 1u;
+                if (shapes[i].type != SHAPE_CONVEX) {
+                    h = rayShape(o, d, r.tMax, loadXf(xf + 10ull * i), shapes[i]);
+                    flags = 0u;
+                    if (!h.hit) continue;
+                }
+                const float t = (h.t > tNear) ? h.t : tNear;
+                if (!have || t < best.t || (t == best.t && i < best.body)) {
+                    have = true;
+                    best = AxrefRayHit{i, t, h.n.x, h.n.y, h.n.z, flags};
+                }
+            }
+            out[q] = best;
+        }
+    });
+    return 0;
+}
+
 
 }   // extern "C"

@@ -66,6 +66,23 @@ int32_t axref_narrowphase(const float* xf, const AxrefShape* shapes, uint32_t n,
                           uint64_t cap, uint64_t* outCount, float* outDist,
                           AxrefNarrowStats* stats, int nthreads);
 
+/* stage 4: contact manifolds (1..4 points per contact; box-box face clipping, single point otherwise),
+ * one per contact in the given order.  == AxcdManifold.                                        */
+typedef struct AxrefManifold {
+    uint32_t a, b; float nx, ny, nz; uint32_t count; float px[4], py[4], pz[4], depth[4];
+} AxrefManifold;
+int32_t axref_manifolds(const float* xf, const AxrefShape* shapes, uint32_t n, const AxrefContact* contacts,
+                        uint64_t ncontacts, AxrefManifold* out, uint64_t* outPointCount, int nthreads);
+
+/* scene queries (brute force over all bodies).  AABB query: (query, body) hits in (query, body) order.
+ * Ray cast: closest hit per ray; body == 0xffffffff when nothing is hit.  == AxcdRay / AxcdRayHit. */
+typedef struct AxrefRay { float ox, oy, oz, dx, dy, dz, tMax; uint32_t world; } AxrefRay;
+typedef struct AxrefRayHit { uint32_t body; float t, nx, ny, nz; uint32_t flags; } AxrefRayHit;
+int32_t axref_query_aabbs(const float* aabb, uint32_t n, const uint32_t* worldId, const float* qboxes,
+                          const uint32_t* qworld, uint32_t nq, uint32_t* outHits, uint64_t cap, uint64_t* outCount);
+int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* aabb, uint32_t n,
+                      const uint32_t* worldId, const AxrefRay* rays, uint32_t nq, AxrefRayHit* out, int nthreads);
+
 /* one pair, for closed-form checks: returns 1 if contact. dist = core GJK distance minus radii
  * (<= 0 for contacts; exact only when cfg->wantDistances).                                    */
 int32_t axref_collide_pair(const float xfA[10], const AxrefShape* sa, const float xfB[10],

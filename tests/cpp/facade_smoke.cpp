@@ -41,6 +41,21 @@ int main() {
     if (got.isFailure() || got.value() != contacts) return 8;
     for (std::uint32_t k = 0; k < contacts; ++k)
         if (!(out[k].a < out[k].b) || !(out[k].depth >= 0.0f)) return 9;
-    std::printf("%u %u\n", pairs, contacts);
+    // the "next" rows through the same façade: manifolds and scene queries
+    if (world.buildManifolds().isFailure()) return 10;
+    std::vector<collision::ContactManifold> man(contacts ? contacts : 1);
+    std::uint32_t points = 0;
+    auto gm = world.getManifolds(man.data(), static_cast<std::uint32_t>(man.size()), &points);
+    if (gm.isFailure() || gm.value() != contacts || points < contacts) return 11;
+    auto st = world.stats();
+    if (st.isFailure() || st.value().contactPointCount != points) return 12;
+    math::AABB everything{{-1e9f, -1e9f, -1e9f}, {1e9f, 1e9f, 1e9f}};
+    std::vector<collision::QueryHit> hits(n);
+    auto qh = world.queryAABBs(&everything, 1, hits.data(), n);
+    if (qh.isFailure() || qh.value() != n) return 13;
+    collision::Ray ray{xf[0].position.x, xf[0].position.y, xf[0].position.z - 50.0f, 0.0f, 0.0f, 1.0f, 100.0f, 0};
+    collision::RayHit rh{};
+    if (world.rayCast(&ray, 1, &rh).isFailure() || rh.body == 0xffffffffu) return 14;
+    std::printf("%u %u %u\n", pairs, contacts, points);
     return 0;
 }

@@ -13,6 +13,15 @@ SHAPE_DT = np.dtype([("type", "<u4"), ("p0", "<f4"), ("p1", "<f4"), ("p2", "<f4"
 CONTACT_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),
                        ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("depth", "<f4"),
                        ("status", "<u4")])
+MANIFOLD_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                        ("count", "<u4"), ("px", "<f4", (4,)), ("py", "<f4", (4,)), ("pz", "<f4", (4,)),
+                        ("depth", "<f4", (4,))])
+assert MANIFOLD_DT.itemsize == 88
+RAY_DT = np.dtype([("ox", "<f4"), ("oy", "<f4"), ("oz", "<f4"), ("dx", "<f4"), ("dy", "<f4"), ("dz", "<f4"),
+                   ("tMax", "<f4"), ("world", "<u4")])
+RAYHIT_DT = np.dtype([("body", "<u4"), ("t", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                      ("flags", "<u4")])
+NO_HIT = 0xFFFFFFFF
 
 
 class NarrowCfg(C.Structure):
@@ -45,6 +54,9 @@ def lib():
         _LIB.axref_broadphase_grid_f.restype = C.c_int32
         _LIB.axref_narrowphase.restype = C.c_int32
         _LIB.axref_collide_pair.restype = C.c_int32
+        _LIB.axref_manifolds.restype = C.c_int32
+        _LIB.axref_query_aabbs.restype = C.c_int32
+        _LIB.axref_raycast.restype = C.c_int32
         _LIB.axref_aabb_intersects.restype = C.c_int
     return _LIB
 
@@ -152,6 +164,60 @@ def narrowphase(xf, shapes, pairs, hull=None, cfg=None, want_distances=False, nt
                                  _p(dist), C.byref(st), C.c_int(nthreads))
     assert rc == 0, rc
     return out[:cnt.value].copy(), (dist[:npairs] if dist is not None else None), st
+
+
+def manifolds(xf, shapes, contacts, nthreads=1):
+    """One manifold per contact (same order); returns (records, total contact-point count)."""
+    xf = f32(xf).reshape(-1, 10)
+    shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
+    contacts = np.ascontiguousarray(contacts, dtype=CONTACT_DT)
+    out = np.zeros(max(len(contacts), 1), MANIFOLD_DT)
+    tot = C.c_uint64(0)
+    rc = lib().axref_manifolds(_p(xf), _p(shapes), C.c_uint32(xf.shape[0]), _p(contacts),
+                               C.c_uint64(len(contacts)), _p(out), C.byref(tot), C.c_int(nthreads))
+    assert rc == 0, rc
+    return out[:len(contacts)].copy(), int(tot.value)
+
+
+def make_rays(origins, dirs, t_max, world=0):
+    origins, dirs = f32(origins).reshape(-1, 3), f32(dirs).reshape(-1, 3)
+    r = np.zeros(len(origins), RAY_DT)
+    r["ox"], r["oy"], r["oz"] = origins[:, 0], origins[:, 1], origins[:, 2]
+    r["dx"], r["dy"], r["dz"] = dirs[:, 0], dirs[:, 1], dirs[:, 2]
+    r["tMax"] = t_max
+    r["world"] = world
+    return r
+
+
+def query_aabbs(aabb, qboxes, world_id=None, qworld=None):
+    aabb = f32(aabb).reshape(-1, 6)
+    qboxes = f32(qboxes).reshape(-1, 6)
+    wid = np.ascontiguousarray(world_id, dtype=np.uint32) if world_id is not None else None
+    qw = np.ascontiguousarray(qworld, dtype=np.uint32) if qworld is not None else None
+    cap = 1 << 16
+    while True:
+        out = np.zeros((cap, 2), np.uint32)
+        cnt = C.c_uint64(0)
+        rc = lib().axref_query_aabbs(_p(aabb), C.c_uint32(len(aabb)), _p(wid), _p(qboxes), _p(qw),
+                                     C.c_uint32(len(qboxes)), _p(out), C.c_uint64(cap), C.byref(cnt))
+        if rc == 601:
+            cap = int(cnt.value)
+            continue
+        assert rc == 0, rc
+        return out[:cnt.value].copy()
+
+
+def raycast(xf, shapes, aabb, rays, world_id=None, nthreads=8):
+    xf = f32(xf).reshape(-1, 10)
+    shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
+    aabb = f32(aabb).reshape(-1, 6)
+    rays = np.ascontiguousarray(rays, dtype=RAY_DT)
+    wid = np.ascontiguousarray(world_id, dtype=np.uint32) if world_id is not None else None
+    out = np.zeros(max(1, len(rays)), RAYHIT_DT)
+    rc = lib().axref_raycast(_p(xf), _p(shapes), _p(aabb), C.c_uint32(len(xf)), _p(wid), _p(rays),
+                             C.c_uint32(len(rays)), _p(out), C.c_int(nthreads))
+    assert rc == 0, rc
+    return out[:len(rays)].copy()
 
 
 def collide_pair(xfa, sa, xfb, sb, hull=None, cfg=None, want_distances=True):

@@ -31,4 +31,6 @@ def test_facade_c0_counts():
     _build()
     r = subprocess.run([EXE], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.split() == ["2875", "1381"]   # C0 fixture: candidate pairs, contacts
+    out = r.stdout.split()
+    assert out[:2] == ["2875", "1381"]   # C0 fixture: candidate pairs, contacts
+    assert int(out[2]) >= 1381           # contact points over all manifolds

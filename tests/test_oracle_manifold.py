@@ -1,0 +1,198 @@
+"""Validates the oracle's contact-manifold stage independently of its own code:
+closed-form stacked boxes, an independent float64 numpy clipper (2-D rectangle clipping in the
+reference face's own coordinates instead of 3-D plane clipping), and geometric properties on a
+random scene.  The CUDA path is then compared with this oracle in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+
+def _contact(a, sa, b, sb):
+    hit, c, _, _ = O.collide_pair(a, sa, b, sb)
+    assert hit
+    c = c.copy()
+    c["a"], c["b"] = 0, 1
+    return c
+
+
+def _manifold(a, sa, b, sb):
+    c = _contact(a, sa, b, sb)
+    m, tot = O.manifolds(np.stack([a, b]), np.array([sa, sb], dtype=O.SHAPE_DT), np.array([c]))
+    assert tot == m[0]["count"]
+    return c, m[0]
+
+
+def _points(m):
+    k = int(m["count"])
+    return np.stack([m["px"][:k], m["py"][:k], m["pz"][:k]], axis=1).astype(np.float64), m["depth"][:k].astype(np.float64)
+
+
+def test_sphere_pairs_keep_the_single_point():
+    a, b = O.xf((0, 0, 0)), O.xf((0.9, 0, 0))
+    for sa, sb in ((O.sphere(0.5), O.sphere(0.5)), (O.sphere(0.5), O.box(0.5, 0.5, 0.5)),
+                   (O.box(0.5, 0.5, 0.5), O.sphere(0.5)), (O.capsule(0.45, 1.0), O.box(0.5, 0.5, 0.5))):
+        c, m = _manifold(a, sa, b, sb)
+        assert m["count"] == 1
+        assert (m["px"][0], m["py"][0], m["pz"][0], m["depth"][0]) == (c["px"], c["py"], c["pz"], c["depth"])
+        assert (m["nx"], m["ny"], m["nz"]) == (c["nx"], c["ny"], c["nz"])
+
+
+def test_stacked_boxes_give_the_overlap_rectangle():
+    # unit cube on a 2x2x1 slab, shifted so the overlap rectangle is [0.25,1]x[-0.5,0.5], 0.1 deep
+    a = O.xf((0, 0, 0))
+    b = O.xf((0.75, 0, 0.9))
+    c, m = _manifold(a, O.box(1.0, 1.0, 0.5), b, O.box(0.5, 0.5, 0.5))
+    np.testing.assert_allclose([c["nx"], c["ny"], c["nz"]], [0, 0, 1], atol=1e-5)
+    p, d = _points(m)
+    assert m["count"] == 4
+    np.testing.assert_allclose(d, 0.1, atol=1e-5)
+    np.testing.assert_allclose(p[:, 2], 0.45, atol=1e-5)   # midway between z=0.4 (B's bottom) and z=0.5 (A's top)
+    got = sorted((round(x, 4), round(y, 4)) for x, y in p[:, :2])
+    assert got == [(0.25, -0.5), (0.25, 0.5), (1.0, -0.5), (1.0, 0.5)]
+
+
+def test_yawed_stack_is_reduced_to_four_points_of_the_octagon():
+    a = O.xf((0, 0, 0))
+    b = O.xf((0, 0, 0.95), O.axis_angle((0, 0, 1), np.pi / 4))
+    c, m = _manifold(a, O.box(0.5, 0.5, 0.5), b, O.box(0.5, 0.5, 0.5))
+    p, d = _points(m)
+    assert m["count"] == 4
+    np.testing.assert_allclose(d, 0.05, atol=1e-5)
+    # every point is a vertex of the octagon: on the boundary of both squares' intersection
+    r = np.sqrt(0.5) * 0.5
+    for x, y in p[:, :2]:
+        on_a = np.isclose(max(abs(x), abs(y)), 0.5, atol=1e-5)
+        on_b = np.isclose((abs(x) + abs(y)) * np.sqrt(0.5), 0.5, atol=1e-5)
+        assert on_a and on_b, (x, y, r)
+    # spread: the four points span the patch (area of their hull well above a sliver)
+    q = p[:, :2] - p[:, :2].mean(axis=0)
+    assert np.linalg.matrix_rank(q, tol=1e-3) == 2
+
+
+# ---- independent float64 restatement: clip in the reference face's 2-D coordinates ------------------
+def _rot(q):
+    x, y, z, w = [float(v) for v in q]
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _clip2d(poly, lo, hi):
+    """Sutherland-Hodgman of a 2-D polygon against the rectangle [lo, hi] (float64)."""
+    for axis in (0, 1):
+        for sign, bound in ((1.0, hi[axis]), (-1.0, -lo[axis])):
+            out = []
+            for k in range(len(poly)):
+                p, q = poly[k - 1], poly[k]
+                dp, dq = sign * p[axis] - bound, sign * q[axis] - bound
+                if (dp <= 0) != (dq <= 0):
+                    out.append(p + (q - p) * (dp / (dp - dq)))
+                if dq <= 0:
+                    out.append(q)
+            poly = out
+            if not poly:
+                return poly
+    return poly
+
+
+def _numpy_candidates(c, xa, sa, xb, sb):
+    """All clipped vertices at or below the reference face (before reduction): (positions, depths)."""
+    n = np.array([c["nx"], c["ny"], c["nz"]], dtype=np.float64)
+    fr = []
+    for x, s in ((xa, sa), (xb, sb)):
+        x = x.astype(np.float64)
+        fr.append((x[:3], _rot(x[3:7]), np.abs(np.array(s[1:4], dtype=np.float64) * x[7:10])))
+    al = [np.abs(n @ f[1]) for f in fr]
+    ref_is_a = al[0].max() >= al[1].max()
+    (cr, Rr, hr), (ci, Ri, hi_) = (fr[0], fr[1]) if ref_is_a else (fr[1], fr[0])
+    ndir = n if ref_is_a else -n
+    i = int(np.argmax(np.abs(ndir @ Rr)))
+    nr = Rr[:, i] * np.sign(ndir @ Rr[:, i])
+    j = int(np.argmax(np.abs(nr @ Ri)))
+    fcen = ci - Ri[:, j] * np.sign(nr @ Ri[:, j]) * hi_[j]
+    u, v = (j + 1) % 3, (j + 2) % 3
+    quad = [fcen + su * Ri[:, u] * hi_[u] + sv * Ri[:, v] * hi_[v] for su, sv in ((1, 1), (-1, 1), (-1, -1), (1, -1))]
+    wu, wv = (i + 1) % 3, (i + 2) % 3
+    # coordinates (s, t, height) in the reference box's frame
+    loc = [np.array([(p - cr) @ Rr[:, wu], (p - cr) @ Rr[:, wv], (p - cr) @ nr]) for p in quad]
+    out = _clip2d(loc, np.array([-hr[wu], -hr[wv]]), np.array([hr[wu], hr[wv]]))
+    pos, dep = [], []
+    for q in out:
+        sep = q[2] - hr[i]
+        if sep <= 0:
+            w = cr + Rr[:, wu] * q[0] + Rr[:, wv] * q[1] + nr * (q[2] - 0.5 * sep)
+            pos.append(w)
+            dep.append(-sep)
+    return np.array(pos).reshape(-1, 3), np.array(dep)
+
+
+def _box_sdist(p, x, s):
+    """Signed-ish distance of world point p to the box (<= 0 inside), float64."""
+    x = x.astype(np.float64)
+    loc = (p - x[:3]) @ _rot(x[3:7])
+    h = np.abs(np.array(s[1:4], dtype=np.float64) * x[7:10])
+    q = np.abs(loc) - h
+    return np.linalg.norm(np.maximum(q, 0.0)) + min(q.max(), 0.0)
+
+
+def test_random_box_pairs_against_the_numpy_clipper():
+    rng = np.random.default_rng(7)
+    multi = reduced = 0
+    for _ in range(600):
+        qa = rng.normal(size=4); qa /= np.linalg.norm(qa)
+        qb = rng.normal(size=4); qb /= np.linalg.norm(qb)
+        if rng.random() < 0.4:   # near-parallel faces: the interesting manifolds
+            qb = qa.copy()
+            if rng.random() < 0.5:
+                qb = qb + rng.normal(size=4) * 0.02
+                qb /= np.linalg.norm(qb)
+        sa = O.box(*rng.uniform(0.25, 0.6, 3))
+        sb = O.box(*rng.uniform(0.25, 0.6, 3))
+        xa = O.xf(rng.uniform(-1, 1, 3), qa, rng.uniform(0.8, 1.3, 3))
+        xb = O.xf(xa[:3] + rng.uniform(-0.6, 0.6, 3), qb)
+        hit, c, _, _ = O.collide_pair(xa, sa, xb, sb)
+        if not hit:
+            continue
+        c = c.copy(); c["a"], c["b"] = 0, 1
+        m, _ = O.manifolds(np.stack([xa, xb]), np.array([sa, sb], dtype=O.SHAPE_DT), np.array([c]))
+        p, d = _points(m[0])
+        cand_p, cand_d = _numpy_candidates(c, xa, sa, xb, sb)
+        if len(cand_p) == 0:
+            assert m[0]["count"] == 1
+            continue
+        # every reported point is one of the independently clipped vertices, with its depth
+        assert 1 <= len(p) <= min(4, len(cand_p))
+        for pk, dk in zip(p, d):
+            e = np.linalg.norm(cand_p - pk, axis=1)
+            k = int(np.argmin(e))
+            assert e[k] < 2e-4, (pk, cand_p)
+            assert abs(cand_d[k] - dk) < 2e-4
+        if len(cand_p) <= 4:
+            assert len(p) == len(cand_p)
+        else:
+            reduced += 1
+            assert len(p) == 4
+            assert abs(d.max() - cand_d.max()) < 2e-4   # the deepest vertex survives the reduction
+        multi += len(p) > 1
+        # geometry: each point lies within half its depth of both boxes
+        for pk, dk in zip(p, d):
+            assert _box_sdist(pk, xa, sa) <= 0.5 * dk + 2e-4
+            assert _box_sdist(pk, xb, sb) <= 0.5 * dk + 2e-4
+    assert multi > 100 and reduced > 10, (multi, reduced)
+
+
+def test_scene_totals_and_determinism():
+    import axcd
+    s = axcd.config_scene("C0")
+    rc, bb = O.refit(s.xf, s.shapes, s.hull)
+    pairs = O.broadphase(bb, brute=True)
+    con, _, _ = O.narrowphase(s.xf, s.shapes, pairs, s.hull)
+    m1, t1 = O.manifolds(s.xf, s.shapes, con)
+    m2, t2 = O.manifolds(s.xf, s.shapes, con, nthreads=4)
+    assert m1.tobytes() == m2.tobytes() and t1 == t2 == int(m1["count"].sum())
+    assert np.array_equal(m1["a"], con["a"]) and np.array_equal(m1["b"], con["b"])
+    bb_mask = (s.shapes["type"][con["a"]] == 1) & (s.shapes["type"][con["b"]] == 1)
+    assert (m1["count"][~bb_mask] == 1).all()
+    assert (m1["count"] >= 1).all() and (m1["count"] <= 4).all()
+    assert (m1["count"][bb_mask] > 1).any()

@@ -1,0 +1,210 @@
+"""GPU parity tests for the SURVEY 8(f) "next" rows built on top of the hot path: contact manifolds
+(rank 2) and scene queries on the LBVH (rank 4).  Same bar as tests/test_gpu_parity.py: index
+results bit-exact against the CPU oracle, floats within REL = 1e-4 relative (and, because both sides
+evaluate the same expression trees without contraction, additionally asserted bit-identical)."""
+import numpy as np
+import pytest
+
+import axcd
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def _bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.tobytes() == b.tobytes()
+
+
+def _manifold_parity(s, **kw):
+    w = axcd.CollisionWorld.for_scene(s, **kw)
+    st = w.step()
+    assert w.stats().contactPointCount == 0          # nothing built yet
+    w.build_manifolds()
+    gm, pts = w.manifolds()
+    gc = w.contacts()
+    assert len(gm) == st.numContacts == len(gc)
+    om, opts = O.manifolds(s.xf, s.shapes, gc, nthreads=8)
+    assert np.array_equal(gm["a"], om["a"]) and np.array_equal(gm["b"], om["b"])
+    assert np.array_equal(gm["count"], om["count"])                      # integer results: bit-exact
+    assert pts == opts == int(gm["count"].sum()) == w.stats().contactPointCount
+    for f in ("nx", "ny", "nz"):
+        assert _bits_equal(gm[f], om[f])
+    for f in ("px", "py", "pz", "depth"):
+        np.testing.assert_allclose(gm[f], om[f], rtol=REL, atol=REL * 1e-2)
+    bitwise = all(_bits_equal(gm[f], om[f]) for f in ("px", "py", "pz", "depth"))
+    w.close()
+    return gm, bitwise
+
+
+def test_manifolds_c0_bit_exact():
+    gm, bitwise = _manifold_parity(axcd.config_scene("C0"))
+    assert bitwise
+    assert (gm["count"] > 1).any() and (gm["count"] <= 4).all()
+
+
+def _dense_boxes(n=20000, seed=5, L=22.0):
+    rng = np.random.default_rng(seed)
+    s = axcd.generate_scene(n, seed, L, frac_box=1.0, frac_sphere=0.0)
+    # many near-parallel faces (the multi-point manifolds): snap two thirds of the rotations to a
+    # common frame, half of those with a small perturbation; non-unit scales
+    k = rng.random(n)
+    base = np.array([0.0, 0.0, 0.0, 1.0], np.float32)
+    q = s.xf[:, 3:7].copy()
+    q[k < 0.33] = base
+    m = (k >= 0.33) & (k < 0.66)
+    qq = base + rng.normal(size=(int(m.sum()), 4)).astype(np.float32) * 0.03
+    q[m] = qq / np.linalg.norm(qq, axis=1, keepdims=True)
+    s.xf[:, 3:7] = q.astype(np.float32)
+    s.xf[:, 7:10] = rng.uniform(0.7, 1.5, (n, 3)).astype(np.float32)
+    return s
+
+
+def test_manifolds_dense_near_parallel_boxes():
+    gm, bitwise = _manifold_parity(_dense_boxes(), pairs_per_body=32)
+    assert bitwise
+    hist = np.bincount(gm["count"], minlength=5)
+    assert hist[4] > 500 and hist[2] > 50 and hist[1] > 0, hist
+
+
+def test_manifolds_mixed_shapes_and_call_order():
+    s = axcd.config_scene("C2", scale=0.02)       # boxes / spheres / hulls
+    gm, bitwise = _manifold_parity(s)
+    assert bitwise
+    w = axcd.CollisionWorld.for_scene(s)
+    with pytest.raises(axcd.AxcdError) as e:
+        w.build_manifolds()                       # no narrowphase yet
+    assert e.value.code == 503
+    w.step()
+    w.build_manifolds()
+    with pytest.raises(axcd.AxcdError) as e:
+        w.build_manifolds()                       # once per narrowphase
+    assert e.value.code == 503
+    w.step()
+    with pytest.raises(axcd.AxcdError) as e:
+        w.manifolds()                             # stale after a new step
+    assert e.value.code == 503
+    w.close()
+
+
+def test_manifolds_headline_full_size():
+    gm, bitwise = _manifold_parity(axcd.config_scene("headline"))
+    assert bitwise
+    assert len(gm) == 1_538_646
+
+
+# ------------------------------------------------------------------ scene queries ---------------
+def _query_scene(n=20000, seed=12, L=27.0):
+    rng = np.random.default_rng(seed)
+    s = axcd.generate_scene(n, seed, L, frac_box=0.4, frac_sphere=0.4)      # 20 % hulls
+    k = np.where(s.shapes["type"] == 0)[0][::2]
+    s.shapes["type"][k] = 2                                                  # capsules
+    s.shapes["p0"][k] = rng.uniform(0.15, 0.3, len(k)).astype(np.float32)
+    s.shapes["p1"][k] = rng.uniform(0.3, 0.9, len(k)).astype(np.float32)
+    s.xf[:, 7:10] = rng.uniform(0.7, 1.4, (n, 3)).astype(np.float32)
+    return s, L
+
+
+def test_query_aabbs_matches_oracle():
+    s, L = _query_scene()
+    w = axcd.CollisionWorld.for_scene(s)
+    w.update()
+    bb = w.aabbs()
+    rng = np.random.default_rng(1)
+    nq = 3000
+    c = rng.uniform(-1, L + 1, (nq, 3))
+    h = rng.uniform(0.01, 2.0, (nq, 3)) ** 2
+    q = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    q[0] = bb[17]                                  # identical box
+    q[1, :3], q[1, 3:] = bb[23, 3:], bb[23, 3:] + 0.5   # touching at one corner: closed intervals
+    q[2] = (-1e9, -1e9, -1e9, 1e9, 1e9, 1e9)       # everything
+    q[3] = (5, 5, 5, 4, 6, 6)                      # inverted: nothing
+    q[4] = (np.nan, 0, 0, 1, 1, 1)                 # NaN: nothing
+    got = w.query_aabbs(q)
+    exp = O.query_aabbs(bb, q)
+    assert np.array_equal(got, exp)
+    assert (got[:, 0] == 2).sum() == s.n and not (got[:, 0] == 3).any() and not (got[:, 0] == 4).any()
+    assert ((got[:, 0] == 1) & (got[:, 1] == 23)).any()
+    w.close()
+
+
+def test_raycast_matches_oracle():
+    s, L = _query_scene()
+    w = axcd.CollisionWorld.for_scene(s)
+    w.update()
+    bb = w.aabbs()
+    rng = np.random.default_rng(4)
+    nq = 4000
+    o = rng.uniform(-2, L + 2, (nq, 3))
+    d = rng.normal(size=(nq, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:300] *= rng.uniform(0.2, 3.0, (300, 1))     # non-unit directions
+    d[300] = (1, 0, 0)                              # zero components
+    d[301] = (0, 0, -1)
+    d[302] = (0, 0, 0)                              # degenerate ray: only "origin inside" hits
+    o[303:400] = s.xf[1000:1097, :3]                # origins inside shapes: t = 0
+    rays = O.make_rays(o, d, rng.uniform(3.0, 40.0, nq).astype(np.float32))
+    got = w.raycast(rays)
+    exp = O.raycast(s.xf, s.shapes, bb, rays)
+    assert np.array_equal(got["body"], exp["body"])                       # bit-exact closest body
+    assert np.array_equal(got["flags"], exp["flags"])
+    for f in ("t", "nx", "ny", "nz"):
+        np.testing.assert_allclose(got[f], exp[f], rtol=REL, atol=REL * 1e-2)
+    assert all(_bits_equal(got[f], exp[f]) for f in ("t", "nx", "ny", "nz"))
+    hit = got["body"] != axcd.NO_HIT
+    assert 0.2 < hit.mean() < 1.0
+    assert (got["t"][303:400] == 0).sum() > 80
+    kinds = set(np.unique(s.shapes["type"][got["body"][hit]]))
+    assert kinds == {0, 1, 2, 4}
+    w.close()
+
+
+def test_queries_in_batched_worlds():
+    s = axcd.config_scene("C3", scale=64 / 4096)       # 64 worlds x 256 bodies, all in the same cube
+    w = axcd.CollisionWorld.for_scene(s)
+    w.update()
+    bb = w.aabbs()
+    rng = np.random.default_rng(8)
+    nq = 1000
+    c = rng.uniform(0, 6.35, (nq, 3))
+    h = rng.uniform(0.1, 1.5, (nq, 3))
+    q = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    qw = rng.integers(0, 64, nq).astype(np.uint32)
+    qw[:5] = 63
+    qw[5:10] = 0
+    got = w.query_aabbs(q, qw)
+    exp = O.query_aabbs(bb, q, s.world_id, qw)
+    assert np.array_equal(got, exp)
+    assert (s.world_id[got[:, 1]] == qw[got[:, 0]]).all()
+    assert np.array_equal(w.query_aabbs(q), O.query_aabbs(bb, q))      # NULL world = all worlds
+    o = rng.uniform(-1, 7, (nq, 3))
+    d = rng.normal(size=(nq, 3))
+    rays = O.make_rays(o, d, 20.0)
+    rays["world"] = qw
+    gr = w.raycast(rays)
+    er = O.raycast(s.xf, s.shapes, bb, rays, world_id=s.world_id)
+    assert np.array_equal(gr["body"], er["body"])
+    assert all(_bits_equal(gr[f], er[f]) for f in ("t", "nx", "ny", "nz", "flags"))
+    hit = gr["body"] != axcd.NO_HIT
+    assert hit.any() and (s.world_id[gr["body"][hit]] == qw[hit]).all()
+    w.close()
+
+
+def test_queries_tiny_scenes_and_errors():
+    for n in (1, 2, 3):
+        s = axcd.generate_scene(n, 3, 1.5)
+        w = axcd.CollisionWorld.for_scene(s)
+        with pytest.raises(axcd.AxcdError) as e:
+            w.raycast(O.make_rays([[0, 0, 0]], [[1, 0, 0]], 1.0))    # no broadphase yet
+        assert e.value.code == 503
+        w.update()
+        bb = w.aabbs()
+        q = np.array([[-5, -5, -5, 5, 5, 5], [10, 10, 10, 11, 11, 11]], np.float32)
+        assert np.array_equal(w.query_aabbs(q), O.query_aabbs(bb, q))
+        rays = O.make_rays(s.xf[:, :3] - [0, 0, 4], [[0, 0, 1]] * n, 10.0)
+        gr, er = w.raycast(rays), O.raycast(s.xf, s.shapes, bb, rays)
+        assert gr.tobytes() == er.tobytes()
+        assert (gr["body"] != axcd.NO_HIT).all()
+        assert len(w.query_aabbs(np.zeros((0, 6), np.float32))) == 0
+        w.close()

@@ -50,8 +50,8 @@ def g(k, key):
         return str(data[k].get(key))
 
 
-ncu_tbl = ["| kernel | us | regs | warps active % | issue active % | thread/inst | DRAM rd+wr MB | DRAM % of peak | L2 hit % | top stalls (per issue) |",
-           "|---|---|---|---|---|---|---|---|---|---|"]
+ncu_tbl = ["| kernel | us | regs | warps active % | issue active % | FP32 (fma) pipe % | thread/inst | DRAM rd+wr MB | DRAM % of peak | L2 hit % | top stalls (per issue) |",
+           "|---|---|---|---|---|---|---|---|---|---|---|"]
 for k in data:
     st = {s.split('_stalled_')[1].split('_per_issue')[0]: float(v) for s, v in data[k].items() if '_stalled_' in s and v != 'n/a'}
     top = sorted(st.items(), key=lambda x: -x[1])[:3]
@@ -59,6 +59,7 @@ for k in data:
     rd, wr = float(data[k]['dram__bytes_read.sum']), float(data[k]['dram__bytes_write.sum'])
     ncu_tbl.append(f"| {k} | {t if t > 5 else t * 1000:.1f} | {data[k]['launch__registers_per_thread']} | "
                    f"{g(k, 'sm__warps_active.avg.pct_of_peak_sustained_active')} | {g(k, 'smsp__issue_active.avg.pct_of_peak_sustained_active')} | "
+                   f"{g(k, 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active')} | "
                    f"{g(k, 'smsp__thread_inst_executed_per_inst_executed.ratio')} | {rd + wr:.1f} | "
                    f"{g(k, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} | {g(k, 'lts__t_sector_hit_rate.pct')} | "
                    f"{', '.join(f'{a} {b:.1f}' for a, b in top)} |")

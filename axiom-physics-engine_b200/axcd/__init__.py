@@ -20,6 +20,7 @@ SCENE_LIB_PATH = os.path.join(PKG_DIR, "libaxcd_scene.so")
 SHAPE_SPHERE, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_PLANE, SHAPE_CONVEX, SHAPE_MESH = range(6)
 FLAG_PAIR_DISTANCES = 1
 FLAG_EPA_COOPERATIVE = 2
+FLAG_TEMPORAL_COHERENCE = 4
 
 SHAPE_DT = np.dtype([("type", "<u4"), ("p0", "<f4"), ("p1", "<f4"), ("p2", "<f4")])
 CONTACT_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),
@@ -40,7 +41,7 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
-    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast",
+    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake",
     "axcd_set_filters", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
     "axcd_set_ghosts_device",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
@@ -66,7 +67,8 @@ class Stats(C.Structure):
                 ("gjkMs", C.c_float), ("epaMs", C.c_float), ("totalMs", C.c_float),
                 ("broadphaseTime", C.c_float), ("narrowphaseTime", C.c_float),
                 ("bytesMoved", C.c_uint64), ("kernelLaunches", C.c_uint32),
-                ("contactPointCount", C.c_uint32)]
+                ("contactPointCount", C.c_uint32),
+                ("movedBodies", C.c_uint32), ("broadphaseSkipped", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -110,7 +112,7 @@ def load_library():
                      "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
                      "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
                      "axcd_pack_ghosts", "axcd_set_ghosts_device", "axcd_set_filters",
-                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast"):
+                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -127,6 +129,7 @@ def load_library():
         lib.axcd_get_manifolds.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.axcd_query_aabbs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                          C.c_void_p]
+        lib.axcd_set_awake.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         lib.axcd_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.axcd_test_sort_pairs32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                C.c_uint32]
@@ -433,6 +436,14 @@ class CollisionWorld:
         out = np.zeros(max(1, len(rays)), RAYHIT_DT)
         self._check(self._lib.axcd_raycast(self._ctx, _ptr(rays), len(rays), _ptr(out)), "axcd_raycast")
         return out[:len(rays)]
+
+    def set_awake(self, awake):
+        """awake: (n,) array, 0 = sleeping; None switches the rule off.  Sleeping-sleeping pairs are dropped."""
+        if awake is None:
+            self._check(self._lib.axcd_set_awake(self._ctx, None, 0), "axcd_set_awake")
+            return
+        a = np.ascontiguousarray(np.asarray(awake) != 0, dtype=np.uint8)
+        self._check(self._lib.axcd_set_awake(self._ctx, _ptr(a), len(a)), "axcd_set_awake")
 
     def set_filters(self, filters):
         """filters: (n,3) array of (categoryBits, maskBits, groupIndex) or None to switch filtering off."""

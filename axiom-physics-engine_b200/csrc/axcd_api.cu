@@ -83,6 +83,13 @@ struct AxcdContext {
     AxcdContact* dContacts = nullptr;
     AxcdManifold* dManifolds = nullptr;   // allocated by the first axcd_build_manifolds
     bool manifoldsValid = false;          // built for the current narrowphase result
+    uint8_t* dAwake = nullptr;            // per body: 0 = sleeping (NULL semantics when !awakeOn)
+    bool awakeOn = false;
+    bool fatValid = false;                // coherent mode: dAabb holds fat boxes of the current shapes
+    bool pairsCached = false;             // coherent mode: dPairs / cachedPairs describe the current fat boxes
+    uint32_t cachedFound = 0;             // pair count of the cached broadphase (as found, may exceed capacity)
+    bool broadSkipped = false;            // the last axcd_broadphase reused the cached pairs
+    uint32_t movedLast = 0;
     int sortedBuf = 0;                    // which of dKeys/dVals holds the sorted order of the last broadphase
     // scene-query scratch (grow-only)
     void* dQIn = nullptr;      size_t qInBytes = 0;      // query boxes / rays (+ worlds)
@@ -150,6 +157,8 @@ uint32_t sortTilesFor(uint64_t n) { return (uint32_t)((n + kSortTile - 1) / kSor
 // Morton resolution.
 int resizeBodies(AxcdContext* ctx, uint32_t n) {
     ctx->n = n;
+    ctx->fatValid = false;      // a different body set: no fat box or cached pair list carries over
+    ctx->pairsCached = false;
     uint32_t P = 1;
     while (P < n) P <<= 1;
     ctx->segP = P;
@@ -237,7 +246,7 @@ void axcd_destroy(AxcdContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dType8, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
+    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dType8, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dAwake, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dManifolds, ctx->dQIn, ctx->dQCount, ctx->dQSeg, ctx->dQOut, ctx->dPairDist, ctx->dSortHist,
@@ -396,6 +405,8 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
         const int rc = resizeBodies(ctx, n);
         if (rc) return rc;
     }
+    ctx->fatValid = false;      // new bodies: every fat box is rebuilt by the next refit
+    ctx->pairsCached = false;
     ctx->stage = ST_SHAPES;
     return AXCD_OK;
 }
@@ -427,9 +438,17 @@ int32_t axcd_refit(AxcdContext* ctx) {
     CU(cudaMemcpyAsync(ctx->dCtr, ctx->dCtrInit, sizeof(Counters), cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->n) {
         const uint32_t blocks = (ctx->n + kRefitThreads - 1) / kRefitThreads;
-        refitKernel<<<blocks, kRefitThreads, 0, ctx->stream>>>(
-            reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
-            reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin, ctx->dCtr);
+        if (ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE) {
+            refitKernel<true><<<blocks, kRefitThreads, 0, ctx->stream>>>(
+                reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
+                reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin,
+                ctx->fatValid ? 0u : 1u, ctx->dCtr);
+            ctx->fatValid = true;
+        } else {
+            refitKernel<false><<<blocks, kRefitThreads, 0, ctx->stream>>>(
+                reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
+                reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin, 0u, ctx->dCtr);
+        }
         CU(cudaGetLastError());
     }
     ctx->launches[0] = ctx->n ? 1 : 0;
@@ -447,6 +466,23 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
     cudaStream_t st = ctx->stream;
     ctx->numPairs = ctx->foundPairs = 0;
     ctx->launches[1] = 0;
+    ctx->broadSkipped = false;
+    if ((ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE) && n >= 2) {
+        // Temporal coherence: the candidate set is a function of the fat boxes only.  If no body left
+        // its fat box since the cached broadphase, the cached canonical pair list is still exact.
+        uint32_t moved = 0;
+        CU(cudaMemcpyAsync(&moved, &ctx->dCtr->movedBodies, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->movedLast = moved;
+        if (moved == 0 && ctx->pairsCached) {
+            // the per-step counter reset cleared the device-side pair count: restore it
+            CU(cudaMemcpyAsync(&ctx->dCtr->pairCount, &ctx->cachedFound, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            for (int e : {EV_SORT, EV_BUILD, EV_PAIR, EV_PAIRSORT, EV_BROAD_END}) recordEv(ctx, e);
+            ctx->broadSkipped = true;
+            ctx->stage = ST_BROAD;
+            return AXCD_OK;
+        }
+    }
     if (n >= 2) {
         // ---- Morton keys + radix sort ----------------------------------------------------------
         const uint32_t blocks = (n + kRefitThreads - 1) / kRefitThreads;
@@ -499,7 +535,8 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
                                                      ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
                                                      ctx->cfg.maxPairs, ctx->dBodyCount,
                                                      SlabRule{ctx->slabOn ? 1 : 0, ctx->slabLo, ctx->slabHi, ctx->dBodyKeys},
-                                                     ctx->filtersOn ? ctx->dFilters : nullptr, ctx->dCtr);
+                                                     ctx->filtersOn ? ctx->dFilters : nullptr,
+                                                     ctx->awakeOn ? ctx->dAwake : nullptr, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIR);
         // ---- canonical order: counting sort by body a, then tiny per-body sorts by b ------------------
@@ -526,6 +563,12 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
     }
     recordEv(ctx, EV_BROAD_END);
     ctx->stage = ST_BROAD;
+    if (ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE) {
+        // remember the pair count of this broadphase for the steps that can reuse it
+        CU(cudaMemcpyAsync(&ctx->cachedFound, &ctx->dCtr->pairCount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->pairsCached = true;
+    }
     return AXCD_OK;
 }
 
@@ -600,6 +643,8 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
         if (rc) return rc;
     }
     out->numBodies = ctx->n;
+    out->movedBodies = (ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE) ? ctx->hostCtr.movedBodies : ctx->n;
+    out->broadphaseSkipped = (ctx->stage >= ST_BROAD && ctx->broadSkipped) ? 1u : 0u;
     if (ctx->stage >= ST_BROAD) {
         out->numPairs = ctx->numPairs;
         out->requiredPairs = ctx->foundPairs;
@@ -846,10 +891,30 @@ int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRay
     return AXCD_OK;
 }
 
+int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t n) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    ctx->pairsCached = false;   // the candidate rule changed
+    if (!awake) {
+        ctx->awakeOn = false;
+        return AXCD_OK;
+    }
+    if (n > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (!ctx->dAwake) {
+        CU(dalloc(&ctx->dAwake, (size_t)ctx->cfg.maxBodies));
+        CU(cudaMemsetAsync(ctx->dAwake, 1, ctx->cfg.maxBodies, ctx->stream));   // bodies beyond n (ghosts) are awake
+    }
+    if (n) CU(cudaMemcpyAsync(ctx->dAwake, awake, n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->awakeOn = true;
+    return AXCD_OK;
+}
+
 int32_t axcd_set_filters(AxcdContext* ctx, const AxcdFilter* filters, uint32_t n) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
     if (!filters) {
         ctx->filtersOn = false;
+        ctx->pairsCached = false;
         return AXCD_OK;
     }
     if (n > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
@@ -864,6 +929,7 @@ int32_t axcd_set_filters(AxcdContext* ctx, const AxcdFilter* filters, uint32_t n
     free(tmp);
     if (e != cudaSuccess) return fail(ctx, e, "filter upload");
     ctx->filtersOn = true;
+    ctx->pairsCached = false;
     return AXCD_OK;
 }
 
@@ -871,6 +937,8 @@ int32_t axcd_set_slab(AxcdContext* ctx, float xLo, float xHi, uint32_t enable) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
     if (enable && !(xLo <= xHi)) return AXCD_ERR_INVALID_PARAM;
     if (enable && ctx->cfg.numWorlds > 1) return AXCD_ERR_INVALID_PARAM;   // slabs split ONE scene
+    // the ghost set changes every step, so there is no persistent fat-box state to be coherent with
+    if (enable && (ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE)) return AXCD_ERR_INVALID_PARAM;
     ctx->slabOn = enable != 0;
     ctx->slabLo = xLo;
     ctx->slabHi = xHi;
@@ -892,6 +960,8 @@ int32_t axcd_set_ghosts(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts, con
     if (nGhosts && (!transforms40 || !shapes || !keys)) return AXCD_ERR_NULL_POINTER;
     if (nOwned != ctx->nOwned) return AXCD_ERR_INVALID_PARAM;
     if ((uint64_t)nOwned + nGhosts > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    ctx->fatValid = false;
+    ctx->pairsCached = false;
     for (uint32_t i = 0; i < nGhosts; ++i)
         if (shapes[i].type != AXCD_SHAPE_SPHERE && shapes[i].type != AXCD_SHAPE_BOX &&
             shapes[i].type != AXCD_SHAPE_CAPSULE)
@@ -956,6 +1026,8 @@ int32_t axcd_set_ghosts_device(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhos
     if (nGhosts && !devRecords) return AXCD_ERR_NULL_POINTER;
     if (nOwned != ctx->nOwned) return AXCD_ERR_INVALID_PARAM;
     if ((uint64_t)nOwned + nGhosts > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    ctx->fatValid = false;
+    ctx->pairsCached = false;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (nGhosts) {
         unpackGhostsKernel<<<(nGhosts + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const float4*>(devRecords), nGhosts, nOwned,

@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(kTravThreads)
 findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ leafHi,
                 const BvhNode* __restrict__ nodes, const uint32_t* __restrict__ worldEnd, uint32_t n,
                 uint2* __restrict__ pairs, uint32_t maxPairs, uint32_t* __restrict__ bodyCount,
-                SlabRule slab, const uint4* __restrict__ filters, Counters* __restrict__ ctr) {
+                SlabRule slab, const uint4* __restrict__ filters, const uint8_t* __restrict__ awake,
+                Counters* __restrict__ ctr) {
     __shared__ uint2 sPool[kTravPool];
     __shared__ uint32_t sCount, sBase;
     if (threadIdx.x == 0) sCount = 0;
@@ -265,6 +266,9 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                 const uint32_t bodyJ = __float_as_uint(__ldg(&leafLo[child].w));
                 uint2 pr = make_uint2(min(bodyI, bodyJ), max(bodyI, bodyJ));
                 if (filters && !shouldCollide(filters, bodyI, bodyJ)) continue;
+                // sleeping bodies (debug::DebugRigidBody::isAwake, physics_debug_draw.hpp:123): a pair of
+                // two sleeping bodies is not a candidate
+                if (awake && !(__ldg(awake + bodyI) | __ldg(awake + bodyJ))) continue;
                 if (slab.enabled) {
                     // one huge scene split into x-slabs: this rank reports the pair only if the left end
                     // of the pair's x-overlap, max(min_i.x, min_j.x), lies in its slab (exactly one rank

@@ -32,13 +32,94 @@ __device__ __forceinline__ void expandPoint(V3& lo, V3& hi, V3 p) {
     hi.z = (p.z > hi.z) ? p.z : hi.z;
 }
 
+// Tight world-space box of one body (no margin): the per-shape refit rules of SURVEY.md A.2.
+__device__ __forceinline__ void fitBody(V3 pos, float4 q, V3 scl, uint4 sh, const float4* __restrict__ hull,
+                                        V3& lo, V3& hi) {
+    const float p0 = __uint_as_float(sh.y), p1 = __uint_as_float(sh.z), p2 = __uint_as_float(sh.w);
+    if (sh.x == AXCD_SHAPE_SPHERE) {
+        // AABB::fromCenterExtents(position, Vec3(r)) (aabb.hpp:213-215); rotation and scale
+        // ignored as in the reference's sphere placement (src/debug/physics_debug_draw.cpp:246-248)
+        lo = pos - mk3(p0, p0, p0);
+        hi = pos + mk3(p0, p0, p0);
+    } else if (sh.x == AXCD_SHAPE_BOX) {
+        // 8 corners in the order of src/debug/debug_draw.cpp:99-108, AABB(Vec3) then expand().
+        // The corners come in antipodal pairs +-c, and every step of transformPoint before the
+        // final "+ position" is odd under round-to-nearest: (-c)*scale == -(c*scale) and
+        // quatRotate(q, -v) == -quatRotate(q, v) bit for bit (products and fmaf negate exactly).
+        // So 4 rotations r_k give all 8 corners as pos +- r_k, and because fl(pos + r) is
+        // monotone in r the select-based min/max over the 8 corners equals pos -+ max_k |r_k|.
+        // Exceptions, sent down the literal 8-corner path: a zero position component (the sign
+        // of an exact zero sum, -0 + -0, depends on the sign of a zero r) and non-finite data
+        // (NaN corners are skipped by expand(), which is order-dependent).
+        const V3 sc = mk3(p0 * scl.x, p1 * scl.y, p2 * scl.z);   // corner 6 = (+,+,+), scaled
+        const V3 r0 = quatRotate(q, sc);                               // corner 6 (-> 0)
+        const V3 r1 = quatRotate(q, mk3(sc.x, -sc.y, -sc.z));           // corner 1 (-> 7)
+        const V3 r2 = quatRotate(q, mk3(sc.x, -sc.y, sc.z));            // corner 2 (-> 4)
+        const V3 r3 = quatRotate(q, mk3(sc.x, sc.y, -sc.z));            // corner 5 (-> 3)
+        const V3 m = mk3(fmaxf(fmaxf(fabsf(r0.x), fabsf(r1.x)), fmaxf(fabsf(r2.x), fabsf(r3.x))),
+                         fmaxf(fmaxf(fabsf(r0.y), fabsf(r1.y)), fmaxf(fabsf(r2.y), fabsf(r3.y))),
+                         fmaxf(fmaxf(fabsf(r0.z), fabsf(r1.z)), fmaxf(fabsf(r2.z), fabsf(r3.z))));
+        // finite check on everything the result depends on; NaN anywhere makes the sum NaN
+        // (fmaxf would drop a NaN operand, so the r_k are summed, not m)
+        const float chk = (fabsf(r0.x) + fabsf(r0.y) + fabsf(r0.z)) + (fabsf(r1.x) + fabsf(r1.y) + fabsf(r1.z)) +
+                          (fabsf(r2.x) + fabsf(r2.y) + fabsf(r2.z)) + (fabsf(r3.x) + fabsf(r3.y) + fabsf(r3.z)) +
+                          (fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z));
+        if (chk < 3.0e38f && pos.x != 0.0f && pos.y != 0.0f && pos.z != 0.0f) {
+            lo = pos - m;
+            hi = pos + m;
+        } else {
+            // corner k of debug_draw.cpp:99-108: x sign + for k in {1,2,5,6}, y sign + for k >= 4,
+            // z sign + for k in {2,3,6,7}
+            V3 c0 = transformPoint(pos, q, scl, mk3(-p0, -p1, -p2));
+            lo = c0;
+            hi = c0;
+#pragma unroll 1
+            for (int k = 1; k < 8; ++k) {
+                const float cx = ((k ^ (k >> 1)) & 1) ? p0 : -p0;
+                const float cy = (k & 4) ? p1 : -p1;
+                const float cz = (k & 2) ? p2 : -p2;
+                expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(cx, cy, cz)));
+            }
+        }
+    } else if (sh.x == AXCD_SHAPE_CAPSULE) {
+        // p0 = radius, p1 = height: box of the two end spheres, endpoints placed as the reference
+        // does (src/debug/physics_debug_draw.cpp:254-266: local (0, -+height/2, 0) through
+        // transformPoint); the radius is not scaled
+        const V3 half = mk3(0.0f, p1 * 0.5f, 0.0f);
+        const V3 start = transformPoint(pos, q, scl, -half);
+        const V3 end = transformPoint(pos, q, scl, half);
+        lo = start;
+        hi = start;
+        expandPoint(lo, hi, end);
+        lo = lo - mk3(p0, p0, p0);
+        hi = hi + mk3(p0, p0, p0);
+    } else {   // AXCD_SHAPE_CONVEX (validated on the host): min/max over transformPoint(v_i)
+        const uint32_t first = sh.y, count = sh.z;
+        float4 v = __ldg(hull + first);
+        V3 c0 = transformPoint(pos, q, scl, mk3(v.x, v.y, v.z));
+        lo = c0;
+        hi = c0;
+        for (uint32_t k = 1; k < count; ++k) {
+            v = __ldg(hull + first + k);
+            expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(v.x, v.y, v.z)));
+        }
+    }
+}
+
+// COHERENT = false: every body gets its tight box expanded by `margin` (AABB::expand(float)).
+// COHERENT = true (temporal coherence): aabb4 holds persistent FAT boxes.  A body
+// whose tight box still lies inside its fat box keeps it; otherwise (or when `force` is set: first step
+// after the shapes changed) the fat box becomes the tight box expanded by `margin` and the body is
+// counted in ctr->movedBodies.  If nothing moved the candidate-pair set cannot have changed and the host
+// skips the broadphase (axcd_broadphase).
+template <bool COHERENT>
 __global__ void __launch_bounds__(kRefitThreads)
 refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 (base 16B aligned)
             const uint4* __restrict__ shapes,    // AxcdShape as uint4
             const float4* __restrict__ hull,     // hull vertices padded to float4
             float4* __restrict__ aabb4,          // n*24 bytes viewed as float4
             uint8_t* __restrict__ type8,         // out: shape type per body, compact (pair classification gathers it)
-            uint32_t n, float margin, Counters* __restrict__ ctr) {
+            uint32_t n, float margin, uint32_t force, Counters* __restrict__ ctr) {
     __shared__ __align__(16) float sIn[kRefitThreads * 10];
     __shared__ __align__(16) float sOut[kRefitThreads * 6];
     __shared__ float sRed[6][kRefitThreads / 32];
@@ -46,6 +127,15 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
     const uint32_t base = blockIdx.x * kRefitThreads;
     const uint32_t cnt = min((uint32_t)kRefitThreads, n - base);
     const int tid = threadIdx.x;
+
+    if (COHERENT) {   // stage the block's current fat boxes into sOut (same path as the stores below)
+        const uint32_t nFloats = cnt * 6, nVec = nFloats / 4;
+        const float4* src = aabb4 + (size_t)base * 6 / 4;
+        float4* dst = reinterpret_cast<float4*>(sOut);
+        for (uint32_t i = tid; i < nVec; i += kRefitThreads) dst[i] = src[i];
+        const float* srcF = reinterpret_cast<const float*>(src);
+        for (uint32_t i = nVec * 4 + tid; i < nFloats; i += kRefitThreads) sOut[i] = srcF[i];
+    }
 
     // ---- stage the block's transforms: coalesced 128-bit loads --------------------------------
     {
@@ -68,82 +158,29 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
         const V3 scl = mk3(t[7], t[8], t[9]);
         const uint4 sh = __ldg(shapes + base + tid);
         type8[base + tid] = (uint8_t)sh.x;
-        const float p0 = __uint_as_float(sh.y), p1 = __uint_as_float(sh.z), p2 = __uint_as_float(sh.w);
-        if (sh.x == AXCD_SHAPE_SPHERE) {
-            // AABB::fromCenterExtents(position, Vec3(r)) (aabb.hpp:213-215); rotation and scale
-            // ignored as in the reference's sphere placement (src/debug/physics_debug_draw.cpp:246-248)
-            lo = pos - mk3(p0, p0, p0);
-            hi = pos + mk3(p0, p0, p0);
-        } else if (sh.x == AXCD_SHAPE_BOX) {
-            // 8 corners in the order of src/debug/debug_draw.cpp:99-108, AABB(Vec3) then expand().
-            // The corners come in antipodal pairs +-c, and every step of transformPoint before the
-            // final "+ position" is odd under round-to-nearest: (-c)*scale == -(c*scale) and
-            // quatRotate(q, -v) == -quatRotate(q, v) bit for bit (products and fmaf negate exactly).
-            // So 4 rotations r_k give all 8 corners as pos +- r_k, and because fl(pos + r) is
-            // monotone in r the select-based min/max over the 8 corners equals pos -+ max_k |r_k|.
-            // Exceptions, sent down the literal 8-corner path: a zero position component (the sign
-            // of an exact zero sum, -0 + -0, depends on the sign of a zero r) and non-finite data
-            // (NaN corners are skipped by expand(), which is order-dependent).
-            const V3 sc = mk3(p0 * scl.x, p1 * scl.y, p2 * scl.z);   // corner 6 = (+,+,+), scaled
-            const V3 r0 = quatRotate(q, sc);                               // corner 6 (-> 0)
-            const V3 r1 = quatRotate(q, mk3(sc.x, -sc.y, -sc.z));           // corner 1 (-> 7)
-            const V3 r2 = quatRotate(q, mk3(sc.x, -sc.y, sc.z));            // corner 2 (-> 4)
-            const V3 r3 = quatRotate(q, mk3(sc.x, sc.y, -sc.z));            // corner 5 (-> 3)
-            const V3 m = mk3(fmaxf(fmaxf(fabsf(r0.x), fabsf(r1.x)), fmaxf(fabsf(r2.x), fabsf(r3.x))),
-                             fmaxf(fmaxf(fabsf(r0.y), fabsf(r1.y)), fmaxf(fabsf(r2.y), fabsf(r3.y))),
-                             fmaxf(fmaxf(fabsf(r0.z), fabsf(r1.z)), fmaxf(fabsf(r2.z), fabsf(r3.z))));
-            // finite check on everything the result depends on; NaN anywhere makes the sum NaN
-            // (fmaxf would drop a NaN operand, so the r_k are summed, not m)
-            const float chk = (fabsf(r0.x) + fabsf(r0.y) + fabsf(r0.z)) + (fabsf(r1.x) + fabsf(r1.y) + fabsf(r1.z)) +
-                              (fabsf(r2.x) + fabsf(r2.y) + fabsf(r2.z)) + (fabsf(r3.x) + fabsf(r3.y) + fabsf(r3.z)) +
-                              (fabsf(pos.x) + fabsf(pos.y) + fabsf(pos.z));
-            if (chk < 3.0e38f && pos.x != 0.0f && pos.y != 0.0f && pos.z != 0.0f) {
-                lo = pos - m;
-                hi = pos + m;
-            } else {
-                // corner k of debug_draw.cpp:99-108: x sign + for k in {1,2,5,6}, y sign + for k >= 4,
-                // z sign + for k in {2,3,6,7}
-                V3 c0 = transformPoint(pos, q, scl, mk3(-p0, -p1, -p2));
-                lo = c0;
-                hi = c0;
-#pragma unroll 1
-                for (int k = 1; k < 8; ++k) {
-                    const float cx = ((k ^ (k >> 1)) & 1) ? p0 : -p0;
-                    const float cy = (k & 4) ? p1 : -p1;
-                    const float cz = (k & 2) ? p2 : -p2;
-                    expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(cx, cy, cz)));
-                }
-            }
-        } else if (sh.x == AXCD_SHAPE_CAPSULE) {
-            // p0 = radius, p1 = height: box of the two end spheres, endpoints placed as the reference
-            // does (src/debug/physics_debug_draw.cpp:254-266: local (0, -+height/2, 0) through
-            // transformPoint); the radius is not scaled
-            const V3 half = mk3(0.0f, p1 * 0.5f, 0.0f);
-            const V3 start = transformPoint(pos, q, scl, -half);
-            const V3 end = transformPoint(pos, q, scl, half);
-            lo = start;
-            hi = start;
-            expandPoint(lo, hi, end);
-            lo = lo - mk3(p0, p0, p0);
-            hi = hi + mk3(p0, p0, p0);
-        } else {   // AXCD_SHAPE_CONVEX (validated on the host): min/max over transformPoint(v_i)
-            const uint32_t first = sh.y, count = sh.z;
-            float4 v = __ldg(hull + first);
-            V3 c0 = transformPoint(pos, q, scl, mk3(v.x, v.y, v.z));
-            lo = c0;
-            hi = c0;
-            for (uint32_t k = 1; k < count; ++k) {
-                v = __ldg(hull + first + k);
-                expandPoint(lo, hi, transformPoint(pos, q, scl, mk3(v.x, v.y, v.z)));
-            }
-        }
-        if (margin != 0.0f) {   // AABB::expand(float) (aabb.hpp:156-160)
-            lo = lo - mk3(margin, margin, margin);
-            hi = hi + mk3(margin, margin, margin);
-        }
+        fitBody(pos, q, scl, sh, hull, lo, hi);
         float* o = sOut + tid * 6;
-        o[0] = lo.x; o[1] = lo.y; o[2] = lo.z;
-        o[3] = hi.x; o[4] = hi.y; o[5] = hi.z;
+        bool keep = false;
+        if (COHERENT && !force) {
+            // contained (closed): keep the fat box.  Any NaN compares false -> refit.
+            keep = o[0] <= lo.x && o[1] <= lo.y && o[2] <= lo.z && lo.x <= hi.x && lo.y <= hi.y && lo.z <= hi.z &&
+                   hi.x <= o[3] && hi.y <= o[4] && hi.z <= o[5];
+        }
+        if (keep) {
+            lo = mk3(o[0], o[1], o[2]);
+            hi = mk3(o[3], o[4], o[5]);
+        } else {
+            if (margin != 0.0f) {   // AABB::expand(float) (aabb.hpp:156-160)
+                lo = lo - mk3(margin, margin, margin);
+                hi = hi + mk3(margin, margin, margin);
+            }
+            o[0] = lo.x; o[1] = lo.y; o[2] = lo.z;
+            o[3] = hi.x; o[4] = hi.y; o[5] = hi.z;
+        }
+        if (COHERENT) {
+            const uint32_t bal = __ballot_sync(__activemask(), !keep);
+            if (!keep && (tid & 31) == __ffs(bal) - 1) atomicAdd(&ctr->movedBodies, (uint32_t)__popc(bal));
+        }
     }
 
     // ---- scene bounds of the AABB centres (for Morton normalisation; quality only) ------------

@@ -110,7 +110,14 @@ enum {
     /* Run EPA with the cooperative kernel (8 lanes per pair, faces in registers) instead of the
      * default one-thread-per-pair kernel.  Same results; slower on B200 so far (profiles/), kept
      * for A/B measurements.                                                                     */
-    AXCD_FLAG_EPA_COOPERATIVE = 2u
+    AXCD_FLAG_EPA_COOPERATIVE = 2u,
+    /* Temporal coherence: the AABB buffer holds persistent FAT boxes — a body's
+     * box is rebuilt (tight box expanded by aabbMargin, AABB::expand(float), aabb.hpp:156-160) only when
+     * its tight box leaves it — and axcd_broadphase reuses the previous candidate list when no body
+     * moved out of its fat box (AxcdStats.movedBodies == 0 -> broadphaseSkipped = 1).  The candidate set
+     * is then the overlap set of the fat boxes (a superset of the tight one); the contact set is
+     * unchanged, because the narrowphase works on the exact shapes.  Not available in x-slab mode.  */
+    AXCD_FLAG_TEMPORAL_COHERENCE = 4u
 };
 
 typedef struct AxcdStats {
@@ -124,6 +131,9 @@ typedef struct AxcdStats {
     uint32_t kernelLaunches; /* kernels launched by the last refit+broadphase+narrowphase       */
     uint32_t contactPointCount; /* gui::PhysicsWorldStats::contactPointCount (physics_panel.hpp:21):
                                    manifold points of the last axcd_build_manifolds, else 0      */
+    uint32_t movedBodies;       /* AXCD_FLAG_TEMPORAL_COHERENCE: bodies whose fat box was rebuilt by
+                                   the last refit (numBodies without the flag)                   */
+    uint32_t broadphaseSkipped; /* 1 if the last axcd_broadphase reused the cached candidate list */
 } AxcdStats;
 
 typedef struct AxcdContext AxcdContext; /* opaque */
@@ -226,6 +236,12 @@ typedef struct AxcdFilter {
     int32_t groupIndex;
 } AxcdFilter;
 AXCD_API int32_t axcd_set_filters(AxcdContext* ctx, const AxcdFilter* filters, uint32_t n);
+
+/* Sleeping bodies (debug::DebugRigidBody::isAwake, include/axiom/debug/physics_debug_draw.hpp:123;
+ * gui::SleepInfo, include/axiom/gui/body_inspector.hpp:45-51): awake[i] == 0 marks body i asleep; a
+ * pair of two sleeping bodies is not a candidate (applied where candidate pairs are emitted).  NULL
+ * switches the rule off (all awake, the default).                                                 */
+AXCD_API int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t n);
 
 /* ---- one huge scene across several GPUs: x-slab mode ---------
  * Bodies [0, nOwned) are the ones this rank owns (set with axcd_set_shapes / axcd_set_transforms as

@@ -208,3 +208,81 @@ def test_queries_tiny_scenes_and_errors():
         assert (gr["body"] != axcd.NO_HIT).all()
         assert len(w.query_aabbs(np.zeros((0, 6), np.float32))) == 0
         w.close()
+
+
+# ------------------------------------------------------------------ temporal coherence (rank 3) --
+def _expand(tight, margin):
+    m = np.float32(margin)
+    return np.concatenate([tight[:, :3] - m, tight[:, 3:] + m], axis=1).astype(np.float32)
+
+
+def test_temporal_coherence_fat_boxes_and_pair_cache():
+    s = axcd.config_scene("C1", scale=0.2)
+    margin = 0.05
+    w = axcd.CollisionWorld.for_scene(s, aabbMargin=margin, flags=axcd.FLAG_TEMPORAL_COHERENCE, pairs_per_body=16)
+    rng = np.random.default_rng(0)
+    xf = s.xf.copy()
+    fat = None
+    skipped = []
+    for step in range(7):
+        if step in (1, 2, 4):                       # small motions: every tight box stays inside its fat box
+            xf[:, :3] += rng.uniform(-0.012, 0.012, (s.n, 3)).astype(np.float32)
+        if step == 3:                               # a few bodies jump: their fat boxes are rebuilt
+            k = rng.choice(s.n, 50, replace=False)
+            xf[k, :3] += rng.uniform(-1.5, 1.5, (50, 3)).astype(np.float32)
+        w.set_transforms(xf)
+        st = w.step()
+        rc, tight = O.refit(xf, s.shapes, s.hull, nthreads=8)
+        if fat is None:
+            fat, moved = _expand(tight, margin), s.n
+        else:
+            inside = ((fat[:, :3] <= tight[:, :3]).all(1) & (tight[:, :3] <= tight[:, 3:]).all(1)
+                      & (tight[:, 3:] <= fat[:, 3:]).all(1))
+            fat[~inside] = _expand(tight[~inside], margin)
+            moved = int((~inside).sum())
+        assert st.movedBodies == moved, (step, st.movedBodies, moved)
+        assert st.broadphaseSkipped == (1 if (moved == 0 and step > 0) else 0), step
+        skipped.append(st.broadphaseSkipped)
+        assert _bits_equal(w.aabbs(), fat)                                   # fat boxes, bit-exact
+        pairs = O.broadphase(fat, nthreads=8)
+        assert np.array_equal(w.pairs(), pairs)                             # candidate set of the fat boxes
+        con, _, _ = O.narrowphase(xf, s.shapes, pairs, s.hull, nthreads=8)
+        gc = w.contacts()
+        assert gc.tobytes() == con.tobytes()
+        # the contact set does not depend on the margin: same as the plain (tight-box) pipeline
+        con_t, _, _ = O.narrowphase(xf, s.shapes, O.broadphase(tight, nthreads=8), s.hull, nthreads=8)
+        assert np.array_equal(gc["a"], con_t["a"]) and np.array_equal(gc["b"], con_t["b"])
+    assert skipped == [0, 1, 1, 0, 1, 1, 1], skipped
+    # changing the candidate rule invalidates the cache even when nothing moved
+    w.set_awake(np.ones(s.n, np.uint8))
+    w.set_transforms(xf)
+    assert w.step().broadphaseSkipped == 0
+    w.close()
+    # slab mode has no persistent fat-box state
+    w = axcd.CollisionWorld(16, flags=axcd.FLAG_TEMPORAL_COHERENCE)
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_slab(0.0, 1.0)
+    assert e.value.code == 600
+    w.close()
+
+
+def test_sleeping_pairs_are_dropped():
+    s = axcd.config_scene("C1", scale=0.2)
+    rng = np.random.default_rng(1)
+    awake = (rng.random(s.n) < 0.5).astype(np.uint8)
+    w = axcd.CollisionWorld.for_scene(s)
+    w.set_awake(awake)
+    st = w.step()
+    rc, bb = O.refit(s.xf, s.shapes, s.hull, nthreads=8)
+    allp = O.broadphase(bb, nthreads=8)
+    keep = (awake[allp[:, 0]] | awake[allp[:, 1]]) != 0
+    pairs = allp[keep]
+    assert 0 < len(pairs) < len(allp)
+    assert np.array_equal(w.pairs(), pairs)
+    con, _, _ = O.narrowphase(s.xf, s.shapes, pairs, s.hull, nthreads=8)
+    assert w.contacts().tobytes() == con.tobytes()
+    w.set_awake(None)                              # rule off: the full candidate set again
+    w.set_transforms(s.xf)
+    w.step()
+    assert np.array_equal(w.pairs(), allp)
+    w.close()

@@ -100,6 +100,8 @@ struct AxcdContext {
     uint32_t* dSortHist = nullptr;
     uint32_t* dSortStatus = nullptr;
     Counters* dCtr = nullptr;
+    Counters* dCtrBase = nullptr;    // two counter blocks: step k uses one, its refit kernel resets the other for step k+1
+    int ctrParity = 0;
     Counters* dCtrInit = nullptr;    // per-step initial value of the counters (device copy: async reset)
     cudaEvent_t ev[EV_COUNT];
     bool evValid[EV_COUNT];
@@ -250,7 +252,7 @@ void axcd_destroy(AxcdContext* ctx) {
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dManifolds, ctx->dQIn, ctx->dQCount, ctx->dQSeg, ctx->dQOut, ctx->dPairDist, ctx->dSortHist,
-                    ctx->dSortStatus, ctx->dCtr, ctx->dCtrInit};
+                    ctx->dSortStatus, ctx->dCtrBase, ctx->dCtrInit};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (int i = 0; i < EV_COUNT; ++i)
@@ -338,7 +340,8 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dSortHist, (size_t)kMaxPasses * kRadix));
         const size_t maxTiles = sortTilesFor(nb > np ? nb : np);
         CU(dalloc(&ctx->dSortStatus, (size_t)kMaxPasses * maxTiles * kRadix));
-        CU(dalloc(&ctx->dCtr, 1));
+        CU(dalloc(&ctx->dCtrBase, 2));
+        ctx->dCtr = ctx->dCtrBase;
         CU(dalloc(&ctx->dCtrInit, 1));
         {
             Counters init;
@@ -348,6 +351,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
                 init.boundsMax[k] = 0u;
             }
             CU(cudaMemcpy(ctx->dCtrInit, &init, sizeof(Counters), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(ctx->dCtrBase + 1, &init, sizeof(Counters), cudaMemcpyHostToDevice));
         }
         CU(cudaMemsetAsync(ctx->dCtr, 0, sizeof(Counters), ctx->stream));
         // slotKernel reads the per-pair flags 8 bytes at a time and masks the tail: keep the tail defined
@@ -435,19 +439,26 @@ int32_t axcd_refit(AxcdContext* ctx) {
     recordEv(ctx, EV_START);
     ctx->manifoldsValid = false;
     // reset per-step counters: bounds (min = +inf encoding, max = -inf encoding) and counts
-    CU(cudaMemcpyAsync(ctx->dCtr, ctx->dCtrInit, sizeof(Counters), cudaMemcpyDeviceToDevice, ctx->stream));
+    // per-step counters (scene bounds at +-inf encodings, counts at zero): this step takes the block the
+    // previous refit kernel reset, and its own refit kernel resets the other one for the next step — no
+    // memcpy node in front of the first kernel
+    ctx->ctrParity ^= 1;
+    ctx->dCtr = ctx->dCtrBase + ctx->ctrParity;
+    Counters* ctrNext = ctx->dCtrBase + (ctx->ctrParity ^ 1);
+    if (!ctx->n) CU(cudaMemcpyAsync(ctrNext, ctx->dCtrInit, sizeof(Counters), cudaMemcpyDeviceToDevice, ctx->stream));
     if (ctx->n) {
         const uint32_t blocks = (ctx->n + kRefitThreads - 1) / kRefitThreads;
         if (ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE) {
             refitKernel<true><<<blocks, kRefitThreads, 0, ctx->stream>>>(
                 reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
                 reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin,
-                ctx->fatValid ? 0u : 1u, ctx->dCtr);
+                ctx->fatValid ? 0u : 1u, ctx->dCtr, ctrNext, ctx->dCtrInit);
             ctx->fatValid = true;
         } else {
             refitKernel<false><<<blocks, kRefitThreads, 0, ctx->stream>>>(
                 reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
-                reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin, 0u, ctx->dCtr);
+                reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin, 0u, ctx->dCtr,
+                ctrNext, ctx->dCtrInit);
         }
         CU(cudaGetLastError());
     }

@@ -11,8 +11,8 @@
 // triangle, farthest outside that triangle).  Every other pair class, and a box-box contact whose
 // clip comes out empty, keeps the narrowphase point.  Same expression trees as the CPU oracle.
 //
-// One thread per contact; the 88-byte records of a 128-contact block are staged in shared memory and
-// written with coalesced 128-bit stores.  Algorithmic bytes: 40 B contact + 2 x 56 B pose/shape
+// Tiles of 256 contacts per 128-thread block; the 88-byte records are staged in shared memory and
+// written with coalesced 128-bit stores; box-box contacts are compacted and clipped densely.  Algorithmic bytes: 40 B contact + 2 x 56 B pose/shape
 // gathers in, 88 B out per contact.
 #pragma once
 
@@ -23,7 +23,7 @@ namespace axcd {
 constexpr int kManThreads = 128;
 constexpr int kManWords = sizeof(AxcdManifold) / 4;   // 22
 static_assert(sizeof(AxcdManifold) == 88, "AxcdManifold layout");
-static_assert((kManThreads * sizeof(AxcdManifold)) % 16 == 0, "a block's records are whole float4s");
+static_assert((2 * kManThreads * sizeof(AxcdManifold)) % 16 == 0, "a tile's records are whole float4s");
 
 struct BoxFrame {
     V3 c;        // centre relative to A's position
@@ -52,10 +52,26 @@ __device__ __forceinline__ V3 pickAxis(const BoxFrame& f, int i) { return (i == 
 __device__ __forceinline__ float pickHalf(const BoxFrame& f, int i) { return (i == 0) ? f.h[0] : ((i == 1) ? f.h[1] : f.h[2]); }
 __device__ __forceinline__ float pick3(float d0, float d1, float d2, int i) { return (i == 0) ? d0 : ((i == 1) ? d1 : d2); }
 
-// Fills pos/dep with the clipped, kept and reduced points (A-centred frame); returns their count
-// (0: the narrowphase point stands).
-__device__ __noinline__ int boxBoxManifold(const BoxFrame& A, const BoxFrame& B, V3 n, V3* __restrict__ outPos,
-                                           float* __restrict__ outDep) {
+// Per-thread polygon storage in shared memory: column `tid` of a [words][kManThreads] array, so the
+// same word of all threads is contiguous (conflict-free for uniform indices).
+struct PolyCol {
+    float* base;
+    __device__ __forceinline__ V3 get(int k) const {
+        return mk3(base[(3 * k) * kManThreads], base[(3 * k + 1) * kManThreads], base[(3 * k + 2) * kManThreads]);
+    }
+    __device__ __forceinline__ void set(int k, V3 v) const {
+        base[(3 * k) * kManThreads] = v.x;
+        base[(3 * k + 1) * kManThreads] = v.y;
+        base[(3 * k + 2) * kManThreads] = v.z;
+    }
+    __device__ __forceinline__ float& f(int k) const { return base[k * kManThreads]; }
+};
+
+// Clips, keeps and reduces (A-centred frame).  On return poly.get(0..nk) are the kept positions in
+// polygon order, dep.f(0..nk) their depths, and the returned mask says which of them survive the
+// reduction to four; *outNk = nk (0: the narrowphase point stands).
+__device__ __forceinline__ uint32_t boxBoxManifold(const BoxFrame& A, const BoxFrame& B, V3 n, PolyCol poly, PolyCol tmp,
+                                                   int* outNk) {
     const float da0 = dot3(n, A.ax[0]), da1 = dot3(n, A.ax[1]), da2 = dot3(n, A.ax[2]);
     const float db0 = dot3(n, B.ax[0]), db1 = dot3(n, B.ax[1]), db2 = dot3(n, B.ax[2]);
     const int ia = argmaxAbs3(da0, da1, da2), ib = argmaxAbs3(db0, db1, db2);
@@ -73,85 +89,94 @@ __device__ __noinline__ int boxBoxManifold(const BoxFrame& A, const BoxFrame& B,
     const int ju = (j + 1) % 3, jv = (j + 2) % 3;
     const V3 fc = I.c + pickAxis(I, j) * (sI * pickHalf(I, j));
     const V3 eu = pickAxis(I, ju) * pickHalf(I, ju), ev = pickAxis(I, jv) * pickHalf(I, jv);
-    V3 poly[8], tmp[8];
     int np = 4;
-    poly[0] = (fc + eu) + ev;
-    poly[1] = (fc - eu) + ev;
-    poly[2] = (fc - eu) - ev;
-    poly[3] = (fc + eu) - ev;
-    // clip against the reference face's side planes: s * dot(p - cR, ax_w) <= h_w
+    poly.set(0, (fc + eu) + ev);
+    poly.set(1, (fc - eu) + ev);
+    poly.set(2, (fc - eu) - ev);
+    poly.set(3, (fc + eu) - ev);
+    // clip against the reference face's side planes: s * dot(p - cR, ax_w) <= h_w  (ping-pong poly <-> tmp)
+    PolyCol src = poly, dst = tmp;
     for (int side = 0; side < 4 && np > 0; ++side) {
         const int w = (i + 1 + (side >> 1)) % 3;
         const float s = (side & 1) ? -1.0f : 1.0f;
         const V3 pn = pickAxis(R, w) * s;
         const float hw = pickHalf(R, w);
         int nt = 0;
-        V3 prev = poly[np - 1];
+        V3 prev = src.get(np - 1);
         float dprev = dot3(prev - R.c, pn) - hw;
         for (int k = 0; k < np; ++k) {
-            const V3 cur = poly[k];
+            const V3 cur = src.get(k);
             const float dcur = dot3(cur - R.c, pn) - hw;
             const bool inPrev = dprev <= 0.0f, inCur = dcur <= 0.0f;
             if (inPrev != inCur) {
                 const float t = dprev / (dprev - dcur);
-                tmp[nt++] = prev + (cur - prev) * t;
+                dst.set(nt++, prev + (cur - prev) * t);
             }
-            if (inCur) tmp[nt++] = cur;
+            if (inCur) dst.set(nt++, cur);
             prev = cur;
             dprev = dcur;
         }
         np = nt;
-        for (int k = 0; k < np; ++k) poly[k] = tmp[k];
+        const PolyCol sw = src; src = dst; dst = sw;
     }
-    // keep the vertices on or below the reference face
-    V3 pos[8];
-    float dep[8];
+    // four passes: the clipped polygon is back in `poly`, `tmp` is free and takes the depths.
+    // keep the vertices on or below the reference face (in place: nk <= k)
     int nk = 0;
     const float hi = pickHalf(R, i);
     for (int k = 0; k < np; ++k) {
-        const float sep = dot3(poly[k] - R.c, nr) - hi;
+        const V3 pk = poly.get(k);
+        const float sep = dot3(pk - R.c, nr) - hi;
         if (sep <= 0.0f) {
-            pos[nk] = poly[k] - nr * (sep * 0.5f);
-            dep[nk] = -sep;
+            poly.set(nk, pk - nr * (sep * 0.5f));
+            tmp.f(nk) = -sep;
             ++nk;
         }
     }
-    if (nk == 0) return 0;
+    *outNk = nk;
+    if (nk == 0) return 0u;
     uint32_t keep = (1u << nk) - 1u;
     if (nk > 4) {
         // reduction: deepest, farthest from it, largest triangle, then the vertex farthest outside it
         int p0 = 0;
-        for (int k = 1; k < nk; ++k)
-            if (dep[k] > dep[p0]) p0 = k;
+        float d0 = tmp.f(0);
+        for (int k = 1; k < nk; ++k) {
+            const float dk = tmp.f(k);
+            if (dk > d0) { d0 = dk; p0 = k; }
+        }
+        const V3 q0 = poly.get(p0);
         int p1 = -1;
         float best = -1.0f;
         for (int k = 0; k < nk; ++k) {
             if (k == p0) continue;
-            const V3 d = pos[k] - pos[p0];
+            const V3 d = poly.get(k) - q0;
             const float dd = dot3(d, d);
             if (dd > best) { best = dd; p1 = k; }
         }
-        const V3 e = pos[p1] - pos[p0];
-        float area[8];
-        for (int k = 0; k < nk; ++k) area[k] = dot3(cross3(e, pos[k] - pos[p0]), nr);
+        const V3 q1 = poly.get(p1);
+        const V3 e = q1 - q0;
+        // signed areas against the edge p0->p1 go to the upper half of the depth column
         int p2 = -1;
         best = 0.0f;
         for (int k = 0; k < nk; ++k) {
+            const float ar = dot3(cross3(e, poly.get(k) - q0), nr);
+            tmp.f(8 + k) = ar;
             if (k == p0 || k == p1) continue;
-            if (fabsf(area[k]) > best) { best = fabsf(area[k]); p2 = k; }
+            if (fabsf(ar) > best) { best = fabsf(ar); p2 = k; }
         }
         keep = (1u << p0) | (1u << p1);
         if (p2 >= 0) {
             keep |= 1u << p2;
-            const float flip = (area[p2] >= 0.0f) ? -1.0f : 1.0f;
-            const V3 e12 = pos[p2] - pos[p1], e20 = pos[p0] - pos[p2];
+            const V3 q2 = poly.get(p2);
+            const float flip = (tmp.f(8 + p2) >= 0.0f) ? -1.0f : 1.0f;
+            const V3 e12 = q2 - q1, e20 = q0 - q2;
             int p3 = -1;
             best = 0.0f;
             for (int k = 0; k < nk; ++k) {
                 if (k == p0 || k == p1 || k == p2) continue;
-                const float o01 = area[k] * flip;
-                const float o12 = dot3(cross3(e12, pos[k] - pos[p1]), nr) * flip;
-                const float o20 = dot3(cross3(e20, pos[k] - pos[p2]), nr) * flip;
+                const V3 pk = poly.get(k);
+                const float o01 = tmp.f(8 + k) * flip;
+                const float o12 = dot3(cross3(e12, pk - q1), nr) * flip;
+                const float o20 = dot3(cross3(e20, pk - q2), nr) * flip;
                 float v = o01;
                 if (o12 > v) v = o12;
                 if (o20 > v) v = o20;
@@ -160,76 +185,88 @@ __device__ __noinline__ int boxBoxManifold(const BoxFrame& A, const BoxFrame& B,
             if (p3 >= 0) keep |= 1u << p3;
         }
     }
-    int cnt = 0;
-    for (int k = 0; k < nk; ++k) {
-        if (!((keep >> k) & 1u)) continue;
-        outPos[cnt] = pos[k];
-        outDep[cnt] = dep[k];
-        ++cnt;
-    }
-    return cnt;
+    return keep;
 }
+
+// One block handles tiles of kManTile contacts: every thread writes the single-point record of its
+// contacts into the shared staging area, the tile's box-box contacts are compacted into a list, and the
+// first threads of the block clip them with all lanes busy (polygons in shared-memory columns, nothing
+// in local memory); the finished tile leaves with coalesced 128-bit stores.
+constexpr int kManTile = 2 * kManThreads;
 
 __global__ void __launch_bounds__(kManThreads)
 manifoldKernel(const AxcdContact* __restrict__ contacts, const uint32_t* __restrict__ contactCount, uint32_t maxContacts,
                const float* __restrict__ xf, const uint4* __restrict__ shapes, float4* __restrict__ out4,
                uint32_t* __restrict__ pointCount) {
-    __shared__ __align__(16) float sOut[kManThreads * kManWords];
-    __shared__ uint32_t sPts[kManThreads / 32];
+    __shared__ __align__(16) float sOut[kManTile * kManWords];     // 22.5 KB
+    __shared__ float sPoly[2 * 24 * kManThreads];                  // 24 KB: two 8-vertex polygons per thread
+    __shared__ uint16_t sList[kManTile];
+    __shared__ uint32_t sCount, sPts;
     const uint32_t total = min(*contactCount, maxContacts);
     const int tid = threadIdx.x;
-    for (uint32_t base = blockIdx.x * kManThreads; base < total; base += gridDim.x * kManThreads) {
-        const uint32_t cnt = min((uint32_t)kManThreads, total - base);
-        uint32_t myPoints = 0;
-        if (tid < (int)cnt) {
+    for (uint32_t base = blockIdx.x * kManTile; base < total; base += gridDim.x * kManTile) {
+        const uint32_t cnt = min((uint32_t)kManTile, total - base);
+        if (tid == 0) { sCount = 0; sPts = 0; }
+        __syncthreads();
+        // ---- phase 1: default (single-point) records; list the box-box contacts ------------------
+        for (uint32_t l = tid; l < cnt; l += kManThreads) {
             // 40-byte contact record, 8-byte aligned
-            const float2* cr = reinterpret_cast<const float2*>(contacts + base + tid);
+            const float2* cr = reinterpret_cast<const float2*>(contacts + base + l);
             const float2 c0 = __ldg(cr), c1 = __ldg(cr + 1), c2 = __ldg(cr + 2), c3 = __ldg(cr + 3), c4 = __ldg(cr + 4);
             const uint32_t a = __float_as_uint(c0.x), b = __float_as_uint(c0.y);
-            const V3 cpos = mk3(c1.x, c1.y, c2.x);
-            const V3 n = mk3(c2.y, c3.x, c3.y);
-            const float cdepth = c4.x;
-            const uint4 sa = __ldg(shapes + a), sb = __ldg(shapes + b);
-            V3 pos[4];
-            float dep[4];
-            int np = 0;
-            V3 origin = mk3(0.0f, 0.0f, 0.0f);
-            if (sa.x == AXCD_SHAPE_BOX && sb.x == AXCD_SHAPE_BOX) {
-                const BodyPose ta = loadPose(xf, a), tb = loadPose(xf, b);
-                origin = ta.p;
-                const BoxFrame A = makeBoxFrame(ta, sa, origin), B = makeBoxFrame(tb, sb, origin);
-                np = boxBoxManifold(A, B, n, pos, dep);
-            }
-            float* o = sOut + tid * kManWords;
+            float* o = sOut + l * kManWords;
             uint32_t* ou = reinterpret_cast<uint32_t*>(o);
             ou[0] = a; ou[1] = b;
-            o[2] = n.x; o[3] = n.y; o[4] = n.z;
+            o[2] = c2.y; o[3] = c3.x; o[4] = c3.y;
+            ou[5] = 1u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) { o[6 + k] = 0.0f; o[10 + k] = 0.0f; o[14 + k] = 0.0f; o[18 + k] = 0.0f; }
-            if (np == 0) {
-                ou[5] = 1u;
-                o[6] = cpos.x; o[10] = cpos.y; o[14] = cpos.z; o[18] = cdepth;
-                myPoints = 1;
-            } else {
-                ou[5] = (uint32_t)np;
-                for (int k = 0; k < np; ++k) {
-                    const V3 w = pos[k] + origin;
-                    o[6 + k] = w.x; o[10 + k] = w.y; o[14 + k] = w.z; o[18 + k] = dep[k];
-                }
-                myPoints = (uint32_t)np;
+            o[6] = c1.x; o[10] = c1.y; o[14] = c2.x; o[18] = c4.x;
+            const bool bb = __ldg(&shapes[a].x) == AXCD_SHAPE_BOX && __ldg(&shapes[b].x) == AXCD_SHAPE_BOX;
+            const uint32_t bal = __ballot_sync(__activemask(), bb);
+            if (bb) {
+                const int lane = tid & 31;
+                uint32_t wbase = 0;
+                const int leader = __ffs(bal) - 1;
+                if (lane == leader) wbase = atomicAdd(&sCount, (uint32_t)__popc(bal));
+                wbase = __shfl_sync(bal, wbase, leader);
+                sList[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)l;
             }
         }
-        // contact-point total (PhysicsWorldStats::contactPointCount): warp sums, one atomic per block tile
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) myPoints += __shfl_xor_sync(0xffffffffu, myPoints, off);
-        if ((tid & 31) == 0) sPts[tid >> 5] = myPoints;
         __syncthreads();
-        if (tid == 0) {
-            uint32_t s = 0;
-            for (int w = 0; w < kManThreads / 32; ++w) s += sPts[w];
-            if (s) atomicAdd(pointCount, s);
+        // ---- phase 2: clip the box-box contacts, dense over the threads --------------------------------
+        const uint32_t nbb = sCount;
+        uint32_t extra = 0;   // points beyond the one every contact already has
+        for (uint32_t t = tid; t < nbb; t += kManThreads) {
+            const uint32_t l = sList[t];
+            float* o = sOut + l * kManWords;
+            const uint32_t* ou = reinterpret_cast<const uint32_t*>(o);
+            const uint32_t a = ou[0], b = ou[1];
+            const V3 n = mk3(o[2], o[3], o[4]);
+            const BodyPose ta = loadPose(xf, a), tb = loadPose(xf, b);
+            const V3 origin = ta.p;
+            const BoxFrame A = makeBoxFrame(ta, __ldg(shapes + a), origin), B = makeBoxFrame(tb, __ldg(shapes + b), origin);
+            const PolyCol poly{sPoly + tid}, tmp{sPoly + 24 * kManThreads + tid};
+            int nk = 0;
+            const uint32_t keep = boxBoxManifold(A, B, n, poly, tmp, &nk);
+            if (nk == 0) continue;   // degenerate clip: the narrowphase point stands
+            int c = 0;
+            for (int k = 0; k < nk; ++k) {
+                if (!((keep >> k) & 1u)) continue;
+                const V3 w = poly.get(k) + origin;
+                o[6 + c] = w.x; o[10 + c] = w.y; o[14 + c] = w.z; o[18 + c] = tmp.f(k);
+                ++c;
+            }
+            reinterpret_cast<uint32_t*>(o)[5] = (uint32_t)c;
+            extra += (uint32_t)c - 1u;
         }
-        // coalesced 128-bit stores of the block's records (base * 88 B is a multiple of 16 B)
+        // contact-point total (PhysicsWorldStats::contactPointCount)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) extra += __shfl_xor_sync(0xffffffffu, extra, off);
+        if ((tid & 31) == 0 && extra) atomicAdd(&sPts, extra);
+        __syncthreads();
+        if (tid == 0) atomicAdd(pointCount, sPts + cnt);
+        // ---- coalesced 128-bit stores of the tile's records (base * 88 B is a multiple of 16 B) ----------
         const uint32_t nWords = cnt * kManWords;
         const uint32_t nVec = nWords / 4;
         float4* dst = out4 + (size_t)base * kManWords / 4;

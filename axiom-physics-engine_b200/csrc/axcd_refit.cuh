@@ -13,7 +13,10 @@
 
 namespace axcd {
 
-constexpr int kRefitThreads = 256;
+#ifndef AXCD_REFIT_THREADS
+#define AXCD_REFIT_THREADS 256
+#endif
+constexpr int kRefitThreads = AXCD_REFIT_THREADS;
 
 // Transform::transformPoint (reference: src/math/transform.cpp:86-93)
 __device__ __forceinline__ V3 transformPoint(V3 pos, float4 q, V3 scale, V3 p) {
@@ -119,14 +122,19 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
             const float4* __restrict__ hull,     // hull vertices padded to float4
             float4* __restrict__ aabb4,          // n*24 bytes viewed as float4
             uint8_t* __restrict__ type8,         // out: shape type per body, compact (pair classification gathers it)
-            uint32_t n, float margin, uint32_t force, Counters* __restrict__ ctr) {
+            uint32_t n, float margin, uint32_t force, Counters* __restrict__ ctr,
+            Counters* __restrict__ ctrNext,      // the next step's counter block: reset here (nobody reads it before)
+            const Counters* __restrict__ ctrInit) {
     __shared__ __align__(16) float sIn[kRefitThreads * 10];
     __shared__ __align__(16) float sOut[kRefitThreads * 6];
-    __shared__ float sRed[6][kRefitThreads / 32];
+    __shared__ uint32_t sRed[6][kRefitThreads / 32];
 
     const uint32_t base = blockIdx.x * kRefitThreads;
     const uint32_t cnt = min((uint32_t)kRefitThreads, n - base);
     const int tid = threadIdx.x;
+    static_assert(sizeof(Counters) / 4 <= kRefitThreads, "one thread per counter word");
+    if (blockIdx.x == 0 && tid < (int)(sizeof(Counters) / 4))
+        reinterpret_cast<uint32_t*>(ctrNext)[tid] = reinterpret_cast<const uint32_t*>(ctrInit)[tid];
 
     if (COHERENT) {   // stage the block's current fat boxes into sOut (same path as the stores below)
         const uint32_t nFloats = cnt * 6, nVec = nFloats / 4;
@@ -189,15 +197,13 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
         V3 c = (lo + hi) * 0.5f;
         const float big = 3.0e38f;
         bool fin = valid && fabsf(c.x) < big && fabsf(c.y) < big && fabsf(c.z) < big;   // false for NaN
-        float v[6] = {fin ? c.x : big, fin ? c.y : big, fin ? c.z : big,
-                      fin ? c.x : -big, fin ? c.y : -big, fin ? c.z : -big};
+        // ordered-uint encodings reduce with one redux.sync each (integer min/max on the warp)
+        uint32_t v[6] = {floatToOrdered(fin ? c.x : big), floatToOrdered(fin ? c.y : big), floatToOrdered(fin ? c.z : big),
+                         floatToOrdered(fin ? c.x : -big), floatToOrdered(fin ? c.y : -big), floatToOrdered(fin ? c.z : -big)};
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                v[k] = fminf(v[k], __shfl_xor_sync(0xffffffffu, v[k], off));
-                v[k + 3] = fmaxf(v[k + 3], __shfl_xor_sync(0xffffffffu, v[k + 3], off));
-            }
+        for (int k = 0; k < 3; ++k) {
+            v[k] = __reduce_min_sync(0xffffffffu, v[k]);
+            v[k + 3] = __reduce_max_sync(0xffffffffu, v[k + 3]);
         }
         if ((tid & 31) == 0) {
 #pragma unroll
@@ -206,13 +212,13 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
     }
     __syncthreads();
     if (tid < 6) {
-        float r = sRed[tid][0];
+        uint32_t r = sRed[tid][0];
         for (int w = 1; w < kRefitThreads / 32; ++w)
-            r = (tid < 3) ? fminf(r, sRed[tid][w]) : fmaxf(r, sRed[tid][w]);
+            r = (tid < 3) ? min(r, sRed[tid][w]) : max(r, sRed[tid][w]);
         if (tid < 3) {
-            if (r < 3.0e38f) atomicMin(&ctr->boundsMin[tid], floatToOrdered(r));
+            if (r < floatToOrdered(3.0e38f)) atomicMin(&ctr->boundsMin[tid], r);
         } else {
-            if (r > -3.0e38f) atomicMax(&ctr->boundsMax[tid - 3], floatToOrdered(r));
+            if (r > floatToOrdered(-3.0e38f)) atomicMax(&ctr->boundsMax[tid - 3], r);
         }
     }
 

@@ -11,7 +11,10 @@
 namespace axcd {
 
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
+#ifndef AXCD_SORT_ITEMS
+#define AXCD_SORT_ITEMS 16
+#endif
+constexpr int kSortItems = AXCD_SORT_ITEMS;
 constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per tile
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kRadix = 256;

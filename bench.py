@@ -231,6 +231,69 @@ def run_slab(args):
         dist.destroy_process_group()
 
 
+def measure_next_rows(w, s, stream, hbm_peak, device):
+    """Timings of the stages built on top of the hot path on the bench scene.
+    Reported beside the headline, never inside it."""
+    import numpy as np
+    import torch
+    import axcd
+    out = {}
+    # rank 2: contact manifolds of the last step (device time, CUDA events on the context stream)
+    reps = 5
+    ms = 0.0
+    for _ in range(reps):
+        w.step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        w.build_manifolds()
+        e1.record(stream)
+        st = w.stats()
+        ms += e0.elapsed_time(e1)
+    ms /= reps
+    nbytes = st.numContacts * (40 + 88)
+    out["manifolds"] = {"ms": round(ms, 4), "contacts": int(st.numContacts), "contact_points": int(st.contactPointCount),
+                        "algorithmic_bytes": int(nbytes), "achieved_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
+                        "frac_of_hbm_peak": round(nbytes / (ms * 1e-3) / 1e9 / hbm_peak, 4)}
+    # rank 4: scene queries through the blocking C ABI calls (host buffers in and out)
+    rng = np.random.default_rng(0)
+    nq = 1 << 18
+    L = float(s.xf[:, :3].max())
+    o = rng.uniform(0, L, (nq, 3)).astype(np.float32)
+    d = rng.normal(size=(nq, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros(nq, axcd.RAY_DT)
+    rays["ox"], rays["oy"], rays["oz"] = o[:, 0], o[:, 1], o[:, 2]
+    rays["dx"], rays["dy"], rays["dz"] = d[:, 0], d[:, 1], d[:, 2]
+    rays["tMax"] = 50.0
+    boxes = np.concatenate([o - 1.0, o + 1.0], axis=1)
+    w.raycast(rays[:1024])
+    t0 = time.perf_counter()
+    hits = w.raycast(rays)
+    t1 = time.perf_counter()
+    qh = w.query_aabbs(boxes)   # first call sizes the output (601 + retry is part of the public call)
+    t2 = time.perf_counter()
+    qh = w.query_aabbs(boxes)
+    t3 = time.perf_counter()
+    out["raycast"] = {"rays": nq, "t_max": 50.0, "hit_fraction": round(float((hits["body"] != axcd.NO_HIT).mean()), 4),
+                      "mrays_per_s_e2e": round(nq / (t1 - t0) / 1e6, 2)}
+    out["aabb_query"] = {"queries": nq, "hits": int(len(qh)), "mqueries_per_s_e2e": round(nq / (t3 - t2) / 1e6, 2),
+                         "first_call_ms": round(1e3 * (t2 - t1), 3)}
+    # rank 3: temporal coherence — the same scene with fat boxes; a step in which no body left its fat box
+    wc = axcd.CollisionWorld.for_scene(s, device=device, stream=stream.cuda_stream, aabbMargin=0.05,
+                                       flags=axcd.FLAG_TEMPORAL_COHERENCE, pairs_per_body=12)
+    full = wc.step()
+    skip_ms, sk = 0.0, None
+    for _ in range(reps):
+        wc.set_transforms(s.xf)
+        sk = wc.step()
+        skip_ms += sk.totalMs
+    out["temporal_coherence"] = {"margin": 0.05, "full_step_ms": round(full.totalMs, 4), "full_step_pairs": int(full.numPairs),
+                                 "cached_step_ms": round(skip_ms / reps, 4), "broadphase_skipped": int(sk.broadphaseSkipped),
+                                 "moved_bodies": int(sk.movedBodies), "contacts": int(sk.numContacts)}
+    wc.close()
+    return out
+
+
 def run_ours(args):
     if args.workload == "C4":
         return run_slab(args)
@@ -338,6 +401,11 @@ def run_ours(args):
     h2d = int(s.n) * 40
     d2h = int(st2.numContacts) * 40 + 4 + 128   # contacts + count + stats block
 
+    # ---- the SURVEY 8(f) "next" rows on the same scene (rank 0, N=1): manifolds, scene queries, coherence ---
+    next_rows = None
+    if rank == 0 and world == 1 and args.workload == "headline" and not args.no_next_rows:
+        next_rows = measure_next_rows(w, s, stream, hbm_peak, local)
+
     # ---- roofline of the dominant kernel + per-stage table -------------------------------------------
     # Algorithmic bytes per stage: what the stage must read and write once.
     n, npairs, ncon, nepa = st.numBodies, st.numPairs, st.numContacts, st.numPenetrating
@@ -411,6 +479,8 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if next_rows:
+            line["next_rows"] = next_rows
         print(json.dumps(line))
     w.close()
     if world > 1:
@@ -425,6 +495,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the manifold / query / coherence timings")
     ap.add_argument("--scale", type=float, default=0.125, help="C4 only: fraction of the 16M bodies")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -3,7 +3,7 @@
 # usage (on the GPU box): bash profiles/variant_sweep.sh A B C ...
 mkdir -p gpurun_out
 for t in "$@"; do
-  AXCD_LIB=$PWD/axiom-physics-engine_b200/variants/libaxcd_$t.so timeout 300 python bench.py --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/sweep_$t.json 2> gpurun_out/sweep_$t.err
+  AXCD_LIB=$PWD/axiom-physics-engine_b200/variants/libaxcd_$t.so timeout 300 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-next-rows > gpurun_out/sweep_$t.json 2> gpurun_out/sweep_$t.err
   python - "$t" <<'PY'
 import json,sys
 t=sys.argv[1]

@@ -234,6 +234,175 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
     }
 }
 
+// ---- TMA-pipelined refit (the default, non-coherent path) ------------------------------------------------
+// Persistent blocks walk the 256-body tiles of the scene.  One elected thread moves each tile's 10,240 B
+// of transforms global -> shared with a bulk async copy (cp.async.bulk, completion on an mbarrier) one
+// tile AHEAD of the compute, and sends each finished 6,144 B AABB tile shared -> global with a bulk
+// store, so the LSU instruction stream of the old staging loops disappears and loads, math and stores of
+// consecutive tiles overlap inside one block.  Scene bounds accumulate in registers across tiles (one
+// block reduction at the end).  The last, partial tile (and any tile whose byte count is not a multiple
+// of 16) goes through plain loads.
+#ifndef AXCD_REFIT_TMA_BLOCKS
+#define AXCD_REFIT_TMA_BLOCKS 4   // resident blocks per SM the grid is sized for
+#endif
+constexpr int kRefitTmaBlocksPerSM = AXCD_REFIT_TMA_BLOCKS;
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smemAddr(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulkLoad(void* dstShared, const void* srcGlobal, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemAddr(dstShared)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulkStore(void* dstGlobal, const void* srcShared, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(smemAddr(srcShared)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kRefitThreads, kRefitTmaBlocksPerSM)
+refitTmaKernel(const float* __restrict__ xf,        // n*10 floats (base 16B aligned)
+               const uint4* __restrict__ shapes, const float4* __restrict__ hull,
+               float* __restrict__ aabb,            // n*6 floats (base 16B aligned)
+               uint8_t* __restrict__ type8, uint32_t n, float margin, Counters* __restrict__ ctr,
+               Counters* __restrict__ ctrNext, const Counters* __restrict__ ctrInit) {
+    __shared__ __align__(128) float sIn[2][kRefitThreads * 10];
+    __shared__ __align__(128) float sOut[2][kRefitThreads * 6];
+    __shared__ __align__(8) uint64_t sBar[2];
+    __shared__ uint32_t sRed[6][kRefitThreads / 32];
+    constexpr uint32_t kInBytes = kRefitThreads * 40, kOutBytes = kRefitThreads * 24;
+    static_assert(kInBytes % 16 == 0 && kOutBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid < (int)(sizeof(Counters) / 4))
+        reinterpret_cast<uint32_t*>(ctrNext)[tid] = reinterpret_cast<const uint32_t*>(ctrInit)[tid];
+    const uint32_t fullTiles = n / kRefitThreads;
+    if (tid == 0) {
+        mbarInit(&sBar[0], 1);
+        mbarInit(&sBar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const float big = 3.0e38f;
+    float bmin[3] = {big, big, big}, bmax[3] = {-big, -big, -big};   // this thread's running bounds of box centres
+    auto accumulate = [&](V3 lo, V3 hi) {
+        const V3 c = (lo + hi) * 0.5f;   // AABB::center() (aabb.hpp:62)
+        if (fabsf(c.x) < big && fabsf(c.y) < big && fabsf(c.z) < big) {   // false for NaN
+            bmin[0] = fminf(bmin[0], c.x); bmin[1] = fminf(bmin[1], c.y); bmin[2] = fminf(bmin[2], c.z);
+            bmax[0] = fmaxf(bmax[0], c.x); bmax[1] = fmaxf(bmax[1], c.y); bmax[2] = fmaxf(bmax[2], c.z);
+        }
+    };
+
+    uint32_t tile = blockIdx.x;
+    int stage = 0;
+    uint32_t phase0 = 0, phase1 = 0;
+    if (tid == 0 && tile < fullTiles) {
+        mbarExpectTx(&sBar[0], kInBytes);
+        bulkLoad(sIn[0], xf + (size_t)tile * kRefitThreads * 10, kInBytes, &sBar[0]);
+    }
+    for (; tile < fullTiles; tile += gridDim.x) {
+        const uint32_t next = tile + gridDim.x;
+        // sIn[stage^1] was last read in the previous iteration, before its second __syncthreads
+        if (tid == 0 && next < fullTiles) {
+            mbarExpectTx(&sBar[stage ^ 1], kInBytes);
+            bulkLoad(sIn[stage ^ 1], xf + (size_t)next * kRefitThreads * 10, kInBytes, &sBar[stage ^ 1]);
+        }
+        const uint32_t body = tile * kRefitThreads + tid;
+        const uint4 sh = __ldg(shapes + body);
+        mbarWait(&sBar[stage], stage ? phase1 : phase0);
+        if (stage) phase1 ^= 1u; else phase0 ^= 1u;
+        const float2* t = reinterpret_cast<const float2*>(sIn[stage] + tid * 10);   // 40-byte record, 8-byte aligned
+        const float2 t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4];
+        V3 lo, hi;
+        fitBody(mk3(t0.x, t0.y, t1.x), make_float4(t1.y, t2.x, t2.y, t3.x), mk3(t3.y, t4.x, t4.y), sh, hull, lo, hi);
+        type8[body] = (uint8_t)sh.x;
+        if (margin != 0.0f) {   // AABB::expand(float) (aabb.hpp:156-160)
+            lo = lo - mk3(margin, margin, margin);
+            hi = hi + mk3(margin, margin, margin);
+        }
+        accumulate(lo, hi);
+        // sOut[stage] was handed to a bulk store two iterations ago: its reads must be finished
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        float2* o = reinterpret_cast<float2*>(sOut[stage] + tid * 6);               // 24-byte record, 8-byte aligned
+        o[0] = make_float2(lo.x, lo.y);
+        o[1] = make_float2(lo.z, hi.x);
+        o[2] = make_float2(hi.y, hi.z);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) bulkStore(aabb + (size_t)tile * kRefitThreads * 6, sOut[stage], kOutBytes);
+        stage ^= 1;
+    }
+    // ---- the partial last tile: plain loads and stores, one block -----------------------------------------------
+    if (blockIdx.x == fullTiles % gridDim.x) {
+        const uint32_t body = fullTiles * kRefitThreads + tid;
+        if (body < n) {
+            const float2* t = reinterpret_cast<const float2*>(xf + (size_t)body * 10);
+            const float2 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), t3 = __ldg(t + 3), t4 = __ldg(t + 4);
+            const uint4 sh = __ldg(shapes + body);
+            V3 lo, hi;
+            fitBody(mk3(t0.x, t0.y, t1.x), make_float4(t1.y, t2.x, t2.y, t3.x), mk3(t3.y, t4.x, t4.y), sh, hull, lo, hi);
+            type8[body] = (uint8_t)sh.x;
+            if (margin != 0.0f) {
+                lo = lo - mk3(margin, margin, margin);
+                hi = hi + mk3(margin, margin, margin);
+            }
+            accumulate(lo, hi);
+            float2* o = reinterpret_cast<float2*>(aabb + (size_t)body * 6);
+            o[0] = make_float2(lo.x, lo.y);
+            o[1] = make_float2(lo.z, hi.x);
+            o[2] = make_float2(hi.y, hi.z);
+        }
+    }
+    // ---- scene bounds: one block reduction, one atomic per component --------------------------------------------
+    {
+        uint32_t v[6] = {floatToOrdered(bmin[0]), floatToOrdered(bmin[1]), floatToOrdered(bmin[2]),
+                         floatToOrdered(bmax[0]), floatToOrdered(bmax[1]), floatToOrdered(bmax[2])};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = __reduce_min_sync(0xffffffffu, v[k]);
+            v[k + 3] = __reduce_max_sync(0xffffffffu, v[k + 3]);
+        }
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sRed[k][tid >> 5] = v[k];
+        }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        uint32_t r = sRed[tid][0];
+        for (int w = 1; w < kRefitThreads / 32; ++w)
+            r = (tid < 3) ? min(r, sRed[tid][w]) : max(r, sRed[tid][w]);
+        if (tid < 3) {
+            if (r < floatToOrdered(3.0e38f)) atomicMin(&ctr->boundsMin[tid], r);
+        } else {
+            if (r > floatToOrdered(-3.0e38f)) atomicMax(&ctr->boundsMax[tid - 3], r);
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the stores
+}
+
 // ---- Morton keys -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t expandBits10(uint32_t v) {   // 10 bits -> every third bit
     v &= 0x3ffu;

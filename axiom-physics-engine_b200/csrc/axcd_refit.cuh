@@ -243,9 +243,13 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
 // block reduction at the end).  The last, partial tile (and any tile whose byte count is not a multiple
 // of 16) goes through plain loads.
 #ifndef AXCD_REFIT_TMA_BLOCKS
-#define AXCD_REFIT_TMA_BLOCKS 4   // resident blocks per SM the grid is sized for
+#define AXCD_REFIT_TMA_BLOCKS 5   // resident blocks per SM the grid is sized for
 #endif
 constexpr int kRefitTmaBlocksPerSM = AXCD_REFIT_TMA_BLOCKS;
+#ifndef AXCD_REFIT_STAGES
+#define AXCD_REFIT_STAGES 2       // input tiles in flight per block (prefetch distance = stages - 1)
+#endif
+constexpr int kRefitStages = AXCD_REFIT_STAGES;
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
@@ -286,9 +290,9 @@ refitTmaKernel(const float* __restrict__ xf,        // n*10 floats (base 16B ali
                float* __restrict__ aabb,            // n*6 floats (base 16B aligned)
                uint8_t* __restrict__ type8, uint32_t n, float margin, Counters* __restrict__ ctr,
                Counters* __restrict__ ctrNext, const Counters* __restrict__ ctrInit) {
-    __shared__ __align__(128) float sIn[2][kRefitThreads * 10];
+    __shared__ __align__(128) float sIn[kRefitStages][kRefitThreads * 10];
     __shared__ __align__(128) float sOut[2][kRefitThreads * 6];
-    __shared__ __align__(8) uint64_t sBar[2];
+    __shared__ __align__(8) uint64_t sBar[kRefitStages];
     __shared__ uint32_t sRed[6][kRefitThreads / 32];
     constexpr uint32_t kInBytes = kRefitThreads * 40, kOutBytes = kRefitThreads * 24;
     static_assert(kInBytes % 16 == 0 && kOutBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -298,8 +302,7 @@ refitTmaKernel(const float* __restrict__ xf,        // n*10 floats (base 16B ali
         reinterpret_cast<uint32_t*>(ctrNext)[tid] = reinterpret_cast<const uint32_t*>(ctrInit)[tid];
     const uint32_t fullTiles = n / kRefitThreads;
     if (tid == 0) {
-        mbarInit(&sBar[0], 1);
-        mbarInit(&sBar[1], 1);
+        for (int k = 0; k < kRefitStages; ++k) mbarInit(&sBar[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -315,23 +318,29 @@ refitTmaKernel(const float* __restrict__ xf,        // n*10 floats (base 16B ali
     };
 
     uint32_t tile = blockIdx.x;
-    int stage = 0;
-    uint32_t phase0 = 0, phase1 = 0;
-    if (tid == 0 && tile < fullTiles) {
-        mbarExpectTx(&sBar[0], kInBytes);
-        bulkLoad(sIn[0], xf + (size_t)tile * kRefitThreads * 10, kInBytes, &sBar[0]);
+    int stage = 0, ostage = 0;
+    uint32_t phaseBits = 0;
+    if (tid == 0) {   // prologue: the first stages-1 tiles of this block
+        for (int k = 0; k < kRefitStages - 1; ++k) {
+            const uint32_t t = tile + (uint32_t)k * gridDim.x;
+            if (t < fullTiles) {
+                mbarExpectTx(&sBar[k], kInBytes);
+                bulkLoad(sIn[k], xf + (size_t)t * kRefitThreads * 10, kInBytes, &sBar[k]);
+            }
+        }
     }
     for (; tile < fullTiles; tile += gridDim.x) {
-        const uint32_t next = tile + gridDim.x;
-        // sIn[stage^1] was last read in the previous iteration, before its second __syncthreads
+        // prefetch into the stage consumed in the previous iteration (last read before its second __syncthreads)
+        const uint32_t next = tile + (uint32_t)(kRefitStages - 1) * gridDim.x;
+        const int pstage = (stage + kRefitStages - 1) % kRefitStages;
         if (tid == 0 && next < fullTiles) {
-            mbarExpectTx(&sBar[stage ^ 1], kInBytes);
-            bulkLoad(sIn[stage ^ 1], xf + (size_t)next * kRefitThreads * 10, kInBytes, &sBar[stage ^ 1]);
+            mbarExpectTx(&sBar[pstage], kInBytes);
+            bulkLoad(sIn[pstage], xf + (size_t)next * kRefitThreads * 10, kInBytes, &sBar[pstage]);
         }
         const uint32_t body = tile * kRefitThreads + tid;
         const uint4 sh = __ldg(shapes + body);
-        mbarWait(&sBar[stage], stage ? phase1 : phase0);
-        if (stage) phase1 ^= 1u; else phase0 ^= 1u;
+        mbarWait(&sBar[stage], (phaseBits >> stage) & 1u);
+        phaseBits ^= 1u << stage;
         const float2* t = reinterpret_cast<const float2*>(sIn[stage] + tid * 10);   // 40-byte record, 8-byte aligned
         const float2 t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4];
         V3 lo, hi;
@@ -342,17 +351,18 @@ refitTmaKernel(const float* __restrict__ xf,        // n*10 floats (base 16B ali
             hi = hi + mk3(margin, margin, margin);
         }
         accumulate(lo, hi);
-        // sOut[stage] was handed to a bulk store two iterations ago: its reads must be finished
+        // sOut[ostage] was handed to a bulk store two iterations ago: its reads must be finished
         if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncthreads();
-        float2* o = reinterpret_cast<float2*>(sOut[stage] + tid * 6);               // 24-byte record, 8-byte aligned
+        float2* o = reinterpret_cast<float2*>(sOut[ostage] + tid * 6);              // 24-byte record, 8-byte aligned
         o[0] = make_float2(lo.x, lo.y);
         o[1] = make_float2(lo.z, hi.x);
         o[2] = make_float2(hi.y, hi.z);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
         __syncthreads();
-        if (tid == 0) bulkStore(aabb + (size_t)tile * kRefitThreads * 6, sOut[stage], kOutBytes);
-        stage ^= 1;
+        if (tid == 0) bulkStore(aabb + (size_t)tile * kRefitThreads * 6, sOut[ostage], kOutBytes);
+        stage = (stage + 1) % kRefitStages;
+        ostage ^= 1;
     }
     // ---- the partial last tile: plain loads and stores, one block -----------------------------------------------
     if (blockIdx.x == fullTiles % gridDim.x) {

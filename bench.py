@@ -331,10 +331,15 @@ def run_ours(args):
     hbm_peak, peak_src = load_peaks()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    flush_rd = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+
+    flush_mode = os.environ.get("BENCH_FLUSH", "write")
 
     def flush_l2():
         with torch.cuda.stream(stream):
             flush.fill_(1)
+            if flush_mode == "write+read":   # experiment: leave the L2 full of CLEAN lines (no write-backs to pay)
+                flush_rd.sum()
 
     def barrier():
         if world > 1:

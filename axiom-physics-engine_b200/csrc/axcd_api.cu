@@ -63,7 +63,9 @@ struct AxcdContext {
     float4* dSegLo = nullptr;        // segment tree over sorted leaves, heap layout, 2*P entries
     float4* dSegHi = nullptr;
     uint32_t segP = 0;               // leaf level size (power of two >= n)
-    BvhNode* dNodes = nullptr;
+    Node32* dNodes32 = nullptr;      // compact nodes of the pair traversal (32 B per internal node)
+    BvhNode* dNodes = nullptr;       // float nodes for the scene queries: allocated and built by the first query after a broadphase
+    bool queryNodesValid = false;
     uint32_t* dWorldEnd = nullptr;
     uint2* dPairsTmp = nullptr;      // candidate pairs as found (unordered)
     uint2* dPairs = nullptr;         // candidate pairs, canonical order
@@ -249,7 +251,7 @@ void axcd_destroy(AxcdContext* ctx) {
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dType8, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dAwake, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
-                    ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes,
+                    ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes, ctx->dNodes32,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dManifolds, ctx->dQIn, ctx->dQCount, ctx->dQSeg, ctx->dQOut, ctx->dPairDist, ctx->dSortHist,
                     ctx->dSortStatus, ctx->dCtrBase, ctx->dCtrInit};
@@ -324,7 +326,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
             CU(dalloc(&ctx->dSegLo, 2 * P));
             CU(dalloc(&ctx->dSegHi, 2 * P));
         }
-        CU(dalloc(&ctx->dNodes, nb));
+        CU(dalloc(&ctx->dNodes32, nb));
         CU(dalloc(&ctx->dEpaWork, (size_t)cfg->maxContacts));
         CU(dalloc(&ctx->dEpaOverflow, (size_t)cfg->maxContacts));
         ctx->spillCap = cfg->maxContacts < 65536u ? cfg->maxContacts : 65536u;
@@ -538,13 +540,14 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
                 }
             }
         }
-        buildTopologyKernel<<<b256, 256, 0, st>>>(sKeys, n, ctx->dSegLo, ctx->dSegHi, P, ctx->dNodes);
+        buildTopologyKernel<true><<<b256, 256, 0, st>>>(sKeys, n, ctx->dSegLo, ctx->dSegHi, P, ctx->dNodes32);
+        ctx->queryNodesValid = false;
         CU(cudaGetLastError());
         recordEv(ctx, EV_BUILD);
         // ---- traversal ---------------------------------------------------------------------------
         CU(cudaMemsetAsync(ctx->dBodyCount, 0, sizeof(uint32_t) * n, st));
         const uint32_t tb = (n + kTravThreads - 1) / kTravThreads;
-        findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes,
+        findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes32, ctx->dSegLo, ctx->dSegHi,
                                                      ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
                                                      ctx->cfg.maxPairs, ctx->dBodyCount,
                                                      SlabRule{ctx->slabOn ? 1 : 0, ctx->slabLo, ctx->slabHi, ctx->dBodyKeys},
@@ -820,6 +823,17 @@ cudaError_t growScratch(void** p, size_t* cur, size_t need) {
     if (e == cudaSuccess) *cur = need;
     return e;
 }
+// The scene queries walk 64-byte float nodes; the step only builds the compact ones, so the first query
+// after a broadphase fits the float nodes from the same sorted keys and range tree (still resident).
+int ensureQueryNodes(AxcdContext* ctx) {
+    if (ctx->queryNodesValid || ctx->n < 2) return AXCD_OK;
+    if (!ctx->dNodes) CU(dalloc(&ctx->dNodes, (size_t)ctx->cfg.maxBodies));
+    buildTopologyKernel<false><<<(ctx->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->dKeys[ctx->sortedBuf], ctx->n, ctx->dSegLo,
+                                                                             ctx->dSegHi, ctx->segP, ctx->dNodes);
+    CU(cudaGetLastError());
+    ctx->queryNodesValid = true;
+    return AXCD_OK;
+}
 QueryTree queryTreeOf(const AxcdContext* ctx) {
     QueryTree T;
     T.leafLo = ctx->dSegLo + ctx->segP;
@@ -861,6 +875,10 @@ int32_t axcd_query_aabbs(AxcdContext* ctx, const float* boxes6, const uint32_t* 
     const bool useWorld = ctx->hasWorlds && queryWorld;
     if (useWorld) CU(cudaMemcpyAsync(dQW, queryWorld, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(dStatus, 0, sizeof(uint32_t) * (scanTiles + 3), st));
+    {
+        const int rc = ensureQueryNodes(ctx);
+        if (rc) return rc;
+    }
     const QueryTree T = queryTreeOf(ctx);
     const uint32_t blocks = (nq + kQueryThreads - 1) / kQueryThreads;
     queryAabbKernel<false><<<blocks, kQueryThreads, 0, st>>>(T, dBoxes, useWorld ? dQW : nullptr, nq, dCounts, nullptr, nullptr);
@@ -895,6 +913,10 @@ int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRay
     CU(growScratch(&ctx->dQIn, &ctx->qInBytes, (size_t)nq * sizeof(AxcdRay)));
     CU(growScratch(&ctx->dQOut, &ctx->qOutBytes, (size_t)nq * sizeof(AxcdRayHit)));
     CU(cudaMemcpyAsync(ctx->dQIn, rays, (size_t)nq * sizeof(AxcdRay), cudaMemcpyHostToDevice, st));
+    {
+        const int rc = ensureQueryNodes(ctx);
+        if (rc) return rc;
+    }
     const QueryTree T = queryTreeOf(ctx);
     raycastKernel<<<(nq + kQueryThreads - 1) / kQueryThreads, kQueryThreads, 0, st>>>(
         T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes, static_cast<uint32_t*>(ctx->dQOut));

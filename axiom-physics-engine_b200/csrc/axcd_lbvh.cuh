@@ -49,6 +49,67 @@ __device__ __forceinline__ int karrasDelta(const uint32_t* __restrict__ keys, in
     return x ? __clz(x) : 32 + __clz((uint32_t)i ^ (uint32_t)j);
 }
 
+// ---- compact traversal nodes -----------------------------------------------------------------------
+// The pair traversal is bound by L1TEX throughput (ncu: 80 % of peak, every visited node costs four
+// divergent 16-byte loads per lane), so the nodes it walks are 32 bytes instead of 64: both child boxes
+// quantised to 16 bits per coordinate on the grid of the scene box, plus (split | leaf flags, last).
+// `first` is not stored: the left child inherits its parent's, the right child's equals its own index.
+// The quantiser Q is ONE monotone function (subtract, multiply, floor, clamp — each monotone under
+// round-to-nearest) applied to every coordinate, min and max alike, so a.min <= b.max implies
+// Q(a.min) <= Q(b.max): the quantised test can only add candidates, never lose one, and every leaf hit
+// is confirmed with AABB::intersects on the exact leaf boxes.
+struct __align__(32) Node32 {
+    uint32_t la, lb, lc;      // left child box, packed for the SWAR overlap test (see packChild)
+    uint32_t ra, rb, rc;      // right child box
+    uint32_t split;           // bits 0..29 split, bit 30: left child is a leaf, bit 31: right child is a leaf
+    uint32_t last;
+};
+static_assert(sizeof(Node32) == 32, "Node32 must be one 32-byte record");
+constexpr uint32_t kSplitMask = 0x3fffffffu, kLeftLeaf = 1u << 30, kRightLeaf = 1u << 31;
+constexpr uint32_t kGuard = 0x80008000u;   // bit 15 of each half: the borrow guard of the SWAR compare
+constexpr float kQuantCells = 32767.0f;    // 15 bits per coordinate
+
+struct QuantFrame {
+    float s0x, s0y, s0z, ivx, ivy, ivz;
+};
+// Grid of the scene box = root of the range tree (heap index 1): 32767 cells per axis.
+__device__ __forceinline__ QuantFrame loadQuantFrame(const float4* __restrict__ segLo, const float4* __restrict__ segHi) {
+    const float4 a = __ldg(segLo + 1), b = __ldg(segHi + 1);
+    QuantFrame f;
+    f.s0x = a.x; f.s0y = a.y; f.s0z = a.z;
+    const float ex = b.x - a.x, ey = b.y - a.y, ez = b.z - a.z;
+    f.ivx = (ex > 0.0f && ex < 3.0e38f) ? kQuantCells / ex : 0.0f;   // degenerate / infinite axis: everything in cell 0
+    f.ivy = (ey > 0.0f && ey < 3.0e38f) ? kQuantCells / ey : 0.0f;
+    f.ivz = (ez > 0.0f && ez < 3.0e38f) ? kQuantCells / ez : 0.0f;
+    return f;
+}
+__device__ __forceinline__ uint32_t quantCoord(float x, float s0, float iv) {
+    const float t = floorf((x - s0) * iv);
+    return (uint32_t)fminf(fmaxf(t, 0.0f), kQuantCells);   // NaN -> 0
+}
+// A box is stored as three words of two 15-bit fields each, arranged so that the closed-interval
+// overlap test against a query box is three guarded subtractions:
+//   child:  a = min.x | min.y << 16      b = min.z | (C - max.z) << 16      c = (C - max.x) | (C - max.y) << 16
+//   query:  a = max.x | max.y << 16      b = max.z | (C - min.z) << 16      c = (C - min.x) | (C - min.y) << 16   (| guard)
+// with C = 32767.  Field by field, query >= child says: q.max >= c.min on x, y, z and c.max >= q.min on
+// z, x, y — exactly AABB::intersects on the quantised boxes.  (query | guard) - child keeps the guard
+// bit of a half iff that half of the query is >= the child's (15-bit fields cannot borrow past it).
+__device__ __forceinline__ void packChild(const QuantFrame& f, const float* b /*6*/, uint32_t& a, uint32_t& bb, uint32_t& c) {
+    const uint32_t C = (uint32_t)kQuantCells;
+    a = quantCoord(b[0], f.s0x, f.ivx) | (quantCoord(b[1], f.s0y, f.ivy) << 16);
+    bb = quantCoord(b[2], f.s0z, f.ivz) | ((C - quantCoord(b[5], f.s0z, f.ivz)) << 16);
+    c = (C - quantCoord(b[3], f.s0x, f.ivx)) | ((C - quantCoord(b[4], f.s0y, f.ivy)) << 16);
+}
+__device__ __forceinline__ void packQuery(const QuantFrame& f, const float* b /*6*/, uint32_t& a, uint32_t& bb, uint32_t& c) {
+    const uint32_t C = (uint32_t)kQuantCells;
+    a = (quantCoord(b[3], f.s0x, f.ivx) | (quantCoord(b[4], f.s0y, f.ivy) << 16)) | kGuard;
+    bb = (quantCoord(b[5], f.s0z, f.ivz) | ((C - quantCoord(b[2], f.s0z, f.ivz)) << 16)) | kGuard;
+    c = ((C - quantCoord(b[0], f.s0x, f.ivx)) | ((C - quantCoord(b[1], f.s0y, f.ivy)) << 16)) | kGuard;
+}
+__device__ __forceinline__ bool quantIntersect(uint32_t qa, uint32_t qb, uint32_t qc, uint32_t ca, uint32_t cb, uint32_t cc) {
+    return (((qa - ca) & (qb - cb) & (qc - cc)) & kGuard) == kGuard;
+}
+
 // ---- boxes of aligned leaf ranges (segment tree over the Morton-sorted leaves) --------------------
 // Heap layout over P = 2^k >= n leaves: node h covers the leaves of its subtree, leaves live at
 // [P, 2P) (slots >= n hold empty boxes), parents of h are h >> 1.  Any sorted range [l, r] is then the
@@ -152,8 +213,11 @@ __device__ __forceinline__ void segQuery(const float4* __restrict__ lo, const fl
 
 // One thread per internal node i in [0, n-1): finds its leaf range and split (Karras 2012), then
 // fits both children's boxes with two range queries and writes the finished 64-byte node.
+// COMPACT = true writes the 32-byte quantised nodes the pair traversal walks; false writes the 64-byte
+// float nodes the scene queries use (built on demand by the first query after a broadphase).
+template <bool COMPACT>
 __global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t n, const float4* __restrict__ segLo,
-                                    const float4* __restrict__ segHi, uint32_t P, BvhNode* __restrict__ nodes) {
+                                    const float4* __restrict__ segHi, uint32_t P, void* __restrict__ nodesOut) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = (int)n;
     if (i >= N - 1) return;
@@ -177,11 +241,22 @@ __global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t 
     float L[6], R[6];
     segQuery(segLo, segHi, P, (uint32_t)first, (uint32_t)gamma, L);
     segQuery(segLo, segHi, P, (uint32_t)gamma + 1u, (uint32_t)last, R);
-    float4* o = reinterpret_cast<float4*>(nodes + i);
-    o[0] = make_float4(L[0], L[1], L[2], L[3]);
-    o[1] = make_float4(L[4], L[5], R[0], R[1]);
-    o[2] = make_float4(R[2], R[3], R[4], R[5]);
-    reinterpret_cast<uint4*>(o)[3] = make_uint4((uint32_t)first, (uint32_t)gamma, (uint32_t)last, 0u);
+    if (COMPACT) {
+        const QuantFrame f = loadQuantFrame(segLo, segHi);
+        uint32_t a0, a1, a2, b0, b1, b2;
+        packChild(f, L, a0, a1, a2);
+        packChild(f, R, b0, b1, b2);
+        const uint32_t sp = (uint32_t)gamma | (first == gamma ? kLeftLeaf : 0u) | (gamma + 1 == last ? kRightLeaf : 0u);
+        uint4* o = reinterpret_cast<uint4*>(static_cast<Node32*>(nodesOut) + i);
+        o[0] = make_uint4(a0, a1, a2, b0);
+        o[1] = make_uint4(b1, b2, sp, (uint32_t)last);
+    } else {
+        float4* o = reinterpret_cast<float4*>(static_cast<BvhNode*>(nodesOut) + i);
+        o[0] = make_float4(L[0], L[1], L[2], L[3]);
+        o[1] = make_float4(L[4], L[5], R[0], R[1]);
+        o[2] = make_float4(R[2], R[3], R[4], R[5]);
+        reinterpret_cast<uint4*>(o)[3] = make_uint4((uint32_t)first, (uint32_t)gamma, (uint32_t)last, 0u);
+    }
 }
 
 // ---- traversal ------------------------------------------------------------------------------------
@@ -220,7 +295,8 @@ struct SlabRule {
 // pairs of every body a in bodyCount[a] for the counting sort that follows (orderPairs*).
 __global__ void __launch_bounds__(kTravThreads)
 findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ leafHi,
-                const BvhNode* __restrict__ nodes, const uint32_t* __restrict__ worldEnd, uint32_t n,
+                const Node32* __restrict__ nodes, const float4* __restrict__ segLo, const float4* __restrict__ segHi,
+                const uint32_t* __restrict__ worldEnd, uint32_t n,
                 uint2* __restrict__ pairs, uint32_t maxPairs, uint32_t* __restrict__ bodyCount,
                 SlabRule slab, const uint4* __restrict__ filters, const uint8_t* __restrict__ awake,
                 Counters* __restrict__ ctr) {
@@ -234,36 +310,47 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
         const float4 lo = leafLo[i], hi = leafHi[i];
         const uint32_t bodyI = __float_as_uint(lo.w);
         const uint32_t wEnd = worldEnd ? worldEnd[__float_as_uint(hi.w)] : n - 1;
-        // The node to visit next is carried in a register; the stack (local memory) only holds the
-        // second child when both are internal, so a plain descent never round-trips through it.
+        uint32_t qxy, qzX, qYZ;
+        {
+            const QuantFrame f = loadQuantFrame(segLo, segHi);
+            const float b[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+            packQuery(f, b, qxy, qzX, qYZ);
+        }
+        // The node to visit next is carried in registers (index and the first leaf of its range); the
+        // stack (local memory) only ever holds right children, whose first leaf equals their index, so a
+        // plain descent never round-trips through it.
         constexpr uint32_t kNone = 0xffffffffu;
         uint32_t stack[kTravStack];
         int sp = 0;
-        uint32_t ni = 0;
+        uint32_t ni = 0, first = 0;
         while (true) {
-            const float4* np = reinterpret_cast<const float4*>(nodes + ni);
-            const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-            const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(np) + 3);
-            const uint32_t first = q3.x, split = q3.y, last = q3.z;
+            const uint4* np = reinterpret_cast<const uint4*>(nodes + ni);
+            const uint4 q0 = __ldg(np), q1 = __ldg(np + 1);
+            const uint32_t split = q1.z & kSplitMask, last = q1.w;
             // left child: sorted leaves [first, split]
-            const bool hitL = split > i && first <= wEnd &&
-                              boxesIntersect(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y);
+            const bool hitL = split > i && first <= wEnd && quantIntersect(qxy, qzX, qYZ, q0.x, q0.y, q0.z);
             // right child: sorted leaves [split+1, last]
-            const bool hitR = last > i && split + 1 <= wEnd &&
-                              boxesIntersect(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
-            uint32_t next = kNone;
+            const bool hitR = last > i && split + 1 <= wEnd && quantIntersect(qxy, qzX, qYZ, q0.w, q1.x, q1.y);
+            uint32_t next = kNone, nextFirst = 0;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const bool hit = c ? hitR : hitL;
                 if (!hit) continue;
-                const bool leaf = c ? (split + 1 == last) : (first == split);
+                const bool leaf = (q1.z & (c ? kRightLeaf : kLeftLeaf)) != 0u;
                 const uint32_t child = c ? split + 1 : split;
                 if (!leaf) {
-                    if (next == kNone) next = child;
-                    else if (sp < kTravStack) stack[sp++] = child;
+                    if (next == kNone) {
+                        next = child;
+                        nextFirst = c ? child : first;
+                    } else if (sp < kTravStack) {
+                        stack[sp++] = child;   // c == 1 here: a right child
+                    }
                     continue;
                 }
-                const uint32_t bodyJ = __float_as_uint(__ldg(&leafLo[child].w));
+                // exact test on the leaf's own box (AABB::intersects, closed intervals)
+                const float4 jl = __ldg(leafLo + child), jh = __ldg(leafHi + child);
+                if (!boxesIntersect(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, jl.x, jl.y, jl.z, jh.x, jh.y, jh.z)) continue;
+                const uint32_t bodyJ = __float_as_uint(jl.w);
                 uint2 pr = make_uint2(min(bodyI, bodyJ), max(bodyI, bodyJ));
                 if (filters && !shouldCollide(filters, bodyI, bodyJ)) continue;
                 // sleeping bodies (debug::DebugRigidBody::isAwake, physics_debug_draw.hpp:123): a pair of
@@ -274,8 +361,7 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                     // of the pair's x-overlap, max(min_i.x, min_j.x), lies in its slab (exactly one rank
                     // does), and orients it by global id so both bodies play the same role as in a
                     // single-GPU run
-                    const float jx = c ? q1.z : q0.x;   // min.x of the leaf child, as stored in the node
-                    const float xs = (lo.x > jx) ? lo.x : jx;
+                    const float xs = (lo.x > jl.x) ? lo.x : jl.x;
                     if (!(xs >= slab.lo && xs < slab.hi)) continue;
                     if (slab.keys[pr.x] > slab.keys[pr.y]) pr = make_uint2(pr.y, pr.x);
                 }
@@ -290,9 +376,15 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                     }
                 }
             }
-            if (next != kNone) ni = next;
-            else if (sp > 0) ni = stack[--sp];
-            else break;
+            if (next != kNone) {
+                ni = next;
+                first = nextFirst;
+            } else if (sp > 0) {
+                ni = stack[--sp];
+                first = ni;
+            } else {
+                break;
+            }
         }
     }
     __syncthreads();

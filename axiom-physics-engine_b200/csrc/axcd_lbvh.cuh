@@ -261,7 +261,7 @@ __global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t 
 
 // ---- traversal ------------------------------------------------------------------------------------
 #ifndef AXCD_TRAV_THREADS
-#define AXCD_TRAV_THREADS 64
+#define AXCD_TRAV_THREADS 128
 #endif
 #ifndef AXCD_TRAV_POOL
 #define AXCD_TRAV_POOL 1024
@@ -269,6 +269,9 @@ __global__ void buildTopologyKernel(const uint32_t* __restrict__ keys, uint32_t 
 constexpr int kTravThreads = AXCD_TRAV_THREADS;
 constexpr int kTravPool = AXCD_TRAV_POOL;   // pairs staged per block before the coalesced flush
 constexpr int kTravStack = 64;
+#ifndef AXCD_TRAV_WIDE
+#define AXCD_TRAV_WIDE 1   // 1: two nodes in flight per thread (0: one)
+#endif
 
 // AABB::intersects (aabb.hpp:132-135): closed intervals, any NaN -> false
 __device__ __forceinline__ bool boxesIntersect(float ax0, float ay0, float az0, float ax1, float ay1, float az1,
@@ -316,6 +319,89 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
             const float b[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
             packQuery(f, b, qxy, qzX, qYZ);
         }
+#if AXCD_TRAV_WIDE
+        // Two nodes in flight per thread: the node carried in registers plus one popped from the stack are
+        // loaded together, so two of the dependent L2 round trips of a walk overlap (the order in which
+        // nodes are visited does not change the pair set).  Stack entries carry (node, first leaf).
+        constexpr uint32_t kNone = 0xffffffffu;
+        uint32_t stackN[kTravStack], stackF[kTravStack];
+        int sp = 0;
+        uint32_t ni = 0, first = 0;
+        while (true) {
+            const bool haveB = sp > 0;
+            uint32_t nb = ni, firstB = first;
+            if (haveB) {
+                --sp;
+                nb = stackN[sp];
+                firstB = stackF[sp];
+            }
+            const uint4* npA = reinterpret_cast<const uint4*>(nodes + ni);
+            const uint4* npB = reinterpret_cast<const uint4*>(nodes + nb);
+            const uint4 a0 = __ldg(npA), a1 = __ldg(npA + 1);
+            const uint4 b0 = __ldg(npB), b1 = __ldg(npB + 1);
+            uint32_t next = kNone, nextFirst = 0;
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                if (which == 1 && !haveB) break;
+                const uint4 q0 = which ? b0 : a0, q1 = which ? b1 : a1;
+                const uint32_t fst = which ? firstB : first;
+                const uint32_t split = q1.z & kSplitMask, last = q1.w;
+                const bool hitL = split > i && fst <= wEnd && quantIntersect(qxy, qzX, qYZ, q0.x, q0.y, q0.z);
+                const bool hitR = last > i && split + 1 <= wEnd && quantIntersect(qxy, qzX, qYZ, q0.w, q1.x, q1.y);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const bool hit = c ? hitR : hitL;
+                    if (!hit) continue;
+                    const bool leaf = (q1.z & (c ? kRightLeaf : kLeftLeaf)) != 0u;
+                    const uint32_t child = c ? split + 1 : split;
+                    if (!leaf) {
+                        const uint32_t cf = c ? child : fst;
+                        if (next == kNone) {
+                            next = child;
+                            nextFirst = cf;
+                        } else if (sp < kTravStack) {
+                            stackN[sp] = child;
+                            stackF[sp] = cf;
+                            ++sp;
+                        }
+                        continue;
+                    }
+                    const float4 jl = __ldg(leafLo + child), jh = __ldg(leafHi + child);
+                    if (!boxesIntersect(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, jl.x, jl.y, jl.z, jh.x, jh.y, jh.z)) continue;
+                    const uint32_t bodyJ = __float_as_uint(jl.w);
+                    uint2 pr = make_uint2(min(bodyI, bodyJ), max(bodyI, bodyJ));
+                    if (filters && !shouldCollide(filters, bodyI, bodyJ)) continue;
+                    if (awake && !(__ldg(awake + bodyI) | __ldg(awake + bodyJ))) continue;
+                    if (slab.enabled) {
+                        const float xs = (lo.x > jl.x) ? lo.x : jl.x;
+                        if (!(xs >= slab.lo && xs < slab.hi)) continue;
+                        if (slab.keys[pr.x] > slab.keys[pr.y]) pr = make_uint2(pr.y, pr.x);
+                    }
+                    const uint32_t slot = atomicAdd(&sCount, 1u);
+                    if (slot < kTravPool) {
+                        sPool[slot] = pr;
+                    } else {
+                        const uint32_t g = atomicAdd(&ctr->pairCount, 1u);
+                        if (g < maxPairs) {
+                            pairs[g] = pr;
+                            atomicAdd(&bodyCount[pr.x], 1u);
+                        }
+                    }
+                }
+            }
+            if (next != kNone) {
+                ni = next;
+                first = nextFirst;
+            } else if (sp > 0) {
+                --sp;
+                ni = stackN[sp];
+                first = stackF[sp];
+            } else {
+                break;
+            }
+        }
+    }
+#else
         // The node to visit next is carried in registers (index and the first leaf of its range); the
         // stack (local memory) only ever holds right children, whose first leaf equals their index, so a
         // plain descent never round-trips through it.
@@ -387,6 +473,7 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
             }
         }
     }
+#endif
     __syncthreads();
     const uint32_t cnt = min(sCount, (uint32_t)kTravPool);
     if (threadIdx.x == 0 && cnt) sBase = atomicAdd(&ctr->pairCount, cnt);

@@ -20,7 +20,7 @@ for r in rows:
     if r[-2] == 'ns':
         val /= 1000
     agg.setdefault(name, []).append(val)
-steps = len(agg.get('axcd::refitKernel', [1]))
+steps = len(agg.get('axcd::refitTmaKernel', agg.get('axcd::refitKernel', [1])))
 tot = sum(sum(v) for k, v in agg.items() if 'at::' not in k)
 launch_tbl = ["| kernel | launches/step | avg us | us/step | share |", "|---|---|---|---|---|"]
 for k, v in agg.items():
@@ -98,7 +98,7 @@ Shares agree with the CUDA-event stage times above.
 """
 open(out_md, 'w').write(md)
 traffic = {k + "_dram_bytes_per_launch": (float(v['dram__bytes_read.sum']) + float(v['dram__bytes_write.sum'])) * 1e6
-           for k, v in data.items() if k in ('epaKernel', 'gjkKernel', 'findPairsKernel', 'refitKernel')}
+           for k, v in data.items() if k in ('epaKernel', 'gjkKernel', 'findPairsKernel', 'refitTmaKernel', 'manifoldKernel')}
 traffic["source"] = out_md
 json.dump(traffic, open(out_md.replace('_ncu_summary.md', '_traffic.json'), 'w'), indent=1)
 print(md[:1500])

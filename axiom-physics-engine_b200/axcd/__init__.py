@@ -34,6 +34,8 @@ RAY_DT = np.dtype([("ox", "<f4"), ("oy", "<f4"), ("oz", "<f4"), ("dx", "<f4"), (
 RAYHIT_DT = np.dtype([("body", "<u4"), ("t", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
                       ("flags", "<u4")])
 NO_HIT = 0xFFFFFFFF
+SWEEP_DT = np.dtype([("hit", "<u4"), ("toi", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                     ("iterations", "<u4")])
 
 # every symbol include/axcd.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
@@ -41,7 +43,7 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
-    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake",
+    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs",
     "axcd_set_filters", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
     "axcd_set_ghosts_device",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
@@ -112,7 +114,7 @@ def load_library():
                      "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
                      "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
                      "axcd_pack_ghosts", "axcd_set_ghosts_device", "axcd_set_filters",
-                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake"):
+                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -130,6 +132,7 @@ def load_library():
         lib.axcd_query_aabbs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                          C.c_void_p]
         lib.axcd_set_awake.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        lib.axcd_ccd_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.axcd_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.axcd_test_sort_pairs32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                C.c_uint32]
@@ -436,6 +439,16 @@ class CollisionWorld:
         out = np.zeros(max(1, len(rays)), RAYHIT_DT)
         self._check(self._lib.axcd_raycast(self._ctx, _ptr(rays), len(rays), _ptr(out)), "axcd_raycast")
         return out[:len(rays)]
+
+    def ccd_pairs(self, pairs, displacement):
+        """Time of impact of body pairs under linear motion; displacement is (n,3) per body."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        disp = np.ascontiguousarray(displacement, dtype=np.float32).reshape(-1, 3)
+        assert len(disp) == self.n
+        out = np.zeros(max(1, len(pairs)), SWEEP_DT)
+        self._check(self._lib.axcd_ccd_pairs(self._ctx, _ptr(pairs), len(pairs), _ptr(disp), _ptr(out)),
+                    "axcd_ccd_pairs")
+        return out[:len(pairs)]
 
     def set_awake(self, awake):
         """awake: (n,) array, 0 = sleeping; None switches the rule off.  Sleeping-sleeping pairs are dropped."""

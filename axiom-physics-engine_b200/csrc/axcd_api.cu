@@ -13,6 +13,7 @@
 #include "axcd_narrow.cuh"
 #include "axcd_manifold.cuh"
 #include "axcd_query.cuh"
+#include "axcd_ccd.cuh"
 #include "axcd_refit.cuh"
 #include "axcd_sort.cuh"
 
@@ -922,6 +923,39 @@ int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRay
         T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes, static_cast<uint32_t*>(ctx->dQOut));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(outHits, ctx->dQOut, (size_t)nq * sizeof(AxcdRayHit), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AXCD_OK;
+}
+
+int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs, const float* displacement3,
+                       AxcdSweep* out) {
+    if (!ctx || (npairs && (!pairs2 || !displacement3 || !out))) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;
+    if (npairs == 0) return AXCD_OK;
+    if (npairs > (1u << 28)) return AXCD_ERR_OUT_OF_RANGE;
+    for (uint32_t k = 0; k < 2 * npairs; ++k)
+        if (pairs2[k] >= ctx->n) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    // scratch: pairs | displacements in dQIn, results in dQOut
+    const size_t pairBytes = ((size_t)npairs * 8 + 15) & ~(size_t)15;
+    CU(growScratch(&ctx->dQIn, &ctx->qInBytes, pairBytes + (size_t)ctx->n * 12));
+    CU(growScratch(&ctx->dQOut, &ctx->qOutBytes, (size_t)npairs * sizeof(AxcdSweep)));
+    uint2* dPairs = static_cast<uint2*>(ctx->dQIn);
+    float* dDisp = reinterpret_cast<float*>(static_cast<char*>(ctx->dQIn) + pairBytes);
+    CU(cudaMemcpyAsync(dPairs, pairs2, (size_t)npairs * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dDisp, displacement3, (size_t)ctx->n * 12, cudaMemcpyHostToDevice, st));
+    NarrowParams p;
+    p.gjkMaxIters = ctx->cfg.gjkMaxIters;
+    p.epaMaxIters = ctx->cfg.epaMaxIters;
+    p.epaMaxFaces = ctx->cfg.epaMaxFaces;
+    p.gjkTol = ctx->cfg.gjkTol;
+    p.epaTol = ctx->cfg.epaTol;
+    p.wantDistances = 1u;
+    ccdKernel<<<(npairs + kCcdThreads - 1) / kCcdThreads, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull,
+                                                                               dDisp, p, static_cast<uint32_t*>(ctx->dQOut));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, ctx->dQOut, (size_t)npairs * sizeof(AxcdSweep), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return AXCD_OK;
 }

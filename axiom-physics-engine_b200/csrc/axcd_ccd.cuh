@@ -1,0 +1,72 @@
+// GJK-based continuous collision detection ("GJK-based CCD", reference:
+// CLAUDE.md:136): time of impact of body pairs under LINEAR motion by conservative advancement.  B moves
+// by D = dispB - dispA relative to A over t in [0,1]; each step runs the exact GJK distance (cores minus
+// radii); gap / (approach speed along the closest direction) is a lower bound of the time to contact for
+// convex shapes, so t advances by it until the gap is <= tol (hit), the shapes move apart, or t > 1.
+// One thread per pair; same expression trees as the CPU oracle.
+#pragma once
+
+#include "axcd_narrow.cuh"
+
+namespace axcd {
+
+constexpr float kCcdTol = 1e-4f;
+constexpr int kCcdMaxIters = 48;
+constexpr int kCcdThreads = 64;
+
+__global__ void __launch_bounds__(kCcdThreads)
+ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restrict__ xf, const uint4* __restrict__ shapes,
+          const float4* __restrict__ hull, const float* __restrict__ disp, NarrowParams cfg, uint32_t* __restrict__ out) {
+    const uint32_t k = blockIdx.x * kCcdThreads + threadIdx.x;
+    if (k >= npairs) return;
+    cfg.wantDistances = 1u;
+    const uint2 pr = __ldg(pairs + k);
+    const BodyPose ta = loadPose(xf, pr.x), tb = loadPose(xf, pr.y);
+    const V3 origin = ta.p;
+    const Core A = makeCore(ta, __ldg(shapes + pr.x), hull, origin);
+    Core B = makeCore(tb, __ldg(shapes + pr.y), hull, origin);
+    const V3 c0 = B.c;
+    const V3 dA = mk3(__ldg(disp + 3 * (size_t)pr.x), __ldg(disp + 3 * (size_t)pr.x + 1), __ldg(disp + 3 * (size_t)pr.x + 2));
+    const V3 dB = mk3(__ldg(disp + 3 * (size_t)pr.y), __ldg(disp + 3 * (size_t)pr.y + 1), __ldg(disp + 3 * (size_t)pr.y + 2));
+    const V3 D = dB - dA;
+    const float rs = A.r + B.r;
+    uint32_t hit = 0u;
+    float toi = 1.0f;
+    V3 nOut = mk3(0.f, 0.f, 0.f), nLast = nOut;
+    float t = 0.0f;
+    int it = 0;
+    for (; it < kCcdMaxIters; ++it) {
+        B.c = c0 + D * t;
+        Simplex s;
+        const GjkResult g = gjk(A, B, cfg, rs, s);
+        if (g.state == GJK_OVERLAP) {   // cores touch at t: the normal is the last closest direction (zero at t = 0)
+            hit = 1u;
+            toi = t;
+            nOut = nLast;
+            break;
+        }
+        const float dist = sqrtf(g.vv);
+        const float gap = dist - rs;
+        const V3 n = -(g.v * (1.0f / dist));   // from a to b
+        nLast = n;
+        if (gap <= kCcdTol) {
+            hit = 1u;
+            toi = t;
+            nOut = n;
+            break;
+        }
+        const float approach = dot3(D, g.v) / dist;   // speed at which B closes in along the closest direction
+        if (!(approach > 0.0f)) break;                // moving apart or sliding past
+        t = t + gap / approach;
+        if (!(t <= 1.0f)) break;
+    }
+    uint32_t* o = out + (size_t)k * 6;
+    o[0] = hit;
+    o[1] = __float_as_uint(toi);
+    o[2] = __float_as_uint(nOut.x);
+    o[3] = __float_as_uint(nOut.y);
+    o[4] = __float_as_uint(nOut.z);
+    o[5] = (uint32_t)it;
+}
+
+}  // namespace axcd

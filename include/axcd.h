@@ -226,6 +226,21 @@ typedef struct AxcdRayHit {
 } AxcdRayHit;
 AXCD_API int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRayHit* outHits);
 
+/* GJK-based continuous collision detection ("GJK-based CCD", reference: CLAUDE.md:136): time of impact of
+ * the given body pairs under LINEAR motion over one step.  displacement3 holds one (dx,dy,dz) per body
+ * (n x 3 floats: velocity * dt); rotations stay fixed during the sweep.  Conservative advancement on the
+ * exact GJK distance: toi in [0,1] is the first parameter at which the surfaces come within 1e-4 of each
+ * other (hit = 1), normal points from a to b along the closest direction (zero if the pair already overlaps at t = 0);
+ * hit = 0, toi = 1 when they do not meet during the step.  Needs shapes and transforms only.  Blocking. */
+typedef struct AxcdSweep {
+    uint32_t hit;
+    float toi;
+    float nx, ny, nz;
+    uint32_t iterations;   /* conservative-advancement steps taken */
+} AxcdSweep;
+AXCD_API int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs,
+                                const float* displacement3, AxcdSweep* out);
+
 /* Collision filtering, gui::FilterInfo semantics (include/axiom/gui/body_inspector.hpp:38-42):
  * two bodies with the same non-zero groupIndex collide iff it is positive; otherwise both
  * (maskBits & other.categoryBits) must be non-zero.  Applied when candidate pairs are emitted.

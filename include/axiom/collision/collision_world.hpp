@@ -84,6 +84,7 @@ using ContactPoint = AxcdContact;   // debug::DebugContactPoint + pair ids (phys
 using ContactManifold = AxcdManifold;   // 1..4 DebugContactPoints sharing one normal
 using Ray = AxcdRay;
 using RayHit = AxcdRayHit;
+using Sweep = AxcdSweep;
 struct BodyPair { std::uint32_t a, b; };
 struct QueryHit { std::uint32_t query, body; };
 
@@ -171,6 +172,12 @@ public:
     }
     core::Result<void> rayCast(const Ray* rays, std::uint32_t count, RayHit* outHits) {
         return wrap(axcd_raycast(ctx_, rays, count, outHits));
+    }
+    /// GJK-based CCD: time of impact of body pairs under linear motion (displacements: bodyCount() x 3 floats).
+    core::Result<void> sweepPairs(const BodyPair* pairs, std::uint32_t count, const math::Vec3* displacements,
+                                  Sweep* out) {
+        return wrap(axcd_ccd_pairs(ctx_, reinterpret_cast<const std::uint32_t*>(pairs), count,
+                                   reinterpret_cast<const float*>(displacements), out));
     }
     std::uint32_t bodyCount() const noexcept { return bodyCount_; }
 

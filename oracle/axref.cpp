@@ -1212,6 +1212,58 @@ ShapeHit rayShape(V3 o, V3 d, float tMax, const Xf& t, const AxrefShape& sh) {
     return h;   // hulls are answered at AABB level by the caller
 }
 
+
+// ------------------------------------------------------------------------------------------
+// GJK-based continuous collision detection ("GJK-based CCD", CLAUDE.md:136): time of
+// impact of a pair under LINEAR motion by conservative advancement.  B moves by D = dispB - dispA relative
+// to A over t in [0,1]; at each step the exact GJK distance (cores minus radii) gives a gap and the
+// closest direction, gap / (approach speed along it) is a lower bound of the time to contact for convex
+// shapes, and t advances by it until the gap is <= tol (hit), the shapes move apart, or t > 1 (miss).
+// ------------------------------------------------------------------------------------------
+const float CCD_TOL = 1e-4f;
+const int CCD_MAX_ITERS = 48;
+void sweepPair(const Xf& ta, const AxrefShape& sa, V3 dispA, const Xf& tb, const AxrefShape& sb, V3 dispB,
+               const float* hull, const AxrefNarrowCfg& cfgIn, AxrefSweep& out) {
+    AxrefNarrowCfg cfg = cfgIn;
+    cfg.wantDistances = 1;
+    const V3 origin = ta.p;
+    const Core A = makeCore(ta, sa, hull, origin);
+    Core B = makeCore(tb, sb, hull, origin);
+    const V3 c0 = B.c;
+    const V3 D = dispB - dispA;
+    const float rs = A.r + B.r;
+    out = AxrefSweep{0u, 1.0f, 0.0f, 0.0f, 0.0f, 0u};
+    float t = 0.0f;
+    V3 nLast = mk(0.0f, 0.0f, 0.0f);
+    int it = 0;
+    for (; it < CCD_MAX_ITERS; ++it) {
+        B.c = c0 + D * t;
+        Simplex s;
+        const GjkResult g = gjk(A, B, cfg, rs, s);
+        if (g.state == GJK_OVERLAP) {   // cores touch at t: the normal is the last closest direction (zero at t = 0)
+            out.hit = 1u;
+            out.toi = t;
+            out.nx = nLast.x; out.ny = nLast.y; out.nz = nLast.z;
+            break;
+        }
+        const float dist = std::sqrt(g.vv);
+        const float gap = dist - rs;
+        const V3 n = -(g.v * (1.0f / dist));   // from a to b
+        nLast = n;
+        if (gap <= CCD_TOL) {
+            out.hit = 1u;
+            out.toi = t;
+            out.nx = n.x; out.ny = n.y; out.nz = n.z;
+            break;
+        }
+        const float approach = dot(D, g.v) / dist;   // speed at which B closes in along the closest direction
+        if (!(approach > 0.0f)) break;               // moving apart or sliding past
+        t = t + gap / approach;
+        if (!(t <= 1.0f)) break;
+    }
+    out.iterations = (uint32_t)it;
+}
+
 }   // namespace
 
 // =============================================================================================
@@ -1539,6 +1591,29 @@ int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* aa
             out[q] = best;
         }
     });
+    return 0;
+}
+
+
+int32_t axref_ccd_pairs(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                        const uint32_t* pairs, uint64_t npairs, const float* disp, const AxrefNarrowCfg* cfg,
+                        AxrefSweep* out, int nthreads) {
+    if (!cfg || (npairs && (!pairs || !disp || !out))) return 202;
+    std::vector<int> err((size_t)std::max(1, nthreads), 0);
+    parallelFor(npairs, nthreads, [&](int t, uint64_t lo, uint64_t hi) {
+        for (uint64_t k = lo; k < hi; ++k) {
+            const uint32_t a = pairs[2 * k], b = pairs[2 * k + 1];
+            if (a >= n || b >= n) {
+                err[(size_t)t] = 601;
+                continue;
+            }
+            sweepPair(loadXf(xf + 10ull * a), shapes[a], mk(disp[3ull * a], disp[3ull * a + 1], disp[3ull * a + 2]),
+                      loadXf(xf + 10ull * b), shapes[b], mk(disp[3ull * b], disp[3ull * b + 1], disp[3ull * b + 2]),
+                      hullXYZ, *cfg, out[k]);
+        }
+    });
+    for (int e : err)
+        if (e) return e;
     return 0;
 }
 

@@ -83,6 +83,13 @@ int32_t axref_query_aabbs(const float* aabb, uint32_t n, const uint32_t* worldId
 int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* aabb, uint32_t n,
                       const uint32_t* worldId, const AxrefRay* rays, uint32_t nq, AxrefRayHit* out, int nthreads);
 
+/* GJK-based CCD: time of impact of the given pairs under linear motion (disp = n x 3 displacements over
+ * the step), conservative advancement on the exact GJK distance.  == AxcdSweep.                  */
+typedef struct AxrefSweep { uint32_t hit; float toi, nx, ny, nz; uint32_t iterations; } AxrefSweep;
+int32_t axref_ccd_pairs(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                        const uint32_t* pairs, uint64_t npairs, const float* disp, const AxrefNarrowCfg* cfg,
+                        AxrefSweep* out, int nthreads);
+
 /* one pair, for closed-form checks: returns 1 if contact. dist = core GJK distance minus radii
  * (<= 0 for contacts; exact only when cfg->wantDistances).                                    */
 int32_t axref_collide_pair(const float xfA[10], const AxrefShape* sa, const float xfB[10],

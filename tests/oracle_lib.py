@@ -22,6 +22,8 @@ RAY_DT = np.dtype([("ox", "<f4"), ("oy", "<f4"), ("oz", "<f4"), ("dx", "<f4"), (
 RAYHIT_DT = np.dtype([("body", "<u4"), ("t", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
                       ("flags", "<u4")])
 NO_HIT = 0xFFFFFFFF
+SWEEP_DT = np.dtype([("hit", "<u4"), ("toi", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
+                     ("iterations", "<u4")])
 
 
 class NarrowCfg(C.Structure):
@@ -57,6 +59,7 @@ def lib():
         _LIB.axref_manifolds.restype = C.c_int32
         _LIB.axref_query_aabbs.restype = C.c_int32
         _LIB.axref_raycast.restype = C.c_int32
+        _LIB.axref_ccd_pairs.restype = C.c_int32
         _LIB.axref_aabb_intersects.restype = C.c_int
     return _LIB
 
@@ -218,6 +221,21 @@ def raycast(xf, shapes, aabb, rays, world_id=None, nthreads=8):
                              C.c_uint32(len(rays)), _p(out), C.c_int(nthreads))
     assert rc == 0, rc
     return out[:len(rays)].copy()
+
+
+def ccd_pairs(xf, shapes, pairs, disp, hull=None, cfg=None, nthreads=8):
+    xf = f32(xf).reshape(-1, 10)
+    shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
+    hull = f32(hull if hull is not None else np.zeros((0, 3))).reshape(-1, 3)
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+    disp = f32(disp).reshape(-1, 3)
+    assert len(disp) == len(xf)
+    cfg = cfg or default_cfg(True)
+    out = np.zeros(max(1, len(pairs)), SWEEP_DT)
+    rc = lib().axref_ccd_pairs(_p(xf), _p(shapes), C.c_uint32(len(xf)), _p(hull), _p(pairs), C.c_uint64(len(pairs)),
+                               _p(disp), C.byref(cfg), _p(out), C.c_int(nthreads))
+    assert rc == 0, rc
+    return out[:len(pairs)].copy()
 
 
 def collide_pair(xfa, sa, xfb, sb, hull=None, cfg=None, want_distances=True):

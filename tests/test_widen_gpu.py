@@ -286,3 +286,30 @@ def test_sleeping_pairs_are_dropped():
     w.step()
     assert np.array_equal(w.pairs(), allp)
     w.close()
+
+
+# ------------------------------------------------------------------ GJK-based CCD (rank 4) ---------
+def test_ccd_pairs_match_oracle():
+    s, L = _query_scene(n=20000, seed=31, L=40.0)           # sparse: most pairs start separated
+    rng = np.random.default_rng(6)
+    w = axcd.CollisionWorld.for_scene(s)
+    perm = rng.permutation(s.n).astype(np.uint32)             # every body in exactly one pair
+    npairs = s.n // 2
+    a, b = perm[:npairs], perm[npairs:]
+    pairs = np.stack([a, b], axis=1).astype(np.uint32)
+    # aim b at a with scatter, so that roughly half the sweeps hit
+    aim = s.xf[a, :3] - s.xf[b, :3]
+    disp = rng.normal(size=(s.n, 3)).astype(np.float32) * 0.05
+    disp[b] = (aim * rng.uniform(0.8, 1.6, (npairs, 1)) + rng.normal(size=(npairs, 3)) * 0.3).astype(np.float32)
+    got = w.ccd_pairs(pairs, disp)
+    exp = O.ccd_pairs(s.xf, s.shapes, pairs, disp, s.hull)
+    assert np.array_equal(got["hit"], exp["hit"])                      # bit-exact decisions
+    assert np.array_equal(got["iterations"], exp["iterations"])
+    for f in ("toi", "nx", "ny", "nz"):
+        np.testing.assert_allclose(got[f], exp[f], rtol=REL, atol=REL * 1e-2)
+    assert got.tobytes() == exp.tobytes()
+    assert 0.15 < got["hit"].mean() < 0.9
+    with pytest.raises(axcd.AxcdError) as e:
+        w.ccd_pairs(np.array([[0, s.n]], np.uint32), disp)             # body index out of range
+    assert e.value.code == 601
+    w.close()

@@ -89,3 +89,23 @@ def test_scene_generator_is_deterministic_and_matches_rng():
     assert set(np.unique(c2.shapes["type"])) == {0, 1, 4}
     nh = (c2.shapes["type"] == 4).sum()
     assert len(c2.hull) == 16 * nh
+
+
+def test_struct_sizes_match_the_header(tmp_path):
+    """sizeof() of every record in include/axcd.h, as a C compiler sees it, equals the size of the
+    ctypes / numpy mirror the host side uses (guards against silent ABI drift)."""
+    import subprocess
+    import numpy as np
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "axcd.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(AxcdShape),sizeof(AxcdContact),sizeof(AxcdConfig),sizeof(AxcdStats),sizeof(AxcdFilter),'
+                   'sizeof(AxcdManifold),sizeof(AxcdRay),sizeof(AxcdRayHit),sizeof(AxcdSweep),sizeof(void*));return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [axcd.SHAPE_DT.itemsize, axcd.CONTACT_DT.itemsize, C.sizeof(axcd.Config), C.sizeof(axcd.Stats), 12,
+            axcd.MANIFOLD_DT.itemsize, axcd.RAY_DT.itemsize, axcd.RAYHIT_DT.itemsize, axcd.SWEEP_DT.itemsize, 8]
+    assert got == want, (got, want)
+    import oracle_lib as O   # the oracle mirrors the same records
+    assert O.MANIFOLD_DT == axcd.MANIFOLD_DT and O.RAY_DT == axcd.RAY_DT and O.RAYHIT_DT == axcd.RAYHIT_DT
+    assert O.SWEEP_DT == axcd.SWEEP_DT and O.CONTACT_DT == axcd.CONTACT_DT

@@ -458,12 +458,21 @@ int32_t axcd_refit(AxcdContext* ctx) {
                 ctx->fatValid ? 0u : 1u, ctx->dCtr, ctrNext, ctx->dCtrInit);
             ctx->fatValid = true;
         } else {
+#if defined(AXCD_REFIT_NO_TMA)
+            // diagnostic build: the block-staged kernel (compute-sanitizer's initcheck does not see the
+            // bulk-store writes of the TMA kernel and reports every later read of the AABBs)
+            refitKernel<false><<<blocks, kRefitThreads, 0, ctx->stream>>>(
+                reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
+                reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin, 0u, ctx->dCtr,
+                ctrNext, ctx->dCtrInit);
+#else
             (void)blocks;
             uint32_t tiles = (ctx->n + kRefitThreads - 1) / kRefitThreads;
             const uint32_t grid = tiles < (uint32_t)kNumSMs * kRefitTmaBlocksPerSM ? tiles : kNumSMs * kRefitTmaBlocksPerSM;
             refitTmaKernel<<<grid, kRefitThreads, 0, ctx->stream>>>(
                 ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dAabb, ctx->dType8, ctx->n, ctx->cfg.aabbMargin, ctx->dCtr,
                 ctrNext, ctx->dCtrInit);
+#endif
         }
         CU(cudaGetLastError());
     }

@@ -136,7 +136,7 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
     if (blockIdx.x == 0 && tid < (int)(sizeof(Counters) / 4))
         reinterpret_cast<uint32_t*>(ctrNext)[tid] = reinterpret_cast<const uint32_t*>(ctrInit)[tid];
 
-    if (COHERENT) {   // stage the block's current fat boxes into sOut (same path as the stores below)
+    if (COHERENT && !force) {   // stage the block's current fat boxes into sOut (same path as the stores below)
         const uint32_t nFloats = cnt * 6, nVec = nFloats / 4;
         const float4* src = aabb4 + (size_t)base * 6 / 4;
         float4* dst = reinterpret_cast<float4*>(sOut);

@@ -54,3 +54,36 @@ def test_cuda_path_reproduces_golden_outputs(tag):
         assert np.array_equal(bits(con[f]), bits(gold[f])), f                 # and in fact bit-identical
     np.testing.assert_allclose(w.pair_distances(), G[f"{tag}_dist"], rtol=1e-4, atol=1e-6)
     w.close()
+
+
+# ---- the stages on top of the hot path (tests/golden/make_golden_next.py) ---------------------------------
+GN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next_rows_golden.npz"))
+
+
+@pytest.mark.parametrize("tag", ["c0", "mix"])
+def test_oracle_reproduces_next_row_goldens(tag):
+    xf, shapes, hull = GN[f"{tag}_xf"], GN[f"{tag}_shapes"], GN[f"{tag}_hull"]
+    rc, bb = O.refit(xf, shapes, hull)
+    con, _, _ = O.narrowphase(xf, shapes, O.broadphase(bb), hull)
+    assert con.tobytes() == GN[f"{tag}_contacts"].tobytes()
+    man, pts = O.manifolds(xf, shapes, con)
+    assert man.tobytes() == GN[f"{tag}_manifolds"].tobytes() and pts == int(GN[f"{tag}_points"])
+    assert O.raycast(xf, shapes, bb, GN[f"{tag}_rays"]).tobytes() == GN[f"{tag}_rayhits"].tobytes()
+    assert np.array_equal(O.query_aabbs(bb, GN[f"{tag}_qboxes"]), GN[f"{tag}_qhits"])
+    assert O.ccd_pairs(xf, shapes, GN[f"{tag}_cpairs"], GN[f"{tag}_disp"], hull).tobytes() == GN[f"{tag}_sweeps"].tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["c0", "mix"])
+def test_cuda_path_reproduces_next_row_goldens(tag):
+    s = axcd.Scene(GN[f"{tag}_xf"], GN[f"{tag}_shapes"], GN[f"{tag}_hull"])
+    w = axcd.CollisionWorld.for_scene(s, pairs_per_body=16)
+    w.step()
+    assert w.contacts().tobytes() == GN[f"{tag}_contacts"].tobytes()
+    w.build_manifolds()
+    man, pts = w.manifolds()
+    assert man.tobytes() == GN[f"{tag}_manifolds"].tobytes() and pts == int(GN[f"{tag}_points"])
+    assert w.raycast(GN[f"{tag}_rays"]).tobytes() == GN[f"{tag}_rayhits"].tobytes()
+    assert np.array_equal(w.query_aabbs(GN[f"{tag}_qboxes"]), GN[f"{tag}_qhits"])
+    assert w.ccd_pairs(GN[f"{tag}_cpairs"], GN[f"{tag}_disp"]).tobytes() == GN[f"{tag}_sweeps"].tobytes()
+    w.close()

@@ -706,6 +706,10 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
     }
     out->kernelLaunches = ctx->launches[0] + (ctx->stage >= ST_BROAD ? ctx->launches[1] : 0) +
                           (ctx->stage >= ST_NARROW ? ctx->launches[2] : 0);
+    if (ctx->stage >= ST_BROAD && ctx->hostCtr.travOverflow) {
+        snprintf(ctx->lastErr, sizeof(ctx->lastErr), "LBVH traversal stack overflow: candidate pairs would be missing");
+        return AXCD_ERR_GPU_FAILED;
+    }
     if (ctx->foundPairs > ctx->cfg.maxPairs || ctx->foundContacts > ctx->cfg.maxContacts) return AXCD_ERR_OUT_OF_RANGE;
     return AXCD_OK;
 }

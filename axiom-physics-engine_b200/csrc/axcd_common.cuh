@@ -96,6 +96,7 @@ struct Counters {
     uint32_t fallbackCursor; // next unclaimed overflow item (full-cap EPA)
     uint32_t gjkChunks;      // 32-pair class-homogeneous chunks queued for the GJK kernel
     uint32_t gjkChunkCursor; // next unclaimed chunk
+    uint32_t travOverflow;   // set if a traversal stack ever filled up (the step then reports 505 instead of losing pairs)
     uint32_t movedBodies;    // temporal coherence: bodies whose tight box left their fat box this step
     uint32_t manifoldPoints; // contact points over all manifolds (PhysicsWorldStats::contactPointCount)
 };

@@ -324,7 +324,11 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
         // loaded together, so two of the dependent L2 round trips of a walk overlap (the order in which
         // nodes are visited does not change the pair set).  Stack entries carry (node, first leaf).
         constexpr uint32_t kNone = 0xffffffffu;
-        uint32_t stackN[kTravStack], stackF[kTravStack];
+        // With two nodes expanded per trip the stack can hold two pending subtrees per level; the Karras
+        // tree is at most 64 levels deep (32 key bits + 32 tie-break bits), so 128 entries cannot fill up.
+        // Should that reasoning ever fail, the overflow is reported (505) rather than pairs being dropped.
+        constexpr int kWideStack = 2 * kTravStack;
+        uint32_t stackN[kWideStack], stackF[kWideStack];
         int sp = 0;
         uint32_t ni = 0, first = 0;
         while (true) {
@@ -359,10 +363,12 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
                         if (next == kNone) {
                             next = child;
                             nextFirst = cf;
-                        } else if (sp < kTravStack) {
+                        } else if (sp < kWideStack) {
                             stackN[sp] = child;
                             stackF[sp] = cf;
                             ++sp;
+                        } else {
+                            atomicExch(&ctr->travOverflow, 1u);
                         }
                         continue;
                     }

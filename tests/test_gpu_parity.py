@@ -452,3 +452,34 @@ def test_degenerate_pair_zoo_bit_exact():
     st, bitwise = run_and_compare(s)
     assert bitwise
     assert st.numPairs > npairs // 2 and st.numContacts > npairs // 4
+
+
+def test_deep_tree_everything_overlaps():
+    """Worst case for the traversal stacks: a deep LBVH (Morton keys with long common prefixes: positions
+    in a geometric progression, plus exact duplicates that are split by the index tie-break) in which
+    every box overlaps every other, so every subtree is entered.  A stack overflow would surface as
+    error 505 (never as silently missing pairs); the pair set must be all n(n-1)/2 pairs."""
+    n = 2400
+    xf = np.zeros((n, 10), np.float32)
+    k = np.arange(n)
+    base = (100.0 * 2.0 ** -(k % 24)).astype(np.float32)          # 24 nested scales ...
+    xf[:, 0], xf[:, 1], xf[:, 2] = base, base * 0.5, base * 0.25   # ... 100 exact duplicates of each
+    xf[:, 6] = 1.0
+    xf[:, 7:] = 1.0
+    shapes = np.zeros(n, axcd.SHAPE_DT)
+    shapes["type"] = 0
+    shapes["p0"] = 500.0                                          # every sphere's box covers the scene
+    s = axcd.Scene(xf, shapes)
+    w = axcd.CollisionWorld(n, max_pairs=n * (n - 1) // 2 + 16, max_contacts=16)
+    w.set_shapes(s.shapes)
+    w.set_transforms(s.xf)
+    w.update()
+    st = w.stats()
+    assert st.numPairs == n * (n - 1) // 2
+    gp = w.pairs()
+    iu = np.triu_indices(n, 1)
+    assert np.array_equal(gp, np.stack(iu, axis=1).astype(np.uint32))
+    # the scene queries walk the same tree with their own stacks
+    hits = w.query_aabbs(np.array([[-1e4, -1e4, -1e4, 1e4, 1e4, 1e4]], np.float32))
+    assert np.array_equal(hits[:, 1], np.arange(n, dtype=np.uint32))
+    w.close()

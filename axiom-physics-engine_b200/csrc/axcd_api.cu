@@ -12,8 +12,8 @@
 #include "axcd_epa_warp.cuh"
 #include "axcd_narrow.cuh"
 #include "axcd_manifold.cuh"
-#include "axcd_query.cuh"
 #include "axcd_ccd.cuh"
+#include "axcd_query.cuh"
 #include "axcd_refit.cuh"
 #include "axcd_sort.cuh"
 
@@ -932,8 +932,16 @@ int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRay
         if (rc) return rc;
     }
     const QueryTree T = queryTreeOf(ctx);
+    NarrowParams p;
+    p.gjkMaxIters = ctx->cfg.gjkMaxIters;
+    p.epaMaxIters = ctx->cfg.epaMaxIters;
+    p.epaMaxFaces = ctx->cfg.epaMaxFaces;
+    p.gjkTol = ctx->cfg.gjkTol;
+    p.epaTol = ctx->cfg.epaTol;
+    p.wantDistances = 1u;
     raycastKernel<<<(nq + kQueryThreads - 1) / kQueryThreads, kQueryThreads, 0, st>>>(
-        T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes, static_cast<uint32_t*>(ctx->dQOut));
+        T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+        static_cast<uint32_t*>(ctx->dQOut));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(outHits, ctx->dQOut, (size_t)nq * sizeof(AxcdRayHit), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

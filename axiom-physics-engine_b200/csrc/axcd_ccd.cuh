@@ -14,25 +14,20 @@ constexpr float kCcdTol = 1e-4f;
 constexpr int kCcdMaxIters = 48;
 constexpr int kCcdThreads = 64;
 
-__global__ void __launch_bounds__(kCcdThreads)
-ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restrict__ xf, const uint4* __restrict__ shapes,
-          const float4* __restrict__ hull, const float* __restrict__ disp, NarrowParams cfg, uint32_t* __restrict__ out) {
-    const uint32_t k = blockIdx.x * kCcdThreads + threadIdx.x;
-    if (k >= npairs) return;
+struct SweepResult {
+    uint32_t hit;
+    float toi;
+    V3 n;
+    uint32_t iterations;
+};
+
+// Conservative advancement of core B (moved by D * t, t in [0,1]) against the fixed core A.
+__device__ __forceinline__ SweepResult sweepCores(const Core& A, Core B, V3 D, NarrowParams cfg) {
     cfg.wantDistances = 1u;
-    const uint2 pr = __ldg(pairs + k);
-    const BodyPose ta = loadPose(xf, pr.x), tb = loadPose(xf, pr.y);
-    const V3 origin = ta.p;
-    const Core A = makeCore(ta, __ldg(shapes + pr.x), hull, origin);
-    Core B = makeCore(tb, __ldg(shapes + pr.y), hull, origin);
     const V3 c0 = B.c;
-    const V3 dA = mk3(__ldg(disp + 3 * (size_t)pr.x), __ldg(disp + 3 * (size_t)pr.x + 1), __ldg(disp + 3 * (size_t)pr.x + 2));
-    const V3 dB = mk3(__ldg(disp + 3 * (size_t)pr.y), __ldg(disp + 3 * (size_t)pr.y + 1), __ldg(disp + 3 * (size_t)pr.y + 2));
-    const V3 D = dB - dA;
     const float rs = A.r + B.r;
-    uint32_t hit = 0u;
-    float toi = 1.0f;
-    V3 nOut = mk3(0.f, 0.f, 0.f), nLast = nOut;
+    SweepResult out{0u, 1.0f, mk3(0.f, 0.f, 0.f), 0u};
+    V3 nLast = mk3(0.f, 0.f, 0.f);
     float t = 0.0f;
     int it = 0;
     for (; it < kCcdMaxIters; ++it) {
@@ -40,9 +35,9 @@ ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restr
         Simplex s;
         const GjkResult g = gjk(A, B, cfg, rs, s);
         if (g.state == GJK_OVERLAP) {   // cores touch at t: the normal is the last closest direction (zero at t = 0)
-            hit = 1u;
-            toi = t;
-            nOut = nLast;
+            out.hit = 1u;
+            out.toi = t;
+            out.n = nLast;
             break;
         }
         const float dist = sqrtf(g.vv);
@@ -50,9 +45,9 @@ ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restr
         const V3 n = -(g.v * (1.0f / dist));   // from a to b
         nLast = n;
         if (gap <= kCcdTol) {
-            hit = 1u;
-            toi = t;
-            nOut = n;
+            out.hit = 1u;
+            out.toi = t;
+            out.n = n;
             break;
         }
         const float approach = dot3(D, g.v) / dist;   // speed at which B closes in along the closest direction
@@ -60,13 +55,29 @@ ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restr
         t = t + gap / approach;
         if (!(t <= 1.0f)) break;
     }
+    out.iterations = (uint32_t)it;
+    return out;
+}
+
+__global__ void __launch_bounds__(kCcdThreads)
+ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restrict__ xf, const uint4* __restrict__ shapes,
+          const float4* __restrict__ hull, const float* __restrict__ disp, NarrowParams cfg, uint32_t* __restrict__ out) {
+    const uint32_t k = blockIdx.x * kCcdThreads + threadIdx.x;
+    if (k >= npairs) return;
+    const uint2 pr = __ldg(pairs + k);
+    const BodyPose ta = loadPose(xf, pr.x), tb = loadPose(xf, pr.y);
+    const V3 origin = ta.p;
+    const V3 dA = mk3(__ldg(disp + 3 * (size_t)pr.x), __ldg(disp + 3 * (size_t)pr.x + 1), __ldg(disp + 3 * (size_t)pr.x + 2));
+    const V3 dB = mk3(__ldg(disp + 3 * (size_t)pr.y), __ldg(disp + 3 * (size_t)pr.y + 1), __ldg(disp + 3 * (size_t)pr.y + 2));
+    const SweepResult r = sweepCores(makeCore(ta, __ldg(shapes + pr.x), hull, origin), makeCore(tb, __ldg(shapes + pr.y), hull, origin),
+                                     dB - dA, cfg);
     uint32_t* o = out + (size_t)k * 6;
-    o[0] = hit;
-    o[1] = __float_as_uint(toi);
-    o[2] = __float_as_uint(nOut.x);
-    o[3] = __float_as_uint(nOut.y);
-    o[4] = __float_as_uint(nOut.z);
-    o[5] = (uint32_t)it;
+    o[0] = r.hit;
+    o[1] = __float_as_uint(r.toi);
+    o[2] = __float_as_uint(r.n.x);
+    o[3] = __float_as_uint(r.n.y);
+    o[4] = __float_as_uint(r.n.z);
+    o[5] = r.iterations;
 }
 
 }  // namespace axcd

@@ -6,8 +6,8 @@
 //   AABB query: every body whose AABB meets the query box under AABB::intersects (closed intervals,
 //               include/axiom/math/aabb.hpp:132-135); hits come back sorted by (query, body).
 //   Ray cast  : a body is hit iff the slab test against its AABB passes within [0, tMax] AND its shape
-//               test (sphere / oriented box / capsule, closed forms) reports t in [0, tMax]; hull bodies
-//               answer with their AABB (flags = 1).  Reported t = max(shape t, AABB entry t), closest =
+//               test reports t in [0, tMax]: sphere / oriented box / capsule in closed form, convex hulls by
+//               conservative advancement on the GJK distance (first t with the gap <= 1e-4).  Reported t = max(shape t, AABB entry t), closest =
 //               minimum (t, body index), so the answer does not depend on the traversal order.  The
 //               slab test is monotone under box union (round-to-nearest is monotone), so pruning a node
 //               whose entry t exceeds the best t so far can never drop the winner.
@@ -15,6 +15,7 @@
 
 #include "axcd_lbvh.cuh"
 #include "axcd_narrow.cuh"
+#include "axcd_ccd.cuh"
 
 namespace axcd {
 
@@ -253,7 +254,29 @@ __device__ __noinline__ ShapeHit rayShape(V3 o, V3 d, float tMax, const BodyPose
         h.n = bn;
         return h;
     }
-    return h;   // hulls are answered at AABB level by the caller
+    return h;   // hulls: rayHull
+}
+
+// Ray against a convex hull: the ray origin is a point core at rest, the hull moves by -d * tMax; the time
+// of impact of that sweep (conservative advancement on the GJK distance) is t / tMax.  Surface normal =
+// from the hull towards the ray origin.
+__device__ __noinline__ ShapeHit rayHull(V3 o, V3 d, float tMax, const BodyPose& t, uint4 sh, const float4* __restrict__ hull,
+                                         const NarrowParams& cfg) {
+    ShapeHit h{false, 0.0f, mk3(0.f, 0.f, 0.f)};
+    Core P;
+    P.kind = CORE_POINT;
+    P.c = mk3(0.f, 0.f, 0.f);
+    P.e0 = P.e1 = P.e2 = P.c;
+    P.s = P.c;
+    P.verts = nullptr;
+    P.nv = 0;
+    P.r = 0.0f;
+    const SweepResult sw = sweepCores(P, makeCore(t, sh, hull, o), -(d * tMax), cfg);
+    if (!sw.hit) return h;
+    h.hit = true;
+    h.t = sw.toi * tMax;
+    h.n = -sw.n;
+    return h;
 }
 
 struct RayBest {
@@ -267,15 +290,13 @@ struct RayBest {
 // Exact test of one body whose AABB the ray enters at tNear; updates the best hit.
 __device__ __forceinline__ void rayTestBody(uint32_t body, float tNear, V3 o, V3 d, float tMax,
                                             const float* __restrict__ xf, const uint4* __restrict__ shapes,
-                                            RayBest& best) {
+                                            const float4* __restrict__ hull, const NarrowParams& cfg, RayBest& best) {
     const uint4 sh = __ldg(shapes + body);
-    ShapeHit h{true, tNear, mk3(0.f, 0.f, 0.f)};
-    uint32_t flags = 1u;
-    if (sh.x != AXCD_SHAPE_CONVEX) {
-        h = rayShape(o, d, tMax, loadPose(xf, body), sh);
-        flags = 0u;
-        if (!h.hit) return;
-    }
+    const uint32_t flags = 0u;
+    ShapeHit h;
+    if (sh.x != AXCD_SHAPE_CONVEX) h = rayShape(o, d, tMax, loadPose(xf, body), sh);
+    else h = rayHull(o, d, tMax, loadPose(xf, body), sh, hull, cfg);
+    if (!h.hit) return;
     const float t = (h.t > tNear) ? h.t : tNear;
     if (!best.have || t < best.t || (t == best.t && body < best.body)) {
         best.have = true;
@@ -289,7 +310,8 @@ __device__ __forceinline__ void rayTestBody(uint32_t body, float tNear, V3 o, V3
 // rays: 32-byte records (origin, direction, tMax, world); hits: 24-byte records.
 __global__ void __launch_bounds__(kQueryThreads)
 raycastKernel(QueryTree T, const float4* __restrict__ rays, uint32_t nq, const float* __restrict__ xf,
-              const uint4* __restrict__ shapes, uint32_t* __restrict__ hits) {
+              const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
+              uint32_t* __restrict__ hits) {
     const uint32_t q = blockIdx.x * kQueryThreads + threadIdx.x;
     if (q >= nq) return;
     const float4 r0 = __ldg(rays + 2 * (size_t)q), r1 = __ldg(rays + 2 * (size_t)q + 1);
@@ -302,7 +324,7 @@ raycastKernel(QueryTree T, const float4* __restrict__ rays, uint32_t nq, const f
         float tNear;
         const bool worldOk = !T.hasWorlds || T.worldId[0] == w;
         if (worldOk && raySlab(o, d, a[0], a[1], a[2], a[3], a[4], a[5], tMax, tNear))
-            rayTestBody(0u, tNear, o, d, tMax, xf, shapes, best);
+            rayTestBody(0u, tNear, o, d, tMax, xf, shapes, hull, cfg, best);
     } else if (T.n >= 2) {
         uint32_t rlo = 0, rhi = T.n - 1;
         if (T.hasWorlds) worldRange(T, w, rlo, rhi);
@@ -322,12 +344,12 @@ raycastKernel(QueryTree T, const float4* __restrict__ rays, uint32_t nq, const f
                 // leaves are tested at once; internal children are visited nearer first
                 if (hitL && first == split) {
                     if (split >= rlo && split <= rhi)
-                        rayTestBody(__float_as_uint(__ldg(&T.leafLo[split].w)), tL, o, d, tMax, xf, shapes, best);
+                        rayTestBody(__float_as_uint(__ldg(&T.leafLo[split].w)), tL, o, d, tMax, xf, shapes, hull, cfg, best);
                     hitL = false;
                 }
                 if (hitR && split + 1 == last) {
                     if (last >= rlo && last <= rhi)
-                        rayTestBody(__float_as_uint(__ldg(&T.leafLo[last].w)), tR, o, d, tMax, xf, shapes, best);
+                        rayTestBody(__float_as_uint(__ldg(&T.leafLo[last].w)), tR, o, d, tMax, xf, shapes, hull, cfg, best);
                     hitR = false;
                 }
                 uint32_t next = kNoHit;

@@ -207,11 +207,12 @@ AXCD_API int32_t axcd_query_aabbs(AxcdContext* ctx, const float* boxes6, const u
                                   uint32_t nq, uint32_t* outHits2, uint32_t cap, uint32_t* outCount);
 
 /* Closest-hit ray cast.  A body is hit iff the ray passes the slab test of its AABB within [0, tMax]
- * and its shape test does: spheres, oriented boxes and capsules in closed form; convex hulls answer
- * with their AABB (flags = 1).  t is the parameter along (dx,dy,dz), which need not be unit length;
- * the normal is the unit surface normal at the hit (zero when the origin is inside the shape, t = 0, or
- * for AABB-level hits).  No hit: body = 0xffffffff, t = tMax.  Ties go to the lower body index.
- * `world` selects the world in batched mode (ignored when numWorlds == 1).                          */
+ * and its shape test does: spheres, oriented boxes and capsules in closed form; convex hulls by
+ * conservative advancement on the GJK distance (t = first parameter at which the ray point is within
+ * 1e-4 of the hull).  t is the parameter along (dx,dy,dz), which need not be unit length; the normal is
+ * the unit surface normal at the hit (zero when the origin is inside the shape, t = 0).  No hit:
+ * body = 0xffffffff, t = tMax.  Ties go to the lower body index.  `world` selects the world in batched
+ * mode (ignored when numWorlds == 1).  flags is reserved (0).                                      */
 typedef struct AxcdRay {
     float ox, oy, oz;
     float dx, dy, dz;

@@ -1078,8 +1078,8 @@ void buildManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, co
 // same closest body.
 //   AABB query: every body whose AABB meets the query box under AABB::intersects (closed intervals).
 //   Ray cast  : a body is hit iff the ray's slab test against its AABB passes within [0, tMax] AND the
-//               shape test (sphere / oriented box / capsule in closed form) reports t in [0, tMax]; hull
-//               bodies answer with their AABB (flag 1).  The reported t is max(shape t, AABB entry t);
+//               shape test reports t in [0, tMax]: sphere / oriented box / capsule in closed form, convex
+//               hulls by conservative advancement on the GJK distance (first t with the gap <= 1e-4).  The reported t is max(shape t, AABB entry t);
 //               the closest hit is the minimum (t, body index).  Origin inside a shape: t = 0, normal 0.
 // ------------------------------------------------------------------------------------------
 inline bool raySlab(V3 o, V3 d, const float* lo, const float* hi, float tMax, float* tNear) {
@@ -1222,15 +1222,11 @@ ShapeHit rayShape(V3 o, V3 d, float tMax, const Xf& t, const AxrefShape& sh) {
 // ------------------------------------------------------------------------------------------
 const float CCD_TOL = 1e-4f;
 const int CCD_MAX_ITERS = 48;
-void sweepPair(const Xf& ta, const AxrefShape& sa, V3 dispA, const Xf& tb, const AxrefShape& sb, V3 dispB,
-               const float* hull, const AxrefNarrowCfg& cfgIn, AxrefSweep& out) {
+// Conservative advancement of core B (moved by D * t, t in [0,1]) against the fixed core A.
+void sweepCores(const Core& A, Core B, V3 D, const AxrefNarrowCfg& cfgIn, AxrefSweep& out) {
     AxrefNarrowCfg cfg = cfgIn;
     cfg.wantDistances = 1;
-    const V3 origin = ta.p;
-    const Core A = makeCore(ta, sa, hull, origin);
-    Core B = makeCore(tb, sb, hull, origin);
     const V3 c0 = B.c;
-    const V3 D = dispB - dispA;
     const float rs = A.r + B.r;
     out = AxrefSweep{0u, 1.0f, 0.0f, 0.0f, 0.0f, 0u};
     float t = 0.0f;
@@ -1262,6 +1258,29 @@ void sweepPair(const Xf& ta, const AxrefShape& sa, V3 dispA, const Xf& tb, const
         if (!(t <= 1.0f)) break;
     }
     out.iterations = (uint32_t)it;
+}
+
+void sweepPair(const Xf& ta, const AxrefShape& sa, V3 dispA, const Xf& tb, const AxrefShape& sb, V3 dispB,
+               const float* hull, const AxrefNarrowCfg& cfg, AxrefSweep& out) {
+    const V3 origin = ta.p;
+    sweepCores(makeCore(ta, sa, hull, origin), makeCore(tb, sb, hull, origin), dispB - dispA, cfg, out);
+}
+
+// Ray against a convex hull: the ray origin is a point core at rest, the hull moves by -d * tMax; the
+// time of impact of that sweep is t / tMax.  Surface normal = from the hull towards the ray origin.
+ShapeHit rayHull(V3 o, V3 d, float tMax, const Xf& t, const AxrefShape& sh, const float* hull, const AxrefNarrowCfg& cfg) {
+    ShapeHit h{false, 0.0f, mk(0, 0, 0)};
+    Core P{};
+    P.kind = CORE_POINT;
+    P.c = mk(0.0f, 0.0f, 0.0f);
+    P.r = 0.0f;
+    AxrefSweep sw;
+    sweepCores(P, makeCore(t, sh, hull, o), -(d * tMax), cfg, sw);
+    if (!sw.hit) return h;
+    h.hit = true;
+    h.t = sw.toi * tMax;
+    h.n = mk(-sw.nx, -sw.ny, -sw.nz);
+    return h;
 }
 
 }   // namespace
@@ -1563,8 +1582,9 @@ int32_t axref_query_aabbs(const float* aabb, uint32_t n, const uint32_t* worldId
     return cnt > cap ? 601 : 0;
 }
 
-int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* aabb, uint32_t n,
+int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* hullXYZ, const float* aabb, uint32_t n,
                       const uint32_t* worldId, const AxrefRay* rays, uint32_t nq, AxrefRayHit* out, int nthreads) {
+    const AxrefNarrowCfg cfg{32u, 32u, 64u, 1e-6f, 1e-4f, 1u};   // the library defaults (axcd_default_config)
     parallelFor(nq, nthreads, [&](int, uint64_t lo, uint64_t hi) {
         for (uint64_t q = lo; q < hi; ++q) {
             const AxrefRay& r = rays[q];
@@ -1575,13 +1595,11 @@ int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* aa
                 if (worldId && worldId[i] != r.world) continue;
                 float tNear;
                 if (!raySlab(o, d, aabb + 6ull * i, aabb + 6ull * i + 3, r.tMax, &tNear)) continue;
-                ShapeHit h{true, tNear, mk(0, 0, 0)};
-                uint32_t flags = 1u;
-                if (shapes[i].type != SHAPE_CONVEX) {
-                    h = rayShape(o, d, r.tMax, loadXf(xf + 10ull * i), shapes[i]);
-                    flags = 0u;
-                    if (!h.hit) continue;
-                }
+                ShapeHit h;
+                const uint32_t flags = 0u;
+                if (shapes[i].type != SHAPE_CONVEX) h = rayShape(o, d, r.tMax, loadXf(xf + 10ull * i), shapes[i]);
+                else h = rayHull(o, d, r.tMax, loadXf(xf + 10ull * i), shapes[i], hullXYZ, cfg);
+                if (!h.hit) continue;
                 const float t = (h.t > tNear) ? h.t : tNear;
                 if (!have || t < best.t || (t == best.t && i < best.body)) {
                     have = true;

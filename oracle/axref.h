@@ -80,7 +80,7 @@ typedef struct AxrefRay { float ox, oy, oz, dx, dy, dz, tMax; uint32_t world; } 
 typedef struct AxrefRayHit { uint32_t body; float t, nx, ny, nz; uint32_t flags; } AxrefRayHit;
 int32_t axref_query_aabbs(const float* aabb, uint32_t n, const uint32_t* worldId, const float* qboxes,
                           const uint32_t* qworld, uint32_t nq, uint32_t* outHits, uint64_t cap, uint64_t* outCount);
-int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* aabb, uint32_t n,
+int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* hullXYZ, const float* aabb, uint32_t n,
                       const uint32_t* worldId, const AxrefRay* rays, uint32_t nq, AxrefRayHit* out, int nthreads);
 
 /* GJK-based CCD: time of impact of the given pairs under linear motion (disp = n x 3 displacements over

@@ -39,7 +39,7 @@ for tag, s, L in (("c0", axcd.config_scene("C0"), 10.0), ("mix", mix_scene(), 8.
     o = rng.uniform(-1, L + 1, (300, 3)).astype(np.float32)
     d = rng.normal(size=(300, 3)).astype(np.float32)
     rays = O.make_rays(o, d, 25.0)
-    hits = O.raycast(s.xf, s.shapes, bb, rays)
+    hits = O.raycast(s.xf, s.shapes, bb, rays, hull=s.hull)
     qboxes = np.concatenate([o - 0.6, o + 0.6], axis=1).astype(np.float32)
     qhits = O.query_aabbs(bb, qboxes)
     perm = rng.permutation(s.n).astype(np.uint32)

@@ -210,14 +210,15 @@ def query_aabbs(aabb, qboxes, world_id=None, qworld=None):
         return out[:cnt.value].copy()
 
 
-def raycast(xf, shapes, aabb, rays, world_id=None, nthreads=8):
+def raycast(xf, shapes, aabb, rays, world_id=None, nthreads=8, hull=None):
     xf = f32(xf).reshape(-1, 10)
     shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
+    hull = f32(hull if hull is not None else np.zeros((0, 3))).reshape(-1, 3)
     aabb = f32(aabb).reshape(-1, 6)
     rays = np.ascontiguousarray(rays, dtype=RAY_DT)
     wid = np.ascontiguousarray(world_id, dtype=np.uint32) if world_id is not None else None
     out = np.zeros(max(1, len(rays)), RAYHIT_DT)
-    rc = lib().axref_raycast(_p(xf), _p(shapes), _p(aabb), C.c_uint32(len(xf)), _p(wid), _p(rays),
+    rc = lib().axref_raycast(_p(xf), _p(shapes), _p(hull), _p(aabb), C.c_uint32(len(xf)), _p(wid), _p(rays),
                              C.c_uint32(len(rays)), _p(out), C.c_int(nthreads))
     assert rc == 0, rc
     return out[:len(rays)].copy()

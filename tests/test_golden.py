@@ -68,7 +68,7 @@ def test_oracle_reproduces_next_row_goldens(tag):
     assert con.tobytes() == GN[f"{tag}_contacts"].tobytes()
     man, pts = O.manifolds(xf, shapes, con)
     assert man.tobytes() == GN[f"{tag}_manifolds"].tobytes() and pts == int(GN[f"{tag}_points"])
-    assert O.raycast(xf, shapes, bb, GN[f"{tag}_rays"]).tobytes() == GN[f"{tag}_rayhits"].tobytes()
+    assert O.raycast(xf, shapes, bb, GN[f"{tag}_rays"], hull=hull).tobytes() == GN[f"{tag}_rayhits"].tobytes()
     assert np.array_equal(O.query_aabbs(bb, GN[f"{tag}_qboxes"]), GN[f"{tag}_qhits"])
     assert O.ccd_pairs(xf, shapes, GN[f"{tag}_cpairs"], GN[f"{tag}_disp"], hull).tobytes() == GN[f"{tag}_sweeps"].tobytes()
 

@@ -146,20 +146,40 @@ def test_ray_closest_body_in_a_scene():
     assert nhit > 20
 
 
-def test_ray_miss_world_filter_and_hull_flag():
+def test_ray_miss_world_filter_and_exact_hull_hits():
     s = axcd.generate_scene(50, 4, 4.0, frac_box=0.3, frac_sphere=0.3)     # 40 % hulls
     _, bb = O.refit(s.xf, s.shapes, s.hull)
     rays = O.make_rays([[-50, -50, -50], [2, 2, -5]], [[-1, 0, 0], [0, 0, 1]], 100.0)
-    hits = O.raycast(s.xf, s.shapes, bb, rays)
+    hits = O.raycast(s.xf, s.shapes, bb, rays, hull=s.hull)
     assert hits[0]["body"] == O.NO_HIT and hits[0]["t"] == np.float32(100.0)
     # world filter: bodies of the other world are invisible
     wid = (np.arange(s.n) % 2).astype(np.uint32)
     r0 = O.make_rays([[2, 2, -5]] * 2, [[0, 0, 1]] * 2, 100.0)
     r0["world"] = [0, 1]
-    h = O.raycast(s.xf, s.shapes, bb, r0, world_id=wid)
+    h = O.raycast(s.xf, s.shapes, bb, r0, world_id=wid, hull=s.hull)
     for k in (0, 1):
         if h[k]["body"] != O.NO_HIT:
             assert wid[h[k]["body"]] == k
-    hull_hits = [x for x in O.raycast(s.xf, s.shapes, bb, O.make_rays(s.xf[:, :3] - [0, 0, 30], [[0, 0, 1]] * s.n, 100.0))
-                 if x["body"] != O.NO_HIT and s.shapes["type"][x["body"]] == 4]
-    assert hull_hits and all(x["flags"] == 1 for x in hull_hits)
+    # hull bodies: exact hits by conservative advancement, checked against the hull's half-spaces
+    from scipy.spatial import ConvexHull
+    hid = np.where(s.shapes["type"] == 4)[0]
+    checked = 0
+    for i in hid[:12]:
+        first, cnt = np.array([s.shapes["p0"][i]], np.float32).view(np.uint32)[0], np.array([s.shapes["p1"][i]], np.float32).view(np.uint32)[0]
+        x = s.xf[i].astype(np.float64)
+        R = _rot(x[3:7])
+        pts = (s.hull[first:first + cnt].astype(np.float64) * x[7:10]) @ R.T + x[:3]
+        eq = ConvexHull(pts).equations            # n.x + d <= 0 inside
+        o = x[:3] + np.array([0.06, -0.04, -6.0])
+        d = np.array([0.0, 0.0, 1.0])
+        num, den = -(eq[:, :3] @ o + eq[:, 3]), eq[:, :3] @ d
+        t_in = max([num[k] / den[k] for k in range(len(eq)) if den[k] < 0] + [0.0])
+        t_out = min([num[k] / den[k] for k in range(len(eq)) if den[k] > 0] + [1e30])
+        h = O.raycast(s.xf[i:i + 1], s.shapes[i:i + 1], bb[i:i + 1], O.make_rays([o], [d], 50.0), hull=s.hull)[0]
+        if t_in <= t_out:
+            assert h["body"] == 0 and h["flags"] == 0
+            assert -3e-4 < t_in - h["t"] < 3e-4, (t_in, h)       # stops when the gap is <= 1e-4
+            checked += 1
+        else:
+            assert h["body"] == O.NO_HIT
+    assert checked >= 5

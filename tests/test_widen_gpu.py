@@ -146,7 +146,7 @@ def test_raycast_matches_oracle():
     o[303:400] = s.xf[1000:1097, :3]                # origins inside shapes: t = 0
     rays = O.make_rays(o, d, rng.uniform(3.0, 40.0, nq).astype(np.float32))
     got = w.raycast(rays)
-    exp = O.raycast(s.xf, s.shapes, bb, rays)
+    exp = O.raycast(s.xf, s.shapes, bb, rays, hull=s.hull)
     assert np.array_equal(got["body"], exp["body"])                       # bit-exact closest body
     assert np.array_equal(got["flags"], exp["flags"])
     for f in ("t", "nx", "ny", "nz"):
@@ -183,7 +183,7 @@ def test_queries_in_batched_worlds():
     rays = O.make_rays(o, d, 20.0)
     rays["world"] = qw
     gr = w.raycast(rays)
-    er = O.raycast(s.xf, s.shapes, bb, rays, world_id=s.world_id)
+    er = O.raycast(s.xf, s.shapes, bb, rays, world_id=s.world_id, hull=s.hull)
     assert np.array_equal(gr["body"], er["body"])
     assert all(_bits_equal(gr[f], er[f]) for f in ("t", "nx", "ny", "nz", "flags"))
     hit = gr["body"] != axcd.NO_HIT
@@ -203,7 +203,7 @@ def test_queries_tiny_scenes_and_errors():
         q = np.array([[-5, -5, -5, 5, 5, 5], [10, 10, 10, 11, 11, 11]], np.float32)
         assert np.array_equal(w.query_aabbs(q), O.query_aabbs(bb, q))
         rays = O.make_rays(s.xf[:, :3] - [0, 0, 4], [[0, 0, 1]] * n, 10.0)
-        gr, er = w.raycast(rays), O.raycast(s.xf, s.shapes, bb, rays)
+        gr, er = w.raycast(rays), O.raycast(s.xf, s.shapes, bb, rays, hull=s.hull)
         assert gr.tobytes() == er.tobytes()
         assert (gr["body"] != axcd.NO_HIT).all()
         assert len(w.query_aabbs(np.zeros((0, 6), np.float32))) == 0

@@ -67,6 +67,7 @@ struct AxcdContext {
     Node32* dNodes32 = nullptr;      // compact nodes of the pair traversal (32 B per internal node)
     BvhNode* dNodes = nullptr;       // float nodes for the scene queries: allocated and built by the first query after a broadphase
     bool queryNodesValid = false;
+    bool hasHulls = false;           // any convex-hull shape in the current scene (ghosts are never hulls)
     uint32_t* dWorldEnd = nullptr;
     uint2* dPairsTmp = nullptr;      // candidate pairs as found (unordered)
     uint2* dPairs = nullptr;         // candidate pairs, canonical order
@@ -378,9 +379,11 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
     if (nHullVerts && !hullXYZ) return AXCD_ERR_NULL_POINTER;
     if (n > ctx->cfg.maxBodies || nHullVerts > ctx->cfg.maxHullVerts) return AXCD_ERR_OUT_OF_RANGE;
     if (ctx->cfg.numWorlds > 1 && n && !worldId) return AXCD_ERR_INVALID_PARAM;
+    bool anyHull = false;
     for (uint32_t i = 0; i < n; ++i) {
         const AxcdShape& s = shapes[i];
         if (s.type == AXCD_SHAPE_CONVEX) {
+            anyHull = true;
             uint32_t first, cnt;
             memcpy(&first, &s.p0, 4);
             memcpy(&cnt, &s.p1, 4);
@@ -390,6 +393,7 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
         }
         if (ctx->cfg.numWorlds > 1 && worldId[i] >= ctx->cfg.numWorlds) return AXCD_ERR_OUT_OF_RANGE;
     }
+    ctx->hasHulls = anyHull;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     CU(cudaMemcpyAsync(ctx->dShapes, shapes, sizeof(AxcdShape) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (nHullVerts) {
@@ -939,9 +943,13 @@ int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRay
     p.gjkTol = ctx->cfg.gjkTol;
     p.epaTol = ctx->cfg.epaTol;
     p.wantDistances = 1u;
-    raycastKernel<<<(nq + kQueryThreads - 1) / kQueryThreads, kQueryThreads, 0, st>>>(
-        T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes, ctx->dHull, p,
-        static_cast<uint32_t*>(ctx->dQOut));
+    const uint32_t rb = (nq + kQueryThreads - 1) / kQueryThreads;
+    if (ctx->hasHulls)
+        raycastKernel<true><<<rb, kQueryThreads, 0, st>>>(T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes,
+                                                          ctx->dHull, p, static_cast<uint32_t*>(ctx->dQOut));
+    else
+        raycastKernel<false><<<rb, kQueryThreads, 0, st>>>(T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes,
+                                                           ctx->dHull, p, static_cast<uint32_t*>(ctx->dQOut));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(outHits, ctx->dQOut, (size_t)nq * sizeof(AxcdRayHit), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -288,13 +288,14 @@ struct RayBest {
 };
 
 // Exact test of one body whose AABB the ray enters at tNear; updates the best hit.
+template <bool HULLS>
 __device__ __forceinline__ void rayTestBody(uint32_t body, float tNear, V3 o, V3 d, float tMax,
                                             const float* __restrict__ xf, const uint4* __restrict__ shapes,
                                             const float4* __restrict__ hull, const NarrowParams& cfg, RayBest& best) {
     const uint4 sh = __ldg(shapes + body);
     const uint32_t flags = 0u;
     ShapeHit h;
-    if (sh.x != AXCD_SHAPE_CONVEX) h = rayShape(o, d, tMax, loadPose(xf, body), sh);
+    if (!HULLS || sh.x != AXCD_SHAPE_CONVEX) h = rayShape(o, d, tMax, loadPose(xf, body), sh);
     else h = rayHull(o, d, tMax, loadPose(xf, body), sh, hull, cfg);
     if (!h.hit) return;
     const float t = (h.t > tNear) ? h.t : tNear;
@@ -307,7 +308,9 @@ __device__ __forceinline__ void rayTestBody(uint32_t body, float tNear, V3 o, V3
     }
 }
 
-// rays: 32-byte records (origin, direction, tMax, world); hits: 24-byte records.
+// rays: 32-byte records (origin, direction, tMax, world); hits: 24-byte records.  HULLS = false is the lean
+// instantiation for scenes without convex hulls (the GJK machinery of rayHull costs 56 more registers).
+template <bool HULLS>
 __global__ void __launch_bounds__(kQueryThreads)
 raycastKernel(QueryTree T, const float4* __restrict__ rays, uint32_t nq, const float* __restrict__ xf,
               const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
@@ -324,7 +327,7 @@ raycastKernel(QueryTree T, const float4* __restrict__ rays, uint32_t nq, const f
         float tNear;
         const bool worldOk = !T.hasWorlds || T.worldId[0] == w;
         if (worldOk && raySlab(o, d, a[0], a[1], a[2], a[3], a[4], a[5], tMax, tNear))
-            rayTestBody(0u, tNear, o, d, tMax, xf, shapes, hull, cfg, best);
+            rayTestBody<HULLS>(0u, tNear, o, d, tMax, xf, shapes, hull, cfg, best);
     } else if (T.n >= 2) {
         uint32_t rlo = 0, rhi = T.n - 1;
         if (T.hasWorlds) worldRange(T, w, rlo, rhi);
@@ -344,12 +347,12 @@ raycastKernel(QueryTree T, const float4* __restrict__ rays, uint32_t nq, const f
                 // leaves are tested at once; internal children are visited nearer first
                 if (hitL && first == split) {
                     if (split >= rlo && split <= rhi)
-                        rayTestBody(__float_as_uint(__ldg(&T.leafLo[split].w)), tL, o, d, tMax, xf, shapes, hull, cfg, best);
+                        rayTestBody<HULLS>(__float_as_uint(__ldg(&T.leafLo[split].w)), tL, o, d, tMax, xf, shapes, hull, cfg, best);
                     hitL = false;
                 }
                 if (hitR && split + 1 == last) {
                     if (last >= rlo && last <= rhi)
-                        rayTestBody(__float_as_uint(__ldg(&T.leafLo[last].w)), tR, o, d, tMax, xf, shapes, hull, cfg, best);
+                        rayTestBody<HULLS>(__float_as_uint(__ldg(&T.leafLo[last].w)), tR, o, d, tMax, xf, shapes, hull, cfg, best);
                     hitR = false;
                 }
                 uint32_t next = kNoHit;

@@ -15,6 +15,9 @@ constexpr int kSortThreads = 256;
 #define AXCD_SORT_ITEMS 16
 #endif
 constexpr int kSortItems = AXCD_SORT_ITEMS;
+#ifndef AXCD_SORT_LOOKBACK
+#define AXCD_SORT_LOOKBACK 4   // predecessor tiles read per look-back round (sweep 1..32: 4-6 best at 1 M keys)
+#endif
 constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per tile
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kRadix = 256;
@@ -144,7 +147,7 @@ radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
             // Decoupled look-back, kLookback predecessors per round: the loads of a round are
             // independent (all in flight together), so a deep walk costs one L2 round trip per
             // kLookback tiles instead of one per tile.
-            constexpr int kLookback = 16;
+            constexpr int kLookback = AXCD_SORT_LOOKBACK;
             int t = (int)tile - 1;
             bool found = false;
             while (!found && t >= 0) {

@@ -19,6 +19,17 @@
 
 using namespace axcd;
 
+// launch shapes of the latency-bound helper kernels (swept on the B200, see profiles/r01_experiments.md)
+#ifndef AXCD_SCATTER_BLOCKS
+#define AXCD_SCATTER_BLOCKS 32    // blocks per SM of scatterPairsKernel (sweep 4/8/16/32)
+#endif
+#ifndef AXCD_TOPO_THREADS
+#define AXCD_TOPO_THREADS 64
+#endif
+#ifndef AXCD_SEGSORT_THREADS
+#define AXCD_SEGSORT_THREADS 64
+#endif
+
 namespace {
 
 enum Stage { ST_NONE = 0, ST_SHAPES = 1, ST_POSES = 2, ST_REFIT = 3, ST_BROAD = 4, ST_NARROW = 5 };
@@ -554,7 +565,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
                 }
             }
         }
-        buildTopologyKernel<true><<<b256, 256, 0, st>>>(sKeys, n, ctx->dSegLo, ctx->dSegHi, P, ctx->dNodes32);
+        buildTopologyKernel<true><<<(n + AXCD_TOPO_THREADS - 1) / AXCD_TOPO_THREADS, AXCD_TOPO_THREADS, 0, st>>>(sKeys, n, ctx->dSegLo, ctx->dSegHi, P, ctx->dNodes32);
         ctx->queryNodesValid = false;
         CU(cudaGetLastError());
         recordEv(ctx, EV_BUILD);
@@ -576,9 +587,9 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         exclusiveScanKernel<<<scanTiles, kScanThreads, 0, st>>>(ctx->dBodyCount, ctx->dBodyStart, ctx->dBodyCount + n, n,
                                                                 ctx->dScanStatus, &ctx->dCtr->scanTicket,
                                                                 &ctx->dCtr->storedPairs);
-        scatterPairsKernel<<<kNumSMs * 8, 256, 0, st>>>(ctx->dPairsTmp, &ctx->dCtr->pairCount, ctx->cfg.maxPairs,
+        scatterPairsKernel<<<kNumSMs * AXCD_SCATTER_BLOCKS, 256, 0, st>>>(ctx->dPairsTmp, &ctx->dCtr->pairCount, ctx->cfg.maxPairs,
                                                         ctx->dBodyCount + n, ctx->dSegB);
-        sortSegmentsKernel<<<b256, 256, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
+        sortSegmentsKernel<<<(n + AXCD_SEGSORT_THREADS - 1) / AXCD_SEGSORT_THREADS, AXCD_SEGSORT_THREADS, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIRSORT);
         // no host round trip here: the narrowphase kernels read the pair count on the device

@@ -15,6 +15,9 @@ constexpr int kSortThreads = 256;
 #define AXCD_SORT_ITEMS 16
 #endif
 constexpr int kSortItems = AXCD_SORT_ITEMS;
+#ifndef AXCD_HIST_ITEMS
+#define AXCD_HIST_ITEMS 8   // keys per thread of the histogram kernel (sets its grid)
+#endif
 #ifndef AXCD_SORT_LOOKBACK
 #define AXCD_SORT_LOOKBACK 4   // predecessor tiles read per look-back round (sweep 1..32: 4-6 best at 1 M keys)
 #endif
@@ -220,7 +223,7 @@ inline int radixSort(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, uint3
     cudaMemsetAsync(scratchHist, 0, sizeof(uint32_t) * kMaxPasses * kRadix, stream);
     cudaMemsetAsync(scratchStatus, 0, sizeof(uint32_t) * (size_t)passes * numTiles * kRadix, stream);
     cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * kMaxPasses, stream);
-    uint32_t histBlocks = (n + kSortThreads * 8 - 1) / (kSortThreads * 8);
+    uint32_t histBlocks = (n + kSortThreads * AXCD_HIST_ITEMS - 1) / (kSortThreads * AXCD_HIST_ITEMS);
     if (histBlocks > (uint32_t)kNumSMs * 8) histBlocks = kNumSMs * 8;
     radixHistogramKernel<K><<<histBlocks, kSortThreads, 0, stream>>>(keysA, n, bitStart, passes, scratchHist);
     radixScanKernel<<<1, kRadix, 0, stream>>>(scratchHist, passes);

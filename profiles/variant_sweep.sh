@@ -9,7 +9,7 @@ import json,sys
 t=sys.argv[1]
 try:
     d=json.loads(open(f"gpurun_out/sweep_{t}.json").read().strip().splitlines()[-1])
-    print(t, "ms/step", round(d["ms_per_step"],4), d['config']['candidate_pairs'], d['config']['contacts'], [(s['stage'], s['ms']) for s in d['stages']])
+    print(t, "ms/step", round(d["ms_per_step"],4), d['config']['candidate_pairs'], d['config']['contacts'], [(s["stage"], s["ms"]) for s in d["stages"]])
 except Exception as e:
     print(t, "FAILED", e, open(f"gpurun_out/sweep_{t}.err").read()[-400:])
 PY

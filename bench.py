@@ -270,16 +270,22 @@ def measure_next_rows(w, s, stream, hbm_peak, device):
     rays["tMax"] = 50.0
     boxes = np.concatenate([o - 1.0, o + 1.0], axis=1)
     w.raycast(rays[:1024])
-    t0 = time.perf_counter()
-    hits = w.raycast(rays)
+    ray_s = 1e9
+    for _ in range(3):           # blocking host calls: best of three
+        t0 = time.perf_counter()
+        hits = w.raycast(rays)
+        ray_s = min(ray_s, time.perf_counter() - t0)
     t1 = time.perf_counter()
     qh = w.query_aabbs(boxes)   # first call sizes the output (601 + retry is part of the public call)
     t2 = time.perf_counter()
-    qh = w.query_aabbs(boxes)
-    t3 = time.perf_counter()
+    q_s = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        qh = w.query_aabbs(boxes)
+        q_s = min(q_s, time.perf_counter() - t0)
     out["raycast"] = {"rays": nq, "t_max": 50.0, "hit_fraction": round(float((hits["body"] != axcd.NO_HIT).mean()), 4),
-                      "mrays_per_s_e2e": round(nq / (t1 - t0) / 1e6, 2)}
-    out["aabb_query"] = {"queries": nq, "hits": int(len(qh)), "mqueries_per_s_e2e": round(nq / (t3 - t2) / 1e6, 2),
+                      "mrays_per_s_e2e": round(nq / ray_s / 1e6, 2)}
+    out["aabb_query"] = {"queries": nq, "hits": int(len(qh)), "mqueries_per_s_e2e": round(nq / q_s / 1e6, 2),
                          "first_call_ms": round(1e3 * (t2 - t1), 3)}
     # rank 3: temporal coherence — the same scene with fat boxes; a step in which no body left its fat box
     wc = axcd.CollisionWorld.for_scene(s, device=device, stream=stream.cuda_stream, aabbMargin=0.05,

@@ -8,8 +8,9 @@
 // Sutherland-Hodgman against the reference face's four side planes, vertices on or below the
 // reference face kept (position = midpoint between the vertex and its projection onto the face,
 // depth = distance below the face), reduced to at most four (deepest, farthest from it, largest
-// triangle, farthest outside that triangle).  Every other pair class, and a box-box contact whose
-// clip comes out empty, keeps the narrowphase point.  Same expression trees as the CPU oracle.
+// triangle, farthest outside that triangle).  Capsule-box contacts clip the capsule's segment against the
+// facing box face (1..2 points).  Every other pair class, and a clip that comes out empty, keeps the
+// narrowphase point.  Same expression trees as the CPU oracle.
 //
 // Tiles of 256 contacts per 128-thread block; the 88-byte records are staged in shared memory and
 // written with coalesced 128-bit stores; box-box contacts are compacted and clipped densely.  Algorithmic bytes: 40 B contact + 2 x 56 B pose/shape
@@ -188,6 +189,48 @@ __device__ __forceinline__ uint32_t boxBoxManifold(const BoxFrame& A, const BoxF
     return keep;
 }
 
+// Capsule against box: the capsule's core segment clipped against the side planes of the box face that
+// faces the capsule; the ends of the clipped segment within the radius of that face are the contact points
+// (1..2).  Returns the number of points written (0: the narrowphase point stands).  Positions are in the
+// frame centred on body a.
+__device__ __forceinline__ int capsuleBoxManifold(const BoxFrame& R, V3 cc, V3 e, float r, V3 toCap, V3* __restrict__ outPos,
+                                                  float* __restrict__ outDep) {
+    const V3 p0 = cc - e, seg = e * 2.0f;
+    const float d0a = dot3(toCap, R.ax[0]), d1a = dot3(toCap, R.ax[1]), d2a = dot3(toCap, R.ax[2]);
+    const int i = argmaxAbs3(d0a, d1a, d2a);
+    const V3 nr = pickAxis(R, i) * ((pick3(d0a, d1a, d2a, i) >= 0.0f) ? 1.0f : -1.0f);
+    float t0 = 0.0f, t1 = 1.0f;
+    for (int side = 0; side < 4; ++side) {
+        const int w = (i + 1 + (side >> 1)) % 3;
+        const V3 pn = pickAxis(R, w) * ((side & 1) ? -1.0f : 1.0f);
+        const float d0 = dot3(p0 - R.c, pn) - pickHalf(R, w);   // <= 0 inside
+        const float dd = dot3(seg, pn);
+        if (dd > 0.0f) {
+            const float t = -d0 / dd;
+            if (t < t1) t1 = t;
+        } else if (dd < 0.0f) {
+            const float t = -d0 / dd;
+            if (t > t0) t0 = t;
+        } else if (d0 > 0.0f) {
+            return 0;   // parallel to the plane and outside it
+        }
+    }
+    if (!(t0 <= t1)) return 0;
+    const int cand = (t0 == t1) ? 1 : 2;
+    const float hi = pickHalf(R, i);
+    int cnt = 0;
+    for (int k = 0; k < cand; ++k) {
+        const V3 q = p0 + seg * (k ? t1 : t0);
+        const float sep = (dot3(q - R.c, nr) - hi) - r;
+        if (sep <= 0.0f) {
+            outPos[cnt] = q - nr * (r + sep * 0.5f);
+            outDep[cnt] = -sep;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
 // One block handles tiles of kManTile contacts: every thread writes the single-point record of its
 // contacts into the shared staging area, the tile's box-box contacts are compacted into a list, and the
 // first threads of the block clip them with all lanes busy (polygons in shared-memory columns, nothing
@@ -222,7 +265,10 @@ manifoldKernel(const AxcdContact* __restrict__ contacts, const uint32_t* __restr
 #pragma unroll
             for (int k = 0; k < 4; ++k) { o[6 + k] = 0.0f; o[10 + k] = 0.0f; o[14 + k] = 0.0f; o[18 + k] = 0.0f; }
             o[6] = c1.x; o[10] = c1.y; o[14] = c2.x; o[18] = c4.x;
-            const bool bb = __ldg(&shapes[a].x) == AXCD_SHAPE_BOX && __ldg(&shapes[b].x) == AXCD_SHAPE_BOX;
+            const uint32_t tyA = __ldg(&shapes[a].x), tyB = __ldg(&shapes[b].x);
+            // contacts that get more than the narrowphase point: box-box and capsule-box
+            const bool bb = (tyA == AXCD_SHAPE_BOX && (tyB == AXCD_SHAPE_BOX || tyB == AXCD_SHAPE_CAPSULE)) ||
+                            (tyA == AXCD_SHAPE_CAPSULE && tyB == AXCD_SHAPE_BOX);
             const uint32_t bal = __ballot_sync(__activemask(), bb);
             if (bb) {
                 const int lane = tid & 31;
@@ -245,7 +291,28 @@ manifoldKernel(const AxcdContact* __restrict__ contacts, const uint32_t* __restr
             const V3 n = mk3(o[2], o[3], o[4]);
             const BodyPose ta = loadPose(xf, a), tb = loadPose(xf, b);
             const V3 origin = ta.p;
-            const BoxFrame A = makeBoxFrame(ta, __ldg(shapes + a), origin), B = makeBoxFrame(tb, __ldg(shapes + b), origin);
+            const uint4 sa = __ldg(shapes + a), sb = __ldg(shapes + b);
+            if (sa.x == AXCD_SHAPE_CAPSULE || sb.x == AXCD_SHAPE_CAPSULE) {
+                const bool boxIsA = sa.x == AXCD_SHAPE_BOX;
+                const BoxFrame R = boxIsA ? makeBoxFrame(ta, sa, origin) : makeBoxFrame(tb, sb, origin);
+                const BodyPose& tC = boxIsA ? tb : ta;
+                const uint4 sC = boxIsA ? sb : sa;
+                V3 c0, c1, c2;
+                quatToColumns(tC.q, c0, c1, c2);
+                const V3 e = c1 * ((__uint_as_float(sC.z) * 0.5f) * tC.s.y);   // half segment, as the narrowphase core
+                V3 cp[2];
+                float cd[2];
+                const int nc = capsuleBoxManifold(R, tC.p - origin, e, __uint_as_float(sC.y), boxIsA ? n : -n, cp, cd);
+                if (nc == 0) continue;
+                for (int k = 0; k < nc; ++k) {
+                    const V3 w = cp[k] + origin;
+                    o[6 + k] = w.x; o[10 + k] = w.y; o[14 + k] = w.z; o[18 + k] = cd[k];
+                }
+                reinterpret_cast<uint32_t*>(o)[5] = (uint32_t)nc;
+                extra += (uint32_t)nc - 1u;
+                continue;
+            }
+            const BoxFrame A = makeBoxFrame(ta, sa, origin), B = makeBoxFrame(tb, sb, origin);
             const PolyCol poly{sPoly + tid}, tmp{sPoly + 24 * kManThreads + tid};
             int nk = 0;
             const uint32_t keep = boxBoxManifold(A, B, n, poly, tmp, &nk);

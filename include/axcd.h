@@ -181,7 +181,8 @@ AXCD_API int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t 
  * include/axiom/debug/physics_debug_draw.hpp:128-132) and the total is what
  * gui::PhysicsWorldStats::contactPointCount reports (include/axiom/gui/physics_panel.hpp:21).
  * Box-box contacts are clipped feature against feature (reference face / incident face, at most
- * four points kept); every other shape pair keeps the narrowphase point.  Unused slots are zero. */
+ * four points kept); capsule-box contacts clip the capsule's segment against the facing box face (one
+ * or two points); every other shape pair keeps the narrowphase point.  Unused slots are zero.       */
 typedef struct AxcdManifold {
     uint32_t a, b;          /* == the contact's                                                  */
     float nx, ny, nz;       /* == the contact's normal (a -> b)                                  */

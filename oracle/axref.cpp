@@ -916,8 +916,9 @@ PairOut collidePair(uint32_t ia, uint32_t ib, const Xf& ta, const AxrefShape& sa
 // contact normal (ties: body a), incident face = the other box's face most anti-parallel to it,
 // clipped (Sutherland-Hodgman) against the reference face's four side planes; vertices on or below
 // the reference face are kept (position = midpoint between the vertex and its projection onto the
-// reference face, depth = distance below the face) and reduced to at most four.  Every other class,
-// and a box-box contact whose clip comes out empty, keeps the single narrowphase point.
+// reference face, depth = distance below the face) and reduced to at most four.  Capsule-box: the capsule's
+// segment clipped against the facing box face (capsuleBoxManifold, 1..2 points).  Every other class, and a
+// clip that comes out empty, keeps the single narrowphase point.
 // ------------------------------------------------------------------------------------------
 struct BoxFrame {
     V3 c;          // centre relative to A's position
@@ -942,6 +943,66 @@ inline int argmaxAbs3(const float d[3]) {   // lowest index on ties
     return k;
 }
 
+// Capsule against box: the capsule's core segment is clipped against the side planes of the box face that
+// faces the capsule (the face most aligned with the contact normal); the ends of the clipped segment that
+// lie within the radius of that face are the contact points (position = midpoint between the capsule's
+// surface point below the end and its projection on the face, depth = radius - height above the face).
+// Two points for a capsule lying on a face, one for a tilted capsule; none kept -> the narrowphase point.
+void capsuleBoxManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, const Xf& tb, const AxrefShape& sb,
+                        AxrefManifold& m) {
+    const V3 origin = ta.p;
+    const V3 n = mk(c.nx, c.ny, c.nz);
+    const bool boxIsA = sa.type == SHAPE_BOX;
+    const BoxFrame R = boxIsA ? makeBoxFrame(ta, sa, origin) : makeBoxFrame(tb, sb, origin);
+    const Xf& tC = boxIsA ? tb : ta;
+    const AxrefShape& sC = boxIsA ? sb : sa;
+    const M3 mm = quatToMat3(tC.q);
+    const V3 e = mm.c1 * ((sC.p1 * 0.5f) * tC.s.y);   // half segment, as the narrowphase core
+    const V3 cc = tC.p - origin;
+    const float r = sC.p0;
+    const V3 p0 = cc - e, seg = e * 2.0f;
+    const V3 toCap = boxIsA ? n : -n;                  // from the box towards the capsule
+    const float d[3] = {dot(toCap, R.ax[0]), dot(toCap, R.ax[1]), dot(toCap, R.ax[2])};
+    const int i = argmaxAbs3(d);
+    const V3 nr = R.ax[i] * ((d[i] >= 0.0f) ? 1.0f : -1.0f);
+    float t0 = 0.0f, t1 = 1.0f;
+    for (int side = 0; side < 4; ++side) {
+        const int w = (i + 1 + (side >> 1)) % 3;
+        const V3 pn = R.ax[w] * ((side & 1) ? -1.0f : 1.0f);
+        const float d0 = dot(p0 - R.c, pn) - R.h[w];   // <= 0 inside
+        const float dd = dot(seg, pn);
+        if (dd > 0.0f) {
+            const float t = -d0 / dd;
+            if (t < t1) t1 = t;
+        } else if (dd < 0.0f) {
+            const float t = -d0 / dd;
+            if (t > t0) t0 = t;
+        } else if (d0 > 0.0f) {
+            return;   // parallel to the plane and outside it
+        }
+    }
+    if (!(t0 <= t1)) return;
+    const float tt[2] = {t0, t1};
+    const int cand = (t0 == t1) ? 1 : 2;
+    int cnt = 0;
+    for (int k = 0; k < cand; ++k) {
+        const V3 q = p0 + seg * tt[k];
+        const float sep = (dot(q - R.c, nr) - R.h[i]) - r;
+        if (sep <= 0.0f) {
+            const V3 w = (q - nr * (r + sep * 0.5f)) + origin;
+            m.px[cnt] = w.x; m.py[cnt] = w.y; m.pz[cnt] = w.z;
+            m.depth[cnt] = -sep;
+            ++cnt;
+        }
+    }
+    if (cnt == 0) {   // nothing within reach of the face (edge / corner contact): the narrowphase point stands
+        m.px[0] = c.px; m.py[0] = c.py; m.pz[0] = c.pz;
+        m.depth[0] = c.depth;
+        return;
+    }
+    m.count = (uint32_t)cnt;
+}
+
 void buildManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, const Xf& tb,
                    const AxrefShape& sb, AxrefManifold& m) {
     m.a = c.a; m.b = c.b;
@@ -950,6 +1011,10 @@ void buildManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, co
     for (int k = 0; k < 4; ++k) { m.px[k] = m.py[k] = m.pz[k] = 0.0f; m.depth[k] = 0.0f; }
     m.px[0] = c.px; m.py[0] = c.py; m.pz[0] = c.pz;
     m.depth[0] = c.depth;
+    if ((sa.type == SHAPE_BOX && sb.type == SHAPE_CAPSULE) || (sa.type == SHAPE_CAPSULE && sb.type == SHAPE_BOX)) {
+        capsuleBoxManifold(c, ta, sa, tb, sb, m);
+        return;
+    }
     if (sa.type != SHAPE_BOX || sb.type != SHAPE_BOX) return;
     const V3 origin = ta.p;
     const V3 n = mk(c.nx, c.ny, c.nz);

@@ -31,7 +31,8 @@ def _points(m):
 def test_sphere_pairs_keep_the_single_point():
     a, b = O.xf((0, 0, 0)), O.xf((0.9, 0, 0))
     for sa, sb in ((O.sphere(0.5), O.sphere(0.5)), (O.sphere(0.5), O.box(0.5, 0.5, 0.5)),
-                   (O.box(0.5, 0.5, 0.5), O.sphere(0.5)), (O.capsule(0.45, 1.0), O.box(0.5, 0.5, 0.5))):
+                   (O.box(0.5, 0.5, 0.5), O.sphere(0.5)), (O.capsule(0.45, 1.0), O.sphere(0.5)),
+                   (O.capsule(0.45, 1.0), O.capsule(0.45, 0.5))):
         c, m = _manifold(a, sa, b, sb)
         assert m["count"] == 1
         assert (m["px"][0], m["py"][0], m["pz"][0], m["depth"][0]) == (c["px"], c["py"], c["pz"], c["depth"])
@@ -196,3 +197,86 @@ def test_scene_totals_and_determinism():
     assert (m1["count"][~bb_mask] == 1).all()
     assert (m1["count"] >= 1).all() and (m1["count"] <= 4).all()
     assert (m1["count"][bb_mask] > 1).any()
+
+
+# ---- capsule against box --------------------------------------------------------------------------------
+def _seg_dist(p, x, sh):
+    """Distance (float64) from world point p to the capsule's core segment."""
+    x = x.astype(np.float64)
+    e = _rot(x[3:7])[:, 1] * (float(sh[2]) * 0.5 * x[8])
+    a, b = x[:3] - e, x[:3] + e
+    u = np.clip((p - a) @ (b - a) / max((b - a) @ (b - a), 1e-300), 0, 1)
+    return np.linalg.norm(p - a - u * (b - a))
+
+
+def test_capsule_lying_on_a_box_gives_two_points():
+    box, cap = O.box(2.0, 2.0, 0.5), O.capsule(0.3, 2.0)
+    a = O.xf((0, 0, 0))
+    b = O.xf((0.2, 0.1, 0.75))                      # axis along y, 0.05 deep into the top face
+    c, m = _manifold(a, box, b, cap)
+    np.testing.assert_allclose([c["nx"], c["ny"], c["nz"]], [0, 0, 1], atol=1e-4)
+    p, d = _points(m)
+    assert m["count"] == 2
+    np.testing.assert_allclose(d, 0.05, atol=1e-5)
+    np.testing.assert_allclose(p, [[0.2, -0.9, 0.475], [0.2, 1.1, 0.475]], atol=1e-5)
+    # the same pair with the capsule as body a: same points, normal flipped
+    c2, m2 = _manifold(b, cap, a, box)
+    p2, d2 = _points(m2)
+    assert m2["count"] == 2
+    np.testing.assert_allclose(sorted(map(tuple, np.round(p2, 5))), sorted(map(tuple, np.round(p, 5))), atol=1e-5)
+    np.testing.assert_allclose([c2["nz"]], [-1], atol=1e-4)
+    # overhanging the edge: the segment is clipped at the face boundary y = 2
+    b3 = O.xf((0.2, 1.8, 0.75))
+    _, m3 = _manifold(a, box, b3, cap)
+    p3, _ = _points(m3)
+    assert m3["count"] == 2
+    np.testing.assert_allclose(sorted(p3[:, 1]), [0.8, 2.0], atol=1e-5)
+    # tilted: only the lower end is within reach of the face
+    b4 = O.xf((0.0, 0.0, 1.2), O.axis_angle((1, 0, 0), np.pi / 6))
+    c4, m4 = _manifold(a, box, b4, cap)
+    assert m4["count"] == 1
+    p4, d4 = _points(m4)
+    assert abs(d4[0] - c4["depth"]) < 1e-3
+
+
+def test_random_capsule_box_manifolds_lie_on_both_shapes():
+    rng = np.random.default_rng(11)
+    two = one = 0
+    for _ in range(500):
+        qa = rng.normal(size=4); qa /= np.linalg.norm(qa)
+        box = O.box(*rng.uniform(0.4, 1.0, 3))
+        cap = O.capsule(rng.uniform(0.15, 0.3), rng.uniform(0.4, 1.5))
+        xa = O.xf(rng.uniform(-1, 1, 3), qa, rng.uniform(0.8, 1.3, 3))
+        R = _rot(qa)
+        # put the capsule near a face, its axis roughly in the face plane
+        k = rng.integers(0, 3)
+        h = abs(box[1 + k] * xa[7 + k])
+        axis = R[:, (k + 1) % 3] * np.cos(0.2 * rng.normal()) + R[:, k] * 0.15 * rng.normal() + R[:, (k + 2) % 3] * rng.normal() * 0.5
+        axis /= np.linalg.norm(axis)
+        y = np.array([0.0, 1.0, 0.0])
+        v = np.cross(y, axis); sn = np.linalg.norm(v); cs = y @ axis
+        qb = np.array([*(v / max(sn, 1e-12) * np.sin(np.arctan2(sn, cs) / 2)), np.cos(np.arctan2(sn, cs) / 2)])
+        pos = xa[:3] + R[:, k] * (h + cap[1] * rng.uniform(0.6, 1.0)) * rng.choice([-1, 1]) + R[:, (k + 1) % 3] * rng.uniform(-0.3, 0.3)
+        xb = O.xf(pos, qb)
+        for (x0, s0, x1, s1) in ((xa, box, xb, cap), (xb, cap, xa, box)):
+            hit, c, _, _ = O.collide_pair(x0, s0, x1, s1)
+            if not hit:
+                continue
+            c = c.copy(); c["a"], c["b"] = 0, 1
+            m, _ = O.manifolds(np.stack([x0, x1]), np.array([s0, s1], dtype=O.SHAPE_DT), np.array([c]))
+            p, d = _points(m[0])
+            assert 1 <= len(p) <= 2
+            two += len(p) == 2
+            one += len(p) == 1
+            if len(p) == 1 and np.allclose(p[0], [c["px"], c["py"], c["pz"]]):
+                continue          # fallback to the narrowphase point
+            xc, sc = (x1, s1) if s1[0] == 2 else (x0, s0)
+            xbx, sbx = (x0, s0) if s1[0] == 2 else (x1, s1)
+            for pk, dk in zip(p, d):
+                # half a depth inside the capsule's surface, and no farther than that from the box
+                # (the end of the clipped segment above the point is at r - dk/2; a tilted segment may pass
+                # closer, never farther)
+                assert _seg_dist(pk, xc, sc) <= sc[1] - 0.5 * dk + 3e-4, (pk, dk)
+                assert _box_sdist(pk, xbx, sbx) <= 3e-4
+                assert dk <= 1.5 * c["depth"] + 2e-3     # measured along the face normal, not the (minimal) contact normal
+    assert two > 60 and one > 60, (two, one)

@@ -313,3 +313,14 @@ def test_ccd_pairs_match_oracle():
         w.ccd_pairs(np.array([[0, s.n]], np.uint32), disp)             # body index out of range
     assert e.value.code == 601
     w.close()
+
+
+def test_manifolds_capsule_box_mix():
+    s, _ = _query_scene(n=20000, seed=41, L=24.0)     # boxes, spheres, capsules, hulls; dense enough to touch
+    gm, bitwise = _manifold_parity(s, pairs_per_body=16)
+    assert bitwise
+    ta, tb = s.shapes["type"][gm["a"]], s.shapes["type"][gm["b"]]
+    capbox = ((ta == 1) & (tb == 2)) | ((ta == 2) & (tb == 1))
+    assert capbox.sum() > 200 and (gm["count"][capbox] == 2).sum() > 20
+    other = ~capbox & ~((ta == 1) & (tb == 1))
+    assert (gm["count"][other] == 1).all()

@@ -327,3 +327,36 @@ def test_distances_mode_matches_default_contact_set():
     for k, (a, b) in enumerate(pairs):
         is_contact[k] = (a, b) in key
     assert (d2[is_contact] <= 0).all() and (d2[~is_contact] > 0).all()
+
+
+def test_epa_depth_is_the_global_minimum_vs_minkowski_hull():
+    """Penetration depth = distance from the origin to the boundary of the Minkowski difference A - B.
+    Independent restatement: scipy's convex hull of all pairwise vertex differences; the nearest facet
+    plane gives the depth and the normal.  Pins EPA's optimality (not just validity along its own normal)."""
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(12)
+    checked = 0
+    for _ in range(150):
+        va = (rng.normal(size=(12, 3)) * rng.uniform(0.3, 0.5, 3)).astype(np.float32)
+        vb = (rng.normal(size=(12, 3)) * rng.uniform(0.3, 0.5, 3)).astype(np.float32)
+        hull = np.vstack([va, vb])
+        ta = O.xf(rng.uniform(0, 0.5, 3), O.axis_angle(rng.normal(size=3), rng.uniform(0, 6.28)), rng.uniform(0.7, 1.3, 3))
+        tb = O.xf(rng.uniform(0, 0.5, 3), O.axis_angle(rng.normal(size=3), rng.uniform(0, 6.28)), rng.uniform(0.7, 1.3, 3))
+        hit, con, dist, epa = O.collide_pair(ta, O.hull_shape(0, 12), tb, O.hull_shape(12, 12), hull)
+        WA = np.array([O.transform_point(ta, v) for v in va], float)
+        WB = np.array([O.transform_point(tb, v) for v in vb], float)
+        md = ConvexHull((WA[:, None, :] - WB[None, :, :]).reshape(-1, 3))
+        off = md.equations[:, 3]                      # n.x + off <= 0 inside; origin inside <=> all off <= 0
+        if not (off < -1e-3).all():
+            continue                                  # separated or grazing: covered by the QP tests
+        k = int(np.argmax(off))
+        depth = -off[k]
+        assert hit and epa and con["status"] == 0
+        assert abs(con["depth"] - depth) < 1e-3 * max(1.0, depth), (con["depth"], depth)
+        # shifting B by depth along the facet's outward normal moves A - B the other way, so the origin leaves
+        # through facet k: the contact normal (a to b) is that outward normal
+        n = np.array([con["nx"], con["ny"], con["nz"]], float)
+        if sorted(off)[-1] - sorted(off)[-2] > 1e-3:  # unique nearest facet: the normal is determined
+            assert np.dot(n, md.equations[k, :3]) > 0.999, (n, md.equations[k, :3])
+        checked += 1
+    assert checked > 60, checked

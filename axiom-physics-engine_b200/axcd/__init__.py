@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
-    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs",
+    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_pin_host_buffer", "axcd_unpin_host_buffer",
     "axcd_set_filters", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
     "axcd_set_ghosts_device",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
@@ -114,7 +114,7 @@ def load_library():
                      "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
                      "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
                      "axcd_pack_ghosts", "axcd_set_ghosts_device", "axcd_set_filters",
-                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs"):
+                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_pin_host_buffer", "axcd_unpin_host_buffer"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -132,6 +132,8 @@ def load_library():
         lib.axcd_query_aabbs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                          C.c_void_p]
         lib.axcd_set_awake.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        lib.axcd_pin_host_buffer.argtypes = [C.c_void_p, C.c_uint64]
+        lib.axcd_unpin_host_buffer.argtypes = [C.c_void_p]
         lib.axcd_ccd_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.axcd_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.axcd_test_sort_pairs32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,

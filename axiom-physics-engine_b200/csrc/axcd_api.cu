@@ -257,6 +257,26 @@ const char* axcd_error_string(int32_t code) {
     }
 }
 
+int32_t axcd_pin_host_buffer(void* hostPtr, uint64_t bytes) {
+    if (!hostPtr) return AXCD_ERR_NULL_POINTER;
+    if (bytes == 0) return AXCD_ERR_INVALID_PARAM;
+    const cudaError_t e = cudaHostRegister(hostPtr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? AXCD_ERR_GPU_ALLOC : AXCD_ERR_GPU_FAILED;
+    }
+    return AXCD_OK;
+}
+
+int32_t axcd_unpin_host_buffer(void* hostPtr) {
+    if (!hostPtr) return AXCD_ERR_NULL_POINTER;
+    if (cudaHostUnregister(hostPtr) != cudaSuccess) {
+        cudaGetLastError();
+        return AXCD_ERR_GPU_FAILED;
+    }
+    return AXCD_OK;
+}
+
 const char* axcd_last_device_error(AxcdContext* ctx) { return ctx ? ctx->lastErr : ""; }
 
 void axcd_destroy(AxcdContext* ctx) {

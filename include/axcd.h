@@ -287,6 +287,12 @@ AXCD_API int32_t axcd_pack_ghosts(AxcdContext* ctx, const float* edges, uint32_t
 AXCD_API int32_t axcd_set_ghosts_device(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts,
                                         const void* devRecords);
 
+/* Page-locks (and later releases) a caller-owned host buffer so that the per-step copies — transforms in,
+ * contacts / manifolds out — run at full PCIe rate; the engine does not need the CUDA headers for it.
+ * Optional: every entry point also accepts pageable memory (about half the copy bandwidth).       */
+AXCD_API int32_t axcd_pin_host_buffer(void* hostPtr, uint64_t bytes);
+AXCD_API int32_t axcd_unpin_host_buffer(void* hostPtr);
+
 /* == axiom::core::errorCodeToString (src/core/error_code.cpp:5-62); static storage.            */
 AXCD_API const char* axcd_error_string(int32_t code);
 /* CUDA error text of the last failure on this context (static storage), "" if none.           */

@@ -92,6 +92,18 @@ struct CollisionConfig : AxcdConfig {
     CollisionConfig() { axcd_default_config(this); }
 };
 
+/// Page-locks a caller-owned buffer for the lifetime of this object (full-rate host <-> device copies).
+class PinnedRegion {
+public:
+    PinnedRegion(void* ptr, std::size_t bytes) : ptr_(axcd_pin_host_buffer(ptr, bytes) == AXCD_OK ? ptr : nullptr) {}
+    ~PinnedRegion() { if (ptr_) axcd_unpin_host_buffer(ptr_); }
+    PinnedRegion(const PinnedRegion&) = delete;
+    PinnedRegion& operator=(const PinnedRegion&) = delete;
+    bool pinned() const noexcept { return ptr_ != nullptr; }
+private:
+    void* ptr_;
+};
+
 /// Owns one device context (one GPU, one stream).  Not thread-safe, like the reference's
 /// device-facing objects (include/axiom/gpu/vk_command.hpp:15).
 class CollisionWorld {

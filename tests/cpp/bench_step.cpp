@@ -2,7 +2,7 @@
 // PhysicsWorld::step would (CLAUDE.md:162-178): setTransforms (host -> device), Broadphase::update,
 // Narrowphase::detectCollisions, getContacts (device -> host).  Prints one line:
 //     bodies pairs contacts ms_per_step_device ms_per_step_end_to_end
-// usage: bench_step [bodies=1000000] [domain=100] [seed=3] [steps=20]
+// usage: bench_step [bodies=1000000] [domain=100] [seed=3] [steps=20] [pin]
 // exit code 77 when no CUDA device is present.
 #include "axiom/collision/collision_world.hpp"
 #include "axcd_scene.h"
@@ -10,6 +10,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
+#include <string>
 #include <vector>
 
 using namespace axiom;
@@ -39,6 +41,14 @@ int main(int argc, char** argv) {
     collision::Broadphase broadphase(world);
     collision::Narrowphase narrowphase(world);
     std::vector<collision::ContactPoint> contacts(cfg.maxContacts);
+    // optional 5th argument "pin": page-lock the per-step buffers (transforms in, contacts out)
+    const bool pin = argc > 5 && std::string(argv[5]) == "pin";
+    std::unique_ptr<collision::PinnedRegion> pinXf, pinCon;
+    if (pin) {
+        pinXf = std::make_unique<collision::PinnedRegion>(xf.data(), xf.size() * sizeof(math::Transform));
+        pinCon = std::make_unique<collision::PinnedRegion>(contacts.data(), contacts.size() * sizeof(collision::ContactPoint));
+        if (!pinXf->pinned() || !pinCon->pinned()) return 10;
+    }
 
     double deviceMs = 0.0;
     std::uint32_t pairs = 0, ncon = 0;

@@ -19,8 +19,8 @@ SCENE_LIB_PATH = os.path.join(PKG_DIR, "libaxcd_scene.so")
 
 SHAPE_SPHERE, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_PLANE, SHAPE_CONVEX, SHAPE_MESH = range(6)
 FLAG_PAIR_DISTANCES = 1
-FLAG_EPA_COOPERATIVE = 2
 FLAG_TEMPORAL_COHERENCE = 4
+FLAG_BOXBOX_GJK_EPA = 8
 
 SHAPE_DT = np.dtype([("type", "<u4"), ("p0", "<f4"), ("p1", "<f4"), ("p2", "<f4")])
 CONTACT_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),
@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_pin_host_buffer", "axcd_unpin_host_buffer",
     "axcd_set_filters", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
     "axcd_set_ghosts_device",
-    "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench",
+    "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench", "axcd_test_fp32_peak",
 ]
 SCENE_SYMBOLS = ["axcd_scene_generate", "axcd_scene_generate_worlds", "axcd_scene_rng_u32"]
 
@@ -146,6 +146,8 @@ def load_library():
         lib.axcd_pack_ghosts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         lib.axcd_set_ghosts_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         lib.axcd_test_sort_bench.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        lib.axcd_test_fp32_peak.restype = C.c_int32
+        lib.axcd_test_fp32_peak.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -513,6 +515,12 @@ class CollisionWorld:
         ms = C.c_float(0)
         self._check(self._lib.axcd_test_sort_bench(self._ctx, n, key_bits, iters, C.byref(ms)), "sort_bench")
         return ms.value
+
+    def fp32_peak(self, iters=4096):
+        """Measured FP32 FMA-chain peak of the device in TFLOP/s."""
+        tf = C.c_float(0)
+        self._check(self._lib.axcd_test_fp32_peak(self._ctx, iters, C.byref(tf)), "fp32_peak")
+        return tf.value
 
     def test_sort_keys64(self, keys, key_bits=64):
         keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()

@@ -8,7 +8,6 @@
 #include "axcd.h"
 #include "axcd_common.cuh"
 #include "axcd_lbvh.cuh"
-#include "axcd_epa_coop.cuh"
 #include "axcd_epa_warp.cuh"
 #include "axcd_narrow.cuh"
 #include "axcd_manifold.cuh"
@@ -42,6 +41,7 @@ struct AxcdContext {
     cudaStream_t stream = nullptr;
     bool ownStream = false;
     int stage = ST_NONE;
+    int numSMs = kNumSMs;    // multiprocessor count of the device (grid sizing of the persistent kernels)
     uint32_t n = 0;          // bodies
     uint32_t nHull = 0;
     bool hasWorlds = false;
@@ -79,6 +79,7 @@ struct AxcdContext {
     BvhNode* dNodes = nullptr;       // float nodes for the scene queries: allocated and built by the first query after a broadphase
     bool queryNodesValid = false;
     bool hasHulls = false;           // any convex-hull shape in the current scene (ghosts are never hulls)
+    bool hasGenericShapes = false;   // any hull or capsule among the owned bodies: pairs that need GJK can exist
     uint32_t* dWorldEnd = nullptr;
     uint2* dPairsTmp = nullptr;      // candidate pairs as found (unordered)
     uint2* dPairs = nullptr;         // candidate pairs, canonical order
@@ -317,6 +318,12 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
     AxcdContext* ctx = new (std::nothrow) AxcdContext();
     if (!ctx) return AXCD_ERR_OUT_OF_MEMORY;
     ctx->cfg = *cfg;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->deviceOrdinal) == cudaSuccess && sms > 0)
+            ctx->numSMs = sms;
+        cudaGetLastError();
+    }
     if (ctx->cfg.epaMaxFaces > (uint32_t)kEpaHardFaces) ctx->cfg.epaMaxFaces = kEpaHardFaces;
     for (int i = 0; i < EV_COUNT; ++i) {
         ctx->ev[i] = nullptr;
@@ -410,7 +417,7 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
     if (nHullVerts && !hullXYZ) return AXCD_ERR_NULL_POINTER;
     if (n > ctx->cfg.maxBodies || nHullVerts > ctx->cfg.maxHullVerts) return AXCD_ERR_OUT_OF_RANGE;
     if (ctx->cfg.numWorlds > 1 && n && !worldId) return AXCD_ERR_INVALID_PARAM;
-    bool anyHull = false;
+    bool anyHull = false, anyCapsule = false;
     for (uint32_t i = 0; i < n; ++i) {
         const AxcdShape& s = shapes[i];
         if (s.type == AXCD_SHAPE_CONVEX) {
@@ -422,9 +429,11 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
         } else if (s.type != AXCD_SHAPE_SPHERE && s.type != AXCD_SHAPE_BOX && s.type != AXCD_SHAPE_CAPSULE) {
             return AXCD_ERR_INVALID_SHAPE;   // Plane / Mesh are not in scope
         }
+        if (s.type == AXCD_SHAPE_CAPSULE) anyCapsule = true;
         if (ctx->cfg.numWorlds > 1 && worldId[i] >= ctx->cfg.numWorlds) return AXCD_ERR_OUT_OF_RANGE;
     }
     ctx->hasHulls = anyHull;
+    ctx->hasGenericShapes = anyHull || anyCapsule;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     CU(cudaMemcpyAsync(ctx->dShapes, shapes, sizeof(AxcdShape) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (nHullVerts) {
@@ -503,7 +512,7 @@ int32_t axcd_refit(AxcdContext* ctx) {
 #else
             (void)blocks;
             uint32_t tiles = (ctx->n + kRefitThreads - 1) / kRefitThreads;
-            const uint32_t grid = tiles < (uint32_t)kNumSMs * kRefitTmaBlocksPerSM ? tiles : kNumSMs * kRefitTmaBlocksPerSM;
+            const uint32_t grid = tiles < (uint32_t)ctx->numSMs * kRefitTmaBlocksPerSM ? tiles : ctx->numSMs * kRefitTmaBlocksPerSM;
             refitTmaKernel<<<grid, kRefitThreads, 0, ctx->stream>>>(
                 ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dAabb, ctx->dType8, ctx->n, ctx->cfg.aabbMargin, ctx->dCtr,
                 ctrNext, ctx->dCtrInit);
@@ -607,7 +616,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         exclusiveScanKernel<<<scanTiles, kScanThreads, 0, st>>>(ctx->dBodyCount, ctx->dBodyStart, ctx->dBodyCount + n, n,
                                                                 ctx->dScanStatus, &ctx->dCtr->scanTicket,
                                                                 &ctx->dCtr->storedPairs);
-        scatterPairsKernel<<<kNumSMs * AXCD_SCATTER_BLOCKS, 256, 0, st>>>(ctx->dPairsTmp, &ctx->dCtr->pairCount, ctx->cfg.maxPairs,
+        scatterPairsKernel<<<ctx->numSMs * AXCD_SCATTER_BLOCKS, 256, 0, st>>>(ctx->dPairsTmp, &ctx->dCtr->pairCount, ctx->cfg.maxPairs,
                                                         ctx->dBodyCount + n, ctx->dSegB);
         sortSegmentsKernel<<<(n + AXCD_SEGSORT_THREADS - 1) / AXCD_SEGSORT_THREADS, AXCD_SEGSORT_THREADS, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
         CU(cudaGetLastError());
@@ -650,43 +659,49 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         p.gjkTol = ctx->cfg.gjkTol;
         p.epaTol = ctx->cfg.epaTol;
         p.wantDistances = (ctx->cfg.flags & AXCD_FLAG_PAIR_DISTANCES) ? 1u : 0u;
+        p.boxBoxGeneric = (ctx->cfg.flags & AXCD_FLAG_BOXBOX_GJK_EPA) ? 1u : 0u;
         // The pair count lives on the device: persistent grids sized for the capacity, capped at a
         // few resident waves.
         const uint32_t mp = ctx->cfg.maxPairs;
         uint32_t tiles = (mp + kGjkThreads - 1) / kGjkThreads;
-        if (tiles > (uint32_t)kNumSMs * AXCD_GJK_MIN_BLOCKS) tiles = kNumSMs * AXCD_GJK_MIN_BLOCKS;   // one resident wave
+        if (tiles > (uint32_t)ctx->numSMs * AXCD_GJK_MIN_BLOCKS) tiles = ctx->numSMs * AXCD_GJK_MIN_BLOCKS;   // one resident wave
         const uint32_t slotTilesMax = (mp + kSlotTile - 1) / kSlotTile;
-        const uint32_t slotBlocks = slotTilesMax < (uint32_t)kNumSMs * 4 ? slotTilesMax : kNumSMs * 4;
+        const uint32_t slotBlocks = slotTilesMax < (uint32_t)ctx->numSMs * 4 ? slotTilesMax : ctx->numSMs * 4;
         CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * (slotTilesMax + 1), st));
         NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow, ctx->dEpaSpill, ctx->spillCap};
         const uint2* pairs = ctx->dPairs;
         const uint32_t* pairCount = &ctx->dCtr->pairCount;
         const uint32_t chunkCap = chunkCapFor(mp);
+        // Pair classes decided in closed form (sphere-sphere, sphere-box, box-box by SAT) and the classes that
+        // need GJK (hulls, capsules; box-box when forced, or when its separation distance is wanted) go to
+        // separate chunk lists and kernels.  A scene that cannot produce a generic pair skips those launches.
+        const bool boxGeneric = p.boxBoxGeneric || p.wantDistances;
+        const uint32_t genericMask = (1u << 5) | (boxGeneric ? (1u << 4) : 0u);
+        const bool anyGeneric = ctx->hasGenericShapes || boxGeneric || ctx->slabOn || ctx->n != ctx->nOwned;
         classifyPairsKernel<<<classifyBlocksFor(mp), kClsThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dChunks,
-                                                                            chunkCap, ctx->dCtr);
-        gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dHull, p,
-                                                 ctx->dFlags, ctx->dTmpContacts, q, ctx->cfg.maxContacts,
-                                                 ctx->dPairDist, ctx->dCtr);
+                                                                            chunkCap, genericMask, ctx->dCtr);
+        closedFormKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dFlags,
+                                                        ctx->dTmpContacts, ctx->dPairDist, ctx->dCtr);
+        if (anyGeneric)
+            gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+                                                     ctx->dFlags, ctx->dTmpContacts, q, ctx->cfg.maxContacts,
+                                                     ctx->dPairDist, ctx->dCtr);
         slotKernel<<<slotBlocks, kSlotThreads, 0, st>>>(ctx->dFlags, pairCount, mp, ctx->dTmpContacts, ctx->dContacts,
                                                         ctx->cfg.maxContacts, ctx->dSlots, ctx->dSlotStatus, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_GJK);
         // EPA: persistent grids, queue lengths are read on the device
-        if (!(ctx->cfg.flags & AXCD_FLAG_EPA_COOPERATIVE)) {
-            epaKernel<<<kNumSMs * kEpaBlocksPerSM, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf,
+        if (anyGeneric) {
+            epaKernel<<<ctx->numSMs * kEpaBlocksPerSM, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf,
                                                                        ctx->dShapes, ctx->dHull, p, ctx->dContacts,
                                                                        ctx->cfg.maxContacts, ctx->dSlots,
                                                                        ctx->dPairDist, ctx->dCtr);
-        } else {
-            epaCoopKernel<<<kNumSMs * 3, kCoopThreads, 0, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf, ctx->dShapes,
-                                                                ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts,
-                                                                ctx->dSlots, ctx->dPairDist, ctx->dCtr);
+            epaWarpFallbackKernel<<<ctx->numSMs * kWarpFbBlocksPerSM, kWarpFbThreads, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+                                                                          ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
+                                                                          ctx->dPairDist, ctx->dCtr);
+            CU(cudaGetLastError());
         }
-        epaWarpFallbackKernel<<<kNumSMs * kWarpFbBlocksPerSM, kWarpFbThreads, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
-                                                                      ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
-                                                                      ctx->dPairDist, ctx->dCtr);
-        CU(cudaGetLastError());
-        ctx->launches[2] = 5;   // classify, GJK, slots, EPA, EPA fallback
+        ctx->launches[2] = anyGeneric ? 6 : 3;   // classify, closed forms, [GJK], slots, [EPA, EPA fallback]
     } else {
         recordEv(ctx, EV_GJK);
     }
@@ -833,7 +848,7 @@ int32_t axcd_build_manifolds(AxcdContext* ctx) {
     if (!ctx->dManifolds) CU(dalloc(&ctx->dManifolds, (size_t)ctx->cfg.maxContacts));
     if (ctx->n >= 2) {
         uint32_t blocks = (ctx->cfg.maxContacts + kManThreads - 1) / kManThreads;
-        if (blocks > (uint32_t)kNumSMs * 8) blocks = kNumSMs * 8;   // the contact count lives on the device
+        if (blocks > (uint32_t)ctx->numSMs * 8) blocks = ctx->numSMs * 8;   // the contact count lives on the device
         manifoldKernel<<<blocks, kManThreads, 0, ctx->stream>>>(ctx->dContacts, &ctx->dCtr->contactCount, ctx->cfg.maxContacts,
                                                                 ctx->dXf, ctx->dShapes,
                                                                 reinterpret_cast<float4*>(ctx->dManifolds),
@@ -974,6 +989,7 @@ int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRay
     p.gjkTol = ctx->cfg.gjkTol;
     p.epaTol = ctx->cfg.epaTol;
     p.wantDistances = 1u;
+    p.boxBoxGeneric = 0u;
     const uint32_t rb = (nq + kQueryThreads - 1) / kQueryThreads;
     if (ctx->hasHulls)
         raycastKernel<true><<<rb, kQueryThreads, 0, st>>>(T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes,
@@ -1012,6 +1028,7 @@ int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs
     p.gjkTol = ctx->cfg.gjkTol;
     p.epaTol = ctx->cfg.epaTol;
     p.wantDistances = 1u;
+    p.boxBoxGeneric = 0u;
     ccdKernel<<<(npairs + kCcdThreads - 1) / kCcdThreads, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull,
                                                                                dDisp, p, static_cast<uint32_t*>(ctx->dQOut));
     CU(cudaGetLastError());
@@ -1218,7 +1235,7 @@ int32_t axcd_test_sort_bench(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uin
     float total = 0.0f;
     const int passes = (int)(keyBits + 7) / 8;
     for (uint32_t it = 0; it <= iters; ++it) {   // iteration 0 is a warm-up
-        fillRandomKeysKernel<<<kNumSMs * 8, 256, 0, st>>>(ctx->dKeys[0], ctx->dVals[0], n, keyBits, 0x9E3779B9u * (it + 1));
+        fillRandomKeysKernel<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->dKeys[0], ctx->dVals[0], n, keyBits, 0x9E3779B9u * (it + 1));
         CU(cudaEventRecord(e0, st));
         radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0, passes,
                                   ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st);
@@ -1231,6 +1248,52 @@ int32_t axcd_test_sort_bench(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uin
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *outMsPerSort = total / (float)iters;
+    return AXCD_OK;
+}
+
+// FP32 FMA-chain peak of the device (the roof the GJK / EPA kernels are measured against): every thread
+// runs 8 independent chains of explicit fmaf (the library is built -fmad=false, explicit calls still fuse),
+// 2 flops per FMA, timed with CUDA events on the context stream.
+namespace {
+__global__ void __launch_bounds__(256) fmaChainKernel(float* __restrict__ out, uint32_t iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+    for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;   // keeps the chains alive; never true in practice
+}
+}  // namespace
+
+int32_t axcd_test_fp32_peak(AxcdContext* ctx, uint32_t iters, float* outTflops) {
+    if (!ctx || !outTflops) return AXCD_ERR_NULL_POINTER;
+    if (iters == 0 || iters > (1u << 20)) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = ctx->numSMs * 8, threads = 256;   // 2048 resident threads per SM
+    float best = 0.0f;
+    for (int rep = 0; rep < 4; ++rep) {   // rep 0 warms up
+        CU(cudaEventRecord(e0, st));
+        fmaChainKernel<<<blocks, threads, 0, st>>>(reinterpret_cast<float*>(ctx->dSortHist), iters, 0.999f, 1e-3f);
+        CU(cudaEventRecord(e1, st));
+        CU(cudaStreamSynchronize(st));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)blocks * threads;
+        const float tf = (float)(flops / (ms * 1e-3) / 1e12);
+        if (rep && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *outTflops = best;
     return AXCD_OK;
 }
 

@@ -8,7 +8,8 @@
 
 namespace axcd {
 
-constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs.  Sizing constant (chunk capacity, classifier grid); launch grids of the
+                               // persistent kernels use the device's own count (AxcdContext::numSMs, queried at create)
 
 // decoupled look-back status words: 2 flag bits + 30 value bits
 constexpr uint32_t kFlagAggregate = 1u << 30;
@@ -96,6 +97,8 @@ struct Counters {
     uint32_t fallbackCursor; // next unclaimed overflow item (full-cap EPA)
     uint32_t gjkChunks;      // 32-pair class-homogeneous chunks queued for the GJK kernel
     uint32_t gjkChunkCursor; // next unclaimed chunk
+    uint32_t gjkChunksGeneric;       // chunks of the classes that need GJK (stored from the back of the chunk array)
+    uint32_t gjkChunkCursorGeneric;  // next unclaimed chunk of that list
     uint32_t travOverflow;   // set if a traversal stack ever filled up (the step then reports 505 instead of losing pairs)
     uint32_t movedBodies;    // temporal coherence: bodies whose tight box left their fat box this step
     uint32_t manifoldPoints; // contact points over all manifolds (PhysicsWorldStats::contactPointCount)

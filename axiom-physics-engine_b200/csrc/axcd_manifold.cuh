@@ -26,21 +26,7 @@ constexpr int kManWords = sizeof(AxcdManifold) / 4;   // 22
 static_assert(sizeof(AxcdManifold) == 88, "AxcdManifold layout");
 static_assert((2 * kManThreads * sizeof(AxcdManifold)) % 16 == 0, "a tile's records are whole float4s");
 
-struct BoxFrame {
-    V3 c;        // centre relative to A's position
-    V3 ax[3];    // unit axes: the columns of Quat::toMatrix
-    float h[3];  // half lengths |halfExtent * scale|
-};
-
-__device__ __forceinline__ BoxFrame makeBoxFrame(const BodyPose& t, uint4 sh, V3 origin) {
-    BoxFrame f;
-    quatToColumns(t.q, f.ax[0], f.ax[1], f.ax[2]);
-    f.c = t.p - origin;
-    f.h[0] = fabsf(__uint_as_float(sh.y) * t.s.x);
-    f.h[1] = fabsf(__uint_as_float(sh.z) * t.s.y);
-    f.h[2] = fabsf(__uint_as_float(sh.w) * t.s.z);
-    return f;
-}
+// BoxFrame / makeBoxFrame: axcd_narrow.cuh (shared with the box-box SAT)
 
 __device__ __forceinline__ int argmaxAbs3(float d0, float d1, float d2) {   // lowest index on ties
     int k = 0;

@@ -32,6 +32,7 @@ struct NarrowParams {
     uint32_t gjkMaxIters, epaMaxIters, epaMaxFaces;
     float gjkTol, epaTol;
     uint32_t wantDistances;
+    uint32_t boxBoxGeneric;   // AXCD_FLAG_BOXBOX_GJK_EPA: box-box pairs through GJK/EPA instead of the SAT
 };
 
 struct BodyPose {
@@ -423,6 +424,174 @@ __device__ __forceinline__ SphereBox sphereBox(V3 cS, float r, V3 cX, const Body
     o.nsx = -out;
     o.ps = cS + o.nsx * r;
     o.px = cS + out * gap;
+    return o;
+}
+
+// ---- box against box, closed form: the 15-axis separating-axis test -------------------------------------
+// (3 face normals of each box + 9 edge-edge cross products), as collision libraries dispatch this pair
+// class.  The Minkowski difference of two boxes is a polytope whose face normals are among those 15
+// directions, so the boxes are apart iff some axis has a negative overlap, and otherwise the penetration
+// depth is the smallest overlap and the contact normal that axis — the answer EPA converges to, at a few
+// hundred flops instead of 10-20 kflop.  Edge axes are compared un-normalised (cross-multiplied), only the
+// winner pays a square root; nearly parallel edge pairs (|a_i x b_j|^2 <= 1e-5) are skipped.  Ties keep the
+// earlier axis.  Witness points: face axis -> the other box's deepest vertex and its projection on the
+// face; edge-edge -> closest points of the two supporting edges (as segments).  Same expression trees as
+// the CPU oracle (oracle/axref.cpp boxBox).
+struct BoxFrame {
+    V3 c;        // centre relative to A's position
+    V3 ax[3];    // unit axes: the columns of Quat::toMatrix
+    float h[3];  // half lengths |halfExtent * scale|
+};
+
+__device__ __forceinline__ BoxFrame makeBoxFrame(const BodyPose& t, uint4 sh, V3 origin) {
+    BoxFrame f;
+    quatToColumns(t.q, f.ax[0], f.ax[1], f.ax[2]);
+    f.c = t.p - origin;
+    f.h[0] = fabsf(__uint_as_float(sh.y) * t.s.x);
+    f.h[1] = fabsf(__uint_as_float(sh.z) * t.s.y);
+    f.h[2] = fabsf(__uint_as_float(sh.w) * t.s.z);
+    return f;
+}
+
+constexpr float kSatParallelEps = 1e-5f;
+struct BoxBox {
+    bool contact;
+    float depth;
+    V3 n, pa, pb;   // unit normal from A to B, witness points on A and on B
+};
+__device__ __forceinline__ BoxBox boxBox(const BoxFrame& A, const BoxFrame& B) {
+    BoxBox o;
+    o.contact = false;
+    o.depth = 0.0f;
+    o.n = o.pa = o.pb = mk3(0.f, 0.f, 0.f);
+    const V3 t = B.c - A.c;
+    float R[3][3], AR[3][3], tA[3], tB[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        tA[i] = dot3(t, A.ax[i]);
+        tB[i] = dot3(t, B.ax[i]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            R[i][j] = dot3(A.ax[i], B.ax[j]);
+            AR[i][j] = fabsf(R[i][j]);
+        }
+    }
+    float bestOv = FLT_MAX, bestL2 = 1.0f;
+    int axis = -1;
+    bool apart = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {   // faces of A
+        const float rb = (B.h[0] * AR[i][0] + B.h[1] * AR[i][1]) + B.h[2] * AR[i][2];
+        const float ov = (A.h[i] + rb) - fabsf(tA[i]);
+        apart = apart || (ov < 0.0f);
+        if (ov < bestOv) {
+            bestOv = ov;
+            axis = i;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {   // faces of B
+        const float ra = (A.h[0] * AR[0][j] + A.h[1] * AR[1][j]) + A.h[2] * AR[2][j];
+        const float ov = (ra + B.h[j]) - fabsf(tB[j]);
+        apart = apart || (ov < 0.0f);
+        if (ov < bestOv) {
+            bestOv = ov;
+            axis = 3 + j;
+        }
+    }
+    if (apart || axis < 0) return o;   // a separating face axis, or NaN input (every compare false)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            const V3 L = cross3(A.ax[i], B.ax[j]);
+            const float l2 = dot3(L, L);
+            const float ra = A.h[i1] * AR[i2][j] + A.h[i2] * AR[i1][j];
+            const float rb = B.h[j1] * AR[i][j2] + B.h[j2] * AR[i][j1];
+            const float ov = (ra + rb) - fabsf(dot3(t, L));   // scaled by |L|
+            if (l2 > kSatParallelEps) {
+                apart = apart || (ov < 0.0f);
+                // ov / |L| < bestOv / |bestL|, cross-multiplied (all terms >= 0 unless already apart)
+                if (!apart && (ov * ov) * bestL2 < (bestOv * bestOv) * l2) {
+                    bestOv = ov;
+                    bestL2 = l2;
+                    axis = 6 + 3 * i + j;
+                }
+            }
+        }
+    }
+    if (apart) return o;
+    o.contact = true;
+    if (axis < 3) {
+        const int i = axis;
+        const float tAi = (i == 0) ? tA[0] : ((i == 1) ? tA[1] : tA[2]);
+        const V3 axi = (i == 0) ? A.ax[0] : ((i == 1) ? A.ax[1] : A.ax[2]);
+        const bool pos = tAi >= 0.0f;
+        o.n = pos ? axi : -axi;
+        o.depth = bestOv;
+        V3 v = B.c;   // B's deepest vertex: support of B in direction -n
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float rij = (i == 0) ? R[0][j] : ((i == 1) ? R[1][j] : R[2][j]);
+            const float dj = pos ? rij : -rij;
+            v = v + B.ax[j] * ((dj > 0.0f) ? -B.h[j] : B.h[j]);
+        }
+        o.pb = v;
+        o.pa = v + o.n * o.depth;
+    } else if (axis < 6) {
+        const int j = axis - 3;
+        const float tBj = (j == 0) ? tB[0] : ((j == 1) ? tB[1] : tB[2]);
+        const V3 axj = (j == 0) ? B.ax[0] : ((j == 1) ? B.ax[1] : B.ax[2]);
+        const bool pos = tBj >= 0.0f;
+        o.n = pos ? axj : -axj;
+        o.depth = bestOv;
+        V3 v = A.c;   // A's deepest vertex: support of A in direction n
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float rij = (j == 0) ? R[i][0] : ((j == 1) ? R[i][1] : R[i][2]);
+            const float di = pos ? rij : -rij;
+            v = v + A.ax[i] * ((di >= 0.0f) ? A.h[i] : -A.h[i]);
+        }
+        o.pa = v;
+        o.pb = v - o.n * o.depth;
+    } else {
+        const int i = (axis - 6) / 3, j = (axis - 6) % 3;
+        const V3 u = (i == 0) ? A.ax[0] : ((i == 1) ? A.ax[1] : A.ax[2]);
+        const V3 v = (j == 0) ? B.ax[0] : ((j == 1) ? B.ax[1] : B.ax[2]);
+        const float hu = (i == 0) ? A.h[0] : ((i == 1) ? A.h[1] : A.h[2]);
+        const float hv = (j == 0) ? B.h[0] : ((j == 1) ? B.h[1] : B.h[2]);
+        const V3 L = cross3(u, v);
+        const float invl = 1.0f / sqrtf(bestL2);
+        const bool pos = dot3(t, L) >= 0.0f;
+        o.n = L * (pos ? invl : -invl);
+        o.depth = bestOv * invl;
+        // centres of the two supporting edges
+        V3 ea = A.c, eb = B.c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k != i) ea = ea + A.ax[k] * ((dot3(o.n, A.ax[k]) >= 0.0f) ? A.h[k] : -A.h[k]);
+            if (k != j) eb = eb + B.ax[k] * ((dot3(o.n, B.ax[k]) > 0.0f) ? -B.h[k] : B.h[k]);
+        }
+        // closest points of the segments ea + u*s (|s| <= hu) and eb + v*q (|q| <= hv)
+        const V3 r = ea - eb;
+        const float a = dot3(u, u), e = dot3(v, v), b = dot3(u, v);
+        const float c = dot3(u, r), f = dot3(v, r);
+        const float denom = a * e - b * b;   // > 0: the edges are not parallel
+        float s = (b * f - c * e) / denom;
+        s = fminf(fmaxf(s, -hu), hu);
+        float q = (b * s + f) / e;
+        if (q < -hv) {
+            q = -hv;
+            s = fminf(fmaxf((b * q - c) / a, -hu), hu);
+        } else if (q > hv) {
+            q = hv;
+            s = fminf(fmaxf((b * q - c) / a, -hu), hu);
+        }
+        o.pa = ea + u * s;
+        o.pb = eb + v * q;
+    }
     return o;
 }
 
@@ -871,19 +1040,27 @@ __host__ __device__ constexpr uint32_t chunkCapFor(uint32_t maxPairs) {
     return maxPairs / 32 + classifyBlocksFor(maxPairs) * kNumClasses + 1;   // full chunks + every block's padded tails
 }
 
+// Two chunk lists share the `chunks` array: classes decided in closed form (sphere-sphere, sphere-box,
+// box-box by SAT) fill it from the front (ctr->gjkChunks), the classes in `genericMask` (hulls / capsules;
+// box-box when forced through GJK) from the back (ctr->gjkChunksGeneric), so closedFormKernel and gjkKernel
+// each walk their own list.
 __global__ void __launch_bounds__(kClsThreads)
 classifyPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
                     const uint8_t* __restrict__ type8, uint32_t* __restrict__ chunks, uint32_t chunkCap,
-                    Counters* __restrict__ ctr) {
+                    uint32_t genericMask, Counters* __restrict__ ctr) {
     __shared__ uint32_t sCarry[kNumClasses][32];   // < 32 leftovers per class from the earlier tiles
     __shared__ uint32_t sCarryN[kNumClasses];
     __shared__ uint32_t sCnt[kNumClasses];         // carry + this tile, per class
     __shared__ uint32_t sBase[kNumClasses];        // start of each class in sItems
     __shared__ uint32_t sChunkStart[kNumClasses + 1];   // first chunk (within the tile) of each class
+    __shared__ uint32_t sDst[kNumClasses];         // position of each class's first chunk in its list
     __shared__ uint32_t sItems[kClsTile + kNumClasses * 32];
-    __shared__ uint32_t sChunkBase;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t npairs = min(*pairCount, maxPairs);
+    // list position -> chunk index: closed list from the front, generic list from the back
+    auto chunkIndex = [&](int c, uint32_t posInList) -> uint32_t {
+        return ((genericMask >> c) & 1u) ? chunkCap - 1u - posInList : posInList;   // wraps past chunkCap if the list is too long
+    };
     if (tid < kNumClasses) sCarryN[tid] = 0;
     __syncthreads();
     for (uint32_t tileBase = blockIdx.x * kClsTile; tileBase < npairs; tileBase += gridDim.x * kClsTile) {
@@ -910,15 +1087,20 @@ classifyPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict_
         }
         __syncthreads();
         if (tid == 0) {
-            uint32_t run = 0, ch = 0;
+            uint32_t run = 0, ch = 0, chList[2] = {0u, 0u}, rel[kNumClasses];
             for (int c = 0; c < kNumClasses; ++c) {
                 sBase[c] = run;
                 sChunkStart[c] = ch;
                 run += sCnt[c];
                 ch += sCnt[c] >> 5;
+                const int g = (genericMask >> c) & 1u;
+                rel[c] = chList[g];
+                chList[g] += sCnt[c] >> 5;
             }
             sChunkStart[kNumClasses] = ch;
-            sChunkBase = ch ? atomicAdd(&ctr->gjkChunks, ch) : 0u;
+            const uint32_t base0 = chList[0] ? atomicAdd(&ctr->gjkChunks, chList[0]) : 0u;
+            const uint32_t base1 = chList[1] ? atomicAdd(&ctr->gjkChunksGeneric, chList[1]) : 0u;
+            for (int c = 0; c < kNumClasses; ++c) sDst[c] = (((genericMask >> c) & 1u) ? base1 : base0) + rel[c];
         }
         __syncthreads();
         if (tid < kNumClasses * 32) {
@@ -936,7 +1118,7 @@ classifyPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict_
             int c = 0;
 #pragma unroll
             for (int t = 1; t < kNumClasses; ++t) c += (ch >= sChunkStart[t]) ? 1 : 0;
-            const uint32_t g = sChunkBase + ch;
+            const uint32_t g = chunkIndex(c, sDst[c] + (ch - sChunkStart[c]));
             if (g < chunkCap) chunks[(size_t)g * 32 + (e & 31)] = sItems[sBase[c] + ((ch - sChunkStart[c]) << 5) + (e & 31)];
         }
         uint32_t carryVal = 0, rem = 0;
@@ -955,25 +1137,113 @@ classifyPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict_
     }
     // what is left: one padded chunk per class that still holds pairs
     if (tid == 0) {
-        uint32_t ch = 0;
+        uint32_t chList[2] = {0u, 0u}, rel[kNumClasses];
         for (int c = 0; c < kNumClasses; ++c) {
-            sChunkStart[c] = ch;
-            ch += sCarryN[c] ? 1u : 0u;
+            const int g = (genericMask >> c) & 1u;
+            rel[c] = chList[g];
+            chList[g] += sCarryN[c] ? 1u : 0u;
         }
-        sChunkBase = ch ? atomicAdd(&ctr->gjkChunks, ch) : 0u;
+        const uint32_t base0 = chList[0] ? atomicAdd(&ctr->gjkChunks, chList[0]) : 0u;
+        const uint32_t base1 = chList[1] ? atomicAdd(&ctr->gjkChunksGeneric, chList[1]) : 0u;
+        for (int c = 0; c < kNumClasses; ++c) sDst[c] = (((genericMask >> c) & 1u) ? base1 : base0) + rel[c];
     }
     __syncthreads();
     if (tid < kNumClasses * 32) {
         const int c = tid >> 5, i = tid & 31;
-        const uint32_t g = sChunkBase + sChunkStart[c];
+        const uint32_t g = chunkIndex(c, sDst[c]);
         if (sCarryN[c] && g < chunkCap) chunks[(size_t)g * 32 + i] = ((uint32_t)i < sCarryN[c]) ? sCarry[c][i] : kNoPair;
     }
 }
 
+// ---- kernel 1a: the pair classes that are decided in closed form ------------------------------------------
+// One lane per candidate pair, one class-homogeneous chunk of 32 pairs per warp at a time (claimed by
+// ticket): sphere-sphere, sphere-box / box-sphere (clamp in the box frame) and box-box (15-axis SAT).
+// Per pair it writes flag[k] (0 = no contact, 1 = contact) and the record to tmp[k]; contact slots are
+// assigned afterwards, in pair order, by slotKernel.
+#ifndef AXCD_CLOSED_MIN_BLOCKS
+#define AXCD_CLOSED_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(kGjkThreads, AXCD_CLOSED_MIN_BLOCKS)
+closedFormKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, uint32_t chunkCap,
+                 const float* __restrict__ xf, const uint4* __restrict__ shapes, uint8_t* __restrict__ flags,
+                 AxcdContact* __restrict__ tmp, float* __restrict__ pairDist, Counters* __restrict__ ctr) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nChunks = min(ctr->gjkChunks, chunkCap);
+    while (true) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&ctr->gjkChunkCursor, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= nChunks) break;
+        const uint32_t k = __ldg(chunks + (size_t)chunk * 32 + lane);   // global pair index
+        if (k == kNoPair) continue;
+        const uint2 pk = __ldg(pairs + k);
+        const uint32_t ia = pk.x, ib = pk.y;
+        const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
+        const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
+        const V3 origin = ta.p;
+        bool contact = false;
+        V3 n = mk3(0.f, 0.f, 0.f), pos = n;
+        float depth = 0.f, dist = 0.f;
+        if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_SPHERE) {
+            const float ra = __uint_as_float(sa.y), rb = __uint_as_float(sb.y);
+            const V3 d = tb.p - origin;
+            const float len = sqrtf(dot3(d, d));
+            const float rs = ra + rb;
+            depth = rs - len;
+            dist = len - rs;
+            if (depth >= 0.0f) {
+                contact = true;
+                n = (len > 0.0f) ? d * (1.0f / len) : mk3(1.0f, 0.0f, 0.0f);
+                const V3 pa = n * ra;
+                const V3 pb = d - n * rb;
+                pos = (pa + pb) * 0.5f + origin;
+            }
+        } else if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_BOX) {
+            const SphereBox r = sphereBox(mk3(0.f, 0.f, 0.f), __uint_as_float(sa.y), tb.p - origin, tb, sb);
+            dist = r.dist;
+            if (r.contact) {
+                contact = true;
+                depth = r.depth;
+                n = r.nsx;
+                pos = (r.ps + r.px) * 0.5f + origin;
+            }
+        } else if (sa.x == AXCD_SHAPE_BOX && sb.x == AXCD_SHAPE_SPHERE) {
+            const SphereBox r = sphereBox(tb.p - origin, __uint_as_float(sb.y), mk3(0.f, 0.f, 0.f), ta, sa);
+            dist = r.dist;
+            if (r.contact) {
+                contact = true;
+                depth = r.depth;
+                n = -r.nsx;
+                pos = (r.px + r.ps) * 0.5f + origin;
+            }
+        } else {   // box-box (the classifier sends nothing else here)
+            const BoxBox r = boxBox(makeBoxFrame(ta, sa, origin), makeBoxFrame(tb, sb, origin));
+            dist = FLT_MAX;   // separated: no distance in this mode (with PAIR_DISTANCES box-box goes to gjkKernel)
+            if (r.contact) {
+                contact = true;
+                depth = r.depth;
+                dist = -r.depth;
+                n = r.n;
+                pos = (r.pa + r.pb) * 0.5f + origin;
+            }
+        }
+        if (pairDist) pairDist[k] = contact ? ((dist < 0.0f) ? dist : 0.0f) : dist;
+        flags[k] = contact ? (uint8_t)1 : (uint8_t)0;
+        if (contact) storeContact(tmp + k, ia, ib, pos, n, depth, 0u);
+    }
+}
+
+// The SAT as a call for gjkKernel (box-box reaches it only with AXCD_FLAG_PAIR_DISTANCES): keeps the
+// closed form's registers out of the GJK kernel's allocation.
+__device__ __noinline__ BoxBox boxBoxCall(const BodyPose& ta, uint4 sa, const BodyPose& tb, uint4 sb, V3 origin) {
+    return boxBox(makeBoxFrame(ta, sa, origin), makeBoxFrame(tb, sb, origin));
+}
+
+// ---- kernel 1: GJK over the pairs of the generic classes ---------------------------------------------------
 // One lane per candidate pair, one class-homogeneous chunk of 32 pairs per warp at a time (claimed
 // by ticket).  Per pair it writes flag[k]: 0 = no contact, 1 = shallow contact (cores apart, radii
-// overlapping, or a closed-form sphere case; record written to tmp[k]), 2 = cores overlap (EpaWork
-// queued; EPA writes the record).  Contact slots are assigned afterwards, in pair order, by slotKernel.
+// overlapping; record written to tmp[k]), 2 = cores overlap (EpaWork queued; EPA writes the record).
+// Contact slots are assigned afterwards, in pair order, by slotKernel.
 #ifndef AXCD_GJK_MIN_BLOCKS
 #define AXCD_GJK_MIN_BLOCKS 5
 #endif
@@ -984,13 +1254,13 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, 
           AxcdContact* __restrict__ tmp, NarrowQueues q, uint32_t queueCap, float* __restrict__ pairDist,
           Counters* __restrict__ ctr) {
     const int lane = threadIdx.x & 31;
-    const uint32_t nChunks = min(ctr->gjkChunks, chunkCap);
+    const uint32_t nChunks = min(ctr->gjkChunksGeneric, chunkCap);
     while (true) {
     uint32_t chunk = 0;
-    if (lane == 0) chunk = atomicAdd(&ctr->gjkChunkCursor, 1u);
+    if (lane == 0) chunk = atomicAdd(&ctr->gjkChunkCursorGeneric, 1u);
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     if (chunk >= nChunks) break;
-    const uint32_t k = __ldg(chunks + (size_t)chunk * 32 + lane);   // global pair index
+    const uint32_t k = __ldg(chunks + (size_t)(chunkCap - 1u - chunk) * 32 + lane);   // the generic list grows from the back
     if (k == kNoPair) continue;
 
     // ---- per-pair GJK ----------------------------------------------------------------------------
@@ -1005,43 +1275,29 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, 
     const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
     const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
     const V3 origin = ta.p;
-    if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_SPHERE) {
-        const float ra = __uint_as_float(sa.y), rb = __uint_as_float(sb.y);
-        const V3 d = tb.p - origin;
-        const float len = sqrtf(dot3(d, d));
-        const float rs = ra + rb;
-        depth = rs - len;
-        dist = len - rs;
-        if (depth >= 0.0f) {
-            kind = 1;
-            n = (len > 0.0f) ? d * (1.0f / len) : mk3(1.0f, 0.0f, 0.0f);
-            const V3 pa = n * ra;
-            const V3 pb = d - n * rb;
-            pos = (pa + pb) * 0.5f + origin;
-        }
-    } else if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_BOX) {
-        const SphereBox r = sphereBox(mk3(0.f, 0.f, 0.f), __uint_as_float(sa.y), tb.p - origin, tb, sb);
-        dist = r.dist;
+    // box-box without the generic flag gets here only for its distance (AXCD_FLAG_PAIR_DISTANCES): the
+    // contact decision and the record still come from the SAT
+    bool satApart = false;
+    if (sa.x == AXCD_SHAPE_BOX && sb.x == AXCD_SHAPE_BOX && !cfg.boxBoxGeneric) {
+        const BoxBox r = boxBoxCall(ta, sa, tb, sb, origin);
         if (r.contact) {
             kind = 1;
             depth = r.depth;
-            n = r.nsx;
-            pos = (r.ps + r.px) * 0.5f + origin;
+            dist = -r.depth;
+            n = r.n;
+            pos = (r.pa + r.pb) * 0.5f + origin;
+        } else {
+            satApart = true;
         }
-    } else if (sa.x == AXCD_SHAPE_BOX && sb.x == AXCD_SHAPE_SPHERE) {
-        const SphereBox r = sphereBox(tb.p - origin, __uint_as_float(sb.y), mk3(0.f, 0.f, 0.f), ta, sa);
-        dist = r.dist;
-        if (r.contact) {
-            kind = 1;
-            depth = r.depth;
-            n = -r.nsx;
-            pos = (r.px + r.ps) * 0.5f + origin;
-        }
-    } else {
+    }
+    if (kind == 0) {
         const Core A = makeCore(ta, sa, hull, origin);
         const Core B = makeCore(tb, sb, hull, origin);
         const float rs = A.r + B.r;
         const GjkResult g = gjk(A, B, cfg, rs, s);
+        if (satApart) {
+            dist = (g.state == GJK_SEPARATED) ? sqrtf(g.vv) : 0.0f;
+        } else {
         status = g.status;
         if (g.state == GJK_SEPARATED) {
             const float len = sqrtf(g.vv);
@@ -1060,6 +1316,7 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, 
             }
         } else {
             kind = 2;
+        }
         }
     }
     if (pairDist) pairDist[k] = (kind == 1) ? ((dist < 0.0f) ? dist : 0.0f) : dist;   // kind 2: EPA overwrites

@@ -333,7 +333,7 @@ def run_ours(args):
     else:
         s = axcd.config_scene(args.workload)
     stream = torch.cuda.Stream()
-    w = axcd.CollisionWorld.for_scene(s, device=local, stream=stream.cuda_stream)
+    w = axcd.CollisionWorld.for_scene(s, device=local, stream=stream.cuda_stream, flags=args.flags)
     hbm_peak, peak_src = load_peaks()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -528,6 +528,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the manifold / query / coherence timings")
     ap.add_argument("--scale", type=float, default=0.125, help="C4 only: fraction of the 16M bodies")
+    ap.add_argument("--flags", type=int, default=0, help="AXCD_FLAG_* bits for the context (8 = box-box through GJK/EPA)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

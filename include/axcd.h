@@ -107,17 +107,19 @@ enum {
      * axcd_get_pair_distances works.  Off by default: separated pairs then stop at the first
      * separating axis.                                                                          */
     AXCD_FLAG_PAIR_DISTANCES = 1u,
-    /* Run EPA with the cooperative kernel (8 lanes per pair, faces in registers) instead of the
-     * default one-thread-per-pair kernel.  Same results; slower on B200 so far (profiles/), kept
-     * for A/B measurements.                                                                     */
-    AXCD_FLAG_EPA_COOPERATIVE = 2u,
+    /* 2u is reserved (round 1 kept an alternative, slower EPA kernel behind it; removed).              */
     /* Temporal coherence: the AABB buffer holds persistent FAT boxes — a body's
      * box is rebuilt (tight box expanded by aabbMargin, AABB::expand(float), aabb.hpp:156-160) only when
      * its tight box leaves it — and axcd_broadphase reuses the previous candidate list when no body
      * moved out of its fat box (AxcdStats.movedBodies == 0 -> broadphaseSkipped = 1).  The candidate set
      * is then the overlap set of the fat boxes (a superset of the tight one); the contact set is
      * unchanged, because the narrowphase works on the exact shapes.  Not available in x-slab mode.  */
-    AXCD_FLAG_TEMPORAL_COHERENCE = 4u
+    AXCD_FLAG_TEMPORAL_COHERENCE = 4u,
+    /* Box-box pairs are decided in closed form by default (15-axis separating-axis test: contact iff no
+     * axis separates, depth = the smallest overlap, normal = that axis — what EPA converges to).  This
+     * flag sends them through the generic GJK + EPA path instead, like hulls and capsules (A/B
+     * measurements, and tests that validate one against the other).                               */
+    AXCD_FLAG_BOXBOX_GJK_EPA = 8u
 };
 
 typedef struct AxcdStats {
@@ -308,6 +310,10 @@ AXCD_API int32_t axcd_test_sort_keys64(AxcdContext* ctx, uint64_t* keys, uint32_
  * `iters` sorts (CUDA events on the context stream, inputs regenerated on the device each time). */
 AXCD_API int32_t axcd_test_sort_bench(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uint32_t iters,
                                       float* outMsPerSort);
+/* Measured FP32 peak of the device: an FMA-chain kernel (8 independent chains per thread, `iters` x 128
+ * FMAs per thread, 2048 threads per SM), best of three, in TFLOP/s.  The roof the GJK / EPA kernels are
+ * reported against (BASELINE.md asks for a peak measured on the box, not the nominal one).        */
+AXCD_API int32_t axcd_test_fp32_peak(AxcdContext* ctx, uint32_t iters, float* outTflops);
 
 #ifdef __cplusplus
 }

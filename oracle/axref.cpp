@@ -820,6 +820,157 @@ SphereBox sphereBox(V3 cS, float r, V3 cX, const Xf& tX, const AxrefShape& sX) {
     return o;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Box against box in closed form: the 15-axis separating-axis test (3 face normals of each box +
+// 9 edge-edge cross products), as collision libraries dispatch this pair class.  The Minkowski
+// difference of two boxes is a polytope whose face normals are among those 15 directions, so
+//   * the boxes are apart  <=>  some axis has a negative overlap, and
+//   * the penetration depth = the smallest overlap, the contact normal = that axis
+// (the answer EPA converges to; tests/test_oracle_narrow.py checks one against the other and against
+// the convex hull of the Minkowski difference).  Edge-edge axes are compared un-normalised
+// (overlap^2 * |L'|^2 cross-multiplied) so only the winning axis costs a square root; a pair of
+// nearly parallel edges (|a_i x b_j|^2 <= 1e-5) is skipped — its axis degenerates into the face
+// axes.  Ties keep the earlier axis (faces of A, faces of B, then edges i-major).
+// Witness points: face axis -> the other box's deepest vertex (support-point tie rule: a zero dot
+// picks the + side) and its projection onto the face; edge-edge -> the closest points of the two
+// supporting edges (as segments).  All points relative to A's position.
+// ------------------------------------------------------------------------------------------
+struct BoxFrame {
+    V3 c;          // centre relative to A's position
+    V3 ax[3];      // unit axes: the columns of Quat::toMatrix
+    float h[3];    // half lengths |halfExtent * scale|
+};
+BoxFrame makeBoxFrame(const Xf& t, const AxrefShape& sh, V3 origin) {
+    BoxFrame f;
+    M3 m = quatToMat3(t.q);
+    f.c = t.p - origin;
+    f.ax[0] = m.c0; f.ax[1] = m.c1; f.ax[2] = m.c2;
+    f.h[0] = std::fabs(sh.p0 * t.s.x);
+    f.h[1] = std::fabs(sh.p1 * t.s.y);
+    f.h[2] = std::fabs(sh.p2 * t.s.z);
+    return f;
+}
+
+const float SAT_PARALLEL_EPS = 1e-5f;
+struct BoxBox {
+    bool contact;
+    float depth;
+    V3 n, pa, pb;   // unit normal from A to B, witness points on A and on B
+};
+BoxBox boxBox(const BoxFrame& A, const BoxFrame& B) {
+    BoxBox o{};
+    const V3 t = B.c - A.c;
+    float R[3][3], AR[3][3], tA[3], tB[3];
+    for (int i = 0; i < 3; ++i) {
+        tA[i] = dot(t, A.ax[i]);
+        tB[i] = dot(t, B.ax[i]);
+        for (int j = 0; j < 3; ++j) {
+            R[i][j] = dot(A.ax[i], B.ax[j]);
+            AR[i][j] = std::fabs(R[i][j]);
+        }
+    }
+    // best axis so far: overlap bestOv measured along an axis of squared length bestL2
+    float bestOv = FLT_MAX, bestL2 = 1.0f;
+    int axis = -1;
+    for (int i = 0; i < 3; ++i) {   // faces of A
+        const float rb = (B.h[0] * AR[i][0] + B.h[1] * AR[i][1]) + B.h[2] * AR[i][2];
+        const float ov = (A.h[i] + rb) - std::fabs(tA[i]);
+        if (ov < 0.0f) return o;
+        if (ov < bestOv) {
+            bestOv = ov;
+            axis = i;
+        }
+    }
+    for (int j = 0; j < 3; ++j) {   // faces of B
+        const float ra = (A.h[0] * AR[0][j] + A.h[1] * AR[1][j]) + A.h[2] * AR[2][j];
+        const float ov = (ra + B.h[j]) - std::fabs(tB[j]);
+        if (ov < 0.0f) return o;
+        if (ov < bestOv) {
+            bestOv = ov;
+            axis = 3 + j;
+        }
+    }
+    if (axis < 0) return o;   // NaN input: every compare was false
+    for (int i = 0; i < 3; ++i) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        for (int j = 0; j < 3; ++j) {
+            const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            const V3 L = cross(A.ax[i], B.ax[j]);
+            const float l2 = dot(L, L);
+            if (!(l2 > SAT_PARALLEL_EPS)) continue;
+            const float ra = A.h[i1] * AR[i2][j] + A.h[i2] * AR[i1][j];
+            const float rb = B.h[j1] * AR[i][j2] + B.h[j2] * AR[i][j1];
+            const float ov = (ra + rb) - std::fabs(dot(t, L));   // scaled by |L|
+            if (ov < 0.0f) return o;
+            // ov / |L| < bestOv / |bestL|, cross-multiplied (all terms >= 0)
+            if ((ov * ov) * bestL2 < (bestOv * bestOv) * l2) {
+                bestOv = ov;
+                bestL2 = l2;
+                axis = 6 + 3 * i + j;
+            }
+        }
+    }
+    o.contact = true;
+    if (axis < 3) {
+        const int i = axis;
+        const bool pos = tA[i] >= 0.0f;
+        o.n = pos ? A.ax[i] : -A.ax[i];
+        o.depth = bestOv;
+        V3 v = B.c;   // B's deepest vertex: support of B in direction -n
+        for (int j = 0; j < 3; ++j) {
+            const float dj = pos ? R[i][j] : -R[i][j];
+            v = v + B.ax[j] * ((dj > 0.0f) ? -B.h[j] : B.h[j]);
+        }
+        o.pb = v;
+        o.pa = v + o.n * o.depth;
+    } else if (axis < 6) {
+        const int j = axis - 3;
+        const bool pos = tB[j] >= 0.0f;
+        o.n = pos ? B.ax[j] : -B.ax[j];
+        o.depth = bestOv;
+        V3 v = A.c;   // A's deepest vertex: support of A in direction n
+        for (int i = 0; i < 3; ++i) {
+            const float di = pos ? R[i][j] : -R[i][j];
+            v = v + A.ax[i] * ((di >= 0.0f) ? A.h[i] : -A.h[i]);
+        }
+        o.pa = v;
+        o.pb = v - o.n * o.depth;
+    } else {
+        const int i = (axis - 6) / 3, j = (axis - 6) % 3;
+        const V3 L = cross(A.ax[i], B.ax[j]);
+        const float invl = 1.0f / std::sqrt(bestL2);
+        const bool pos = dot(t, L) >= 0.0f;
+        o.n = L * (pos ? invl : -invl);
+        o.depth = bestOv * invl;
+        // centres of the two supporting edges
+        V3 ea = A.c, eb = B.c;
+        for (int k = 0; k < 3; ++k) {
+            if (k != i) ea = ea + A.ax[k] * ((dot(o.n, A.ax[k]) >= 0.0f) ? A.h[k] : -A.h[k]);
+            if (k != j) eb = eb + B.ax[k] * ((dot(o.n, B.ax[k]) > 0.0f) ? -B.h[k] : B.h[k]);
+        }
+        // closest points of the segments ea + u*s (|s| <= hA_i) and eb + v*q (|q| <= hB_j)
+        const V3 u = A.ax[i], v = B.ax[j];
+        const V3 r = ea - eb;
+        const float a = dot(u, u), e = dot(v, v), b = dot(u, v);
+        const float c = dot(u, r), f = dot(v, r);
+        const float denom = a * e - b * b;   // > 0: the edges are not parallel
+        float s = (b * f - c * e) / denom;
+        s = std::fmin(std::fmax(s, -A.h[i]), A.h[i]);
+        float q = (b * s + f) / e;
+        if (q < -B.h[j]) {
+            q = -B.h[j];
+            s = std::fmin(std::fmax((b * q - c) / a, -A.h[i]), A.h[i]);
+        } else if (q > B.h[j]) {
+            q = B.h[j];
+            s = std::fmin(std::fmax((b * q - c) / a, -A.h[i]), A.h[i]);
+        }
+        o.pa = ea + u * s;
+        o.pb = eb + v * q;
+    }
+    return o;
+}
+
 struct PairOut {
     bool contact;
     bool usedEpa;
@@ -864,6 +1015,27 @@ PairOut collidePair(uint32_t ia, uint32_t ib, const Xf& ta, const AxrefShape& sa
         pa = r.px;
         pb = r.ps;
     } else {
+        // box-box: closed form (15-axis SAT) unless the generic path is forced.  The contact decision and
+        // the contact record always come from the SAT; with wantDistances a separated pair additionally
+        // runs GJK for its exact distance.
+        const bool sat = sa.type == SHAPE_BOX && sb.type == SHAPE_BOX && !(cfg.flags & AXREF_BOXBOX_GJK_EPA);
+        if (sat) {
+            BoxBox r = boxBox(makeBoxFrame(ta, sa, origin), makeBoxFrame(tb, sb, origin));
+            if (r.contact) {
+                o.dist = -r.depth;
+                o.contact = true;
+                V3 mid = (r.pa + r.pb) * 0.5f + origin;
+                o.c.px = mid.x; o.c.py = mid.y; o.c.pz = mid.z;
+                o.c.nx = r.n.x; o.c.ny = r.n.y; o.c.nz = r.n.z;
+                o.c.depth = r.depth;
+                o.c.status = 0;
+                return o;
+            }
+            if (!cfg.wantDistances) {
+                o.dist = FLT_MAX;   // separated; no distance is computed in this mode
+                return o;
+            }
+        }
         Core A = makeCore(ta, sa, hull, origin);
         Core B = makeCore(tb, sb, hull, origin);
         float rs = A.r + B.r;
@@ -871,6 +1043,10 @@ PairOut collidePair(uint32_t ia, uint32_t ib, const Xf& ta, const AxrefShape& sa
         GjkResult g = gjk(A, B, cfg, rs, s);
         o.iters = g.iters;
         status = g.status;
+        if (sat) {   // separated by the SAT: GJK only supplies the distance
+            o.dist = (g.state == GJK_SEPARATED) ? std::sqrt(g.vv) : 0.0f;
+            return o;
+        }
         if (g.state == GJK_SEPARATED) {
             float dist = std::sqrt(g.vv);
             if (!g.exact) {
@@ -920,21 +1096,6 @@ PairOut collidePair(uint32_t ia, uint32_t ib, const Xf& ta, const AxrefShape& sa
 // segment clipped against the facing box face (capsuleBoxManifold, 1..2 points).  Every other class, and a
 // clip that comes out empty, keeps the single narrowphase point.
 // ------------------------------------------------------------------------------------------
-struct BoxFrame {
-    V3 c;          // centre relative to A's position
-    V3 ax[3];      // unit axes: the columns of Quat::toMatrix
-    float h[3];    // half lengths |halfExtent * scale|
-};
-BoxFrame makeBoxFrame(const Xf& t, const AxrefShape& sh, V3 origin) {
-    BoxFrame f;
-    M3 m = quatToMat3(t.q);
-    f.c = t.p - origin;
-    f.ax[0] = m.c0; f.ax[1] = m.c1; f.ax[2] = m.c2;
-    f.h[0] = std::fabs(sh.p0 * t.s.x);
-    f.h[1] = std::fabs(sh.p1 * t.s.y);
-    f.h[2] = std::fabs(sh.p2 * t.s.z);
-    return f;
-}
 inline int argmaxAbs3(const float d[3]) {   // lowest index on ties
     int k = 0;
     float best = std::fabs(d[0]);
@@ -1649,7 +1810,7 @@ int32_t axref_query_aabbs(const float* aabb, uint32_t n, const uint32_t* worldId
 
 int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* hullXYZ, const float* aabb, uint32_t n,
                       const uint32_t* worldId, const AxrefRay* rays, uint32_t nq, AxrefRayHit* out, int nthreads) {
-    const AxrefNarrowCfg cfg{32u, 32u, 64u, 1e-6f, 1e-4f, 1u};   // the library defaults (axcd_default_config)
+    const AxrefNarrowCfg cfg{32u, 32u, 64u, 1e-6f, 1e-4f, 1u, 0u};   // the library defaults (axcd_default_config)
     parallelFor(nq, nthreads, [&](int, uint64_t lo, uint64_t hi) {
         for (uint64_t q = lo; q < hi; ++q) {
             const AxrefRay& r = rays[q];

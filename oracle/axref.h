@@ -27,7 +27,9 @@ typedef struct AxrefNarrowCfg {
     uint32_t gjkMaxIters, epaMaxIters, epaMaxFaces;
     float gjkTol, epaTol;
     uint32_t wantDistances;   /* 1: run GJK to convergence on every pair and report distances */
+    uint32_t flags;           /* AXREF_BOXBOX_GJK_EPA: box-box pairs through GJK/EPA instead of the SAT */
 } AxrefNarrowCfg;
+enum { AXREF_BOXBOX_GJK_EPA = 1u };
 typedef struct AxrefNarrowStats {
     uint64_t numContacts, numPenetrating, gjkFailures, epaFailures, gjkIterations;
 } AxrefNarrowStats;

@@ -26,13 +26,16 @@ def run(scene):
     con, dist, _ = O.narrowphase(scene.xf, scene.shapes, pairs, scene.hull, want_distances=True)
     con2, _, _ = O.narrowphase(scene.xf, scene.shapes, pairs, scene.hull)
     assert np.array_equal(con, con2)
-    return bb, pairs, con, dist
+    # box-box through GJK/EPA instead of the closed-form SAT (AXCD_FLAG_BOXBOX_GJK_EPA)
+    cong, _, _ = O.narrowphase(scene.xf, scene.shapes, pairs, scene.hull, cfg=O.default_cfg(False, True))
+    return bb, pairs, con, dist, cong
 
 
 out = {}
 for tag, scene in (("c0", axcd.config_scene("C0")), ("c2s", axcd.config_scene("C2", scale=0.0005))):
-    bb, pairs, con, dist = run(scene)
+    bb, pairs, con, dist, cong = run(scene)
     out.update({f"{tag}_xf": scene.xf, f"{tag}_shapes": scene.shapes, f"{tag}_hull": scene.hull,
-                f"{tag}_aabb": bb, f"{tag}_pairs": pairs, f"{tag}_contacts": con, f"{tag}_dist": dist})
-    print(tag, scene.n, "bodies", len(pairs), "pairs", len(con), "contacts")
+                f"{tag}_aabb": bb, f"{tag}_pairs": pairs, f"{tag}_contacts": con, f"{tag}_dist": dist,
+                f"{tag}_contacts_generic": cong})
+    print(tag, scene.n, "bodies", len(pairs), "pairs", len(con), "contacts", len(cong), "contacts (generic box-box)")
 np.savez_compressed(os.path.join(HERE, "c0_golden.npz"), **out)

@@ -29,7 +29,7 @@ SWEEP_DT = np.dtype([("hit", "<u4"), ("toi", "<f4"), ("nx", "<f4"), ("ny", "<f4"
 class NarrowCfg(C.Structure):
     _fields_ = [("gjkMaxIters", C.c_uint32), ("epaMaxIters", C.c_uint32),
                 ("epaMaxFaces", C.c_uint32), ("gjkTol", C.c_float), ("epaTol", C.c_float),
-                ("wantDistances", C.c_uint32)]
+                ("wantDistances", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class NarrowStats(C.Structure):
@@ -38,8 +38,11 @@ class NarrowStats(C.Structure):
                 ("gjkIterations", C.c_uint64)]
 
 
-def default_cfg(want_distances=False):
-    return NarrowCfg(32, 32, 64, 1e-6, 1e-4, 1 if want_distances else 0)
+BOXBOX_GJK_EPA = 1   # AxrefNarrowCfg.flags: box-box pairs through GJK/EPA instead of the closed-form SAT
+
+
+def default_cfg(want_distances=False, boxbox_generic=False):
+    return NarrowCfg(32, 32, 64, 1e-6, 1e-4, 1 if want_distances else 0, BOXBOX_GJK_EPA if boxbox_generic else 0)
 
 
 def lib():

@@ -30,6 +30,9 @@ def test_oracle_reproduces_golden_outputs(tag):
     for f in ("px", "py", "pz", "nx", "ny", "nz", "depth"):
         assert np.array_equal(bits(con[f]), bits(gold[f])), f
     assert np.array_equal(bits(dist), bits(G[f"{tag}_dist"]))
+    # box-box through GJK/EPA instead of the closed-form SAT
+    cong, _, _ = O.narrowphase(xf, shapes, pairs, hull, cfg=O.default_cfg(False, True))
+    assert cong.tobytes() == G[f"{tag}_contacts_generic"].tobytes()
 
 
 def test_scene_generator_reproduces_golden_blobs():
@@ -53,6 +56,11 @@ def test_cuda_path_reproduces_golden_outputs(tag):
         np.testing.assert_allclose(con[f], gold[f], rtol=1e-4, atol=1e-6)     # stated FP32 tolerance
         assert np.array_equal(bits(con[f]), bits(gold[f])), f                 # and in fact bit-identical
     np.testing.assert_allclose(w.pair_distances(), G[f"{tag}_dist"], rtol=1e-4, atol=1e-6)
+    w.close()
+    # box-box through GJK/EPA (AXCD_FLAG_BOXBOX_GJK_EPA): the generic kernels on the same pairs
+    w = axcd.CollisionWorld.for_scene(s, flags=axcd.FLAG_BOXBOX_GJK_EPA)
+    w.step()
+    assert w.contacts().tobytes() == G[f"{tag}_contacts_generic"].tobytes()
     w.close()
 
 

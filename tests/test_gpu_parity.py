@@ -17,11 +17,12 @@ pytestmark = pytest.mark.gpu
 REL = 1e-4
 
 
-def oracle_step(s, margin=0.0, brute=False, nthreads=8, want_distances=False):
+def oracle_step(s, margin=0.0, brute=False, nthreads=8, want_distances=False, boxbox_generic=False):
     rc, bb = O.refit(s.xf, s.shapes, s.hull, margin=margin, nthreads=nthreads)
     assert rc == 0
     pairs = O.broadphase(bb, s.world_id, brute=brute, nthreads=nthreads)
-    con, dist, st = O.narrowphase(s.xf, s.shapes, pairs, s.hull, nthreads=nthreads, want_distances=want_distances)
+    con, dist, st = O.narrowphase(s.xf, s.shapes, pairs, s.hull, nthreads=nthreads,
+                                  cfg=O.default_cfg(want_distances, boxbox_generic), want_distances=want_distances)
     return bb, pairs, con, dist, st
 
 
@@ -43,10 +44,14 @@ def assert_contacts_match(gc, oc):
         np.testing.assert_allclose(gc[f], oc[f], rtol=REL, atol=REL * 1e-2)
 
 
-def run_and_compare(s, margin=0.0, brute=False, **kw):
+def run_and_compare(s, margin=0.0, brute=False, boxbox_generic=False, nthreads=8, **kw):
+    """boxbox_generic: box-box pairs through GJK/EPA on both sides (AXCD_FLAG_BOXBOX_GJK_EPA) instead of the
+    closed-form SAT."""
+    if boxbox_generic:
+        kw["flags"] = kw.get("flags", 0) | axcd.FLAG_BOXBOX_GJK_EPA
     w = axcd.CollisionWorld.for_scene(s, aabbMargin=margin, **kw)
     st = w.step()
-    bb, pairs, con, _, ost = oracle_step(s, margin=margin, brute=brute)
+    bb, pairs, con, _, ost = oracle_step(s, margin=margin, brute=brute, boxbox_generic=boxbox_generic, nthreads=nthreads)
     assert_bits_equal(w.aabbs(), bb)                                              # bit-exact AABBs
     gp = w.pairs()
     assert st.numPairs == len(pairs)
@@ -90,14 +95,20 @@ def test_radix_sort_keys64_vs_numpy(n):
 
 
 # ------------------------------------------------------------------ parity per config ----------
-def test_c0_reference_scene_vs_bruteforce_oracle():
-    st, bitwise = run_and_compare(axcd.config_scene("C0"), brute=True)
+BOXBOX_MODES = pytest.mark.parametrize("generic", [False, True], ids=["sat", "gjk_epa"])
+
+
+@BOXBOX_MODES
+def test_c0_reference_scene_vs_bruteforce_oracle(generic):
+    st, bitwise = run_and_compare(axcd.config_scene("C0"), brute=True, boxbox_generic=generic)
     assert st.numPairs == 2875 and st.numContacts == 1381
+    assert (st.numPenetrating > 0) == generic     # boxes and spheres only: EPA runs only when box-box is forced through it
     assert bitwise, "contact floats expected bit-identical (no FMA contraction on either side)"
 
 
-def test_c1_100k_single_scene():
-    st, bitwise = run_and_compare(axcd.config_scene("C1"))
+@BOXBOX_MODES
+def test_c1_100k_single_scene(generic):
+    st, bitwise = run_and_compare(axcd.config_scene("C1"), boxbox_generic=generic)
     assert st.numPairs > 250_000
     assert bitwise
 
@@ -125,10 +136,25 @@ def test_traversal_heavy_tailed_sizes():
     w.close()
 
 
-def test_c2_hull_mix_epa_heavy_scaled():
-    st, bitwise = run_and_compare(axcd.config_scene("C2", scale=0.05))
-    assert st.numPenetrating > 0.2 * st.numPairs
+@BOXBOX_MODES
+def test_c2_hull_mix_epa_heavy_scaled(generic):
+    st, bitwise = run_and_compare(axcd.config_scene("C2", scale=0.05), boxbox_generic=generic)
+    assert st.numPenetrating > (0.2 if generic else 0.1) * st.numPairs
     assert bitwise
+
+
+def test_c2_hull_mix_full_size_1m():
+    """Config C2 at its named size: 1 M bodies, 40 % boxes / 30 % spheres / 30 % 16-vertex hulls."""
+    st, bitwise = run_and_compare(axcd.config_scene("C2"), nthreads=16)
+    assert st.numBodies == 1_000_000 and st.numPenetrating > 0.1 * st.numPairs
+    assert bitwise
+
+
+def test_c3_all_4096_worlds_full_size():
+    """Config C3 at its named size: 4096 independent 256-body worlds in one launch."""
+    s = axcd.config_scene("C3")
+    st, bitwise = run_and_compare(s, nthreads=16)
+    assert st.numBodies == 4096 * 256 and bitwise
 
 
 def test_c3_batched_worlds_no_cross_world_pairs():
@@ -139,11 +165,6 @@ def test_c3_batched_worlds_no_cross_world_pairs():
     p = w.pairs()
     assert (s.world_id[p[:, 0]] == s.world_id[p[:, 1]]).all()
     w.close()
-
-
-def test_cooperative_epa_flag_is_bit_identical():
-    st, bitwise = run_and_compare(axcd.config_scene("C2", scale=0.02), flags=axcd.FLAG_EPA_COOPERATIVE)
-    assert bitwise and st.numPenetrating > 0
 
 
 def test_non_unit_scales_boxes_and_hulls():
@@ -172,11 +193,12 @@ def test_aabb_margin_inflates_candidates():
     assert st1.numPairs > st0.numPairs and st1.numContacts == st0.numContacts
 
 
-def test_pair_distances_mode():
+@BOXBOX_MODES
+def test_pair_distances_mode(generic):
     s = axcd.config_scene("C2", scale=0.01)
-    w = axcd.CollisionWorld.for_scene(s, flags=axcd.FLAG_PAIR_DISTANCES)
+    w = axcd.CollisionWorld.for_scene(s, flags=axcd.FLAG_PAIR_DISTANCES | (axcd.FLAG_BOXBOX_GJK_EPA if generic else 0))
     w.step()
-    _, pairs, con, dist, _ = oracle_step(s, want_distances=True)
+    _, pairs, con, dist, _ = oracle_step(s, want_distances=True, boxbox_generic=generic)
     assert np.array_equal(w.pairs(), pairs)
     assert_contacts_match(w.contacts(), con)
     gd = w.pair_distances()
@@ -185,12 +207,13 @@ def test_pair_distances_mode():
 
 
 # ------------------------------------------------------------------ full size ------------------
-def test_headline_1m_bodies_full_size():
+@BOXBOX_MODES
+def test_headline_1m_bodies_full_size(generic):
     s = axcd.config_scene("headline")
-    w = axcd.CollisionWorld.for_scene(s)
+    w = axcd.CollisionWorld.for_scene(s, flags=axcd.FLAG_BOXBOX_GJK_EPA if generic else 0)
     st = w.step()
     # oracle grid broadphase and narrowphase finish in seconds on the box's host cores
-    bb, pairs, con, _, ost = oracle_step(s, nthreads=16)
+    bb, pairs, con, _, ost = oracle_step(s, nthreads=16, boxbox_generic=generic)
     assert_bits_equal(w.aabbs(), bb)
     gp = w.pairs()
     assert np.array_equal(gp, pairs)
@@ -452,6 +475,8 @@ def test_degenerate_pair_zoo_bit_exact():
     st, bitwise = run_and_compare(s)
     assert bitwise
     assert st.numPairs > npairs // 2 and st.numContacts > npairs // 4
+    st, bitwise = run_and_compare(s, boxbox_generic=True)
+    assert bitwise
 
 
 def test_deep_tree_everything_overlaps():

@@ -167,12 +167,18 @@ def test_sphere_vs_rotated_scaled_box_closed_form():
                     np.testing.assert_allclose([con["px"], con["py"], con["pz"]], (surf_box + surf_sph) / 2, atol=5e-4)
 
 
-def test_axis_aligned_box_box_min_overlap_axis():
+# box-box runs through the closed-form SAT by default and through GJK/EPA with the generic flag
+# (AXCD_FLAG_BOXBOX_GJK_EPA); both must give the closed-form answers below
+BOXBOX_MODES = pytest.mark.parametrize("generic", [False, True], ids=["sat", "gjk_epa"])
+
+
+@BOXBOX_MODES
+def test_axis_aligned_box_box_min_overlap_axis(generic):
     rng = np.random.default_rng(3)
     for _ in range(300):
         ha, hb = rng.uniform(0.3, 1.0, 3), rng.uniform(0.3, 1.0, 3)
         t = rng.uniform(-2.0, 2.0, 3)
-        hit, con, dist, epa = O.collide_pair(O.xf(), O.box(*ha), O.xf(t), O.box(*hb))
+        hit, con, dist, epa = O.collide_pair(O.xf(), O.box(*ha), O.xf(t), O.box(*hb), cfg=O.default_cfg(True, generic))
         haf, hbf, tf = (np.float32(x).astype(float) for x in (ha, hb, t))
         gap = np.abs(tf) - haf - hbf
         if (gap > 0).any():
@@ -181,7 +187,7 @@ def test_axis_aligned_box_box_min_overlap_axis():
             assert abs(dist - expect) < TOL
         else:
             k = int(np.argmax(gap))
-            assert hit and epa
+            assert hit and epa == generic
             assert abs(con["depth"] + gap[k]) < TOL
             srt = np.sort(gap)
             if srt[-1] - srt[-2] > 1e-3:
@@ -190,22 +196,26 @@ def test_axis_aligned_box_box_min_overlap_axis():
                 np.testing.assert_allclose([con["nx"], con["ny"], con["nz"]], n, atol=2e-4)
 
 
-def test_box_rotated_45_touching_at_sqrt2():
+@BOXBOX_MODES
+def test_box_rotated_45_touching_at_sqrt2(generic):
     # mirrors tests/math/aabb_test.cpp:330-349 (cube +-1 rotated 45 deg about Z reaches sqrt 2)
     q = O.axis_angle((0, 0, 1), np.pi / 4)
     r2 = float(np.sqrt(2.0))
     for gap in (0.25, 0.01, -0.01, -0.25):
-        hit, con, dist, _ = O.collide_pair(O.xf(), O.box(1, 1, 1), O.xf((1 + r2 + gap, 0, 0), q), O.box(1, 1, 1))
+        hit, con, dist, _ = O.collide_pair(O.xf(), O.box(1, 1, 1), O.xf((1 + r2 + gap, 0, 0), q), O.box(1, 1, 1),
+                                           cfg=O.default_cfg(True, generic))
         assert abs(dist - gap) < TOL
         assert hit == (gap < 0)
         if hit:
             np.testing.assert_allclose([con["nx"], con["ny"], con["nz"]], (1, 0, 0), atol=2e-4)
 
 
-def test_identical_shapes_identical_poses():
+@BOXBOX_MODES
+def test_identical_shapes_identical_poses(generic):
     q = O.axis_angle((1, 2, 3), 0.7)
-    hit, con, dist, epa = O.collide_pair(O.xf((1, 1, 1), q), O.box(0.5, 0.75, 1.0), O.xf((1, 1, 1), q), O.box(0.5, 0.75, 1.0))
-    assert hit and epa and con["status"] == 0
+    hit, con, dist, epa = O.collide_pair(O.xf((1, 1, 1), q), O.box(0.5, 0.75, 1.0), O.xf((1, 1, 1), q), O.box(0.5, 0.75, 1.0),
+                                         cfg=O.default_cfg(True, generic))
+    assert hit and epa == generic and con["status"] == 0
     assert abs(con["depth"] - 1.0) < TOL     # thinnest direction: 2 * 0.5
     n = np.array([con["nx"], con["ny"], con["nz"]])
     assert abs(np.linalg.norm(n) - 1) < 1e-5
@@ -223,9 +233,11 @@ def test_point_like_hulls():
     assert hit and con["depth"] == 0.0
 
 
-def test_stacked_boxes_resting_contact():
+@BOXBOX_MODES
+def test_stacked_boxes_resting_contact(generic):
     # exactly touching faces: either classification is float noise, but it must not blow up
-    hit, con, dist, _ = O.collide_pair(O.xf((0, 0, 0)), O.box(1, 1, 1), O.xf((0.25, 2.0, -0.25)), O.box(1, 1, 1))
+    hit, con, dist, _ = O.collide_pair(O.xf((0, 0, 0)), O.box(1, 1, 1), O.xf((0.25, 2.0, -0.25)), O.box(1, 1, 1),
+                                       cfg=O.default_cfg(True, generic))
     assert abs(dist) < TOL
     if hit:
         assert con["depth"] < TOL
@@ -233,7 +245,8 @@ def test_stacked_boxes_resting_contact():
 
 
 # ---------------------------------------------------------------- randomized cross-checks -----
-def test_random_box_box_vs_sat_and_qp():
+@BOXBOX_MODES
+def test_random_box_box_vs_sat_and_qp(generic):
     rng = np.random.default_rng(4)
     n_pen = n_sep = 0
     for _ in range(400):
@@ -242,12 +255,12 @@ def test_random_box_box_vs_sat_and_qp():
         qa = O.axis_angle(rng.normal(size=3), rng.uniform(0, 6.28))
         qb = O.axis_angle(rng.normal(size=3), rng.uniform(0, 6.28))
         haf, hbf = np.float32(ha).astype(float), np.float32(hb).astype(float)
-        hit, con, dist, epa = O.collide_pair(O.xf(pa, qa), O.box(*ha), O.xf(pb, qb), O.box(*hb))
+        hit, con, dist, epa = O.collide_pair(O.xf(pa, qa), O.box(*ha), O.xf(pb, qb), O.box(*hb), cfg=O.default_cfg(True, generic))
         assert con["status"] == 0
         depth = sat_box_box_depth(np.float32(pa), qa, haf, np.float32(pb), qb, hbf)
         if depth > 0:
             n_pen += 1
-            assert hit and epa, (depth, dist)
+            assert hit and epa == generic, (depth, dist)
             assert abs(con["depth"] - depth) < TOL
             # moving B by depth along n must separate (SAT depth ~ 0 afterwards)
             n = np.array([con["nx"], con["ny"], con["nz"]], float)
@@ -360,3 +373,55 @@ def test_epa_depth_is_the_global_minimum_vs_minkowski_hull():
             assert np.dot(n, md.equations[k, :3]) > 0.999, (n, md.equations[k, :3])
         checked += 1
     assert checked > 60, checked
+
+
+def test_box_box_sat_vs_minkowski_hull_and_vs_epa():
+    """The closed-form box-box answer (15-axis SAT) against two independent statements of the same quantity:
+    the nearest facet of the convex hull of the Minkowski difference (scipy) — depth and normal are the
+    global minimum — and the generic GJK/EPA path of this oracle on the same pair.  Also the witness points:
+    each lies on its box's supporting plane for the contact normal."""
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(21)
+    checked = 0
+    for _ in range(300):
+        ha, hb = rng.uniform(0.25, 0.5, 3), rng.uniform(0.25, 0.5, 3)
+        sa, sb = rng.uniform(0.7, 1.4, 3), rng.uniform(0.7, 1.4, 3)
+        qa = O.axis_angle(rng.normal(size=3), rng.uniform(0, 6.28))
+        qb = O.axis_angle(rng.normal(size=3), rng.uniform(0, 6.28))
+        ca = rng.uniform(0, 0.3, 3)
+        cb = ca + rng.normal(size=3) * 0.35
+        ta, tb = O.xf(ca, qa, sa), O.xf(cb, qb, sb)
+        hit, con, dist, epa = O.collide_pair(ta, O.box(*ha), tb, O.box(*hb))
+        hit2, con2, dist2, epa2 = O.collide_pair(ta, O.box(*ha), tb, O.box(*hb), cfg=O.default_cfg(True, True))
+        assert not epa and (epa2 or not hit2)
+        haf = np.float32(ha).astype(float) * np.float32(sa).astype(float)
+        hbf = np.float32(hb).astype(float) * np.float32(sb).astype(float)
+        WA = box_vertices(np.float32(ca), qa, haf)
+        WB = box_vertices(np.float32(cb), qb, hbf)
+        md = ConvexHull((WA[:, None, :] - WB[None, :, :]).reshape(-1, 3))
+        off = md.equations[:, 3]
+        if not (off < -1e-3).all():
+            if (off > 1e-3).any():
+                assert not hit and not hit2      # clearly apart
+            continue
+        k = int(np.argmax(off))
+        depth = -off[k]
+        assert hit and hit2
+        assert abs(con["depth"] - depth) < 2e-5 * max(1.0, depth), (con["depth"], depth)   # the SAT is exact
+        assert abs(con2["depth"] - depth) < 1e-3 * max(1.0, depth)                         # EPA within its tolerance
+        n = np.array([con["nx"], con["ny"], con["nz"]], float)
+        assert abs(np.linalg.norm(n) - 1) < 1e-5
+        if sorted(off)[-1] - sorted(off)[-2] > 1e-3:
+            assert np.dot(n, md.equations[k, :3]) > 0.9999
+            assert np.dot(n, [con2["nx"], con2["ny"], con2["nz"]]) > 0.999
+        # witness points: position = their midpoint, and they are depth apart along n on the supporting planes
+        Ra, Rb = rot_matrix(qa), rot_matrix(qb)
+        sup_a = float(np.sum(haf * np.abs(Ra.T @ n)))
+        sup_b = float(np.sum(hbf * np.abs(Rb.T @ n)))
+        pos = np.array([con["px"], con["py"], con["pz"]], float)
+        # midpoint of a point on A's supporting plane (offset +sup_a along n from A's centre) and a point on
+        # B's (offset -sup_b from B's centre): its n-coordinate is the mean of the two plane offsets
+        expect = 0.5 * ((np.float32(ca).astype(float) @ n + sup_a) + (np.float32(cb).astype(float) @ n - sup_b))
+        assert abs(pos @ n - expect) < 1e-4
+        checked += 1
+    assert checked > 100, checked

@@ -21,6 +21,7 @@ SHAPE_SPHERE, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_PLANE, SHAPE_CONVEX, SHAPE_MESH = 
 FLAG_PAIR_DISTANCES = 1
 FLAG_TEMPORAL_COHERENCE = 4
 FLAG_BOXBOX_GJK_EPA = 8
+FLAG_NO_GRAPH = 16
 
 SHAPE_DT = np.dtype([("type", "<u4"), ("p0", "<f4"), ("p1", "<f4"), ("p2", "<f4")])
 CONTACT_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),
@@ -34,18 +35,20 @@ RAY_DT = np.dtype([("ox", "<f4"), ("oy", "<f4"), ("oz", "<f4"), ("dx", "<f4"), (
 RAYHIT_DT = np.dtype([("body", "<u4"), ("t", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
                       ("flags", "<u4")])
 NO_HIT = 0xFFFFFFFF
+FILTER_DT = np.dtype([("categoryBits", "<u4"), ("maskBits", "<u4"), ("groupIndex", "<i2"), ("reserved_", "<u2")])
 SWEEP_DT = np.dtype([("hit", "<u4"), ("toi", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"),
                      ("iterations", "<u4")])
 
 # every symbol include/axcd.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "axcd_default_config", "axcd_create", "axcd_destroy", "axcd_set_shapes",
-    "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step",
+    "axcd_default_config", "axcd_device_count", "axcd_create", "axcd_destroy", "axcd_set_shapes",
+    "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_step_async",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_pin_host_buffer", "axcd_unpin_host_buffer",
     "axcd_set_filters", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
-    "axcd_set_ghosts_device",
+    "axcd_set_ghosts_device", "axcd_nccl_unique_id", "axcd_slab_init", "axcd_slab_init_comm",
+    "axcd_slab_step_async", "axcd_slab_step", "axcd_get_body_keys",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench", "axcd_test_fp32_peak",
 ]
 SCENE_SYMBOLS = ["axcd_scene_generate", "axcd_scene_generate_worlds", "axcd_scene_rng_u32"]
@@ -70,7 +73,8 @@ class Stats(C.Structure):
                 ("broadphaseTime", C.c_float), ("narrowphaseTime", C.c_float),
                 ("bytesMoved", C.c_uint64), ("kernelLaunches", C.c_uint32),
                 ("contactPointCount", C.c_uint32),
-                ("movedBodies", C.c_uint32), ("broadphaseSkipped", C.c_uint32)]
+                ("movedBodies", C.c_uint32), ("broadphaseSkipped", C.c_uint32), ("graphLaunched", C.c_uint32),
+                ("ghostBodies", C.c_uint32), ("exchangeMs", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -122,6 +126,18 @@ def load_library():
         for name in ("axcd_refit", "axcd_broadphase", "axcd_narrowphase"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.axcd_step.argtypes = [C.c_void_p, C.c_void_p]
+        lib.axcd_step_async.restype = C.c_int32
+        lib.axcd_step_async.argtypes = [C.c_void_p]
+        for name in ("axcd_nccl_unique_id", "axcd_slab_init", "axcd_slab_init_comm", "axcd_slab_step_async",
+                     "axcd_slab_step"):
+            getattr(lib, name).restype = C.c_int32
+        lib.axcd_nccl_unique_id.argtypes = [C.c_void_p]
+        lib.axcd_slab_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        lib.axcd_slab_init_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        lib.axcd_slab_step_async.argtypes = [C.c_void_p]
+        lib.axcd_slab_step.argtypes = [C.c_void_p, C.c_void_p]
+        lib.axcd_get_body_keys.restype = C.c_int32
+        lib.axcd_get_body_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         lib.axcd_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.axcd_get_aabbs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         lib.axcd_get_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
@@ -171,6 +187,15 @@ def error_string(code):
         return load_library().axcd_error_string(C.c_int32(code)).decode()
     except Exception:
         return "?"
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId created by the library (rank 0 calls this and broadcasts the bytes)."""
+    buf = (C.c_char * 128)()
+    rc = load_library().axcd_nccl_unique_id(buf)
+    if rc != 0:
+        raise AxcdError(rc, "axcd_nccl_unique_id")
+    return bytes(buf)
 
 
 def default_config(**kw):
@@ -361,6 +386,10 @@ class CollisionWorld:
         self._check(self._lib.axcd_step(self._ctx, C.byref(st)), "axcd_step")
         return st
 
+    def step_async(self):
+        """Enqueues the fused step (one CUDA graph launch once the configuration is stable) and returns."""
+        self._check(self._lib.axcd_step_async(self._ctx), "axcd_step_async")
+
     def stats(self):
         st = Stats()
         self._check(self._lib.axcd_get_stats(self._ctx, C.byref(st)), "axcd_get_stats")
@@ -467,7 +496,11 @@ class CollisionWorld:
         if filters is None:
             self._check(self._lib.axcd_set_filters(self._ctx, None, 0), "axcd_set_filters")
             return
-        f = np.ascontiguousarray(filters, dtype=np.int64).reshape(-1, 3).astype(np.uint32)
+        src = np.ascontiguousarray(filters, dtype=np.int64).reshape(-1, 3)
+        f = np.zeros(len(src), FILTER_DT)   # the layout of gui::FilterInfo: uint32, uint32, int16 (+ padding)
+        f["categoryBits"] = src[:, 0].astype(np.uint32)
+        f["maskBits"] = src[:, 1].astype(np.uint32)
+        f["groupIndex"] = src[:, 2].astype(np.int16)
         self._check(self._lib.axcd_set_filters(self._ctx, _ptr(f), len(f)), "axcd_set_filters")
 
     # ---- x-slab mode (one scene across several GPUs) -------------------------------------------
@@ -496,6 +529,29 @@ class CollisionWorld:
         self._check(self._lib.axcd_pack_ghosts(self._ctx, _ptr(e), num_ranks, my_rank, ptrs, _ptr(counts)),
                     "axcd_pack_ghosts")
         return [p or 0 for p in ptrs], counts
+
+    # the exchange inside the library (NCCL bound at run time)
+    def slab_init(self, unique_id, rank, num_ranks, edges):
+        """unique_id: 128 bytes from nccl_unique_id() of rank 0 (broadcast by the host); collective."""
+        e = np.ascontiguousarray(edges, dtype=np.float32)
+        assert len(e) == num_ranks + 1
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.axcd_slab_init(self._ctx, buf, rank, num_ranks, _ptr(e)), "axcd_slab_init")
+
+    def slab_step(self):
+        st = Stats()
+        self._check(self._lib.axcd_slab_step(self._ctx, C.byref(st)), "axcd_slab_step")
+        self.n = st.numBodies
+        return st
+
+    def slab_step_async(self):
+        self._check(self._lib.axcd_slab_step_async(self._ctx), "axcd_slab_step_async")
+
+    def body_keys(self):
+        """Global ids of the local bodies (owned, then this step's ghosts)."""
+        out = np.zeros(max(1, self.n), np.uint32)
+        self._check(self._lib.axcd_get_body_keys(self._ctx, _ptr(out), len(out)), "axcd_get_body_keys")
+        return out[:self.n]
 
     def set_ghosts_device(self, n_owned, n_ghosts, dev_ptr):
         self._check(self._lib.axcd_set_ghosts_device(self._ctx, n_owned, n_ghosts, C.c_void_p(dev_ptr)),

@@ -332,13 +332,38 @@ class SlabRank:
         received = self.exchange_device(send, dist) if self.size > 1 else []
         return self.step_with_device(received)
 
+    # ---- the exchange inside the library (axcd_slab_init / axcd_slab_step: NCCL, no torch on the data path) ----
+    def init_native(self, dist=None):
+        """Creates the library's own NCCL communicator.  The 128-byte unique id comes from rank 0 and
+        travels through torch.distributed (plumbing only; a C++ host would use its own launcher)."""
+        from . import nccl_unique_id
+        if self.size > 1 and dist is not None:
+            import torch
+            dev = f"cuda:{self.w.cfg.deviceOrdinal}" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if self.rank == 0:
+                t.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            uid = bytes(t.cpu().numpy().tobytes())
+        else:
+            uid = nccl_unique_id()
+        self.w.slab_init(uid, self.rank, self.size, np.asarray(self.edges, np.float32))
+
+    def step_native(self):
+        """One collective slab step entirely behind the C ABI.  Returns AxcdStats (with exchangeMs, ghostBodies)."""
+        st = self.w.slab_step()
+        self.local_gid = None
+        return st
+
     def pairs_global(self):
         if self.local_gid is None:
-            raise RuntimeError("global ids of device-side ghosts are not mirrored on the host; use step()")
+            self.local_gid = self.w.body_keys()
         p = self.local_gid[self.w.pairs()]
         return p[np.lexsort((p[:, 1], p[:, 0]))]
 
     def contacts_global(self):
+        if self.local_gid is None:
+            self.local_gid = self.w.body_keys()
         c = self.w.contacts().copy()
         c["a"], c["b"] = self.local_gid[c["a"]], self.local_gid[c["b"]]
         return c[np.lexsort((c["b"], c["a"]))]

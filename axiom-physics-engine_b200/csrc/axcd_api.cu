@@ -5,6 +5,8 @@
 #include <cstring>
 #include <new>
 
+#include <dlfcn.h>
+
 #include "axcd.h"
 #include "axcd_common.cuh"
 #include "axcd_lbvh.cuh"
@@ -69,6 +71,18 @@ struct AxcdContext {
     float4* dGhostSend = nullptr;    // slab mode: numRanks send buffers of ghost records
     uint32_t* dGhostCount = nullptr;
     uint32_t ghostRanks = 0, ghostCap = 0;
+    // x-slab mode with the exchange inside the library (axcd_slab_init / axcd_slab_step): NCCL communicator,
+    // slab edges on the device, the size matrix of the handshake and the receive buffer
+    void* slabComm = nullptr;        // ncclComm_t
+    bool slabOwnsComm = false;
+    uint32_t slabRank = 0, slabRanks = 0;
+    float* dEdges = nullptr;         // slabRanks + 1 slab edges
+    uint32_t* dCountMatrix = nullptr;   // slabRanks x slabRanks: row r = records rank r sends to each rank
+    uint32_t* hCountMatrix = nullptr;   // pinned host copy
+    float4* dGhostRecv = nullptr;       // ghostCap records
+    uint32_t lastGhosts = 0;
+    float lastExchangeMs = 0.0f;
+    cudaEvent_t evX0 = nullptr, evX1 = nullptr;
     float* dAabb = nullptr;          // n * 6 floats (axiom::math::AABB AoS)
     uint32_t* dKeys[2] = {nullptr, nullptr};
     uint32_t* dVals[2] = {nullptr, nullptr};
@@ -121,6 +135,20 @@ struct AxcdContext {
     Counters* dCtrInit = nullptr;    // per-step initial value of the counters (device copy: async reset)
     cudaEvent_t ev[EV_COUNT];
     bool evValid[EV_COUNT];
+    // ---- CUDA graph of the fused step (axcd_step / axcd_step_async) --------------------------------
+    // One executable graph per counter-block parity.  `gen` counts every call that changes what the
+    // stage functions would launch (body count, filters, slab rule, ...); a graph is replayed only while
+    // its generation is current, and captured only once the configuration has been stable for a step.
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t gen = 0;
+        uint32_t launches[3] = {0, 0, 0};
+        int sortedBuf = 0;
+    } graph[2];
+    uint64_t gen = 1, lastStepGen = 0;
+    bool capturing = false;      // stage functions are being recorded into a graph: no event records
+    bool graphsOff = false;      // AXCD_NO_GRAPH=1, or a capture failed once
+    bool lastStepGraph = false;  // the last fused step was a graph launch (no per-stage times)
 };
 
 namespace {
@@ -138,6 +166,8 @@ int fail(AxcdContext* c, cudaError_t e, const char* what) {
         if (_e != cudaSuccess) return fail(ctx, _e, #call);        \
     } while (0)
 
+void slabRelease(AxcdContext* ctx);   // NCCL communicator and slab buffers (defined with the slab entry points)
+
 template <typename T>
 cudaError_t dalloc(T** p, size_t count) {
     return cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (count ? count : 1));
@@ -150,6 +180,7 @@ int bitsFor(uint32_t n) {   // bits needed to represent values in [0, n)
 }
 
 void recordEv(AxcdContext* c, int e) {
+    if (c->capturing) return;   // timing events are not part of the step graph
     cudaEventRecord(c->ev[e], c->stream);
     c->evValid[e] = true;
 }
@@ -175,6 +206,7 @@ uint32_t sortTilesFor(uint64_t n) { return (uint32_t)((n + kSortTile - 1) / kSor
 // Morton resolution.
 int resizeBodies(AxcdContext* ctx, uint32_t n) {
     ctx->n = n;
+    ctx->gen++;
     ctx->fatValid = false;      // a different body set: no fat box or cached pair list carries over
     ctx->pairsCached = false;
     uint32_t P = 1;
@@ -280,6 +312,15 @@ int32_t axcd_unpin_host_buffer(void* hostPtr) {
 
 const char* axcd_last_device_error(AxcdContext* ctx) { return ctx ? ctx->lastErr : ""; }
 
+int32_t axcd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 void axcd_destroy(AxcdContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
@@ -293,6 +334,9 @@ void axcd_destroy(AxcdContext* ctx) {
         if (b) cudaFree(b);
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (auto& g : ctx->graph)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    slabRelease(ctx);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
@@ -325,6 +369,10 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         cudaGetLastError();
     }
     if (ctx->cfg.epaMaxFaces > (uint32_t)kEpaHardFaces) ctx->cfg.epaMaxFaces = kEpaHardFaces;
+    {
+        const char* ng = getenv("AXCD_NO_GRAPH");
+        if (ng && ng[0] == '1') ctx->graphsOff = true;
+    }
     for (int i = 0; i < EV_COUNT; ++i) {
         ctx->ev[i] = nullptr;
         ctx->evValid[i] = false;
@@ -430,10 +478,19 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
             return AXCD_ERR_INVALID_SHAPE;   // Plane / Mesh are not in scope
         }
         if (s.type == AXCD_SHAPE_CAPSULE) anyCapsule = true;
+        // sizes must be finite and non-negative (a flat box or a zero radius is a valid degenerate shape)
+        if (s.type == AXCD_SHAPE_SPHERE && !(s.p0 >= 0.0f && s.p0 < 3.0e38f)) return AXCD_ERR_INVALID_SHAPE;
+        if (s.type == AXCD_SHAPE_BOX && !(s.p0 >= 0.0f && s.p0 < 3.0e38f && s.p1 >= 0.0f && s.p1 < 3.0e38f && s.p2 >= 0.0f && s.p2 < 3.0e38f))
+            return AXCD_ERR_INVALID_SHAPE;
+        if (s.type == AXCD_SHAPE_CAPSULE && !(s.p0 >= 0.0f && s.p0 < 3.0e38f && s.p1 >= 0.0f && s.p1 < 3.0e38f)) return AXCD_ERR_INVALID_SHAPE;
         if (ctx->cfg.numWorlds > 1 && worldId[i] >= ctx->cfg.numWorlds) return AXCD_ERR_OUT_OF_RANGE;
     }
     ctx->hasHulls = anyHull;
     ctx->hasGenericShapes = anyHull || anyCapsule;
+    ctx->gen++;
+    ctx->filtersOn = false;   // per-body filter words describe the previous body set: set them again
+    if (ctx->awakeOn && ctx->dAwake) cudaMemsetAsync(ctx->dAwake, 1, ctx->cfg.maxBodies, ctx->stream);
+    ctx->awakeOn = false;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     CU(cudaMemcpyAsync(ctx->dShapes, shapes, sizeof(AxcdShape) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (nHullVerts) {
@@ -485,6 +542,10 @@ int32_t axcd_refit(AxcdContext* ctx) {
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     recordEv(ctx, EV_START);
     ctx->manifoldsValid = false;
+    // temporal coherence: the skip decision reads the moved-body count of the LAST refit only.  If the
+    // previous refit was never consumed by a broadphase, the bodies it moved are not in the cached pair
+    // list and this refit will not count them again: the cache cannot be trusted.
+    if (ctx->stage == ST_REFIT) ctx->pairsCached = false;
     // reset per-step counters: bounds (min = +inf encoding, max = -inf encoding) and counts
     // per-step counters (scene bounds at +-inf encodings, counts at zero): this step takes the block the
     // previous refit kernel reset, and its own refit kernel resets the other one for the next step — no
@@ -555,14 +616,25 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
     if (n >= 2) {
         // ---- Morton keys + radix sort ----------------------------------------------------------
         const uint32_t blocks = (n + kRefitThreads - 1) / kRefitThreads;
-        mortonKernel<<<blocks, kRefitThreads, 0, st>>>(reinterpret_cast<const float4*>(ctx->dAabb),
-                                                       ctx->hasWorlds ? ctx->dWorld : nullptr, ctx->dKeys[0],
-                                                       ctx->dVals[0], n, ctx->mortonBits, ctx->dCtr);
-        CU(cudaGetLastError());
         const int keyBits = 3 * ctx->mortonBits + ctx->worldBits;
         const int passes = (keyBits + 7) / 8;
+        // scratch the later kernels expect zeroed: cleared by the Morton kernel, not by memset nodes
+        const uint32_t scanTilesZ = (n + kScanTile - 1) / kScanTile;
+        const uint32_t slotTilesZ = (ctx->cfg.maxPairs + kSlotTile - 1) / kSlotTile;
+        ZeroList zl;
+        zl.ptr[0] = ctx->dBodyCount;   zl.words[0] = n;
+        zl.ptr[1] = ctx->dScanStatus;  zl.words[1] = scanTilesZ + 1;
+        zl.ptr[2] = ctx->dSlotStatus;  zl.words[2] = slotTilesZ + 1;
+        zl.ptr[3] = ctx->dSortHist;    zl.words[3] = kMaxPasses * kRadix;
+        zl.ptr[4] = ctx->dSortStatus;  zl.words[4] = (uint32_t)passes * sortTilesFor(n) * kRadix;
+        mortonKernel<<<blocks, kRefitThreads, 0, st>>>(reinterpret_cast<const float4*>(ctx->dAabb),
+                                                       ctx->hasWorlds ? ctx->dWorld : nullptr, ctx->dKeys[0],
+                                                       ctx->dVals[0], n, ctx->mortonBits, ctx->dCtr, zl);
+        CU(cudaGetLastError());
+        // the radix tickets live in the per-step counter block, which the refit kernel reset
         const int sb = radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0,
-                                                 passes, ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st);
+                                                 passes, ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st,
+                                                 ctx->numSMs, true);
         CU(cudaGetLastError());
         recordEv(ctx, EV_SORT);
         ctx->sortedBuf = sb;
@@ -599,7 +671,6 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         CU(cudaGetLastError());
         recordEv(ctx, EV_BUILD);
         // ---- traversal ---------------------------------------------------------------------------
-        CU(cudaMemsetAsync(ctx->dBodyCount, 0, sizeof(uint32_t) * n, st));
         const uint32_t tb = (n + kTravThreads - 1) / kTravThreads;
         findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes32, ctx->dSegLo, ctx->dSegHi,
                                                      ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
@@ -611,7 +682,6 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         recordEv(ctx, EV_PAIR);
         // ---- canonical order: counting sort by body a, then tiny per-body sorts by b ------------------
         const uint32_t scanTiles = (n + kScanTile - 1) / kScanTile;
-        CU(cudaMemsetAsync(ctx->dScanStatus, 0, sizeof(uint32_t) * (scanTiles + 1), st));
         // the scan writes the segment starts twice: dBodyStart stays, the copy is the scatter's fill cursor
         exclusiveScanKernel<<<scanTiles, kScanThreads, 0, st>>>(ctx->dBodyCount, ctx->dBodyStart, ctx->dBodyCount + n, n,
                                                                 ctx->dScanStatus, &ctx->dCtr->scanTicket,
@@ -667,7 +737,9 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         if (tiles > (uint32_t)ctx->numSMs * AXCD_GJK_MIN_BLOCKS) tiles = ctx->numSMs * AXCD_GJK_MIN_BLOCKS;   // one resident wave
         const uint32_t slotTilesMax = (mp + kSlotTile - 1) / kSlotTile;
         const uint32_t slotBlocks = slotTilesMax < (uint32_t)ctx->numSMs * 4 ? slotTilesMax : ctx->numSMs * 4;
-        CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * (slotTilesMax + 1), st));
+        // the slot scan's status words were cleared by this step's Morton kernel; a step that reused the
+        // cached broadphase (temporal coherence) did not run it
+        if (ctx->broadSkipped) CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * (slotTilesMax + 1), st));
         NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow, ctx->dEpaSpill, ctx->spillCap};
         const uint2* pairs = ctx->dPairs;
         const uint32_t* pairCount = &ctx->dCtr->pairCount;
@@ -745,8 +817,9 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
         out->gjkMs = evMs(ctx, EV_N0, EV_GJK);
         out->epaMs = evMs(ctx, EV_GJK, EV_END);
         out->narrowphaseTime = evMs(ctx, EV_N0, EV_END);
-        out->totalMs = evMs(ctx, EV_START, EV_END);
+        out->totalMs = evMs(ctx, EV_START, EV_END);   // a graph-launched step has this one only
     }
+    out->graphLaunched = ctx->lastStepGraph ? 1u : 0u;
     // algorithmic bytes: refit 80 B/body, Morton 32 B/body, sort (16 B * passes + 4) per
     // element, pair sort (16 B * passes + 8) per pair, narrowphase gather 96 B/pair + 40 B/contact
     {
@@ -764,13 +837,90 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
     return AXCD_OK;
 }
 
-int32_t axcd_step(AxcdContext* ctx, AxcdStats* outStats) {
+// The fused step, asynchronous.  Replays the CUDA graph of refit + broadphase + narrowphase when one is
+// current for this counter parity; captures one when the launch configuration has been stable since the
+// previous step; otherwise (first step, configuration just changed, temporal coherence with its host-side
+// decision, graphs switched off) calls the stage functions directly.
+int32_t axcd_step_async(AxcdContext* ctx) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    const bool graphable = !ctx->graphsOff && !(ctx->cfg.flags & (AXCD_FLAG_TEMPORAL_COHERENCE | AXCD_FLAG_NO_GRAPH)) &&
+                           ctx->n >= 2;
+    const bool stable = ctx->lastStepGen == ctx->gen;
+    ctx->lastStepGen = ctx->gen;
+    ctx->lastStepGraph = false;
+    if (graphable) {
+        const int parity = ctx->ctrParity ^ 1;   // the parity axcd_refit is about to switch to
+        AxcdContext::StepGraph& g = ctx->graph[parity];
+        if (g.exec && g.gen != ctx->gen) {
+            cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+        }
+        if (!g.exec && stable) {
+            // record the stage functions into a graph (they skip their timing events while capturing)
+            cudaGraph_t graph = nullptr;
+            const int parityBefore = ctx->ctrParity;
+            const int stageBefore = ctx->stage;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                ctx->capturing = true;
+                int32_t rc = axcd_refit(ctx);
+                if (!rc) rc = axcd_broadphase(ctx);
+                if (!rc) rc = axcd_narrowphase(ctx);
+                ctx->capturing = false;
+                const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+                if (!rc && e == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                    g.gen = ctx->gen;
+                    g.launches[0] = ctx->launches[0];
+                    g.launches[1] = ctx->launches[1];
+                    g.launches[2] = ctx->launches[2];
+                    g.sortedBuf = ctx->sortedBuf;
+                } else {
+                    g.exec = nullptr;
+                    ctx->graphsOff = true;   // something on the path is not capturable here: stay on direct launches
+                }
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+            } else {
+                cudaGetLastError();
+                ctx->graphsOff = true;
+            }
+            // nothing has run yet: rewind the host-side state the recording advanced
+            ctx->ctrParity = parityBefore;
+            ctx->dCtr = ctx->dCtrBase + ctx->ctrParity;
+            ctx->stage = stageBefore;
+        }
+        if (g.exec) {
+            ctx->ctrParity = parity;
+            ctx->dCtr = ctx->dCtrBase + parity;
+            for (int e = 0; e < EV_COUNT; ++e) ctx->evValid[e] = false;
+            recordEv(ctx, EV_START);
+            CU(cudaGraphLaunch(g.exec, ctx->stream));
+            recordEv(ctx, EV_END);
+            ctx->launches[0] = g.launches[0];
+            ctx->launches[1] = g.launches[1];
+            ctx->launches[2] = g.launches[2];
+            ctx->sortedBuf = g.sortedBuf;
+            ctx->numPairs = ctx->foundPairs = 0;
+            ctx->numContacts = ctx->foundContacts = 0;
+            ctx->manifoldsValid = false;
+            ctx->queryNodesValid = false;
+            ctx->broadSkipped = false;
+            ctx->stage = ST_NARROW;
+            ctx->lastStepGraph = true;
+            return AXCD_OK;
+        }
+    }
     int32_t rc = axcd_refit(ctx);
     if (rc) return rc;
     rc = axcd_broadphase(ctx);
     if (rc) return rc;
-    rc = axcd_narrowphase(ctx);
+    return axcd_narrowphase(ctx);
+}
+
+int32_t axcd_step(AxcdContext* ctx, AxcdStats* outStats) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    int32_t rc = axcd_step_async(ctx);
     if (rc) return rc;
     AxcdStats tmp;
     rc = axcd_get_stats(ctx, outStats ? outStats : &tmp);
@@ -1040,11 +1190,13 @@ int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs
 int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t n) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
     ctx->pairsCached = false;   // the candidate rule changed
+    ctx->gen++;
     if (!awake) {
         ctx->awakeOn = false;
         return AXCD_OK;
     }
     if (n > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    if (n != ctx->nOwned) return AXCD_ERR_INVALID_PARAM;   // one flag per owned body (ghosts count as awake)
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (!ctx->dAwake) {
         CU(dalloc(&ctx->dAwake, (size_t)ctx->cfg.maxBodies));
@@ -1058,18 +1210,22 @@ int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t n) {
 
 int32_t axcd_set_filters(AxcdContext* ctx, const AxcdFilter* filters, uint32_t n) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
+    ctx->gen++;
     if (!filters) {
         ctx->filtersOn = false;
         ctx->pairsCached = false;
         return AXCD_OK;
     }
-    if (n > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    // one record per body held (the traversal reads the filter of every body it pairs); ghost bodies of the
+    // slab mode carry no filter words, so filtering and slabs do not combine in this version
+    if (ctx->slabOn || ctx->n != ctx->nOwned) return AXCD_ERR_INVALID_PARAM;
+    if (ctx->stage < ST_SHAPES || n != ctx->n) return AXCD_ERR_INVALID_PARAM;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (!ctx->dFilters) CU(dalloc(&ctx->dFilters, (size_t)ctx->cfg.maxBodies));
     uint4* tmp = static_cast<uint4*>(malloc(sizeof(uint4) * (n ? n : 1)));
     if (!tmp) return AXCD_ERR_OUT_OF_MEMORY;
     for (uint32_t i = 0; i < n; ++i)
-        tmp[i] = make_uint4(filters[i].categoryBits, filters[i].maskBits, (uint32_t)filters[i].groupIndex, 0u);
+        tmp[i] = make_uint4(filters[i].categoryBits, filters[i].maskBits, (uint32_t)(int32_t)filters[i].groupIndex, 0u);
     cudaError_t e = cudaMemcpyAsync(ctx->dFilters, tmp, sizeof(uint4) * n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     free(tmp);
@@ -1085,6 +1241,8 @@ int32_t axcd_set_slab(AxcdContext* ctx, float xLo, float xHi, uint32_t enable) {
     if (enable && ctx->cfg.numWorlds > 1) return AXCD_ERR_INVALID_PARAM;   // slabs split ONE scene
     // the ghost set changes every step, so there is no persistent fat-box state to be coherent with
     if (enable && (ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE)) return AXCD_ERR_INVALID_PARAM;
+    if (enable && ctx->filtersOn) return AXCD_ERR_INVALID_PARAM;   // ghost records carry no filter words
+    if (ctx->slabOn != (enable != 0) || ctx->slabLo != xLo || ctx->slabHi != xHi) ctx->gen++;
     ctx->slabOn = enable != 0;
     ctx->slabLo = xLo;
     ctx->slabHi = xHi;
@@ -1096,6 +1254,15 @@ int32_t axcd_set_body_keys(AxcdContext* ctx, const uint32_t* keys, uint32_t firs
     if ((uint64_t)first + count > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (count) CU(cudaMemcpyAsync(ctx->dBodyKeys + first, keys, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+    return AXCD_OK;
+}
+
+int32_t axcd_get_body_keys(AxcdContext* ctx, uint32_t* outKeys, uint32_t cap) {
+    if (!ctx || (!outKeys && ctx->n)) return AXCD_ERR_NULL_POINTER;
+    if (cap < ctx->n) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (ctx->n) CU(cudaMemcpyAsync(outKeys, ctx->dBodyKeys, sizeof(uint32_t) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return AXCD_OK;
 }
 
@@ -1186,6 +1353,224 @@ int32_t axcd_set_ghosts_device(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhos
     }
     ctx->stage = ST_POSES;
     return AXCD_OK;
+}
+
+// ---- x-slab mode with the ghost exchange inside the library --------------------------------
+// NCCL is bound at run time (dlopen of libnccl.so.2), so libaxcd.so loads and every single-GPU entry point
+// works on a machine without NCCL; a process that already loaded NCCL (torch) shares that copy.
+}  // extern "C"
+namespace {
+typedef struct ncclComm* NcclComm;
+struct NcclUniqueId { char internal[128]; };
+enum { kNcclUint32 = 3, kNcclFloat32 = 7 };   // ncclDataType_t values (nccl.h)
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi* ncclApi() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return &api;
+    auto sym = [&](const char* s) { return dlsym(api.lib, s); };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Send && api.Recv &&
+             api.GroupStart && api.GroupEnd;
+    return &api;
+}
+int ncclFail(AxcdContext* c, int rc, const char* what) {
+    NcclApi* N = ncclApi();
+    if (c) snprintf(c->lastErr, sizeof(c->lastErr), "%s: NCCL error %d (%s)", what, rc,
+                    (N->GetErrorString ? N->GetErrorString(rc) : "?"));
+    return AXCD_ERR_GPU_FAILED;
+}
+#define NC(call)                                              \
+    do {                                                      \
+        const int _r = (call);                                \
+        if (_r != 0) return ncclFail(ctx, _r, #call);         \
+    } while (0)
+
+void slabRelease(AxcdContext* ctx) {
+    if (ctx->slabComm && ctx->slabOwnsComm && ncclApi()->ok) ncclApi()->CommDestroy(static_cast<NcclComm>(ctx->slabComm));
+    ctx->slabComm = nullptr;
+    if (ctx->dEdges) cudaFree(ctx->dEdges);
+    if (ctx->dCountMatrix) cudaFree(ctx->dCountMatrix);
+    if (ctx->dGhostRecv) cudaFree(ctx->dGhostRecv);
+    if (ctx->hCountMatrix) cudaFreeHost(ctx->hCountMatrix);
+    if (ctx->evX0) cudaEventDestroy(ctx->evX0);
+    if (ctx->evX1) cudaEventDestroy(ctx->evX1);
+    ctx->dEdges = nullptr;
+    ctx->dCountMatrix = nullptr;
+    ctx->dGhostRecv = nullptr;
+    ctx->hCountMatrix = nullptr;
+    ctx->evX0 = ctx->evX1 = nullptr;
+    cudaGetLastError();
+}
+
+int slabSetup(AxcdContext* ctx, void* comm, bool owns, uint32_t rank, uint32_t numRanks, const float* edges) {
+    if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;   // owned shapes and poses first
+    if (ctx->cfg.numWorlds > 1 || (ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE)) return AXCD_ERR_INVALID_PARAM;
+    if (ctx->nHull) return AXCD_ERR_INVALID_SHAPE;   // hull ghosts would need their vertices shipped too
+    for (uint32_t r = 0; r < numRanks; ++r)
+        if (!(edges[r] <= edges[r + 1])) return AXCD_ERR_INVALID_PARAM;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    slabRelease(ctx);
+    ctx->slabComm = comm;
+    ctx->slabOwnsComm = owns;
+    ctx->slabRank = rank;
+    ctx->slabRanks = numRanks;
+    const uint32_t cap = ctx->cfg.maxBodies - ctx->nOwned;
+    if (ctx->dGhostSend) cudaFree(ctx->dGhostSend);
+    if (ctx->dGhostCount) cudaFree(ctx->dGhostCount);
+    ctx->dGhostSend = nullptr;
+    ctx->dGhostCount = nullptr;
+    CU(dalloc(&ctx->dGhostSend, (size_t)numRanks * cap * (kGhostWords / 4)));
+    CU(dalloc(&ctx->dGhostCount, (size_t)numRanks));
+    ctx->ghostRanks = numRanks;
+    ctx->ghostCap = cap;
+    CU(dalloc(&ctx->dGhostRecv, (size_t)cap * (kGhostWords / 4)));
+    CU(dalloc(&ctx->dEdges, (size_t)numRanks + 1));
+    CU(dalloc(&ctx->dCountMatrix, (size_t)numRanks * numRanks));
+    CU(cudaMallocHost(reinterpret_cast<void**>(&ctx->hCountMatrix), sizeof(uint32_t) * numRanks * numRanks));
+    CU(cudaEventCreate(&ctx->evX0));
+    CU(cudaEventCreate(&ctx->evX1));
+    CU(cudaMemcpyAsync(ctx->dEdges, edges, sizeof(float) * (numRanks + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return axcd_set_slab(ctx, edges[rank], edges[rank + 1], 1u);
+}
+}  // namespace
+extern "C" {
+
+int32_t axcd_nccl_unique_id(void* out128) {
+    if (!out128) return AXCD_ERR_NULL_POINTER;
+    NcclApi* N = ncclApi();
+    if (!N->ok) return AXCD_ERR_GPU_INIT;
+    NcclUniqueId id;
+    if (N->GetUniqueId(&id) != 0) return AXCD_ERR_GPU_FAILED;
+    memcpy(out128, &id, sizeof(id));
+    return AXCD_OK;
+}
+
+int32_t axcd_slab_init(AxcdContext* ctx, const void* uniqueId128, uint32_t rank, uint32_t numRanks, const float* edges) {
+    if (!ctx || !uniqueId128 || !edges) return AXCD_ERR_NULL_POINTER;
+    if (numRanks == 0 || numRanks > 64 || rank >= numRanks) return AXCD_ERR_INVALID_PARAM;
+    NcclApi* N = ncclApi();
+    if (!N->ok) {
+        snprintf(ctx->lastErr, sizeof(ctx->lastErr), "libnccl.so.2 could not be loaded");
+        return AXCD_ERR_GPU_INIT;
+    }
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    NcclUniqueId id;
+    memcpy(&id, uniqueId128, sizeof(id));
+    NcclComm comm = nullptr;
+    NC(N->CommInitRank(&comm, (int)numRanks, id, (int)rank));
+    const int rc = slabSetup(ctx, comm, true, rank, numRanks, edges);
+    if (rc != AXCD_OK && ctx->slabComm != comm) N->CommDestroy(comm);
+    return rc;
+}
+
+int32_t axcd_slab_init_comm(AxcdContext* ctx, void* ncclComm, uint32_t rank, uint32_t numRanks, const float* edges) {
+    if (!ctx || !ncclComm || !edges) return AXCD_ERR_NULL_POINTER;
+    if (numRanks == 0 || numRanks > 64 || rank >= numRanks) return AXCD_ERR_INVALID_PARAM;
+    if (!ncclApi()->ok) return AXCD_ERR_GPU_INIT;
+    return slabSetup(ctx, ncclComm, false, rank, numRanks, edges);
+}
+
+// One slab step, asynchronous after the size handshake: refit of the owned bodies -> device-side ghost
+// selection for every other rank (one kernel) -> ncclAllGather of the per-destination counts -> one host
+// read of the size matrix (the only host synchronisation of the step; NCCL receive counts are host
+// arguments) -> grouped ncclSend / ncclRecv of the 64-byte ghost records, GPU to GPU over NVLink -> ghosts
+// appended behind the owned bodies -> the fused step (CUDA graph once the ghost count is stable).
+int32_t axcd_slab_step_async(AxcdContext* ctx) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (!ctx->slabComm || ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;
+    NcclApi* N = ncclApi();
+    NcclComm comm = static_cast<NcclComm>(ctx->slabComm);
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    const uint32_t R = ctx->slabRanks, me = ctx->slabRank, cap = ctx->ghostCap, nOwned = ctx->nOwned;
+    CU(cudaEventRecord(ctx->evX0, st));
+    {
+        const int rc = axcd_refit(ctx);   // boxes of the owned bodies (stale ghosts behind them are refit too; harmless)
+        if (rc) return rc;
+    }
+    CU(cudaMemsetAsync(ctx->dGhostCount, 0, sizeof(uint32_t) * R, st));
+    if (nOwned && R > 1) {
+        packGhostsAllKernel<<<(nOwned + 255) / 256, 256, 0, st>>>(ctx->dAabb, ctx->dXf, ctx->dShapes, ctx->dBodyKeys, nOwned,
+                                                                 ctx->dEdges, R, me, ctx->dGhostSend, cap, ctx->dGhostCount);
+        CU(cudaGetLastError());
+    }
+    // size handshake: everybody learns the whole R x R count matrix
+    NC(N->AllGather(ctx->dGhostCount, ctx->dCountMatrix, R, kNcclUint32, comm, st));
+    CU(cudaMemcpyAsync(ctx->hCountMatrix, ctx->dCountMatrix, sizeof(uint32_t) * R * R, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint32_t* M = ctx->hCountMatrix;
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < R; ++r) {
+        if (M[r * R + me] > 0 && r != me) total += M[r * R + me];
+        for (uint32_t d = 0; d < R; ++d)
+            if (M[r * R + d] > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;   // a send buffer overflowed somewhere
+    }
+    for (uint32_t d = 0; d < R; ++d)
+        if (d != me && M[me * R + d] > cap) return AXCD_ERR_OUT_OF_RANGE;
+    if (total > cap) return AXCD_ERR_OUT_OF_RANGE;
+    // the records, rank to rank
+    NC(N->GroupStart());
+    uint64_t off = 0;
+    for (uint32_t r = 0; r < R; ++r) {
+        if (r == me) continue;
+        const uint32_t nSend = M[me * R + r], nRecv = M[r * R + me];
+        if (nSend)
+            NC(N->Send(ctx->dGhostSend + (size_t)r * cap * (kGhostWords / 4), (size_t)nSend * kGhostWords, kNcclFloat32, (int)r, comm, st));
+        if (nRecv) {
+            NC(N->Recv(ctx->dGhostRecv + off * (kGhostWords / 4), (size_t)nRecv * kGhostWords, kNcclFloat32, (int)r, comm, st));
+            off += nRecv;
+        }
+    }
+    NC(N->GroupEnd());
+    {
+        const int rc = axcd_set_ghosts_device(ctx, nOwned, (uint32_t)total, ctx->dGhostRecv);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->evX1, st));
+    ctx->lastGhosts = (uint32_t)total;
+    return axcd_step_async(ctx);
+}
+
+int32_t axcd_slab_step(AxcdContext* ctx, AxcdStats* outStats) {
+    int32_t rc = axcd_slab_step_async(ctx);
+    if (rc) return rc;
+    AxcdStats tmp;
+    AxcdStats* out = outStats ? outStats : &tmp;
+    rc = axcd_get_stats(ctx, out);
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, ctx->evX0, ctx->evX1) == cudaSuccess) out->exchangeMs = ms;
+    cudaGetLastError();
+    out->ghostBodies = ctx->lastGhosts;
+    return rc;
 }
 
 // ---- test hooks ----------------------------------------------------------------------------------

@@ -55,6 +55,13 @@ __device__ __forceinline__ SweepResult sweepCores(const Core& A, Core B, V3 D, N
         t = t + gap / approach;
         if (!(t <= 1.0f)) break;
     }
+    if (it == kCcdMaxIters) {
+        // the advancement ran out of iterations (grazing / very slow approach) while still closing in within
+        // the step: report the conservative answer — contact at the time reached — rather than a miss
+        out.hit = 1u;
+        out.toi = t;
+        out.n = nLast;
+    }
     out.iterations = (uint32_t)it;
     return out;
 }

@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t boxBoxManifold(const BoxFrame& A, const BoxF
     poly.set(3, (fc + eu) - ev);
     // clip against the reference face's side planes: s * dot(p - cR, ax_w) <= h_w  (ping-pong poly <-> tmp)
     PolyCol src = poly, dst = tmp;
+    bool over = false;
     for (int side = 0; side < 4 && np > 0; ++side) {
         const int w = (i + 1 + (side >> 1)) % 3;
         const float s = (side & 1) ? -1.0f : 1.0f;
@@ -95,17 +96,24 @@ __device__ __forceinline__ uint32_t boxBoxManifold(const BoxFrame& A, const BoxF
             const V3 cur = src.get(k);
             const float dcur = dot3(cur - R.c, pn) - hw;
             const bool inPrev = dprev <= 0.0f, inCur = dcur <= 0.0f;
+            // a convex quad clipped by four planes has at most 8 vertices; sign noise on a degenerate
+            // (zero-extent) reference face could produce more crossings: never write past the 8 slots
             if (inPrev != inCur) {
                 const float t = dprev / (dprev - dcur);
-                dst.set(nt++, prev + (cur - prev) * t);
+                if (nt < 8) dst.set(nt++, prev + (cur - prev) * t);
+                else over = true;
             }
-            if (inCur) dst.set(nt++, cur);
+            if (inCur) {
+                if (nt < 8) dst.set(nt++, cur);
+                else over = true;
+            }
             prev = cur;
             dprev = dcur;
         }
         np = nt;
         const PolyCol sw = src; src = dst; dst = sw;
     }
+    if (over) np = 0;   // the narrowphase point stands
     // four passes: the clipped polygon is back in `poly`, `tmp` is free and takes the depths.
     // keep the vertices on or below the reference face (in place: nk <= k)
     int nk = 0;

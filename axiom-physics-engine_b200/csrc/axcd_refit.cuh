@@ -425,14 +425,25 @@ __device__ __forceinline__ uint32_t expandBits10(uint32_t v) {   // 10 bits -> e
 
 // key = worldId << (3*bitsPerAxis) | morton(centre).  Reads the 24-byte AABBs through a shared
 // stage (coalesced 128-bit loads), writes key (4 B) + body index (4 B): 32 B/body.
+// Scratch words the later kernels of a step expect zeroed (per-body pair counts, look-back status words of
+// the scans and of the radix passes, the radix histograms).  mortonKernel clears them on its way — one
+// thread per body is more than enough — so no memset node precedes those kernels.
+struct ZeroList {
+    uint32_t* ptr[5];
+    uint32_t words[5];
+};
+
 __global__ void __launch_bounds__(kRefitThreads)
 mortonKernel(const float4* __restrict__ aabb4, const uint32_t* __restrict__ worldId,
              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n,
-             int bitsPerAxis, const Counters* __restrict__ ctr) {
+             int bitsPerAxis, const Counters* __restrict__ ctr, ZeroList zl) {
     __shared__ __align__(16) float sIn[kRefitThreads * 6];
     const uint32_t base = blockIdx.x * kRefitThreads;
     const uint32_t cnt = min((uint32_t)kRefitThreads, n - base);
     const int tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        for (uint32_t i = base + tid; i < zl.words[k]; i += gridDim.x * kRefitThreads) zl.ptr[k][i] = 0u;
     {
         const uint32_t nFloats = cnt * 6, nVec = nFloats / 4;
         const float4* src = aabb4 + (size_t)base * 6 / 4;
@@ -497,6 +508,42 @@ __global__ void packGhostsKernel(const float* __restrict__ aabb, const float* __
     o[1] = make_float4(t[4], t[5], t[6], t[7]);
     o[2] = make_float4(t[8], t[9], __uint_as_float(sh.x), __uint_as_float(sh.y));
     o[3] = make_float4(__uint_as_float(sh.z), __uint_as_float(sh.w), __uint_as_float(__ldg(keys + i)), 0.0f);
+}
+
+// The same selection for ALL destination ranks in one pass over the owned bodies: slab r = [edges[r],
+// edges[r+1]) for r != myRank; out holds numRanks send buffers of `cap` records each, counters one word per
+// rank.  (Slabs are contiguous, so a body usually matches none or one neighbour.)
+__global__ void packGhostsAllKernel(const float* __restrict__ aabb, const float* __restrict__ xf,
+                                    const uint4* __restrict__ shapes, const uint32_t* __restrict__ keys,
+                                    uint32_t nOwned, const float* __restrict__ edges, uint32_t numRanks, uint32_t myRank,
+                                    float4* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    float mn = 0.0f, mx = 0.0f;
+    const bool live = i < nOwned;
+    if (live) {
+        mn = __ldg(aabb + (size_t)i * 6);
+        mx = __ldg(aabb + (size_t)i * 6 + 3);
+    }
+    for (uint32_t r = 0; r < numRanks; ++r) {
+        if (r == myRank) continue;
+        const bool take = live && mn < __ldg(edges + r + 1) && mx >= __ldg(edges + r);
+        const uint32_t bal = __ballot_sync(0xffffffffu, take);
+        if (!bal) continue;
+        uint32_t base = 0;
+        if (lane == __ffs(bal) - 1) base = atomicAdd(counters + r, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+        if (!take) continue;
+        const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+        if (slot >= cap) continue;   // counted, not stored: the host sees counter > cap
+        const float* t = xf + (size_t)i * 10;
+        const uint4 sh = __ldg(shapes + i);
+        float4* o = out + ((size_t)r * cap + slot) * (kGhostWords / 4);
+        o[0] = make_float4(t[0], t[1], t[2], t[3]);
+        o[1] = make_float4(t[4], t[5], t[6], t[7]);
+        o[2] = make_float4(t[8], t[9], __uint_as_float(sh.x), __uint_as_float(sh.y));
+        o[3] = make_float4(__uint_as_float(sh.z), __uint_as_float(sh.w), __uint_as_float(__ldg(keys + i)), 0.0f);
+    }
 }
 
 // Appends received ghost records after the owned bodies.

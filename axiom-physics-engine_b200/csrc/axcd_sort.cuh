@@ -217,12 +217,15 @@ radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
 template <typename K, bool HAS_VAL>
 inline int radixSort(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, uint32_t n, int bitStart,
                      int passes, uint32_t* scratchHist, uint32_t* scratchStatus,
-                     uint32_t* tickets /* kMaxPasses words */, cudaStream_t stream, int numSMs = kNumSMs) {
+                     uint32_t* tickets /* kMaxPasses words */, cudaStream_t stream, int numSMs = kNumSMs,
+                     bool scratchZeroed = false /* the caller already cleared hist / status / tickets */) {
     if (n == 0 || passes == 0) return 0;
     const uint32_t numTiles = (n + kSortTile - 1) / kSortTile;
-    cudaMemsetAsync(scratchHist, 0, sizeof(uint32_t) * kMaxPasses * kRadix, stream);
-    cudaMemsetAsync(scratchStatus, 0, sizeof(uint32_t) * (size_t)passes * numTiles * kRadix, stream);
-    cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * kMaxPasses, stream);
+    if (!scratchZeroed) {
+        cudaMemsetAsync(scratchHist, 0, sizeof(uint32_t) * kMaxPasses * kRadix, stream);
+        cudaMemsetAsync(scratchStatus, 0, sizeof(uint32_t) * (size_t)passes * numTiles * kRadix, stream);
+        cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * kMaxPasses, stream);
+    }
     uint32_t histBlocks = (n + kSortThreads * AXCD_HIST_ITEMS - 1) / (kSortThreads * AXCD_HIST_ITEMS);
     if (histBlocks > (uint32_t)numSMs * 8) histBlocks = numSMs * 8;
     radixHistogramKernel<K><<<histBlocks, kSortThreads, 0, stream>>>(keysA, n, bitStart, passes, scratchHist);

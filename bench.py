@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the collision hot path (refit -> broadphase -> GJK/EPA).
+"""bench.py — headline benchmark of the collision hot path (refit -> broadphase -> narrowphase).
 
 Metric (BASELINE.json): candidate+contact pairs/sec (and ms/step) at 1M bodies.  A "step" is one
 pass of the path over the scene: axcd_refit + axcd_broadphase + axcd_narrowphase.
@@ -8,15 +8,19 @@ pass of the path over the scene: axcd_refit + axcd_broadphase + axcd_narrowphase
 
 * N = 1: the headline workload — 1,000,000 mixed boxes/spheres, L = 100, seed 3.
 * N > 1 (launched by torchrun, one rank per GPU): independent worlds, one 1M-body scene per rank
-  (seed 3 + rank), no data-path collective -> weak scaling; `value` = all ranks' pairs / max time.
-* `value`   : inputs already resident in HBM (transforms uploaded once), CUDA-event timed per step,
-              L2 flushed between timed steps.
+  (seed 3 + rank), no data-path collective -> weak scaling; `value` = all ranks' pairs / max time.  The
+  same invocation then also runs the two multi-GPU configurations BASELINE.json names and reports them
+  as extra keys: `c3` (4096 x 256-body worlds split over the ranks, strong scaling, no collective) and
+  `c4` (the 16M-body scene in x-slabs with the ghost exchange over NCCL inside libaxcd.so).
+* `value`   : inputs already resident in HBM (transforms uploaded once), the fused step as the public API
+              runs it (axcd_step_async: one CUDA graph launch), CUDA-event timed per step, L2 flushed
+              between timed steps.  The per-stage table comes from separate steps through the staged calls.
 * `e2e`     : the same metric through the public API with HOST buffers: every step uploads the
               transforms from pinned host memory (H2D inside the timed region) and reads the
               contacts back to pinned host memory (D2H).
 * `--impl reference`: the CPU oracle (the only "reference implementation" that exists for this
-              path — the upstream snapshot has no collision code) on all host cores, on a bounded
-              sample of the same workload.
+              path — the upstream snapshot has no collision code) on all host cores, on the SAME full-size
+              workload (one step of the 1M-body scene is a few hundred ms of CPU work).
 """
 import argparse
 import json
@@ -32,13 +36,24 @@ sys.path.insert(0, os.path.join(ROOT, "axiom-physics-engine_b200"))
 METRIC = "candidate+contact pairs/sec at 1M bodies"
 UNIT = "pairs/s"
 WORKLOADS = {
-    # name: (config_scene name, description)
     "headline": "1M mixed boxes/spheres, L=100, seed 3 (refit + sort + LBVH + GJK/EPA)",
     "C1": "100k mixed boxes/spheres, L=46.4, seed 2",
     "C2": "1M bodies 40% box / 30% sphere / 30% 16-vertex hulls, L=100, seed 4 (EPA-heavy)",
     "C3": "4096 independent 256-body worlds batched, L=6.35, seed 1000+world",
     "C4": "16M-body single scene (scaled by --scale), x-slab decomposition with ghost exchange over NCCL",
 }
+L2_NOTE = "256 MiB written, then 256 MiB read, between timed steps: L2 cold and clean"
+# flops per unit of the FP32-bound kernels: GJK ~2 kflop per pair that runs it, EPA 10-20
+# kflop per penetrating pair (midpoint)
+GJK_FLOP_PER_PAIR = 2.0e3
+EPA_FLOP_PER_PAIR = 15.0e3
+
+
+def make_config(workload, world, n, npairs, ncon, nepa):
+    """The `config` object, identical for our arm and the reference arm of the same workload."""
+    return {"workload": WORKLOADS[workload], "bodies_per_gpu": int(n), "candidate_pairs": int(npairs),
+            "contacts": int(ncon), "epa_runs": int(nepa), "l2": L2_NOTE,
+            "parallelism": "one independent scene per rank, no collective" if world > 1 else "single GPU"}
 
 
 def load_peaks():
@@ -53,28 +68,50 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons of one GPU during the timed region (rank 0 only: one sampler
+    per job, not one per rank).  NVML through nvidia_ml_py when importable, else nvidia-smi."""
 
     def __init__(self, device):
         self.device = device
         self.samples = []
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
 
-    def _run(self):
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = get(self._h)
+        bits = (0x8, 0x40, 0x20, 0x4)   # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        return [str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for b in bits]
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                              "--format=csv,noheader,nounits"], capture_output=True,
+                             text=True, timeout=5).stdout.strip()
+        return [x.strip() for x in out.split(",")] if out else None
+
+    def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                s = self._sample_nvml() if self._nvml else self._sample_smi()
+                if s:
+                    self.samples.append(s)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02 if self._nvml else 0.1)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -108,127 +145,170 @@ def host_threads():
 
 
 def oracle_step(O, s, nthreads):
-    """One full step of the CPU oracle; returns (pairs, contacts, seconds, per-stage seconds)."""
+    """One full step of the CPU oracle; returns (pairs, contacts, epa runs, seconds, per-stage seconds)."""
     t0 = time.perf_counter()
     rc, bb = O.refit(s.xf, s.shapes, s.hull, nthreads=nthreads)
     t1 = time.perf_counter()
     pairs = O.broadphase(bb, s.world_id, nthreads=nthreads, cap=max(1024, 8 * s.n))
     t2 = time.perf_counter()
-    con, _, _ = O.narrowphase(s.xf, s.shapes, pairs, s.hull, nthreads=nthreads)
+    con, _, nst = O.narrowphase(s.xf, s.shapes, pairs, s.hull, nthreads=nthreads)
     t3 = time.perf_counter()
-    return len(pairs), len(con), t3 - t0, (t1 - t0, t2 - t1, t3 - t2)
+    return len(pairs), len(con), int(nst.numPenetrating), t3 - t0, (t1 - t0, t2 - t1, t3 - t2)
 
 
 def run_reference(args):
-    """--impl reference: the CPU oracle timed on the host cores (rank 0 only)."""
+    """--impl reference: the CPU oracle timed on the host cores (rank 0 only), full-size workload."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import axcd
     import oracle_lib as O
     nthreads = host_threads()
-    scale = {"headline": 0.25, "C2": 0.1, "C1": 1.0, "C3": 0.25, "C4": 0.015}[args.workload]
-    s = axcd.config_scene(args.workload, scale=scale)
-    for _ in range(args.warmup):
+    workload = args.workload if args.workload != "C4" else "headline"
+    s = axcd.config_scene(workload)
+    # a full step is ~0.3-0.5 s of CPU work on 16 threads: bound the loop so the arm ends within minutes
+    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 20))
+    for _ in range(warm):
         oracle_step(O, s, nthreads)
     tot_units, tot_s = 0, 0.0
-    for _ in range(args.steps):
-        np_, nc, sec, _ = oracle_step(O, s, nthreads)
+    for _ in range(steps):
+        np_, nc, nepa, sec, parts = oracle_step(O, s, nthreads)
         tot_units += np_ + nc
         tot_s += sec
     value = tot_units / tot_s
-    sample = (f"{s.n} bodies of the {args.workload} workload at the same density "
-              f"(scale {scale}), full refit+grid broadphase+GJK/EPA per step")
+    sample = (f"{steps} full steps of the same {s.n}-body workload on {nthreads} host threads "
+              f"(last step: refit {parts[0]:.2f}s, grid broadphase {parts[1]:.2f}s, narrowphase {parts[2]:.2f}s)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "bodies_in_sample": int(s.n),
-                   "note": "the upstream snapshot has no collision code; the reference arm is the "
-                           "in-repo CPU oracle (oracle/axref.cpp) on the host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
-                         "sample": sample},
+        "config": make_config(workload, world, s.n, np_, nc, nepa),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
+                         "steps_timed": steps},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "the upstream snapshot has no collision code; the reference arm is the in-repo CPU oracle "
+                "(oracle/axref.cpp) on the host cores; one scene on rank 0 at every N",
     }
     print(json.dumps(line))
 
 
-def run_slab(args):
-    """--workload C4: one scene split into x-slabs, one slab per rank; ghosts travel over NCCL
-    (axcd/sharding.py SlabRank).  Ghost selection, the ownership rule and the orientation by global id all
-    run on the device; the exchange goes through torch.distributed, so this mode is
-    timed with a wall clock (barrier + synchronize on both sides), max over ranks; the device time of
-    the collision step alone is reported next to it."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import axcd
-    from axcd import sharding
+# ------------------------------------------------------------------------------------------------------
+# measurement helpers (our arm)
+# ------------------------------------------------------------------------------------------------------
+class Flusher:
+    """L2 flush between timed steps: write a 256 MiB buffer (> 126 MB L2), then read another 256 MiB, so the
+    cache is cold AND clean when the step starts.  The write alone leaves ~126 MB of the flush buffer dirty in
+    L2 and the first kernels of the step pay for its write-back (a cost of the benchmark, not of the path)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    s = axcd.config_scene("C4", scale=args.scale)
-    edges = sharding.plan_slabs(s.xf[:, 0], world)
-    mine = np.nonzero(sharding.owner_of(s.xf[:, 0], edges) == rank)[0]
-    owned = sharding._subset(s, mine)
-    gid = mine.astype(np.uint32)
-    dev = f"cuda:{local}"
-    rk = sharding.SlabRank(owned, gid, edges, rank, world, device=local)
-    d = dist if world > 1 else None
+    def __init__(self, torch, stream):
+        self.torch, self.stream = torch, stream
+        self.wr = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        self.rd = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def __call__(self, mode="write+read"):
+        with self.torch.cuda.stream(self.stream):
+            self.wr.fill_(1)
+            if mode == "write+read":
+                self.rd.sum()
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        st = rk.step_device(d)
-    steps = max(1, min(args.steps, 20))
-    barrier()
-    t0 = time.perf_counter()
-    units = 0
-    dev_ms = 0.0
+
+def time_fused_steps(torch, w, stream, flush, steps, warmup):
+    """`steps` fused steps (axcd_step_async = one graph launch once stable), each between two CUDA events on
+    the context stream with an L2 flush before it.  Returns (sum of ms, last stats)."""
+    for _ in range(warmup):
+        st = w.step()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush()
+        ev[i][0].record(stream)
+        w.step_async()
+        ev[i][1].record(stream)
+        st = w.stats()           # synchronises; counts
+    return sum(a.elapsed_time(b) for a, b in ev), st
+
+
+STAGE_KEYS = ("refitMs", "sortMs", "buildMs", "pairMs", "pairSortMs", "gjkMs", "epaMs")
+
+
+def time_staged_steps(w, flush, steps):
+    """Per-stage CUDA-event times through the staged calls (direct launches with events between stages)."""
+    acc = {k: 0.0 for k in STAGE_KEYS}
+    tot = 0.0
     for _ in range(steps):
-        st = rk.step_device(d)
-        units += st.numPairs + st.numContacts
-        dev_ms += st.totalMs
-    barrier()
-    sec = time.perf_counter() - t0
-    gp, gc = np.zeros(st.numPairs), np.zeros(st.numContacts)
-    t = torch.tensor([sec, float(units), float(len(gp)), float(len(gc))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        sec, units, npairs, ncon = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
+        flush()
+        w.update()               # Broadphase::update(): refit + broadphase
+        w.detect_collisions()    # Narrowphase::detectCollisions()
+        st = w.stats()
+        for k in acc:
+            acc[k] += getattr(st, k)
+        tot += st.totalMs
+    return {k: v / steps for k, v in acc.items()}, tot / steps, st
+
+
+def stage_table(avg, st, hbm_peak, fp32_peak, generic_pairs):
+    """Per-stage roofline rows.  Algorithmic bytes / flops per stage as stated in DESIGN.md section 2."""
+    n, npairs, ncon, nepa = st.numBodies, st.numPairs, st.numContacts, st.numPenetrating
+    bits_n = max(1, (max(n, 2) - 1).bit_length())          # as bitsFor() in csrc/axcd_api.cu
+    key_bits = 3 * max(1, min(10, (bits_n + 2) // 3 + 1))   # Morton bits per axis chosen from N
+    passes = (key_bits + 7) // 8
+    info = {
+        "refitMs": ("refitTmaKernel", "hbm", n * 80),
+        "sortMs": ("mortonKernel + onesweep radix sort (%d passes)" % passes, "hbm", n * 32 + n * (16 * passes + 4)),
+        "buildMs": ("leaf gather + range tree + Karras topology/fit (32-byte nodes)", "hbm", n * (24 + 32) + n * 64 + n * 32),
+        "pairMs": ("findPairsKernel (LBVH traversal)", "hbm", n * 32 + npairs * 8),
+        "pairSortMs": ("pair counting sort (scan + scatter + segment sort)", "hbm", n * 12 + npairs * (8 + 4 + 4 + 8)),
+        "epaMs": ("epaKernel (+fallback)", "fp32", nepa * EPA_FLOP_PER_PAIR),
+    }
+    if generic_pairs > 0.05 * max(1, npairs):
+        info["gjkMs"] = ("classify + closedFormKernel + gjkKernel + slotKernel", "fp32", generic_pairs * GJK_FLOP_PER_PAIR)
     else:
-        npairs, ncon = float(len(gp)), float(len(gc))
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": units / sec, "unit": UNIT, "n_gpus": world, "steps": steps,
-            "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1e3 * sec / steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS["C4"], "bodies_total": int(s.n), "scale": args.scale,
-                       "candidate_pairs": int(npairs), "contacts": int(ncon),
-                       "parallelism": f"{world} x-slabs, ghost bodies exchanged point-to-point over NCCL, "
-                                      "x* ownership rule for de-duplication",
-                       "device_ms_per_step_rank0": dev_ms / steps,
-                       "note": "wall-clock per step = refit + device-side ghost selection + NCCL exchange of "
-                               "the ghost records + refit/broadphase/narrowphase; device_ms is the "
-                               "CUDA-event time of the last three on rank 0"},
-            "gpu_launches": None}))
-    if world > 1:
-        dist.destroy_process_group()
+        info["gjkMs"] = ("classify + closedFormKernel (sphere / box closed forms, box-box SAT) + slotKernel", "hbm",
+                         npairs * (8 + 4 + 2 * 56 + 1 + 1) + ncon * 80)
+    rows = []
+    for k, ms in avg.items():
+        name, bound, work = info[k]
+        row = {"stage": k[:-2], "kernels": name, "ms": round(ms, 4), "bound": bound}
+        if bound == "hbm":
+            gbs = work / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            row.update({"algorithmic_bytes": int(work), "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)})
+        else:
+            tf = work / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            row.update({"algorithmic_flops": int(work), "achieved_tflops": round(tf, 3),
+                        "frac_of_fp32_peak": round(tf / fp32_peak, 4) if fp32_peak else None})
+        rows.append(row)
+    return rows, info
+
+
+def roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, workload):
+    dom = max(avg, key=avg.get)
+    name, bound, work = info[dom]
+    row = next(r for r in rows if r["stage"] == dom[:-2])
+    if bound == "hbm":
+        ach, peak, unit = row["achieved_gbs"], hbm_peak, "GB/s"
+        src = peak_src
+    else:
+        ach, peak, unit = row["achieved_tflops"], fp32_peak, "TFLOP/s"
+        src = "measured in this run: FMA-chain kernel, 8 chains per thread, 2048 threads per SM (axcd_test_fp32_peak)"
+    # DRAM traffic of the dominant kernel per launch from this round's `ncu --set full` capture of the same
+    # workload — used only while the captured kernel time still matches the live one (else null: stale)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        ent = tj.get(workload, {}).get(dom[:-2])
+        if ent and abs(ent["ncu_kernel_ms"] - avg[dom]) <= 0.25 * avg[dom]:
+            traffic = ent["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return {"kernel": name, "bound": bound, "achieved": ach, "peak": round(peak, 2) if peak else None, "unit": unit,
+            "frac": round(ach / peak, 4) if peak else None, "traffic": traffic, "peak_source": src,
+            "launch_ms": round(avg[dom], 4),
+            "note": "dominant stage of the step by CUDA-event time through the staged calls; algorithmic work per "
+                    "DESIGN.md section 2; every stage's own row is in `stages`"}
 
 
 def measure_next_rows(w, s, stream, hbm_peak, device):
@@ -238,7 +318,6 @@ def measure_next_rows(w, s, stream, hbm_peak, device):
     import torch
     import axcd
     out = {}
-    # rank 2: contact manifolds of the last step (device time, CUDA events on the context stream)
     reps = 5
     ms = 0.0
     w.step()
@@ -257,7 +336,6 @@ def measure_next_rows(w, s, stream, hbm_peak, device):
     out["manifolds"] = {"ms": round(ms, 4), "contacts": int(st.numContacts), "contact_points": int(st.contactPointCount),
                         "algorithmic_bytes": int(nbytes), "achieved_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
                         "frac_of_hbm_peak": round(nbytes / (ms * 1e-3) / 1e9 / hbm_peak, 4)}
-    # rank 4: scene queries through the blocking C ABI calls (host buffers in and out)
     rng = np.random.default_rng(0)
     nq = 1 << 18
     L = float(s.xf[:, :3].max())
@@ -287,7 +365,6 @@ def measure_next_rows(w, s, stream, hbm_peak, device):
                       "mrays_per_s_e2e": round(nq / ray_s / 1e6, 2)}
     out["aabb_query"] = {"queries": nq, "hits": int(len(qh)), "mqueries_per_s_e2e": round(nq / q_s / 1e6, 2),
                          "first_call_ms": round(1e3 * (t2 - t1), 3)}
-    # rank 3: temporal coherence — the same scene with fat boxes; a step in which no body left its fat box
     wc = axcd.CollisionWorld.for_scene(s, device=device, stream=stream.cuda_stream, aabbMargin=0.05,
                                        flags=axcd.FLAG_TEMPORAL_COHERENCE, pairs_per_body=12)
     full = wc.step()
@@ -303,10 +380,106 @@ def measure_next_rows(w, s, stream, hbm_peak, device):
     return out
 
 
-def run_ours(args):
-    if args.workload == "C4":
-        return run_slab(args)
+def generic_pairs_of(scene, st):
+    """Pairs that run GJK: those with a hull or capsule on either side (estimated from the shape mix: the
+    bench scenes place shapes independently of position)."""
     import numpy as np
+    t = scene.shapes["type"]
+    frac = float(np.mean((t == 2) | (t == 4)))
+    return st.numPairs * (1.0 - (1.0 - frac) ** 2)
+
+
+def measure_side_workload(torch, axcd, scene, flags, stream, flush, device, hbm_peak, peak_src, fp32_peak, workload,
+                          steps, generic_pairs_fn):
+    """A second workload (or the same one under other flags) measured beside the headline on rank 0."""
+    w = axcd.CollisionWorld.for_scene(scene, device=device, stream=stream.cuda_stream, flags=flags)
+    tot, st = time_fused_steps(torch, w, stream, flush, steps, 3)
+    avg, staged_total, st2 = time_staged_steps(w, flush, min(steps, 10))
+    rows, info = stage_table(avg, st2, hbm_peak, fp32_peak, int(generic_pairs_fn(scene, st)))
+    out = {"workload": WORKLOADS[workload], "flags": int(flags), "ms_per_step": round(tot / steps, 4),
+           "pairs_per_s": (st.numPairs + st.numContacts) / (tot / steps * 1e-3),
+           "candidate_pairs": int(st.numPairs), "contacts": int(st.numContacts), "epa_runs": int(st.numPenetrating),
+           "graph_launched": int(st.graphLaunched), "ms_per_step_staged_calls": round(staged_total, 4),
+           "stages": rows, "roofline": roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, workload)}
+    w.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# multi-GPU configurations (N > 1)
+# ------------------------------------------------------------------------------------------------------
+def allreduce(torch, dist, vals, op):
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=op)
+    return [float(x) for x in t]
+
+
+def measure_c3(torch, dist, axcd, rank, world, local, stream, flush, steps):
+    """Config C3: 4096 x 256-body worlds, worlds [r*W/R, (r+1)*W/R) on rank r, no collective on the data path."""
+    from axcd import sharding
+    s, _ = sharding.shard_worlds(axcd.config_scene("C3"), rank, world)
+    w = axcd.CollisionWorld.for_scene(s, device=local, stream=stream.cuda_stream)
+    for _ in range(3):
+        w.step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    tot, st = time_fused_steps(torch, w, stream, flush, steps, 0)
+    dist.barrier()
+    torch.cuda.synchronize()
+    units = float((st.numPairs + st.numContacts) * steps)
+    tmax = allreduce(torch, dist, [tot], dist.ReduceOp.MAX)[0]
+    usum, psum, csum = allreduce(torch, dist, [units, float(st.numPairs), float(st.numContacts)], dist.ReduceOp.SUM)
+    w.close()
+    return {"workload": WORKLOADS["C3"], "scaling": "strong", "worlds_per_gpu": int(s.num_worlds),
+            "bodies_per_gpu": int(st.numBodies), "ms_per_step": tmax / steps, "pairs_per_s": usum / (tmax * 1e-3),
+            "candidate_pairs": int(psum), "contacts": int(csum), "steps": steps, "graph_launched": int(st.graphLaunched),
+            "timing": "CUDA events around the fused step on each rank, L2 flushed, max over ranks"}
+
+
+def measure_c4(torch, dist, axcd, rank, world, local, scale, steps):
+    """Config C4: one 16M-body scene in x-slabs, one slab per rank; the ghost exchange runs inside libaxcd.so over
+    NCCL (axcd_slab_step).  Wall-clock per step (barrier + synchronize on both sides, max over ranks) with the
+    device times of the exchange and of the collision step beside it."""
+    import numpy as np
+    from axcd import sharding
+    s = axcd.config_scene("C4", scale=scale)
+    edges = sharding.plan_slabs(s.xf[:, 0], world)
+    mine = np.nonzero(sharding.owner_of(s.xf[:, 0], edges) == rank)[0]
+    owned = sharding._subset(s, mine)
+    rk = sharding.SlabRank(owned, mine.astype(np.uint32), edges, rank, world, device=local)
+    del s
+    rk.init_native(dist)
+    for _ in range(3):
+        st = rk.step_native()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_ms = xch_ms = 0.0
+    for _ in range(steps):
+        st = rk.step_native()
+        dev_ms += st.totalMs
+        xch_ms += st.exchangeMs
+    dist.barrier()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    smax, dmax, xmax = allreduce(torch, dist, [sec, dev_ms, xch_ms], dist.ReduceOp.MAX)
+    psum, csum, gsum = allreduce(torch, dist, [float(st.numPairs), float(st.numContacts), float(st.ghostBodies)],
+                                 dist.ReduceOp.SUM)
+    out = {"workload": WORKLOADS["C4"], "scaling": "strong", "scale": scale, "bodies_total": int(round(16_000_000 * scale)),
+           "bodies_per_gpu_owned": int(owned.n), "ghost_bodies_total": int(gsum),
+           "ms_per_step_wall": 1e3 * smax / steps, "ms_per_step_device_collision": dmax / steps,
+           "ms_per_step_device_exchange": xmax / steps,
+           "pairs_per_s": (psum + csum) * steps / smax, "candidate_pairs": int(psum), "contacts": int(csum),
+           "steps": steps, "graph_launched": int(st.graphLaunched),
+           "parallelism": f"{world} x-slabs; ghost records selected on the device, sizes by ncclAllGather, records by "
+                          "grouped ncclSend/ncclRecv inside libaxcd.so; x* ownership rule in the traversal kernel",
+           "timing": "wall clock over the timed steps between barrier+synchronize pairs, max over ranks; device times "
+                     "are CUDA events on each rank's stream (max over ranks)"}
+    rk.close()
+    return out
+
+
+def run_ours(args):
     import torch
     import torch.distributed as dist
     import axcd
@@ -322,6 +495,27 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    flush = Flusher(torch, stream)
+    hbm_peak, peak_src = load_peaks()
+
+    if args.workload == "C4":   # stand-alone slab run (the default N>1 run reports it as the `c4` key)
+        if world < 2:
+            raise SystemExit("--workload C4 needs torchrun with at least 2 ranks")
+        c4 = measure_c4(torch, dist, axcd, rank, world, local, args.scale, max(1, min(args.steps, 20)))
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": c4["pairs_per_s"], "unit": UNIT, "n_gpus": world,
+                              "steps": c4["steps"], "warmup": 3, "ms_per_step": c4["ms_per_step_wall"],
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                              "data": "synthetic", "config": {"workload": WORKLOADS["C4"]}, "c4": c4, "gpu_launches": None}))
+        dist.destroy_process_group()
+        return
+
     # ---- workload ---------------------------------------------------------------------------------
     scaling = "weak"
     if args.workload == "headline" and world > 1:
@@ -332,69 +526,36 @@ def run_ours(args):
         scaling = "strong"
     else:
         s = axcd.config_scene(args.workload)
-    stream = torch.cuda.Stream()
     w = axcd.CollisionWorld.for_scene(s, device=local, stream=stream.cuda_stream, flags=args.flags)
-    hbm_peak, peak_src = load_peaks()
 
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    flush_rd = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
-
-    # L2 flush between timed steps: write a 256 MiB buffer (> 126 MB L2), then read another 256 MiB, so the
-    # cache is cold AND clean when the step starts.  The write alone leaves ~126 MB of the flush buffer
-    # dirty in L2 and the first kernels of the step pay for its write-back (a cost of the benchmark, not
-    # of the path); BENCH_FLUSH=write selects that mode, and the refit stage is reported under both.
-    flush_mode = os.environ.get("BENCH_FLUSH", "write+read")
-
-    def flush_l2(mode=None):
-        with torch.cuda.stream(stream):
-            flush.fill_(1)
-            if (mode or flush_mode) == "write+read":
-                flush_rd.sum()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing (`value`) ------------------------------------------------------------
+    # ---- device-resident timing (`value`): the fused step, one CUDA graph launch per step ----------------
     for _ in range(max(args.warmup, 3)):
         st = w.step()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    stage_ms = {k: 0.0 for k in ("refitMs", "sortMs", "buildMs", "pairMs", "pairSortMs", "gjkMs", "epaMs")}
-    for i in range(args.steps):
-        flush_l2()
-        ev[i][0].record(stream)
-        w.update()               # Broadphase::update(): refit + broadphase
-        w.detect_collisions()    # Narrowphase::detectCollisions()
-        ev[i][1].record(stream)
-        st = w.stats()           # synchronises; counts + per-stage CUDA-event times
-        for k in stage_ms:
-            stage_ms[k] += getattr(st, k)
+    if sampler:
+        sampler.start()
+    total_ms, st = time_fused_steps(torch, w, stream, flush, args.steps, 0)
     barrier()
-    clocks = sampler.stop()
-    # the refit stage again under the write-only flush (dirty L2), for the record
+    clocks = sampler.stop() if sampler else None
+    graph_launched = int(st.graphLaunched)
+    units = float((st.numPairs + st.numContacts) * args.steps)
+    if world > 1:
+        total_ms = allreduce(torch, dist, [total_ms], dist.ReduceOp.MAX)[0]
+        units = allreduce(torch, dist, [units], dist.ReduceOp.SUM)[0]
+    ms_per_step = total_ms / args.steps
+    value = units / (total_ms * 1e-3)
+
+    # ---- per-stage times through the staged calls (events between stages, direct launches) ----------------
+    stage_steps = max(3, min(args.steps, 20))
+    avg, staged_total, st_s = time_staged_steps(w, flush, stage_steps)
     refit_dirty = 0.0
-    for _ in range(10):
-        flush_l2("write")
+    for _ in range(10):   # the refit stage again under the write-only flush (dirty L2), for the record
+        flush("write")
         w.update()
         w.detect_collisions()
         refit_dirty += w.stats().refitMs
     refit_dirty /= 10
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    units = (st.numPairs + st.numContacts) * args.steps
-    t = torch.tensor([total_ms, float(units)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, units = float(tmax[0]), float(tsum[1])
-    ms_per_step = total_ms / args.steps
-    value = units / (total_ms * 1e-3)
 
     # ---- end-to-end through the public API with host buffers (`e2e`) ---------------------------------
     h_xf = torch.from_numpy(s.xf.copy()).pin_memory()
@@ -416,104 +577,95 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([e2e_ms, float(e2e_units)], dtype=torch.float64, device="cuda")
+    e2e_units = float(e2e_units)
     if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        e2e_ms, e2e_units = float(tmax[0]), float(tsum[1])
+        e2e_ms = allreduce(torch, dist, [e2e_ms], dist.ReduceOp.MAX)[0]
+        e2e_units = allreduce(torch, dist, [e2e_units], dist.ReduceOp.SUM)[0]
     e2e_value = e2e_units / (e2e_ms * 1e-3)
     h2d = int(s.n) * 40
     d2h = int(st2.numContacts) * 40 + 4 + 128   # contacts + count + stats block
 
+    # ---- roofline: measured FP32 peak, per-stage table, dominant kernel -----------------------------------
+    fp32_peak = w.fp32_peak() if rank == 0 else None
+    rows, info = stage_table(avg, st_s, hbm_peak, fp32_peak or 1.0, int(generic_pairs_of(s, st_s)))
+    for r in rows:
+        if r["stage"] == "refit" and refit_dirty > 0:
+            r["ms_write_only_flush"] = round(refit_dirty, 4)
+            r["frac_of_hbm_peak_write_only_flush"] = round(r["algorithmic_bytes"] / (refit_dirty * 1e-3) / 1e9 / hbm_peak, 4)
+    roofline = roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, args.workload)
+
+    single = rank == 0 and world == 1 and args.workload == "headline" and args.flags == 0
     # ---- the SURVEY 8(f) "next" rows on the same scene (rank 0, N=1): manifolds, scene queries, coherence ---
-    next_rows = None
-    if rank == 0 and world == 1 and args.workload == "headline" and not args.no_next_rows:
-        next_rows = measure_next_rows(w, s, stream, hbm_peak, local)
+    next_rows = measure_next_rows(w, s, stream, hbm_peak, local) if single and not args.no_next_rows else None
+    n_launch = int(st.kernelLaunches)
+    w.close()
 
-    # ---- roofline of the dominant kernel + per-stage table -------------------------------------------
-    # Algorithmic bytes per stage: what the stage must read and write once.
-    n, npairs, ncon, nepa = st.numBodies, st.numPairs, st.numContacts, st.numPenetrating
-    avg = {k: v / args.steps for k, v in stage_ms.items()}
-    bits_n = max(1, (max(n, 2) - 1).bit_length())          # as bitsFor() in csrc/axcd_api.cu
-    key_bits = 3 * max(1, min(10, (bits_n + 2) // 3 + 1))   # Morton bits per axis chosen from N
-    passes = (key_bits + 7) // 8
-    stage_info = {
-        "refitMs": ("refitTmaKernel", n * 80),
-        "sortMs": ("mortonKernel + onesweep radix sort (%d passes)" % passes, n * 32 + n * (16 * passes + 4)),
-        "buildMs": ("leaf gather + range tree + Karras topology/fit (32-byte nodes)", n * (24 + 32) + n * 64 + n * 32),
-        "pairMs": ("findPairsKernel (LBVH traversal)", n * 32 + npairs * 8),
-        "pairSortMs": ("pair counting sort (scan + scatter + segment sort)", n * 12 + npairs * (8 + 4 + 4 + 8)),
-        "gjkMs": ("gjkKernel + slotKernel", npairs * (8 + 2 * 56 + 1 + 1) + (ncon - nepa) * 84 + nepa * 80),
-        "epaMs": ("epaKernel (+fallback)", nepa * (80 + 2 * 56 + 40)),
-    }
-    stages = []
-    for k, ms in avg.items():
-        name, nbytes = stage_info[k]
-        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        stages.append({"stage": k[:-2], "kernels": name, "ms": round(ms, 4), "algorithmic_bytes": int(nbytes),
-                       "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)})
-        if k == "refitMs" and refit_dirty > 0:
-            stages[-1]["ms_write_only_flush"] = round(refit_dirty, 4)
-            stages[-1]["frac_of_hbm_peak_write_only_flush"] = round(nbytes / (refit_dirty * 1e-3) / 1e9 / hbm_peak, 4)
-    dom = max(avg, key=avg.get)
-    dom_name, dom_bytes = stage_info[dom]
-    dom_gbs = dom_bytes / (avg[dom] * 1e-3) / 1e9
-    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of
-    # this same workload (profiles/); null for other workloads
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        key = {"epaMs": "epaKernel", "gjkMs": "gjkKernel", "pairMs": "findPairsKernel", "refitMs": "refitTmaKernel"}.get(dom)
-        if args.workload == "headline" and key:
-            traffic = tj.get(key + "_dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"kernel": dom_name, "bound": "hbm", "achieved": round(dom_gbs, 1), "peak": hbm_peak,
-                "unit": "GB/s", "frac": round(dom_gbs / hbm_peak, 4), "traffic": traffic,
-                "peak_source": peak_src, "launch_ms": round(avg[dom], 4),
-                "note": "the dominant kernel (EPA/GJK) is FP32-CUDA-core issue/latency bound, not HBM "
-                        "bound: its HBM fraction is reported because the contract asks for one; the "
-                        "HBM-bound stages (refit, sort) are in `stages`; ncu evidence in profiles/"}
+    # ---- beside the headline (rank 0, N=1): box-box through GJK/EPA, and the hull mix C2 --------------------
+    generic = c2 = None
+    if single and not args.no_side_workloads:
+        side_steps = max(3, min(args.steps, 20))
+        generic = measure_side_workload(torch, axcd, s, axcd.FLAG_BOXBOX_GJK_EPA, stream, flush, local, hbm_peak, peak_src,
+                                        fp32_peak, "headline", side_steps,
+                                        lambda sc, q: q.numPairs * 0.25)   # box-box pairs of a 50/50 mix
+        c2 = measure_side_workload(torch, axcd, axcd.config_scene("C2"), 0, stream, flush, local, hbm_peak, peak_src,
+                                   fp32_peak, "C2", side_steps, generic_pairs_of)
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample ----------------------
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle, one full step of the same workload ----------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.flags == 0:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O
         nthreads = host_threads()
-        np_, nc_, sec, parts = oracle_step(O, s, nthreads)
+        np_, nc_, _, sec, parts = oracle_step(O, s, nthreads)
         cpu = {"value": (np_ + nc_) / sec, "unit": UNIT, "cores": nthreads, "kind": "port",
                "sample": f"one full step of the same {s.n}-body workload on {nthreads} host threads "
-                         f"(refit {parts[0]:.2f}s, grid broadphase {parts[1]:.2f}s, GJK/EPA {parts[2]:.2f}s)",
+                         f"(refit {parts[0]:.2f}s, grid broadphase {parts[1]:.2f}s, narrowphase {parts[2]:.2f}s)",
                "ms_per_step": 1e3 * sec,
-               "pairs_match_gpu": bool(np_ == npairs and nc_ == ncon)}
+               "pairs_match_gpu": bool(np_ == st.numPairs and nc_ == st.numContacts)}
+
+    # ---- the multi-GPU configurations BASELINE.json names, in the same invocation (N > 1) ------------------
+    c3 = c4 = None
+    if world > 1 and args.workload == "headline" and not args.no_multi:
+        ms_steps = max(3, min(args.steps, 20))
+        try:
+            c3 = measure_c3(torch, dist, axcd, rank, world, local, stream, flush, ms_steps)
+        except Exception as e:   # keep the headline line even if a side configuration fails
+            c3 = {"error": repr(e)[:300]}
+        try:
+            c4 = measure_c4(torch, dist, axcd, rank, world, local, args.scale_c4, ms_steps)
+        except Exception as e:
+            c4 = {"error": repr(e)[:300]}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "bodies_per_gpu": int(n),
-                       "candidate_pairs": int(npairs), "contacts": int(ncon),
-                       "epa_runs": int(st.numPenetrating),
-                       "l2": ("256 MiB written, then 256 MiB read, between timed steps: L2 cold and clean"
-                              if flush_mode == "write+read" else
-                              "256 MiB buffer written between timed steps (L2 flush; leaves dirty lines)"),
-                       "parallelism": "one independent scene per rank, no collective" if world > 1 else "single GPU"},
+            "config": make_config(args.workload, world, st.numBodies, st.numPairs, st.numContacts, st.numPenetrating),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps},
-            "gpu_launches": int(st.kernelLaunches) * args.steps,
-            "clocks": clocks, "roofline": roofline, "stages": stages,
+            "gpu_launches": n_launch * args.steps,
+            "step_launch": {"graph_launched": graph_launched, "kernels_per_step": n_launch,
+                            "ms_per_step_staged_calls": round(staged_total, 4),
+                            "note": "value / ms_per_step time the fused step as axcd_step runs it: one CUDA graph "
+                                    "launch; the stage table uses the staged calls (direct launches, events between stages)"},
+            "clocks": clocks, "roofline": roofline, "stages": rows,
+            "fp32_peak_tflops": round(fp32_peak, 2) if fp32_peak else None,
             "target_ms_per_step": 2.0,
         }
         if cpu:
             line["cpu_baseline"] = cpu
         if next_rows:
             line["next_rows"] = next_rows
+        if generic:
+            line["boxbox_through_gjk_epa"] = generic
+        if c2:
+            line["c2"] = c2
+        if c3:
+            line["c3"] = c3
+        if c4:
+            line["c4"] = c4
         print(json.dumps(line))
-    w.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -527,7 +679,10 @@ def main():
     ap.add_argument("--workload", default="headline", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the manifold / query / coherence timings")
-    ap.add_argument("--scale", type=float, default=0.125, help="C4 only: fraction of the 16M bodies")
+    ap.add_argument("--no-side-workloads", action="store_true", help="skip the GJK/EPA box-box and C2 lines beside the headline")
+    ap.add_argument("--no-multi", action="store_true", help="N>1: skip the c3 / c4 configurations")
+    ap.add_argument("--scale", type=float, default=0.125, help="--workload C4 only: fraction of the 16M bodies")
+    ap.add_argument("--scale-c4", type=float, default=1.0, help="N>1 default run: fraction of the 16M bodies for the c4 key")
     ap.add_argument("--flags", type=int, default=0, help="AXCD_FLAG_* bits for the context (8 = box-box through GJK/EPA)")
     args = ap.parse_args()
     if args.impl == "reference":

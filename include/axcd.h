@@ -119,7 +119,11 @@ enum {
      * axis separates, depth = the smallest overlap, normal = that axis — what EPA converges to).  This
      * flag sends them through the generic GJK + EPA path instead, like hulls and capsules (A/B
      * measurements, and tests that validate one against the other).                               */
-    AXCD_FLAG_BOXBOX_GJK_EPA = 8u
+    AXCD_FLAG_BOXBOX_GJK_EPA = 8u,
+    /* axcd_step / axcd_step_async normally replay a CUDA graph of the whole step once the launch
+     * configuration has been stable for a step.  This flag (or AXCD_NO_GRAPH=1 in the environment) keeps
+     * them on direct launches.                                                                       */
+    AXCD_FLAG_NO_GRAPH = 16u
 };
 
 typedef struct AxcdStats {
@@ -136,11 +140,18 @@ typedef struct AxcdStats {
     uint32_t movedBodies;       /* AXCD_FLAG_TEMPORAL_COHERENCE: bodies whose fat box was rebuilt by
                                    the last refit (numBodies without the flag)                   */
     uint32_t broadphaseSkipped; /* 1 if the last axcd_broadphase reused the cached candidate list */
+    uint32_t graphLaunched;     /* 1 if the last fused step was one CUDA graph launch: totalMs is then the
+                                   only timing (per-stage times need the staged calls)               */
+    uint32_t ghostBodies;       /* axcd_slab_step: ghost bodies received from the other ranks this step  */
+    float exchangeMs;           /* axcd_slab_step: owned refit + ghost selection + NCCL handshake and exchange
+                                   + unpack, CUDA events on the context stream (includes the one host read) */
 } AxcdStats;
 
 typedef struct AxcdContext AxcdContext; /* opaque */
 
 AXCD_API void axcd_default_config(AxcdConfig* cfg);
+/* Number of CUDA devices visible to the process (0 without a driver / device): valid deviceOrdinal range. */
+AXCD_API int32_t axcd_device_count(void);
 AXCD_API int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out);
 AXCD_API void axcd_destroy(AxcdContext* ctx);
 
@@ -155,6 +166,11 @@ AXCD_API int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint
  * stride (>= 40).  n must equal the n of axcd_set_shapes.  Host -> device copy.                */
 AXCD_API int32_t axcd_set_transforms(AxcdContext* ctx, const void* transforms, uint32_t n,
                                      uint32_t strideBytes);
+/* Buffer lifetime: the copy is enqueued on the context stream and the call returns.  From pageable memory
+ * the driver stages the data before returning; from page-locked memory (axcd_pin_host_buffer, recommended
+ * for the per-step buffer) the DMA is truly asynchronous, so the caller must leave the buffer untouched
+ * until the next blocking call on this context (axcd_step, axcd_get_stats, any axcd_get_*) has returned.
+ * The same rule holds for axcd_set_ghosts and axcd_set_body_keys.                                    */
 
 /* The three stages (asynchronous on the context stream) and the fused step (synchronises and
  * fills stats).  Each stage runs once per refit, in order: axcd_broadphase needs an axcd_refit
@@ -164,6 +180,13 @@ AXCD_API int32_t axcd_refit(AxcdContext* ctx);
 AXCD_API int32_t axcd_broadphase(AxcdContext* ctx);
 AXCD_API int32_t axcd_narrowphase(AxcdContext* ctx);
 AXCD_API int32_t axcd_step(AxcdContext* ctx, AxcdStats* outStats);
+/* The fused step without the final synchronisation: refit + broadphase + narrowphase are enqueued on the
+ * context stream (as ONE CUDA graph launch once the launch configuration — body count, filters, slab rule
+ * — has been stable for a step, otherwise as the individual kernels) and the call returns.  Counts and
+ * results are fetched with axcd_get_stats / axcd_get_* as after axcd_step.  A graph-launched step reports
+ * totalMs only; broadphaseTime / narrowphaseTime and the per-stage times are filled by the staged calls
+ * axcd_refit / axcd_broadphase / axcd_narrowphase, which always launch directly.                    */
+AXCD_API int32_t axcd_step_async(AxcdContext* ctx);
 /* Waits for the stream, then reports counts/timings of the last stages run.  Returns 601 if a
  * capacity was exceeded (requiredPairs / requiredContacts say by how much).                    */
 AXCD_API int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* outStats);
@@ -248,11 +271,15 @@ AXCD_API int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32
 /* Collision filtering, gui::FilterInfo semantics (include/axiom/gui/body_inspector.hpp:38-42):
  * two bodies with the same non-zero groupIndex collide iff it is positive; otherwise both
  * (maskBits & other.categoryBits) must be non-zero.  Applied when candidate pairs are emitted.
- * filters = n records, or NULL to switch filtering off (the default).                           */
+ * AxcdFilter has the memory layout of gui::FilterInfo (uint32, uint32, int16 + 2 bytes of padding = 12
+ * bytes), so an engine-side FilterInfo array passes through unchanged.  filters = one record per body
+ * (n == the body count of axcd_set_shapes, 600 otherwise), or NULL to switch filtering off (the default;
+ * axcd_set_shapes also switches it off).  Not available in x-slab mode (ghost records carry no filter).  */
 typedef struct AxcdFilter {
     uint32_t categoryBits;
     uint32_t maskBits;
-    int32_t groupIndex;
+    int16_t groupIndex;
+    uint16_t reserved_;      /* padding of gui::FilterInfo; ignored */
 } AxcdFilter;
 AXCD_API int32_t axcd_set_filters(AxcdContext* ctx, const AxcdFilter* filters, uint32_t n);
 
@@ -260,7 +287,7 @@ AXCD_API int32_t axcd_set_filters(AxcdContext* ctx, const AxcdFilter* filters, u
  * gui::SleepInfo, include/axiom/gui/body_inspector.hpp:45-51): awake[i] == 0 marks body i asleep; a
  * pair of two sleeping bodies is not a candidate (applied where candidate pairs are emitted).  NULL
  * switches the rule off (all awake, the default).                                                 */
-AXCD_API int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t n);
+AXCD_API int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t n);   /* n == owned body count */
 
 /* ---- one huge scene across several GPUs: x-slab mode ---------
  * Bodies [0, nOwned) are the ones this rank owns (set with axcd_set_shapes / axcd_set_transforms as
@@ -273,6 +300,8 @@ AXCD_API int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t
 AXCD_API int32_t axcd_set_slab(AxcdContext* ctx, float xLo, float xHi, uint32_t enable);
 AXCD_API int32_t axcd_set_body_keys(AxcdContext* ctx, const uint32_t* keys, uint32_t first,
                                     uint32_t count);
+/* Global ids (keys) of the bodies currently held: the owned ones, then this step's ghosts.  Blocking.    */
+AXCD_API int32_t axcd_get_body_keys(AxcdContext* ctx, uint32_t* outKeys, uint32_t cap);
 AXCD_API int32_t axcd_set_ghosts(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts,
                                  const void* transforms40, const AxcdShape* shapes,
                                  const uint32_t* keys);
@@ -288,6 +317,27 @@ AXCD_API int32_t axcd_pack_ghosts(AxcdContext* ctx, const float* edges, uint32_t
                                   uint32_t myRank, void** outDevPtrs, uint32_t* outCounts);
 AXCD_API int32_t axcd_set_ghosts_device(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts,
                                         const void* devRecords);
+
+/* The whole exchange inside the library, over NCCL (ncclAllGather of the per-destination counts, then one
+ * grouped ncclSend / ncclRecv of the ghost records, GPU to GPU): no host staging, no framework in between.
+ * NCCL is bound at run time (dlopen libnccl.so.2): without it these calls return 500, everything else works.
+ *   axcd_nccl_unique_id : rank 0 creates the 128-byte ncclUniqueId; the host broadcasts it by any means
+ *   axcd_slab_init      : every rank, after axcd_set_shapes / axcd_set_transforms / axcd_set_body_keys of its
+ *                         OWNED bodies: creates the communicator on the context's device (collective call),
+ *                         allocates the send / receive buffers (capacity maxBodies - nOwned ghost records) and
+ *                         switches the slab rule on for [edges[rank], edges[rank+1]); edges has numRanks+1 entries
+ *   axcd_slab_init_comm : the same with a communicator the host already owns (ncclComm_t passed as void*)
+ *   axcd_slab_step      : one step of the sharded scene — refit of the owned bodies, device-side ghost
+ *                         selection, size handshake, exchange, append, then the fused step on owned + ghosts.
+ *                         Collective: every rank of the communicator must call it.  _async returns after the
+ *                         handshake's single host read, with the step enqueued.                          */
+AXCD_API int32_t axcd_nccl_unique_id(void* out128);
+AXCD_API int32_t axcd_slab_init(AxcdContext* ctx, const void* uniqueId128, uint32_t rank, uint32_t numRanks,
+                                const float* edges);
+AXCD_API int32_t axcd_slab_init_comm(AxcdContext* ctx, void* ncclComm, uint32_t rank, uint32_t numRanks,
+                                     const float* edges);
+AXCD_API int32_t axcd_slab_step_async(AxcdContext* ctx);
+AXCD_API int32_t axcd_slab_step(AxcdContext* ctx, AxcdStats* outStats);
 
 /* Page-locks (and later releases) a caller-owned host buffer so that the per-step copies — transforms in,
  * contacts / manifolds out — run at full PCIe rate; the engine does not need the CUDA headers for it.

@@ -18,6 +18,7 @@
 
 #include "axcd.h"
 
+#include <cstddef>
 #include <cstdint>
 #include <memory>
 #include <utility>
@@ -28,6 +29,10 @@
 #include "axiom/math/aabb.hpp"
 #include "axiom/math/transform.hpp"
 #define AXIOM_COLLISION_HAS_ENGINE_TYPES 1
+#if __has_include("axiom/gui/body_inspector.hpp") && defined(AXIOM_COLLISION_WITH_GUI_TYPES)
+#include "axiom/gui/body_inspector.hpp"   // gui::FilterInfo (pulls in the GUI headers: opt-in)
+#define AXIOM_COLLISION_HAS_GUI_TYPES 1
+#endif
 #else
 namespace axiom::core {
 enum class ErrorCode : int {   // numeric values of include/axiom/core/error_code.hpp:21-57
@@ -85,6 +90,14 @@ using ContactManifold = AxcdManifold;   // 1..4 DebugContactPoints sharing one n
 using Ray = AxcdRay;
 using RayHit = AxcdRayHit;
 using Sweep = AxcdSweep;
+/// gui::FilterInfo's layout (include/axiom/gui/body_inspector.hpp:38-42): uint32 categoryBits, uint32 maskBits,
+/// int16 groupIndex (+ 2 bytes of padding).  A FilterInfo array can be passed as-is.
+using Filter = AxcdFilter;
+static_assert(sizeof(Filter) == 12, "Filter must have gui::FilterInfo's 12-byte layout");
+#ifdef AXIOM_COLLISION_HAS_GUI_TYPES
+static_assert(sizeof(gui::FilterInfo) == sizeof(Filter) && offsetof(gui::FilterInfo, groupIndex) == offsetof(Filter, groupIndex),
+              "gui::FilterInfo layout changed");
+#endif
 struct BodyPair { std::uint32_t a, b; };
 struct QueryHit { std::uint32_t query, body; };
 
@@ -190,6 +203,50 @@ public:
                                   Sweep* out) {
         return wrap(axcd_ccd_pairs(ctx_, reinterpret_cast<const std::uint32_t*>(pairs), count,
                                    reinterpret_cast<const float*>(displacements), out));
+    }
+    /// The fused step without the final synchronisation (one CUDA graph launch once the launch
+    /// configuration is stable); fetch counts with stats().
+    core::Result<void> stepAsync() { return wrap(axcd_step_async(ctx_)); }
+
+    /// Collision filtering with gui::FilterInfo semantics, one record per body; nullptr switches it off.
+    core::Result<void> setFilters(const Filter* filters, std::uint32_t count) {
+        return wrap(axcd_set_filters(ctx_, filters, count));
+    }
+#ifdef AXIOM_COLLISION_HAS_GUI_TYPES
+    core::Result<void> setFilters(const gui::FilterInfo* filters, std::uint32_t count) {
+        return wrap(axcd_set_filters(ctx_, reinterpret_cast<const Filter*>(filters), count));   // same layout (asserted above)
+    }
+#endif
+    /// Sleeping bodies (debug::DebugRigidBody::isAwake): awake[i] == 0 marks body i asleep; pairs of two
+    /// sleeping bodies are dropped.  nullptr switches the rule off.
+    core::Result<void> setAwake(const std::uint8_t* awake, std::uint32_t count) {
+        return wrap(axcd_set_awake(ctx_, awake, count));
+    }
+
+    /// One huge scene across several GPUs (x-slabs).  Call after setShapes / setTransforms of the OWNED bodies.
+    /// globalIds[i] = id of owned body i in the whole scene; edges has numRanks + 1 entries.  initSlab with
+    /// a unique id creates the NCCL communicator inside the library (collective over all ranks);
+    /// initSlabWithComm takes an ncclComm_t the host already owns.  slabStep is collective as well.
+    static core::Result<void> ncclUniqueId(void* out128) { return wrap(axcd_nccl_unique_id(out128)); }
+    core::Result<void> setBodyKeys(const std::uint32_t* globalIds, std::uint32_t count) {
+        return wrap(axcd_set_body_keys(ctx_, globalIds, 0, count));
+    }
+    core::Result<void> initSlab(const void* ncclUniqueId128, std::uint32_t rank, std::uint32_t numRanks, const float* edges) {
+        return wrap(axcd_slab_init(ctx_, ncclUniqueId128, rank, numRanks, edges));
+    }
+    core::Result<void> initSlabWithComm(void* ncclComm, std::uint32_t rank, std::uint32_t numRanks, const float* edges) {
+        return wrap(axcd_slab_init_comm(ctx_, ncclComm, rank, numRanks, edges));
+    }
+    core::Result<AxcdStats> slabStep() {
+        AxcdStats s{};
+        const std::int32_t rc = axcd_slab_step(ctx_, &s);
+        if (rc != AXCD_OK) return fail<AxcdStats>(rc);
+        return core::Result<AxcdStats>::success(s);
+    }
+    /// Global ids of the bodies currently held (owned, then this step's ghosts): pair / contact indices are
+    /// local; map them through this to report in scene ids.
+    core::Result<void> getBodyKeys(std::uint32_t* out, std::uint32_t capacity) {
+        return wrap(axcd_get_body_keys(ctx_, out, capacity));
     }
     std::uint32_t bodyCount() const noexcept { return bodyCount_; }
 

@@ -1203,6 +1203,7 @@ void buildManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, co
     poly[2] = (fc - eu) - ev;
     poly[3] = (fc + eu) - ev;
     // clip against the reference face's side planes: s * dot(p - cR, ax_w) <= h_w
+    bool over = false;
     for (int side = 0; side < 4 && np > 0; ++side) {
         const int w = (i + 1 + (side >> 1)) % 3;
         const float s = (side & 1) ? -1.0f : 1.0f;
@@ -1215,17 +1216,23 @@ void buildManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, co
             const V3 cur = poly[k];
             const float dcur = dot(cur - R.c, pn) - hw;
             const bool inPrev = dprev <= 0.0f, inCur = dcur <= 0.0f;
+            // never past the 8 slots (sign noise on a degenerate reference face): overflow -> narrowphase point
             if (inPrev != inCur) {
                 const float t = dprev / (dprev - dcur);
-                tmp[nt++] = prev + (cur - prev) * t;
+                if (nt < 8) tmp[nt++] = prev + (cur - prev) * t;
+                else over = true;
             }
-            if (inCur) tmp[nt++] = cur;
+            if (inCur) {
+                if (nt < 8) tmp[nt++] = cur;
+                else over = true;
+            }
             prev = cur;
             dprev = dcur;
         }
         np = nt;
         for (int k = 0; k < np; ++k) poly[k] = tmp[k];
     }
+    if (over) np = 0;
     // keep the vertices on or below the reference face
     V3 pos[8];
     float dep[8];
@@ -1482,6 +1489,13 @@ void sweepCores(const Core& A, Core B, V3 D, const AxrefNarrowCfg& cfgIn, AxrefS
         if (!(approach > 0.0f)) break;               // moving apart or sliding past
         t = t + gap / approach;
         if (!(t <= 1.0f)) break;
+    }
+    if (it == CCD_MAX_ITERS) {
+        // out of iterations while still closing in within the step: the conservative answer is a hit at
+        // the time reached (a "no hit" here would be a tunnelling false negative)
+        out.hit = 1u;
+        out.toi = t;
+        out.nx = nLast.x; out.ny = nLast.y; out.nz = nLast.z;
     }
     out.iterations = (uint32_t)it;
 }

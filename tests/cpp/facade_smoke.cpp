@@ -9,6 +9,13 @@
 
 using namespace axiom;
 
+#ifdef AXIOM_EXPECT_ENGINE_TYPES   // set by the test that compiles this file against the Axiom tree's own headers
+#ifndef AXIOM_COLLISION_HAS_ENGINE_TYPES
+#error "the facade did not pick up axiom/core/result.hpp and axiom/math/transform.hpp"
+#endif
+static_assert(sizeof(math::Transform) == 40 && sizeof(math::AABB) == 24, "engine math types at the boundary");
+#endif
+
 int main() {
     const std::uint32_t n = 1000;   // config C0: seed 1, L = 10, 50/50 boxes and spheres
     AxcdSceneSpec spec{n, 0.5f, 0.5f, 10.0f, 0.25f, 0.5f, 16, 1};
@@ -56,6 +63,21 @@ int main() {
     collision::Ray ray{xf[0].position.x, xf[0].position.y, xf[0].position.z - 50.0f, 0.0f, 0.0f, 1.0f, 100.0f, 0};
     collision::RayHit rh{};
     if (world.rayCast(&ray, 1, &rh).isFailure() || rh.body == 0xffffffffu) return 14;
+    // filters (gui::FilterInfo layout), sleeping flags and the asynchronous fused step
+    std::vector<collision::Filter> filt(n);
+    for (std::uint32_t i = 0; i < n; ++i) filt[i] = collision::Filter{1u, 0xFFFFu, static_cast<std::int16_t>(-1), 0};
+    if (world.setFilters(filt.data(), n).isFailure()) return 15;    // everybody in one negative group: nothing collides
+    if (world.stepAsync().isFailure()) return 16;
+    auto fs = world.stats();
+    if (fs.isFailure() || fs.value().numPairs != 0) return 17;
+    if (world.setFilters(nullptr, 0).isFailure()) return 18;
+    std::vector<std::uint8_t> awake(n, 0);
+    if (world.setAwake(awake.data(), n).isFailure()) return 19;     // everybody asleep: no pair has an awake body
+    auto as = world.step();
+    if (as.isFailure() || as.value().numPairs != 0) return 20;
+    if (world.setAwake(nullptr, 0).isFailure()) return 21;
+    auto again = world.step();
+    if (again.isFailure() || again.value().numPairs != pairs || again.value().numContacts != contacts) return 22;
     std::printf("%u %u %u\n", pairs, contacts, points);
     return 0;
 }

@@ -508,3 +508,60 @@ def test_deep_tree_everything_overlaps():
     hits = w.query_aabbs(np.array([[-1e4, -1e4, -1e4, 1e4, 1e4, 1e4]], np.float32))
     assert np.array_equal(hits[:, 1], np.arange(n, dtype=np.uint32))
     w.close()
+
+
+# ------------------------------------------------------------------ the step as a CUDA graph ---
+def test_graph_replay_matches_direct_launches():
+    """axcd_step replays a CUDA graph of the whole step once the launch configuration has been stable for a
+    step; results must be identical to the direct launches (AXCD_FLAG_NO_GRAPH), step after step, also when
+    the poses change between steps."""
+    s = axcd.config_scene("C1", scale=0.3)
+    wg = axcd.CollisionWorld.for_scene(s)
+    wd = axcd.CollisionWorld.for_scene(s, flags=axcd.FLAG_NO_GRAPH)
+    rng = np.random.default_rng(5)
+    seen_graph = False
+    for it in range(6):
+        xf = s.xf.copy()
+        xf[:, :3] += rng.normal(size=(s.n, 3)).astype(np.float32) * 0.05 * it
+        wg.set_transforms(xf)
+        wd.set_transforms(xf)
+        sg, sd = wg.step(), wd.step()
+        seen_graph = seen_graph or bool(sg.graphLaunched)
+        assert not sd.graphLaunched
+        assert (sg.numPairs, sg.numContacts, sg.kernelLaunches) == (sd.numPairs, sd.numContacts, sd.kernelLaunches)
+        assert np.array_equal(wg.pairs(), wd.pairs())
+        assert wg.contacts().tobytes() == wd.contacts().tobytes()
+        assert_bits_equal(wg.aabbs(), wd.aabbs())
+    assert seen_graph, "the steady-state step must be a graph launch"
+    # a configuration change (filters on) drops the graph; the next steps stay correct
+    filt = np.stack([np.ones(s.n), np.full(s.n, 0xFFFF), rng.integers(-2, 3, s.n)], axis=1)
+    wg.set_filters(filt)
+    wd.set_filters(filt)
+    for _ in range(3):
+        sg, sd = wg.step(), wd.step()
+        assert np.array_equal(wg.pairs(), wd.pairs()) and sg.numPairs < s.n * 8
+    # staged calls after graph steps still give per-stage timings
+    wg.update()
+    wg.detect_collisions()
+    st = wg.stats()
+    assert st.pairMs > 0 and st.graphLaunched == 0
+    wg.close()
+    wd.close()
+
+
+def test_filter_and_awake_argument_checks():
+    s = axcd.config_scene("C0")
+    w = axcd.CollisionWorld.for_scene(s)
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_filters(np.ones((s.n - 1, 3)))          # one record per body, no fewer
+    assert e.value.code == 600
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_awake(np.ones(s.n - 1))
+    assert e.value.code == 600
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_shapes(np.array([(1, -1.0, 1.0, 1.0)], axcd.SHAPE_DT))   # negative half extent
+    assert e.value.code == 300
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_shapes(np.array([(0, np.inf, 0.0, 0.0)], axcd.SHAPE_DT))  # non-finite radius
+    assert e.value.code == 300
+    w.close()

@@ -324,3 +324,27 @@ def test_manifolds_capsule_box_mix():
     assert capbox.sum() > 200 and (gm["count"][capbox] == 2).sum() > 20
     other = ~capbox & ~((ta == 1) & (tb == 1))
     assert (gm["count"][other] == 1).all()
+
+
+def test_temporal_coherence_two_refits_before_a_broadphase():
+    """refit(); refit(); broadphase(): the second refit counts no moved body (the first one already rebuilt the
+    fat boxes), so the cached candidate list must NOT be reused — the bodies moved by the first refit are not
+    in it."""
+    s = axcd.config_scene("C0")
+    w = axcd.CollisionWorld.for_scene(s, aabbMargin=0.05, flags=axcd.FLAG_TEMPORAL_COHERENCE, pairs_per_body=16)
+    w.step()
+    xf = s.xf.copy()
+    xf[:, :3] += np.float32(0.4) * np.sign(np.float32(5.0) - xf[:, :3])      # everybody moves out of its fat box, inwards
+    w.set_transforms(xf)
+    w.refit()
+    w.aabbs()                 # e.g. a debug draw between the two
+    w.refit()
+    w._check(w._lib.axcd_broadphase(w._ctx), "axcd_broadphase")
+    w.detect_collisions()
+    st = w.stats()
+    assert st.broadphaseSkipped == 0
+    ref = axcd.CollisionWorld.for_scene(axcd.Scene(xf, s.shapes, s.hull), aabbMargin=0.05, pairs_per_body=16)
+    ref.step()
+    assert w.contacts().tobytes() == ref.contacts().tobytes()
+    w.close()
+    ref.close()

@@ -22,6 +22,7 @@ FLAG_PAIR_DISTANCES = 1
 FLAG_TEMPORAL_COHERENCE = 4
 FLAG_BOXBOX_GJK_EPA = 8
 FLAG_NO_GRAPH = 16
+FLAG_REFIT_MAT4_ROUTE = 32
 
 SHAPE_DT = np.dtype([("type", "<u4"), ("p0", "<f4"), ("p1", "<f4"), ("p2", "<f4")])
 CONTACT_DT = np.dtype([("a", "<u4"), ("b", "<u4"), ("px", "<f4"), ("py", "<f4"), ("pz", "<f4"),

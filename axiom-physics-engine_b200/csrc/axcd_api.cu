@@ -563,6 +563,13 @@ int32_t axcd_refit(AxcdContext* ctx) {
                 ctx->fatValid ? 0u : 1u, ctx->dCtr, ctrNext, ctx->dCtrInit);
             ctx->fatValid = true;
         } else {
+            if (ctx->cfg.flags & AXCD_FLAG_REFIT_MAT4_ROUTE) {
+                // boxes through AABB::transform(Transform::toMatrix()) (row a15): the block-staged kernel
+                refitKernel<false, true><<<blocks, kRefitThreads, 0, ctx->stream>>>(
+                    reinterpret_cast<const float4*>(ctx->dXf), ctx->dShapes, ctx->dHull,
+                    reinterpret_cast<float4*>(ctx->dAabb), ctx->dType8, ctx->n, ctx->cfg.aabbMargin, 0u, ctx->dCtr,
+                    ctrNext, ctx->dCtrInit);
+            } else {
 #if defined(AXCD_REFIT_NO_TMA)
             // diagnostic build: the block-staged kernel (compute-sanitizer's initcheck does not see the
             // bulk-store writes of the TMA kernel and reports every later read of the AABBs)
@@ -578,6 +585,7 @@ int32_t axcd_refit(AxcdContext* ctx) {
                 ctx->dXf, ctx->dShapes, ctx->dHull, ctx->dAabb, ctx->dType8, ctx->n, ctx->cfg.aabbMargin, ctx->dCtr,
                 ctrNext, ctx->dCtrInit);
 #endif
+            }
         }
         CU(cudaGetLastError());
     }

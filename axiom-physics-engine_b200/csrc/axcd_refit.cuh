@@ -35,10 +35,41 @@ __device__ __forceinline__ void expandPoint(V3& lo, V3& hi, V3 p) {
     hi.z = (p.z > hi.z) ? p.z : hi.z;
 }
 
+// The alternative box route: AABB(-h, h).transform(Transform::toMatrix()), reference:
+// src/math/aabb.cpp:8-35 over src/math/transform.cpp:13-24.  M = T * R * S has mat3_cast(q) with column j scaled
+// by scale_j as its upper-left 3x3 and the position as its last column (products with the identity's zeros and
+// ones are exact); the 8 corners of the LOCAL box in aabb.cpp's order go through glm's mat4 * vec4(c, 1) =
+// (m[0]*x + m[1]*y) + (m[2]*z + m[3]), each product-sum one fused operation; AABB(Vec3) then expand().
+__device__ __forceinline__ void fitBoxMat4(V3 pos, float4 q, V3 scl, float hx, float hy, float hz, V3& lo, V3& hi) {
+    const float qxx = q.x * q.x, qyy = q.y * q.y, qzz = q.z * q.z;
+    const float qxz = q.x * q.z, qxy = q.x * q.y, qyz = q.y * q.z;
+    const float qwx = q.w * q.x, qwy = q.w * q.y, qwz = q.w * q.z;
+    const V3 c0 = mk3(1.0f - 2.0f * (qyy + qzz), 2.0f * (qxy + qwz), 2.0f * (qxz - qwy)) * scl.x;
+    const V3 c1 = mk3(2.0f * (qxy - qwz), 1.0f - 2.0f * (qxx + qzz), 2.0f * (qyz + qwx)) * scl.y;
+    const V3 c2 = mk3(2.0f * (qxz + qwy), 2.0f * (qyz - qwx), 1.0f - 2.0f * (qxx + qyy)) * scl.z;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float cx = (k & 1) ? hx : -hx, cy = (k & 2) ? hy : -hy, cz = (k & 4) ? hz : -hz;
+        const V3 p = mk3(fmaf(c1.x, cy, c0.x * cx) + fmaf(c2.x, cz, pos.x), fmaf(c1.y, cy, c0.y * cx) + fmaf(c2.y, cz, pos.y),
+                         fmaf(c1.z, cy, c0.z * cx) + fmaf(c2.z, cz, pos.z));
+        if (k == 0) {
+            lo = p;
+            hi = p;
+        } else {
+            expandPoint(lo, hi, p);
+        }
+    }
+}
+
 // Tight world-space box of one body (no margin): the per-shape refit rules of SURVEY.md A.2.
+template <bool MAT4 = false>
 __device__ __forceinline__ void fitBody(V3 pos, float4 q, V3 scl, uint4 sh, const float4* __restrict__ hull,
                                         V3& lo, V3& hi) {
     const float p0 = __uint_as_float(sh.y), p1 = __uint_as_float(sh.z), p2 = __uint_as_float(sh.w);
+    if (MAT4 && sh.x == AXCD_SHAPE_BOX) {
+        fitBoxMat4(pos, q, scl, p0, p1, p2, lo, hi);
+        return;
+    }
     if (sh.x == AXCD_SHAPE_SPHERE) {
         // AABB::fromCenterExtents(position, Vec3(r)) (aabb.hpp:213-215); rotation and scale
         // ignored as in the reference's sphere placement (src/debug/physics_debug_draw.cpp:246-248)
@@ -115,7 +146,7 @@ __device__ __forceinline__ void fitBody(V3 pos, float4 q, V3 scl, uint4 sh, cons
 // after the shapes changed) the fat box becomes the tight box expanded by `margin` and the body is
 // counted in ctr->movedBodies.  If nothing moved the candidate-pair set cannot have changed and the host
 // skips the broadphase (axcd_broadphase).
-template <bool COHERENT>
+template <bool COHERENT, bool MAT4 = false>
 __global__ void __launch_bounds__(kRefitThreads)
 refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 (base 16B aligned)
             const uint4* __restrict__ shapes,    // AxcdShape as uint4
@@ -166,7 +197,7 @@ refitKernel(const float4* __restrict__ xf4,      // n*40 bytes viewed as float4 
         const V3 scl = mk3(t[7], t[8], t[9]);
         const uint4 sh = __ldg(shapes + base + tid);
         type8[base + tid] = (uint8_t)sh.x;
-        fitBody(pos, q, scl, sh, hull, lo, hi);
+        fitBody<MAT4>(pos, q, scl, sh, hull, lo, hi);
         float* o = sOut + tid * 6;
         bool keep = false;
         if (COHERENT && !force) {

@@ -123,7 +123,11 @@ enum {
     /* axcd_step / axcd_step_async normally replay a CUDA graph of the whole step once the launch
      * configuration has been stable for a step.  This flag (or AXCD_NO_GRAPH=1 in the environment) keeps
      * them on direct launches.                                                                       */
-    AXCD_FLAG_NO_GRAPH = 16u
+    AXCD_FLAG_NO_GRAPH = 16u,
+    /* Boxes are refit through the reference's OTHER route, AABB::transform(Transform::toMatrix()) (8 corners of
+     * the local box through the TRS matrix; src/math/aabb.cpp:8-35, src/math/transform.cpp:13-24), instead of
+     * 8 x Transform::transformPoint.  Same box up to rounding; kept for hosts that refit that way.      */
+    AXCD_FLAG_REFIT_MAT4_ROUTE = 32u
 };
 
 typedef struct AxcdStats {

@@ -46,11 +46,12 @@ inline V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }    
 inline V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }                        // vec3.hpp:100
 // dot / cross: the reference writes them as plain products and sums (vec3.hpp:179-191) and builds
 // with -mfma and GCC's default contraction, which turns those into fused multiply-adds in a
-// compiler-chosen pattern.  This restatement pins ONE explicit pattern (std::fmaf = one rounding),
-// identical in the CUDA kernels, so CPU and GPU stay bit-identical while the GPU keeps FFMA throughput.
-inline float dot(V3 a, V3 b) { return std::fmaf(a.z, b.z, std::fmaf(a.y, b.y, a.x * b.x)); }
+// compiler-chosen pattern.  This restatement pins ONE explicit pattern (std::fmaf = one rounding) — the one
+// GCC 13 generates for those formulas under the reference's own flags, checked bit for bit against the
+// compiled reference headers in tests/test_oracle_vs_reference.py — identical in the CUDA kernels.
+inline float dot(V3 a, V3 b) { return std::fmaf(a.z, b.z, std::fmaf(a.x, b.x, a.y * b.y)); }
 inline V3 cross(V3 a, V3 b) {
-    return mk(std::fmaf(a.y, b.z, -(a.z * b.y)), std::fmaf(a.z, b.x, -(a.x * b.z)),
+    return mk(std::fmaf(-a.z, b.y, a.y * b.z), std::fmaf(-a.x, b.z, a.z * b.x),
               std::fmaf(a.x, b.y, -(a.y * b.x)));
 }
 inline bool same(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
@@ -112,6 +113,27 @@ inline V3 transformPoint(const Xf& t, V3 p) {
     V3 scaled = mk(p.x * t.s.x, p.y * t.s.y, p.z * t.s.z);
     V3 rotated = quatRotate(t.q, scaled);
     return rotated + t.p;
+}
+
+// Quat::conjugate (include/axiom/math/quat.hpp:96): negates the vector part
+inline Q4 conjugate(Q4 q) { return Q4{-q.x, -q.y, -q.z, q.w}; }
+// Transform::transformDirection (src/math/transform.cpp:95-100): scale, rotate, no translation
+inline V3 transformDirection(const Xf& t, V3 d) {
+    V3 scaled = mk(d.x * t.s.x, d.y * t.s.y, d.z * t.s.z);
+    return quatRotate(t.q, scaled);
+}
+// Transform::inverseTransformPoint (src/math/transform.cpp:113-122): untranslate, conjugate-rotate, multiply by 1/scale
+inline V3 inverseTransformPoint(const Xf& t, V3 p) {
+    V3 translated = p - t.p;
+    V3 rotated = quatRotate(conjugate(t.q), translated);
+    V3 inv = mk(1.0f / t.s.x, 1.0f / t.s.y, 1.0f / t.s.z);
+    return mk(rotated.x * inv.x, rotated.y * inv.y, rotated.z * inv.z);
+}
+// Transform::inverseTransformDirection (src/math/transform.cpp:124-131)
+inline V3 inverseTransformDirection(const Xf& t, V3 d) {
+    V3 rotated = quatRotate(conjugate(t.q), d);
+    V3 inv = mk(1.0f / t.s.x, 1.0f / t.s.y, 1.0f / t.s.z);
+    return mk(rotated.x * inv.x, rotated.y * inv.y, rotated.z * inv.z);
 }
 
 // AABB (include/axiom/math/aabb.hpp)
@@ -185,8 +207,35 @@ void parallelFor(uint64_t n, int nthreads, F&& fn) {
 // ------------------------------------------------------------------------------------------
 // Stage 1: refit
 // ------------------------------------------------------------------------------------------
+// The alternative refit route through AABB::transform(Mat4) (src/math/aabb.cpp:8-35) with M = Transform::toMatrix()
+// = T * R * S (src/math/transform.cpp:13-24): M's upper-left 3x3 is mat3_cast(q) with column j scaled by scale_j
+// (the products with the identity's zeros and ones are exact), the last column is the position; the 8 corners
+// of the LOCAL box [-h, h] in aabb.cpp's order (x fastest) go through glm's mat4 * vec4(c, 1) =
+// (m[0]*x + m[1]*y) + (m[2]*z + m[3]), each product-sum one fused operation; AABB(Vec3) then expand().
+Box refitBoxMat4(const Xf& t, float hx, float hy, float hz) {
+    M3 r = quatToMat3(t.q);
+    const V3 c0 = r.c0 * t.s.x, c1 = r.c1 * t.s.y, c2 = r.c2 * t.s.z;
+    auto xform = [&](V3 c) {
+        return mk(std::fmaf(c1.x, c.y, c0.x * c.x) + std::fmaf(c2.x, c.z, t.p.x),
+                  std::fmaf(c1.y, c.y, c0.y * c.x) + std::fmaf(c2.y, c.z, t.p.y),
+                  std::fmaf(c1.z, c.y, c0.z * c.x) + std::fmaf(c2.z, c.z, t.p.z));
+    };
+    Box b;
+    for (int k = 0; k < 8; ++k) {
+        const V3 c = mk((k & 1) ? hx : -hx, (k & 2) ? hy : -hy, (k & 4) ? hz : -hz);
+        const V3 p = xform(c);
+        if (k == 0) {
+            b.lo = p;
+            b.hi = p;
+        } else {
+            expandPoint(b, p);
+        }
+    }
+    return b;
+}
+
 int refitOne(const Xf& t, const AxrefShape& s, const float* hull, uint32_t nHull, float margin,
-             float* out) {
+             float* out, bool mat4Route = false) {
     Box b;
     if (s.type == SHAPE_SPHERE) {
         // AABB::fromCenterExtents(position, Vec3(r)) (aabb.hpp:213-215); rotation/scale ignored
@@ -194,6 +243,8 @@ int refitOne(const Xf& t, const AxrefShape& s, const float* hull, uint32_t nHull
         V3 r = mk(s.p0, s.p0, s.p0);
         b.lo = t.p - r;
         b.hi = t.p + r;
+    } else if (s.type == SHAPE_BOX && mat4Route) {
+        b = refitBoxMat4(t, s.p0, s.p1, s.p2);
     } else if (s.type == SHAPE_BOX) {
         // corner order of src/debug/debug_draw.cpp:99-108
         float hx = s.p0, hy = s.p1, hz = s.p2;
@@ -1556,20 +1607,74 @@ void axref_rng_float(uint64_t seed, uint32_t n, float* out) {
 }
 int axref_aabb_intersects(const float a[6], const float b[6]) { return intersects(a, b) ? 1 : 0; }
 
-int32_t axref_refit(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
-                    uint32_t nHullVerts, float margin, float* outAabb, int nthreads) {
+int32_t axref_refit_route(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                          uint32_t nHullVerts, float margin, float* outAabb, int nthreads, int mat4Route) {
     if (n && (!xf || !shapes || !outAabb)) return 202;
     std::vector<int> err((size_t)std::max(1, nthreads), 0);
     parallelFor(n, nthreads, [&](int t, uint64_t lo, uint64_t hi) {
         for (uint64_t i = lo; i < hi; ++i) {
             int e = refitOne(loadXf(xf + 10 * i), shapes[i], hullXYZ, nHullVerts, margin,
-                             outAabb + 6 * i);
+                             outAabb + 6 * i, mat4Route != 0);
             if (e) err[(size_t)t] = e;
         }
     });
     for (int e : err)
         if (e) return e;
     return 0;
+}
+int32_t axref_refit(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                    uint32_t nHullVerts, float margin, float* outAabb, int nthreads) {
+    return axref_refit_route(xf, shapes, n, hullXYZ, nHullVerts, margin, outAabb, nthreads, 0);
+}
+
+// ---- the remaining math restatements, exported for tests/test_oracle_vs_reference.py ----------------------
+float axref_vec3_dot(const float a[3], const float b[3]) { return dot(mk(a[0], a[1], a[2]), mk(b[0], b[1], b[2])); }
+void axref_vec3_cross(const float a[3], const float b[3], float o[3]) {
+    V3 c = cross(mk(a[0], a[1], a[2]), mk(b[0], b[1], b[2]));
+    o[0] = c.x; o[1] = c.y; o[2] = c.z;
+}
+void axref_quat_conjugate(const float q[4], float o[4]) {
+    Q4 c = conjugate(Q4{q[0], q[1], q[2], q[3]});
+    o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = c.w;
+}
+void axref_transform_direction(const float xf[10], const float d[3], float o[3]) {
+    V3 r = transformDirection(loadXf(xf), mk(d[0], d[1], d[2]));
+    o[0] = r.x; o[1] = r.y; o[2] = r.z;
+}
+void axref_inverse_transform_point(const float xf[10], const float p[3], float o[3]) {
+    V3 r = inverseTransformPoint(loadXf(xf), mk(p[0], p[1], p[2]));
+    o[0] = r.x; o[1] = r.y; o[2] = r.z;
+}
+void axref_inverse_transform_direction(const float xf[10], const float d[3], float o[3]) {
+    V3 r = inverseTransformDirection(loadXf(xf), mk(d[0], d[1], d[2]));
+    o[0] = r.x; o[1] = r.y; o[2] = r.z;
+}
+// AABB ops as the broadphase / refit / LBVH code uses them (aabb.hpp:47,62,68,143-173,213-215)
+void axref_aabb_expand_point(const float a[6], const float p[3], float o[6]) {
+    Box b{mk(a[0], a[1], a[2]), mk(a[3], a[4], a[5])};
+    expandPoint(b, mk(p[0], p[1], p[2]));
+    o[0] = b.lo.x; o[1] = b.lo.y; o[2] = b.lo.z; o[3] = b.hi.x; o[4] = b.hi.y; o[5] = b.hi.z;
+}
+void axref_aabb_merge(const float a[6], const float b[6], float o[6]) {   // aabb.hpp:166-173, :223-229
+    for (int k = 0; k < 3; ++k) {
+        o[k] = (b[k] < a[k]) ? b[k] : a[k];
+        o[k + 3] = (b[k + 3] > a[k + 3]) ? b[k + 3] : a[k + 3];
+    }
+}
+void axref_aabb_center(const float a[6], float o[3]) {   // aabb.hpp:62: (min + max) * 0.5f
+    for (int k = 0; k < 3; ++k) o[k] = (a[k] + a[k + 3]) * 0.5f;
+}
+void axref_aabb_expand_margin(const float a[6], float margin, float o[6]) {   // aabb.hpp:156-160
+    for (int k = 0; k < 3; ++k) {
+        o[k] = a[k] - margin;
+        o[k + 3] = a[k + 3] + margin;
+    }
+}
+void axref_aabb_from_center_extents(const float c[3], const float h[3], float o[6]) {   // aabb.hpp:213-215
+    for (int k = 0; k < 3; ++k) {
+        o[k] = c[k] - h[k];
+        o[k + 3] = c[k] + h[k];
+    }
 }
 
 int32_t axref_broadphase_brute_f(const float* aabb, uint32_t n, const uint32_t* worldId, const uint32_t* filt,

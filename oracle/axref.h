@@ -42,10 +42,26 @@ void axref_transform_point(const float xf[10], const float p[3], float out[3]);
 void axref_rng_u32(uint64_t seed, uint32_t n, uint32_t* out);
 void axref_rng_float(uint64_t seed, uint32_t n, float* out);
 int  axref_aabb_intersects(const float a[6], const float b[6]);
+float axref_vec3_dot(const float a[3], const float b[3]);
+void axref_vec3_cross(const float a[3], const float b[3], float o[3]);
+void axref_quat_conjugate(const float q[4], float o[4]);                                  /* quat.hpp:96 */
+void axref_transform_direction(const float xf[10], const float d[3], float o[3]);         /* transform.cpp:95-100 */
+void axref_inverse_transform_point(const float xf[10], const float p[3], float o[3]);     /* transform.cpp:113-122 */
+void axref_inverse_transform_direction(const float xf[10], const float d[3], float o[3]); /* transform.cpp:124-131 */
+void axref_aabb_expand_point(const float a[6], const float p[3], float o[6]);
+void axref_aabb_merge(const float a[6], const float b[6], float o[6]);
+void axref_aabb_center(const float a[6], float o[3]);
+void axref_aabb_expand_margin(const float a[6], float margin, float o[6]);
+void axref_aabb_from_center_extents(const float c[3], const float h[3], float o[6]);
 
 /* stage 1: refit.  xf = n x 10 floats (axiom::math::Transform), out = n x 6 floats (AABB).    */
 int32_t axref_refit(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
                     uint32_t nHullVerts, float margin, float* outAabb, int nthreads);
+
+/* the same with the box route selectable: mat4Route != 0 refits boxes through AABB::transform(Transform::toMatrix())
+ * (src/math/aabb.cpp:8-35) instead of 8 x Transform::transformPoint — SURVEY.md 8(a) row a15.            */
+int32_t axref_refit_route(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                          uint32_t nHullVerts, float margin, float* outAabb, int nthreads, int mat4Route);
 
 /* stage 2: candidate pairs, canonical (a<b, sorted).  *outCount is the true count even when it
  * exceeds cap (only cap pairs are written).  worldId may be NULL.                             */

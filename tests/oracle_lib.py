@@ -115,14 +115,16 @@ def aabb_intersects(a, b):
     return bool(lib().axref_aabb_intersects(_p(f32(a)), _p(f32(b))))
 
 
-def refit(xf, shapes, hull=None, margin=0.0, nthreads=1):
+def refit(xf, shapes, hull=None, margin=0.0, nthreads=1, mat4_route=False):
+    """mat4_route: boxes through AABB::transform(Transform::toMatrix()) (row a15) instead of 8 x transformPoint."""
     xf = f32(xf).reshape(-1, 10)
     n = xf.shape[0]
     shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
     hull = f32(hull if hull is not None else np.zeros((0, 3))).reshape(-1, 3)
     out = np.zeros((n, 6), np.float32)
-    rc = lib().axref_refit(_p(xf), _p(shapes), C.c_uint32(n), _p(hull), C.c_uint32(len(hull)),
-                           C.c_float(margin), _p(out), C.c_int(nthreads))
+    lib().axref_refit_route.restype = C.c_int32
+    rc = lib().axref_refit_route(_p(xf), _p(shapes), C.c_uint32(n), _p(hull), C.c_uint32(len(hull)),
+                                 C.c_float(margin), _p(out), C.c_int(nthreads), C.c_int(1 if mat4_route else 0))
     return rc, out
 
 

@@ -565,3 +565,22 @@ def test_filter_and_awake_argument_checks():
         w.set_shapes(np.array([(0, np.inf, 0.0, 0.0)], axcd.SHAPE_DT))  # non-finite radius
     assert e.value.code == 300
     w.close()
+
+
+def test_refit_mat4_route_matches_oracle_bit_for_bit():
+    """AXCD_FLAG_REFIT_MAT4_ROUTE (SURVEY.md 8(a) row a15): boxes refit through AABB::transform(Transform::toMatrix())
+    as src/math/aabb.cpp:8-35 does it.  AABBs bit-identical to the oracle's restatement of that route (which
+    tests/test_oracle_vs_reference.py pins to the compiled reference functions), pair and contact sets exact."""
+    s = axcd.config_scene("C2", scale=0.02)
+    s.xf[:, 7:10] = np.random.default_rng(3).uniform(0.5, 1.6, (s.n, 3)).astype(np.float32)
+    w = axcd.CollisionWorld.for_scene(s, flags=axcd.FLAG_REFIT_MAT4_ROUTE)
+    st = w.step()
+    rc, bb = O.refit(s.xf, s.shapes, s.hull, mat4_route=True)
+    assert_bits_equal(w.aabbs(), bb)
+    rc, bb0 = O.refit(s.xf, s.shapes, s.hull)
+    assert not np.array_equal(bb.view(np.uint32), bb0.view(np.uint32))     # the two routes round differently
+    pairs = O.broadphase(bb, nthreads=8)
+    assert np.array_equal(w.pairs(), pairs)
+    con, _, _ = O.narrowphase(s.xf, s.shapes, pairs, s.hull, nthreads=8)
+    assert w.contacts().tobytes() == con.tobytes()
+    w.close()

@@ -51,6 +51,7 @@ ABI_SYMBOLS = [
     "axcd_set_ghosts_device", "axcd_nccl_unique_id", "axcd_slab_init", "axcd_slab_init_comm",
     "axcd_slab_step_async", "axcd_slab_step", "axcd_get_body_keys",
     "axcd_test_sort_pairs32", "axcd_test_sort_keys64", "axcd_test_sort_bench", "axcd_test_fp32_peak",
+    "axcd_test_sort_morton", "axcd_test_sort_bench_morton",
 ]
 SCENE_SYMBOLS = ["axcd_scene_generate", "axcd_scene_generate_worlds", "axcd_scene_rng_u32"]
 
@@ -75,7 +76,8 @@ class Stats(C.Structure):
                 ("bytesMoved", C.c_uint64), ("kernelLaunches", C.c_uint32),
                 ("contactPointCount", C.c_uint32),
                 ("movedBodies", C.c_uint32), ("broadphaseSkipped", C.c_uint32), ("graphLaunched", C.c_uint32),
-                ("ghostBodies", C.c_uint32), ("exchangeMs", C.c_float)]
+                ("ghostBodies", C.c_uint32), ("sortFallback", C.c_uint32), ("sortMaxBucket", C.c_uint32),
+                ("exchangeMs", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -571,6 +573,23 @@ class CollisionWorld:
         """Average ms of one device-resident (key,value) radix sort of n pseudo-random keys."""
         ms = C.c_float(0)
         self._check(self._lib.axcd_test_sort_bench(self._ctx, n, key_bits, iters, C.byref(ms)), "sort_bench")
+        return ms.value
+
+    def test_sort_morton(self, keys, key_bits=32, mode=1):
+        """The step's Morton sort on caller keys (identity payload).  Returns (sorted keys, permutation, fallback)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        ok, ov = np.zeros(len(keys), np.uint32), np.zeros(len(keys), np.uint32)
+        fb = C.c_uint32(0)
+        self._lib.axcd_test_sort_morton.restype = C.c_int32
+        self._check(self._lib.axcd_test_sort_morton(self._ctx, _ptr(keys), C.c_uint32(len(keys)), C.c_uint32(key_bits),
+                                                    C.c_uint32(mode), _ptr(ok), _ptr(ov), C.byref(fb)), "sort_morton")
+        return ok, ov, fb.value
+
+    def sort_bench_morton(self, n, key_bits=32, iters=10, mode=1):
+        ms = C.c_float(0)
+        self._lib.axcd_test_sort_bench_morton.restype = C.c_int32
+        self._check(self._lib.axcd_test_sort_bench_morton(self._ctx, C.c_uint32(n), C.c_uint32(key_bits), C.c_uint32(iters),
+                                                          C.c_uint32(mode), C.byref(ms)), "sort_bench_morton")
         return ms.value
 
     def fp32_peak(self, iters=4096):

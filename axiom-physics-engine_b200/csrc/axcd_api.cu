@@ -129,6 +129,12 @@ struct AxcdContext {
     float* dPairDist = nullptr;
     uint32_t* dSortHist = nullptr;
     uint32_t* dSortStatus = nullptr;
+    // bucket sort of the Morton keys (axcd_sort.cuh): counts / starts / cursors per bucket, (key, index) staging
+    uint32_t* dBucketCounts = nullptr;
+    uint32_t* dBucketStarts = nullptr;
+    uint32_t* dBucketCursors = nullptr;
+    uint2* dBucketTmp = nullptr;
+    bool bucketSortOff = false;      // AXCD_NO_BUCKET_SORT=1: always the LSD radix sort
     Counters* dCtr = nullptr;
     Counters* dCtrBase = nullptr;    // two counter blocks: step k uses one, its refit kernel resets the other for step k+1
     int ctrParity = 0;
@@ -329,7 +335,8 @@ void axcd_destroy(AxcdContext* ctx) {
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes, ctx->dNodes32,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dManifolds, ctx->dQIn, ctx->dQCount, ctx->dQSeg, ctx->dQOut, ctx->dPairDist, ctx->dSortHist,
-                    ctx->dSortStatus, ctx->dCtrBase, ctx->dCtrInit};
+                    ctx->dSortStatus, ctx->dCtrBase, ctx->dCtrInit, ctx->dBucketCounts, ctx->dBucketStarts, ctx->dBucketCursors,
+                    ctx->dBucketTmp};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (int i = 0; i < EV_COUNT; ++i)
@@ -372,6 +379,8 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
     {
         const char* ng = getenv("AXCD_NO_GRAPH");
         if (ng && ng[0] == '1') ctx->graphsOff = true;
+        const char* nbs = getenv("AXCD_NO_BUCKET_SORT");
+        if (nbs && nbs[0] == '1') ctx->bucketSortOff = true;
     }
     for (int i = 0; i < EV_COUNT; ++i) {
         ctx->ev[i] = nullptr;
@@ -430,6 +439,11 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dSortHist, (size_t)kMaxPasses * kRadix));
         const size_t maxTiles = sortTilesFor(nb > np ? nb : np);
         CU(dalloc(&ctx->dSortStatus, (size_t)kMaxPasses * maxTiles * kRadix));
+        CU(dalloc(&ctx->dBucketCounts, (size_t)(1u << kMaxBucketBits)));
+        CU(dalloc(&ctx->dBucketStarts, (size_t)(1u << kMaxBucketBits) + 1));
+        CU(dalloc(&ctx->dBucketCursors, (size_t)(1u << kMaxBucketBits)));
+        CU(dalloc(&ctx->dBucketTmp, nb));
+        CU(cudaMemsetAsync(ctx->dBucketCounts, 0, sizeof(uint32_t) << kMaxBucketBits, ctx->stream));
         CU(dalloc(&ctx->dCtrBase, 2));
         ctx->dCtr = ctx->dCtrBase;
         CU(dalloc(&ctx->dCtrInit, 1));
@@ -605,6 +619,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
     ctx->numPairs = ctx->foundPairs = 0;
     ctx->launches[1] = 0;
     ctx->broadSkipped = false;
+    uint32_t bucketLaunches = 0;
     if ((ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE) && n >= 2) {
         // Temporal coherence: the candidate set is a function of the fat boxes only.  If no body left
         // its fat box since the cached broadphase, the cached canonical pair list is still exact.
@@ -635,14 +650,34 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         zl.ptr[2] = ctx->dSlotStatus;  zl.words[2] = slotTilesZ + 1;
         zl.ptr[3] = ctx->dSortHist;    zl.words[3] = kMaxPasses * kRadix;
         zl.ptr[4] = ctx->dSortStatus;  zl.words[4] = (uint32_t)passes * sortTilesFor(n) * kRadix;
+        // Morton keys, then the bucket sort (one MSD pass + per-bucket shared-memory sorts); the LSD radix kernels
+        // are launched behind it and run only if a bucket overflowed (device-side flag, no host round trip)
+        const BucketPlan bp = ctx->bucketSortOff ? BucketPlan{0, 0} : bucketPlanFor(n, keyBits);
         mortonKernel<<<blocks, kRefitThreads, 0, st>>>(reinterpret_cast<const float4*>(ctx->dAabb),
                                                        ctx->hasWorlds ? ctx->dWorld : nullptr, ctx->dKeys[0],
-                                                       ctx->dVals[0], n, ctx->mortonBits, ctx->dCtr, zl);
+                                                       ctx->dVals[0], n, ctx->mortonBits, ctx->dCtr, zl,
+                                                       bp.bucketBits ? ctx->dBucketCounts : nullptr, bp.shift);
         CU(cudaGetLastError());
+        const uint32_t* lsdEnable = nullptr;
+        bucketLaunches = 0;
+        if (bp.bucketBits) {
+            const uint32_t nbk = 1u << bp.bucketBits;
+            const int outBuf = passes & 1;   // where the LSD sort would leave its result: everything downstream reads that
+            bucketScanKernel<<<1, 1024, 0, st>>>(ctx->dBucketCounts, ctx->dBucketStarts, ctx->dBucketCursors, nbk,
+                                                 &ctx->dCtr->sortFallback, &ctx->dCtr->sortMaxBucket);
+            bucketScatterKernel<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->dKeys[0], n, bp.shift, ctx->dBucketCursors, ctx->dBucketTmp,
+                                                                 &ctx->dCtr->sortFallback);
+            const uint32_t sortBlocks = nbk < (uint32_t)ctx->numSMs * 16 ? nbk : (uint32_t)ctx->numSMs * 16;
+            bucketSortKernel<<<sortBlocks, kBucketThreads, 0, st>>>(ctx->dBucketTmp, ctx->dBucketStarts, nbk, ctx->dKeys[outBuf],
+                                                                    ctx->dVals[outBuf], &ctx->dCtr->sortFallback);
+            CU(cudaGetLastError());
+            lsdEnable = &ctx->dCtr->sortFallback;
+            bucketLaunches = 3;
+        }
         // the radix tickets live in the per-step counter block, which the refit kernel reset
         const int sb = radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0,
                                                  passes, ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st,
-                                                 ctx->numSMs, true);
+                                                 ctx->numSMs, true, lsdEnable);
         CU(cudaGetLastError());
         recordEv(ctx, EV_SORT);
         ctx->sortedBuf = sb;
@@ -702,7 +737,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         // no host round trip here: the narrowphase kernels read the pair count on the device
         // morton, (hist, scan, passes), gather, [worldEnds], range tree, topology+fit, traversal, scan, scatter,
         // segment sort
-        ctx->launches[1] = 1 + (2 + passes) + 1 + (ctx->hasWorlds ? 1 : 0) + segLaunches + 1 + 1 + 3;
+        ctx->launches[1] = 1 + bucketLaunches + (2 + passes) + 1 + (ctx->hasWorlds ? 1 : 0) + segLaunches + 1 + 1 + 3;
     } else {
         recordEv(ctx, EV_SORT);
         recordEv(ctx, EV_BUILD);
@@ -828,6 +863,8 @@ int32_t axcd_get_stats(AxcdContext* ctx, AxcdStats* out) {
         out->totalMs = evMs(ctx, EV_START, EV_END);   // a graph-launched step has this one only
     }
     out->graphLaunched = ctx->lastStepGraph ? 1u : 0u;
+    out->sortFallback = (ctx->stage >= ST_BROAD) ? ctx->hostCtr.sortFallback : 0u;
+    out->sortMaxBucket = (ctx->stage >= ST_BROAD) ? ctx->hostCtr.sortMaxBucket : 0u;
     // algorithmic bytes: refit 80 B/body, Morton 32 B/body, sort (16 B * passes + 4) per
     // element, pair sort (16 B * passes + 8) per pair, narrowphase gather 96 B/pair + 40 B/contact
     {
@@ -1632,6 +1669,88 @@ int32_t axcd_test_sort_bench(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uin
         CU(cudaEventRecord(e0, st));
         radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0, passes,
                                   ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st);
+        CU(cudaEventRecord(e1, st));
+        CU(cudaStreamSynchronize(st));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (it) total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *outMsPerSort = total / (float)iters;
+    return AXCD_OK;
+}
+
+// Sorts n keys with an identity payload the way a step sorts its Morton keys (mode 1: bucket sort with the LSD
+// fallback armed, mode 0: LSD only); outputs sorted keys and the permutation, *outFallback = 1 if the LSD
+// kernels did the work.
+int32_t axcd_test_sort_morton(AxcdContext* ctx, const uint32_t* keys, uint32_t n, uint32_t keyBits, uint32_t mode,
+                              uint32_t* outKeys, uint32_t* outVals, uint32_t* outFallback) {
+    if (!ctx || (n && (!keys || !outKeys || !outVals))) return AXCD_ERR_NULL_POINTER;
+    if (n > ctx->cfg.maxBodies || keyBits == 0 || keyBits > 32) return AXCD_ERR_OUT_OF_RANGE;
+    if (n == 0) return AXCD_OK;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    const int passes = (int)(keyBits + 7) / 8;
+    const BucketPlan bp = mode ? bucketPlanFor(n, (int)keyBits) : BucketPlan{0, 0};
+    CU(cudaMemcpyAsync(ctx->dKeys[0], keys, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    uint32_t* flag = &ctx->dCtr->sortFallback;
+    CU(cudaMemsetAsync(flag, 0, 4, st));
+    iotaCountKernel<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->dKeys[0], ctx->dVals[0], n, bp.bucketBits ? ctx->dBucketCounts : nullptr, bp.shift);
+    const uint32_t* enable = nullptr;
+    if (bp.bucketBits) {
+        const uint32_t nbk = 1u << bp.bucketBits;
+        const int outBuf = passes & 1;
+        bucketScanKernel<<<1, 1024, 0, st>>>(ctx->dBucketCounts, ctx->dBucketStarts, ctx->dBucketCursors, nbk, flag, &ctx->dCtr->sortMaxBucket);
+        bucketScatterKernel<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->dKeys[0], n, bp.shift, ctx->dBucketCursors, ctx->dBucketTmp, flag);
+        const uint32_t sortBlocks = nbk < (uint32_t)ctx->numSMs * 16 ? nbk : (uint32_t)ctx->numSMs * 16;
+        bucketSortKernel<<<sortBlocks, kBucketThreads, 0, st>>>(ctx->dBucketTmp, ctx->dBucketStarts, nbk, ctx->dKeys[outBuf], ctx->dVals[outBuf], flag);
+        enable = flag;
+    }
+    const int sb = radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0, passes,
+                                             ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st, ctx->numSMs, false, enable);
+    CU(cudaGetLastError());
+    uint32_t fb = 0;
+    CU(cudaMemcpyAsync(&fb, flag, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(outKeys, ctx->dKeys[sb], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(outVals, ctx->dVals[sb], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (outFallback) *outFallback = bp.bucketBits ? fb : 1u;
+    return AXCD_OK;
+}
+
+// Device-resident timing of that sort on n pseudo-random keys (identity payload): average ms of `iters` sorts,
+// key generation + bucket counting excluded for mode 0 and included (it is part of the method) for mode 1.
+int32_t axcd_test_sort_bench_morton(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uint32_t iters, uint32_t mode,
+                                    float* outMsPerSort) {
+    if (!ctx || !outMsPerSort) return AXCD_ERR_NULL_POINTER;
+    if (n == 0 || n > ctx->cfg.maxBodies || keyBits == 0 || keyBits > 32 || iters == 0) return AXCD_ERR_OUT_OF_RANGE;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float total = 0.0f;
+    const int passes = (int)(keyBits + 7) / 8;
+    const BucketPlan bp = mode ? bucketPlanFor(n, (int)keyBits) : BucketPlan{0, 0};
+    uint32_t* flag = &ctx->dCtr->sortFallback;
+    for (uint32_t it = 0; it <= iters; ++it) {   // iteration 0 is a warm-up
+        fillRandomKeysKernel<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->dKeys[0], ctx->dVals[0], n, keyBits, 0x9E3779B9u * (it + 1));
+        CU(cudaMemsetAsync(flag, 0, 4, st));
+        CU(cudaEventRecord(e0, st));
+        const uint32_t* enable = nullptr;
+        if (bp.bucketBits) {
+            const uint32_t nbk = 1u << bp.bucketBits;
+            const int outBuf = passes & 1;
+            iotaCountKernel<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->dKeys[0], ctx->dVals[0], n, ctx->dBucketCounts, bp.shift);
+            bucketScanKernel<<<1, 1024, 0, st>>>(ctx->dBucketCounts, ctx->dBucketStarts, ctx->dBucketCursors, nbk, flag, &ctx->dCtr->sortMaxBucket);
+            bucketScatterKernel<<<ctx->numSMs * 8, 256, 0, st>>>(ctx->dKeys[0], n, bp.shift, ctx->dBucketCursors, ctx->dBucketTmp, flag);
+            const uint32_t sortBlocks = nbk < (uint32_t)ctx->numSMs * 16 ? nbk : (uint32_t)ctx->numSMs * 16;
+            bucketSortKernel<<<sortBlocks, kBucketThreads, 0, st>>>(ctx->dBucketTmp, ctx->dBucketStarts, nbk, ctx->dKeys[outBuf], ctx->dVals[outBuf], flag);
+            enable = flag;
+        }
+        radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0, passes, ctx->dSortHist,
+                                  ctx->dSortStatus, ctx->dCtr->sortTicket, st, ctx->numSMs, false, enable);
         CU(cudaEventRecord(e1, st));
         CU(cudaStreamSynchronize(st));
         float ms = 0.0f;

@@ -104,6 +104,8 @@ struct Counters {
     uint32_t travOverflow;   // set if a traversal stack ever filled up (the step then reports 505 instead of losing pairs)
     uint32_t movedBodies;    // temporal coherence: bodies whose tight box left their fat box this step
     uint32_t manifoldPoints; // contact points over all manifolds (PhysicsWorldStats::contactPointCount)
+    uint32_t sortFallback;   // bucket sort gave up (a bucket over its capacity): the LSD radix kernels sort instead
+    uint32_t sortMaxBucket;  // largest Morton bucket of the step
 };
 
 }  // namespace axcd

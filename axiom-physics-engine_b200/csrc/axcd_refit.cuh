@@ -467,7 +467,8 @@ struct ZeroList {
 __global__ void __launch_bounds__(kRefitThreads)
 mortonKernel(const float4* __restrict__ aabb4, const uint32_t* __restrict__ worldId,
              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n,
-             int bitsPerAxis, const Counters* __restrict__ ctr, ZeroList zl) {
+             int bitsPerAxis, const Counters* __restrict__ ctr, ZeroList zl,
+             uint32_t* __restrict__ bucketCounts /* or nullptr */, int bucketShift) {
     __shared__ __align__(16) float sIn[kRefitThreads * 6];
     const uint32_t base = blockIdx.x * kRefitThreads;
     const uint32_t cnt = min((uint32_t)kRefitThreads, n - base);
@@ -504,6 +505,7 @@ mortonKernel(const float4* __restrict__ aabb4, const uint32_t* __restrict__ worl
     if (worldId) code |= __ldg(worldId + base + tid) << (3 * bitsPerAxis);
     keys[base + tid] = code;
     vals[base + tid] = base + tid;
+    if (bucketCounts) atomicAdd(bucketCounts + (code >> bucketShift), 1u);   // bucket sort, step 1 (axcd_sort.cuh)
 }
 
 // ---- x-slab mode: ghost records --------------------------------------------------------------------

@@ -36,8 +36,9 @@ __device__ __forceinline__ uint32_t digitOf(K key, int shift) {
 template <typename K>
 __global__ void __launch_bounds__(kSortThreads)
 radixHistogramKernel(const K* __restrict__ keys, uint32_t n, int bitStart, int passes,
-                     uint32_t* __restrict__ hist) {
+                     uint32_t* __restrict__ hist, const uint32_t* __restrict__ enable = nullptr) {
     __shared__ uint32_t sh[kMaxPasses * kRadix];
+    if (enable && !*enable) return;   // fallback of the bucket sort: runs only when that one gave up
     for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) sh[i] = 0;
     __syncthreads();
     const uint32_t stride = gridDim.x * kSortThreads;
@@ -54,8 +55,9 @@ radixHistogramKernel(const K* __restrict__ keys, uint32_t n, int bitStart, int p
 
 // In-place exclusive scan of each pass's 256 bins; one block of 256 threads, one warp-scan tree.
 __global__ void __launch_bounds__(kRadix)
-radixScanKernel(uint32_t* __restrict__ hist, int passes) {
+radixScanKernel(uint32_t* __restrict__ hist, int passes, const uint32_t* __restrict__ enable = nullptr) {
     __shared__ uint32_t warpSum[kRadix / 32];
+    if (enable && !*enable) return;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int p = 0; p < passes; ++p) {
         const uint32_t v = hist[p * kRadix + tid];
@@ -81,8 +83,10 @@ __global__ void __launch_bounds__(kSortThreads)
 radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
                     const uint32_t* __restrict__ valsIn, uint32_t* __restrict__ valsOut,
                     uint32_t n, int shift, const uint32_t* __restrict__ globalBase,
-                    volatile uint32_t* __restrict__ status, uint32_t* __restrict__ ticket) {
+                    volatile uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
+                    const uint32_t* __restrict__ enable = nullptr) {
     __shared__ K sKeys[kSortTile];
+    if (enable && !*enable) return;
     __shared__ uint32_t sVals[HAS_VAL ? kSortTile : 1];
     __shared__ uint32_t sWarpHist[kSortWarps][kRadix];
     __shared__ uint32_t sDigitStart[kRadix];
@@ -218,7 +222,8 @@ template <typename K, bool HAS_VAL>
 inline int radixSort(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, uint32_t n, int bitStart,
                      int passes, uint32_t* scratchHist, uint32_t* scratchStatus,
                      uint32_t* tickets /* kMaxPasses words */, cudaStream_t stream, int numSMs = kNumSMs,
-                     bool scratchZeroed = false /* the caller already cleared hist / status / tickets */) {
+                     bool scratchZeroed = false /* the caller already cleared hist / status / tickets */,
+                     const uint32_t* enable = nullptr /* device flag: kernels return at once while it is 0 */) {
     if (n == 0 || passes == 0) return 0;
     const uint32_t numTiles = (n + kSortTile - 1) / kSortTile;
     if (!scratchZeroed) {
@@ -228,8 +233,8 @@ inline int radixSort(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, uint3
     }
     uint32_t histBlocks = (n + kSortThreads * AXCD_HIST_ITEMS - 1) / (kSortThreads * AXCD_HIST_ITEMS);
     if (histBlocks > (uint32_t)numSMs * 8) histBlocks = numSMs * 8;
-    radixHistogramKernel<K><<<histBlocks, kSortThreads, 0, stream>>>(keysA, n, bitStart, passes, scratchHist);
-    radixScanKernel<<<1, kRadix, 0, stream>>>(scratchHist, passes);
+    radixHistogramKernel<K><<<histBlocks, kSortThreads, 0, stream>>>(keysA, n, bitStart, passes, scratchHist, enable);
+    radixScanKernel<<<1, kRadix, 0, stream>>>(scratchHist, passes, enable);
     K* kin = keysA;
     K* kout = keysB;
     uint32_t* vin = valsA;
@@ -237,11 +242,163 @@ inline int radixSort(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, uint3
     for (int p = 0; p < passes; ++p) {
         radixOnesweepKernel<K, HAS_VAL><<<numTiles, kSortThreads, 0, stream>>>(
             kin, kout, vin, vout, n, bitStart + 8 * p, scratchHist + p * kRadix,
-            scratchStatus + (size_t)p * numTiles * kRadix, tickets + p);
+            scratchStatus + (size_t)p * numTiles * kRadix, tickets + p, enable);
         K* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
     return passes & 1;
+}
+
+// ---- bucket sort of the Morton keys (the step's default; the LSD sort above is its fallback) --------------------
+// The Morton sort of a step orders (key, body index) pairs whose payload starts out as the identity.  For keys
+// that spread over their top bits — bodies spread over the scene — one MSD pass is enough:
+//   1. mortonKernel counts the keys per bucket (top `bucketBits` bits; about 256 keys per bucket) while it
+//      writes them,
+//   2. bucketScanKernel turns the counts into bucket starts and finds the largest bucket,
+//   3. bucketScatterKernel drops every (key, index) into its bucket (one returning atomic per key; the order
+//      inside a bucket does not matter),
+//   4. bucketSortKernel sorts each bucket by (key, index) in shared memory (bitonic, one block per bucket) and
+//      writes keys and indices out — the same total order as the stable LSD sort.
+// Against 3 LSD passes (16 B read+write per key and pass, plus per-tile look-back chains that serialise when
+// all tiles are co-resident) this moves 4 + 8 + 16 B per key in three short kernels.  If any bucket exceeds
+// kBucketCap (a clustered scene: most bodies in a few Morton cells) step 2 raises ctr->sortFallback, steps 3-4
+// return at once and the LSD kernels — always launched behind them, returning at once otherwise — sort instead.
+constexpr int kBucketCap = 1024;       // keys a bucket-sort block takes
+constexpr int kBucketThreads = 256;
+constexpr int kMaxBucketBits = 16;
+
+struct BucketPlan {
+    int bucketBits;   // 0: bucket sort off
+    int shift;        // bucket = key >> shift
+};
+// about 256 keys per bucket, never more buckets than the key has leading bits for
+inline BucketPlan bucketPlanFor(uint32_t n, int keyBits) {
+    int nb = 1;
+    while (nb < 32 && (1ull << nb) < n) ++nb;
+    int b = nb - 8;
+    if (b > kMaxBucketBits) b = kMaxBucketBits;
+    if (b > keyBits) b = keyBits;
+    if (b < 1 || n < 4096) return BucketPlan{0, 0};
+    return BucketPlan{b, keyBits - b};
+}
+
+// One block: exclusive scan of the bucket counts -> starts[0..numBuckets] (and a copy as the scatter cursors),
+// largest bucket -> fallback flag; clears the counts for the next step.
+__global__ void __launch_bounds__(1024)
+bucketScanKernel(uint32_t* __restrict__ counts, uint32_t* __restrict__ starts, uint32_t* __restrict__ cursors,
+                 uint32_t numBuckets, uint32_t* __restrict__ fallbackFlag, uint32_t* __restrict__ maxBucketOut) {
+    __shared__ uint32_t sWarp[32];
+    __shared__ uint32_t sCarry, sMax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        sCarry = 0;
+        sMax = 0;
+    }
+    __syncthreads();
+    uint32_t localMax = 0;
+    for (uint32_t base = 0; base < numBuckets; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t v = (i < numBuckets) ? counts[i] : 0u;
+        if (i < numBuckets) counts[i] = 0u;
+        localMax = max(localMax, v);
+        uint32_t inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) sWarp[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            wbase += (w < warp) ? sWarp[w] : 0u;
+            total += sWarp[w];
+        }
+        const uint32_t excl = sCarry + wbase + inc - v;
+        if (i < numBuckets) {
+            starts[i] = excl;
+            cursors[i] = excl;
+        }
+        __syncthreads();
+        if (tid == 0) sCarry += total;
+        __syncthreads();
+    }
+    localMax = __reduce_max_sync(0xffffffffu, localMax);
+    if (lane == 0) atomicMax(&sMax, localMax);
+    __syncthreads();
+    if (tid == 0) {
+        starts[numBuckets] = sCarry;
+        *maxBucketOut = sMax;
+        *fallbackFlag = (sMax > (uint32_t)kBucketCap) ? 1u : 0u;
+    }
+}
+
+// (key, index) of every element into its bucket; tmp holds uint2 (key, index).
+__global__ void __launch_bounds__(256)
+bucketScatterKernel(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ cursors,
+                    uint2* __restrict__ tmp, const uint32_t* __restrict__ fallbackFlag) {
+    if (*fallbackFlag) return;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint32_t k = keys[i];
+        const uint32_t pos = atomicAdd(&cursors[k >> shift], 1u);
+        tmp[pos] = make_uint2(k, i);
+    }
+}
+
+// One block per bucket: bitonic sort of (key << 32 | index) in shared memory, padded to the next power of two.
+__global__ void __launch_bounds__(kBucketThreads)
+bucketSortKernel(const uint2* __restrict__ tmp, const uint32_t* __restrict__ starts, uint32_t numBuckets,
+                 uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ fallbackFlag) {
+    __shared__ unsigned long long sElem[kBucketCap];
+    if (*fallbackFlag) return;
+    const int tid = threadIdx.x;
+    for (uint32_t b = blockIdx.x; b < numBuckets; b += gridDim.x) {
+        const uint32_t start = starts[b], count = starts[b + 1] - start;
+        if (count == 0) continue;
+        uint32_t S = 1;
+        while (S < count) S <<= 1;
+        for (uint32_t i = tid; i < S; i += kBucketThreads) {
+            unsigned long long e = ~0ull;
+            if (i < count) {
+                const uint2 kv = tmp[start + i];
+                e = ((unsigned long long)kv.x << 32) | kv.y;
+            }
+            sElem[i] = e;
+        }
+        __syncthreads();
+        for (uint32_t k = 2; k <= S; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = tid; t < (S >> 1); t += kBucketThreads) {
+                    // t-th compare-exchange of this stage: partner indices (lo, lo | j)
+                    const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const uint32_t hi = lo | j;
+                    const bool up = (lo & k) == 0;
+                    const unsigned long long a = sElem[lo], c = sElem[hi];
+                    if ((a > c) == up) {
+                        sElem[lo] = c;
+                        sElem[hi] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = tid; i < count; i += kBucketThreads) {
+            const unsigned long long e = sElem[i];
+            keysOut[start + i] = (uint32_t)(e >> 32);
+            valsOut[start + i] = (uint32_t)e;
+        }
+        __syncthreads();
+    }
+}
+
+// identity payload + bucket counts for the sort test hooks (what mortonKernel does for a step's keys)
+__global__ void iotaCountKernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n,
+                                uint32_t* __restrict__ bucketCounts, int shift) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        vals[i] = i;
+        if (bucketCounts) atomicAdd(bucketCounts + (keys[i] >> shift), 1u);
+    }
 }
 
 // pseudo-random keys for the sort timing hook (splitmix-style hash of the index)

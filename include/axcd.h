@@ -147,6 +147,9 @@ typedef struct AxcdStats {
     uint32_t graphLaunched;     /* 1 if the last fused step was one CUDA graph launch: totalMs is then the
                                    only timing (per-stage times need the staged calls)               */
     uint32_t ghostBodies;       /* axcd_slab_step: ghost bodies received from the other ranks this step  */
+    uint32_t sortFallback;      /* 1 if the Morton bucket sort gave up (a bucket over its capacity: clustered scene)
+                                   and the LSD radix kernels sorted this step                             */
+    uint32_t sortMaxBucket;     /* largest Morton bucket of the step (capacity 1024)                        */
     float exchangeMs;           /* axcd_slab_step: owned refit + ghost selection + NCCL handshake and exchange
                                    + unpack, CUDA events on the context stream (includes the one host read) */
 } AxcdStats;
@@ -364,6 +367,13 @@ AXCD_API int32_t axcd_test_sort_keys64(AxcdContext* ctx, uint64_t* keys, uint32_
  * `iters` sorts (CUDA events on the context stream, inputs regenerated on the device each time). */
 AXCD_API int32_t axcd_test_sort_bench(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uint32_t iters,
                                       float* outMsPerSort);
+/* The step's own Morton sort (identity payload) on caller keys: mode 1 = bucket sort with the LSD fallback armed,
+ * mode 0 = LSD only.  *outFallback = 1 if the LSD kernels produced the result.  _bench_: device-resident timing
+ * on n pseudo-random keys, average ms per sort.                                                      */
+AXCD_API int32_t axcd_test_sort_morton(AxcdContext* ctx, const uint32_t* keys, uint32_t n, uint32_t keyBits,
+                                       uint32_t mode, uint32_t* outKeys, uint32_t* outVals, uint32_t* outFallback);
+AXCD_API int32_t axcd_test_sort_bench_morton(AxcdContext* ctx, uint32_t n, uint32_t keyBits, uint32_t iters,
+                                             uint32_t mode, float* outMsPerSort);
 /* Measured FP32 peak of the device: an FMA-chain kernel (8 independent chains per thread, `iters` x 128
  * FMAs per thread, 2048 threads per SM), best of three, in TFLOP/s.  The roof the GJK / EPA kernels are
  * reported against (BASELINE.md asks for a peak measured on the box, not the nominal one).        */

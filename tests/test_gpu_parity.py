@@ -584,3 +584,38 @@ def test_refit_mat4_route_matches_oracle_bit_for_bit():
     con, _, _ = O.narrowphase(s.xf, s.shapes, pairs, s.hull, nthreads=8)
     assert w.contacts().tobytes() == con.tobytes()
     w.close()
+
+
+# ------------------------------------------------------------------ the step's Morton sort ------
+@pytest.mark.parametrize("n", [4096, 100_000, 1_000_003])
+@pytest.mark.parametrize("bits", [12, 24, 30])
+def test_morton_bucket_sort_vs_numpy(n, bits):
+    """The step sorts (Morton key, body index) with one MSD bucket pass + per-bucket shared-memory sorts, and falls
+    back to the LSD radix kernels on the device when a bucket overflows.  Both must give the stable order."""
+    rng = np.random.default_rng(n + bits)
+    w = axcd.CollisionWorld(max(n, 16))
+    uniform = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
+    clustered = (rng.integers(0, 1 << min(bits, 10), n, dtype=np.uint64)).astype(np.uint32)    # top bits all zero: one bucket
+    few = np.repeat(rng.integers(0, 1 << bits, 7, dtype=np.uint64).astype(np.uint32), n // 7 + 1)[:n]   # 7 distinct keys
+    for keys, expect_fb in ((uniform, 0), (clustered, 1 if bits > 10 else None), (few, 1)):
+        order = np.argsort(keys, kind="stable")
+        for mode in (1, 0):
+            k2, v2, fb = w.test_sort_morton(keys, bits, mode)
+            assert np.array_equal(k2, keys[order]) and np.array_equal(v2, order.astype(np.uint32)), (mode, fb)
+            if mode == 0:
+                assert fb == 1
+            elif expect_fb is not None and bits >= 12 and n >= 100_000:
+                assert fb == expect_fb, (fb, expect_fb)
+    w.close()
+
+
+def test_clustered_scene_takes_the_sort_fallback_and_stays_exact():
+    """Most bodies piled into one corner of a huge scene box: the Morton keys collapse into a few buckets, the
+    bucket sort gives up on the device and the LSD kernels sort instead — same pairs, same contacts."""
+    s = axcd.config_scene("C1", scale=0.5)
+    s.xf[:, :3] *= np.float32(0.25)
+    s.xf[0, :3] = 4000.0          # one far outlier stretches the scene box
+    st, bitwise = run_and_compare(s, pairs_per_body=64)
+    assert bitwise and st.sortFallback == 1 and st.sortMaxBucket > 1024
+    st2, _ = run_and_compare(axcd.config_scene("C1", scale=0.5))
+    assert st2.sortFallback == 0 and 0 < st2.sortMaxBucket <= 1024

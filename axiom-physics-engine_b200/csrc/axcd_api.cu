@@ -134,7 +134,10 @@ struct AxcdContext {
     uint32_t* dBucketStarts = nullptr;
     uint32_t* dBucketCursors = nullptr;
     uint2* dBucketTmp = nullptr;
-    bool bucketSortOff = false;      // AXCD_NO_BUCKET_SORT=1: always the LSD radix sort
+    bool bucketSortOff = true;       // the bucket sort is opt-in (AXCD_BUCKET_SORT=1): measured slower than the LSD sort
+                                     // at 1 M keys so far (profiles/r02_experiments.md)
+    bool splitNarrow = false;        // AXCD_SPLIT_NARROW=1: classify + closed forms + slots as separate kernels even
+                                     // when the fused closed-form narrowphase applies (A/B measurements)
     Counters* dCtr = nullptr;
     Counters* dCtrBase = nullptr;    // two counter blocks: step k uses one, its refit kernel resets the other for step k+1
     int ctrParity = 0;
@@ -379,8 +382,10 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
     {
         const char* ng = getenv("AXCD_NO_GRAPH");
         if (ng && ng[0] == '1') ctx->graphsOff = true;
-        const char* nbs = getenv("AXCD_NO_BUCKET_SORT");
-        if (nbs && nbs[0] == '1') ctx->bucketSortOff = true;
+        const char* sn = getenv("AXCD_SPLIT_NARROW");
+        if (sn && sn[0] == '1') ctx->splitNarrow = true;
+        const char* nbs = getenv("AXCD_BUCKET_SORT");
+        if (nbs && nbs[0] == '1') ctx->bucketSortOff = false;
     }
     for (int i = 0; i < EV_COUNT; ++i) {
         ctx->ev[i] = nullptr;
@@ -555,6 +560,7 @@ int32_t axcd_refit(AxcdContext* ctx) {
     if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     recordEv(ctx, EV_START);
+    if (!ctx->capturing) ctx->lastStepGraph = false;   // a staged (or direct) step: per-stage events are recorded
     ctx->manifoldsValid = false;
     // temporal coherence: the skip decision reads the moved-body count of the LAST refit only.  If the
     // previous refit was never consumed by a broadphase, the bodies it moved are not in the cached pair
@@ -793,6 +799,17 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         const bool boxGeneric = p.boxBoxGeneric || p.wantDistances;
         const uint32_t genericMask = (1u << 5) | (boxGeneric ? (1u << 4) : 0u);
         const bool anyGeneric = ctx->hasGenericShapes || boxGeneric || ctx->slabOn || ctx->n != ctx->nOwned;
+        if (!anyGeneric && !ctx->dPairDist && !ctx->splitNarrow) {
+            // every pair is decided in closed form: classification, closed forms and in-order compaction in ONE kernel
+            const uint32_t fusedTilesMax = (mp + kFusedTile - 1) / kFusedTile;
+            const uint32_t fusedBlocks = fusedTilesMax < (uint32_t)ctx->numSMs * 3 ? fusedTilesMax : (uint32_t)ctx->numSMs * 3;
+            narrowClosedFusedKernel<<<fusedBlocks, kFusedThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dXf, ctx->dShapes,
+                                                                           ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlotStatus,
+                                                                           ctx->dCtr);
+            CU(cudaGetLastError());
+            recordEv(ctx, EV_GJK);
+            ctx->launches[2] = 1;
+        } else {
         classifyPairsKernel<<<classifyBlocksFor(mp), kClsThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dChunks,
                                                                             chunkCap, genericMask, ctx->dCtr);
         closedFormKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dFlags,
@@ -817,6 +834,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
             CU(cudaGetLastError());
         }
         ctx->launches[2] = anyGeneric ? 6 : 3;   // classify, closed forms, [GJK], slots, [EPA, EPA fallback]
+        }
     } else {
         recordEv(ctx, EV_GJK);
     }

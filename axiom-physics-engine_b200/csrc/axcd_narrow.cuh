@@ -1233,6 +1233,197 @@ closedFormKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ c
     }
 }
 
+// ---- the whole narrowphase in one pass, for scenes whose pairs are all decided in closed form ----------------
+// (spheres and boxes only: sphere-sphere, sphere-box, box-box by SAT — the headline, C3 and C4 scenes).  A tile of
+// 1024 canonical pairs per block trip:
+//   1. load the pairs (coalesced), classify them by the two shape types, counting-sort the tile's local indices by
+//      class in shared memory, so that every warp then works through class-homogeneous runs of 32;
+//   2. evaluate the closed forms; a contact's 40-byte record is parked in shared memory under its local index;
+//   3. scan the contact flags in pair order, chain the tile into the global order with a decoupled look-back
+//      (tiles are claimed by ticket, so every predecessor has started), and copy the records out contiguously:
+//      contacts come out in canonical pair order without per-pair flags, slots or staging records in HBM.
+// It replaces classifyPairsKernel + closedFormKernel + slotKernel (and the 40 B/pair tmp records between them).
+constexpr int kFusedThreads = 256;
+constexpr int kFusedItems = 4;
+constexpr int kFusedTile = kFusedThreads * kFusedItems;   // 1024 pairs
+constexpr int kFusedRecWords = 7;                          // position, normal, depth (ids come from the pair, status is 0)
+
+__global__ void __launch_bounds__(kFusedThreads, 3)
+narrowClosedFusedKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
+                        const uint8_t* __restrict__ type8, const float* __restrict__ xf, const uint4* __restrict__ shapes,
+                        AxcdContact* __restrict__ contacts, uint32_t maxContacts,
+                        volatile uint32_t* __restrict__ tileStatus, Counters* __restrict__ ctr) {
+    __shared__ float sRec[kFusedTile * kFusedRecWords];   // 28 KB: contact floats by local pair index
+    __shared__ uint2 sPair[kFusedTile];
+    __shared__ uint16_t sIdx[kFusedTile];                  // local indices, sorted by class
+    __shared__ __align__(16) uint8_t sFlag[kFusedTile];
+    __shared__ uint32_t sCnt[4], sBase[4];
+    __shared__ uint32_t sWarp[kFusedThreads / 32];
+    __shared__ uint32_t sTile, sSlotBase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t npairs = min(*pairCount, maxPairs);
+    while (true) {
+        __syncthreads();
+        if (tid == 0) sTile = atomicAdd(&ctr->gjkTicket, 1u);
+        if (tid < 4) sCnt[tid] = 0;
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if ((uint64_t)tile * kFusedTile >= npairs) break;
+        const uint32_t tileBase = tile * kFusedTile;
+        const uint32_t tileCount = min((uint32_t)kFusedTile, npairs - tileBase);
+        // ---- 1. load + classify + counting sort of the local indices by class (0 SS, 1 sphere-box either way, 2 BB) ---
+        int cls[kFusedItems];
+        uint32_t pos[kFusedItems];
+#pragma unroll
+        for (int j = 0; j < kFusedItems; ++j) {
+            const uint32_t li = j * kFusedThreads + tid;
+            cls[j] = -1;
+            if (li < tileCount) {
+                const uint2 pk = __ldg(pairs + tileBase + li);
+                sPair[li] = pk;
+                const uint32_t ta = __ldg(type8 + pk.x), tb = __ldg(type8 + pk.y);
+                cls[j] = (ta == AXCD_SHAPE_BOX ? 1 : 0) + (tb == AXCD_SHAPE_BOX ? 1 : 0);
+            }
+            sFlag[li] = 0;
+            const uint32_t peers = __match_any_sync(0xffffffffu, cls[j]);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader && cls[j] >= 0) base = atomicAdd(&sCnt[cls[j]], (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            pos[j] = base + __popc(peers & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            sBase[0] = 0;
+            sBase[1] = sCnt[0];
+            sBase[2] = sCnt[0] + sCnt[1];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kFusedItems; ++j)
+            if (cls[j] >= 0) sIdx[sBase[cls[j]] + pos[j]] = (uint16_t)(j * kFusedThreads + tid);
+        __syncthreads();
+        // ---- 2. the closed forms; warp w takes runs w, w + 8, ... of 32 sorted entries (classes interleave evenly) -----
+        for (uint32_t e = warp * 32 + lane; e < tileCount; e += kFusedThreads) {
+            const uint32_t li = sIdx[e];
+            const uint2 pk = sPair[li];
+            const uint32_t ia = pk.x, ib = pk.y;
+            const BodyPose ta = loadPose(xf, ia), tb = loadPose(xf, ib);
+            const uint4 sa = __ldg(shapes + ia), sb = __ldg(shapes + ib);
+            const V3 origin = ta.p;
+            bool contact = false;
+            V3 n = mk3(0.f, 0.f, 0.f), cpos = n;
+            float depth = 0.f;
+            if (sa.x == AXCD_SHAPE_SPHERE && sb.x == AXCD_SHAPE_SPHERE) {
+                const float ra = __uint_as_float(sa.y), rb = __uint_as_float(sb.y);
+                const V3 d = tb.p - origin;
+                const float len = sqrtf(dot3(d, d));
+                const float rs = ra + rb;
+                depth = rs - len;
+                if (depth >= 0.0f) {
+                    contact = true;
+                    n = (len > 0.0f) ? d * (1.0f / len) : mk3(1.0f, 0.0f, 0.0f);
+                    const V3 pa = n * ra;
+                    const V3 pb = d - n * rb;
+                    cpos = (pa + pb) * 0.5f + origin;
+                }
+            } else if (sa.x == AXCD_SHAPE_SPHERE) {
+                const SphereBox r = sphereBox(mk3(0.f, 0.f, 0.f), __uint_as_float(sa.y), tb.p - origin, tb, sb);
+                if (r.contact) {
+                    contact = true;
+                    depth = r.depth;
+                    n = r.nsx;
+                    cpos = (r.ps + r.px) * 0.5f + origin;
+                }
+            } else if (sb.x == AXCD_SHAPE_SPHERE) {
+                const SphereBox r = sphereBox(tb.p - origin, __uint_as_float(sb.y), mk3(0.f, 0.f, 0.f), ta, sa);
+                if (r.contact) {
+                    contact = true;
+                    depth = r.depth;
+                    n = -r.nsx;
+                    cpos = (r.px + r.ps) * 0.5f + origin;
+                }
+            } else {
+                const BoxBox r = boxBox(makeBoxFrame(ta, sa, origin), makeBoxFrame(tb, sb, origin));
+                if (r.contact) {
+                    contact = true;
+                    depth = r.depth;
+                    n = r.n;
+                    cpos = (r.pa + r.pb) * 0.5f + origin;
+                }
+            }
+            if (contact) {
+                sFlag[li] = 1;
+                float* o = sRec + li * kFusedRecWords;
+                o[0] = cpos.x; o[1] = cpos.y; o[2] = cpos.z;
+                o[3] = n.x; o[4] = n.y; o[5] = n.z;
+                o[6] = depth;
+            }
+        }
+        __syncthreads();
+        // ---- 3. contact slots in pair order: block scan + decoupled look-back over the tiles --------------------------
+        const uint32_t fl = *reinterpret_cast<const uint32_t*>(sFlag + tid * kFusedItems);   // 4 one-byte flags
+        const uint32_t sum = __popc(fl & 0x01010101u);
+        uint32_t inc = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) sWarp[warp] = inc;
+        __syncthreads();
+        uint32_t warpPrefix = 0, tileTotal = 0;
+#pragma unroll
+        for (int i = 0; i < kFusedThreads / 32; ++i) {
+            warpPrefix += (i < warp) ? sWarp[i] : 0u;
+            tileTotal += sWarp[i];
+        }
+        if (warp == 0) {
+            uint32_t excl = 0;
+            if (tile == 0) {
+                if (lane == 0) tileStatus[0] = kFlagInclusive | tileTotal;
+            } else {
+                if (lane == 0) tileStatus[tile] = kFlagAggregate | tileTotal;
+                int t = (int)tile - 1;
+                while (true) {
+                    const int idx = t - lane;
+                    uint32_t sv = kFlagInclusive;   // lanes before tile 0 act as an inclusive zero
+                    if (idx >= 0) {
+                        do { sv = tileStatus[idx]; } while ((sv & kFlagMask) == 0);
+                    }
+                    const uint32_t incMask = __ballot_sync(0xffffffffu, (sv & kFlagMask) == kFlagInclusive);
+                    const int firstInc = incMask ? (__ffs(incMask) - 1) : 32;
+                    uint32_t v = (lane <= firstInc) ? (sv & kValueMask) : 0u;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    excl += v;
+                    if (incMask) break;
+                    t -= 32;
+                }
+                if (lane == 0) tileStatus[tile] = kFlagInclusive | (excl + tileTotal);
+            }
+            if (lane == 0) {
+                sSlotBase = excl;
+                if ((uint64_t)(tile + 1) * kFusedTile >= npairs) ctr->contactCount = excl + tileTotal;   // last tile
+            }
+        }
+        __syncthreads();
+        uint32_t slot = sSlotBase + warpPrefix + inc - sum;
+#pragma unroll
+        for (int i = 0; i < kFusedItems; ++i) {
+            if ((fl >> (8 * i)) & 1u) {
+                if (slot < maxContacts) {
+                    const uint32_t li = tid * kFusedItems + i;
+                    const float* r = sRec + li * kFusedRecWords;
+                    const uint2 pk = sPair[li];
+                    storeContact(contacts + slot, pk.x, pk.y, mk3(r[0], r[1], r[2]), mk3(r[3], r[4], r[5]), r[6], 0u);
+                }
+                ++slot;
+            }
+        }
+    }
+}
+
 // The SAT as a call for gjkKernel (box-box reaches it only with AXCD_FLAG_PAIR_DISTANCES): keeps the
 // closed form's registers out of the GJK kernel's allocation.
 __device__ __noinline__ BoxBox boxBoxCall(const BodyPose& ta, uint4 sa, const BodyPose& tb, uint4 sb, V3 origin) {

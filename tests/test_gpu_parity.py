@@ -597,7 +597,7 @@ def test_morton_bucket_sort_vs_numpy(n, bits):
     uniform = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
     clustered = (rng.integers(0, 1 << min(bits, 10), n, dtype=np.uint64)).astype(np.uint32)    # top bits all zero: one bucket
     few = np.repeat(rng.integers(0, 1 << bits, 7, dtype=np.uint64).astype(np.uint32), n // 7 + 1)[:n]   # 7 distinct keys
-    for keys, expect_fb in ((uniform, 0), (clustered, 1 if bits > 10 else None), (few, 1)):
+    for keys, expect_fb in ((uniform, 0), (clustered, 1 if bits >= 24 else None), (few, 1)):
         order = np.argsort(keys, kind="stable")
         for mode in (1, 0):
             k2, v2, fb = w.test_sort_morton(keys, bits, mode)
@@ -612,10 +612,35 @@ def test_morton_bucket_sort_vs_numpy(n, bits):
 def test_clustered_scene_takes_the_sort_fallback_and_stays_exact():
     """Most bodies piled into one corner of a huge scene box: the Morton keys collapse into a few buckets, the
     bucket sort gives up on the device and the LSD kernels sort instead — same pairs, same contacts."""
-    s = axcd.config_scene("C1", scale=0.5)
-    s.xf[:, :3] *= np.float32(0.25)
-    s.xf[0, :3] = 4000.0          # one far outlier stretches the scene box
-    st, bitwise = run_and_compare(s, pairs_per_body=64)
-    assert bitwise and st.sortFallback == 1 and st.sortMaxBucket > 1024
-    st2, _ = run_and_compare(axcd.config_scene("C1", scale=0.5))
-    assert st2.sortFallback == 0 and 0 < st2.sortMaxBucket <= 1024
+    import os
+    os.environ["AXCD_BUCKET_SORT"] = "1"      # read at axcd_create
+    try:
+        s = axcd.config_scene("C1", scale=0.5)
+        s.xf[:, :3] *= np.float32(0.5)
+        s.xf[0, :3] = 4000.0          # one far outlier stretches the scene box
+        st, bitwise = run_and_compare(s, pairs_per_body=96)
+        assert bitwise and st.sortFallback == 1 and st.sortMaxBucket > 1024
+        st2, bitwise2 = run_and_compare(axcd.config_scene("C1", scale=0.5))
+        assert bitwise2 and st2.sortFallback == 0 and 0 < st2.sortMaxBucket <= 1024
+    finally:
+        del os.environ["AXCD_BUCKET_SORT"]
+
+
+def test_fused_closed_form_narrowphase_matches_the_split_kernels():
+    """Sphere / box scenes run the whole narrowphase in one kernel (classify + closed forms + in-order compaction);
+    AXCD_SPLIT_NARROW=1 keeps the three separate kernels.  Same contacts, byte for byte, same order."""
+    import os
+    s = axcd.config_scene("C1")
+    w1 = axcd.CollisionWorld.for_scene(s)
+    st1 = w1.step()
+    os.environ["AXCD_SPLIT_NARROW"] = "1"
+    try:
+        w2 = axcd.CollisionWorld.for_scene(s)
+    finally:
+        del os.environ["AXCD_SPLIT_NARROW"]
+    st2 = w2.step()
+    assert st1.kernelLaunches < st2.kernelLaunches
+    assert (st1.numPairs, st1.numContacts) == (st2.numPairs, st2.numContacts)
+    assert w1.contacts().tobytes() == w2.contacts().tobytes()
+    w1.close()
+    w2.close()

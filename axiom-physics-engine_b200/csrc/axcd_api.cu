@@ -136,6 +136,7 @@ struct AxcdContext {
     uint2* dBucketTmp = nullptr;
     bool bucketSortOff = true;       // the bucket sort is opt-in (AXCD_BUCKET_SORT=1): measured slower than the LSD sort
                                      // at 1 M keys so far (profiles/r02_experiments.md)
+    bool travInline = false;         // AXCD_TRAV_INLINE=1: the traversal kernel with inline leaf tests
     bool splitNarrow = false;        // AXCD_SPLIT_NARROW=1: classify + closed forms + slots as separate kernels even
                                      // when the fused closed-form narrowphase applies (A/B measurements)
     Counters* dCtr = nullptr;
@@ -382,6 +383,8 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
     {
         const char* ng = getenv("AXCD_NO_GRAPH");
         if (ng && ng[0] == '1') ctx->graphsOff = true;
+        const char* ti = getenv("AXCD_TRAV_INLINE");
+        if (ti && ti[0] == '1') ctx->travInline = true;
         const char* sn = getenv("AXCD_SPLIT_NARROW");
         if (sn && sn[0] == '1') ctx->splitNarrow = true;
         const char* nbs = getenv("AXCD_BUCKET_SORT");
@@ -721,12 +724,19 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         recordEv(ctx, EV_BUILD);
         // ---- traversal ---------------------------------------------------------------------------
         const uint32_t tb = (n + kTravThreads - 1) / kTravThreads;
-        findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes32, ctx->dSegLo, ctx->dSegHi,
-                                                     ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
-                                                     ctx->cfg.maxPairs, ctx->dBodyCount,
-                                                     SlabRule{ctx->slabOn ? 1 : 0, ctx->slabLo, ctx->slabHi, ctx->dBodyKeys},
-                                                     ctx->filtersOn ? ctx->dFilters : nullptr,
-                                                     ctx->awakeOn ? ctx->dAwake : nullptr, ctx->dCtr);
+        const SlabRule slabRule{ctx->slabOn ? 1 : 0, ctx->slabLo, ctx->slabHi, ctx->dBodyKeys};
+        if (ctx->travInline)   // AXCD_TRAV_INLINE=1: leaf tests inline in the walk (the round-1 kernel; A/B measurements)
+            findPairsKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes32, ctx->dSegLo, ctx->dSegHi,
+                                                         ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
+                                                         ctx->cfg.maxPairs, ctx->dBodyCount, slabRule,
+                                                         ctx->filtersOn ? ctx->dFilters : nullptr,
+                                                         ctx->awakeOn ? ctx->dAwake : nullptr, ctx->dCtr);
+        else
+            findPairsDenseKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes32, ctx->dSegLo, ctx->dSegHi,
+                                                              ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
+                                                              ctx->cfg.maxPairs, ctx->dBodyCount, slabRule,
+                                                              ctx->filtersOn ? ctx->dFilters : nullptr,
+                                                              ctx->awakeOn ? ctx->dAwake : nullptr, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIR);
         // ---- canonical order: counting sort by body a, then tiny per-body sorts by b ------------------

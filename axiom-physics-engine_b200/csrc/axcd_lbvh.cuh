@@ -495,6 +495,189 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
     }
 }
 
+// ---- traversal with deferred, dense leaf tests (the default) ----------------------------------------------------
+// Profile of the kernel above (ncu, headline scene): a third of its instructions belong to the leaf branch — load the
+// other leaf's float box, exact AABB::intersects, filter / sleep / slab rules, pool slot — and execute with ~3 of 32
+// lanes active, because in any given trip only a few lanes of a warp hit a leaf while the others wait.  Here a lane
+// that reaches a leaf only RECORDS the candidate (its own sorted index, the other leaf's) in a per-warp shared-memory
+// buffer (one warp-wide prefix sum per trip), and whenever 32 candidates have accumulated the warp tests them
+// densely, one per lane, with a ballot-aggregated append to the block's pair pool.  The internal-node walk is the
+// same two-nodes-in-flight loop; the candidate set and therefore the pair set are unchanged.
+constexpr int kCandCap = 32 + 32 * 4;   // leftover (< 32) + at most 4 new candidates per lane and trip
+
+__device__ __forceinline__ void testLeafCandidates(uint2 cand, bool valid, const float4* __restrict__ leafLo,
+                                                   const float4* __restrict__ leafHi, const SlabRule& slab,
+                                                   const uint4* __restrict__ filters, const uint8_t* __restrict__ awake,
+                                                   uint2* __restrict__ sPool, uint32_t* __restrict__ sCount,
+                                                   uint2* __restrict__ pairs, uint32_t maxPairs,
+                                                   uint32_t* __restrict__ bodyCount, Counters* __restrict__ ctr) {
+    const int lane = threadIdx.x & 31;
+    bool keep = false;
+    uint2 pr = make_uint2(0u, 0u);
+    if (valid) {
+        const float4 il = __ldg(leafLo + cand.x), ih = __ldg(leafHi + cand.x);
+        const float4 jl = __ldg(leafLo + cand.y), jh = __ldg(leafHi + cand.y);
+        // exact test on the leaves' own boxes (AABB::intersects, closed intervals)
+        keep = boxesIntersect(il.x, il.y, il.z, ih.x, ih.y, ih.z, jl.x, jl.y, jl.z, jh.x, jh.y, jh.z);
+        const uint32_t bodyI = __float_as_uint(il.w), bodyJ = __float_as_uint(jl.w);
+        pr = make_uint2(min(bodyI, bodyJ), max(bodyI, bodyJ));
+        if (keep && filters) keep = shouldCollide(filters, bodyI, bodyJ);
+        // sleeping bodies (debug::DebugRigidBody::isAwake, physics_debug_draw.hpp:123): a pair of two sleeping
+        // bodies is not a candidate
+        if (keep && awake) keep = (__ldg(awake + bodyI) | __ldg(awake + bodyJ)) != 0;
+        if (keep && slab.enabled) {
+            // one huge scene split into x-slabs: this rank reports the pair only if the left end of the pair's
+            // x-overlap, max(min_i.x, min_j.x), lies in its slab (exactly one rank does), and orients it by
+            // global id so both bodies play the same role as in a single-GPU run
+            const float xs = (il.x > jl.x) ? il.x : jl.x;
+            keep = xs >= slab.lo && xs < slab.hi;
+            if (keep && slab.keys[pr.x] > slab.keys[pr.y]) pr = make_uint2(pr.y, pr.x);
+        }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (!bal) return;
+    uint32_t base = 0;
+    if (lane == __ffs(bal) - 1) base = atomicAdd(sCount, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+    if (!keep) return;
+    const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+    if (slot < (uint32_t)kTravPool) {
+        sPool[slot] = pr;
+    } else {   // pool full: append directly
+        const uint32_t g = atomicAdd(&ctr->pairCount, 1u);
+        if (g < maxPairs) {
+            pairs[g] = pr;
+            atomicAdd(&bodyCount[pr.x], 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTravThreads)
+findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict__ leafHi,
+                     const Node32* __restrict__ nodes, const float4* __restrict__ segLo, const float4* __restrict__ segHi,
+                     const uint32_t* __restrict__ worldEnd, uint32_t n,
+                     uint2* __restrict__ pairs, uint32_t maxPairs, uint32_t* __restrict__ bodyCount,
+                     SlabRule slab, const uint4* __restrict__ filters, const uint8_t* __restrict__ awake,
+                     Counters* __restrict__ ctr) {
+    __shared__ uint2 sPool[kTravPool];
+    __shared__ uint2 sCand[kTravThreads / 32][kCandCap];
+    __shared__ uint32_t sCount, sBase;
+    if (threadIdx.x == 0) sCount = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * kTravThreads + threadIdx.x;
+    constexpr uint32_t kNone = 0xffffffffu;
+    constexpr int kWideStack = 2 * kTravStack;
+    uint32_t stackN[kWideStack], stackF[kWideStack];
+    int sp = 0;
+    uint32_t ni = 0, first = 0;
+    bool active = i < n && n >= 2;
+    uint32_t wEnd = 0, qxy = 0, qzX = 0, qYZ = 0;
+    if (active) {
+        const float4 lo = leafLo[i], hi = leafHi[i];
+        wEnd = worldEnd ? worldEnd[__float_as_uint(hi.w)] : n - 1;
+        const QuantFrame f = loadQuantFrame(segLo, segHi);
+        const float b[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+        packQuery(f, b, qxy, qzX, qYZ);
+    }
+    uint32_t cnt = 0;   // candidates waiting in this warp's buffer (warp-uniform)
+    while (__any_sync(0xffffffffu, active)) {
+        uint32_t cand[4] = {kNone, kNone, kNone, kNone};
+        if (active) {
+            const bool haveB = sp > 0;
+            uint32_t nb = ni, firstB = first;
+            if (haveB) {
+                --sp;
+                nb = stackN[sp];
+                firstB = stackF[sp];
+            }
+            const uint4* npA = reinterpret_cast<const uint4*>(nodes + ni);
+            const uint4* npB = reinterpret_cast<const uint4*>(nodes + nb);
+            const uint4 a0 = __ldg(npA), a1 = __ldg(npA + 1);
+            const uint4 b0 = __ldg(npB), b1 = __ldg(npB + 1);
+            uint32_t next = kNone, nextFirst = 0;
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const uint4 q0 = which ? b0 : a0, q1 = which ? b1 : a1;
+                const uint32_t fst = which ? firstB : first;
+                const uint32_t split = q1.z & kSplitMask, last = q1.w;
+                const bool on = which == 0 || haveB;
+                const bool hitL = on && split > i && fst <= wEnd && quantIntersect(qxy, qzX, qYZ, q0.x, q0.y, q0.z);
+                const bool hitR = on && last > i && split + 1 <= wEnd && quantIntersect(qxy, qzX, qYZ, q0.w, q1.x, q1.y);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const bool hit = c ? hitR : hitL;
+                    const bool leaf = (q1.z & (c ? kRightLeaf : kLeftLeaf)) != 0u;
+                    const uint32_t child = c ? split + 1 : split;
+                    if (hit && leaf) cand[which * 2 + c] = child;
+                    if (hit && !leaf) {
+                        const uint32_t cf = c ? child : fst;
+                        if (next == kNone) {
+                            next = child;
+                            nextFirst = cf;
+                        } else if (sp < kWideStack) {
+                            stackN[sp] = child;
+                            stackF[sp] = cf;
+                            ++sp;
+                        } else {
+                            atomicExch(&ctr->travOverflow, 1u);
+                        }
+                    }
+                }
+            }
+            if (next != kNone) {
+                ni = next;
+                first = nextFirst;
+            } else if (sp > 0) {
+                --sp;
+                ni = stackN[sp];
+                first = stackF[sp];
+            } else {
+                active = false;
+            }
+        }
+        // ---- append this trip's leaf candidates to the warp's buffer: one prefix sum over the lanes' counts --------
+        const uint32_t mine = (cand[0] != kNone) + (cand[1] != kNone) + (cand[2] != kNone) + (cand[3] != kNone);
+        if (__any_sync(0xffffffffu, mine != 0u)) {
+            uint32_t inc = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+            uint32_t at = cnt + inc - mine;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (cand[k] != kNone) sCand[warp][at++] = make_uint2(i, cand[k]);
+            cnt += total;
+            __syncwarp();
+            while (cnt >= 32u) {   // a full warp's worth: test them densely, one candidate per lane
+                cnt -= 32u;
+                testLeafCandidates(sCand[warp][cnt + lane], true, leafLo, leafHi, slab, filters, awake, sPool, &sCount, pairs,
+                                   maxPairs, bodyCount, ctr);
+            }
+            __syncwarp();
+        }
+    }
+    if (cnt) testLeafCandidates(sCand[warp][min(cnt - 1u, (uint32_t)lane)], (uint32_t)lane < cnt, leafLo, leafHi, slab, filters, awake,
+                                sPool, &sCount, pairs, maxPairs, bodyCount, ctr);
+    __syncthreads();
+    const uint32_t poolCnt = min(sCount, (uint32_t)kTravPool);
+    if (threadIdx.x == 0 && poolCnt) sBase = atomicAdd(&ctr->pairCount, poolCnt);
+    __syncthreads();
+    if (poolCnt) {
+        const uint32_t base = sBase;
+        for (uint32_t k = threadIdx.x; k < poolCnt; k += kTravThreads)
+            if (base + k < maxPairs) {
+                const uint2 pr = sPool[k];
+                pairs[base + k] = pr;
+                atomicAdd(&bodyCount[pr.x], 1u);
+            }
+    }
+}
+
 // ---- canonical pair order by counting sort ---------------------------------------------------------
 // bodyStart = exclusive scan of bodyCount (done with exclusiveScanKernel, which also writes the copy
 // that serves as the fill cursor).  scatterPairsKernel drops

@@ -812,7 +812,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         if (!anyGeneric && !ctx->dPairDist && !ctx->splitNarrow) {
             // every pair is decided in closed form: classification, closed forms and in-order compaction in ONE kernel
             const uint32_t fusedTilesMax = (mp + kFusedTile - 1) / kFusedTile;
-            const uint32_t fusedBlocks = fusedTilesMax < (uint32_t)ctx->numSMs * 3 ? fusedTilesMax : (uint32_t)ctx->numSMs * 3;
+            const uint32_t fusedBlocks = fusedTilesMax < (uint32_t)ctx->numSMs * AXCD_FUSED_MINBLOCKS ? fusedTilesMax : (uint32_t)ctx->numSMs * AXCD_FUSED_MINBLOCKS;
             narrowClosedFusedKernel<<<fusedBlocks, kFusedThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dXf, ctx->dShapes,
                                                                            ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlotStatus,
                                                                            ctx->dCtr);

@@ -1243,12 +1243,16 @@ closedFormKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ c
 //      (tiles are claimed by ticket, so every predecessor has started), and copy the records out contiguously:
 //      contacts come out in canonical pair order without per-pair flags, slots or staging records in HBM.
 // It replaces classifyPairsKernel + closedFormKernel + slotKernel (and the 40 B/pair tmp records between them).
-constexpr int kFusedThreads = 256;
+#ifndef AXCD_FUSED_THREADS
+#define AXCD_FUSED_THREADS 256
+#define AXCD_FUSED_MINBLOCKS 4   // 64 registers; sweep 256x3 / 256x4 / 128x6 / 128x8 / 64x12: 0.216 / 0.197 / 0.217 / 0.214 / 0.213 ms
+#endif
+constexpr int kFusedThreads = AXCD_FUSED_THREADS;
 constexpr int kFusedItems = 4;
 constexpr int kFusedTile = kFusedThreads * kFusedItems;   // 1024 pairs
 constexpr int kFusedRecWords = 7;                          // position, normal, depth (ids come from the pair, status is 0)
 
-__global__ void __launch_bounds__(kFusedThreads, 3)
+__global__ void __launch_bounds__(kFusedThreads, AXCD_FUSED_MINBLOCKS)
 narrowClosedFusedKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
                         const uint8_t* __restrict__ type8, const float* __restrict__ xf, const uint4* __restrict__ shapes,
                         AxcdContact* __restrict__ contacts, uint32_t maxContacts,

@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("AXCD_LIB") or os.path.join(PKG_DIR, "libaxcd.so")
 SCENE_LIB_PATH = os.path.join(PKG_DIR, "libaxcd_scene.so")
 
-SHAPE_SPHERE, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_PLANE, SHAPE_CONVEX, SHAPE_MESH = range(6)
+SHAPE_SPHERE, SHAPE_BOX, SHAPE_CAPSULE, SHAPE_PLANE, SHAPE_CONVEX, SHAPE_MESH, SHAPE_CYLINDER = range(7)
 FLAG_PAIR_DISTANCES = 1
 FLAG_TEMPORAL_COHERENCE = 4
 FLAG_BOXBOX_GJK_EPA = 8

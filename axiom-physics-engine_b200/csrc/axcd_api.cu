@@ -93,7 +93,8 @@ struct AxcdContext {
     BvhNode* dNodes = nullptr;       // float nodes for the scene queries: allocated and built by the first query after a broadphase
     bool queryNodesValid = false;
     bool hasHulls = false;           // any convex-hull shape in the current scene (ghosts are never hulls)
-    bool hasGenericShapes = false;   // any hull or capsule among the owned bodies: pairs that need GJK can exist
+    bool hasGenericShapes = false;   // any hull, capsule or cylinder among the owned bodies: pairs that need GJK can exist
+    bool hasSweptRayShapes = false;  // any hull or cylinder: ray casts against them run the conservative advancement
     uint32_t* dWorldEnd = nullptr;
     uint2* dPairsTmp = nullptr;      // candidate pairs as found (unordered)
     uint2* dPairs = nullptr;         // candidate pairs, canonical order
@@ -487,7 +488,7 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
     if (nHullVerts && !hullXYZ) return AXCD_ERR_NULL_POINTER;
     if (n > ctx->cfg.maxBodies || nHullVerts > ctx->cfg.maxHullVerts) return AXCD_ERR_OUT_OF_RANGE;
     if (ctx->cfg.numWorlds > 1 && n && !worldId) return AXCD_ERR_INVALID_PARAM;
-    bool anyHull = false, anyCapsule = false;
+    bool anyHull = false, anyCapsule = false, anyCylinder = false;
     for (uint32_t i = 0; i < n; ++i) {
         const AxcdShape& s = shapes[i];
         if (s.type == AXCD_SHAPE_CONVEX) {
@@ -496,10 +497,15 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
             memcpy(&first, &s.p0, 4);
             memcpy(&cnt, &s.p1, 4);
             if (cnt == 0 || cnt > 65535u || (uint64_t)first + cnt > nHullVerts) return AXCD_ERR_INVALID_SHAPE;
-        } else if (s.type != AXCD_SHAPE_SPHERE && s.type != AXCD_SHAPE_BOX && s.type != AXCD_SHAPE_CAPSULE) {
+        } else if (s.type != AXCD_SHAPE_SPHERE && s.type != AXCD_SHAPE_BOX && s.type != AXCD_SHAPE_CAPSULE &&
+                   s.type != AXCD_SHAPE_CYLINDER) {
             return AXCD_ERR_INVALID_SHAPE;   // Plane / Mesh are not in scope
         }
         if (s.type == AXCD_SHAPE_CAPSULE) anyCapsule = true;
+        if (s.type == AXCD_SHAPE_CYLINDER) {
+            anyCylinder = true;
+            if (!(s.p0 >= 0.0f && s.p0 < 3.0e38f && s.p1 >= 0.0f && s.p1 < 3.0e38f)) return AXCD_ERR_INVALID_SHAPE;
+        }
         // sizes must be finite and non-negative (a flat box or a zero radius is a valid degenerate shape)
         if (s.type == AXCD_SHAPE_SPHERE && !(s.p0 >= 0.0f && s.p0 < 3.0e38f)) return AXCD_ERR_INVALID_SHAPE;
         if (s.type == AXCD_SHAPE_BOX && !(s.p0 >= 0.0f && s.p0 < 3.0e38f && s.p1 >= 0.0f && s.p1 < 3.0e38f && s.p2 >= 0.0f && s.p2 < 3.0e38f))
@@ -508,7 +514,8 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
         if (ctx->cfg.numWorlds > 1 && worldId[i] >= ctx->cfg.numWorlds) return AXCD_ERR_OUT_OF_RANGE;
     }
     ctx->hasHulls = anyHull;
-    ctx->hasGenericShapes = anyHull || anyCapsule;
+    ctx->hasSweptRayShapes = anyHull || anyCylinder;
+    ctx->hasGenericShapes = anyHull || anyCapsule || anyCylinder;
     ctx->gen++;
     ctx->filtersOn = false;   // per-body filter words describe the previous body set: set them again
     if (ctx->awakeOn && ctx->dAwake) cudaMemsetAsync(ctx->dAwake, 1, ctx->cfg.maxBodies, ctx->stream);
@@ -1214,7 +1221,7 @@ int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRay
     p.wantDistances = 1u;
     p.boxBoxGeneric = 0u;
     const uint32_t rb = (nq + kQueryThreads - 1) / kQueryThreads;
-    if (ctx->hasHulls)
+    if (ctx->hasSweptRayShapes)
         raycastKernel<true><<<rb, kQueryThreads, 0, st>>>(T, static_cast<const float4*>(ctx->dQIn), nq, ctx->dXf, ctx->dShapes,
                                                           ctx->dHull, p, static_cast<uint32_t*>(ctx->dQOut));
     else
@@ -1350,7 +1357,7 @@ int32_t axcd_set_ghosts(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhosts, con
     ctx->pairsCached = false;
     for (uint32_t i = 0; i < nGhosts; ++i)
         if (shapes[i].type != AXCD_SHAPE_SPHERE && shapes[i].type != AXCD_SHAPE_BOX &&
-            shapes[i].type != AXCD_SHAPE_CAPSULE)
+            shapes[i].type != AXCD_SHAPE_CAPSULE && shapes[i].type != AXCD_SHAPE_CYLINDER)
             return AXCD_ERR_INVALID_SHAPE;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     cudaStream_t st = ctx->stream;

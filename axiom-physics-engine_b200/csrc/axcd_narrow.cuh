@@ -16,7 +16,7 @@
 
 namespace axcd {
 
-enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2, CORE_SEGMENT = 3 };
+enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2, CORE_SEGMENT = 3, CORE_CYLINDER = 4 };
 
 struct Core {
     int kind;
@@ -80,6 +80,15 @@ __device__ __forceinline__ Core makeCore(const BodyPose& t, uint4 sh, const floa
         quatToColumns(t.q, c0, c1, c2);
         k.e0 = c1 * ((p1 * 0.5f) * t.s.y);
         k.r = p0;
+    } else if (sh.x == AXCD_SHAPE_CYLINDER) {
+        // radial frame E0, E2 (rotation columns x / z scaled by scale * radius) and half axis E1 (column y scaled by
+        // scale.y * height / 2): a rim point is c +- E1 + E0 * cos + E2 * sin
+        k.kind = CORE_CYLINDER;
+        V3 c0, c1, c2;
+        quatToColumns(t.q, c0, c1, c2);
+        k.e0 = c0 * (t.s.x * p0);
+        k.e1 = c1 * (t.s.y * (p1 * 0.5f));
+        k.e2 = c2 * (t.s.z * p0);
     } else if (sh.x == AXCD_SHAPE_BOX) {
         k.kind = CORE_BOX;
         V3 c0, c1, c2;
@@ -97,12 +106,39 @@ __device__ __forceinline__ Core makeCore(const BodyPose& t, uint4 sh, const floa
     return k;
 }
 
+// Cylinder support.  The rim direction is quantised to 4 x 8192 directions (a 32768-gon inscribed in the rim: chord
+// error 5e-9 of the radius, below float resolution) so that a support point is named by 16 bits — sign of the E0
+// part, sign of the E2 part, 13 bits of the |E2 share| in the diamond parametrisation |u| + |w| = 1, cap sign —
+// and is rebuilt bit for bit from that id by cylinderPoint (same expression trees as oracle/axref.cpp).
+__device__ __forceinline__ uint32_t cylinderId(const Core& k, V3 d) {
+    const float a = dot3(d, k.e0), b = dot3(d, k.e2);
+    const float s = fabsf(a) + fabsf(b);
+    uint32_t m = 0;
+    if (s > 0.0f) {
+        const float w = fabsf(b) / s;
+        m = (uint32_t)(w * 8191.0f + 0.5f);
+        if (m > 8191u) m = 8191u;
+    }
+    return (!(a >= 0.0f) ? 1u : 0u) | (!(b >= 0.0f) ? 2u : 0u) | (m << 2) | (!(dot3(d, k.e1) >= 0.0f) ? 0x8000u : 0u);
+}
+__device__ __forceinline__ V3 cylinderPoint(const Core& k, uint32_t id) {
+    const float w = (float)((id >> 2) & 8191u) / 8191.0f, u = 1.0f - w;
+    const float inv = 1.0f / sqrtf(u * u + w * w);
+    const float fx = (id & 1u) ? -(u * inv) : (u * inv), fz = (id & 2u) ? -(w * inv) : (w * inv);
+    const V3 cap = (id & 0x8000u) ? -k.e1 : k.e1;
+    return ((k.e0 * fx + cap) + k.e2 * fz) + k.c;
+}
+
 // Support point of a core in world-aligned direction d (any length).  `id` names the chosen
 // vertex (box: one sign bit per axis, hull: vertex index) so the point can be rebuilt later with
 // pointFromId instead of being stored; both produce the same floats (same operation sequence).
 __device__ __forceinline__ V3 support(const Core& k, V3 d, uint32_t& id) {
     id = 0;
     if (k.kind == CORE_POINT) return k.c;
+    if (k.kind == CORE_CYLINDER) {
+        id = cylinderId(k, d);
+        return cylinderPoint(k, id);
+    }
     if (k.kind == CORE_SEGMENT) {
         const bool n0 = !(dot3(d, k.e0) >= 0.0f);
         id = n0 ? 1u : 0u;
@@ -136,6 +172,7 @@ __device__ __forceinline__ V3 support(const Core& k, V3 d, uint32_t& id) {
 
 __device__ __forceinline__ V3 pointFromId(const Core& k, uint32_t id) {
     if (k.kind == CORE_POINT) return k.c;
+    if (k.kind == CORE_CYLINDER) return cylinderPoint(k, id);
     if (k.kind == CORE_SEGMENT) return k.c + ((id & 1u) ? -k.e0 : k.e0);
     if (k.kind == CORE_BOX) {
         V3 p = k.c;
@@ -1013,8 +1050,8 @@ constexpr int kGjkThreads = AXCD_GJK_THREADS;
 // Pair class by core kinds, so that a warp runs one kind of support function.
 __device__ __forceinline__ int pairClass(uint32_t typeA, uint32_t typeB) {
     if (typeA == AXCD_SHAPE_CONVEX || typeB == AXCD_SHAPE_CONVEX || typeA == AXCD_SHAPE_CAPSULE ||
-        typeB == AXCD_SHAPE_CAPSULE)
-        return 5;   // hulls and capsules share the "other" class
+        typeB == AXCD_SHAPE_CAPSULE || typeA == AXCD_SHAPE_CYLINDER || typeB == AXCD_SHAPE_CYLINDER)
+        return 5;   // hulls, capsules and cylinders share the "other" class
     if (typeA == AXCD_SHAPE_SPHERE) return (typeB == AXCD_SHAPE_SPHERE) ? 1 : 2;   // SS, point-box
     return (typeB == AXCD_SHAPE_SPHERE) ? 3 : 4;                                   // box-point, box-box
 }

@@ -295,7 +295,7 @@ __device__ __forceinline__ void rayTestBody(uint32_t body, float tNear, V3 o, V3
     const uint4 sh = __ldg(shapes + body);
     const uint32_t flags = 0u;
     ShapeHit h;
-    if (!HULLS || sh.x != AXCD_SHAPE_CONVEX) h = rayShape(o, d, tMax, loadPose(xf, body), sh);
+    if (!HULLS || (sh.x != AXCD_SHAPE_CONVEX && sh.x != AXCD_SHAPE_CYLINDER)) h = rayShape(o, d, tMax, loadPose(xf, body), sh);
     else h = rayHull(o, d, tMax, loadPose(xf, body), sh, hull, cfg);
     if (!h.hit) return;
     const float t = (h.t > tNear) ? h.t : tNear;

@@ -127,6 +127,23 @@ __device__ __forceinline__ void fitBody(V3 pos, float4 q, V3 scl, uint4 sh, cons
         expandPoint(lo, hi, end);
         lo = lo - mk3(p0, p0, p0);
         hi = hi + mk3(p0, p0, p0);
+    } else if (sh.x == AXCD_SHAPE_CYLINDER) {
+        // p0 = radius, p1 = height, local Y axis.  Exact box of the scaled cylinder: along world axis k the half
+        // extent is the support distance h/2 * |l.y| + r * |(l.x, l.z)| of the local direction l = scale * (R^T e_k)
+        const float qxx = q.x * q.x, qyy = q.y * q.y, qzz = q.z * q.z;
+        const float qxz = q.x * q.z, qxy = q.x * q.y, qyz = q.y * q.z;
+        const float qwx = q.w * q.x, qwy = q.w * q.y, qwz = q.w * q.z;
+        const float cx[3] = {1.0f - 2.0f * (qyy + qzz), 2.0f * (qxy + qwz), 2.0f * (qxz - qwy)};
+        const float cy[3] = {2.0f * (qxy - qwz), 1.0f - 2.0f * (qxx + qzz), 2.0f * (qyz + qwx)};
+        const float cz[3] = {2.0f * (qxz + qwy), 2.0f * (qyz - qwx), 1.0f - 2.0f * (qxx + qyy)};
+        float ext[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float lx = cx[k] * scl.x, ly = cy[k] * scl.y, lz = cz[k] * scl.z;
+            ext[k] = (p1 * 0.5f) * fabsf(ly) + p0 * sqrtf(lx * lx + lz * lz);
+        }
+        lo = pos - mk3(ext[0], ext[1], ext[2]);
+        hi = pos + mk3(ext[0], ext[1], ext[2]);
     } else {   // AXCD_SHAPE_CONVEX (validated on the host): min/max over transformPoint(v_i)
         const uint32_t first = sh.y, count = sh.z;
         float4 v = __ldg(hull + first);

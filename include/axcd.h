@@ -53,15 +53,21 @@ enum {
 };
 
 /* ---- shape types: numeric order of debug::ShapeType (include/axiom/debug/physics_debug_draw.hpp:87-94)
- * Sphere, Box, Capsule and Convex are in scope; Plane/Mesh -> AXCD_ERR_INVALID_SHAPE.            */
+ * Sphere, Box, Capsule, Convex and Cylinder are in scope; Plane/Mesh -> AXCD_ERR_INVALID_SHAPE.  */
 enum { AXCD_SHAPE_SPHERE = 0, AXCD_SHAPE_BOX = 1, AXCD_SHAPE_CAPSULE = 2, AXCD_SHAPE_PLANE = 3,
-       AXCD_SHAPE_CONVEX = 4, AXCD_SHAPE_MESH = 5 };
+       AXCD_SHAPE_CONVEX = 4, AXCD_SHAPE_MESH = 5,
+       /* gui::ShapeType::Cylinder (include/axiom/gui/body_inspector.hpp:24).  debug::ShapeType has no cylinder, so
+        * the value lies past that enum's range.                                                          */
+       AXCD_SHAPE_CYLINDER = 6 };
 
 /* Flattened debug::DebugShape (physics_debug_draw.hpp:97-112): 16-byte POD.
  *   Sphere : p0 = radius                                  (DebugShape::radius)
  *   Box    : p0,p1,p2 = halfExtents.x/y/z                  (DebugShape::halfExtents)
  *   Capsule: p0 = radius, p1 = height of the segment between the cap centres, local Y axis
  *            (DebugShape::radius / height; src/debug/physics_debug_draw.cpp:254-266)
+ *   Cylinder: p0 = radius, p1 = height, local Y axis like the capsule; placed by Transform::transformPoint, so a
+ *            non-uniform scale gives an elliptic cylinder.  The rim is resolved to 32768 directions (5e-9 of
+ *            the radius, below float resolution).
  *   Convex : p0 = bit pattern of uint32 firstVertex, p1 = bit pattern of uint32 vertexCount,
  *            indexing the xyz-packed hull vertex pool (DebugShape::vertices / vertexCount,
  *            src/debug/physics_debug_draw.cpp:285-288).                                         */

@@ -181,7 +181,7 @@ struct Rng {
     float nextFloat() { return static_cast<float>(next()) / static_cast<float>(0x100000000ULL); }
 };
 
-enum { SHAPE_SPHERE = 0, SHAPE_BOX = 1, SHAPE_CAPSULE = 2, SHAPE_CONVEX = 4 };
+enum { SHAPE_SPHERE = 0, SHAPE_BOX = 1, SHAPE_CAPSULE = 2, SHAPE_CONVEX = 4, SHAPE_CYLINDER = 6 };
 
 inline uint32_t fbits(float f) {
     uint32_t u;
@@ -267,6 +267,20 @@ int refitOne(const Xf& t, const AxrefShape& s, const float* hull, uint32_t nHull
         V3 r = mk(s.p0, s.p0, s.p0);
         b.lo = b.lo - r;
         b.hi = b.hi + r;
+    } else if (s.type == SHAPE_CYLINDER) {
+        // gui::ShapeType::Cylinder (include/axiom/gui/body_inspector.hpp:24): p0 = radius, p1 = height, local Y axis
+        // like the capsule (src/debug/physics_debug_draw.cpp:254-266), placed by transformPoint (scale, rotate,
+        // translate).  Exact box of the scaled cylinder: along world axis k the half extent is the support
+        // distance h/2 * |l.y| + r * |(l.x, l.z)| of the local direction l = scale * (R^T e_k).
+        M3 m = quatToMat3(t.q);
+        const float cx[3] = {m.c0.x, m.c0.y, m.c0.z}, cy[3] = {m.c1.x, m.c1.y, m.c1.z}, cz[3] = {m.c2.x, m.c2.y, m.c2.z};
+        float ext[3];
+        for (int k = 0; k < 3; ++k) {
+            const float lx = cx[k] * t.s.x, ly = cy[k] * t.s.y, lz = cz[k] * t.s.z;
+            ext[k] = (s.p1 * 0.5f) * std::fabs(ly) + s.p0 * std::sqrt(lx * lx + lz * lz);
+        }
+        b.lo = t.p - mk(ext[0], ext[1], ext[2]);
+        b.hi = t.p + mk(ext[0], ext[1], ext[2]);
     } else if (s.type == SHAPE_CONVEX) {
         uint32_t first = fbits(s.p0), cnt = fbits(s.p1);
         if (cnt == 0 || static_cast<uint64_t>(first) + cnt > nHull) return 300;
@@ -293,7 +307,7 @@ int refitOne(const Xf& t, const AxrefShape& s, const float* hull, uint32_t nHull
 // Stage 3: narrowphase.  Convex "cores" in a frame translated so body A's position is the origin
 // (axes stay world-aligned).  Sphere = point core + radius margin; box and hull have no margin.
 // ------------------------------------------------------------------------------------------
-enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2, CORE_SEGMENT = 3 };
+enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2, CORE_SEGMENT = 3, CORE_CYLINDER = 4 };
 struct Core {
     int kind;
     V3 c;            // centre relative to A's position
@@ -317,6 +331,14 @@ Core makeCore(const Xf& t, const AxrefShape& sh, const float* hull, V3 origin) {
         M3 m = quatToMat3(t.q);
         k.e0 = m.c1 * ((sh.p1 * 0.5f) * t.s.y);
         k.r = sh.p0;
+    } else if (sh.type == SHAPE_CYLINDER) {
+        // radial frame E0, E2 (rotation columns x / z scaled by scale * radius) and half axis E1 (column y scaled by
+        // scale.y * height / 2): a rim point is c +- E1 + E0 * cos + E2 * sin
+        k.kind = CORE_CYLINDER;
+        M3 m = quatToMat3(t.q);
+        k.e0 = m.c0 * (t.s.x * sh.p0);
+        k.e1 = m.c1 * (t.s.y * (sh.p1 * 0.5f));
+        k.e2 = m.c2 * (t.s.z * sh.p0);
     } else if (sh.type == SHAPE_BOX) {
         k.kind = CORE_BOX;
         M3 m = quatToMat3(t.q);
@@ -334,9 +356,33 @@ Core makeCore(const Xf& t, const AxrefShape& sh, const float* hull, V3 origin) {
     return k;
 }
 
+// Cylinder support.  The rim direction is quantised to 4 x 8192 directions (a 32768-gon inscribed in the rim:
+// chord error 5e-9 of the radius, below float resolution) so that a support point is named by 16 bits — sign of
+// the E0 part, sign of the E2 part, 13 bits of |E2 share| in the diamond parametrisation |u| + |w| = 1, cap sign
+// — and can be rebuilt bit for bit from that id (the CUDA path keeps ids, not points, in its polytopes).
+inline uint32_t cylinderId(const Core& k, V3 d) {
+    const float a = dot(d, k.e0), b = dot(d, k.e2);
+    const float s = std::fabs(a) + std::fabs(b);
+    uint32_t m = 0;
+    if (s > 0.0f) {
+        const float w = std::fabs(b) / s;
+        m = (uint32_t)(w * 8191.0f + 0.5f);
+        if (m > 8191u) m = 8191u;
+    }
+    return (!(a >= 0.0f) ? 1u : 0u) | (!(b >= 0.0f) ? 2u : 0u) | (m << 2) | (!(dot(d, k.e1) >= 0.0f) ? 0x8000u : 0u);
+}
+inline V3 cylinderPoint(const Core& k, uint32_t id) {
+    const float w = (float)((id >> 2) & 8191u) / 8191.0f, u = 1.0f - w;
+    const float inv = 1.0f / std::sqrt(u * u + w * w);
+    const float fx = (id & 1u) ? -(u * inv) : (u * inv), fz = (id & 2u) ? -(w * inv) : (w * inv);
+    const V3 cap = (id & 0x8000u) ? -k.e1 : k.e1;
+    return ((k.e0 * fx + cap) + k.e2 * fz) + k.c;
+}
+
 // Support point of a core in world-aligned direction d (need not be unit length).
 V3 support(const Core& k, V3 d) {
     if (k.kind == CORE_POINT) return k.c;
+    if (k.kind == CORE_CYLINDER) return cylinderPoint(k, cylinderId(k, d));
     if (k.kind == CORE_SEGMENT) return k.c + ((dot(d, k.e0) >= 0.0f) ? k.e0 : -k.e0);
     if (k.kind == CORE_BOX) {
         V3 p = k.c;
@@ -1942,7 +1988,7 @@ int32_t axref_raycast(const float* xf, const AxrefShape* shapes, const float* hu
                 if (!raySlab(o, d, aabb + 6ull * i, aabb + 6ull * i + 3, r.tMax, &tNear)) continue;
                 ShapeHit h;
                 const uint32_t flags = 0u;
-                if (shapes[i].type != SHAPE_CONVEX) h = rayShape(o, d, r.tMax, loadXf(xf + 10ull * i), shapes[i]);
+                if (shapes[i].type != SHAPE_CONVEX && shapes[i].type != SHAPE_CYLINDER) h = rayShape(o, d, r.tMax, loadXf(xf + 10ull * i), shapes[i]);
                 else h = rayHull(o, d, r.tMax, loadXf(xf + 10ull * i), shapes[i], hullXYZ, cfg);
                 if (!h.hit) continue;
                 const float t = (h.t > tNear) ? h.t : tNear;

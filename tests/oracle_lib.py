@@ -282,6 +282,10 @@ def capsule(r, height):
     return (2, r, height, 0.0)
 
 
+def cylinder(r, height):
+    return (6, r, height, 0.0)
+
+
 def hull_shape(first, count):
     return (4, np.array([first], np.uint32).view(np.float32)[0],
             np.array([count], np.uint32).view(np.float32)[0], 0.0)

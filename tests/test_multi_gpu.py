@@ -54,10 +54,25 @@ def _run_ranks(size, scene_name, scale, steps=4):
     procs = [ctx.Process(target=_worker, args=(r, size, port, scene_name, scale, steps, q)) for r in range(size)]
     for p in procs:
         p.start()
+    # read the result BEFORE joining: rank 0 blocks in put() until the (large) payload has been drained
+    import time
+    deadline = time.time() + 240
+    result = None
+    while time.time() < deadline:
+        if not q.empty():
+            result = q.get()
+            break
+        if any(p.exitcode not in (None, 0) for p in procs):
+            break
+        time.sleep(0.2)
     for p in procs:
-        p.join(timeout=600)
+        p.join(timeout=30)
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+    assert result is not None, ("no result from the ranks", [p.exitcode for p in procs])
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    return q.get()
+    return result
 
 
 @pytest.mark.parametrize("size", [2, 4])

@@ -94,6 +94,7 @@ struct AxcdContext {
     bool queryNodesValid = false;
     bool hasHulls = false;           // any convex-hull shape in the current scene (ghosts are never hulls)
     bool hasGenericShapes = false;   // any hull, capsule or cylinder among the owned bodies: pairs that need GJK can exist
+    bool hasCylinders = false;       // any cylinder among the owned bodies: the cylinder-capable kernel instantiations run
     bool hasSweptRayShapes = false;  // any hull or cylinder: ray casts against them run the conservative advancement
     uint32_t* dWorldEnd = nullptr;
     uint2* dPairsTmp = nullptr;      // candidate pairs as found (unordered)
@@ -442,7 +443,8 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dFlags, np + kSlotTile));
         CU(dalloc(&ctx->dSlots, np));
         CU(dalloc(&ctx->dTmpContacts, np));
-        CU(cudaFuncSetAttribute(epaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaSmemBytes));
+        CU(cudaFuncSetAttribute(epaKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaSmemBytes));
+        CU(cudaFuncSetAttribute(epaKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEpaSmemBytes));
         CU(dalloc(&ctx->dContacts, (size_t)cfg->maxContacts));
         if (cfg->flags & AXCD_FLAG_PAIR_DISTANCES) CU(dalloc(&ctx->dPairDist, np));
         CU(dalloc(&ctx->dSortHist, (size_t)kMaxPasses * kRadix));
@@ -515,6 +517,7 @@ int32_t axcd_set_shapes(AxcdContext* ctx, const AxcdShape* shapes, uint32_t n, c
     }
     ctx->hasHulls = anyHull;
     ctx->hasSweptRayShapes = anyHull || anyCylinder;
+    ctx->hasCylinders = anyCylinder;
     ctx->hasGenericShapes = anyHull || anyCapsule || anyCylinder;
     ctx->gen++;
     ctx->filtersOn = false;   // per-body filter words describe the previous body set: set them again
@@ -831,23 +834,39 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
                                                                             chunkCap, genericMask, ctx->dCtr);
         closedFormKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dFlags,
                                                         ctx->dTmpContacts, ctx->dPairDist, ctx->dCtr);
-        if (anyGeneric)
-            gjkKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dHull, p,
-                                                     ctx->dFlags, ctx->dTmpContacts, q, ctx->cfg.maxContacts,
-                                                     ctx->dPairDist, ctx->dCtr);
+        // cylinder-capable instantiations only where a cylinder can occur (ghost bodies of a slab may be cylinders)
+        const bool cyl = ctx->hasCylinders || ctx->slabOn || ctx->n != ctx->nOwned;
+        if (anyGeneric) {
+            if (cyl)
+                gjkKernel<true><<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+                                                               ctx->dFlags, ctx->dTmpContacts, q, ctx->cfg.maxContacts,
+                                                               ctx->dPairDist, ctx->dCtr);
+            else
+                gjkKernel<false><<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dHull, p,
+                                                                ctx->dFlags, ctx->dTmpContacts, q, ctx->cfg.maxContacts,
+                                                                ctx->dPairDist, ctx->dCtr);
+        }
         slotKernel<<<slotBlocks, kSlotThreads, 0, st>>>(ctx->dFlags, pairCount, mp, ctx->dTmpContacts, ctx->dContacts,
                                                         ctx->cfg.maxContacts, ctx->dSlots, ctx->dSlotStatus, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_GJK);
         // EPA: persistent grids, queue lengths are read on the device
         if (anyGeneric) {
-            epaKernel<<<ctx->numSMs * kEpaBlocksPerSM, kEpaThreads, kEpaSmemBytes, st>>>(q, ctx->cfg.maxContacts, pairs, ctx->dXf,
-                                                                       ctx->dShapes, ctx->dHull, p, ctx->dContacts,
-                                                                       ctx->cfg.maxContacts, ctx->dSlots,
-                                                                       ctx->dPairDist, ctx->dCtr);
-            epaWarpFallbackKernel<<<ctx->numSMs * kWarpFbBlocksPerSM, kWarpFbThreads, 0, st>>>(q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p,
-                                                                          ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
-                                                                          ctx->dPairDist, ctx->dCtr);
+            if (cyl) {
+                epaKernel<true><<<ctx->numSMs * kEpaBlocksPerSM, kEpaThreads, kEpaSmemBytes, st>>>(
+                    q, ctx->cfg.maxContacts, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts,
+                    ctx->dSlots, ctx->dPairDist, ctx->dCtr);
+                epaWarpFallbackKernel<true><<<ctx->numSMs * kWarpFbBlocksPerSM, kWarpFbThreads, 0, st>>>(
+                    q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
+                    ctx->dPairDist, ctx->dCtr);
+            } else {
+                epaKernel<false><<<ctx->numSMs * kEpaBlocksPerSM, kEpaThreads, kEpaSmemBytes, st>>>(
+                    q, ctx->cfg.maxContacts, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts,
+                    ctx->dSlots, ctx->dPairDist, ctx->dCtr);
+                epaWarpFallbackKernel<false><<<ctx->numSMs * kWarpFbBlocksPerSM, kWarpFbThreads, 0, st>>>(
+                    q, pairs, ctx->dXf, ctx->dShapes, ctx->dHull, p, ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlots,
+                    ctx->dPairDist, ctx->dCtr);
+            }
             CU(cudaGetLastError());
         }
         ctx->launches[2] = anyGeneric ? 6 : 3;   // classify, closed forms, [GJK], slots, [EPA, EPA fallback]
@@ -1259,8 +1278,12 @@ int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs
     p.epaTol = ctx->cfg.epaTol;
     p.wantDistances = 1u;
     p.boxBoxGeneric = 0u;
-    ccdKernel<<<(npairs + kCcdThreads - 1) / kCcdThreads, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull,
-                                                                               dDisp, p, static_cast<uint32_t*>(ctx->dQOut));
+    if (ctx->hasCylinders || ctx->n != ctx->nOwned)
+        ccdKernel<true><<<(npairs + kCcdThreads - 1) / kCcdThreads, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull,
+                                                                                         dDisp, p, static_cast<uint32_t*>(ctx->dQOut));
+    else
+        ccdKernel<false><<<(npairs + kCcdThreads - 1) / kCcdThreads, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull,
+                                                                                          dDisp, p, static_cast<uint32_t*>(ctx->dQOut));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, ctx->dQOut, (size_t)npairs * sizeof(AxcdSweep), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

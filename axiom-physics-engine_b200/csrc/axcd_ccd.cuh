@@ -22,7 +22,8 @@ struct SweepResult {
 };
 
 // Conservative advancement of core B (moved by D * t, t in [0,1]) against the fixed core A.
-__device__ __forceinline__ SweepResult sweepCores(const Core& A, Core B, V3 D, NarrowParams cfg) {
+template <bool CYL>
+__device__ __forceinline__ SweepResult sweepCores(const CoreT<CYL>& A, CoreT<CYL> B, V3 D, NarrowParams cfg) {
     cfg.wantDistances = 1u;
     const V3 c0 = B.c;
     const float rs = A.r + B.r;
@@ -66,6 +67,7 @@ __device__ __forceinline__ SweepResult sweepCores(const Core& A, Core B, V3 D, N
     return out;
 }
 
+template <bool CYL>
 __global__ void __launch_bounds__(kCcdThreads)
 ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restrict__ xf, const uint4* __restrict__ shapes,
           const float4* __restrict__ hull, const float* __restrict__ disp, NarrowParams cfg, uint32_t* __restrict__ out) {
@@ -76,7 +78,7 @@ ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restr
     const V3 origin = ta.p;
     const V3 dA = mk3(__ldg(disp + 3 * (size_t)pr.x), __ldg(disp + 3 * (size_t)pr.x + 1), __ldg(disp + 3 * (size_t)pr.x + 2));
     const V3 dB = mk3(__ldg(disp + 3 * (size_t)pr.y), __ldg(disp + 3 * (size_t)pr.y + 1), __ldg(disp + 3 * (size_t)pr.y + 2));
-    const SweepResult r = sweepCores(makeCore(ta, __ldg(shapes + pr.x), hull, origin), makeCore(tb, __ldg(shapes + pr.y), hull, origin),
+    const SweepResult r = sweepCores(makeCore<CYL>(ta, __ldg(shapes + pr.x), hull, origin), makeCore<CYL>(tb, __ldg(shapes + pr.y), hull, origin),
                                      dB - dA, cfg);
     uint32_t* o = out + (size_t)k * 6;
     o[0] = r.hit;

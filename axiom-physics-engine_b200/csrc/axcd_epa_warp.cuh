@@ -53,6 +53,7 @@ __device__ __forceinline__ void warpPlane(const WarpPoly& e, int i0, int i1, int
     F.d[j] = dot3(n, p0);
 }
 
+template <bool CYL>
 __global__ void __launch_bounds__(kWarpFbThreads, AXCD_WARPFB_BLOCKS)
 epaWarpFallbackKernel(NarrowQueues q, const uint2* __restrict__ pairs, const float* __restrict__ xf,
                       const uint4* __restrict__ shapes, const float4* __restrict__ hull, NarrowParams cfg,
@@ -73,7 +74,7 @@ epaWarpFallbackKernel(NarrowQueues q, const uint2* __restrict__ pairs, const flo
         if (lane == 0) item = atomicAdd(&ctr->fallbackCursor, 1u);
         item = __shfl_sync(kFull, item, 0);
         if (item >= count) break;
-        EpaLane L;
+        EpaLaneT<CYL> L;
         EpaState<WarpPoly::Mask> st;
         EpaResult r;
         WarpFaces F;

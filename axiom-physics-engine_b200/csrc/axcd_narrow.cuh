@@ -18,7 +18,12 @@ namespace axcd {
 
 enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2, CORE_SEGMENT = 3, CORE_CYLINDER = 4 };
 
-struct Core {
+// CYL: whether cylinder cores can occur.  Scenes without cylinders instantiate every GJK / EPA kernel with
+// CYL = false, so the cylinder's support code (two divisions and a square root per call) costs them nothing —
+// inlined, or even as an out-of-line call, it cost the hull-mix scene C2 8 % of its step.
+template <bool CYL>
+struct CoreT {
+    static constexpr bool kCyl = CYL;
     int kind;
     V3 c;            // centre relative to A's position
     V3 e0, e1, e2;   // box: rotation columns * (halfExtent*scale); hull: rotation columns
@@ -61,8 +66,11 @@ __device__ __forceinline__ void quatToColumns(float4 q, V3& c0, V3& c1, V3& c2) 
     c2 = mk3(2.0f * (qxz + qwy), 2.0f * (qyz - qwx), 1.0f - 2.0f * (qxx + qyy));
 }
 
-__device__ __forceinline__ Core makeCore(const BodyPose& t, uint4 sh, const float4* __restrict__ hull, V3 origin) {
-    Core k;
+using Core = CoreT<false>;
+
+template <bool CYL = false>
+__device__ __forceinline__ CoreT<CYL> makeCore(const BodyPose& t, uint4 sh, const float4* __restrict__ hull, V3 origin) {
+    CoreT<CYL> k;
     k.c = t.p - origin;
     k.r = 0.0f;
     k.verts = nullptr;
@@ -80,7 +88,7 @@ __device__ __forceinline__ Core makeCore(const BodyPose& t, uint4 sh, const floa
         quatToColumns(t.q, c0, c1, c2);
         k.e0 = c1 * ((p1 * 0.5f) * t.s.y);
         k.r = p0;
-    } else if (sh.x == AXCD_SHAPE_CYLINDER) {
+    } else if (CYL && sh.x == AXCD_SHAPE_CYLINDER) {
         // radial frame E0, E2 (rotation columns x / z scaled by scale * radius) and half axis E1 (column y scaled by
         // scale.y * height / 2): a rim point is c +- E1 + E0 * cos + E2 * sin
         k.kind = CORE_CYLINDER;
@@ -110,7 +118,8 @@ __device__ __forceinline__ Core makeCore(const BodyPose& t, uint4 sh, const floa
 // error 5e-9 of the radius, below float resolution) so that a support point is named by 16 bits — sign of the E0
 // part, sign of the E2 part, 13 bits of the |E2 share| in the diamond parametrisation |u| + |w| = 1, cap sign —
 // and is rebuilt bit for bit from that id by cylinderPoint (same expression trees as oracle/axref.cpp).
-__device__ __forceinline__ uint32_t cylinderId(const Core& k, V3 d) {
+template <bool CYL>
+__device__ __forceinline__ uint32_t cylinderId(const CoreT<CYL>& k, V3 d) {
     const float a = dot3(d, k.e0), b = dot3(d, k.e2);
     const float s = fabsf(a) + fabsf(b);
     uint32_t m = 0;
@@ -121,7 +130,8 @@ __device__ __forceinline__ uint32_t cylinderId(const Core& k, V3 d) {
     }
     return (!(a >= 0.0f) ? 1u : 0u) | (!(b >= 0.0f) ? 2u : 0u) | (m << 2) | (!(dot3(d, k.e1) >= 0.0f) ? 0x8000u : 0u);
 }
-__device__ __forceinline__ V3 cylinderPoint(const Core& k, uint32_t id) {
+template <bool CYL>
+__device__ __forceinline__ V3 cylinderPoint(const CoreT<CYL>& k, uint32_t id) {
     const float w = (float)((id >> 2) & 8191u) / 8191.0f, u = 1.0f - w;
     const float inv = 1.0f / sqrtf(u * u + w * w);
     const float fx = (id & 1u) ? -(u * inv) : (u * inv), fz = (id & 2u) ? -(w * inv) : (w * inv);
@@ -132,10 +142,11 @@ __device__ __forceinline__ V3 cylinderPoint(const Core& k, uint32_t id) {
 // Support point of a core in world-aligned direction d (any length).  `id` names the chosen
 // vertex (box: one sign bit per axis, hull: vertex index) so the point can be rebuilt later with
 // pointFromId instead of being stored; both produce the same floats (same operation sequence).
-__device__ __forceinline__ V3 support(const Core& k, V3 d, uint32_t& id) {
+template <bool CYL>
+__device__ __forceinline__ V3 support(const CoreT<CYL>& k, V3 d, uint32_t& id) {
     id = 0;
     if (k.kind == CORE_POINT) return k.c;
-    if (k.kind == CORE_CYLINDER) {
+    if (CYL && k.kind == CORE_CYLINDER) {
         id = cylinderId(k, d);
         return cylinderPoint(k, id);
     }
@@ -170,9 +181,10 @@ __device__ __forceinline__ V3 support(const Core& k, V3 d, uint32_t& id) {
     return ((k.e0 * lv.x + k.e1 * lv.y) + k.e2 * lv.z) + k.c;
 }
 
-__device__ __forceinline__ V3 pointFromId(const Core& k, uint32_t id) {
+template <bool CYL>
+__device__ __forceinline__ V3 pointFromId(const CoreT<CYL>& k, uint32_t id) {
     if (k.kind == CORE_POINT) return k.c;
-    if (k.kind == CORE_CYLINDER) return cylinderPoint(k, id);
+    if (CYL && k.kind == CORE_CYLINDER) return cylinderPoint(k, id);
     if (k.kind == CORE_SEGMENT) return k.c + ((id & 1u) ? -k.e0 : k.e0);
     if (k.kind == CORE_BOX) {
         V3 p = k.c;
@@ -187,7 +199,8 @@ __device__ __forceinline__ V3 pointFromId(const Core& k, uint32_t id) {
 }
 
 // Point of the Minkowski difference A - B in direction d; id = idA | idB << 16.
-__device__ __forceinline__ V3 supportDiff(const Core& A, const Core& B, V3 d, uint32_t& id) {
+template <bool CYL>
+__device__ __forceinline__ V3 supportDiff(const CoreT<CYL>& A, const CoreT<CYL>& B, V3 d, uint32_t& id) {
     uint32_t ia, ib;
     const V3 a = support(A, d, ia);
     const V3 b = support(B, -d, ib);
@@ -339,7 +352,8 @@ struct GjkResult {
     uint32_t status;
 };
 
-__device__ __forceinline__ GjkResult gjk(const Core& A, const Core& B, const NarrowParams& cfg, float marginSum,
+template <bool CYL>
+__device__ __forceinline__ GjkResult gjk(const CoreT<CYL>& A, const CoreT<CYL>& B, const NarrowParams& cfg, float marginSum,
                                          Simplex& s) {
     GjkResult r;
     r.status = 0;
@@ -758,8 +772,8 @@ struct EpaState {
 
 // Grows the simplex to an oriented tetrahedron.  Returns 0 when the expansion can start, 1 when the
 // Minkowski difference is degenerate at the origin and `touching` already is the answer.
-template <int MAXV, int MAXF, int MAXE, int STRIDE>
-__device__ __forceinline__ int epaInit(const Core& A, const Core& B, int n0, const V3* y0, const uint32_t* id0,
+template <int MAXV, int MAXF, int MAXE, int STRIDE, bool CYL>
+__device__ __forceinline__ int epaInit(const CoreT<CYL>& A, const CoreT<CYL>& B, int n0, const V3* y0, const uint32_t* id0,
                                        const Poly<MAXV, MAXF, MAXE, STRIDE>& e,
                                        EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st,
                                        EpaResult& touching) {
@@ -863,8 +877,8 @@ __device__ __forceinline__ int epaInit(const Core& A, const Core& B, int n0, con
 #define AXCD_STR_(x) #x
 #define AXCD_UNROLL(n) _Pragma(AXCD_STR_(unroll n))
 // One expansion step.  Returns true when the pair is finished (converged, capped or overflowed).
-template <int MAXV, int MAXF, int MAXE, int STRIDE>
-__device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const NarrowParams& cfg,
+template <int MAXV, int MAXF, int MAXE, int STRIDE, bool CYL>
+__device__ __forceinline__ bool epaIterate(const CoreT<CYL>& A, const CoreT<CYL>& B, const NarrowParams& cfg,
                                            const Poly<MAXV, MAXF, MAXE, STRIDE>& e,
                                            EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st) {
     using Mask = typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask;
@@ -974,8 +988,8 @@ __device__ __forceinline__ bool epaIterate(const Core& A, const Core& B, const N
     return false;
 }
 
-template <int MAXV, int MAXF, int MAXE, int STRIDE>
-__device__ __forceinline__ EpaResult epaFinish(const Core& A, const Poly<MAXV, MAXF, MAXE, STRIDE>& e,
+template <int MAXV, int MAXF, int MAXE, int STRIDE, bool CYL>
+__device__ __forceinline__ EpaResult epaFinish(const CoreT<CYL>& A, const Poly<MAXV, MAXF, MAXE, STRIDE>& e,
                                                const EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st) {
     if (st.degenerate) return epaTouching(mk3(1.f, 0.f, 0.f), pointFromId(A, e.id(0) & 0xffffu));
     EpaResult r;
@@ -1002,8 +1016,8 @@ __device__ __forceinline__ EpaResult epaFinish(const Core& A, const Poly<MAXV, M
     return r;
 }
 
-template <int MAXV, int MAXF, int MAXE, int STRIDE>
-__device__ __forceinline__ EpaResult epaRun(const Core& A, const Core& B, const NarrowParams& cfg, int n0,
+template <int MAXV, int MAXF, int MAXE, int STRIDE, bool CYL>
+__device__ __forceinline__ EpaResult epaRun(const CoreT<CYL>& A, const CoreT<CYL>& B, const NarrowParams& cfg, int n0,
                                             const V3* y0, const uint32_t* id0,
                                             const Poly<MAXV, MAXF, MAXE, STRIDE>& e) {
     EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask> st;
@@ -1479,6 +1493,7 @@ __device__ __noinline__ BoxBox boxBoxCall(const BodyPose& ta, uint4 sa, const Bo
 #ifndef AXCD_GJK_MIN_BLOCKS
 #define AXCD_GJK_MIN_BLOCKS 5
 #endif
+template <bool CYL>
 __global__ void __launch_bounds__(kGjkThreads, AXCD_GJK_MIN_BLOCKS)
 gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, uint32_t chunkCap,
           const float* __restrict__ xf, const uint4* __restrict__ shapes,
@@ -1523,8 +1538,8 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, 
         }
     }
     if (kind == 0) {
-        const Core A = makeCore(ta, sa, hull, origin);
-        const Core B = makeCore(tb, sb, hull, origin);
+        const CoreT<CYL> A = makeCore<CYL>(ta, sa, hull, origin);
+        const CoreT<CYL> B = makeCore<CYL>(tb, sb, hull, origin);
         const float rs = A.r + B.r;
         const GjkResult g = gjk(A, B, cfg, rs, s);
         if (satApart) {
@@ -1699,17 +1714,18 @@ constexpr int kEpaChunk = 64;        // queue items a warp claims at a time
 constexpr int kEpaBatchLanes = AXCD_EPA_BATCH;    // refill / finalize once this many lanes wait for it
 
 // What a lane carries for the pair it is expanding.
-struct EpaLane {
-    Core A, B;
+template <bool CYL>
+struct EpaLaneT {
+    CoreT<CYL> A, B;
     V3 origin;
     uint32_t pairIdx, ia, ib, status, queueIdx;
 };
 
-template <int MAXV, int MAXF, int MAXE, int STRIDE>
+template <int MAXV, int MAXF, int MAXE, int STRIDE, bool CYL>
 __device__ __forceinline__ int epaBegin(const EpaWork* __restrict__ wk, const uint2* __restrict__ pairs,
                                         const float* __restrict__ xf, const uint4* __restrict__ shapes,
                                         const float4* __restrict__ hull, const Poly<MAXV, MAXF, MAXE, STRIDE>& poly,
-                                        EpaLane& L, EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st,
+                                        EpaLaneT<CYL>& L, EpaState<typename Poly<MAXV, MAXF, MAXE, STRIDE>::Mask>& st,
                                         EpaResult& touching, bool skipInit = false) {
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(wk));
     const float4 f0 = __ldg(reinterpret_cast<const float4*>(wk) + 1), f1 = __ldg(reinterpret_cast<const float4*>(wk) + 2),
@@ -1726,13 +1742,14 @@ __device__ __forceinline__ int epaBegin(const EpaWork* __restrict__ wk, const ui
     const BodyPose ta = loadPose(xf, L.ia), tb = loadPose(xf, L.ib);
     const uint4 sa = __ldg(shapes + L.ia), sb = __ldg(shapes + L.ib);
     L.origin = ta.p;
-    L.A = makeCore(ta, sa, hull, L.origin);
-    L.B = makeCore(tb, sb, hull, L.origin);
+    L.A = makeCore<CYL>(ta, sa, hull, L.origin);
+    L.B = makeCore<CYL>(tb, sb, hull, L.origin);
     if (skipInit) return 0;   // the caller restores a spilled polytope instead
     return epaInit(L.A, L.B, n0, y0, id0, poly, st, touching);
 }
 
-__device__ __forceinline__ void epaEmit(const EpaLane& L, const EpaResult& r, AxcdContact* __restrict__ contacts,
+template <bool CYL>
+__device__ __forceinline__ void epaEmit(const EpaLaneT<CYL>& L, const EpaResult& r, AxcdContact* __restrict__ contacts,
                                         uint32_t maxContacts, const uint32_t* __restrict__ slots,
                                         float* __restrict__ pairDist, Counters* __restrict__ ctr) {
     uint32_t status = L.status;
@@ -1754,6 +1771,7 @@ __device__ __forceinline__ void epaEmit(const EpaLane& L, const EpaResult& r, Ax
 // trip, and refills / finalisations are batched (>= kEpaBatchLanes lanes, or nothing else to do), so
 // a pair that needs 2 steps does not hold its lane hostage to a neighbour that needs 15.  Warps claim
 // queue items in chunks; the queue length is only known on the device.
+template <bool CYL>
 __global__ void __launch_bounds__(kEpaThreads, kEpaBlocksPerSM)
 epaKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs,
           const float* __restrict__ xf, const uint4* __restrict__ shapes, const float4* __restrict__ hull,
@@ -1767,7 +1785,7 @@ epaKernel(NarrowQueues q, uint32_t queueCap, const uint2* __restrict__ pairs,
     const uint32_t count = min(ctr->epaCount, queueCap);
     enum { EMPTY = 0, RUNNING = 1, DONE = 2 };
     int state = EMPTY;
-    EpaLane L;
+    EpaLaneT<CYL> L;
     EpaState<P::Mask> st;
     uint32_t cur = 0, end = 0;   // this warp's claimed queue range (warp-uniform)
     bool drained = false;        // no more items to claim (warp-uniform)

@@ -263,7 +263,7 @@ __device__ __noinline__ ShapeHit rayShape(V3 o, V3 d, float tMax, const BodyPose
 __device__ __noinline__ ShapeHit rayHull(V3 o, V3 d, float tMax, const BodyPose& t, uint4 sh, const float4* __restrict__ hull,
                                          const NarrowParams& cfg) {
     ShapeHit h{false, 0.0f, mk3(0.f, 0.f, 0.f)};
-    Core P;
+    CoreT<true> P;   // the swept path serves hulls and cylinders: always the cylinder-capable instantiation
     P.kind = CORE_POINT;
     P.c = mk3(0.f, 0.f, 0.f);
     P.e0 = P.e1 = P.e2 = P.c;
@@ -271,7 +271,7 @@ __device__ __noinline__ ShapeHit rayHull(V3 o, V3 d, float tMax, const BodyPose&
     P.verts = nullptr;
     P.nv = 0;
     P.r = 0.0f;
-    const SweepResult sw = sweepCores(P, makeCore(t, sh, hull, o), -(d * tMax), cfg);
+    const SweepResult sw = sweepCores(P, makeCore<true>(t, sh, hull, o), -(d * tMax), cfg);
     if (!sw.hit) return h;
     h.hit = true;
     h.t = sw.toi * tMax;

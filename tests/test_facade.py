@@ -77,5 +77,5 @@ def test_cpp_slab_host_two_ranks_over_nccl():
     exe = os.path.join(os.path.dirname(EXE), "slab_host")
     r = subprocess.run([exe, "200000", "58.5", "7", "2", "5"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    ranks, n, pairs, contacts, ghosts, wall_ms, graph = r.stdout.split()
+    ranks, n, pairs, contacts, ghosts, wall_ms, graph = r.stdout.strip().splitlines()[-1].split()   # NCCL may print its banner first
     assert (int(ranks), int(n)) == (2, 200000) and int(pairs) > 500000 and int(ghosts) > 0 and int(graph) == 1

@@ -426,7 +426,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dBodyCount, 2 * nb));
         CU(dalloc(&ctx->dBodyStart, nb + 1));
         CU(dalloc(&ctx->dSegB, np));
-        CU(dalloc(&ctx->dScanStatus, nb / kScanTile + 2));
+        CU(dalloc(&ctx->dScanStatus, nb / kScanTile + 2 + 128));
         {
             size_t P = 1;
             while (P < nb) P <<= 1;
@@ -438,7 +438,9 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dEpaOverflow, (size_t)cfg->maxContacts));
         ctx->spillCap = cfg->maxContacts < 65536u ? cfg->maxContacts : 65536u;
         CU(dalloc(&ctx->dEpaSpill, (size_t)ctx->spillCap * (Poly<kEpaFastVerts, kEpaFastFaces, kEpaFastEdges, 1>::kWords + kSpillStateWords)));
-        CU(dalloc(&ctx->dSlotStatus, np / kSlotTile + 2));
+        // one status word per tile of the slot scan (2048 pairs) or of the fused narrowphase (1024 pairs), plus the
+        // slack the 128-wide look-back may read past the last tile
+        CU(dalloc(&ctx->dSlotStatus, np / kFusedTile + 2 + 128));
         CU(dalloc(&ctx->dChunks, (size_t)chunkCapFor(cfg->maxPairs) * 32));
         CU(dalloc(&ctx->dFlags, np + kSlotTile));
         CU(dalloc(&ctx->dSlots, np));
@@ -662,10 +664,10 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         const int passes = (keyBits + 7) / 8;
         // scratch the later kernels expect zeroed: cleared by the Morton kernel, not by memset nodes
         const uint32_t scanTilesZ = (n + kScanTile - 1) / kScanTile;
-        const uint32_t slotTilesZ = (ctx->cfg.maxPairs + kSlotTile - 1) / kSlotTile;
+        const uint32_t slotTilesZ = (ctx->cfg.maxPairs + kFusedTile - 1) / kFusedTile + 128;
         ZeroList zl;
         zl.ptr[0] = ctx->dBodyCount;   zl.words[0] = n;
-        zl.ptr[1] = ctx->dScanStatus;  zl.words[1] = scanTilesZ + 1;
+        zl.ptr[1] = ctx->dScanStatus;  zl.words[1] = scanTilesZ + 1 + 128;
         zl.ptr[2] = ctx->dSlotStatus;  zl.words[2] = slotTilesZ + 1;
         zl.ptr[3] = ctx->dSortHist;    zl.words[3] = kMaxPasses * kRadix;
         zl.ptr[4] = ctx->dSortStatus;  zl.words[4] = (uint32_t)passes * sortTilesFor(n) * kRadix;
@@ -808,7 +810,8 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         const uint32_t slotBlocks = slotTilesMax < (uint32_t)ctx->numSMs * 4 ? slotTilesMax : ctx->numSMs * 4;
         // the slot scan's status words were cleared by this step's Morton kernel; a step that reused the
         // cached broadphase (temporal coherence) did not run it
-        if (ctx->broadSkipped) CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * (slotTilesMax + 1), st));
+        if (ctx->broadSkipped)
+            CU(cudaMemsetAsync(ctx->dSlotStatus, 0, sizeof(uint32_t) * ((mp + kFusedTile - 1) / kFusedTile + 129), st));
         NarrowQueues q{ctx->dEpaWork, ctx->dEpaOverflow, ctx->dEpaSpill, ctx->spillCap};
         const uint2* pairs = ctx->dPairs;
         const uint32_t* pairCount = &ctx->dCtr->pairCount;
@@ -1173,7 +1176,8 @@ int32_t axcd_query_aabbs(AxcdContext* ctx, const float* boxes6, const uint32_t* 
     const uint32_t scanTiles = (nq + kScanTile - 1) / kScanTile;
     // layout of dQCount: counts[nqPad] | starts[nqPad] | cursor copy[nqPad] | status[scanTiles + 1] | ticket | total
     const uint32_t nqPad = (nq + 3u) & ~3u;   // the scan stores 16-byte vectors: keep every sub-buffer aligned
-    const size_t words = 3 * (size_t)nqPad + scanTiles + 1 + 2;
+    const uint32_t statusWords = ((scanTiles + 1 + 128 + 3u) & ~3u);   // + the look-back's read slack, 16-byte multiple
+    const size_t words = 3 * (size_t)nqPad + statusWords + 2;
     CU(growScratch(&ctx->dQIn, &ctx->qInBytes, (size_t)nq * 28));
     CU(growScratch(&ctx->dQCount, &ctx->qCountBytes, words * 4));
     float* dBoxes = static_cast<float*>(ctx->dQIn);
@@ -1182,12 +1186,12 @@ int32_t axcd_query_aabbs(AxcdContext* ctx, const float* boxes6, const uint32_t* 
     uint32_t* dStarts = dCounts + nqPad;
     uint32_t* dCursor = dStarts + nqPad;
     uint32_t* dStatus = dCursor + nqPad;
-    uint32_t* dTicket = dStatus + scanTiles + 1;
+    uint32_t* dTicket = dStatus + statusWords;
     uint32_t* dTotal = dTicket + 1;
     CU(cudaMemcpyAsync(dBoxes, boxes6, (size_t)nq * 24, cudaMemcpyHostToDevice, st));
     const bool useWorld = ctx->hasWorlds && queryWorld;
     if (useWorld) CU(cudaMemcpyAsync(dQW, queryWorld, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(dStatus, 0, sizeof(uint32_t) * (scanTiles + 3), st));
+    CU(cudaMemsetAsync(dStatus, 0, sizeof(uint32_t) * (statusWords + 2), st));
     {
         const int rc = ensureQueryNodes(ctx);
         if (rc) return rc;

@@ -65,6 +65,47 @@ __host__ __device__ __forceinline__ float orderedToFloat(uint32_t u) {
 #endif
 }
 
+// Exclusive prefix of `tile` over per-tile status words (flag | value) of a single-pass scan: warp-wide look-back,
+// 128 predecessor tiles per round (one 16-byte volatile load per lane).  All in-flight tiles sit in the "aggregate"
+// state together, so the walk back to the last inclusive prefix is about one wave of tiles long: 4 words per lane
+// make it 4x fewer dependent L2 round trips than a word per lane.  `status` must be readable up to the next
+// multiple of 128 words past `tile`.  Call with all 32 lanes of a warp.
+__device__ __forceinline__ uint32_t lookbackWide(const volatile uint32_t* status, uint32_t tile, int lane) {
+    uint32_t excl = 0;
+    for (int chunk = (int)((tile - 1u) >> 7); chunk >= 0; --chunk) {
+        const uint32_t base = (uint32_t)chunk * 128u + 4u * (uint32_t)lane;
+        uint32_t w[4];
+        bool ready;
+        do {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                         : "l"(status + base)
+                         : "memory");
+            ready = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (base + k < tile && (w[k] & kFlagMask) == 0u) ready = false;   // not published yet
+        } while (!__all_sync(0xffffffffu, ready));
+        int myTop = -1;   // highest of this lane's words that holds an inclusive prefix
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (base + k < tile && (w[k] & kFlagMask) == kFlagInclusive) myTop = k;
+        const uint32_t hasInc = __ballot_sync(0xffffffffu, myTop >= 0);
+        const int top = hasInc ? 31 - __clz(hasInc) : -1;   // the lane holding the nearest inclusive prefix
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool take = base + k < tile && (lane > top || (lane == top && k >= myTop));
+            sum += take ? (w[k] & kValueMask) : 0u;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        excl += sum;
+        if (hasInc) break;
+    }
+    return excl;
+}
+
 constexpr int kNumClasses = 6;
 
 // One 64-byte LBVH internal node: both children's boxes live in the parent, so a traversal step is

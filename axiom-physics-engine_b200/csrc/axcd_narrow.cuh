@@ -1439,22 +1439,7 @@ narrowClosedFusedKernel(const uint2* __restrict__ pairs, const uint32_t* __restr
                 if (lane == 0) tileStatus[0] = kFlagInclusive | tileTotal;
             } else {
                 if (lane == 0) tileStatus[tile] = kFlagAggregate | tileTotal;
-                int t = (int)tile - 1;
-                while (true) {
-                    const int idx = t - lane;
-                    uint32_t sv = kFlagInclusive;   // lanes before tile 0 act as an inclusive zero
-                    if (idx >= 0) {
-                        do { sv = tileStatus[idx]; } while ((sv & kFlagMask) == 0);
-                    }
-                    const uint32_t incMask = __ballot_sync(0xffffffffu, (sv & kFlagMask) == kFlagInclusive);
-                    const int firstInc = incMask ? (__ffs(incMask) - 1) : 32;
-                    uint32_t v = (lane <= firstInc) ? (sv & kValueMask) : 0u;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                    excl += v;
-                    if (incMask) break;
-                    t -= 32;
-                }
+                excl = lookbackWide(tileStatus, tile, lane);
                 if (lane == 0) tileStatus[tile] = kFlagInclusive | (excl + tileTotal);
             }
             if (lane == 0) {
@@ -1600,6 +1585,7 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, 
 constexpr int kSlotThreads = 256;
 constexpr int kSlotItems = 8;
 constexpr int kSlotTile = kSlotThreads * kSlotItems;
+static_assert(kFusedTile <= kSlotTile, "the status buffer is sized by the smaller tile");
 
 __global__ void __launch_bounds__(kSlotThreads)
 slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
@@ -1641,28 +1627,13 @@ slotKernel(const uint8_t* __restrict__ flags, const uint32_t* __restrict__ pairC
         warpPrefix += (i < warp) ? sWarp[i] : 0u;
         tileTotal += sWarp[i];
     }
-    if (warp == 0) {   // warp-parallel decoupled look-back
+    if (warp == 0) {   // warp-parallel decoupled look-back, 128 tiles per round
         uint32_t excl = 0;
         if (tile == 0) {
             if (lane == 0) tileStatus[0] = kFlagInclusive | tileTotal;
         } else {
             if (lane == 0) tileStatus[tile] = kFlagAggregate | tileTotal;
-            int t = (int)tile - 1;
-            while (true) {
-                const int idx = t - lane;
-                uint32_t sv = kFlagInclusive;   // lanes before tile 0 act as an inclusive zero
-                if (idx >= 0) {
-                    do { sv = tileStatus[idx]; } while ((sv & kFlagMask) == 0);
-                }
-                const uint32_t incMask = __ballot_sync(0xffffffffu, (sv & kFlagMask) == kFlagInclusive);
-                const int firstInc = incMask ? (__ffs(incMask) - 1) : 32;
-                uint32_t v = (lane <= firstInc) ? (sv & kValueMask) : 0u;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                excl += v;
-                if (incMask) break;
-                t -= 32;
-            }
+            excl = lookbackWide(tileStatus, tile, lane);
             if (lane == 0) tileStatus[tile] = kFlagInclusive | (excl + tileTotal);
         }
         if (lane == 0) {

@@ -418,7 +418,7 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 static_assert(kScanItems == 8, "the scan kernel moves 8 words per thread as two uint4");
 
-// out[i] = out2[i] = sum of in[0..i); *total = sum of all.  status: numTiles words, zero-initialised.
+// out[i] = out2[i] = sum of in[0..i); *total = sum of all.  status: numTiles + 128 words, zero-initialised.
 __global__ void __launch_bounds__(kScanThreads)
 exclusiveScanKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ out2, uint32_t n,
                     volatile uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
@@ -455,28 +455,13 @@ exclusiveScanKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
         wbase += (i < warp) ? sWarp[i] : 0u;
         tileTotal += sWarp[i];
     }
-    if (warp == 0) {   // warp-parallel decoupled look-back: 32 predecessor tiles per step
+    if (warp == 0) {   // warp-parallel decoupled look-back: 128 predecessor tiles per round (status: +128 words of slack)
         uint32_t excl = 0;
         if (tile == 0) {
             if (lane == 0) status[0] = kFlagInclusive | tileTotal;
         } else {
             if (lane == 0) status[tile] = kFlagAggregate | tileTotal;
-            int t = (int)tile - 1;
-            while (true) {
-                const int idx = t - lane;
-                uint32_t sv = kFlagInclusive;   // lanes before tile 0 act as an inclusive zero
-                if (idx >= 0) {
-                    do { sv = status[idx]; } while ((sv & kFlagMask) == 0);
-                }
-                const uint32_t incMask = __ballot_sync(0xffffffffu, (sv & kFlagMask) == kFlagInclusive);
-                const int firstInc = incMask ? (__ffs(incMask) - 1) : 32;
-                uint32_t v2 = (lane <= firstInc) ? (sv & kValueMask) : 0u;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, off);
-                excl += v2;
-                if (incMask) break;
-                t -= 32;
-            }
+            excl = lookbackWide(status, tile, lane);
             if (lane == 0) status[tile] = kFlagInclusive | (excl + tileTotal);
         }
         if (lane == 0) {

@@ -216,7 +216,9 @@ class SlabRank:
         self.owned, self.gid = owned, np.ascontiguousarray(owned_gid, np.uint32)
         self.edges, self.rank, self.size = edges, rank, size
         cap = int(owned.n * (1.0 + ghost_frac)) + 4096
-        self.w = CollisionWorld(cap, max_pairs=pairs_per_body * cap, max_hull_verts=len(owned.hull), device=device)
+        # hull ghosts bring their vertices (axcd_slab_step): room for them behind the owned ones
+        hull_cap = int(len(owned.hull) * (1.0 + ghost_frac)) + (8192 if len(owned.hull) else 0)
+        self.w = CollisionWorld(cap, max_pairs=pairs_per_body * cap, max_hull_verts=hull_cap, device=device)
         self.w.set_shapes(owned.shapes, owned.hull)
         self.w.set_transforms(owned.xf)
         self.w.set_body_keys(self.gid, 0)

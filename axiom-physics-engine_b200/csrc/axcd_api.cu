@@ -80,6 +80,8 @@ struct AxcdContext {
     uint32_t* dCountMatrix = nullptr;   // slabRanks x slabRanks: row r = records rank r sends to each rank
     uint32_t* hCountMatrix = nullptr;   // pinned host copy
     float4* dGhostRecv = nullptr;       // ghostCap records
+    float4* dGhostVertSend = nullptr;   // slabRanks x ghostVertCap hull vertices of the ghosts sent
+    uint32_t ghostVertCap = 0;          // maxHullVerts - nHull: room behind the owned vertices in the hull pool
     uint32_t lastGhosts = 0;
     float lastExchangeMs = 0.0f;
     cudaEvent_t evX0 = nullptr, evX1 = nullptr;
@@ -1450,8 +1452,10 @@ int32_t axcd_set_ghosts_device(AxcdContext* ctx, uint32_t nOwned, uint32_t nGhos
     ctx->pairsCached = false;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (nGhosts) {
+        GhostOffsets none;
+        none.numRanks = 0;
         unpackGhostsKernel<<<(nGhosts + 255) / 256, 256, 0, ctx->stream>>>(static_cast<const float4*>(devRecords), nGhosts, nOwned,
-                                                                            ctx->dXf, ctx->dShapes, ctx->dBodyKeys);
+                                                                            ctx->dXf, ctx->dShapes, ctx->dBodyKeys, none, 0u);
         CU(cudaGetLastError());
     }
     if (ctx->n != nOwned + nGhosts) {
@@ -1526,6 +1530,8 @@ void slabRelease(AxcdContext* ctx) {
     if (ctx->dEdges) cudaFree(ctx->dEdges);
     if (ctx->dCountMatrix) cudaFree(ctx->dCountMatrix);
     if (ctx->dGhostRecv) cudaFree(ctx->dGhostRecv);
+    if (ctx->dGhostVertSend) cudaFree(ctx->dGhostVertSend);
+    ctx->dGhostVertSend = nullptr;
     if (ctx->hCountMatrix) cudaFreeHost(ctx->hCountMatrix);
     if (ctx->evX0) cudaEventDestroy(ctx->evX0);
     if (ctx->evX1) cudaEventDestroy(ctx->evX1);
@@ -1540,7 +1546,6 @@ void slabRelease(AxcdContext* ctx) {
 int slabSetup(AxcdContext* ctx, void* comm, bool owns, uint32_t rank, uint32_t numRanks, const float* edges) {
     if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;   // owned shapes and poses first
     if (ctx->cfg.numWorlds > 1 || (ctx->cfg.flags & AXCD_FLAG_TEMPORAL_COHERENCE)) return AXCD_ERR_INVALID_PARAM;
-    if (ctx->nHull) return AXCD_ERR_INVALID_SHAPE;   // hull ghosts would need their vertices shipped too
     for (uint32_t r = 0; r < numRanks; ++r)
         if (!(edges[r] <= edges[r + 1])) return AXCD_ERR_INVALID_PARAM;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
@@ -1555,17 +1560,21 @@ int slabSetup(AxcdContext* ctx, void* comm, bool owns, uint32_t rank, uint32_t n
     ctx->dGhostSend = nullptr;
     ctx->dGhostCount = nullptr;
     CU(dalloc(&ctx->dGhostSend, (size_t)numRanks * cap * (kGhostWords / 4)));
-    CU(dalloc(&ctx->dGhostCount, (size_t)numRanks));
+    CU(dalloc(&ctx->dGhostCount, (size_t)2 * numRanks));   // records, then hull vertices, per destination
     ctx->ghostRanks = numRanks;
     ctx->ghostCap = cap;
+    // hull ghosts bring their vertices: they land behind the owned ones in the hull pool
+    ctx->ghostVertCap = ctx->cfg.maxHullVerts > ctx->nHull ? ctx->cfg.maxHullVerts - ctx->nHull : 0u;
+    if (ctx->ghostVertCap) CU(dalloc(&ctx->dGhostVertSend, (size_t)numRanks * ctx->ghostVertCap));
     CU(dalloc(&ctx->dGhostRecv, (size_t)cap * (kGhostWords / 4)));
     CU(dalloc(&ctx->dEdges, (size_t)numRanks + 1));
-    CU(dalloc(&ctx->dCountMatrix, (size_t)numRanks * numRanks));
-    CU(cudaMallocHost(reinterpret_cast<void**>(&ctx->hCountMatrix), sizeof(uint32_t) * numRanks * numRanks));
+    CU(dalloc(&ctx->dCountMatrix, (size_t)2 * numRanks * numRanks));
+    CU(cudaMallocHost(reinterpret_cast<void**>(&ctx->hCountMatrix), sizeof(uint32_t) * 2 * numRanks * numRanks));
     CU(cudaEventCreate(&ctx->evX0));
     CU(cudaEventCreate(&ctx->evX1));
     CU(cudaMemcpyAsync(ctx->dEdges, edges, sizeof(float) * (numRanks + 1), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->hasSweptRayShapes = true;   // ghost bodies may be hulls or cylinders
     return axcd_set_slab(ctx, edges[rank], edges[rank + 1], 1u);
 }
 }  // namespace
@@ -1624,44 +1633,69 @@ int32_t axcd_slab_step_async(AxcdContext* ctx) {
         const int rc = axcd_refit(ctx);   // boxes of the owned bodies (stale ghosts behind them are refit too; harmless)
         if (rc) return rc;
     }
-    CU(cudaMemsetAsync(ctx->dGhostCount, 0, sizeof(uint32_t) * R, st));
+    const uint32_t vcap = ctx->ghostVertCap;
+    CU(cudaMemsetAsync(ctx->dGhostCount, 0, sizeof(uint32_t) * 2 * R, st));
     if (nOwned && R > 1) {
-        packGhostsAllKernel<<<(nOwned + 255) / 256, 256, 0, st>>>(ctx->dAabb, ctx->dXf, ctx->dShapes, ctx->dBodyKeys, nOwned,
-                                                                 ctx->dEdges, R, me, ctx->dGhostSend, cap, ctx->dGhostCount);
+        packGhostsAllKernel<<<(nOwned + 255) / 256, 256, 0, st>>>(ctx->dAabb, ctx->dXf, ctx->dShapes, ctx->dBodyKeys, ctx->dHull, nOwned,
+                                                                 ctx->dEdges, R, me, ctx->dGhostSend, cap, ctx->dGhostVertSend, vcap,
+                                                                 ctx->dGhostCount);
         CU(cudaGetLastError());
     }
-    // size handshake: everybody learns the whole R x R count matrix
-    NC(N->AllGather(ctx->dGhostCount, ctx->dCountMatrix, R, kNcclUint32, comm, st));
-    CU(cudaMemcpyAsync(ctx->hCountMatrix, ctx->dCountMatrix, sizeof(uint32_t) * R * R, cudaMemcpyDeviceToHost, st));
+    // size handshake: everybody learns the whole count matrix (row r = what rank r sends: R record counts, R vertex counts)
+    NC(N->AllGather(ctx->dGhostCount, ctx->dCountMatrix, 2 * R, kNcclUint32, comm, st));
+    CU(cudaMemcpyAsync(ctx->hCountMatrix, ctx->dCountMatrix, sizeof(uint32_t) * 2 * R * R, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     const uint32_t* M = ctx->hCountMatrix;
-    uint64_t total = 0;
+    auto recs = [&](uint32_t src, uint32_t dst) { return M[src * 2 * R + dst]; };
+    auto verts = [&](uint32_t src, uint32_t dst) { return M[src * 2 * R + R + dst]; };
+    uint64_t total = 0, totalVerts = 0;
     for (uint32_t r = 0; r < R; ++r) {
-        if (M[r * R + me] > 0 && r != me) total += M[r * R + me];
-        for (uint32_t d = 0; d < R; ++d)
-            if (M[r * R + d] > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;   // a send buffer overflowed somewhere
-    }
-    for (uint32_t d = 0; d < R; ++d)
-        if (d != me && M[me * R + d] > cap) return AXCD_ERR_OUT_OF_RANGE;
-    if (total > cap) return AXCD_ERR_OUT_OF_RANGE;
-    // the records, rank to rank
-    NC(N->GroupStart());
-    uint64_t off = 0;
-    for (uint32_t r = 0; r < R; ++r) {
-        if (r == me) continue;
-        const uint32_t nSend = M[me * R + r], nRecv = M[r * R + me];
-        if (nSend)
-            NC(N->Send(ctx->dGhostSend + (size_t)r * cap * (kGhostWords / 4), (size_t)nSend * kGhostWords, kNcclFloat32, (int)r, comm, st));
-        if (nRecv) {
-            NC(N->Recv(ctx->dGhostRecv + off * (kGhostWords / 4), (size_t)nRecv * kGhostWords, kNcclFloat32, (int)r, comm, st));
-            off += nRecv;
+        if (r != me) {
+            total += recs(r, me);
+            totalVerts += verts(r, me);
         }
     }
+    // a send buffer that overflowed anywhere fails the step on every rank (the matrix is the same everywhere)
+    for (uint32_t r = 0; r < R; ++r)
+        for (uint32_t d = 0; d < R; ++d)
+            if (recs(r, d) > ctx->cfg.maxBodies || verts(r, d) > (1u << 30)) return AXCD_ERR_OUT_OF_RANGE;
+    for (uint32_t d = 0; d < R; ++d)
+        if (d != me && (recs(me, d) > cap || verts(me, d) > vcap)) return AXCD_ERR_OUT_OF_RANGE;
+    if (total > cap || totalVerts > vcap) return AXCD_ERR_OUT_OF_RANGE;
+    // the records (and the hull vertices, straight into the hull pool behind the owned ones), rank to rank
+    GhostOffsets go;
+    go.numRanks = R;
+    NC(N->GroupStart());
+    uint64_t off = 0, voff = 0;
+    for (uint32_t r = 0; r < R; ++r) {
+        go.vertBase[r] = ctx->nHull + (uint32_t)voff;
+        if (r != me) {
+            const uint32_t nSend = recs(me, r), nRecv = recs(r, me), vSend = verts(me, r), vRecv = verts(r, me);
+            if (nSend)
+                NC(N->Send(ctx->dGhostSend + (size_t)r * cap * (kGhostWords / 4), (size_t)nSend * kGhostWords, kNcclFloat32, (int)r, comm, st));
+            if (nRecv)
+                NC(N->Recv(ctx->dGhostRecv + off * (kGhostWords / 4), (size_t)nRecv * kGhostWords, kNcclFloat32, (int)r, comm, st));
+            if (vSend) NC(N->Send(ctx->dGhostVertSend + (size_t)r * vcap, (size_t)vSend * 4, kNcclFloat32, (int)r, comm, st));
+            if (vRecv) NC(N->Recv(ctx->dHull + ctx->nHull + voff, (size_t)vRecv * 4, kNcclFloat32, (int)r, comm, st));
+            off += nRecv;
+            voff += vRecv;
+        }
+        go.recEnd[r] = (uint32_t)off;
+    }
     NC(N->GroupEnd());
-    {
-        const int rc = axcd_set_ghosts_device(ctx, nOwned, (uint32_t)total, ctx->dGhostRecv);
+    if ((uint64_t)nOwned + total > ctx->cfg.maxBodies) return AXCD_ERR_OUT_OF_RANGE;
+    ctx->fatValid = false;
+    ctx->pairsCached = false;
+    if (total) {
+        unpackGhostsKernel<<<((uint32_t)total + 255) / 256, 256, 0, st>>>(ctx->dGhostRecv, (uint32_t)total, nOwned, ctx->dXf, ctx->dShapes,
+                                                                         ctx->dBodyKeys, go, 1u);
+        CU(cudaGetLastError());
+    }
+    if (ctx->n != nOwned + (uint32_t)total) {
+        const int rc = resizeBodies(ctx, nOwned + (uint32_t)total);
         if (rc) return rc;
     }
+    ctx->stage = ST_POSES;
     CU(cudaEventRecord(ctx->evX1, st));
     ctx->lastGhosts = (uint32_t)total;
     return axcd_step_async(ctx);

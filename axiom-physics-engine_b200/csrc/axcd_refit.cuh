@@ -562,11 +562,14 @@ __global__ void packGhostsKernel(const float* __restrict__ aabb, const float* __
 
 // The same selection for ALL destination ranks in one pass over the owned bodies: slab r = [edges[r],
 // edges[r+1]) for r != myRank; out holds numRanks send buffers of `cap` records each, counters one word per
-// rank.  (Slabs are contiguous, so a body usually matches none or one neighbour.)
+// rank.  (Slabs are contiguous, so a body usually matches none or one neighbour.)  A convex hull's vertices travel
+// too: they are appended to the destination's vertex send buffer (vertOut, vertCap float4 per rank; counters
+// numRanks .. 2*numRanks-1) and the record's `first` becomes the offset inside that buffer — the receiver rebases it.
 __global__ void packGhostsAllKernel(const float* __restrict__ aabb, const float* __restrict__ xf,
                                     const uint4* __restrict__ shapes, const uint32_t* __restrict__ keys,
-                                    uint32_t nOwned, const float* __restrict__ edges, uint32_t numRanks, uint32_t myRank,
-                                    float4* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+                                    const float4* __restrict__ hull, uint32_t nOwned, const float* __restrict__ edges,
+                                    uint32_t numRanks, uint32_t myRank, float4* __restrict__ out, uint32_t cap,
+                                    float4* __restrict__ vertOut, uint32_t vertCap, uint32_t* __restrict__ counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     float mn = 0.0f, mx = 0.0f;
@@ -585,9 +588,17 @@ __global__ void packGhostsAllKernel(const float* __restrict__ aabb, const float*
         base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
         if (!take) continue;
         const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+        uint4 sh = __ldg(shapes + i);
+        if (sh.x == AXCD_SHAPE_CONVEX) {
+            const uint32_t vbase = atomicAdd(counters + numRanks + r, sh.z);   // counted even when it does not fit
+            if (slot < cap && vbase + sh.z <= vertCap) {
+                float4* vo = vertOut + (size_t)r * vertCap + vbase;
+                for (uint32_t k = 0; k < sh.z; ++k) vo[k] = __ldg(hull + sh.y + k);
+            }
+            sh.y = vbase;
+        }
         if (slot >= cap) continue;   // counted, not stored: the host sees counter > cap
         const float* t = xf + (size_t)i * 10;
-        const uint4 sh = __ldg(shapes + i);
         float4* o = out + ((size_t)r * cap + slot) * (kGhostWords / 4);
         o[0] = make_float4(t[0], t[1], t[2], t[3]);
         o[1] = make_float4(t[4], t[5], t[6], t[7]);
@@ -596,9 +607,18 @@ __global__ void packGhostsAllKernel(const float* __restrict__ aabb, const float*
     }
 }
 
-// Appends received ghost records after the owned bodies.
+// Offsets of each source rank's block inside the receive buffers (records and hull vertices).
+struct GhostOffsets {
+    uint32_t recEnd[64];     // records of source ranks 0..r end here (prefix sums, own rank contributes 0)
+    uint32_t vertBase[64];   // index in the hull pool where source rank r's vertices start
+    uint32_t numRanks;
+};
+
+// Appends received ghost records after the owned bodies.  With `off` (records grouped by source rank) a hull's
+// vertex range is rebased onto where that rank's vertices landed in the hull pool.
 __global__ void unpackGhostsKernel(const float4* __restrict__ in, uint32_t count, uint32_t first,
-                                   float* __restrict__ xf, uint4* __restrict__ shapes, uint32_t* __restrict__ keys) {
+                                   float* __restrict__ xf, uint4* __restrict__ shapes, uint32_t* __restrict__ keys,
+                                   GhostOffsets off, uint32_t rebase) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= count) return;
     const float4* r = in + (size_t)g * (kGhostWords / 4);
@@ -607,7 +627,13 @@ __global__ void unpackGhostsKernel(const float4* __restrict__ in, uint32_t count
     t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w;
     t[4] = b.x; t[5] = b.y; t[6] = b.z; t[7] = b.w;
     t[8] = c.x; t[9] = c.y;
-    shapes[first + g] = make_uint4(__float_as_uint(c.z), __float_as_uint(c.w), __float_as_uint(d.x), __float_as_uint(d.y));
+    uint4 sh = make_uint4(__float_as_uint(c.z), __float_as_uint(c.w), __float_as_uint(d.x), __float_as_uint(d.y));
+    if (rebase && sh.x == AXCD_SHAPE_CONVEX) {
+        uint32_t src = 0;
+        while (src + 1 < off.numRanks && g >= off.recEnd[src]) ++src;
+        sh.y += off.vertBase[src];
+    }
+    shapes[first + g] = sh;
     keys[first + g] = __float_as_uint(d.z);
 }
 

@@ -308,8 +308,9 @@ AXCD_API int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t
  * other ranks with axcd_set_ghosts, after which the context holds nOwned + nGhosts bodies.  With the
  * slab rule enabled a candidate pair is kept only if max(min_a.x, min_b.x) lies in [xLo, xHi) — exactly
  * one rank keeps each pair — and pairs are oriented by key (key[a] < key[b]) instead of by local
- * index, so each contact is computed exactly as a single-GPU run would.  Hull shapes are not
- * accepted as ghosts in this version (-> 300).                                                    */
+ * index, so each contact is computed exactly as a single-GPU run would.  With these building-block calls hull
+ * shapes are not accepted as ghosts (-> 300); axcd_slab_step ships a hull ghost's vertices too (capacity:
+ * maxHullVerts beyond the owned vertices).                                                          */
 AXCD_API int32_t axcd_set_slab(AxcdContext* ctx, float xLo, float xHi, uint32_t enable);
 AXCD_API int32_t axcd_set_body_keys(AxcdContext* ctx, const uint32_t* keys, uint32_t first,
                                     uint32_t count);

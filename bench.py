@@ -260,15 +260,15 @@ def stage_table(avg, st, hbm_peak, fp32_peak, generic_pairs):
         "refitMs": ("refitTmaKernel", "hbm", n * 80),
         "sortMs": ("mortonKernel + onesweep radix sort (%d passes)" % passes, "hbm", n * 32 + n * (16 * passes + 4)),
         "buildMs": ("leaf gather + range tree + Karras topology/fit (32-byte nodes)", "hbm", n * (24 + 32) + n * 64 + n * 32),
-        "pairMs": ("findPairsKernel (LBVH traversal)", "hbm", n * 32 + npairs * 8),
+        "pairMs": ("findPairsDenseKernel (LBVH traversal, dense leaf tests)", "hbm", n * 32 + npairs * 8),
         "pairSortMs": ("pair counting sort (scan + scatter + segment sort)", "hbm", n * 12 + npairs * (8 + 4 + 4 + 8)),
         "epaMs": ("epaKernel (+fallback)", "fp32", nepa * EPA_FLOP_PER_PAIR),
     }
     if generic_pairs > 0.05 * max(1, npairs):
         info["gjkMs"] = ("classify + closedFormKernel + gjkKernel + slotKernel", "fp32", generic_pairs * GJK_FLOP_PER_PAIR)
     else:
-        info["gjkMs"] = ("classify + closedFormKernel (sphere / box closed forms, box-box SAT) + slotKernel", "hbm",
-                         npairs * (8 + 4 + 2 * 56 + 1 + 1) + ncon * 80)
+        info["gjkMs"] = ("narrowClosedFusedKernel (classify + sphere / box closed forms incl. box-box SAT + in-order compaction)", "hbm",
+                         npairs * (8 + 2 + 2 * 56) + ncon * 40)
     rows = []
     for k, ms in avg.items():
         name, bound, work = info[k]

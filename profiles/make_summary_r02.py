@@ -47,9 +47,12 @@ def ncu_table(rep):
             cur = re.sub(r"^void ", "", line.replace('=====', '').strip())
             data[cur] = {}
         else:
-            m = re.match(r'\s+(\S+)\s+(\S+)', line)
+            m = re.match(r'\s+(\S+)\s+(\S+)\s*(\S*)', line)
             if m and cur:
                 data[cur][m.group(1)] = m.group(2)
+                if m.group(1) == 'gpu__time_duration.sum':   # normalise to microseconds
+                    v = float(m.group(2))
+                    data[cur][m.group(1)] = str(v * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(m.group(3), 1.0))
 
     def g(k, key):
         try:
@@ -63,7 +66,7 @@ def ncu_table(rep):
         top = sorted(st.items(), key=lambda x: -x[1])[:3]
         t = float(data[k]['gpu__time_duration.sum'])
         rd, wr = float(data[k]['dram__bytes_read.sum']), float(data[k]['dram__bytes_write.sum'])
-        tbl.append(f"| {k} | {t if t > 5 else t * 1000:.1f} | {data[k]['launch__registers_per_thread']} | "
+        tbl.append(f"| {k} | {t:.1f} | {data[k]['launch__registers_per_thread']} | "
                    f"{g(k, 'sm__warps_active.avg.pct_of_peak_sustained_active')} | {g(k, 'smsp__issue_active.avg.pct_of_peak_sustained_active')} | "
                    f"{g(k, 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active')} | "
                    f"{g(k, 'smsp__thread_inst_executed_per_inst_executed.ratio')} | {float(data[k]['smsp__inst_executed.sum']) / 1e6:.1f} | {rd + wr:.1f} | "
@@ -165,7 +168,7 @@ for wl, m in stage_kernel.items():
         v = first(data, kn)
         if v:
             t = float(v['gpu__time_duration.sum'])
-            traffic[wl][stage] = {"kernel": kn, "ncu_kernel_ms": (t if t < 5 else t / 1000.0) if False else (t / 1000.0 if t > 5 else t),
+            traffic[wl][stage] = {"kernel": kn, "ncu_kernel_ms": t / 1000.0,
                                   "dram_bytes_per_launch": (float(v['dram__bytes_read.sum']) + float(v['dram__bytes_write.sum'])) * 1e6}
 if c2data:
     traffic["C2"] = {}
@@ -173,7 +176,7 @@ if c2data:
         v = first(c2data, kn)
         if v:
             t = float(v['gpu__time_duration.sum'])
-            traffic["C2"][stage] = {"kernel": kn, "ncu_kernel_ms": t / 1000.0 if t > 5 else t,
+            traffic["C2"][stage] = {"kernel": kn, "ncu_kernel_ms": t / 1000.0,
                                     "dram_bytes_per_launch": (float(v['dram__bytes_read.sum']) + float(v['dram__bytes_write.sum'])) * 1e6}
 json.dump(traffic, open(os.path.join(HERE, "r02_traffic.json"), 'w'), indent=1)
 print(md[:1200])

@@ -18,6 +18,7 @@ namespace axcd {
 
 enum { CORE_POINT = 0, CORE_BOX = 1, CORE_HULL = 2, CORE_SEGMENT = 3, CORE_CYLINDER = 4 };
 
+
 // CYL: whether cylinder cores can occur.  Scenes without cylinders instantiate every GJK / EPA kernel with
 // CYL = false, so the cylinder's support code (two divisions and a square root per call) costs them nothing —
 // inlined, or even as an out-of-line call, it cost the hull-mix scene C2 8 % of its step.

@@ -822,7 +822,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         // need GJK (hulls, capsules; box-box when forced, or when its separation distance is wanted) go to
         // separate chunk lists and kernels.  A scene that cannot produce a generic pair skips those launches.
         const bool boxGeneric = p.boxBoxGeneric || p.wantDistances;
-        const uint32_t genericMask = (1u << 5) | (boxGeneric ? (1u << 4) : 0u);
+        const uint32_t genericMask = kGenericClassMask | (boxGeneric ? (1u << 4) : 0u);
         const bool anyGeneric = ctx->hasGenericShapes || boxGeneric || ctx->slabOn || ctx->n != ctx->nOwned;
         if (!anyGeneric && !ctx->dPairDist && !ctx->splitNarrow) {
             // every pair is decided in closed form: classification, closed forms and in-order compaction in ONE kernel

@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t lookbackWide(const volatile uint32_t* status
     return excl;
 }
 
-constexpr int kNumClasses = 6;
+constexpr int kNumClasses = 12;   // pair classes of the narrowphase (pairClass in axcd_narrow.cuh)
 
 // One 64-byte LBVH internal node: both children's boxes live in the parent, so a traversal step is
 // one aligned 64-byte read.  Leaf-ness and child indices follow from (first, split, last):

@@ -1062,11 +1062,23 @@ struct NarrowQueues {
 #endif
 constexpr int kGjkThreads = AXCD_GJK_THREADS;
 
-// Pair class by core kinds, so that a warp runs one kind of support function.
+// Pair class by the two core kinds, so that a warp runs ONE pair of support functions (a warp that mixes a box
+// support with a 16-vertex hull scan executes both for every lane).  1-4: the classes with closed forms (sphere-
+// sphere, sphere-box, box-sphere, box-box); 5: capsule against sphere / box / capsule (point, segment and box
+// supports, all cheap); 6-10: the five (kind A, kind B) combinations with a convex hull; 11: anything with a cylinder.
+enum { CLASS_CAPSULE_MIX = 5, CLASS_LIGHT_HULL = 6, CLASS_HULL_LIGHT = 7, CLASS_BOX_HULL = 8, CLASS_HULL_BOX = 9,
+       CLASS_HULL_HULL = 10, CLASS_CYLINDER = 11 };
+constexpr uint32_t kGenericClassMask = 0xfe0u;   // classes 5..11 always need GJK
+static_assert(kNumClasses == 12, "classes 0..11");
 __device__ __forceinline__ int pairClass(uint32_t typeA, uint32_t typeB) {
-    if (typeA == AXCD_SHAPE_CONVEX || typeB == AXCD_SHAPE_CONVEX || typeA == AXCD_SHAPE_CAPSULE ||
-        typeB == AXCD_SHAPE_CAPSULE || typeA == AXCD_SHAPE_CYLINDER || typeB == AXCD_SHAPE_CYLINDER)
-        return 5;   // hulls, capsules and cylinders share the "other" class
+    if (typeA == AXCD_SHAPE_CYLINDER || typeB == AXCD_SHAPE_CYLINDER) return CLASS_CYLINDER;
+    const bool hullA = typeA == AXCD_SHAPE_CONVEX, hullB = typeB == AXCD_SHAPE_CONVEX;
+    if (hullA || hullB) {
+        if (hullA && hullB) return CLASS_HULL_HULL;
+        if (hullA) return (typeB == AXCD_SHAPE_BOX) ? CLASS_HULL_BOX : CLASS_HULL_LIGHT;
+        return (typeA == AXCD_SHAPE_BOX) ? CLASS_BOX_HULL : CLASS_LIGHT_HULL;
+    }
+    if (typeA == AXCD_SHAPE_CAPSULE || typeB == AXCD_SHAPE_CAPSULE) return CLASS_CAPSULE_MIX;
     if (typeA == AXCD_SHAPE_SPHERE) return (typeB == AXCD_SHAPE_SPHERE) ? 1 : 2;   // SS, point-box
     return (typeB == AXCD_SHAPE_SPHERE) ? 3 : 4;                                   // box-point, box-box
 }
@@ -1078,7 +1090,7 @@ __device__ __forceinline__ int pairClass(uint32_t typeA, uint32_t typeB) {
 // (sphere-sphere / sphere-box / box-sphere / box-box / other) and emits chunks of 32 pair indices of
 // ONE class; gjkKernel's warps then claim chunks by ticket, with no block barrier and no mixed warps.
 // Output order does not matter: every result of gjkKernel is stored by pair index.
-constexpr int kClsThreads = 256;
+constexpr int kClsThreads = 384;   // >= kNumClasses * 32: one thread per carry slot
 constexpr int kClsItems = 4;
 constexpr int kClsTile = kClsThreads * kClsItems;
 constexpr uint32_t kNoPair = 0xffffffffu;

@@ -436,6 +436,16 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
             CU(dalloc(&ctx->dSegHi, 2 * P));
         }
         CU(dalloc(&ctx->dNodes32, nb));
+        // scene-query buffers up front (float nodes, scratch for 64 k queries / 1 M hits): no first-use allocation
+        // on the query path; the scratch still grows on demand for larger batches
+        CU(dalloc(&ctx->dNodes, nb));
+        {
+            const size_t nq0 = 65536, hits0 = 1u << 20;
+            CU(cudaMalloc(&ctx->dQIn, nq0 * 32));        ctx->qInBytes = nq0 * 32;
+            CU(cudaMalloc(&ctx->dQCount, nq0 * 16));     ctx->qCountBytes = nq0 * 16;
+            CU(cudaMalloc(&ctx->dQSeg, hits0 * 4));      ctx->qSegBytes = hits0 * 4;
+            CU(cudaMalloc(&ctx->dQOut, hits0 * 8));      ctx->qOutBytes = hits0 * 8;
+        }
         CU(dalloc(&ctx->dEpaWork, (size_t)cfg->maxContacts));
         CU(dalloc(&ctx->dEpaOverflow, (size_t)cfg->maxContacts));
         ctx->spillCap = cfg->maxContacts < 65536u ? cfg->maxContacts : 65536u;

@@ -75,8 +75,8 @@ def _run_ranks(size, scene_name, scale, steps=4):
     return result
 
 
-@pytest.mark.parametrize("size,scene_name,scale", [(2, "C1", 1.0), (2, "C2", 0.1), (4, "C1", 1.0)],
-                         ids=["2gpu-boxes-spheres-100k", "2gpu-hull-mix-100k", "4gpu-boxes-spheres-100k"])
+@pytest.mark.parametrize("size,scene_name,scale", [(2, "C1", 1.0), (2, "C2", 0.1), (2, "C4", 0.0625), (4, "C1", 1.0)],
+                         ids=["2gpu-boxes-spheres-100k", "2gpu-hull-mix-100k", "2gpu-c4-density-1m", "4gpu-boxes-spheres-100k"])
 def test_slab_exchange_over_nccl_union_equals_single_gpu(size, scene_name, scale):
     """C2: 30 % convex hulls — a hull ghost's vertices travel with its record."""
     import torch

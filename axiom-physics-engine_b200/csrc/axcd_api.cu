@@ -817,7 +817,9 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         // few resident waves.
         const uint32_t mp = ctx->cfg.maxPairs;
         uint32_t tiles = (mp + kGjkThreads - 1) / kGjkThreads;
+        uint32_t closedTiles = tiles;
         if (tiles > (uint32_t)ctx->numSMs * AXCD_GJK_MIN_BLOCKS) tiles = ctx->numSMs * AXCD_GJK_MIN_BLOCKS;   // one resident wave
+        if (closedTiles > (uint32_t)ctx->numSMs * AXCD_CLOSED_MIN_BLOCKS) closedTiles = ctx->numSMs * AXCD_CLOSED_MIN_BLOCKS;
         const uint32_t slotTilesMax = (mp + kSlotTile - 1) / kSlotTile;
         const uint32_t slotBlocks = slotTilesMax < (uint32_t)ctx->numSMs * 4 ? slotTilesMax : ctx->numSMs * 4;
         // the slot scan's status words were cleared by this step's Morton kernel; a step that reused the
@@ -847,7 +849,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
         } else {
         classifyPairsKernel<<<classifyBlocksFor(mp), kClsThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dChunks,
                                                                             chunkCap, genericMask, ctx->dCtr);
-        closedFormKernel<<<tiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dFlags,
+        closedFormKernel<<<closedTiles, kGjkThreads, 0, st>>>(pairs, ctx->dChunks, chunkCap, ctx->dXf, ctx->dShapes, ctx->dFlags,
                                                         ctx->dTmpContacts, ctx->dPairDist, ctx->dCtr);
         // cylinder-capable instantiations only where a cylinder can occur (ghost bodies of a slab may be cylinders)
         const bool cyl = ctx->hasCylinders || ctx->slabOn || ctx->n != ctx->nOwned;

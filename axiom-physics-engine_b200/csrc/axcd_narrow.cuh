@@ -238,7 +238,7 @@ __device__ __forceinline__ V3 closestSegment(V3 a, V3 b, float& la, float& lb, i
 }
 
 // Closest point to the origin on triangle (a,b,c), Voronoi-region walk; mask bits a=1, b=2, c=4.
-__device__ __noinline__ V3 closestTriangle(V3 a, V3 b, V3 c, float& la, float& lb, float& lc, int& mask) {
+__device__ __forceinline__ V3 closestTriangleInline(V3 a, V3 b, V3 c, float& la, float& lb, float& lc, int& mask) {
     const V3 ab = b - a, ac = c - a;
     const float d1 = -dot3(ab, a), d2 = -dot3(ac, a);
     if (d1 <= 0.0f && d2 <= 0.0f) {
@@ -279,6 +279,11 @@ __device__ __noinline__ V3 closestTriangle(V3 a, V3 b, V3 c, float& la, float& l
     return (a + ab * v) + ac * w;
 }
 
+// The same as a call, for the places that run once per pair (EPA set-up and witness points).
+__device__ __noinline__ V3 closestTriangle(V3 a, V3 b, V3 c, float& la, float& lb, float& lc, int& mask) {
+    return closestTriangleInline(a, b, c, la, lb, lc, mask);
+}
+
 // Origin strictly on the far side of plane (a,b,c) from d?  A flat tetrahedron counts as outside.
 __device__ __forceinline__ bool originOutside(V3 a, V3 b, V3 c, V3 d) {
     const V3 n = cross3(b - a, c - a);
@@ -290,6 +295,9 @@ __device__ __forceinline__ bool originOutside(V3 a, V3 b, V3 c, V3 d) {
 }
 
 // Reduce the simplex to the feature closest to the origin; returns that point, sets lam[].
+// Every index into the simplex arrays is a compile-time constant (selects instead of s.y[f], a shift network
+// instead of s.y[n++] = s.y[i]) so the simplex stays in registers, and the triangle code is instantiated once:
+// a triangle is the tetrahedron loop's face 0 without the sidedness test.
 __device__ __forceinline__ V3 solveSimplex(Simplex& s, bool& enclosed) {
     enclosed = false;
     int mask = 0;
@@ -297,31 +305,43 @@ __device__ __forceinline__ V3 solveSimplex(Simplex& s, bool& enclosed) {
     V3 v = mk3(0.f, 0.f, 0.f);
     if (s.n == 2) {
         v = closestSegment(s.y[0], s.y[1], l0, l1, mask);
-    } else if (s.n == 3) {
-        v = closestTriangle(s.y[0], s.y[1], s.y[2], l0, l1, l2, mask);
     } else {
+        const bool tetra = s.n == 4;
+        const int nFaces = tetra ? 4 : 1;
         float best = FLT_MAX;
-        bool any = false;
+        bool any = !tetra;
         // faces (i,j,k | opposite o): (0,1,2|3) (0,2,3|1) (0,3,1|2) (1,3,2|0), examined in this order
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            const int i = (f == 3) ? 1 : 0;
-            const int j = (f == 0) ? 1 : ((f == 1) ? 2 : 3);
-            const int k = (f == 0) ? 2 : ((f == 1) ? 3 : ((f == 2) ? 1 : 2));
-            const int o = (f == 0) ? 3 : ((f == 1) ? 1 : ((f == 2) ? 2 : 0));
-            if (!originOutside(s.y[i], s.y[j], s.y[k], s.y[o])) continue;
-            any = true;
+#pragma unroll 1
+        for (int f = 0; f < nFaces; ++f) {
+            const V3 a = (f == 3) ? s.y[1] : s.y[0];
+            const V3 b = (f == 0) ? s.y[1] : ((f == 1) ? s.y[2] : s.y[3]);
+            const V3 c = (f == 0) ? s.y[2] : ((f == 1) ? s.y[3] : ((f == 2) ? s.y[1] : s.y[2]));
+            if (tetra) {
+                const V3 o = (f == 0) ? s.y[3] : ((f == 1) ? s.y[1] : ((f == 2) ? s.y[2] : s.y[0]));
+                if (!originOutside(a, b, c, o)) continue;
+                any = true;
+            }
             float li, lj, lk;
             int m;
-            const V3 q = closestTriangle(s.y[i], s.y[j], s.y[k], li, lj, lk, m);
+            const V3 q = closestTriangleInline(a, b, c, li, lj, lk, m);
             const float qq = dot3(q, q);
-            if (qq < best) {
+            if (!tetra || qq < best) {
                 best = qq;
                 v = q;
-                float l[4] = {0.f, 0.f, 0.f, 0.f};
-                l[i] = li; l[j] = lj; l[k] = lk;
-                l0 = l[0]; l1 = l[1]; l2 = l[2]; l3 = l[3];
-                mask = ((m & 1) ? (1 << i) : 0) | ((m & 2) ? (1 << j) : 0) | ((m & 4) ? (1 << k) : 0);
+                const int b0 = m & 1, b1 = (m >> 1) & 1, b2 = (m >> 2) & 1;
+                if (f == 0) {
+                    l0 = li; l1 = lj; l2 = lk; l3 = 0.f;
+                    mask = m;
+                } else if (f == 1) {
+                    l0 = li; l1 = 0.f; l2 = lj; l3 = lk;
+                    mask = b0 | (b1 << 2) | (b2 << 3);
+                } else if (f == 2) {
+                    l0 = li; l1 = lk; l2 = 0.f; l3 = lj;
+                    mask = b0 | (b1 << 3) | (b2 << 1);
+                } else {
+                    l0 = 0.f; l1 = li; l2 = lk; l3 = lj;
+                    mask = (b0 << 1) | (b1 << 3) | (b2 << 2);
+                }
             }
         }
         if (!any) {
@@ -329,18 +349,21 @@ __device__ __forceinline__ V3 solveSimplex(Simplex& s, bool& enclosed) {
             return mk3(0.f, 0.f, 0.f);
         }
     }
-    const float l[4] = {l0, l1, l2, l3};
-    int n = 0;
+    s.lam[0] = l0; s.lam[1] = l1; s.lam[2] = l2; s.lam[3] = l3;
+    mask &= (1 << s.n) - 1;
+    // keep the points whose bit is set, in order: drop from the top so lower indices stay put
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (i < s.n && (mask & (1 << i))) {
-            s.y[n] = s.y[i];
-            s.id[n] = s.id[i];
-            s.lam[n] = l[i];
-            ++n;
+    for (int i = 3; i >= 0; --i) {
+        if (!((mask >> i) & 1)) {
+#pragma unroll
+            for (int j = i; j < 3; ++j) {
+                s.y[j] = s.y[j + 1];
+                s.id[j] = s.id[j + 1];
+                s.lam[j] = s.lam[j + 1];
+            }
         }
     }
-    s.n = n;
+    s.n = __popc((uint32_t)mask);
     return v;
 }
 
@@ -385,10 +408,15 @@ __device__ __forceinline__ GjkResult gjk(const CoreT<CYL>& A, const CoreT<CYL>& 
         }
         if (vv - vw <= cfg.gjkTol * vv) break;
         bool dup = false;
-        for (int i = 0; i < s.n; ++i) dup = dup || same3(w, s.y[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dup = dup || (i < s.n && same3(w, s.y[i]));
         if (dup) break;
-        s.y[s.n] = w;
-        s.id[s.n] = wid;
+#pragma unroll
+        for (int i = 1; i < 4; ++i)   // s.n is 1..3 here (solveSimplex never leaves four points)
+            if (s.n == i) {
+                s.y[i] = w;
+                s.id[i] = wid;
+            }
         s.n++;
         bool enclosed;
         const V3 nv = solveSimplex(s, enclosed);
@@ -1489,7 +1517,7 @@ __device__ __noinline__ BoxBox boxBoxCall(const BodyPose& ta, uint4 sa, const Bo
 // overlapping; record written to tmp[k]), 2 = cores overlap (EpaWork queued; EPA writes the record).
 // Contact slots are assigned afterwards, in pair order, by slotKernel.
 #ifndef AXCD_GJK_MIN_BLOCKS
-#define AXCD_GJK_MIN_BLOCKS 5
+#define AXCD_GJK_MIN_BLOCKS 4   // 128 registers; C2 GJK stage with 3 / 4 / 5 / 6 blocks: 0.646 / 0.589 / 0.621 / 0.653 ms
 #endif
 template <bool CYL>
 __global__ void __launch_bounds__(kGjkThreads, AXCD_GJK_MIN_BLOCKS)
@@ -1553,7 +1581,9 @@ gjkKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ chunks, 
                     kind = 1;
                     n = -(g.v * (1.0f / len));
                     V3 ca = mk3(0.f, 0.f, 0.f);
-                    for (int i = 0; i < s.n; ++i) ca = ca + pointFromId(A, s.id[i] & 0xffffu) * s.lam[i];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < s.n) ca = ca + pointFromId(A, s.id[i] & 0xffffu) * s.lam[i];
                     const V3 pa = ca + n * A.r;
                     const V3 pb = (ca - g.v) - n * B.r;
                     pos = (pa + pb) * 0.5f + origin;

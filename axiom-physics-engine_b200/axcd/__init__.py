@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_step_async",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
-    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_pin_host_buffer", "axcd_unpin_host_buffer",
+    "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_ccd_pairs_angular", "axcd_pin_host_buffer", "axcd_unpin_host_buffer",
     "axcd_set_filters", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts", "axcd_pack_ghosts",
     "axcd_set_ghosts_device", "axcd_nccl_unique_id", "axcd_slab_init", "axcd_slab_init_comm",
     "axcd_slab_step_async", "axcd_slab_step", "axcd_get_body_keys",
@@ -121,7 +121,7 @@ def load_library():
                      "axcd_get_contacts", "axcd_test_sort_pairs32", "axcd_test_sort_keys64",
                      "axcd_test_sort_bench", "axcd_set_slab", "axcd_set_body_keys", "axcd_set_ghosts",
                      "axcd_pack_ghosts", "axcd_set_ghosts_device", "axcd_set_filters",
-                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_pin_host_buffer", "axcd_unpin_host_buffer"):
+                     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_ccd_pairs_angular", "axcd_pin_host_buffer", "axcd_unpin_host_buffer"):
             getattr(lib, name).restype = C.c_int32
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
@@ -154,6 +154,7 @@ def load_library():
         lib.axcd_pin_host_buffer.argtypes = [C.c_void_p, C.c_uint64]
         lib.axcd_unpin_host_buffer.argtypes = [C.c_void_p]
         lib.axcd_ccd_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.axcd_ccd_pairs_angular.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.axcd_raycast.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.axcd_test_sort_pairs32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                C.c_uint32]
@@ -476,14 +477,21 @@ class CollisionWorld:
         self._check(self._lib.axcd_raycast(self._ctx, _ptr(rays), len(rays), _ptr(out)), "axcd_raycast")
         return out[:len(rays)]
 
-    def ccd_pairs(self, pairs, displacement):
-        """Time of impact of body pairs under linear motion; displacement is (n,3) per body."""
+    def ccd_pairs(self, pairs, displacement, rotation=None):
+        """Time of impact of body pairs; displacement is (n,3) per body.  rotation (n,3): one rotation vector per
+        body (angular velocity * dt) — the sweep then includes the turning (axcd_ccd_pairs_angular)."""
         pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
         disp = np.ascontiguousarray(displacement, dtype=np.float32).reshape(-1, 3)
         assert len(disp) == self.n
         out = np.zeros(max(1, len(pairs)), SWEEP_DT)
-        self._check(self._lib.axcd_ccd_pairs(self._ctx, _ptr(pairs), len(pairs), _ptr(disp), _ptr(out)),
-                    "axcd_ccd_pairs")
+        if rotation is None:
+            self._check(self._lib.axcd_ccd_pairs(self._ctx, _ptr(pairs), len(pairs), _ptr(disp), _ptr(out)),
+                        "axcd_ccd_pairs")
+        else:
+            rot = np.ascontiguousarray(rotation, dtype=np.float32).reshape(-1, 3)
+            assert len(rot) == self.n
+            self._check(self._lib.axcd_ccd_pairs_angular(self._ctx, _ptr(pairs), len(pairs), _ptr(disp), _ptr(rot), _ptr(out)),
+                        "axcd_ccd_pairs_angular")
         return out[:len(pairs)]
 
     def set_awake(self, awake):

@@ -1270,8 +1270,8 @@ int32_t axcd_raycast(AxcdContext* ctx, const AxcdRay* rays, uint32_t nq, AxcdRay
     return AXCD_OK;
 }
 
-int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs, const float* displacement3,
-                       AxcdSweep* out) {
+static int32_t ccdPairsImpl(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs, const float* displacement3,
+                            const float* rotation3, AxcdSweep* out) {
     if (!ctx || (npairs && (!pairs2 || !displacement3 || !out))) return AXCD_ERR_NULL_POINTER;
     if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;
     if (npairs == 0) return AXCD_OK;
@@ -1280,14 +1280,17 @@ int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs
         if (pairs2[k] >= ctx->n) return AXCD_ERR_OUT_OF_RANGE;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     cudaStream_t st = ctx->stream;
-    // scratch: pairs | displacements in dQIn, results in dQOut
+    // scratch: pairs | displacements | rotation vectors in dQIn, results in dQOut
     const size_t pairBytes = ((size_t)npairs * 8 + 15) & ~(size_t)15;
-    CU(growScratch(&ctx->dQIn, &ctx->qInBytes, pairBytes + (size_t)ctx->n * 12));
+    const size_t vecBytes = ((size_t)ctx->n * 12 + 15) & ~(size_t)15;
+    CU(growScratch(&ctx->dQIn, &ctx->qInBytes, pairBytes + 2 * vecBytes));
     CU(growScratch(&ctx->dQOut, &ctx->qOutBytes, (size_t)npairs * sizeof(AxcdSweep)));
     uint2* dPairs = static_cast<uint2*>(ctx->dQIn);
     float* dDisp = reinterpret_cast<float*>(static_cast<char*>(ctx->dQIn) + pairBytes);
+    float* dRot = reinterpret_cast<float*>(static_cast<char*>(ctx->dQIn) + pairBytes + vecBytes);
     CU(cudaMemcpyAsync(dPairs, pairs2, (size_t)npairs * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(dDisp, displacement3, (size_t)ctx->n * 12, cudaMemcpyHostToDevice, st));
+    if (rotation3) CU(cudaMemcpyAsync(dRot, rotation3, (size_t)ctx->n * 12, cudaMemcpyHostToDevice, st));
     NarrowParams p;
     p.gjkMaxIters = ctx->cfg.gjkMaxIters;
     p.epaMaxIters = ctx->cfg.epaMaxIters;
@@ -1296,16 +1299,31 @@ int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs
     p.epaTol = ctx->cfg.epaTol;
     p.wantDistances = 1u;
     p.boxBoxGeneric = 0u;
-    if (ctx->hasCylinders || ctx->n != ctx->nOwned)
-        ccdKernel<true><<<(npairs + kCcdThreads - 1) / kCcdThreads, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull,
-                                                                                         dDisp, p, static_cast<uint32_t*>(ctx->dQOut));
-    else
-        ccdKernel<false><<<(npairs + kCcdThreads - 1) / kCcdThreads, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull,
-                                                                                          dDisp, p, static_cast<uint32_t*>(ctx->dQOut));
+    const bool cyl = ctx->hasCylinders || ctx->n != ctx->nOwned;
+    const uint32_t blocks = (npairs + kCcdThreads - 1) / kCcdThreads;
+    uint32_t* dOut = static_cast<uint32_t*>(ctx->dQOut);
+    if (rotation3) {
+        if (cyl) ccdAngularKernel<true><<<blocks, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull, dDisp, dRot, p, dOut);
+        else ccdAngularKernel<false><<<blocks, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull, dDisp, dRot, p, dOut);
+    } else {
+        if (cyl) ccdKernel<true><<<blocks, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull, dDisp, p, dOut);
+        else ccdKernel<false><<<blocks, kCcdThreads, 0, st>>>(dPairs, npairs, ctx->dXf, ctx->dShapes, ctx->dHull, dDisp, p, dOut);
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, ctx->dQOut, (size_t)npairs * sizeof(AxcdSweep), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return AXCD_OK;
+}
+
+int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs, const float* displacement3,
+                       AxcdSweep* out) {
+    return ccdPairsImpl(ctx, pairs2, npairs, displacement3, nullptr, out);
+}
+
+int32_t axcd_ccd_pairs_angular(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs, const float* displacement3,
+                               const float* rotation3, AxcdSweep* out) {
+    if (npairs && !rotation3) return AXCD_ERR_NULL_POINTER;
+    return ccdPairsImpl(ctx, pairs2, npairs, displacement3, rotation3, out);
 }
 
 int32_t axcd_set_awake(AxcdContext* ctx, const uint8_t* awake, uint32_t n) {

@@ -67,6 +67,107 @@ __device__ __forceinline__ SweepResult sweepCores(const CoreT<CYL>& A, CoreT<CYL
     return out;
 }
 
+// ---- CCD with rotation ---------------------------------------------------------------------------------
+// Each body moves by disp * t and turns by its rotation vector w (angular velocity * dt, world frame) under
+// first-order integration, q(t) = normalize(q + t * 0.5 * (w, 0) (x) q) — algebraic, bit-identical to the oracle.
+// The turning rate of that path never exceeds |w|, so with rho = the largest distance of a core point from its
+// body's position, gap / (approach of the origins along the closest direction + |wA| rhoA + |wB| rhoB) is a lower
+// bound of the time to contact; both cores are rebuilt from the poses at t every step.
+constexpr int kCcdAngMaxIters = 64;
+
+__device__ __forceinline__ BodyPose poseAt(const BodyPose& t0, V3 d, float4 dq, float t) {
+    BodyPose o = t0;
+    o.p = t0.p + d * t;
+    const float4 u = make_float4(t0.q.x + dq.x * t, t0.q.y + dq.y * t, t0.q.z + dq.z * t, t0.q.w + dq.w * t);
+    const float len2 = (u.x * u.x + u.y * u.y) + (u.z * u.z + u.w * u.w);
+    const float inv = 1.0f / sqrtf(len2);
+    o.q = make_float4(u.x * inv, u.y * inv, u.z * inv, u.w * inv);
+    return o;
+}
+__device__ __forceinline__ float4 halfSpin(V3 w, float4 q) {   // 0.5 * (w, 0) (x) q
+    const V3 qv = mk3(q.x, q.y, q.z);
+    const V3 v = cross3(w, qv) + w * q.w;
+    return make_float4(v.x * 0.5f, v.y * 0.5f, v.z * 0.5f, -dot3(w, qv) * 0.5f);
+}
+template <bool CYL>
+__device__ __forceinline__ float coreReach(const CoreT<CYL>& k) {
+    if (k.kind == CORE_POINT) return 0.0f;
+    if (k.kind == CORE_SEGMENT) return sqrtf(dot3(k.e0, k.e0));
+    if (k.kind == CORE_BOX || k.kind == CORE_CYLINDER) return sqrtf((dot3(k.e0, k.e0) + dot3(k.e1, k.e1)) + dot3(k.e2, k.e2));
+    float best = 0.0f;
+    for (uint32_t i = 0; i < k.nv; ++i) {
+        const float4 v = __ldg(k.verts + i);
+        const V3 lv = mk3(v.x * k.s.x, v.y * k.s.y, v.z * k.s.z);
+        const float d2 = dot3(lv, lv);
+        if (d2 > best) best = d2;
+    }
+    return sqrtf(best);
+}
+
+template <bool CYL>
+__global__ void __launch_bounds__(kCcdThreads)
+ccdAngularKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restrict__ xf, const uint4* __restrict__ shapes,
+                 const float4* __restrict__ hull, const float* __restrict__ disp, const float* __restrict__ rot, NarrowParams cfg,
+                 uint32_t* __restrict__ out) {
+    const uint32_t k = blockIdx.x * kCcdThreads + threadIdx.x;
+    if (k >= npairs) return;
+    cfg.wantDistances = 1u;
+    const uint2 pr = __ldg(pairs + k);
+    const BodyPose ta = loadPose(xf, pr.x), tb = loadPose(xf, pr.y);
+    const uint4 sa = __ldg(shapes + pr.x), sb = __ldg(shapes + pr.y);
+    const V3 origin = ta.p;
+    auto vec = [](const float* __restrict__ p, uint32_t i) { return mk3(__ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2)); };
+    const V3 D = vec(disp, pr.y) - vec(disp, pr.x);
+    const V3 rotA = vec(rot, pr.x), rotB = vec(rot, pr.y);
+    const float4 dqA = halfSpin(rotA, ta.q), dqB = halfSpin(rotB, tb.q);
+    const V3 zero = mk3(0.f, 0.f, 0.f);
+    const float spin = sqrtf(dot3(rotA, rotA)) * coreReach(makeCore<CYL>(ta, sa, hull, origin)) +
+                       sqrtf(dot3(rotB, rotB)) * coreReach(makeCore<CYL>(tb, sb, hull, origin));
+    SweepResult o{0u, 1.0f, zero, 0u};
+    V3 nLast = zero;
+    float t = 0.0f;
+    int it = 0;
+    for (; it < kCcdAngMaxIters; ++it) {
+        const CoreT<CYL> A = makeCore<CYL>(poseAt(ta, zero, dqA, t), sa, hull, origin);
+        const CoreT<CYL> B = makeCore<CYL>(poseAt(tb, D, dqB, t), sb, hull, origin);
+        const float rs = A.r + B.r;
+        Simplex s;
+        const GjkResult g = gjk(A, B, cfg, rs, s);
+        if (g.state == GJK_OVERLAP) {
+            o.hit = 1u;
+            o.toi = t;
+            o.n = nLast;
+            break;
+        }
+        const float dist = sqrtf(g.vv);
+        const float gap = dist - rs;
+        const V3 n = -(g.v * (1.0f / dist));
+        nLast = n;
+        if (gap <= kCcdTol) {
+            o.hit = 1u;
+            o.toi = t;
+            o.n = n;
+            break;
+        }
+        const float approach = dot3(D, g.v) / dist + spin;
+        if (!(approach > 0.0f)) break;
+        t = t + gap / approach;
+        if (!(t <= 1.0f)) break;
+    }
+    if (it == kCcdAngMaxIters) {   // conservative: contact at the time reached
+        o.hit = 1u;
+        o.toi = t;
+        o.n = nLast;
+    }
+    uint32_t* w = out + (size_t)k * 6;
+    w[0] = o.hit;
+    w[1] = __float_as_uint(o.toi);
+    w[2] = __float_as_uint(o.n.x);
+    w[3] = __float_as_uint(o.n.y);
+    w[4] = __float_as_uint(o.n.z);
+    w[5] = (uint32_t)it;
+}
+
 template <bool CYL>
 __global__ void __launch_bounds__(kCcdThreads)
 ccdKernel(const uint2* __restrict__ pairs, uint32_t npairs, const float* __restrict__ xf, const uint4* __restrict__ shapes,

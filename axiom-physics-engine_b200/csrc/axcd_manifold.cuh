@@ -9,8 +9,8 @@
 // reference face kept (position = midpoint between the vertex and its projection onto the face,
 // depth = distance below the face), reduced to at most four (deepest, farthest from it, largest
 // triangle, farthest outside that triangle).  Capsule-box contacts clip the capsule's segment against the
-// facing box face (1..2 points).  Every other pair class, and a clip that comes out empty, keeps the
-// narrowphase point.  Same expression trees as the CPU oracle.
+// facing box face (1..2 points); capsule-capsule contacts with (nearly) parallel axes get the two ends of the
+// overlapping stretch.  Every other pair class, and a clip that comes out empty, keeps the narrowphase point.  Same expression trees as the CPU oracle.
 //
 // Tiles of 256 contacts per 128-thread block; the 88-byte records are staged in shared memory and
 // written with coalesced 128-bit stores; box-box contacts are compacted and clipped densely.  Algorithmic bytes: 40 B contact + 2 x 56 B pose/shape
@@ -225,6 +225,37 @@ __device__ __forceinline__ int capsuleBoxManifold(const BoxFrame& R, V3 cc, V3 e
     return cnt;
 }
 
+// Capsule against capsule with (nearly) parallel axes (|eA x eB|^2 <= 1e-2 |eA|^2 |eB|^2): the two ends of the
+// stretch of A's segment that B's segment overlaps; an end is kept when the surfaces overlap there along the
+// contact normal.  Frame centred on body a (A's segment is -eA..eA).  Returns the number of points (0: the
+// narrowphase point stands).
+__device__ __forceinline__ int capsuleCapsuleManifold(V3 eA, float rA, V3 cB, V3 eB, float rB, V3 n, V3* __restrict__ outPos,
+                                                      float* __restrict__ outDep) {
+    const float aa = dot3(eA, eA), bb = dot3(eB, eB);
+    if (!(aa > 0.0f && bb > 0.0f)) return 0;
+    const V3 cr = cross3(eA, eB);
+    if (!(dot3(cr, cr) <= 1e-2f * (aa * bb))) return 0;
+    const float tc = dot3(cB, eA) / aa, te = dot3(eB, eA) / aa;
+    float lo = tc - te, hi = tc + te;
+    if (lo > hi) { const float t = lo; lo = hi; hi = t; }
+    if (lo < -1.0f) lo = -1.0f;
+    if (hi > 1.0f) hi = 1.0f;
+    if (!(lo < hi)) return 0;
+    int cnt = 0;
+    for (int k = 0; k < 2; ++k) {
+        const V3 pA = eA * (k ? hi : lo);
+        const float sB = dot3(pA - cB, eB) / bb;
+        const V3 pB = cB + eB * sB;
+        const float sep = dot3(pB - pA, n) - (rA + rB);
+        if (sep <= 0.0f) {
+            outPos[cnt] = ((pA + n * rA) + (pB - n * rB)) * 0.5f;
+            outDep[cnt] = -sep;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
 // One block handles tiles of kManTile contacts: every thread writes the single-point record of its
 // contacts into the shared staging area, the tile's box-box contacts are compacted into a list, and the
 // first threads of the block clip them with all lanes busy (polygons in shared-memory columns, nothing
@@ -262,7 +293,7 @@ manifoldKernel(const AxcdContact* __restrict__ contacts, const uint32_t* __restr
             const uint32_t tyA = __ldg(&shapes[a].x), tyB = __ldg(&shapes[b].x);
             // contacts that get more than the narrowphase point: box-box and capsule-box
             const bool bb = (tyA == AXCD_SHAPE_BOX && (tyB == AXCD_SHAPE_BOX || tyB == AXCD_SHAPE_CAPSULE)) ||
-                            (tyA == AXCD_SHAPE_CAPSULE && tyB == AXCD_SHAPE_BOX);
+                            (tyA == AXCD_SHAPE_CAPSULE && (tyB == AXCD_SHAPE_BOX || tyB == AXCD_SHAPE_CAPSULE));
             const uint32_t bal = __ballot_sync(__activemask(), bb);
             if (bb) {
                 const int lane = tid & 31;
@@ -286,6 +317,24 @@ manifoldKernel(const AxcdContact* __restrict__ contacts, const uint32_t* __restr
             const BodyPose ta = loadPose(xf, a), tb = loadPose(xf, b);
             const V3 origin = ta.p;
             const uint4 sa = __ldg(shapes + a), sb = __ldg(shapes + b);
+            if (sa.x == AXCD_SHAPE_CAPSULE && sb.x == AXCD_SHAPE_CAPSULE) {
+                V3 c0, c1, c2;
+                quatToColumns(ta.q, c0, c1, c2);
+                const V3 eA = c1 * ((__uint_as_float(sa.z) * 0.5f) * ta.s.y);
+                quatToColumns(tb.q, c0, c1, c2);
+                const V3 eB = c1 * ((__uint_as_float(sb.z) * 0.5f) * tb.s.y);
+                V3 cp[2];
+                float cd[2];
+                const int nc = capsuleCapsuleManifold(eA, __uint_as_float(sa.y), tb.p - origin, eB, __uint_as_float(sb.y), n, cp, cd);
+                if (nc == 0) continue;
+                for (int k = 0; k < nc; ++k) {
+                    const V3 w = cp[k] + origin;
+                    o[6 + k] = w.x; o[10 + k] = w.y; o[14 + k] = w.z; o[18 + k] = cd[k];
+                }
+                reinterpret_cast<uint32_t*>(o)[5] = (uint32_t)nc;
+                extra += (uint32_t)nc - 1u;
+                continue;
+            }
             if (sa.x == AXCD_SHAPE_CAPSULE || sb.x == AXCD_SHAPE_CAPSULE) {
                 const bool boxIsA = sa.x == AXCD_SHAPE_BOX;
                 const BoxFrame R = boxIsA ? makeBoxFrame(ta, sa, origin) : makeBoxFrame(tb, sb, origin);

@@ -281,6 +281,18 @@ typedef struct AxcdSweep {
 AXCD_API int32_t axcd_ccd_pairs(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs,
                                 const float* displacement3, AxcdSweep* out);
 
+/* The same with rotation: rotation3 holds one rotation vector per body (n x 3 floats: angular velocity * dt,
+ * radians, world frame).  Motion model: position p + displacement * t, orientation
+ *     q(t) = normalize(q + t * 0.5 * (w, 0) (x) q)
+ * — the first-order quaternion integration engines step with, so t = 1 is exactly the pose an integrator using it
+ * reaches (and no sin / cos: the CUDA path and the CPU oracle agree bit for bit).  Conservative advancement: the
+ * turning rate of that path never exceeds |w|, so gap / (linear approach + |wA| reachA + |wB| reachB), with reach =
+ * the largest distance of a core point from its body's position, never oversteps the first contact; at most 64
+ * steps, then the time reached is reported as a (conservative) hit.  Same result record and error behaviour as
+ * axcd_ccd_pairs. */
+AXCD_API int32_t axcd_ccd_pairs_angular(AxcdContext* ctx, const uint32_t* pairs2, uint32_t npairs,
+                                        const float* displacement3, const float* rotation3, AxcdSweep* out);
+
 /* Collision filtering, gui::FilterInfo semantics (include/axiom/gui/body_inspector.hpp:38-42):
  * two bodies with the same non-zero groupIndex collide iff it is positive; otherwise both
  * (maskBits & other.categoryBits) must be non-zero.  Applied when candidate pairs are emitted.

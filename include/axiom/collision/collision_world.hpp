@@ -204,6 +204,13 @@ public:
         return wrap(axcd_ccd_pairs(ctx_, reinterpret_cast<const std::uint32_t*>(pairs), count,
                                    reinterpret_cast<const float*>(displacements), out));
     }
+    /// The same with rotation: one rotation vector (angular velocity * dt) per body; see axcd_ccd_pairs_angular.
+    core::Result<void> sweepPairs(const BodyPair* pairs, std::uint32_t count, const math::Vec3* displacements,
+                                  const math::Vec3* rotations, Sweep* out) {
+        return wrap(axcd_ccd_pairs_angular(ctx_, reinterpret_cast<const std::uint32_t*>(pairs), count,
+                                           reinterpret_cast<const float*>(displacements),
+                                           reinterpret_cast<const float*>(rotations), out));
+    }
     /// The fused step without the final synchronisation (one CUDA graph launch once the launch
     /// configuration is stable); fetch counts with stats().
     core::Result<void> stepAsync() { return wrap(axcd_step_async(ctx_)); }

@@ -1190,8 +1190,9 @@ PairOut collidePair(uint32_t ia, uint32_t ib, const Xf& ta, const AxrefShape& sa
 // clipped (Sutherland-Hodgman) against the reference face's four side planes; vertices on or below
 // the reference face are kept (position = midpoint between the vertex and its projection onto the
 // reference face, depth = distance below the face) and reduced to at most four.  Capsule-box: the capsule's
-// segment clipped against the facing box face (capsuleBoxManifold, 1..2 points).  Every other class, and a
-// clip that comes out empty, keeps the single narrowphase point.
+// segment clipped against the facing box face (capsuleBoxManifold, 1..2 points).  Capsule-capsule with
+// (nearly) parallel axes: the two ends of the overlapping stretch (capsuleCapsuleManifold, 1..2 points).
+// Every other class, and a clip that comes out empty, keeps the single narrowphase point.
 // ------------------------------------------------------------------------------------------
 inline int argmaxAbs3(const float d[3]) {   // lowest index on ties
     int k = 0;
@@ -1261,6 +1262,51 @@ void capsuleBoxManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& s
     m.count = (uint32_t)cnt;
 }
 
+// Capsule against capsule with (nearly) parallel axes — |eA x eB|^2 <= 1e-2 |eA|^2 |eB|^2, about 5.7 degrees:
+// the stretch of A's segment that B's segment overlaps (B's ends in A's axis coordinate, clamped to [-1, 1])
+// gives two candidate points, one at each end of the stretch; a candidate is kept when the two surfaces overlap
+// there along the contact normal (position = midpoint of the two surface points, depth = overlap along n).
+// Crossed capsules, a degenerate stretch, or no candidate kept: the narrowphase point stands.
+void capsuleCapsuleManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, const Xf& tb, const AxrefShape& sb,
+                            AxrefManifold& m) {
+    const V3 origin = ta.p;
+    const V3 n = mk(c.nx, c.ny, c.nz);
+    const V3 eA = quatToMat3(ta.q).c1 * ((sa.p1 * 0.5f) * ta.s.y);
+    const V3 eB = quatToMat3(tb.q).c1 * ((sb.p1 * 0.5f) * tb.s.y);
+    const V3 cB = tb.p - origin;   // A's centre is the origin
+    const float rA = sa.p0, rB = sb.p0;
+    const float aa = dot(eA, eA), bb = dot(eB, eB);
+    if (!(aa > 0.0f && bb > 0.0f)) return;
+    const V3 cr = cross(eA, eB);
+    if (!(dot(cr, cr) <= 1e-2f * (aa * bb))) return;
+    const float tc = dot(cB, eA) / aa, te = dot(eB, eA) / aa;
+    float lo = tc - te, hi = tc + te;
+    if (lo > hi) { const float t = lo; lo = hi; hi = t; }
+    if (lo < -1.0f) lo = -1.0f;
+    if (hi > 1.0f) hi = 1.0f;
+    if (!(lo < hi)) return;
+    const float tt[2] = {lo, hi};
+    int cnt = 0;
+    for (int k = 0; k < 2; ++k) {
+        const V3 pA = eA * tt[k];
+        const float sB = dot(pA - cB, eB) / bb;
+        const V3 pB = cB + eB * sB;
+        const float sep = dot(pB - pA, n) - (rA + rB);
+        if (sep <= 0.0f) {
+            const V3 w = ((pA + n * rA) + (pB - n * rB)) * 0.5f + origin;
+            m.px[cnt] = w.x; m.py[cnt] = w.y; m.pz[cnt] = w.z;
+            m.depth[cnt] = -sep;
+            ++cnt;
+        }
+    }
+    if (cnt == 0) {
+        m.px[0] = c.px; m.py[0] = c.py; m.pz[0] = c.pz;
+        m.depth[0] = c.depth;
+        return;
+    }
+    m.count = (uint32_t)cnt;
+}
+
 void buildManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, const Xf& tb,
                    const AxrefShape& sb, AxrefManifold& m) {
     m.a = c.a; m.b = c.b;
@@ -1271,6 +1317,10 @@ void buildManifold(const AxrefContact& c, const Xf& ta, const AxrefShape& sa, co
     m.depth[0] = c.depth;
     if ((sa.type == SHAPE_BOX && sb.type == SHAPE_CAPSULE) || (sa.type == SHAPE_CAPSULE && sb.type == SHAPE_BOX)) {
         capsuleBoxManifold(c, ta, sa, tb, sb, m);
+        return;
+    }
+    if (sa.type == SHAPE_CAPSULE && sb.type == SHAPE_CAPSULE) {
+        capsuleCapsuleManifold(c, ta, sa, tb, sb, m);
         return;
     }
     if (sa.type != SHAPE_BOX || sb.type != SHAPE_BOX) return;
@@ -1601,6 +1651,95 @@ void sweepPair(const Xf& ta, const AxrefShape& sa, V3 dispA, const Xf& tb, const
                const float* hull, const AxrefNarrowCfg& cfg, AxrefSweep& out) {
     const V3 origin = ta.p;
     sweepCores(makeCore(ta, sa, hull, origin), makeCore(tb, sb, hull, origin), dispB - dispA, cfg, out);
+}
+
+// ---- CCD with rotation ---------------------------------------------------------------------------------
+// Each body moves by disp * t and turns by its rotation vector w (angular velocity * dt, world frame) under the
+// first-order integration physics engines use:  q(t) = normalize(q + t * 0.5 * (w, 0) (x) q)  — algebraic, so the
+// CUDA path and this restatement produce the same bits (no sin / cos).  The turning rate of that path never
+// exceeds |w|, so a core point at distance <= rho from its body's position moves relative to the body at a speed
+// <= |w| * rho, and
+//     gap / (approach speed of the origins along the closest direction + |wA| rhoA + |wB| rhoB)
+// is a lower bound of the time to contact: conservative advancement as in sweepCores, with both cores rebuilt
+// from the poses at t every step.
+const int CCD_ANG_MAX_ITERS = 64;
+
+inline Xf poseAt(const Xf& t0, V3 d, Q4 dq, float t) {
+    Xf o = t0;
+    o.p = t0.p + d * t;
+    const Q4 u{t0.q.x + dq.x * t, t0.q.y + dq.y * t, t0.q.z + dq.z * t, t0.q.w + dq.w * t};
+    const float len2 = (u.x * u.x + u.y * u.y) + (u.z * u.z + u.w * u.w);
+    const float inv = 1.0f / std::sqrt(len2);
+    o.q = Q4{u.x * inv, u.y * inv, u.z * inv, u.w * inv};
+    return o;
+}
+// 0.5 * (w, 0) (x) q
+inline Q4 halfSpin(V3 w, Q4 q) {
+    const V3 qv = mk(q.x, q.y, q.z);
+    const V3 v = cross(w, qv) + w * q.w;
+    return Q4{v.x * 0.5f, v.y * 0.5f, v.z * 0.5f, -dot(w, qv) * 0.5f};
+}
+// Largest distance of a core point from its body's position.
+inline float coreReach(const Core& k) {
+    if (k.kind == CORE_POINT) return 0.0f;
+    if (k.kind == CORE_SEGMENT) return std::sqrt(dot(k.e0, k.e0));
+    if (k.kind == CORE_BOX || k.kind == CORE_CYLINDER) return std::sqrt((dot(k.e0, k.e0) + dot(k.e1, k.e1)) + dot(k.e2, k.e2));
+    float best = 0.0f;
+    for (uint32_t i = 0; i < k.nv; ++i) {
+        const V3 lv = mk(k.verts[3 * i] * k.s.x, k.verts[3 * i + 1] * k.s.y, k.verts[3 * i + 2] * k.s.z);
+        const float d2 = dot(lv, lv);
+        if (d2 > best) best = d2;
+    }
+    return std::sqrt(best);
+}
+
+void sweepPairAngular(const Xf& ta, const AxrefShape& sa, V3 dispA, V3 rotA, const Xf& tb, const AxrefShape& sb, V3 dispB,
+                      V3 rotB, const float* hull, const AxrefNarrowCfg& cfgIn, AxrefSweep& out) {
+    AxrefNarrowCfg cfg = cfgIn;
+    cfg.wantDistances = 1;
+    const V3 origin = ta.p;
+    const V3 D = dispB - dispA;                      // A's position stays put, B carries the relative translation
+    const Q4 dqA = halfSpin(rotA, ta.q), dqB = halfSpin(rotB, tb.q);
+    const V3 zero = mk(0.0f, 0.0f, 0.0f);
+    const float spin = std::sqrt(dot(rotA, rotA)) * coreReach(makeCore(ta, sa, hull, origin)) +
+                       std::sqrt(dot(rotB, rotB)) * coreReach(makeCore(tb, sb, hull, origin));
+    out = AxrefSweep{0u, 1.0f, 0.0f, 0.0f, 0.0f, 0u};
+    float t = 0.0f;
+    V3 nLast = zero;
+    int it = 0;
+    for (; it < CCD_ANG_MAX_ITERS; ++it) {
+        const Core A = makeCore(poseAt(ta, zero, dqA, t), sa, hull, origin);
+        const Core B = makeCore(poseAt(tb, D, dqB, t), sb, hull, origin);
+        const float rs = A.r + B.r;
+        Simplex s;
+        const GjkResult g = gjk(A, B, cfg, rs, s);
+        if (g.state == GJK_OVERLAP) {
+            out.hit = 1u;
+            out.toi = t;
+            out.nx = nLast.x; out.ny = nLast.y; out.nz = nLast.z;
+            break;
+        }
+        const float dist = std::sqrt(g.vv);
+        const float gap = dist - rs;
+        const V3 n = -(g.v * (1.0f / dist));   // from a to b
+        nLast = n;
+        if (gap <= CCD_TOL) {
+            out.hit = 1u;
+            out.toi = t;
+            out.nx = n.x; out.ny = n.y; out.nz = n.z;
+            break;
+        }
+        const float approach = dot(D, g.v) / dist + spin;
+        if (!(approach > 0.0f)) break;               // moving apart faster than any turning can close the gap
+        t = t + gap / approach;
+        if (!(t <= 1.0f)) break;
+    }
+    if (it == CCD_ANG_MAX_ITERS) {                   // conservative: contact at the time reached
+        out.hit = 1u;
+        out.toi = t;
+        out.nx = nLast.x; out.ny = nLast.y; out.nz = nLast.z;
+    }
+    out.iterations = (uint32_t)it;
 }
 
 // Ray against a convex hull: the ray origin is a point core at rest, the hull moves by -d * tMax; the
@@ -2026,5 +2165,37 @@ int32_t axref_ccd_pairs(const float* xf, const AxrefShape* shapes, uint32_t n, c
     return 0;
 }
 
+
+int32_t axref_ccd_pairs_angular(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                                const uint32_t* pairs, uint64_t npairs, const float* disp, const float* rot,
+                                const AxrefNarrowCfg* cfg, AxrefSweep* out, int nthreads) {
+    if (!cfg || (npairs && (!pairs || !disp || !rot || !out))) return 202;
+    std::vector<int> err((size_t)std::max(1, nthreads), 0);
+    parallelFor(npairs, nthreads, [&](int t, uint64_t lo, uint64_t hi) {
+        for (uint64_t k = lo; k < hi; ++k) {
+            const uint32_t a = pairs[2 * k], b = pairs[2 * k + 1];
+            if (a >= n || b >= n) {
+                err[(size_t)t] = 601;
+                continue;
+            }
+            sweepPairAngular(loadXf(xf + 10ull * a), shapes[a], mk(disp[3ull * a], disp[3ull * a + 1], disp[3ull * a + 2]),
+                             mk(rot[3ull * a], rot[3ull * a + 1], rot[3ull * a + 2]), loadXf(xf + 10ull * b), shapes[b],
+                             mk(disp[3ull * b], disp[3ull * b + 1], disp[3ull * b + 2]),
+                             mk(rot[3ull * b], rot[3ull * b + 1], rot[3ull * b + 2]), hullXYZ, *cfg, out[k]);
+        }
+    });
+    for (int e : err)
+        if (e) return e;
+    return 0;
+}
+
+// Pose of a body at parameter t of the CCD-with-rotation motion model (tests sample it to validate the sweep).
+void axref_ccd_pose_at(const float* xf10, const float* disp3, const float* rot3, float t, float* out10) {
+    const Xf t0 = loadXf(xf10);
+    const Xf o = poseAt(t0, mk(disp3[0], disp3[1], disp3[2]), halfSpin(mk(rot3[0], rot3[1], rot3[2]), t0.q), t);
+    out10[0] = o.p.x; out10[1] = o.p.y; out10[2] = o.p.z;
+    out10[3] = o.q.x; out10[4] = o.q.y; out10[5] = o.q.z; out10[6] = o.q.w;
+    out10[7] = o.s.x; out10[8] = o.s.y; out10[9] = o.s.z;
+}
 
 }   // extern "C"

@@ -107,6 +107,12 @@ typedef struct AxrefSweep { uint32_t hit; float toi, nx, ny, nz; uint32_t iterat
 int32_t axref_ccd_pairs(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
                         const uint32_t* pairs, uint64_t npairs, const float* disp, const AxrefNarrowCfg* cfg,
                         AxrefSweep* out, int nthreads);
+/* CCD with rotation: rot = one rotation vector (angular velocity * dt) per body; q(t) = normalize(q + t/2 (w,0)(x)q). */
+int32_t axref_ccd_pairs_angular(const float* xf, const AxrefShape* shapes, uint32_t n, const float* hullXYZ,
+                                const uint32_t* pairs, uint64_t npairs, const float* disp, const float* rot,
+                                const AxrefNarrowCfg* cfg, AxrefSweep* out, int nthreads);
+void axref_ccd_pose_at(const float* xf10, const float* disp3, const float* rot3, float t, float* out10);
+
 
 /* one pair, for closed-form checks: returns 1 if contact. dist = core GJK distance minus radii
  * (<= 0 for contacts; exact only when cfg->wantDistances).                                    */

@@ -229,7 +229,7 @@ def raycast(xf, shapes, aabb, rays, world_id=None, nthreads=8, hull=None):
     return out[:len(rays)].copy()
 
 
-def ccd_pairs(xf, shapes, pairs, disp, hull=None, cfg=None, nthreads=8):
+def ccd_pairs(xf, shapes, pairs, disp, hull=None, cfg=None, nthreads=8, rot=None):
     xf = f32(xf).reshape(-1, 10)
     shapes = np.ascontiguousarray(shapes, dtype=SHAPE_DT)
     hull = f32(hull if hull is not None else np.zeros((0, 3))).reshape(-1, 3)
@@ -238,10 +238,23 @@ def ccd_pairs(xf, shapes, pairs, disp, hull=None, cfg=None, nthreads=8):
     assert len(disp) == len(xf)
     cfg = cfg or default_cfg(True)
     out = np.zeros(max(1, len(pairs)), SWEEP_DT)
-    rc = lib().axref_ccd_pairs(_p(xf), _p(shapes), C.c_uint32(len(xf)), _p(hull), _p(pairs), C.c_uint64(len(pairs)),
-                               _p(disp), C.byref(cfg), _p(out), C.c_int(nthreads))
+    if rot is None:
+        rc = lib().axref_ccd_pairs(_p(xf), _p(shapes), C.c_uint32(len(xf)), _p(hull), _p(pairs), C.c_uint64(len(pairs)),
+                                   _p(disp), C.byref(cfg), _p(out), C.c_int(nthreads))
+    else:
+        rot = f32(rot).reshape(-1, 3)
+        assert len(rot) == len(xf)
+        rc = lib().axref_ccd_pairs_angular(_p(xf), _p(shapes), C.c_uint32(len(xf)), _p(hull), _p(pairs),
+                                           C.c_uint64(len(pairs)), _p(disp), _p(rot), C.byref(cfg), _p(out), C.c_int(nthreads))
     assert rc == 0, rc
     return out[:len(pairs)].copy()
+
+
+def ccd_pose_at(xf10, disp3, rot3, t):
+    """Pose of a body at parameter t of the CCD-with-rotation motion model."""
+    out = np.zeros(10, np.float32)
+    lib().axref_ccd_pose_at(_p(f32(xf10)), _p(f32(disp3)), _p(f32(rot3)), C.c_float(t), _p(out))
+    return out
 
 
 def collide_pair(xfa, sa, xfb, sb, hull=None, cfg=None, want_distances=True):

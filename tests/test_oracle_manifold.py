@@ -30,10 +30,11 @@ def _points(m):
 
 def test_sphere_pairs_keep_the_single_point():
     a, b = O.xf((0, 0, 0)), O.xf((0.9, 0, 0))
-    for sa, sb in ((O.sphere(0.5), O.sphere(0.5)), (O.sphere(0.5), O.box(0.5, 0.5, 0.5)),
-                   (O.box(0.5, 0.5, 0.5), O.sphere(0.5)), (O.capsule(0.45, 1.0), O.sphere(0.5)),
-                   (O.capsule(0.45, 1.0), O.capsule(0.45, 0.5))):
-        c, m = _manifold(a, sa, b, sb)
+    crossed = O.xf((0.2, 0, 0.8), O.axis_angle((0, 0, 1), 0.7))
+    for sa, sb, tb in ((O.sphere(0.5), O.sphere(0.5), b), (O.sphere(0.5), O.box(0.5, 0.5, 0.5), b),
+                       (O.box(0.5, 0.5, 0.5), O.sphere(0.5), b), (O.capsule(0.45, 1.0), O.sphere(0.5), b),
+                       (O.capsule(0.45, 1.0), O.capsule(0.45, 0.5), crossed)):
+        c, m = _manifold(a, sa, tb, sb)
         assert m["count"] == 1
         assert (m["px"][0], m["py"][0], m["pz"][0], m["depth"][0]) == (c["px"], c["py"], c["pz"], c["depth"])
         assert (m["nx"], m["ny"], m["nz"]) == (c["nx"], c["ny"], c["nz"])
@@ -280,3 +281,76 @@ def test_random_capsule_box_manifolds_lie_on_both_shapes():
                 assert _box_sdist(pk, xbx, sbx) <= 3e-4
                 assert dk <= 1.5 * c["depth"] + 2e-3     # measured along the face normal, not the (minimal) contact normal
     assert two > 60 and one > 60, (two, one)
+
+
+# ------------------------------------------------------------------ capsule against capsule -----------
+def test_parallel_capsules_give_the_two_ends_of_the_overlap():
+    capA, capB = O.capsule(0.3, 2.0), O.capsule(0.25, 1.0)
+    a = O.xf((0, 0, 0))
+    b = O.xf((0.5, 0.8, 0))                           # both along y; B's segment spans y in [0.3, 1.3], A's [-1, 1]
+    c, m = _manifold(a, capA, b, capB)
+    np.testing.assert_allclose([c["nx"], c["ny"], c["nz"]], [1, 0, 0], atol=1e-5)
+    p, d = _points(m)
+    assert m["count"] == 2
+    np.testing.assert_allclose(d, 0.05, atol=1e-6)    # 0.3 + 0.25 - 0.5
+    np.testing.assert_allclose(p, [[0.275, 0.3, 0], [0.275, 1.0, 0]], atol=1e-6)
+    # the same pair the other way round: same points, normal flipped
+    c2, m2 = _manifold(b, capB, a, capA)
+    p2, d2 = _points(m2)
+    assert m2["count"] == 2 and c2["nx"] < -0.999
+    np.testing.assert_allclose(sorted(map(tuple, np.round(p2, 5))), sorted(map(tuple, np.round(p, 5))), atol=1e-5)
+    np.testing.assert_allclose(d2, 0.05, atol=1e-6)
+    # end to end along the common axis: no stretch in common -> the narrowphase point
+    b3 = O.xf((0.0, 1.9, 0))
+    c3, m3 = _manifold(a, capA, b3, capB)
+    assert m3["count"] == 1 and (m3["px"][0], m3["py"][0], m3["pz"][0]) == (c3["px"], c3["py"], c3["pz"])
+    # a small tilt (2 degrees, inside the 5.7 degree window) about z: B's far end rises out of reach -> one point, at the near end
+    b4 = O.xf((0.53, 0.8, 0), O.axis_angle((0, 0, 1), -np.radians(2.0)))
+    c4, m4 = _manifold(a, capA, b4, capB)
+    p4, d4 = _points(m4)
+    assert 1 <= m4["count"] <= 2 and d4.max() <= c4["depth"] + 2e-3 and d4.min() < 0.6 * d4.max()
+    # crossed at 40 degrees: single point
+    b5 = O.xf((0.5, 0.0, 0), O.axis_angle((1, 0, 0), 0.7))
+    _, m5 = _manifold(a, capA, b5, capB)
+    assert m5["count"] == 1
+
+
+def test_random_near_parallel_capsule_manifolds_lie_in_both_capsules():
+    rng = np.random.default_rng(17)
+    two = one = 0
+    for _ in range(600):
+        qa = rng.normal(size=4); qa /= np.linalg.norm(qa)
+        sa, sb = O.capsule(rng.uniform(0.15, 0.3), rng.uniform(0.6, 2.0)), O.capsule(rng.uniform(0.15, 0.3), rng.uniform(0.6, 2.0))
+        xa = O.xf(rng.uniform(-1, 1, 3), qa, rng.uniform(0.8, 1.3, 3))
+        R = _rot(qa)
+        # B: A's rotation composed with a tilt of 0..8 degrees, beside A at just under the sum of the radii
+        tilt = O.axis_angle(rng.normal(size=3), np.radians(rng.uniform(0, 8)))
+        qb = O.quat_mul(tilt, qa.astype(np.float32)) if hasattr(O, "quat_mul") else None
+        if qb is None:
+            pytest.skip("oracle_lib has no quat_mul")
+        side = R[:, 0] * np.cos(t := rng.uniform(0, 2 * np.pi)) + R[:, 2] * np.sin(t)
+        pos = xa[:3] + side * (sa[1] + sb[1]) * rng.uniform(0.7, 0.98) + R[:, 1] * rng.uniform(-0.8, 0.8)
+        xb = O.xf(pos, qb, rng.uniform(0.8, 1.3, 3))
+        hit, c, _, _ = O.collide_pair(xa, sa, xb, sb)
+        if not hit:
+            continue
+        c = c.copy(); c["a"], c["b"] = 0, 1
+        m, _ = O.manifolds(np.stack([xa, xb]), np.array([sa, sb], dtype=O.SHAPE_DT), np.array([c]))
+        p, d = _points(m[0])
+        assert 1 <= len(p) <= 2
+        two += len(p) == 2
+        one += len(p) == 1
+        if len(p) == 1 and np.allclose(p[0], [c["px"], c["py"], c["pz"]]):
+            continue
+        n = np.array([c["nx"], c["ny"], c["nz"]], dtype=np.float64)
+        for pk, dk in zip(p, d):
+            # the point is the midpoint of the overlap along n: inside both capsules, about r - depth/2 from each
+            # axis (exactly so for parallel axes; a tilt shifts it sideways by a fraction of the depth), and no
+            # depth exceeds what the narrowphase found by much
+            for xx, ss in ((xa, sa), (xb, sb)):
+                dist = _seg_dist(pk, xx, ss)
+                assert dist <= ss[1] + 0.01, (pk, dk)
+                assert abs(dist - (ss[1] - 0.5 * dk)) <= 0.02, (pk, dk, dist)
+            assert dk <= 1.1 * c["depth"] + 2e-3     # measured along the shared normal, not along pB - pA
+        assert abs(d.max() - c["depth"]) < 0.05          # one end is (close to) the deepest point
+    assert two > 80 and one > 40, (two, one)

@@ -315,6 +315,36 @@ def test_ccd_pairs_match_oracle():
     w.close()
 
 
+def test_ccd_with_rotation_matches_oracle():
+    """axcd_ccd_pairs_angular: translation + first-order turning, bit for bit against the oracle."""
+    s, _ = _query_scene(n=6000, seed=44, L=40.0)
+    w = axcd.CollisionWorld.for_scene(s)
+    rng = np.random.default_rng(15)
+    perm = rng.permutation(s.n).astype(np.uint32)             # every body in exactly one pair
+    a, b = perm[:s.n // 2], perm[s.n // 2:]
+    pairs = np.stack([a, b], axis=1).astype(np.uint32)
+    xf = s.xf.copy()
+    xf[b, :3] = xf[a, :3] + (rng.normal(size=(len(b), 3)) * 2.0).astype(np.float32)
+    w.set_transforms(xf)
+    disp = (rng.normal(size=(s.n, 3)) * 0.05).astype(np.float32)
+    disp[b] = ((xf[a, :3] - xf[b, :3]) * rng.uniform(0.3, 1.4, (len(b), 1)) + rng.normal(size=(len(b), 3)) * 0.3).astype(np.float32)
+    rot = (rng.normal(size=(s.n, 3)) * rng.uniform(0.0, 1.2, (s.n, 1))).astype(np.float32)
+    got = w.ccd_pairs(pairs, disp, rot)
+    exp = O.ccd_pairs(xf, s.shapes, pairs, disp, s.hull, rot=rot)
+    assert np.array_equal(got["hit"], exp["hit"])
+    assert np.array_equal(got["iterations"], exp["iterations"])
+    for f in ("toi", "nx", "ny", "nz"):
+        np.testing.assert_allclose(got[f], exp[f], rtol=REL, atol=REL * 1e-2)
+    assert got.tobytes() == exp.tobytes()
+    assert 0.1 < got["hit"].mean() < 0.95
+    lin = w.ccd_pairs(pairs, disp)
+    assert (lin["toi"] != got["toi"]).mean() > 0.3                       # the turning matters
+    with pytest.raises(axcd.AxcdError) as e:
+        w.ccd_pairs(np.array([[0, s.n]], np.uint32), disp, rot)
+    assert e.value.code == 601
+    w.close()
+
+
 def test_manifolds_capsule_box_mix():
     s, _ = _query_scene(n=20000, seed=41, L=24.0)     # boxes, spheres, capsules, hulls; dense enough to touch
     gm, bitwise = _manifold_parity(s, pairs_per_body=16)
@@ -322,8 +352,31 @@ def test_manifolds_capsule_box_mix():
     ta, tb = s.shapes["type"][gm["a"]], s.shapes["type"][gm["b"]]
     capbox = ((ta == 1) & (tb == 2)) | ((ta == 2) & (tb == 1))
     assert capbox.sum() > 200 and (gm["count"][capbox] == 2).sum() > 20
-    other = ~capbox & ~((ta == 1) & (tb == 1))
+    capcap = (ta == 2) & (tb == 2)
+    other = ~capbox & ~capcap & ~((ta == 1) & (tb == 1))
     assert (gm["count"][other] == 1).all()
+
+
+@pytest.mark.gpu
+def test_manifolds_log_pile_of_near_parallel_capsules():
+    """Capsule-capsule manifolds: a dense pile of capsules whose axes are within a few degrees of a common
+    direction (two thirds of them) or random (the rest) — the near-parallel pairs get two points."""
+    rng = np.random.default_rng(51)
+    s = axcd.generate_scene(30000, 51, 22.0, frac_box=1.0, frac_sphere=0.0)
+    s.shapes["type"][:] = 2
+    s.shapes["p0"][:] = rng.uniform(0.15, 0.3, s.n).astype(np.float32)
+    s.shapes["p1"][:] = rng.uniform(0.8, 2.0, s.n).astype(np.float32)
+    s.shapes["p2"][:] = 0.0
+    common = O.axis_angle((1.0, 0.2, -0.4), 0.9)
+    snap = rng.random(s.n) < 0.67
+    for i in np.nonzero(snap)[0]:
+        tilt = O.axis_angle(rng.normal(size=3), np.radians(rng.uniform(0.0, 7.0)))
+        s.xf[i, 3:7] = O.quat_mul(tilt, common)
+    s.xf[:, 7:10] = rng.uniform(0.8, 1.25, (s.n, 3)).astype(np.float32)
+    gm, bitwise = _manifold_parity(s, pairs_per_body=24)
+    assert bitwise
+    assert (s.shapes["type"][gm["a"]] == 2).all()
+    assert (gm["count"] == 2).sum() > 500 and (gm["count"] == 1).sum() > 500 and gm["count"].max() == 2
 
 
 def test_temporal_coherence_two_refits_before_a_broadphase():

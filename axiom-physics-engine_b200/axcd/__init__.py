@@ -43,7 +43,7 @@ SWEEP_DT = np.dtype([("hit", "<u4"), ("toi", "<f4"), ("nx", "<f4"), ("ny", "<f4"
 # every symbol include/axcd.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "axcd_default_config", "axcd_device_count", "axcd_create", "axcd_destroy", "axcd_set_shapes",
-    "axcd_set_transforms", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_step_async",
+    "axcd_set_transforms", "axcd_set_poses", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_step_async",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_ccd_pairs_angular", "axcd_pin_host_buffer", "axcd_unpin_host_buffer",
@@ -126,6 +126,8 @@ def load_library():
         lib.axcd_set_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_uint32, C.c_void_p]
         lib.axcd_set_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.axcd_set_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.axcd_set_poses.restype = C.c_int32
         for name in ("axcd_refit", "axcd_broadphase", "axcd_narrowphase"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.axcd_step.argtypes = [C.c_void_p, C.c_void_p]
@@ -368,6 +370,19 @@ class CollisionWorld:
             n = xf.nbytes // stride
         self._check(self._lib.axcd_set_transforms(self._ctx, _ptr(xf), n, stride),
                     "axcd_set_transforms")
+
+    def set_poses(self, poses, stride=28):
+        """poses: (n,7) float32 array (position, rotation xyzw), or a buffer of `stride`-byte records; the scales
+        stay as the last set_transforms left them."""
+        if isinstance(poses, np.ndarray) and stride == 28:
+            poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 7)
+            n = poses.shape[0]
+        else:
+            n = poses.nbytes // stride
+        self._check(self._lib.axcd_set_poses(self._ctx, _ptr(poses), n, stride), "axcd_set_poses")
+
+    def set_poses_ptr(self, host_ptr, n, stride=28):
+        self._check(self._lib.axcd_set_poses(self._ctx, C.c_void_p(host_ptr), n, stride), "axcd_set_poses")
 
     def set_transforms_ptr(self, host_ptr, n, stride=40):
         self._check(self._lib.axcd_set_transforms(self._ctx, C.c_void_p(host_ptr), n, stride),

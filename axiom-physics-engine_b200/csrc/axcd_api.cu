@@ -58,6 +58,7 @@ struct AxcdContext {
 
     // device buffers
     float* dXf = nullptr;            // n * 10 floats (axiom::math::Transform AoS)
+    float* dPoseStage = nullptr;     // n * 7 floats: landing area of axcd_set_poses
     uint4* dShapes = nullptr;
     uint8_t* dType8 = nullptr;       // shape type per body, rewritten by every refit
     float4* dHull = nullptr;
@@ -339,7 +340,7 @@ void axcd_destroy(AxcdContext* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {ctx->dXf, ctx->dShapes, ctx->dType8, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dAwake, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
+    void* bufs[] = {ctx->dPoseStage, ctx->dXf, ctx->dShapes, ctx->dType8, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dAwake, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes, ctx->dNodes32,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
                     ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dManifolds, ctx->dQIn, ctx->dQCount, ctx->dQSeg, ctx->dQOut, ctx->dPairDist, ctx->dSortHist,
@@ -410,6 +411,7 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         const size_t nb = cfg->maxBodies, np = cfg->maxPairs;
         // +64 floats of slack: the staged 128-bit loads may touch the tail of the last block
         CU(dalloc(&ctx->dXf, nb * 10 + 64));
+        CU(dalloc(&ctx->dPoseStage, nb * 7));
         CU(dalloc(&ctx->dShapes, nb));
         CU(dalloc(&ctx->dType8, nb));
         CU(dalloc(&ctx->dHull, (size_t)cfg->maxHullVerts));
@@ -577,6 +579,26 @@ int32_t axcd_set_transforms(AxcdContext* ctx, const void* transforms, uint32_t n
         } else {
             CU(cudaMemcpy2DAsync(ctx->dXf, 40, transforms, strideBytes, 40, n, cudaMemcpyHostToDevice, ctx->stream));
         }
+    }
+    ctx->stage = ST_POSES;
+    return AXCD_OK;
+}
+
+int32_t axcd_set_poses(AxcdContext* ctx, const void* poses, uint32_t n, uint32_t strideBytes) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    if (ctx->stage < ST_POSES) return AXCD_ERR_GPU_INVALID_OP;   // the scales come from an earlier axcd_set_transforms
+    if ((n != ctx->n && n != ctx->nOwned) || strideBytes < 28 || (strideBytes & 3u)) return AXCD_ERR_INVALID_PARAM;
+    if (n && !poses) return AXCD_ERR_NULL_POINTER;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (n) {
+        if (strideBytes == 28) {
+            CU(cudaMemcpyAsync(ctx->dPoseStage, poses, (size_t)n * 28, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            CU(cudaMemcpy2DAsync(ctx->dPoseStage, 28, poses, strideBytes, 28, n, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        const uint32_t words = n * 7u;
+        mergePosesKernel<<<(words + 255u) / 256u, 256, 0, ctx->stream>>>(ctx->dPoseStage, ctx->dXf, words);
+        CU(cudaGetLastError());
     }
     ctx->stage = ST_POSES;
     return AXCD_OK;

@@ -637,4 +637,13 @@ __global__ void unpackGhostsKernel(const float4* __restrict__ in, uint32_t count
     keys[first + g] = __float_as_uint(d.z);
 }
 
+// axcd_set_poses: position + rotation (7 floats per body, packed) into the 10-float Transform records; the
+// scales stay as the last axcd_set_transforms left them.
+__global__ void mergePosesKernel(const float* __restrict__ poses, float* __restrict__ xf, uint32_t words) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= words) return;
+    const uint32_t body = i / 7u, comp = i - body * 7u;
+    xf[(size_t)body * 10 + comp] = poses[i];
+}
+
 }  // namespace axcd

@@ -16,8 +16,9 @@ pass of the path over the scene: axcd_refit + axcd_broadphase + axcd_narrowphase
               runs it (axcd_step_async: one CUDA graph launch), CUDA-event timed per step, L2 flushed
               between timed steps.  The per-stage table comes from separate steps through the staged calls.
 * `e2e`     : the same metric through the public API with HOST buffers: every step uploads the
-              transforms from pinned host memory (H2D inside the timed region) and reads the
-              contacts back to pinned host memory (D2H).
+              poses (position + rotation, axcd_set_poses, 28 B per body; the scales are static and resident)
+              from pinned host memory (H2D inside the timed region) and reads the contacts back to pinned
+              host memory (D2H).  `e2e_full_transforms`: the same with whole 40-byte Transforms every step.
 * `--impl reference`: the CPU oracle (the only "reference implementation" that exists for this
               path — the upstream snapshot has no collision code) on all host cores, on the SAME full-size
               workload (one step of the 1M-body scene is a few hundred ms of CPU work).
@@ -480,6 +481,7 @@ def measure_c4(torch, dist, axcd, rank, world, local, scale, steps):
 
 
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import axcd
@@ -560,30 +562,39 @@ def run_ours(args):
 
     # ---- end-to-end through the public API with host buffers (`e2e`) ---------------------------------
     h_xf = torch.from_numpy(s.xf.copy()).pin_memory()
+    h_pose = torch.from_numpy(np.ascontiguousarray(s.xf[:, :7])).pin_memory()     # position + rotation, 28 B per body
     h_con = torch.empty((w.cfg.maxContacts, 10), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        w.set_transforms_ptr(h_xf.data_ptr(), s.n)
-        w.step()
-        w.contacts_into(h_con.data_ptr(), w.cfg.maxContacts)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    e2e_units = 0
-    for _ in range(e2e_steps):
-        w.set_transforms_ptr(h_xf.data_ptr(), s.n)        # H2D, pinned, inside the timed region
-        st2 = w.step()
-        nc = w.contacts_into(h_con.data_ptr(), w.cfg.maxContacts)   # D2H of the step's result
-        e2e_units += st2.numPairs + nc
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    e2e_units = float(e2e_units)
-    if world > 1:
-        e2e_ms = allreduce(torch, dist, [e2e_ms], dist.ReduceOp.MAX)[0]
-        e2e_units = allreduce(torch, dist, [e2e_units], dist.ReduceOp.SUM)[0]
-    e2e_value = e2e_units / (e2e_ms * 1e-3)
-    h2d = int(s.n) * 40
+
+    def e2e_loop(upload):
+        for _ in range(2):
+            upload()
+            w.step()
+            w.contacts_into(h_con.data_ptr(), w.cfg.maxContacts)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        units = 0
+        for _ in range(e2e_steps):
+            upload()                                          # H2D, pinned, inside the timed region
+            st2 = w.step()
+            nc = w.contacts_into(h_con.data_ptr(), w.cfg.maxContacts)   # D2H of the step's result
+            units += st2.numPairs + nc
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        units = float(units)
+        if world > 1:
+            ms = allreduce(torch, dist, [ms], dist.ReduceOp.MAX)[0]
+            units = allreduce(torch, dist, [units], dist.ReduceOp.SUM)[0]
+        return units / (ms * 1e-3), ms, st2
+
+    # every step uploads whole Transforms (40 B per body) ...
+    e2e_full_value, e2e_full_ms, st2 = e2e_loop(lambda: w.set_transforms_ptr(h_xf.data_ptr(), s.n))
+    # ... or, as a rigid-body step does, position + rotation only (axcd_set_poses, 28 B per body): the scales went
+    # to the device with the set_transforms above and do not change from step to step.  This is the `e2e` of the line.
+    e2e_value, e2e_ms, st2 = e2e_loop(lambda: w.set_poses_ptr(h_pose.data_ptr(), s.n))
+    h2d = int(s.n) * 28
     d2h = int(st2.numContacts) * 40 + 4 + 128   # contacts + count + stats block
 
     # ---- roofline: measured FP32 peak, per-stage table, dominant kernel -----------------------------------
@@ -644,7 +655,11 @@ def run_ours(args):
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(args.workload, world, st.numBodies, st.numPairs, st.numContacts, st.numPenetrating),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps,
+                    "upload": "axcd_set_poses: position + rotation, 28 B per body from pinned memory (scales resident)"},
+            "e2e_full_transforms": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": int(s.n) * 40,
+                                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_full_ms / e2e_steps,
+                                    "upload": "axcd_set_transforms: whole 40-byte Transforms every step"},
             "gpu_launches": n_launch * args.steps,
             "step_launch": {"graph_launched": graph_launched, "kernels_per_step": n_launch,
                             "ms_per_step_staged_calls": round(staged_total, 4),

@@ -185,6 +185,13 @@ AXCD_API int32_t axcd_set_transforms(AxcdContext* ctx, const void* transforms, u
  * until the next blocking call on this context (axcd_step, axcd_get_stats, any axcd_get_*) has returned.
  * The same rule holds for axcd_set_ghosts and axcd_set_body_keys.                                    */
 
+/* Per-step poses without the scales: `poses` is an array of 28-byte records (position 0, rotation (x,y,z,w) 12
+ * — the first 28 bytes of a Transform) with the given byte stride (>= 28; 40 reads them out of a Transform
+ * array).  A rigid body's scale does not change from step to step, so after one axcd_set_transforms a step
+ * only has to upload 28 of the 40 bytes per body; the scales stay as the last axcd_set_transforms left them.
+ * Returns 503 before the first axcd_set_transforms.  Same asynchrony and buffer-lifetime rule as above.      */
+AXCD_API int32_t axcd_set_poses(AxcdContext* ctx, const void* poses, uint32_t n, uint32_t strideBytes);
+
 /* The three stages (asynchronous on the context stream) and the fused step (synchronises and
  * fills stats).  Each stage runs once per refit, in order: axcd_broadphase needs an axcd_refit
  * since the last set_transforms, axcd_narrowphase needs a fresh axcd_broadphase; calling a stage

@@ -143,6 +143,15 @@ public:
     core::Result<void> setTransforms(const math::Transform* transforms, std::uint32_t count) {
         return wrap(axcd_set_transforms(ctx_, transforms, count, sizeof(math::Transform)));
     }
+    /// Position + rotation only (28-byte records at the given stride; the scales of the last setTransforms stay):
+    /// what a step has to upload once the bodies' scales are on the device.  setPoses(transforms, n) reads the
+    /// first 28 bytes of each Transform.
+    core::Result<void> setPoses(const void* poses, std::uint32_t count, std::uint32_t strideBytes = 28) {
+        return wrap(axcd_set_poses(ctx_, poses, count, strideBytes));
+    }
+    core::Result<void> setPoses(const math::Transform* transforms, std::uint32_t count) {
+        return wrap(axcd_set_poses(ctx_, transforms, count, sizeof(math::Transform)));
+    }
     core::Result<void> refit() { return wrap(axcd_refit(ctx_)); }
     core::Result<void> broadphase() { return wrap(axcd_broadphase(ctx_)); }
     core::Result<void> narrowphase() { return wrap(axcd_narrowphase(ctx_)); }

@@ -78,6 +78,10 @@ int main() {
     if (world.setAwake(nullptr, 0).isFailure()) return 21;
     auto again = world.step();
     if (again.isFailure() || again.value().numPairs != pairs || again.value().numContacts != contacts) return 22;
+    // position + rotation only (28 of the 40 bytes of each Transform): the same scene again
+    if (world.setPoses(xf.data(), n).isFailure()) return 23;
+    auto posed = world.step();
+    if (posed.isFailure() || posed.value().numPairs != pairs || posed.value().numContacts != contacts) return 24;
     std::printf("%u %u %u\n", pairs, contacts, points);
     return 0;
 }

@@ -644,3 +644,41 @@ def test_fused_closed_form_narrowphase_matches_the_split_kernels():
     assert w1.contacts().tobytes() == w2.contacts().tobytes()
     w1.close()
     w2.close()
+
+
+@pytest.mark.gpu
+def test_set_poses_uploads_position_and_rotation_only():
+    """axcd_set_poses: 28 B per body, scales stay as the last set_transforms left them; packed and strided."""
+    s = axcd.config_scene("C1", scale=0.2)
+    rng = np.random.default_rng(8)
+    s.xf[:, 7:10] = rng.uniform(0.7, 1.3, (s.n, 3)).astype(np.float32)
+    w = axcd.CollisionWorld(s.n, max_pairs=24 * s.n, max_hull_verts=len(s.hull))
+    w.set_shapes(s.shapes, s.hull, s.world_id)
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_poses(s.xf[:, :7])                      # no scales on the device yet
+    assert e.value.code == 503
+    w.set_transforms(s.xf)
+    w.step()
+    xf2 = s.xf.copy()
+    xf2[:, :3] += rng.normal(size=(s.n, 3)).astype(np.float32) * 0.2
+    q = xf2[:, 3:7] + rng.normal(size=(s.n, 4)).astype(np.float32) * 0.2
+    xf2[:, 3:7] = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    for mode in ("packed", "strided"):
+        if mode == "packed":
+            w.set_poses(xf2[:, :7])
+        else:
+            junk = xf2.copy()
+            junk[:, 7:10] = 99.0                      # must not be read
+            w.set_poses(junk, stride=40)
+        st = w.step()
+        rc, bb = O.refit(xf2, s.shapes, s.hull, nthreads=8)
+        pairs = O.broadphase(bb, nthreads=8)
+        con, _, _ = O.narrowphase(xf2, s.shapes, pairs, s.hull, nthreads=8)
+        assert np.array_equal(w.aabbs(), bb)
+        assert np.array_equal(w.pairs(), pairs)
+        assert w.contacts().tobytes() == con.tobytes() and st.numContacts == len(con) > 0
+        xf2[:, :3] += 0.01                            # a different pose for the second mode
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_poses(xf2[:, :7], stride=24)
+    assert e.value.code == 600
+    w.close()

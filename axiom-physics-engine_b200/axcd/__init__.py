@@ -43,7 +43,7 @@ SWEEP_DT = np.dtype([("hit", "<u4"), ("toi", "<f4"), ("nx", "<f4"), ("ny", "<f4"
 # every symbol include/axcd.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "axcd_default_config", "axcd_device_count", "axcd_create", "axcd_destroy", "axcd_set_shapes",
-    "axcd_set_transforms", "axcd_set_poses", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_step_async",
+    "axcd_set_transforms", "axcd_set_poses", "axcd_set_contact_sink", "axcd_refit", "axcd_broadphase", "axcd_narrowphase", "axcd_step", "axcd_step_async",
     "axcd_get_stats", "axcd_get_aabbs", "axcd_get_pairs", "axcd_get_pair_distances",
     "axcd_get_contacts", "axcd_error_string", "axcd_last_device_error",
     "axcd_build_manifolds", "axcd_get_manifolds", "axcd_query_aabbs", "axcd_raycast", "axcd_set_awake", "axcd_ccd_pairs", "axcd_ccd_pairs_angular", "axcd_pin_host_buffer", "axcd_unpin_host_buffer",
@@ -128,6 +128,8 @@ def load_library():
         lib.axcd_set_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         lib.axcd_set_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         lib.axcd_set_poses.restype = C.c_int32
+        lib.axcd_set_contact_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        lib.axcd_set_contact_sink.restype = C.c_int32
         for name in ("axcd_refit", "axcd_broadphase", "axcd_narrowphase"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.axcd_step.argtypes = [C.c_void_p, C.c_void_p]
@@ -310,6 +312,20 @@ def config_scene(name, scale=1.0):
 # ------------------------------------------------------------------------------------------------
 # the collision world (one context == one GPU)
 # ------------------------------------------------------------------------------------------------
+def pin_host_buffer(arr):
+    """Page-locks a numpy array's memory (axcd_pin_host_buffer) so that copies from / to it are asynchronous and
+    it can serve as a contact sink; undo with unpin_host_buffer before the array is freed."""
+    rc = load_library().axcd_pin_host_buffer(C.c_void_p(arr.ctypes.data), C.c_uint64(arr.nbytes))
+    if rc != 0:
+        raise AxcdError(rc, "axcd_pin_host_buffer", "")
+
+
+def unpin_host_buffer(arr):
+    rc = load_library().axcd_unpin_host_buffer(C.c_void_p(arr.ctypes.data))
+    if rc != 0:
+        raise AxcdError(rc, "axcd_unpin_host_buffer", "")
+
+
 class CollisionWorld:
     """Owns an AxcdContext.  Mirrors Broadphase::update/getPairCount and
     Narrowphase::detectCollisions/getContactCount."""
@@ -380,6 +396,12 @@ class CollisionWorld:
         else:
             n = poses.nbytes // stride
         self._check(self._lib.axcd_set_poses(self._ctx, _ptr(poses), n, stride), "axcd_set_poses")
+
+    def set_contact_sink(self, host_ptr, capacity):
+        """host_ptr: address of a page-locked buffer of >= maxContacts 40-byte records (None detaches); every
+        narrowphase from now on also delivers its contacts there."""
+        self._check(self._lib.axcd_set_contact_sink(self._ctx, C.c_void_p(host_ptr) if host_ptr else None, capacity),
+                    "axcd_set_contact_sink")
 
     def set_poses_ptr(self, host_ptr, n, stride=28):
         self._check(self._lib.axcd_set_poses(self._ctx, C.c_void_p(host_ptr), n, stride), "axcd_set_poses")

@@ -59,6 +59,8 @@ struct AxcdContext {
     // device buffers
     float* dXf = nullptr;            // n * 10 floats (axiom::math::Transform AoS)
     float* dPoseStage = nullptr;     // n * 7 floats: landing area of axcd_set_poses
+    AxcdContact* sinkDev = nullptr;  // axcd_set_contact_sink: device-side address of the caller's page-locked buffer
+    AxcdContact* sinkHost = nullptr;
     uint4* dShapes = nullptr;
     uint8_t* dType8 = nullptr;       // shape type per body, rewritten by every refit
     float4* dHull = nullptr;
@@ -308,7 +310,7 @@ const char* axcd_error_string(int32_t code) {
 int32_t axcd_pin_host_buffer(void* hostPtr, uint64_t bytes) {
     if (!hostPtr) return AXCD_ERR_NULL_POINTER;
     if (bytes == 0) return AXCD_ERR_INVALID_PARAM;
-    const cudaError_t e = cudaHostRegister(hostPtr, (size_t)bytes, cudaHostRegisterPortable);
+    const cudaError_t e = cudaHostRegister(hostPtr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return e == cudaErrorMemoryAllocation ? AXCD_ERR_GPU_ALLOC : AXCD_ERR_GPU_FAILED;
@@ -862,9 +864,14 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
             // every pair is decided in closed form: classification, closed forms and in-order compaction in ONE kernel
             const uint32_t fusedTilesMax = (mp + kFusedTile - 1) / kFusedTile;
             const uint32_t fusedBlocks = fusedTilesMax < (uint32_t)ctx->numSMs * AXCD_FUSED_MINBLOCKS ? fusedTilesMax : (uint32_t)ctx->numSMs * AXCD_FUSED_MINBLOCKS;
-            narrowClosedFusedKernel<<<fusedBlocks, kFusedThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dXf, ctx->dShapes,
-                                                                           ctx->dContacts, ctx->cfg.maxContacts, ctx->dSlotStatus,
-                                                                           ctx->dCtr);
+            if (ctx->sinkDev)
+                narrowClosedFusedKernel<true><<<fusedBlocks, kFusedThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dXf, ctx->dShapes,
+                                                                                     ctx->dContacts, ctx->cfg.maxContacts, ctx->sinkDev,
+                                                                                     ctx->dSlotStatus, ctx->dCtr);
+            else
+                narrowClosedFusedKernel<false><<<fusedBlocks, kFusedThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dXf, ctx->dShapes,
+                                                                                      ctx->dContacts, ctx->cfg.maxContacts, nullptr,
+                                                                                      ctx->dSlotStatus, ctx->dCtr);
             CU(cudaGetLastError());
             recordEv(ctx, EV_GJK);
             ctx->launches[2] = 1;
@@ -909,6 +916,13 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
             CU(cudaGetLastError());
         }
         ctx->launches[2] = anyGeneric ? 6 : 3;   // classify, closed forms, [GJK], slots, [EPA, EPA fallback]
+        if (ctx->sinkDev) {   // the fused kernel writes the sink itself; this path copies the finished array
+            copyContactsKernel<<<ctx->numSMs * 4, 256, 0, st>>>(reinterpret_cast<const float2*>(ctx->dContacts),
+                                                               reinterpret_cast<float2*>(ctx->sinkDev), &ctx->dCtr->contactCount,
+                                                               ctx->cfg.maxContacts);
+            CU(cudaGetLastError());
+            ctx->launches[2] += 1;
+        }
         }
     } else {
         recordEv(ctx, EV_GJK);
@@ -1125,6 +1139,26 @@ int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap, uint
     if (cap < ctx->numContacts) return AXCD_ERR_OUT_OF_RANGE;
     CU(cudaMemcpyAsync(out, ctx->dContacts, sizeof(AxcdContact) * ctx->numContacts, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return AXCD_OK;
+}
+
+int32_t axcd_set_contact_sink(AxcdContext* ctx, AxcdContact* hostBuffer, uint32_t capacity) {
+    if (!ctx) return AXCD_ERR_NULL_POINTER;
+    cudaSetDevice(ctx->cfg.deviceOrdinal);
+    if (!hostBuffer) {
+        if (ctx->sinkDev) ctx->gen++;   // the launch configuration changed: graphs are re-captured
+        ctx->sinkDev = ctx->sinkHost = nullptr;
+        return AXCD_OK;
+    }
+    if (capacity < ctx->cfg.maxContacts) return AXCD_ERR_INVALID_PARAM;
+    void* dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, hostBuffer, 0) != cudaSuccess || !dev) {   // not page-locked / not mapped
+        cudaGetLastError();
+        return AXCD_ERR_INVALID_PARAM;
+    }
+    if (dev != ctx->sinkDev) ctx->gen++;
+    ctx->sinkDev = static_cast<AxcdContact*>(dev);
+    ctx->sinkHost = hostBuffer;
     return AXCD_OK;
 }
 

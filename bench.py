@@ -566,19 +566,25 @@ def run_ours(args):
     h_con = torch.empty((w.cfg.maxContacts, 10), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
 
-    def e2e_loop(upload):
+    def e2e_loop(upload, sink):
+        """One e2e step = upload from pinned memory, the fused step, the contacts in pinned host memory: either fetched
+        with axcd_get_contacts after the step (sink False) or delivered by the step itself into the registered
+        contact sink (sink True; AxcdStats::numContacts is their count)."""
+        w.set_contact_sink(h_con.data_ptr() if sink else None, w.cfg.maxContacts)
+
+        def one():
+            upload()                                          # H2D, pinned, inside the timed region
+            st2 = w.step()
+            nc = st2.numContacts if sink else w.contacts_into(h_con.data_ptr(), w.cfg.maxContacts)   # D2H of the result
+            return st2, nc
         for _ in range(2):
-            upload()
-            w.step()
-            w.contacts_into(h_con.data_ptr(), w.cfg.maxContacts)
+            one()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         units = 0
         for _ in range(e2e_steps):
-            upload()                                          # H2D, pinned, inside the timed region
-            st2 = w.step()
-            nc = w.contacts_into(h_con.data_ptr(), w.cfg.maxContacts)   # D2H of the step's result
+            st2, nc = one()
             units += st2.numPairs + nc
         e1.record(stream)
         barrier()
@@ -589,11 +595,15 @@ def run_ours(args):
             units = allreduce(torch, dist, [units], dist.ReduceOp.SUM)[0]
         return units / (ms * 1e-3), ms, st2
 
-    # every step uploads whole Transforms (40 B per body) ...
-    e2e_full_value, e2e_full_ms, st2 = e2e_loop(lambda: w.set_transforms_ptr(h_xf.data_ptr(), s.n))
-    # ... or, as a rigid-body step does, position + rotation only (axcd_set_poses, 28 B per body): the scales went
-    # to the device with the set_transforms above and do not change from step to step.  This is the `e2e` of the line.
-    e2e_value, e2e_ms, st2 = e2e_loop(lambda: w.set_poses_ptr(h_pose.data_ptr(), s.n))
+    # every step uploads whole Transforms (40 B per body) and fetches the contacts with axcd_get_contacts ...
+    e2e_full_value, e2e_full_ms, st2 = e2e_loop(lambda: w.set_transforms_ptr(h_xf.data_ptr(), s.n), sink=False)
+    # ... or, as a rigid-body step does, position + rotation only (axcd_set_poses, 28 B per body: the scales went to the
+    # device with the set_transforms above and do not change from step to step), with the contacts delivered into a
+    # registered page-locked buffer while the narrowphase runs (axcd_set_contact_sink).  This is the `e2e` of the line.
+    e2e_value, e2e_ms, st2 = e2e_loop(lambda: w.set_poses_ptr(h_pose.data_ptr(), s.n), sink=True)
+    sink_ok = bool(np.array_equal(h_con[:st2.numContacts].numpy().view(np.uint32),
+                                  w.contacts().view(np.uint32).reshape(-1, 10)))
+    w.set_contact_sink(None, 0)
     h2d = int(s.n) * 28
     d2h = int(st2.numContacts) * 40 + 4 + 128   # contacts + count + stats block
 
@@ -656,10 +666,13 @@ def run_ours(args):
             "config": make_config(args.workload, world, st.numBodies, st.numPairs, st.numContacts, st.numPenetrating),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps,
-                    "upload": "axcd_set_poses: position + rotation, 28 B per body from pinned memory (scales resident)"},
+                    "upload": "axcd_set_poses: position + rotation, 28 B per body from pinned memory (scales resident)",
+                    "download": "axcd_set_contact_sink: the step delivers the contacts into the pinned host buffer",
+                    "sink_matches_device_contacts": sink_ok},
             "e2e_full_transforms": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": int(s.n) * 40,
                                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_full_ms / e2e_steps,
-                                    "upload": "axcd_set_transforms: whole 40-byte Transforms every step"},
+                                    "upload": "axcd_set_transforms: whole 40-byte Transforms every step",
+                                    "download": "axcd_get_contacts after the step"},
             "gpu_launches": n_launch * args.steps,
             "step_launch": {"graph_launched": graph_launched, "kernels_per_step": n_launch,
                             "ms_per_step_staged_calls": round(staged_total, 4),

@@ -152,6 +152,11 @@ public:
     core::Result<void> setPoses(const math::Transform* transforms, std::uint32_t count) {
         return wrap(axcd_set_poses(ctx_, transforms, count, sizeof(math::Transform)));
     }
+    /// A page-locked host buffer (>= maxContacts records) that every narrowphase from now on also fills with the
+    /// step's contacts, so the host copy travels while the narrowphase runs; nullptr detaches.  Count: stats().
+    core::Result<void> setContactSink(ContactPoint* pinnedHostBuffer, std::uint32_t capacity) {
+        return wrap(axcd_set_contact_sink(ctx_, pinnedHostBuffer, capacity));
+    }
     core::Result<void> refit() { return wrap(axcd_refit(ctx_)); }
     core::Result<void> broadphase() { return wrap(axcd_broadphase(ctx_)); }
     core::Result<void> narrowphase() { return wrap(axcd_narrowphase(ctx_)); }

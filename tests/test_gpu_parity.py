@@ -682,3 +682,41 @@ def test_set_poses_uploads_position_and_rotation_only():
         w.set_poses(xf2[:, :7], stride=24)
     assert e.value.code == 600
     w.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene_name,kw", [("C1", {}), ("C2", {"scale": 0.05})], ids=["closed-form-fused", "generic-gjk-epa"])
+def test_contact_sink_receives_the_steps_contacts(scene_name, kw):
+    """axcd_set_contact_sink: the step delivers the contacts into a page-locked host buffer (written by the fused
+    narrowphase kernel tile by tile, or by a copy kernel behind GJK / EPA); same records, same order."""
+    s = axcd.config_scene(scene_name, **kw)
+    w = axcd.CollisionWorld.for_scene(s, pairs_per_body=16)
+    cap = w.cfg.maxContacts
+    sink = np.zeros(cap, axcd.CONTACT_DT)
+    with pytest.raises(axcd.AxcdError) as e:
+        w.set_contact_sink(sink.ctypes.data, cap)         # pageable memory
+    assert e.value.code == 600
+    axcd.pin_host_buffer(sink)
+    try:
+        with pytest.raises(axcd.AxcdError) as e:
+            w.set_contact_sink(sink.ctypes.data, cap - 1)  # too small
+        assert e.value.code == 600
+        w.set_contact_sink(sink.ctypes.data, cap)
+        for rep in range(3):                               # direct launches, then the captured graph
+            sink[:] = 0
+            w.set_transforms(s.xf)
+            st = w.step()
+            ref = w.contacts()
+            assert st.numContacts == len(ref) > 0
+            assert sink[:len(ref)].tobytes() == ref.tobytes()
+            assert not sink[len(ref):].view(np.uint32).any()
+        con, _, _ = O.narrowphase(s.xf, s.shapes, w.pairs(), s.hull, nthreads=8)
+        assert sink[:len(con)].tobytes() == con.tobytes()
+        w.set_contact_sink(None, 0)                        # detached: the buffer is left alone
+        sink[:] = 0
+        w.set_transforms(s.xf)
+        w.step()
+        assert not sink.view(np.uint32).any()
+    finally:
+        w.close()
+        axcd.unpin_host_buffer(sink)

@@ -285,7 +285,7 @@ def stage_table(avg, st, hbm_peak, fp32_peak, generic_pairs):
     return rows, info
 
 
-def roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, workload):
+def roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, workload, sm_count=None, sm_mhz=None):
     dom = max(avg, key=avg.get)
     name, bound, work = info[dom]
     row = next(r for r in rows if r["stage"] == dom[:-2])
@@ -298,18 +298,31 @@ def roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, workload):
     # DRAM traffic of the dominant kernel per launch from this round's `ncu --set full` capture of the same
     # workload — used only while the captured kernel time still matches the live one (else null: stale)
     traffic = None
+    issue = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         ent = tj.get(workload, {}).get(dom[:-2])
         if ent and abs(ent["ncu_kernel_ms"] - avg[dom]) <= 0.25 * avg[dom]:
             traffic = ent["dram_bytes_per_launch"]
+            if ent.get("warp_instructions_per_launch") and sm_count and sm_mhz:
+                # what actually bounds a kernel that is neither streaming nor FP32-dense: issue slots.  Warp instructions
+                # per launch (a property of kernel + scene, from the same ncu capture) over the live launch time, against
+                # 4 schedulers per SM at the SM clock sampled during the run.
+                ginst = ent["warp_instructions_per_launch"] / (avg[dom] * 1e-3) / 1e9
+                peak_i = sm_count * 4 * sm_mhz * 1e-3
+                issue = {"warp_instructions_per_launch": ent["warp_instructions_per_launch"],
+                         "achieved_ginst_per_s": round(ginst, 1), "peak_ginst_per_s": round(peak_i, 1),
+                         "frac": round(ginst / peak_i, 4), "active_lanes_per_instruction": ent.get("threads_per_instruction"),
+                         "source": "instruction count and lanes: profiles/r02_traffic.json (ncu --set full of this kernel); time and clock: this run"}
     except Exception:
         pass
     return {"kernel": name, "bound": bound, "achieved": ach, "peak": round(peak, 2) if peak else None, "unit": unit,
             "frac": round(ach / peak, 4) if peak else None, "traffic": traffic, "peak_source": src,
-            "launch_ms": round(avg[dom], 4),
+            "launch_ms": round(avg[dom], 4), "issue": issue,
             "note": "dominant stage of the step by CUDA-event time through the staged calls; algorithmic work per "
-                    "DESIGN.md section 2; every stage's own row is in `stages`"}
+                    "DESIGN.md section 2; every stage's own row is in `stages`.  `issue` (when the ncu capture matches "
+                    "this run) is the kernel's share of the SMs' instruction-issue slots: the LBVH walk is bound by "
+                    "those, not by HBM"}
 
 
 def measure_next_rows(w, s, stream, hbm_peak, device):
@@ -614,7 +627,9 @@ def run_ours(args):
         if r["stage"] == "refit" and refit_dirty > 0:
             r["ms_write_only_flush"] = round(refit_dirty, 4)
             r["frac_of_hbm_peak_write_only_flush"] = round(r["algorithmic_bytes"] / (refit_dirty * 1e-3) / 1e9 / hbm_peak, 4)
-    roofline = roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, args.workload)
+    roofline = roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, args.workload,
+                           sm_count=torch.cuda.get_device_properties(local).multi_processor_count,
+                           sm_mhz=(clocks or {}).get("sm_mhz"))
 
     single = rank == 0 and world == 1 and args.workload == "headline" and args.flags == 0
     # ---- the SURVEY 8(f) "next" rows on the same scene (rank 0, N=1): manifolds, scene queries, coherence ---

@@ -103,8 +103,11 @@ Headline workload: 1,000,000 mixed boxes/spheres, L = 100, seed 3 -> {d['config'
 * **{d['ms_per_step']:.3f} ms/step**, **{d['value'] / 1e9:.3f} G pairs/s** device-resident: the fused step as one CUDA graph launch
   ({d['step_launch']['kernels_per_step']} kernels, no memset nodes), CUDA events, L2 flushed between steps.  The same step through the
   staged calls (direct launches, events between stages): {d['step_launch']['ms_per_step_staged_calls']} ms.
-* e2e through the C ABI with pinned host buffers (40 MB H2D + 61.5 MB D2H per step): {d['e2e']['ms_per_step']:.3f} ms/step,
-  {d['e2e']['value'] / 1e9:.3f} G pairs/s (PCIe-bound: 101.5 MB per step).
+* e2e through the C ABI with pinned host buffers: **{d['e2e']['ms_per_step']:.3f} ms/step**, {d['e2e']['value'] / 1e9:.3f} G pairs/s —
+  `axcd_set_poses` uploads position + rotation ({d['e2e']['h2d_bytes_per_step'] / 1e6:.1f} MB; the scales are static and resident) and the step
+  delivers the contacts ({d['e2e']['d2h_bytes_per_step'] / 1e6:.1f} MB) into a page-locked buffer while the narrowphase runs
+  (`axcd_set_contact_sink`; sink == device contacts: {d['e2e'].get('sink_matches_device_contacts')}).  With whole 40-byte Transforms up and
+  `axcd_get_contacts` after the step (the round-1 protocol): {d.get('e2e_full_transforms', {}).get('ms_per_step', 0):.3f} ms/step.  PCIe-bound either way.
 * CPU oracle on the same box ({cb.get('cores')} host threads, one full step of the same scene): {cb.get('ms_per_step', 0):.0f} ms/step,
   {cb.get('value', 0) / 1e6:.1f} M pairs/s; pair and contact counts match the GPU's: {cb.get('pairs_match_gpu')}.
 * clocks during the timed region: {d['clocks']}
@@ -160,7 +163,8 @@ def first(dat, frag):
     return None
 
 
-traffic = {"source": "profiles/r02_ncu_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
+traffic = {"source": "profiles/r02_ncu_summary.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, smsp__inst_executed.sum, "
+                     "smsp__thread_inst_executed_per_inst_executed.ratio per launch)"}
 stage_kernel = {"headline": {"pair": "findPairsDenseKernel", "gjk": "narrowClosedFusedKernel", "refit": "refitTmaKernel"}}
 for wl, m in stage_kernel.items():
     traffic[wl] = {}
@@ -169,7 +173,9 @@ for wl, m in stage_kernel.items():
         if v:
             t = float(v['gpu__time_duration.sum'])
             traffic[wl][stage] = {"kernel": kn, "ncu_kernel_ms": t / 1000.0,
-                                  "dram_bytes_per_launch": (float(v['dram__bytes_read.sum']) + float(v['dram__bytes_write.sum'])) * 1e6}
+                                  "dram_bytes_per_launch": (float(v['dram__bytes_read.sum']) + float(v['dram__bytes_write.sum'])) * 1e6,
+                                  "warp_instructions_per_launch": float(v['smsp__inst_executed.sum']),
+                                  "threads_per_instruction": float(v['smsp__thread_inst_executed_per_inst_executed.ratio'])}
 if c2data:
     traffic["C2"] = {}
     for stage, kn in (("epa", "epaKernel"), ("gjk", "gjkKernel")):
@@ -177,6 +183,8 @@ if c2data:
         if v:
             t = float(v['gpu__time_duration.sum'])
             traffic["C2"][stage] = {"kernel": kn, "ncu_kernel_ms": t / 1000.0,
-                                    "dram_bytes_per_launch": (float(v['dram__bytes_read.sum']) + float(v['dram__bytes_write.sum'])) * 1e6}
+                                    "dram_bytes_per_launch": (float(v['dram__bytes_read.sum']) + float(v['dram__bytes_write.sum'])) * 1e6,
+                                    "warp_instructions_per_launch": float(v['smsp__inst_executed.sum']),
+                                    "threads_per_instruction": float(v['smsp__thread_inst_executed_per_inst_executed.ratio'])}
 json.dump(traffic, open(os.path.join(HERE, "r02_traffic.json"), 'w'), indent=1)
 print(md[:1200])

@@ -28,6 +28,17 @@ for name, kw in (("C0", {}), ("C2", {"scale": 0.003}), ("C3", {"scale": 8 / 4096
     perm = rng.permutation(s.n).astype(np.uint32)
     pairs = np.stack([perm[: s.n // 2], perm[s.n // 2: 2 * (s.n // 2)]], axis=1)
     sw = w.ccd_pairs(pairs, rng.normal(size=(s.n, 3)).astype(np.float32))
+    sw2 = w.ccd_pairs(pairs, rng.normal(size=(s.n, 3)).astype(np.float32), rng.normal(size=(s.n, 3)).astype(np.float32) * 0.5)
+    # pose-only upload and the contact sink (fused narrowphase instantiation / copy kernel)
+    sink = np.zeros(w.cfg.maxContacts, axcd.CONTACT_DT)
+    axcd.pin_host_buffer(sink)
+    w.set_contact_sink(sink.ctypes.data, w.cfg.maxContacts)
+    w.set_poses(s.xf[:, :7])
+    st3 = w.step()
+    assert st3.numContacts == st.numContacts and sink[:st3.numContacts].tobytes() == w.contacts().tobytes()
+    w.set_contact_sink(None, 0)
+    axcd.unpin_host_buffer(sink)
+    assert int(sw2["hit"].sum()) >= 0
     w.set_awake((rng.random(s.n) < 0.5).astype(np.uint8))
     w.set_transforms(s.xf)
     st2 = w.step()

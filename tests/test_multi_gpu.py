@@ -86,7 +86,7 @@ def test_slab_exchange_over_nccl_union_equals_single_gpu(size, scene_name, scale
     s = axcd.config_scene(scene_name, scale=scale)
     w = axcd.CollisionWorld.for_scene(s)
     w.step()
-    assert w.stats().numPenetrating > 0 or scene_name == "C1"
+    assert w.stats().numPenetrating > 0 or scene_name in ("C1", "C4")   # boxes and spheres only: nothing reaches EPA
     ref_pairs, ref_con = w.pairs().copy(), w.contacts().copy()
     w.close()
     pairs = np.concatenate([g[0] for g in got])

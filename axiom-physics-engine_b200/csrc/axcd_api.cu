@@ -212,6 +212,33 @@ float evMs(AxcdContext* c, int a, int b) {
     return ms;
 }
 
+// Upper levels of the range tree over the sorted leaf boxes (leaves at [P, 2P) are in place); returns the launch count.
+// With sortedIdx the bottom pass also gathers the leaf records (segGatherBottomKernel).
+uint32_t launchRangeTree(AxcdContext* ctx, cudaStream_t st, const uint32_t* sortedIdx = nullptr,
+                         const uint32_t* sortedKeys = nullptr, int worldShift = 31) {
+    const uint32_t P = ctx->segP;
+    uint32_t launches = 1;
+    const uint32_t bottomBlocks = P > (uint32_t)kSegLeaves ? P / kSegLeaves : 1;
+    if (sortedIdx)
+        segGatherBottomKernel<<<bottomBlocks, kSegThreads, 0, st>>>(ctx->dAabb, sortedIdx, sortedKeys, ctx->n, worldShift,
+                                                                    ctx->dSegLo, ctx->dSegHi, P);
+    else
+        segBuildBottomKernel<<<bottomBlocks, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, P);
+    uint32_t count = bottomBlocks;   // nodes in the level the bottom pass ended on
+    while (count > 1) {
+        ++launches;
+        if (count <= (uint32_t)kSegLeaves) {
+            segBuildTopKernel<<<1, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, count);
+            count = 1;
+        } else {
+            // a middle pass: treat the level as leaves of a smaller tree
+            segBuildBottomKernel<<<count / kSegLeaves, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, count);
+            count /= kSegLeaves;
+        }
+    }
+    return launches;
+}
+
 uint32_t sortTilesFor(uint64_t n) { return (uint32_t)((n + kSortTile - 1) / kSortTile); }
 
 // Waits for the stream and brings the device counters (pair / contact counts) to the host.
@@ -746,26 +773,9 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         const uint32_t P = ctx->segP;
         float4* leafLo = ctx->dSegLo + P;
         float4* leafHi = ctx->dSegHi + P;
-        gatherLeavesKernel<<<b256, 256, 0, st>>>(ctx->dAabb, sVals, sKeys, leafLo, leafHi, n,
-                                                 ctx->hasWorlds ? worldShift : 31);
+        // leaf gather + bottom levels of the range tree in one kernel, then its upper levels
+        const uint32_t segLaunches = launchRangeTree(ctx, st, sVals, sKeys, ctx->hasWorlds ? worldShift : 31);
         if (ctx->hasWorlds) markWorldEndsKernel<<<b256, 256, 0, st>>>(sKeys, n, worldShift, ctx->dWorldEnd);
-        uint32_t segLaunches = 1;
-        {
-            const uint32_t bottomBlocks = P > (uint32_t)kSegLeaves ? P / kSegLeaves : 1;
-            segBuildBottomKernel<<<bottomBlocks, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, P);
-            uint32_t count = bottomBlocks;   // nodes in the level the bottom pass ended on
-            while (count > 1) {
-                ++segLaunches;
-                if (count <= (uint32_t)kSegLeaves) {
-                    segBuildTopKernel<<<1, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, count);
-                    count = 1;
-                } else {
-                    // a middle pass: treat the level as leaves of a smaller tree
-                    segBuildBottomKernel<<<count / kSegLeaves, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, count);
-                    count /= kSegLeaves;
-                }
-            }
-        }
         buildTopologyKernel<true><<<(n + AXCD_TOPO_THREADS - 1) / AXCD_TOPO_THREADS, AXCD_TOPO_THREADS, 0, st>>>(sKeys, n, ctx->dSegLo, ctx->dSegHi, P, ctx->dNodes32);
         ctx->queryNodesValid = false;
         CU(cudaGetLastError());
@@ -779,12 +789,18 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
                                                          ctx->cfg.maxPairs, ctx->dBodyCount, slabRule,
                                                          ctx->filtersOn ? ctx->dFilters : nullptr,
                                                          ctx->awakeOn ? ctx->dAwake : nullptr, ctx->dCtr);
+        else if (ctx->hasWorlds)
+            findPairsDenseKernel<true><<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes32, ctx->dSegLo, ctx->dSegHi,
+                                                                    ctx->dWorldEnd, n, ctx->dPairsTmp,
+                                                                    ctx->cfg.maxPairs, ctx->dBodyCount, slabRule,
+                                                                    ctx->filtersOn ? ctx->dFilters : nullptr,
+                                                                    ctx->awakeOn ? ctx->dAwake : nullptr, ctx->dCtr);
         else
-            findPairsDenseKernel<<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes32, ctx->dSegLo, ctx->dSegHi,
-                                                              ctx->hasWorlds ? ctx->dWorldEnd : nullptr, n, ctx->dPairsTmp,
-                                                              ctx->cfg.maxPairs, ctx->dBodyCount, slabRule,
-                                                              ctx->filtersOn ? ctx->dFilters : nullptr,
-                                                              ctx->awakeOn ? ctx->dAwake : nullptr, ctx->dCtr);
+            findPairsDenseKernel<false><<<tb, kTravThreads, 0, st>>>(leafLo, leafHi, ctx->dNodes32, ctx->dSegLo, ctx->dSegHi,
+                                                                     nullptr, n, ctx->dPairsTmp,
+                                                                     ctx->cfg.maxPairs, ctx->dBodyCount, slabRule,
+                                                                     ctx->filtersOn ? ctx->dFilters : nullptr,
+                                                                     ctx->awakeOn ? ctx->dAwake : nullptr, ctx->dCtr);
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIR);
         // ---- canonical order: counting sort by body a, then tiny per-body sorts by b ------------------
@@ -795,13 +811,17 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
                                                                 &ctx->dCtr->storedPairs);
         scatterPairsKernel<<<ctx->numSMs * AXCD_SCATTER_BLOCKS, 256, 0, st>>>(ctx->dPairsTmp, &ctx->dCtr->pairCount, ctx->cfg.maxPairs,
                                                         ctx->dBodyCount + n, ctx->dSegB);
+#if AXCD_SEGSORT_COOP
+        sortSegmentsCoopKernel<<<(n + kCoopBodies - 1) / kCoopBodies, kCoopBodies, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
+#else
         sortSegmentsKernel<<<(n + AXCD_SEGSORT_THREADS - 1) / AXCD_SEGSORT_THREADS, AXCD_SEGSORT_THREADS, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
+#endif
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIRSORT);
         // no host round trip here: the narrowphase kernels read the pair count on the device
         // morton, (hist, scan, passes), gather, [worldEnds], range tree, topology+fit, traversal, scan, scatter,
         // segment sort
-        ctx->launches[1] = 1 + bucketLaunches + (2 + passes) + 1 + (ctx->hasWorlds ? 1 : 0) + segLaunches + 1 + 1 + 3;
+        ctx->launches[1] = 1 + bucketLaunches + (2 + passes) + 1 + segLaunches + (ctx->hasWorlds ? 1 : 0) + 1 + 3;
     } else {
         recordEv(ctx, EV_SORT);
         recordEv(ctx, EV_BUILD);

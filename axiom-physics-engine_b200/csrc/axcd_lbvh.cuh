@@ -12,23 +12,9 @@
 
 namespace axcd {
 
-// ---- gather leaves into Morton order ------------------------------------------------------------
-// leafLo[k] = (min.xyz, bits(bodyIndex)), leafHi[k] = (max.xyz, bits(last sorted index of the
-// body's world)) for the body at sorted position k.
-__global__ void gatherLeavesKernel(const float* __restrict__ aabb, const uint32_t* __restrict__ sortedIdx,
-                                   const uint32_t* __restrict__ sortedKeys, float4* __restrict__ leafLo,
-                                   float4* __restrict__ leafHi, uint32_t n, int worldShift) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const uint32_t i = sortedIdx[k];
-    const float* b = aabb + (size_t)i * 6;
-    // 24-byte record: three aligned 8-byte loads
-    const float2 b0 = __ldg(reinterpret_cast<const float2*>(b));
-    const float2 b1 = __ldg(reinterpret_cast<const float2*>(b) + 1);
-    const float2 b2 = __ldg(reinterpret_cast<const float2*>(b) + 2);
-    leafLo[k] = make_float4(b0.x, b0.y, b1.x, __uint_as_float(i));
-    leafHi[k] = make_float4(b1.y, b2.x, b2.y, __uint_as_float(sortedKeys[k] >> worldShift));
-}
+// ---- leaves in Morton order ------------------------------------------------------------------------
+// leafLo[k] = (min.xyz, bits(bodyIndex)), leafHi[k] = (max.xyz, bits(world id)) for the body at sorted position k;
+// written by segGatherBottomKernel below, on its way up the range tree.
 
 // leafHi.w currently holds the world id; replace it by the last sorted index of that world so the
 // traversal can prune other worlds with one compare.  worldEnd[w] filled by markWorldEndsKernel.
@@ -167,6 +153,36 @@ segBuildBottomKernel(float4* __restrict__ lo, float4* __restrict__ hi, uint32_t 
     const uint32_t base = P + blockIdx.x * kSegLeaves;
     for (uint32_t t = threadIdx.x; t < width; t += kSegThreads) {
         const float4 a = lo[base + t], b = hi[base + t];
+        sLo[t][0] = a.x; sLo[t][1] = a.y; sLo[t][2] = a.z;
+        sHi[t][0] = b.x; sHi[t][1] = b.y; sHi[t][2] = b.z;
+    }
+    segReduceUp(lo, hi, base, width, sLo, sHi);
+}
+
+// The bottom pass of a step, fused with the leaf gather: the block fetches the boxes of the
+// bodies at its sorted positions, stores the leaf records the traversal reads, and reduces them upward from shared
+// memory — the leaves are not written and read back in between.  Slots >= n keep the empty boxes resizeBodies left.
+__global__ void __launch_bounds__(kSegThreads)
+segGatherBottomKernel(const float* __restrict__ aabb, const uint32_t* __restrict__ sortedIdx,
+                      const uint32_t* __restrict__ sortedKeys, uint32_t n, int worldShift, float4* __restrict__ lo,
+                      float4* __restrict__ hi, uint32_t P) {
+    __shared__ float sLo[kSegLeaves][3], sHi[kSegLeaves][3];
+    const uint32_t width = min((uint32_t)kSegLeaves, P);
+    const uint32_t k0 = blockIdx.x * kSegLeaves;
+    const uint32_t base = P + k0;
+    const float inf = __int_as_float(0x7f800000);
+    for (uint32_t t = threadIdx.x; t < width; t += kSegThreads) {
+        const uint32_t k = k0 + t;
+        float4 a = make_float4(inf, inf, inf, 0.f), b = make_float4(-inf, -inf, -inf, 0.f);
+        if (k < n) {
+            const uint32_t i = __ldg(sortedIdx + k);
+            const float2* r = reinterpret_cast<const float2*>(aabb + (size_t)i * 6);   // 24-byte record: three 8-byte loads
+            const float2 b0 = __ldg(r), b1 = __ldg(r + 1), b2 = __ldg(r + 2);
+            a = make_float4(b0.x, b0.y, b1.x, __uint_as_float(i));
+            b = make_float4(b1.y, b2.x, b2.y, __uint_as_float(__ldg(sortedKeys + k) >> worldShift));
+            lo[base + t] = a;
+            hi[base + t] = b;
+        }
         sLo[t][0] = a.x; sLo[t][1] = a.y; sLo[t][2] = a.z;
         sHi[t][0] = b.x; sHi[t][1] = b.y; sHi[t][2] = b.z;
     }
@@ -552,6 +568,9 @@ __device__ __forceinline__ void testLeafCandidates(uint2 cand, bool valid, const
     }
 }
 
+// WORLDS = false (one world): the first leaf of a node's range is only needed for the world cut, so the walk neither
+// carries nor stacks it.
+template <bool WORLDS>
 __global__ void __launch_bounds__(kTravThreads)
 findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict__ leafHi,
                      const Node32* __restrict__ nodes, const float4* __restrict__ segLo, const float4* __restrict__ segHi,
@@ -569,14 +588,14 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
     const uint32_t i = blockIdx.x * kTravThreads + threadIdx.x;
     constexpr uint32_t kNone = 0xffffffffu;
     constexpr int kWideStack = 2 * kTravStack;
-    uint32_t stackN[kWideStack], stackF[kWideStack];
+    uint32_t stackN[kWideStack], stackF[WORLDS ? kWideStack : 1];
     int sp = 0;
     uint32_t ni = 0, first = 0;
     bool active = i < n && n >= 2;
     uint32_t wEnd = 0, qxy = 0, qzX = 0, qYZ = 0;
     if (active) {
         const float4 lo = leafLo[i], hi = leafHi[i];
-        wEnd = worldEnd ? worldEnd[__float_as_uint(hi.w)] : n - 1;
+        if (WORLDS) wEnd = worldEnd[__float_as_uint(hi.w)];
         const QuantFrame f = loadQuantFrame(segLo, segHi);
         const float b[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
         packQuery(f, b, qxy, qzX, qYZ);
@@ -590,7 +609,7 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
             if (haveB) {
                 --sp;
                 nb = stackN[sp];
-                firstB = stackF[sp];
+                if (WORLDS) firstB = stackF[sp];
             }
             const uint4* npA = reinterpret_cast<const uint4*>(nodes + ni);
             const uint4* npB = reinterpret_cast<const uint4*>(nodes + nb);
@@ -603,8 +622,8 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
                 const uint32_t fst = which ? firstB : first;
                 const uint32_t split = q1.z & kSplitMask, last = q1.w;
                 const bool on = which == 0 || haveB;
-                const bool hitL = on && split > i && fst <= wEnd && quantIntersect(qxy, qzX, qYZ, q0.x, q0.y, q0.z);
-                const bool hitR = on && last > i && split + 1 <= wEnd && quantIntersect(qxy, qzX, qYZ, q0.w, q1.x, q1.y);
+                const bool hitL = on && split > i && (!WORLDS || fst <= wEnd) && quantIntersect(qxy, qzX, qYZ, q0.x, q0.y, q0.z);
+                const bool hitR = on && last > i && (!WORLDS || split + 1 <= wEnd) && quantIntersect(qxy, qzX, qYZ, q0.w, q1.x, q1.y);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const bool hit = c ? hitR : hitL;
@@ -618,7 +637,7 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
                             nextFirst = cf;
                         } else if (sp < kWideStack) {
                             stackN[sp] = child;
-                            stackF[sp] = cf;
+                            if (WORLDS) stackF[sp] = cf;
                             ++sp;
                         } else {
                             atomicExch(&ctr->travOverflow, 1u);
@@ -632,7 +651,7 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
             } else if (sp > 0) {
                 --sp;
                 ni = stackN[sp];
-                first = stackF[sp];
+                if (WORLDS) first = stackF[sp];
             } else {
                 active = false;
             }
@@ -683,24 +702,46 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
 // that serves as the fill cursor).  scatterPairsKernel drops
 // every pair's b into its body-a segment (order inside a segment is arbitrary); sortSegmentsKernel
 // then sorts each segment and writes the final (a, b) list, which is thereby sorted by (a, b).
+#ifndef AXCD_SCATTER_MATCH
+#define AXCD_SCATTER_MATCH 1   // 1: one returning atomic per group of equal a's in a warp (pairSort 0.081 -> 0.075 ms)
+#endif
+#ifndef AXCD_SEGSORT_COOP
+#define AXCD_SEGSORT_COOP 1   // 1: block-cooperative ranking (sortSegmentsCoopKernel); 0: one thread per body
+#endif
 __global__ void scatterPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount,
                                    uint32_t maxPairs, uint32_t* __restrict__ bodyCursor,   // starts as a copy of bodyStart
                                    uint32_t* __restrict__ segB) {
     const uint32_t np = min(*pairCount, maxPairs);
+#if AXCD_SCATTER_MATCH
+    // lanes of a warp that hold pairs of the same body a share one returning atomic (the traversal emits a query's
+    // candidates next to each other, so equal a's sit in neighbouring lanes)
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t trips = (np + stride - 1u) / stride;
+    for (uint32_t t = 0, k = blockIdx.x * blockDim.x + threadIdx.x; t < trips; ++t, k += stride) {
+        const bool valid = k < np;
+        const uint2 pr = valid ? __ldg(pairs + k) : make_uint2(0xffffffffu, 0u);
+        const uint32_t peers = __match_any_sync(0xffffffffu, pr.x);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader && valid) base = atomicAdd(&bodyCursor[pr.x], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) segB[base + __popc(peers & ((1u << lane) - 1u))] = pr.y;
+    }
+#else
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
         const uint2 pr = pairs[k];
         const uint32_t pos = atomicAdd(&bodyCursor[pr.x], 1u);
         segB[pos] = pr.y;
     }
+#endif
 }
 
 constexpr int kSegLocal = 32;
 
-__global__ void sortSegmentsKernel(const uint32_t* __restrict__ bodyStart, const uint32_t* __restrict__ bodyCount,
-                                   uint32_t n, uint32_t* __restrict__ segB, uint2* __restrict__ out) {
-    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
-    const uint32_t start = bodyStart[a], len = bodyCount[a];
+// One body's segment, sorted by one thread.
+__device__ __forceinline__ void sortOneSegment(uint32_t a, uint32_t start, uint32_t len, const uint32_t* __restrict__ segB,
+                                               uint2* __restrict__ out) {
     if (len == 0) return;
     if (len <= kSegLocal) {
         uint32_t v[kSegLocal];
@@ -723,6 +764,59 @@ __global__ void sortSegmentsKernel(const uint32_t* __restrict__ bodyStart, const
             for (uint32_t m = 0; m < len; ++m) r += (segB[start + m] < x) ? 1u : 0u;
             out[start + r] = make_uint2(a, x);   // b values within a segment are distinct
         }
+    }
+}
+
+__global__ void sortSegmentsKernel(const uint32_t* __restrict__ bodyStart, const uint32_t* __restrict__ bodyCount,
+                                   uint32_t n, uint32_t* __restrict__ segB, uint2* __restrict__ out) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    sortOneSegment(a, bodyStart[a], bodyCount[a], segB, out);
+}
+
+// Block-cooperative form of the segment sort.  The segments of 256 consecutive bodies are one contiguous stretch of
+// segB (bodyStart is a scan), so the block loads that stretch coalesced into shared memory, marks every element with
+// its body, and then works per ELEMENT instead of per body: an element's place in its segment is the number of smaller
+// partners in that segment (partners of one body are distinct).  Loads and stores are coalesced, no lane idles on a
+// short segment while its neighbour sorts a long one, and nothing lives in local memory.  A stretch that does not fit
+// the shared buffer (a very dense neighbourhood) takes the per-body path above.
+constexpr int kCoopBodies = 256;
+constexpr int kCoopCap = 6144;   // elements per block stretch held in shared memory (256 bodies x 24 partners)
+
+__global__ void __launch_bounds__(kCoopBodies)
+sortSegmentsCoopKernel(const uint32_t* __restrict__ bodyStart, const uint32_t* __restrict__ bodyCount, uint32_t n,
+                       const uint32_t* __restrict__ segB, uint2* __restrict__ out) {
+    __shared__ uint32_t sV[kCoopCap];
+    __shared__ uint8_t sOwner[kCoopCap];
+    __shared__ uint32_t sStart[kCoopBodies], sLen[kCoopBodies];
+    __shared__ uint32_t sEnd;
+    const int tid = threadIdx.x;
+    const uint32_t a0 = blockIdx.x * kCoopBodies;
+    const uint32_t a = a0 + tid;
+    const uint32_t start = a < n ? __ldg(bodyStart + a) : 0u;
+    const uint32_t len = a < n ? __ldg(bodyCount + a) : 0u;
+    sStart[tid] = start;
+    sLen[tid] = len;
+    const uint32_t lastBody = min(n - a0, (uint32_t)kCoopBodies) - 1u;
+    if ((uint32_t)tid == lastBody) sEnd = start + len;
+    __syncthreads();
+    const uint32_t base = sStart[0];
+    const uint32_t total = sEnd - base;
+    if (total == 0u) return;
+    if (total > (uint32_t)kCoopCap) {
+        sortOneSegment(a, start, len, segB, out);   // oversized stretch: one thread per body
+        return;
+    }
+    for (uint32_t e = tid; e < total; e += kCoopBodies) sV[e] = __ldg(segB + base + e);
+    for (uint32_t k = 0; k < len; ++k) sOwner[start - base + k] = (uint8_t)tid;
+    __syncthreads();
+    for (uint32_t e = tid; e < total; e += kCoopBodies) {
+        const uint32_t t = sOwner[e];
+        const uint32_t s0 = sStart[t] - base, l = sLen[t];
+        const uint32_t x = sV[e];
+        uint32_t r = 0;
+        for (uint32_t m = 0; m < l; ++m) r += (sV[s0 + m] < x) ? 1u : 0u;
+        out[base + s0 + r] = make_uint2(a0 + t, x);
     }
 }
 

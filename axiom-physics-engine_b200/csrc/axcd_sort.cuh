@@ -413,7 +413,10 @@ __global__ void fillRandomKeysKernel(uint32_t* __restrict__ keys, uint32_t* __re
 }
 
 // ---- single-pass exclusive scan of uint32 (decoupled look-back), used for compaction ------------
-constexpr int kScanThreads = 256;
+#ifndef AXCD_SCAN_THREADS
+#define AXCD_SCAN_THREADS 256
+#endif
+constexpr int kScanThreads = AXCD_SCAN_THREADS;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 static_assert(kScanItems == 8, "the scan kernel moves 8 words per thread as two uint4");

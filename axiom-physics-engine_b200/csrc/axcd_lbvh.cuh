@@ -519,6 +519,9 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
 // buffer (one warp-wide prefix sum per trip), and whenever 32 candidates have accumulated the warp tests them
 // densely, one per lane, with a ballot-aggregated append to the block's pair pool.  The internal-node walk is the
 // same two-nodes-in-flight loop; the candidate set and therefore the pair set are unchanged.
+#ifndef AXCD_TRAV_PROLOGUE
+#define AXCD_TRAV_PROLOGUE 1
+#endif
 constexpr int kCandCap = 32 + 32 * 4;   // leftover (< 32) + at most 4 new candidates per lane and trip
 
 __device__ __forceinline__ void testLeafCandidates(uint2 cand, bool valid, const float4* __restrict__ leafLo,
@@ -600,6 +603,45 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
         const float b[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
         packQuery(f, b, qxy, qzX, qYZ);
     }
+#if AXCD_TRAV_PROLOGUE
+    // ---- warp-uniform descent to the lowest node that holds all of the warp's leaves ------------------------------------
+    // The 32 lanes of a warp own consecutive sorted leaves [w0, w1], so the upper part of their walks is the same
+    // path: down the spine towards their own leaves.  Walking it once per warp, one node per trip and without the
+    // per-lane stack logic, replaces ~10 full trips of the loop below.  At a node whose left child holds the whole warp,
+    // the right child lies entirely behind every lane's leaf: each lane tests it against its own box and stacks it on
+    // a hit (exactly what the general loop would have done); a left child that lies entirely in front of the warp is
+    // pruned for every lane by the "sorted position > i" rule.  The descent stops at the first node whose split
+    // separates two of the warp's leaves, or that has a leaf child; the general loop starts there.
+    {
+        const uint32_t w0 = i - (uint32_t)lane;
+        const uint32_t w1 = min(w0 + 31u, n - 1u);
+        if (w0 < n && n >= 2u) {
+            while (true) {
+                const uint4* np = reinterpret_cast<const uint4*>(nodes + ni);
+                const uint4 a0 = __ldg(np), a1 = __ldg(np + 1);
+                const uint32_t split = a1.z & kSplitMask;
+                if (a1.z & (kLeftLeaf | kRightLeaf)) break;
+                if (w1 <= split) {          // the whole warp lives in the left child
+                    if (active && (!WORLDS || split + 1u <= wEnd) && quantIntersect(qxy, qzX, qYZ, a0.w, a1.x, a1.y)) {
+                        if (sp < kWideStack) {
+                            stackN[sp] = split + 1u;
+                            if (WORLDS) stackF[sp] = split + 1u;
+                            ++sp;
+                        } else {
+                            atomicExch(&ctr->travOverflow, 1u);
+                        }
+                    }
+                    ni = split;             // (first is unchanged)
+                } else if (w0 > split) {    // ... in the right child: the left one is in front of every lane
+                    ni = split + 1u;
+                    first = split + 1u;
+                } else {
+                    break;
+                }
+            }
+        }
+    }
+#endif
     uint32_t cnt = 0;   // candidates waiting in this warp's buffer (warp-uniform)
     while (__any_sync(0xffffffffu, active)) {
         uint32_t cand[4] = {kNone, kNone, kNone, kNone};

@@ -522,7 +522,10 @@ findPairsKernel(const float4* __restrict__ leafLo, const float4* __restrict__ le
 #ifndef AXCD_TRAV_PROLOGUE
 #define AXCD_TRAV_PROLOGUE 1
 #endif
-constexpr int kCandCap = 32 + 32 * 4;   // leftover (< 32) + at most 4 new candidates per lane and trip
+#ifndef AXCD_TRAV_NODES
+#define AXCD_TRAV_NODES 2   // nodes in flight per lane and trip in findPairsDenseKernel
+#endif
+constexpr int kCandCap = 32 + 32 * 2 * AXCD_TRAV_NODES;   // leftover (< 32) + at most two new candidates per node, lane and trip
 
 __device__ __forceinline__ void testLeafCandidates(uint2 cand, bool valid, const float4* __restrict__ leafLo,
                                                    const float4* __restrict__ leafHi, const SlabRule& slab,
@@ -643,29 +646,43 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
     }
 #endif
     uint32_t cnt = 0;   // candidates waiting in this warp's buffer (warp-uniform)
+    constexpr int K = AXCD_TRAV_NODES;   // nodes in flight per lane and trip: the carried one + up to K - 1 popped
     while (__any_sync(0xffffffffu, active)) {
-        uint32_t cand[4] = {kNone, kNone, kNone, kNone};
+        uint32_t cand[2 * K];
+#pragma unroll
+        for (int k = 0; k < 2 * K; ++k) cand[k] = kNone;
         if (active) {
-            const bool haveB = sp > 0;
-            uint32_t nb = ni, firstB = first;
-            if (haveB) {
-                --sp;
-                nb = stackN[sp];
-                if (WORLDS) firstB = stackF[sp];
+            uint32_t nd[K], fs[K];
+            bool on[K];
+            nd[0] = ni;
+            fs[0] = first;
+            on[0] = true;
+#pragma unroll
+            for (int k = 1; k < K; ++k) {
+                on[k] = sp > 0;
+                nd[k] = ni;
+                fs[k] = first;
+                if (on[k]) {
+                    --sp;
+                    nd[k] = stackN[sp];
+                    if (WORLDS) fs[k] = stackF[sp];
+                }
             }
-            const uint4* npA = reinterpret_cast<const uint4*>(nodes + ni);
-            const uint4* npB = reinterpret_cast<const uint4*>(nodes + nb);
-            const uint4 a0 = __ldg(npA), a1 = __ldg(npA + 1);
-            const uint4 b0 = __ldg(npB), b1 = __ldg(npB + 1);
+            uint4 r0[K], r1[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint4* np = reinterpret_cast<const uint4*>(nodes + nd[k]);
+                r0[k] = __ldg(np);
+                r1[k] = __ldg(np + 1);
+            }
             uint32_t next = kNone, nextFirst = 0;
 #pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                const uint4 q0 = which ? b0 : a0, q1 = which ? b1 : a1;
-                const uint32_t fst = which ? firstB : first;
+            for (int which = 0; which < K; ++which) {
+                const uint4 q0 = r0[which], q1 = r1[which];
+                const uint32_t fst = fs[which];
                 const uint32_t split = q1.z & kSplitMask, last = q1.w;
-                const bool on = which == 0 || haveB;
-                const bool hitL = on && split > i && (!WORLDS || fst <= wEnd) && quantIntersect(qxy, qzX, qYZ, q0.x, q0.y, q0.z);
-                const bool hitR = on && last > i && (!WORLDS || split + 1 <= wEnd) && quantIntersect(qxy, qzX, qYZ, q0.w, q1.x, q1.y);
+                const bool hitL = on[which] && split > i && (!WORLDS || fst <= wEnd) && quantIntersect(qxy, qzX, qYZ, q0.x, q0.y, q0.z);
+                const bool hitR = on[which] && last > i && (!WORLDS || split + 1 <= wEnd) && quantIntersect(qxy, qzX, qYZ, q0.w, q1.x, q1.y);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const bool hit = c ? hitR : hitL;
@@ -699,7 +716,9 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
             }
         }
         // ---- append this trip's leaf candidates to the warp's buffer: one prefix sum over the lanes' counts --------
-        const uint32_t mine = (cand[0] != kNone) + (cand[1] != kNone) + (cand[2] != kNone) + (cand[3] != kNone);
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * K; ++k) mine += (cand[k] != kNone) ? 1u : 0u;
         if (__any_sync(0xffffffffu, mine != 0u)) {
             uint32_t inc = mine;
 #pragma unroll
@@ -710,7 +729,7 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
             const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
             uint32_t at = cnt + inc - mine;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 2 * K; ++k)
                 if (cand[k] != kNone) sCand[warp][at++] = make_uint2(i, cand[k]);
             cnt += total;
             __syncwarp();

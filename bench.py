@@ -260,9 +260,9 @@ def stage_table(avg, st, hbm_peak, fp32_peak, generic_pairs):
     info = {
         "refitMs": ("refitTmaKernel", "hbm", n * 80),
         "sortMs": ("mortonKernel + onesweep radix sort (%d passes)" % passes, "hbm", n * 32 + n * (16 * passes + 4)),
-        "buildMs": ("leaf gather + range tree + Karras topology/fit (32-byte nodes)", "hbm", n * (24 + 32) + n * 64 + n * 32),
+        "buildMs": ("leaf gather fused with the range tree + Karras topology/fit (32-byte nodes)", "hbm", n * (24 + 32) + n * 32 + n * 32),
         "pairMs": ("findPairsDenseKernel (LBVH traversal, dense leaf tests)", "hbm", n * 32 + npairs * 8),
-        "pairSortMs": ("pair counting sort (scan + scatter + segment sort)", "hbm", n * 12 + npairs * (8 + 4 + 4 + 8)),
+        "pairSortMs": ("pair counting sort (scan + scatter + block-cooperative segment sort)", "hbm", n * 12 + npairs * (8 + 4 + 4 + 8)),
         "epaMs": ("epaKernel (+fallback)", "fp32", nepa * EPA_FLOP_PER_PAIR),
     }
     if generic_pairs > 0.05 * max(1, npairs):

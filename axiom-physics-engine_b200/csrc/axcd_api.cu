@@ -27,9 +27,6 @@ using namespace axcd;
 #ifndef AXCD_TOPO_THREADS
 #define AXCD_TOPO_THREADS 64
 #endif
-#ifndef AXCD_SEGSORT_THREADS
-#define AXCD_SEGSORT_THREADS 64
-#endif
 
 namespace {
 
@@ -61,6 +58,13 @@ struct AxcdContext {
     float* dPoseStage = nullptr;     // n * 7 floats: landing area of axcd_set_poses
     AxcdContact* sinkDev = nullptr;  // axcd_set_contact_sink: device-side address of the caller's page-locked buffer
     AxcdContact* sinkHost = nullptr;
+    // progress words of the fused narrowphase (page-locked, mapped): [0] pair count + 1, [1 + t] contacts through tile t + 1
+    volatile uint32_t* hProgress = nullptr;
+    uint32_t* dProgress = nullptr;       // the same words as the kernel addresses them
+    uint32_t progressWords = 0;
+    cudaStream_t copyStream = nullptr;   // the sink's DMA chunks travel here while the narrowphase still runs
+    bool sinkPending = false;            // a narrowphase that reports progress was launched and its sink not yet drained
+    bool narrowReportsProgress = false;  // what the last axcd_narrowphase call launched (saved with a captured graph)
     uint4* dShapes = nullptr;
     uint8_t* dType8 = nullptr;       // shape type per body, rewritten by every refit
     float4* dHull = nullptr;
@@ -161,6 +165,7 @@ struct AxcdContext {
         uint64_t gen = 0;
         uint32_t launches[3] = {0, 0, 0};
         int sortedBuf = 0;
+        bool reportsProgress = false;   // its narrowphase reports tile progress to the host (contact sink attached)
     } graph[2];
     uint64_t gen = 1, lastStepGen = 0;
     bool capturing = false;      // stage functions are being recorded into a graph: no event records
@@ -271,7 +276,70 @@ int resizeBodies(AxcdContext* ctx, uint32_t n) {
     return AXCD_OK;
 }
 
+// ---- contact sink of the fused narrowphase: host side ---------------------------------------------------------------
+// The kernel reports, tile by tile and in pair order, how far the device contact array is complete (progress words in
+// page-locked memory, see narrowClosedFusedKernel).  drainContactSink runs inside the next blocking call: it follows
+// the words while the kernel is still running and hands every finished stretch of ~4 MB to the copy engine on a second
+// stream, so the contacts cross PCIe as DMA bursts behind the narrowphase instead of after it.
+int drainContactSink(AxcdContext* ctx) {
+    if (!ctx->sinkPending) return AXCD_OK;
+    ctx->sinkPending = false;
+    if (!ctx->sinkHost || !ctx->hProgress) return AXCD_OK;
+    volatile uint32_t* pr = ctx->hProgress;
+    const uint32_t maxTiles = ctx->progressWords - 1u;
+    // chunk sizes double from 256 KB to 8 MB: the copy engine starts as soon as the first tiles are in, and the later,
+    // larger bursts keep the per-copy set-up off the wire (profiles/r02_experiments.md: fixed 1 / 2 / 4 / 8 / 16 MB
+    // chunks 2.28 / 2.27 / 2.23 / 2.22 / 2.23 ms per e2e step on a box where stores from the SMs gave 2.31)
+    const uint32_t maxChunk = (8u << 20) / (uint32_t)sizeof(AxcdContact);
+    uint32_t chunk = (256u << 10) / (uint32_t)sizeof(AxcdContact);
+    uint32_t tiles = 0xffffffffu;   // unknown until the kernel has stored the pair count
+    uint32_t next = 0, end = 0, copied = 0, spins = 0;
+    bool computeDone = false;
+    while (true) {
+        if (tiles == 0xffffffffu) {
+            const uint32_t np1 = pr[0];
+            if (np1) tiles = (uint32_t)(((uint64_t)(np1 - 1u) + kFusedTile - 1) / kFusedTile);
+        }
+        const uint32_t limit = tiles == 0xffffffffu ? maxTiles : (tiles < maxTiles ? tiles : maxTiles);
+        while (next < limit) {
+            const uint32_t f = pr[1u + next];
+            if (!f) break;
+            end = f - 1u;
+            ++next;
+        }
+        const bool all = tiles != 0xffffffffu && next >= limit;
+        if (end > copied && (end - copied >= chunk || all)) {
+            CU(cudaMemcpyAsync(ctx->sinkHost + copied, ctx->dContacts + copied, sizeof(AxcdContact) * (size_t)(end - copied),
+                               cudaMemcpyDeviceToHost, ctx->copyStream));
+            copied = end;
+            chunk = chunk * 2u < maxChunk ? chunk * 2u : maxChunk;
+        }
+        if (all) break;
+        if (computeDone) return AXCD_ERR_GPU_FAILED;   // the step has ended and the words are still incomplete
+        if ((++spins & 1023u) == 0u) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) computeDone = true;   // one more pass over the words, then give up
+            else if (q != cudaErrorNotReady) CU(q);
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->copyStream));
+    return AXCD_OK;
+}
+
+// Before a narrowphase that reports progress is launched: the previous step's sink is complete and the words are clear.
+int armContactSink(AxcdContext* ctx) {
+    const int rc = drainContactSink(ctx);
+    if (rc) return rc;
+    memset(const_cast<uint32_t*>(ctx->hProgress), 0, sizeof(uint32_t) * ctx->progressWords);
+    ctx->sinkPending = true;
+    return AXCD_OK;
+}
+
 int refreshCountersImpl(AxcdContext* ctx) {
+    {
+        const int rc = drainContactSink(ctx);
+        if (rc) return rc;
+    }
     CU(cudaMemcpyAsync(&ctx->hostCtr, ctx->dCtr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->stage >= ST_BROAD) {
@@ -382,6 +450,8 @@ void axcd_destroy(AxcdContext* ctx) {
     for (auto& g : ctx->graph)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     slabRelease(ctx);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    if (ctx->hProgress) cudaFreeHost(const_cast<uint32_t*>(ctx->hProgress));
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
@@ -811,11 +881,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
                                                                 &ctx->dCtr->storedPairs);
         scatterPairsKernel<<<ctx->numSMs * AXCD_SCATTER_BLOCKS, 256, 0, st>>>(ctx->dPairsTmp, &ctx->dCtr->pairCount, ctx->cfg.maxPairs,
                                                         ctx->dBodyCount + n, ctx->dSegB);
-#if AXCD_SEGSORT_COOP
         sortSegmentsCoopKernel<<<(n + kCoopBodies - 1) / kCoopBodies, kCoopBodies, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
-#else
-        sortSegmentsKernel<<<(n + AXCD_SEGSORT_THREADS - 1) / AXCD_SEGSORT_THREADS, AXCD_SEGSORT_THREADS, 0, st>>>(ctx->dBodyStart, ctx->dBodyCount, n, ctx->dSegB, ctx->dPairs);
-#endif
         CU(cudaGetLastError());
         recordEv(ctx, EV_PAIRSORT);
         // no host round trip here: the narrowphase kernels read the pair count on the device
@@ -845,6 +911,7 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
     cudaSetDevice(ctx->cfg.deviceOrdinal);
     cudaStream_t st = ctx->stream;
     recordEv(ctx, EV_N0);
+    ctx->narrowReportsProgress = false;
     ctx->numContacts = ctx->foundContacts = 0;
     ctx->manifoldsValid = false;
     ctx->launches[2] = 0;
@@ -884,11 +951,16 @@ int32_t axcd_narrowphase(AxcdContext* ctx) {
             // every pair is decided in closed form: classification, closed forms and in-order compaction in ONE kernel
             const uint32_t fusedTilesMax = (mp + kFusedTile - 1) / kFusedTile;
             const uint32_t fusedBlocks = fusedTilesMax < (uint32_t)ctx->numSMs * AXCD_FUSED_MINBLOCKS ? fusedTilesMax : (uint32_t)ctx->numSMs * AXCD_FUSED_MINBLOCKS;
-            if (ctx->sinkDev)
+            if (ctx->sinkDev && ctx->dProgress) {
+                if (!ctx->capturing) {   // (a captured step is armed by axcd_step_async when the graph is launched)
+                    const int rc = armContactSink(ctx);
+                    if (rc) return rc;
+                }
                 narrowClosedFusedKernel<true><<<fusedBlocks, kFusedThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dXf, ctx->dShapes,
-                                                                                     ctx->dContacts, ctx->cfg.maxContacts, ctx->sinkDev,
+                                                                                     ctx->dContacts, ctx->cfg.maxContacts, ctx->dProgress,
                                                                                      ctx->dSlotStatus, ctx->dCtr);
-            else
+                ctx->narrowReportsProgress = true;
+            } else
                 narrowClosedFusedKernel<false><<<fusedBlocks, kFusedThreads, 0, st>>>(pairs, pairCount, mp, ctx->dType8, ctx->dXf, ctx->dShapes,
                                                                                       ctx->dContacts, ctx->cfg.maxContacts, nullptr,
                                                                                       ctx->dSlotStatus, ctx->dCtr);
@@ -1047,6 +1119,7 @@ int32_t axcd_step_async(AxcdContext* ctx) {
                     g.launches[1] = ctx->launches[1];
                     g.launches[2] = ctx->launches[2];
                     g.sortedBuf = ctx->sortedBuf;
+                    g.reportsProgress = ctx->narrowReportsProgress;
                 } else {
                     g.exec = nullptr;
                     ctx->graphsOff = true;   // something on the path is not capturable here: stay on direct launches
@@ -1063,6 +1136,10 @@ int32_t axcd_step_async(AxcdContext* ctx) {
             ctx->stage = stageBefore;
         }
         if (g.exec) {
+            if (g.reportsProgress) {
+                const int rc = armContactSink(ctx);
+                if (rc) return rc;
+            }
             ctx->ctrParity = parity;
             ctx->dCtr = ctx->dCtrBase + parity;
             for (int e = 0; e < EV_COUNT; ++e) ctx->evValid[e] = false;
@@ -1165,6 +1242,10 @@ int32_t axcd_get_contacts(AxcdContext* ctx, AxcdContact* out, uint32_t cap, uint
 int32_t axcd_set_contact_sink(AxcdContext* ctx, AxcdContact* hostBuffer, uint32_t capacity) {
     if (!ctx) return AXCD_ERR_NULL_POINTER;
     cudaSetDevice(ctx->cfg.deviceOrdinal);
+    {   // a step in flight still delivers into the buffer it was launched with
+        const int rc = drainContactSink(ctx);
+        if (rc) return rc;
+    }
     if (!hostBuffer) {
         if (ctx->sinkDev) ctx->gen++;   // the launch configuration changed: graphs are re-captured
         ctx->sinkDev = ctx->sinkHost = nullptr;
@@ -1175,6 +1256,22 @@ int32_t axcd_set_contact_sink(AxcdContext* ctx, AxcdContact* hostBuffer, uint32_
     if (cudaHostGetDevicePointer(&dev, hostBuffer, 0) != cudaSuccess || !dev) {   // not page-locked / not mapped
         cudaGetLastError();
         return AXCD_ERR_INVALID_PARAM;
+    }
+    if (!ctx->hProgress) {   // progress words of the fused narrowphase + the stream its DMA chunks use
+        const uint32_t words = (ctx->cfg.maxPairs + kFusedTile - 1) / kFusedTile + 2u;
+        void* h = nullptr;
+        void* d = nullptr;
+        if (cudaHostAlloc(&h, sizeof(uint32_t) * words, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            if (h) cudaFreeHost(h);
+            return AXCD_ERR_OUT_OF_MEMORY;
+        }
+        memset(h, 0, sizeof(uint32_t) * words);
+        ctx->hProgress = static_cast<volatile uint32_t*>(h);
+        ctx->dProgress = static_cast<uint32_t*>(d);
+        ctx->progressWords = words;
     }
     if (dev != ctx->sinkDev) ctx->gen++;
     ctx->sinkDev = static_cast<AxcdContact*>(dev);
@@ -1302,8 +1399,8 @@ int32_t axcd_query_aabbs(AxcdContext* ctx, const float* boxes6, const uint32_t* 
     CU(growScratch(&ctx->dQOut, &ctx->qOutBytes, (size_t)total * 8));
     queryAabbKernel<true><<<blocks, kQueryThreads, 0, st>>>(T, dBoxes, useWorld ? dQW : nullptr, nq, dCounts, dStarts,
                                                             static_cast<uint32_t*>(ctx->dQSeg));
-    sortSegmentsKernel<<<(nq + 255) / 256, 256, 0, st>>>(dStarts, dCounts, nq, static_cast<uint32_t*>(ctx->dQSeg),
-                                                          static_cast<uint2*>(ctx->dQOut));
+    sortSegmentsCoopKernel<<<(nq + kCoopBodies - 1) / kCoopBodies, kCoopBodies, 0, st>>>(dStarts, dCounts, nq, static_cast<uint32_t*>(ctx->dQSeg),
+                                                                                         static_cast<uint2*>(ctx->dQOut));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(outHits2, ctx->dQOut, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

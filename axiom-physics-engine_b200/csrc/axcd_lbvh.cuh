@@ -761,13 +761,10 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
 // ---- canonical pair order by counting sort ---------------------------------------------------------
 // bodyStart = exclusive scan of bodyCount (done with exclusiveScanKernel, which also writes the copy
 // that serves as the fill cursor).  scatterPairsKernel drops
-// every pair's b into its body-a segment (order inside a segment is arbitrary); sortSegmentsKernel
+// every pair's b into its body-a segment (order inside a segment is arbitrary); sortSegmentsCoopKernel
 // then sorts each segment and writes the final (a, b) list, which is thereby sorted by (a, b).
 #ifndef AXCD_SCATTER_MATCH
 #define AXCD_SCATTER_MATCH 1   // 1: one returning atomic per group of equal a's in a warp (pairSort 0.081 -> 0.075 ms)
-#endif
-#ifndef AXCD_SEGSORT_COOP
-#define AXCD_SEGSORT_COOP 1   // 1: block-cooperative ranking (sortSegmentsCoopKernel); 0: one thread per body
 #endif
 __global__ void scatterPairsKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount,
                                    uint32_t maxPairs, uint32_t* __restrict__ bodyCursor,   // starts as a copy of bodyStart
@@ -826,13 +823,6 @@ __device__ __forceinline__ void sortOneSegment(uint32_t a, uint32_t start, uint3
             out[start + r] = make_uint2(a, x);   // b values within a segment are distinct
         }
     }
-}
-
-__global__ void sortSegmentsKernel(const uint32_t* __restrict__ bodyStart, const uint32_t* __restrict__ bodyCount,
-                                   uint32_t n, uint32_t* __restrict__ segB, uint2* __restrict__ out) {
-    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
-    sortOneSegment(a, bodyStart[a], bodyCount[a], segB, out);
 }
 
 // Block-cooperative form of the segment sort.  The segments of 256 consecutive bodies are one contiguous stretch of

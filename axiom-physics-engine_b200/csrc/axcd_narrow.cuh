@@ -1344,11 +1344,17 @@ constexpr int kFusedItems = 4;
 constexpr int kFusedTile = kFusedThreads * kFusedItems;   // 1024 pairs
 constexpr int kFusedRecWords = 7;                          // position, normal, depth (ids come from the pair, status is 0)
 
-template <bool SINK>
+// PROGRESS = true (a contact sink is attached, axcd_set_contact_sink): the kernel also tells the HOST how far the
+// contact array is complete, through words in page-locked host memory: progress[0] = pair count + 1 (so the host
+// knows how many tiles to expect), progress[1 + t] = (number of contacts of tiles 0..t, capped at the capacity) + 1,
+// stored once tile t's records are in the device array (system-scope fence between the two).  The host drains the
+// tiles in order while the kernel is still running and moves the finished stretch of the array with the copy engine
+// (drainContactSink in axcd_api.cu): DMA bursts reach ~55 GB/s over PCIe where stores from the SMs reached ~49.
+template <bool PROGRESS>
 __global__ void __launch_bounds__(kFusedThreads, AXCD_FUSED_MINBLOCKS)
 narrowClosedFusedKernel(const uint2* __restrict__ pairs, const uint32_t* __restrict__ pairCount, uint32_t maxPairs,
                         const uint8_t* __restrict__ type8, const float* __restrict__ xf, const uint4* __restrict__ shapes,
-                        AxcdContact* __restrict__ contacts, uint32_t maxContacts, AxcdContact* __restrict__ sink,
+                        AxcdContact* __restrict__ contacts, uint32_t maxContacts, volatile uint32_t* __restrict__ progress,
                         volatile uint32_t* __restrict__ tileStatus, Counters* __restrict__ ctr) {
     __shared__ __align__(16) float sRec[kFusedTile * kFusedRecWords];   // 28 KB: contact floats by local pair index
     __shared__ uint2 sPair[kFusedTile];
@@ -1359,8 +1365,15 @@ narrowClosedFusedKernel(const uint2* __restrict__ pairs, const uint32_t* __restr
     __shared__ uint32_t sTile, sSlotBase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t npairs = min(*pairCount, maxPairs);
+    if (PROGRESS && blockIdx.x == 0 && tid == 0) progress[0] = npairs + 1u;
+    uint32_t doneTile = 0, doneEnd = 0;   // thread 0: the tile this block finished last, not yet reported to the host
+    bool haveDone = false;
     while (true) {
-        __syncthreads();
+        __syncthreads();   // (PROGRESS: every thread's records of the previous tile are stored and fenced)
+        if (PROGRESS && tid == 0 && haveDone) {
+            progress[1u + doneTile] = doneEnd + 1u;
+            haveDone = false;
+        }
         if (tid == 0) sTile = atomicAdd(&ctr->gjkTicket, 1u);
         if (tid < 4) sCnt[tid] = 0;
         __syncthreads();
@@ -1490,7 +1503,7 @@ narrowClosedFusedKernel(const uint2* __restrict__ pairs, const uint32_t* __restr
             }
         }
         __syncthreads();
-        if (!SINK) {   // device array only: every thread stores its own records (measured 12 us faster than staging them)
+        {   // every thread stores its own records
             uint32_t slot = sSlotBase + warpPrefix + inc - sum;
 #pragma unroll
             for (int i = 0; i < kFusedItems; ++i) {
@@ -1504,68 +1517,13 @@ narrowClosedFusedKernel(const uint2* __restrict__ pairs, const uint32_t* __restr
                     ++slot;
                 }
             }
-            continue;
         }
-        // ---- 4. the tile's contacts leave as one contiguous run of 40-byte records ------------------------------------
-        // Each thread lifts its (at most four) records into registers, the block re-packs them as whole records at
-        // their position inside the tile's run (the staging area is the record area itself, hence the barrier between
-        // the two), and all threads copy the run out with 128-bit stores: to the device array and, when the caller
-        // gave one (axcd_set_contact_sink), also straight to its page-locked host buffer — the host copy of the
-        // contacts then travels while the narrowphase is still running instead of after it.
-        const uint32_t slotBase = sSlotBase;
-        const uint32_t local0 = warpPrefix + inc - sum;       // position of this thread's first contact inside the tile's run
-        float rec[kFusedItems][kFusedRecWords];
-#pragma unroll
-        for (int i = 0; i < kFusedItems; ++i) {
-            if ((fl >> (8 * i)) & 1u) {
-                const uint32_t li = tid * kFusedItems + i;
-#pragma unroll
-                for (int k = 0; k < kFusedRecWords; ++k) rec[i][k] = sRec[li * kFusedRecWords + k];
-            }
-        }
-        constexpr uint32_t kStageCap = (uint32_t)(kFusedTile * kFusedRecWords) / 10u;   // whole records the record area holds
-        for (uint32_t chunk = 0; chunk < tileTotal; chunk += kStageCap) {
-            __syncthreads();   // everybody has lifted its records (first trip) / copied the previous chunk out
-            uint32_t at = local0;
-#pragma unroll
-            for (int i = 0; i < kFusedItems; ++i) {
-                if ((fl >> (8 * i)) & 1u) {
-                    if (at >= chunk && at < chunk + kStageCap) {
-                        float* o = sRec + (at - chunk) * 10u;
-                        const uint2 pk = sPair[tid * kFusedItems + i];   // the pair list is not part of the staging area
-                        o[0] = __uint_as_float(pk.x); o[1] = __uint_as_float(pk.y);
-                        o[2] = rec[i][0]; o[3] = rec[i][1]; o[4] = rec[i][2];
-                        o[5] = rec[i][3]; o[6] = rec[i][4]; o[7] = rec[i][5];
-                        o[8] = rec[i][6]; o[9] = __uint_as_float(0u);
-                    }
-                    ++at;
-                }
-            }
-            __syncthreads();
-            const uint32_t first = slotBase + chunk;                               // first slot of this chunk
-            uint32_t cnt = min(kStageCap, tileTotal - chunk);
-            cnt = (first >= maxContacts) ? 0u : min(cnt, maxContacts - first);     // never past the capacity
-            const uint32_t words = cnt * 10u;
-            const size_t g0 = (size_t)first * 10u;                                 // even: 40-byte records, 8-byte aligned
-            const uint32_t head = (uint32_t)(g0 & 3u) ? min(2u, words) : 0u;       // two words up to 16-byte alignment
-            const uint32_t nVec = (words - head) / 4u;
-            const uint32_t tail = head + nVec * 4u;
-            float* dstD = reinterpret_cast<float*>(contacts) + g0;
-            float* dstH = reinterpret_cast<float*>(sink) + g0;
-            const float2* src2 = reinterpret_cast<const float2*>(sRec);            // the staging area, 8-byte granules
-            for (uint32_t v = tid; v < nVec; v += kFusedThreads) {
-                const float2 lo = src2[(head + 4u * v) / 2u], hi = src2[(head + 4u * v) / 2u + 1u];
-                const float4 q = make_float4(lo.x, lo.y, hi.x, hi.y);
-                *reinterpret_cast<float4*>(dstD + head + 4u * v) = q;
-                *reinterpret_cast<float4*>(dstH + head + 4u * v) = q;
-            }
-            if (tid == 0 && head) {
-                *reinterpret_cast<float2*>(dstD) = src2[0];
-                *reinterpret_cast<float2*>(dstH) = src2[0];
-            }
-            if (tid == 1 && tail < words) {   // two words left over
-                *reinterpret_cast<float2*>(dstD + tail) = src2[tail / 2u];
-                *reinterpret_cast<float2*>(dstH + tail) = src2[tail / 2u];
+        if (PROGRESS) {
+            __threadfence_system();   // the records before the word the host reads (stored after the next barrier)
+            if (tid == 0) {
+                doneTile = tile;
+                doneEnd = min(sSlotBase + tileTotal, maxContacts);
+                haveDone = true;
             }
         }
     }

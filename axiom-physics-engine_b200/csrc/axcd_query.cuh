@@ -56,7 +56,7 @@ __device__ __forceinline__ void worldRange(const QueryTree& T, uint32_t w, uint3
 
 // ---- AABB overlap query ---------------------------------------------------------------------------
 // FILL = false: counts[q] = number of hits.  FILL = true: writes the hit bodies into the query's segment
-// [starts[q], starts[q] + counts[q]) of segB (unordered; sortSegmentsKernel orders them).
+// [starts[q], starts[q] + counts[q]) of segB (unordered; sortSegmentsCoopKernel orders them).
 template <bool FILL>
 __global__ void __launch_bounds__(kQueryThreads)
 queryAabbKernel(QueryTree T, const float* __restrict__ qboxes, const uint32_t* __restrict__ qworld, uint32_t nq,

@@ -612,7 +612,7 @@ def run_ours(args):
     e2e_full_value, e2e_full_ms, st2 = e2e_loop(lambda: w.set_transforms_ptr(h_xf.data_ptr(), s.n), sink=False)
     # ... or, as a rigid-body step does, position + rotation only (axcd_set_poses, 28 B per body: the scales went to the
     # device with the set_transforms above and do not change from step to step), with the contacts delivered into a
-    # registered page-locked buffer while the narrowphase runs (axcd_set_contact_sink).  This is the `e2e` of the line.
+    # registered page-locked buffer while the narrowphase runs (axcd_set_contact_sink: DMA chunks behind the kernel).  This is the `e2e` of the line.
     e2e_value, e2e_ms, st2 = e2e_loop(lambda: w.set_poses_ptr(h_pose.data_ptr(), s.n), sink=True)
     sink_ok = bool(np.array_equal(h_con[:st2.numContacts].numpy().view(np.uint32),
                                   w.contacts().view(np.uint32).reshape(-1, 10)))
@@ -682,7 +682,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps,
                     "upload": "axcd_set_poses: position + rotation, 28 B per body from pinned memory (scales resident)",
-                    "download": "axcd_set_contact_sink: the step delivers the contacts into the pinned host buffer",
+                    "download": "axcd_set_contact_sink: copy-engine chunks follow the fused narrowphase tile by tile into the pinned host buffer",
                     "sink_matches_device_contacts": sink_ok},
             "e2e_full_transforms": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": int(s.n) * 40,
                                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_full_ms / e2e_steps,

@@ -303,11 +303,13 @@ AXCD_API int32_t axcd_ccd_pairs_angular(AxcdContext* ctx, const uint32_t* pairs2
 /* Contact sink: a page-locked host buffer (axcd_pin_host_buffer, cudaHostAlloc, ...) of at least maxContacts
  * records that every narrowphase from now on fills with the step's contacts — the records axcd_get_contacts
  * returns, in the same order — so that the host copy travels while the narrowphase is still running instead of
- * in a separate copy after it (scenes decided in closed form: the narrowphase kernel stores each finished tile
- * to the device array and to the sink; other scenes: one copy kernel at the end of the narrowphase).  The sink
- * is valid once a blocking call (axcd_step, axcd_get_stats, ...) has returned; the count is
- * AxcdStats::numContacts.  NULL detaches it.  600 if the buffer is not page-locked or too small.  The device
- * array stays complete: axcd_get_contacts, manifolds etc. work as before.                                     */
+ * in a separate copy after it.  Scenes decided in closed form: the narrowphase kernel reports, tile by tile, how
+ * far the device array is complete, and the next blocking call on the context follows that and hands every
+ * finished stretch to the copy engine on a second stream (DMA bursts behind the kernel); other scenes: one copy
+ * kernel at the end of the narrowphase.  The sink is valid once a blocking call (axcd_step, axcd_get_stats,
+ * axcd_get_contacts, ...) has returned; the count is AxcdStats::numContacts.  A new step on the same context
+ * first completes the previous step's sink.  NULL detaches it.  600 if the buffer is not page-locked or too
+ * small.  The device array stays complete: axcd_get_contacts, manifolds etc. work as before.                   */
 AXCD_API int32_t axcd_set_contact_sink(AxcdContext* ctx, AxcdContact* hostBuffer, uint32_t capacity);
 
 /* Collision filtering, gui::FilterInfo semantics (include/axiom/gui/body_inspector.hpp:38-42):

@@ -42,7 +42,7 @@ def launch_table(path):
     extra = [f"{k}: {sum(v) / len(v):.1f} us x {len(v)}" for k, v in agg.items() if any(x in k for x in e2e_only)]
     if extra:
         tbl.append("Kernels only the e2e leg launches (`axcd_set_poses` merge; the narrowphase instantiation that also streams the "
-                   "contacts into the page-locked sink and is therefore PCIe-bound): " + "; ".join(extra) + ".\n")
+                   "contact array's progress to the host, whose copy-engine chunks follow it; system-scope fences per tile): " + "; ".join(extra) + ".\n")
     return tbl
 
 

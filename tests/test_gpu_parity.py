@@ -687,8 +687,8 @@ def test_set_poses_uploads_position_and_rotation_only():
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene_name,kw", [("C1", {}), ("C2", {"scale": 0.05})], ids=["closed-form-fused", "generic-gjk-epa"])
 def test_contact_sink_receives_the_steps_contacts(scene_name, kw):
-    """axcd_set_contact_sink: the step delivers the contacts into a page-locked host buffer (written by the fused
-    narrowphase kernel tile by tile, or by a copy kernel behind GJK / EPA); same records, same order."""
+    """axcd_set_contact_sink: the step delivers the contacts into a page-locked host buffer (copy-engine chunks that
+    follow the fused narrowphase kernel tile by tile, or a copy kernel behind GJK / EPA); same records, same order."""
     s = axcd.config_scene(scene_name, **kw)
     w = axcd.CollisionWorld.for_scene(s, pairs_per_body=16)
     cap = w.cfg.maxContacts

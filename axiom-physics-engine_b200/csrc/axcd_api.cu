@@ -139,6 +139,7 @@ struct AxcdContext {
     void* dQOut = nullptr;     size_t qOutBytes = 0;     // sorted (query, body) hits / ray hits
     float* dPairDist = nullptr;
     uint32_t* dSortHist = nullptr;
+    uint32_t* dStepHist = nullptr;   // the step's digit histograms: filled by the Morton kernel, cleared again behind the sort
     uint32_t* dSortStatus = nullptr;
     // bucket sort of the Morton keys (axcd_sort.cuh): counts / starts / cursors per bucket, (key, index) staging
     uint32_t* dBucketCounts = nullptr;
@@ -226,7 +227,8 @@ uint32_t launchRangeTree(AxcdContext* ctx, cudaStream_t st, const uint32_t* sort
     const uint32_t bottomBlocks = P > (uint32_t)kSegLeaves ? P / kSegLeaves : 1;
     if (sortedIdx)
         segGatherBottomKernel<<<bottomBlocks, kSegThreads, 0, st>>>(ctx->dAabb, sortedIdx, sortedKeys, ctx->n, worldShift,
-                                                                    ctx->dSegLo, ctx->dSegHi, P);
+                                                                    ctx->dSegLo, ctx->dSegHi, P, ctx->dStepHist,
+                                                                    (uint32_t)(kMaxPasses * kRadix));
     else
         segBuildBottomKernel<<<bottomBlocks, kSegThreads, 0, st>>>(ctx->dSegLo, ctx->dSegHi, P);
     uint32_t count = bottomBlocks;   // nodes in the level the bottom pass ended on
@@ -440,7 +442,7 @@ void axcd_destroy(AxcdContext* ctx) {
     void* bufs[] = {ctx->dPoseStage, ctx->dXf, ctx->dShapes, ctx->dType8, ctx->dHull, ctx->dWorld, ctx->dBodyKeys, ctx->dFilters, ctx->dAwake, ctx->dGhostSend, ctx->dGhostCount, ctx->dAabb, ctx->dKeys[0], ctx->dKeys[1],
                     ctx->dVals[0], ctx->dVals[1], ctx->dSegLo, ctx->dSegHi, ctx->dNodes, ctx->dNodes32,
                     ctx->dWorldEnd, ctx->dPairsTmp, ctx->dPairs, ctx->dBodyCount, ctx->dBodyStart, ctx->dSegB, ctx->dScanStatus, ctx->dEpaWork,
-                    ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dManifolds, ctx->dQIn, ctx->dQCount, ctx->dQSeg, ctx->dQOut, ctx->dPairDist, ctx->dSortHist,
+                    ctx->dEpaOverflow, ctx->dEpaSpill, ctx->dSlotStatus, ctx->dChunks, ctx->dFlags, ctx->dSlots, ctx->dTmpContacts, ctx->dContacts, ctx->dManifolds, ctx->dQIn, ctx->dQCount, ctx->dQSeg, ctx->dQOut, ctx->dPairDist, ctx->dSortHist, ctx->dStepHist,
                     ctx->dSortStatus, ctx->dCtrBase, ctx->dCtrInit, ctx->dBucketCounts, ctx->dBucketStarts, ctx->dBucketCursors,
                     ctx->dBucketTmp};
     for (void* b : bufs)
@@ -563,6 +565,8 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
         CU(dalloc(&ctx->dContacts, (size_t)cfg->maxContacts));
         if (cfg->flags & AXCD_FLAG_PAIR_DISTANCES) CU(dalloc(&ctx->dPairDist, np));
         CU(dalloc(&ctx->dSortHist, (size_t)kMaxPasses * kRadix));
+        CU(dalloc(&ctx->dStepHist, (size_t)kMaxPasses * kRadix));
+        CU(cudaMemsetAsync(ctx->dStepHist, 0, sizeof(uint32_t) * kMaxPasses * kRadix, ctx->stream));
         const size_t maxTiles = sortTilesFor(nb > np ? nb : np);
         CU(dalloc(&ctx->dSortStatus, (size_t)kMaxPasses * maxTiles * kRadix));
         CU(dalloc(&ctx->dBucketCounts, (size_t)(1u << kMaxBucketBits)));
@@ -802,15 +806,17 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         zl.ptr[0] = ctx->dBodyCount;   zl.words[0] = n;
         zl.ptr[1] = ctx->dScanStatus;  zl.words[1] = scanTilesZ + 1 + 128;
         zl.ptr[2] = ctx->dSlotStatus;  zl.words[2] = slotTilesZ + 1;
-        zl.ptr[3] = ctx->dSortHist;    zl.words[3] = kMaxPasses * kRadix;
+        zl.ptr[3] = ctx->dSortHist;    zl.words[3] = 0;   // (the step's histograms live in dStepHist: see mortonKernel)
         zl.ptr[4] = ctx->dSortStatus;  zl.words[4] = (uint32_t)passes * sortTilesFor(n) * kRadix;
         // Morton keys, then the bucket sort (one MSD pass + per-bucket shared-memory sorts); the LSD radix kernels
         // are launched behind it and run only if a bucket overflowed (device-side flag, no host round trip)
         const BucketPlan bp = ctx->bucketSortOff ? BucketPlan{0, 0} : bucketPlanFor(n, keyBits);
-        mortonKernel<<<blocks, kRefitThreads, 0, st>>>(reinterpret_cast<const float4*>(ctx->dAabb),
-                                                       ctx->hasWorlds ? ctx->dWorld : nullptr, ctx->dKeys[0],
-                                                       ctx->dVals[0], n, ctx->mortonBits, ctx->dCtr, zl,
-                                                       bp.bucketBits ? ctx->dBucketCounts : nullptr, bp.shift);
+        const uint32_t mortonBlocks = blocks < (uint32_t)ctx->numSMs * 4u ? blocks : (uint32_t)ctx->numSMs * 4u;
+        mortonKernel<<<mortonBlocks, kRefitThreads, 0, st>>>(reinterpret_cast<const float4*>(ctx->dAabb),
+                                                             ctx->hasWorlds ? ctx->dWorld : nullptr, ctx->dKeys[0],
+                                                             ctx->dVals[0], n, ctx->mortonBits, ctx->dCtr, zl,
+                                                             bp.bucketBits ? ctx->dBucketCounts : nullptr, bp.shift,
+                                                             ctx->dStepHist, passes);
         CU(cudaGetLastError());
         const uint32_t* lsdEnable = nullptr;
         bucketLaunches = 0;
@@ -830,8 +836,8 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         }
         // the radix tickets live in the per-step counter block, which the refit kernel reset
         const int sb = radixSort<uint32_t, true>(ctx->dKeys[0], ctx->dKeys[1], ctx->dVals[0], ctx->dVals[1], n, 0,
-                                                 passes, ctx->dSortHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st,
-                                                 ctx->numSMs, true, lsdEnable);
+                                                 passes, ctx->dStepHist, ctx->dSortStatus, ctx->dCtr->sortTicket, st,
+                                                 ctx->numSMs, true, lsdEnable, true);
         CU(cudaGetLastError());
         recordEv(ctx, EV_SORT);
         ctx->sortedBuf = sb;
@@ -887,7 +893,7 @@ int32_t axcd_broadphase(AxcdContext* ctx) {
         // no host round trip here: the narrowphase kernels read the pair count on the device
         // morton, (hist, scan, passes), gather, [worldEnds], range tree, topology+fit, traversal, scan, scatter,
         // segment sort
-        ctx->launches[1] = 1 + bucketLaunches + (2 + passes) + 1 + segLaunches + (ctx->hasWorlds ? 1 : 0) + 1 + 3;
+        ctx->launches[1] = 1 + bucketLaunches + passes + 1 + segLaunches + (ctx->hasWorlds ? 1 : 0) + 1 + 3;
     } else {
         recordEv(ctx, EV_SORT);
         recordEv(ctx, EV_BUILD);

@@ -165,8 +165,11 @@ segBuildBottomKernel(float4* __restrict__ lo, float4* __restrict__ hi, uint32_t 
 __global__ void __launch_bounds__(kSegThreads)
 segGatherBottomKernel(const float* __restrict__ aabb, const uint32_t* __restrict__ sortedIdx,
                       const uint32_t* __restrict__ sortedKeys, uint32_t n, int worldShift, float4* __restrict__ lo,
-                      float4* __restrict__ hi, uint32_t P) {
+                      float4* __restrict__ hi, uint32_t P, uint32_t* __restrict__ zeroPtr, uint32_t zeroWords) {
     __shared__ float sLo[kSegLeaves][3], sHi[kSegLeaves][3];
+    // zero tail: the digit histograms the Morton kernel accumulated for the sort that has just finished; the next
+    // step's Morton kernel expects them cleared
+    for (uint32_t i = blockIdx.x * kSegThreads + threadIdx.x; i < zeroWords; i += gridDim.x * kSegThreads) zeroPtr[i] = 0u;
     const uint32_t width = min((uint32_t)kSegLeaves, P);
     const uint32_t k0 = blockIdx.x * kSegLeaves;
     const uint32_t base = P + k0;

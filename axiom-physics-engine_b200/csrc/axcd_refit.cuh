@@ -481,48 +481,75 @@ struct ZeroList {
     uint32_t words[5];
 };
 
+// The kernel also accumulates the radix sort's digit histograms (one 256-bin histogram per 8-bit digit of the key,
+// `histPasses` of them) — per block in shared memory over all of the block's tiles, then one reduction per non-empty
+// bin — so the sort needs no histogram pass of its own.  `hist` must be zero on entry (cleared by a later kernel of
+// the previous broadphase, see segGatherBottomKernel's zero tail); the grid is a few blocks per SM, each walking
+// several 256-body tiles, which keeps the number of global reductions at that of a dedicated histogram kernel.
 __global__ void __launch_bounds__(kRefitThreads)
 mortonKernel(const float4* __restrict__ aabb4, const uint32_t* __restrict__ worldId,
              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n,
              int bitsPerAxis, const Counters* __restrict__ ctr, ZeroList zl,
-             uint32_t* __restrict__ bucketCounts /* or nullptr */, int bucketShift) {
+             uint32_t* __restrict__ bucketCounts /* or nullptr */, int bucketShift,
+             uint32_t* __restrict__ hist /* or nullptr */, int histPasses) {
     __shared__ __align__(16) float sIn[kRefitThreads * 6];
-    const uint32_t base = blockIdx.x * kRefitThreads;
-    const uint32_t cnt = min((uint32_t)kRefitThreads, n - base);
+    __shared__ uint32_t sHist[4 * 256];
     const int tid = threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 5; ++k)
-        for (uint32_t i = base + tid; i < zl.words[k]; i += gridDim.x * kRefitThreads) zl.ptr[k][i] = 0u;
-    {
-        const uint32_t nFloats = cnt * 6, nVec = nFloats / 4;
-        const float4* src = aabb4 + (size_t)base * 6 / 4;
-        float4* dst = reinterpret_cast<float4*>(sIn);
-        for (uint32_t i = tid; i < nVec; i += kRefitThreads) dst[i] = __ldg(src + i);
-        const float* srcF = reinterpret_cast<const float*>(src);
-        for (uint32_t i = nVec * 4 + tid; i < nFloats; i += kRefitThreads) sIn[i] = __ldg(srcF + i);
-    }
-    __syncthreads();
-    if (tid >= (int)cnt) return;
-    const float* b = sIn + tid * 6;
+        for (uint32_t i = blockIdx.x * kRefitThreads + tid; i < zl.words[k]; i += gridDim.x * kRefitThreads) zl.ptr[k][i] = 0u;
+    if (hist)
+        for (int i = tid; i < histPasses * 256; i += kRefitThreads) sHist[i] = 0u;
+    float lo3[3], inv3[3];
     const float cells = (float)(1u << bitsPerAxis);
-    uint32_t code = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float lo = orderedToFloat(ctr->boundsMin[k]);
-        const float hi = orderedToFloat(ctr->boundsMax[k]);
-        const float c = (b[k] + b[k + 3]) * 0.5f;
-        float ext = hi - lo;
-        float t = (ext > 0.0f) ? (c - lo) / ext : 0.0f;
-        t = t * cells;
-        // NaN / out-of-range centres clamp into the grid (quality only; never affects the pair set)
-        int q = (t >= 0.0f) ? ((t < cells) ? (int)t : (int)cells - 1) : 0;
-        q = min(max(q, 0), (int)cells - 1);
-        code |= expandBits10((uint32_t)q) << (2 - k);
+        lo3[k] = orderedToFloat(ctr->boundsMin[k]);
+        inv3[k] = orderedToFloat(ctr->boundsMax[k]) - lo3[k];   // extent
     }
-    if (worldId) code |= __ldg(worldId + base + tid) << (3 * bitsPerAxis);
-    keys[base + tid] = code;
-    vals[base + tid] = base + tid;
-    if (bucketCounts) atomicAdd(bucketCounts + (code >> bucketShift), 1u);   // bucket sort, step 1 (axcd_sort.cuh)
+    const uint32_t tiles = (n + kRefitThreads - 1) / kRefitThreads;
+    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t base = tile * kRefitThreads;
+        const uint32_t cnt = min((uint32_t)kRefitThreads, n - base);
+        __syncthreads();   // the previous tile's staged boxes have been read (and sHist is cleared, first trip)
+        {
+            const uint32_t nFloats = cnt * 6, nVec = nFloats / 4;
+            const float4* src = aabb4 + (size_t)base * 6 / 4;
+            float4* dst = reinterpret_cast<float4*>(sIn);
+            for (uint32_t i = tid; i < nVec; i += kRefitThreads) dst[i] = __ldg(src + i);
+            const float* srcF = reinterpret_cast<const float*>(src);
+            for (uint32_t i = nVec * 4 + tid; i < nFloats; i += kRefitThreads) sIn[i] = __ldg(srcF + i);
+        }
+        __syncthreads();
+        if (tid >= (int)cnt) continue;
+        const float* b = sIn + tid * 6;
+        uint32_t code = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float lo = lo3[k];
+            const float c = (b[k] + b[k + 3]) * 0.5f;
+            const float ext = inv3[k];
+            float t = (ext > 0.0f) ? (c - lo) / ext : 0.0f;
+            t = t * cells;
+            // NaN / out-of-range centres clamp into the grid (quality only; never affects the pair set)
+            int q = (t >= 0.0f) ? ((t < cells) ? (int)t : (int)cells - 1) : 0;
+            q = min(max(q, 0), (int)cells - 1);
+            code |= expandBits10((uint32_t)q) << (2 - k);
+        }
+        if (worldId) code |= __ldg(worldId + base + tid) << (3 * bitsPerAxis);
+        keys[base + tid] = code;
+        vals[base + tid] = base + tid;
+        if (bucketCounts) atomicAdd(bucketCounts + (code >> bucketShift), 1u);   // bucket sort, step 1 (axcd_sort.cuh)
+        if (hist)
+            for (int p = 0; p < histPasses; ++p) atomicAdd(&sHist[p * 256 + ((code >> (8 * p)) & 0xffu)], 1u);
+    }
+    if (hist) {
+        __syncthreads();
+        for (int i = tid; i < histPasses * 256; i += kRefitThreads) {
+            const uint32_t v = sHist[i];
+            if (v) atomicAdd(&hist[i], v);
+        }
+    }
 }
 
 // ---- x-slab mode: ghost records --------------------------------------------------------------------

@@ -53,36 +53,16 @@ radixHistogramKernel(const K* __restrict__ keys, uint32_t n, int bitStart, int p
     }
 }
 
-// In-place exclusive scan of each pass's 256 bins; one block of 256 threads, one warp-scan tree.
-__global__ void __launch_bounds__(kRadix)
-radixScanKernel(uint32_t* __restrict__ hist, int passes, const uint32_t* __restrict__ enable = nullptr) {
-    __shared__ uint32_t warpSum[kRadix / 32];
-    if (enable && !*enable) return;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int p = 0; p < passes; ++p) {
-        const uint32_t v = hist[p * kRadix + tid];
-        uint32_t inc = v;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
-            if (lane >= off) inc += t;
-        }
-        if (lane == 31) warpSum[w] = inc;
-        __syncthreads();
-        uint32_t basev = 0;
-        for (int i = 0; i < w; ++i) basev += warpSum[i];
-        hist[p * kRadix + tid] = basev + inc - v;
-        __syncthreads();
-    }
-}
-
 // One radix pass.  `status` holds numTiles*256 words for this pass (zero-initialised); `ticket`
 // hands out tile indices in launch order so that a tile's predecessors have always started.
+// `digitHist` is this pass's RAW digit histogram over all keys (256 counts): every block turns it into the exclusive
+// digit bases itself — the same shuffle tree that scans its own tile's digit counts carries the second value — so no
+// scan kernel runs between the histogram and the passes.
 template <typename K, bool HAS_VAL>
 __global__ void __launch_bounds__(kSortThreads)
 radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
                     const uint32_t* __restrict__ valsIn, uint32_t* __restrict__ valsOut,
-                    uint32_t n, int shift, const uint32_t* __restrict__ globalBase,
+                    uint32_t n, int shift, const uint32_t* __restrict__ digitHist,
                     volatile uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
                     const uint32_t* __restrict__ enable = nullptr) {
     __shared__ K sKeys[kSortTile];
@@ -91,7 +71,7 @@ radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
     __shared__ uint32_t sWarpHist[kSortWarps][kRadix];
     __shared__ uint32_t sDigitStart[kRadix];
     __shared__ uint32_t sGlobalOff[kRadix];
-    __shared__ uint32_t sWarpTot[kSortWarps];
+    __shared__ uint32_t sWarpTot[kSortWarps], sWarpTotH[kSortWarps];
     __shared__ uint32_t sTile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -101,6 +81,7 @@ radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
     const uint32_t tile = sTile;
     const uint32_t tileBase = tile * kSortTile;
     const uint32_t tileCount = min((uint32_t)kSortTile, n - tileBase);
+    const uint32_t histRaw = __ldg(digitHist + tid);   // kSortThreads == kRadix: thread d owns digit d
 
     // ---- load (warp-striped: warp w owns a contiguous 512-key span) and rank ------------------
     K key[kSortItems];
@@ -176,22 +157,31 @@ radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
             }
             st[d] = kFlagInclusive | (excl + pub);
         }
-        sGlobalOff[d] = globalBase[d] + excl;
-    }
-    // ---- exclusive scan of the tile's digit counts (position of each digit's run in the tile) --
-    {
-        uint32_t inc = digitCount;
+        // ---- exclusive scans over the digits: the tile's digit counts (position of each digit's run in the tile) and
+        //      the global histogram (first output position of each digit) -------------------------------------------------
+        uint32_t inc = digitCount, incH = histRaw;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
-            if (lane >= off) inc += t;
+            const uint32_t tH = __shfl_up_sync(0xffffffffu, incH, off);
+            if (lane >= off) {
+                inc += t;
+                incH += tH;
+            }
         }
-        if (lane == 31) sWarpTot[warp] = inc;
+        if (lane == 31) {
+            sWarpTot[warp] = inc;
+            sWarpTotH[warp] = incH;
+        }
         __syncthreads();
-        uint32_t basev = 0;
+        uint32_t basev = 0, basevH = 0;
 #pragma unroll
-        for (int i = 0; i < kSortWarps; ++i) basev += (i < warp) ? sWarpTot[i] : 0u;
+        for (int i = 0; i < kSortWarps; ++i) {
+            basev += (i < warp) ? sWarpTot[i] : 0u;
+            basevH += (i < warp) ? sWarpTotH[i] : 0u;
+        }
         sDigitStart[tid] = basev + inc - digitCount;
+        sGlobalOff[d] = (basevH + incH - histRaw) + excl;
     }
     __syncthreads();
 
@@ -223,18 +213,20 @@ inline int radixSort(K* keysA, K* keysB, uint32_t* valsA, uint32_t* valsB, uint3
                      int passes, uint32_t* scratchHist, uint32_t* scratchStatus,
                      uint32_t* tickets /* kMaxPasses words */, cudaStream_t stream, int numSMs = kNumSMs,
                      bool scratchZeroed = false /* the caller already cleared hist / status / tickets */,
-                     const uint32_t* enable = nullptr /* device flag: kernels return at once while it is 0 */) {
+                     const uint32_t* enable = nullptr /* device flag: kernels return at once while it is 0 */,
+                     bool histReady = false /* scratchHist already holds the raw digit histograms (the Morton kernel's) */) {
     if (n == 0 || passes == 0) return 0;
     const uint32_t numTiles = (n + kSortTile - 1) / kSortTile;
     if (!scratchZeroed) {
-        cudaMemsetAsync(scratchHist, 0, sizeof(uint32_t) * kMaxPasses * kRadix, stream);
+        if (!histReady) cudaMemsetAsync(scratchHist, 0, sizeof(uint32_t) * kMaxPasses * kRadix, stream);
         cudaMemsetAsync(scratchStatus, 0, sizeof(uint32_t) * (size_t)passes * numTiles * kRadix, stream);
         cudaMemsetAsync(tickets, 0, sizeof(uint32_t) * kMaxPasses, stream);
     }
-    uint32_t histBlocks = (n + kSortThreads * AXCD_HIST_ITEMS - 1) / (kSortThreads * AXCD_HIST_ITEMS);
-    if (histBlocks > (uint32_t)numSMs * 8) histBlocks = numSMs * 8;
-    radixHistogramKernel<K><<<histBlocks, kSortThreads, 0, stream>>>(keysA, n, bitStart, passes, scratchHist, enable);
-    radixScanKernel<<<1, kRadix, 0, stream>>>(scratchHist, passes, enable);
+    if (!histReady) {
+        uint32_t histBlocks = (n + kSortThreads * AXCD_HIST_ITEMS - 1) / (kSortThreads * AXCD_HIST_ITEMS);
+        if (histBlocks > (uint32_t)numSMs * 8) histBlocks = numSMs * 8;
+        radixHistogramKernel<K><<<histBlocks, kSortThreads, 0, stream>>>(keysA, n, bitStart, passes, scratchHist, enable);
+    }
     K* kin = keysA;
     K* kout = keysB;
     uint32_t* vin = valsA;

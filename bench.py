@@ -259,7 +259,7 @@ def stage_table(avg, st, hbm_peak, fp32_peak, generic_pairs):
     passes = (key_bits + 7) // 8
     info = {
         "refitMs": ("refitTmaKernel", "hbm", n * 80),
-        "sortMs": ("mortonKernel + onesweep radix sort (%d passes)" % passes, "hbm", n * 32 + n * (16 * passes + 4)),
+        "sortMs": ("mortonKernel (keys + digit histograms) + onesweep radix sort (%d passes)" % passes, "hbm", n * 32 + n * 16 * passes),
         "buildMs": ("leaf gather fused with the range tree + Karras topology/fit (32-byte nodes)", "hbm", n * (24 + 32) + n * 32 + n * 32),
         "pairMs": ("findPairsDenseKernel (LBVH traversal, dense leaf tests)", "hbm", n * 32 + npairs * 8),
         "pairSortMs": ("pair counting sort (scan + scatter + block-cooperative segment sort)", "hbm", n * 12 + npairs * (8 + 4 + 4 + 8)),

@@ -549,6 +549,16 @@ int32_t axcd_create(const AxcdConfig* cfg, AxcdContext** out) {
             CU(cudaMalloc(&ctx->dQSeg, hits0 * 4));      ctx->qSegBytes = hits0 * 4;
             CU(cudaMalloc(&ctx->dQOut, hits0 * 8));      ctx->qOutBytes = hits0 * 8;
         }
+        {
+            // CUDA loads a kernel's code at its first launch; ask for the scene-query and manifold kernels now, so that
+            // the first query after a step does not pay for it (measured: 20-300 ms on a freshly started box)
+            cudaFuncAttributes fa;
+            const void* fns[] = {(const void*)buildTopologyKernel<false>, (const void*)queryAabbKernel<false>,
+                                 (const void*)queryAabbKernel<true>,      (const void*)raycastKernel<false>,
+                                 (const void*)raycastKernel<true>,        (const void*)manifoldKernel};
+            for (const void* f : fns) cudaFuncGetAttributes(&fa, f);
+            cudaGetLastError();
+        }
         CU(dalloc(&ctx->dEpaWork, (size_t)cfg->maxContacts));
         CU(dalloc(&ctx->dEpaOverflow, (size_t)cfg->maxContacts));
         ctx->spillCap = cfg->maxContacts < 65536u ? cfg->maxContacts : 65536u;

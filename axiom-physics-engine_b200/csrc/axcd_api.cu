@@ -281,7 +281,7 @@ int resizeBodies(AxcdContext* ctx, uint32_t n) {
 // ---- contact sink of the fused narrowphase: host side ---------------------------------------------------------------
 // The kernel reports, tile by tile and in pair order, how far the device contact array is complete (progress words in
 // page-locked memory, see narrowClosedFusedKernel).  drainContactSink runs inside the next blocking call: it follows
-// the words while the kernel is still running and hands every finished stretch of ~4 MB to the copy engine on a second
+// the words while the kernel is still running and hands every finished stretch (256 KB growing to 8 MB) to the copy engine on a second
 // stream, so the contacts cross PCIe as DMA bursts behind the narrowphase instead of after it.
 int drainContactSink(AxcdContext* ctx) {
     if (!ctx->sinkPending) return AXCD_OK;

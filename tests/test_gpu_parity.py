@@ -720,3 +720,39 @@ def test_contact_sink_receives_the_steps_contacts(scene_name, kw):
     finally:
         w.close()
         axcd.unpin_host_buffer(sink)
+
+
+def test_contact_sink_survives_steps_queued_back_to_back():
+    """Two fused steps queued without a blocking call between them: the second launch first completes the first
+    step's sink (its copy-engine chunks follow progress words the second launch must not clear early), and the sink
+    ends up holding the second step's contacts.  Detaching the sink while a step is in flight completes it too."""
+    s = axcd.config_scene("C1")
+    w = axcd.CollisionWorld.for_scene(s, pairs_per_body=16)
+    cap = w.cfg.maxContacts
+    sink = np.zeros(cap, axcd.CONTACT_DT)
+    axcd.pin_host_buffer(sink)
+    try:
+        w.set_contact_sink(sink.ctypes.data, cap)
+        xf2 = s.xf.copy()
+        xf2[:, 0] += np.float32(0.01) * (np.arange(s.n) % 7).astype(np.float32)   # a slightly different scene
+        for rep in range(3):   # direct launches first, then graph replays
+            w.set_transforms(s.xf)
+            w.step_async()
+            w.set_transforms(xf2)
+            w.step_async()
+            st = w.stats()
+            ref = w.contacts()
+            assert st.numContacts == len(ref) > 0
+            assert sink[:len(ref)].tobytes() == ref.tobytes()
+        con, _, _ = O.narrowphase(xf2, s.shapes, w.pairs(), s.hull, nthreads=8)
+        assert sink[:len(con)].tobytes() == con.tobytes()
+        w.set_transforms(s.xf)
+        w.step_async()
+        w.set_contact_sink(None, 0)          # detach with the step in flight: that step still delivers
+        st = w.stats()
+        ref = w.contacts()
+        assert sink[:len(ref)].tobytes() == ref.tobytes()
+    finally:
+        w.close()
+        axcd.unpin_host_buffer(sink)
+

@@ -51,6 +51,23 @@ struct __align__(32) Node32 {
     uint32_t last;
 };
 static_assert(sizeof(Node32) == 32, "Node32 must be one 32-byte record");
+#ifndef AXCD_LDG256
+#define AXCD_LDG256 1
+#endif
+// One node = one 256-bit load (sm_100: LDG.E.256) instead of two 128-bit ones: the traversal is co-limited by the LSU
+// data pipe (ncu: 68 % of its wavefront peak with two loads per node) and by issue slots, and this halves its node
+// fetch instructions.  Read-only path (.nc), 32-byte aligned by the record type.
+__device__ __forceinline__ void loadNode32(const Node32* __restrict__ p, uint4& lo, uint4& hi) {
+#if AXCD_LDG256
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+#else
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    lo = __ldg(q);
+    hi = __ldg(q + 1);
+#endif
+}
 constexpr uint32_t kSplitMask = 0x3fffffffu, kLeftLeaf = 1u << 30, kRightLeaf = 1u << 31;
 constexpr uint32_t kGuard = 0x80008000u;   // bit 15 of each half: the borrow guard of the SWAR compare
 constexpr float kQuantCells = 32767.0f;    // 15 bits per coordinate
@@ -623,8 +640,8 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
         const uint32_t w1 = min(w0 + 31u, n - 1u);
         if (w0 < n && n >= 2u) {
             while (true) {
-                const uint4* np = reinterpret_cast<const uint4*>(nodes + ni);
-                const uint4 a0 = __ldg(np), a1 = __ldg(np + 1);
+                uint4 a0, a1;
+                loadNode32(nodes + ni, a0, a1);
                 const uint32_t split = a1.z & kSplitMask;
                 if (a1.z & (kLeftLeaf | kRightLeaf)) break;
                 if (w1 <= split) {          // the whole warp lives in the left child
@@ -673,11 +690,7 @@ findPairsDenseKernel(const float4* __restrict__ leafLo, const float4* __restrict
             }
             uint4 r0[K], r1[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const uint4* np = reinterpret_cast<const uint4*>(nodes + nd[k]);
-                r0[k] = __ldg(np);
-                r1[k] = __ldg(np + 1);
-            }
+            for (int k = 0; k < K; ++k) loadNode32(nodes + nd[k], r0[k], r1[k]);
             uint32_t next = kNone, nextFirst = 0;
 #pragma unroll
             for (int which = 0; which < K; ++which) {

@@ -313,6 +313,7 @@ def roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, workload, sm_cou
                 issue = {"warp_instructions_per_launch": ent["warp_instructions_per_launch"],
                          "achieved_ginst_per_s": round(ginst, 1), "peak_ginst_per_s": round(peak_i, 1),
                          "frac": round(ginst / peak_i, 4), "active_lanes_per_instruction": ent.get("threads_per_instruction"),
+                         "lsu_data_pipe_pct_of_peak_ncu": ent.get("lsu_data_pipe_pct_of_peak"),
                          "source": "instruction count and lanes: profiles/r02_traffic.json (ncu --set full of this kernel); time and clock: this run"}
     except Exception:
         pass
@@ -321,8 +322,8 @@ def roofline_of(rows, info, avg, hbm_peak, peak_src, fp32_peak, workload, sm_cou
             "launch_ms": round(avg[dom], 4), "issue": issue,
             "note": "dominant stage of the step by CUDA-event time through the staged calls; algorithmic work per "
                     "DESIGN.md section 2; every stage's own row is in `stages`.  `issue` (when the ncu capture matches "
-                    "this run) is the kernel's share of the SMs' instruction-issue slots: the LBVH walk is bound by "
-                    "those, not by HBM"}
+                    "this run) is the kernel's share of the SMs' instruction-issue slots, with the LSU data-pipe share ncu "
+                    "measured beside it: the LBVH walk is co-limited by those two, not by HBM"}
 
 
 def measure_next_rows(w, s, stream, hbm_peak, device):

@@ -67,8 +67,8 @@ def ncu_table(rep):
             return f"{float(data[k].get(key)):.1f}"
         except Exception:
             return str(data[k].get(key))
-    tbl = ["| kernel | us | regs | warps active % | issue active % | FP32 (fma) pipe % | threads/inst | warp instr (M) | DRAM rd+wr MB | DRAM % of peak | L2 hit % | top stalls (per issue) |",
-           "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    tbl = ["| kernel | us | regs | warps active % | issue active % | FP32 (fma) pipe % | threads/inst | warp instr (M) | LSU data pipe % | DRAM rd+wr MB | DRAM % of peak | L2 hit % | top stalls (per issue) |",
+           "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for k in data:
         st = {s.split('_stalled_')[1].split('_per_issue')[0]: float(v) for s, v in data[k].items() if '_stalled_' in s and v != 'n/a'}
         top = sorted(st.items(), key=lambda x: -x[1])[:3]
@@ -77,7 +77,7 @@ def ncu_table(rep):
         tbl.append(f"| {k} | {t:.1f} | {data[k]['launch__registers_per_thread']} | "
                    f"{g(k, 'sm__warps_active.avg.pct_of_peak_sustained_active')} | {g(k, 'smsp__issue_active.avg.pct_of_peak_sustained_active')} | "
                    f"{g(k, 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active')} | "
-                   f"{g(k, 'smsp__thread_inst_executed_per_inst_executed.ratio')} | {float(data[k]['smsp__inst_executed.sum']) / 1e6:.1f} | {rd + wr:.1f} | "
+                   f"{g(k, 'smsp__thread_inst_executed_per_inst_executed.ratio')} | {float(data[k]['smsp__inst_executed.sum']) / 1e6:.1f} | {g(k, 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed')} | {rd + wr:.1f} | "
                    f"{g(k, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} | {g(k, 'lts__t_sector_hit_rate.pct')} | "
                    f"{', '.join(f'{a} {b:.1f}' for a, b in top)} |")
     return tbl, data
@@ -183,7 +183,8 @@ for wl, m in stage_kernel.items():
             traffic[wl][stage] = {"kernel": kn, "ncu_kernel_ms": t / 1000.0,
                                   "dram_bytes_per_launch": (float(v['dram__bytes_read.sum']) + float(v['dram__bytes_write.sum'])) * 1e6,
                                   "warp_instructions_per_launch": float(v['smsp__inst_executed.sum']),
-                                  "threads_per_instruction": float(v['smsp__thread_inst_executed_per_inst_executed.ratio'])}
+                                  "threads_per_instruction": float(v['smsp__thread_inst_executed_per_inst_executed.ratio']),
+                                  "lsu_data_pipe_pct_of_peak": float(v.get('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'nan'))}
 if c2data:
     traffic["C2"] = {}
     for stage, kn in (("epa", "epaKernel"), ("gjk", "gjkKernel")):

@@ -149,4 +149,19 @@ struct Counters {
     uint32_t sortMaxBucket;  // largest Morton bucket of the step
 };
 
+// ---- lanes of a warp that hold the same small value ---------------------------------------------------------------
+// Peer mask from one ballot per value bit instead of __match_any_sync: the match operation is throughput-limited on
+// B200 (profiles/r02_experiments.md: the radix ranking loop went from 0.081 to 0.069 ms per 1 M-key sort with this).
+template <int BITS>
+__device__ __forceinline__ uint32_t peersByBallot(uint32_t v) {
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < BITS; ++b) {
+        const bool bit = (v >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 }  // namespace axcd

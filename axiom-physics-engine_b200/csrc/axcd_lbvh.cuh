@@ -795,7 +795,7 @@ __global__ void scatterPairsKernel(const uint2* __restrict__ pairs, const uint32
     for (uint32_t t = 0, k = blockIdx.x * blockDim.x + threadIdx.x; t < trips; ++t, k += stride) {
         const bool valid = k < np;
         const uint2 pr = valid ? __ldg(pairs + k) : make_uint2(0xffffffffu, 0u);
-        const uint32_t peers = __match_any_sync(0xffffffffu, pr.x);
+        const uint32_t peers = __match_any_sync(0xffffffffu, pr.x);   // (runs of neighbouring lanes by shuffle + ballot: 2 us slower)
         const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
         if (lane == leader && valid) base = atomicAdd(&bodyCursor[pr.x], (uint32_t)__popc(peers));

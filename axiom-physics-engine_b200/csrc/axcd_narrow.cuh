@@ -1395,7 +1395,7 @@ narrowClosedFusedKernel(const uint2* __restrict__ pairs, const uint32_t* __restr
                 cls[j] = (ta == AXCD_SHAPE_BOX ? 1 : 0) + (tb == AXCD_SHAPE_BOX ? 1 : 0);
             }
             sFlag[li] = 0;
-            const uint32_t peers = __match_any_sync(0xffffffffu, cls[j]);
+            const uint32_t peers = peersByBallot<2>((uint32_t)cls[j]);   // classes 0, 1, 2; -1 (no pair) reads as 3
             const int leader = __ffs(peers) - 1;
             uint32_t base = 0;
             if (lane == leader && cls[j] >= 0) base = atomicAdd(&sCnt[cls[j]], (uint32_t)__popc(peers));

@@ -21,6 +21,9 @@ constexpr int kSortItems = AXCD_SORT_ITEMS;
 #ifndef AXCD_SORT_LOOKBACK
 #define AXCD_SORT_LOOKBACK 4   // predecessor tiles read per look-back round (sweep 1..32: 4-6 best at 1 M keys)
 #endif
+#ifndef AXCD_SORT_BALLOT_RANK
+#define AXCD_SORT_BALLOT_RANK 1   // 1: peer masks from eight ballots; 0: from one __match_any_sync (slower on B200:
+#endif                            //    sort stage 0.081 vs 0.069 ms at 1 M keys, 1.91 vs 1.67 ms at 64 M)
 constexpr int kSortTile = kSortThreads * kSortItems;   // 4096 keys per tile
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kRadix = 256;
@@ -99,7 +102,14 @@ radixOnesweepKernel(const K* __restrict__ keysIn, K* __restrict__ keysOut,
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
         const uint32_t d = digitOf(key[k], shift);
+#if AXCD_SORT_BALLOT_RANK
+        // lanes with the same digit, from eight ballots (one per digit bit) instead of one match operation: ncu showed
+        // 35 % of the kernel's stall samples waiting for match results, and issuing the matches ahead changed nothing
+        // — the match unit's throughput was the limit, while the issue slots were 83 % idle
+        const uint32_t peers = peersByBallot<8>(d);
+#else
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
+#endif
         const int leader = __ffs(peers) - 1;
         uint32_t prev = 0;
         if (lane == leader) {
